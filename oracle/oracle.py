@@ -1,0 +1,322 @@
+"""TEST INFRASTRUCTURE ONLY -- Python face of the CPU oracle (``lp_oracle.c``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+(``laser-polio_b200/``) never does.
+
+The per-agent stages live in C (``lp_oracle.c``); the node-level transmission
+math (reference ``model.py:1327-1407``) is restated here in numpy because it is
+~40 lines of dense array arithmetic whose dtype flow (float32 tallies promoted
+by float64 scalars) numpy reproduces exactly.
+
+Arguments mirror the reference's free functions (same names, same order, arrays
+mutated in place) with the uniform source appended: ``u_inj`` arrays for
+gate-1 runs, else Philox keyed on ``(seed, tick)``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "_build" / "liblp_oracle.so"
+
+FX_SCALE = float(2**30)
+
+STAGE_PARALYSIS, STAGE_RI, STAGE_SIA, STAGE_EXPOSE, STAGE_STRAIN, STAGE_NODE, STAGE_BIRTH, STAGE_LIFESPAN = range(8)
+
+
+def build(force: bool = False) -> Path:
+    src = _HERE / "lp_oracle.c"
+    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []), check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+        _lib.orc_uniform53.restype = C.c_double
+        _lib.orc_uniform53.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a, dtype=None):
+    """Pointer to a C-contiguous numpy array (dtype-checked), or NULL for None."""
+    if a is None:
+        return None
+    if dtype is not None and a.dtype != np.dtype(dtype):
+        raise TypeError(f"expected {np.dtype(dtype)}, got {a.dtype}")
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def philox4x32_10(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32).copy()
+    k = np.asarray(key, dtype=np.uint32).copy()
+    out = np.zeros(4, np.uint32)
+    lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+def uniform53(seed: int, idx: int, tick: int, stage: int, pair: int = 0) -> float:
+    return float(lib().orc_uniform53(seed, idx, tick, stage, pair))
+
+
+# --------------------------------------------------------------------- stages
+def get_deaths(num_nodes, num_people, disease_state, node_id, date_of_death, t, num_dying):
+    """reference model.py:1767-1781"""
+    lib().orc_get_deaths(
+        C.c_int32(num_nodes), C.c_int64(num_people), _p(disease_state, np.int8), _p(node_id, np.int16),
+        _p(date_of_death, np.int32), C.c_int32(t), _p(num_dying, np.int32),
+    )
+
+
+def disease_state_step(
+    node_id, n_nodes, disease_state, strain, active_count, exposure_timer, infection_timer, potentially_paralyzed,
+    paralyzed, ipv_protected, paralysis_timer, p_paralysis, new_potential, new_paralyzed, u_inj=None, seed=0, tick=0,
+):
+    """reference model.py:344-454"""
+    lib().orc_disease_state_step(
+        _p(node_id, np.int16), C.c_int32(n_nodes), _p(disease_state, np.int8), _p(strain, np.int8),
+        C.c_int64(active_count), _p(exposure_timer, np.int8), _p(infection_timer, np.int8),
+        _p(potentially_paralyzed, np.int8), _p(paralyzed, np.int8), _p(ipv_protected, np.int8),
+        _p(paralysis_timer, np.int8), C.c_float(np.float32(p_paralysis)), _p(new_potential, np.int32),
+        _p(new_paralyzed, np.int32), _p(u_inj, np.float64), C.c_uint64(seed), C.c_uint32(tick),
+    )
+
+
+def fast_ri(
+    step_size, node_id, disease_state, strain, ipv_protected, ri_timer, sim_t, vx_prob_ri, vx_prob_ipv, num_people,
+    ri_counts, ri_protected, ipv_counts, chronically_missed, ri_vaccine_strain, u1_inj=None, u2_inj=None, seed=0, tick=0,
+):
+    """reference model.py:1805-1855; the three count outputs are per-node int32 (already thread-reduced)."""
+    n_nodes = len(vx_prob_ri)
+    lib().orc_fast_ri(
+        C.c_int64(step_size), _p(node_id, np.int16), _p(disease_state, np.int8), _p(strain, np.int8),
+        _p(ipv_protected, np.int8), _p(ri_timer, np.int16), C.c_int64(sim_t), _p(vx_prob_ri, np.float64),
+        _p(vx_prob_ipv, np.float64), C.c_int64(num_people), C.c_int32(n_nodes), _p(ri_counts, np.int32),
+        _p(ri_protected, np.int32), _p(ipv_counts, np.int32), _p(chronically_missed, np.uint8),
+        C.c_int8(int(ri_vaccine_strain)), _p(u1_inj, np.float64), _p(u2_inj, np.float64), C.c_uint64(seed),
+        C.c_uint32(tick),
+    )
+
+
+def fast_sia(
+    node_ids, disease_states, strain, dobs, sim_t, vx_prob, vx_eff, count, nodes_to_vaccinate, min_age, max_age,
+    vaccinated, protected, chronically_missed, sia_vaccine_strain, u_inj=None, seed=0, tick=0, event_idx=0,
+):
+    """reference model.py:1995-2060; vaccinated/protected are per-node int32 (already thread-reduced)."""
+    n_nodes = len(vx_prob)
+    lib().orc_fast_sia(
+        _p(node_ids, np.int16), _p(disease_states, np.int8), _p(strain, np.int8), _p(dobs, np.int32),
+        C.c_int64(sim_t), _p(vx_prob, np.float32), C.c_double(vx_eff), C.c_int64(count),
+        _p(nodes_to_vaccinate, np.uint8), C.c_int64(min_age), C.c_int64(max_age), C.c_int32(n_nodes),
+        _p(vaccinated, np.int32), _p(protected, np.int32), _p(chronically_missed, np.uint8),
+        C.c_int8(int(sia_vaccine_strain)), _p(u_inj, np.float64), C.c_uint64(seed), C.c_uint32(tick),
+        C.c_uint32(event_idx),
+    )
+
+
+def tx_step_prep(num_nodes, num_people, n_strains, strains, strain_r0_scalars, disease_states, node_ids,
+                 daily_infectivity, risks, mode="fx"):
+    """reference model.py:932-1007.  mode: 'f32' (reference-like), 'f64' (truth), 'fx' (device fixed point).
+
+    Returns (beta[nodes,strains] f64, exposure[nodes] f64, sus[nodes] i64, beta_fx i64, exposure_fx i64).
+    """
+    m = {"f32": 0, "f64": 1, "fx": 2}[mode]
+    beta = np.zeros((num_nodes, n_strains), np.float64)
+    expo = np.zeros(num_nodes, np.float64)
+    sus = np.zeros(num_nodes, np.int64)
+    beta_fx = np.zeros((num_nodes, n_strains), np.int64)
+    expo_fx = np.zeros(num_nodes, np.int64)
+    srs = np.ascontiguousarray(strain_r0_scalars, dtype=np.float64)
+    lib().orc_tx_step_prep(
+        C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(n_strains), _p(strains, np.int8), _p(srs),
+        _p(disease_states, np.int8), _p(node_ids, np.int16), _p(daily_infectivity, np.float32),
+        _p(risks, np.float32), C.c_int(m), _p(beta), _p(expo), _p(sus), _p(beta_fx), _p(expo_fx),
+    )
+    return beta, expo, sus, beta_fx, expo_fx
+
+
+def count_SEIRP(node_id, disease_state, strain, potentially_paralyzed, paralyzed, n_nodes, n_strains, n_people):
+    """reference model.py:869-929; same 8-tuple as the reference."""
+    S = np.zeros(n_nodes, np.int32); E = np.zeros(n_nodes, np.int32); I = np.zeros(n_nodes, np.int32)  # noqa: E702
+    R = np.zeros(n_nodes, np.int32); PP = np.zeros(n_nodes, np.int32); P = np.zeros(n_nodes, np.int32)  # noqa: E702
+    Ebs = np.zeros((n_nodes, n_strains), np.int32); Ibs = np.zeros((n_nodes, n_strains), np.int32)  # noqa: E702
+    lib().orc_count_seirp(
+        _p(node_id, np.int16), _p(disease_state, np.int8), _p(strain, np.int8), _p(potentially_paralyzed, np.int8),
+        _p(paralyzed, np.int8), C.c_int32(n_nodes), C.c_int32(n_strains), C.c_int64(n_people), _p(S), _p(E), _p(I),
+        _p(R), _p(Ebs), _p(Ibs), _p(PP), _p(P),
+    )
+    return S, E, I, R, Ebs, Ibs, PP, P
+
+
+def tx_infect_ref(num_nodes, num_people, num_strains, sus_by_node, node_ids, strain, disease_state, sus_indices,
+                  sus_probs, risks, prob_exp_by_node_strain, n_exposures_to_create_by_node_strain, seed=0, tick=0):
+    """reference model.py:1010-1149 (distributional restatement, own RNG stream)."""
+    n_new = np.zeros((num_nodes, num_strains), np.int32)
+    sus64 = np.ascontiguousarray(sus_by_node, dtype=np.int64)
+    pe = np.ascontiguousarray(prob_exp_by_node_strain, dtype=np.float64)
+    nc = np.ascontiguousarray(n_exposures_to_create_by_node_strain, dtype=np.int32)
+    lib().orc_tx_infect_ref(
+        C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(num_strains), _p(sus64), _p(node_ids, np.int16),
+        _p(strain, np.int8), _p(disease_state, np.int8), _p(sus_indices, np.int32), _p(sus_probs, np.float32),
+        _p(risks, np.float32), _p(pe), _p(nc), _p(n_new), C.c_uint64(seed), C.c_uint32(tick),
+    )
+    return n_new
+
+
+def tx_infect_bernoulli(num_nodes, num_people, num_strains, node_ids, strain, disease_state, risks, q, strain_cdf,
+                        x_inj=None, u_strain_inj=None, seed=0, tick=0):
+    """Device exposure scheme (option F1 + importation gate): see lp_oracle.c."""
+    n_new = np.zeros((num_nodes, num_strains), np.int32)
+    lib().orc_tx_infect_bernoulli(
+        C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(num_strains), _p(node_ids, np.int16),
+        _p(strain, np.int8), _p(disease_state, np.int8), _p(risks, np.float32), _p(q, np.float32),
+        _p(strain_cdf, np.float64), _p(n_new), _p(x_inj, np.uint32), _p(u_strain_inj, np.float64),
+        C.c_uint64(seed), C.c_uint32(tick),
+    )
+    return n_new
+
+
+# ------------------------------------------------------- node-level math (T2)
+def tx_foi(beta_by_node_strain, network, beta_seasonality, r0_scalars, alive_counts):
+    """reference model.py:1332-1351: network transfer, seasonality x r0_scalars, rate -> probability.
+
+    ``beta_by_node_strain`` keeps whatever dtype the caller passes (float32 in the
+    reference, so the in-place ``+=`` of the transfer rounds to float32 there).
+    Returns (beta_pre copy, prob_exp_by_node_strain float64).
+    """
+    beta = np.array(beta_by_node_strain, copy=True)
+    beta_pre = beta.copy()
+    for s in range(beta.shape[1]):
+        transfer = (beta[:, s] * network.T).T
+        beta[:, s] += transfer.sum(axis=0) - transfer.sum(axis=1)
+    beta = beta * beta_seasonality * np.asarray(r0_scalars)[:, np.newaxis]
+    rate = beta / np.maximum(np.asarray(alive_counts)[:, np.newaxis], 1)
+    prob = np.maximum(1 - np.exp(-rate), 0)
+    return beta_pre, prob
+
+
+def tx_draw_counts_ref(beta_pre, prob, exposure_by_node, zero_inflation, dispersion, rs=np.random):
+    """reference model.py:1362-1407: Poisson / zero-inflated NB count per node + multinomial by strain.
+
+    ``rs`` is ``numpy.random`` (global legacy stream, like the reference) or a RandomState.
+    """
+    n_nodes, n_strains = prob.shape
+    total_prob = prob.sum(axis=1)
+    expected = exposure_by_node * total_prob
+    out = np.zeros_like(prob, dtype=np.int32)
+    for n in range(n_nodes):
+        e = expected[n]
+        if e < 0:
+            e = 0
+        if e == 0:
+            k = 0
+        elif np.sum(beta_pre[n]) == 0:
+            if zero_inflation >= 1.0:
+                k = 0
+            else:
+                mean = e / (1 - zero_inflation)
+                r = max(1, int(np.round(dispersion)))
+                p = r / (r + mean)
+                k = 0 if rs.rand() < zero_inflation else rs.negative_binomial(r, p)
+        else:
+            k = rs.poisson(e)
+        if k > 0:
+            sp = prob[n] / total_prob[n] if total_prob[n] > 0 else np.zeros(n_strains)
+            out[n] = rs.multinomial(k, sp)
+    return out, expected
+
+
+def seasonality(doy: int, days_in_year: int, amplitude: float, peak_doy: float) -> float:
+    """reference utils.py:616-625"""
+    return 1 + amplitude * np.cos(2 * np.pi * (doy - peak_doy) / days_in_year)
+
+
+def tx_node_math_device(beta_fx, exposure_fx, network, beta_seasonality, r0_scalars, alive_counts, zero_inflation,
+                        dispersion, seed, tick):
+    """float64 restatement of the DEVICE node step (lpk_tx_node_math): same formulae as the
+    reference up to the probability (model.py:1332-1351), then instead of an integer count
+    draw it emits the per-node multiplier of the per-agent Bernoulli scheme:
+
+      q[n] = float32(P_n * g_n),  P_n = sum_s prob[n, s]
+      g_n  = 1                          if the node has local infectivity (sum_s beta_pre > 0)
+           = 0 w.p. zi, else Gamma(r, 1/r) / (1 - zi)    otherwise  (model.py:1381-1393's ZINB
+             as a zero-inflated gamma-Poisson mixture), r = max(1, round(dispersion)).
+
+    The gamma variate is drawn by Marsaglia-Tsang from the node's Philox stream
+    (counter = (node, k, tick, NODE)); restated in ``node_importation_multiplier``.
+    Returns (q float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected[nodes]).
+    """
+    beta_pre = np.asarray(beta_fx, np.float64) / FX_SCALE
+    exposure = np.asarray(exposure_fx, np.float64) / FX_SCALE
+    W = np.asarray(network, np.float64)
+    beta = beta_pre + W.T @ beta_pre - beta_pre * W.sum(axis=1)[:, None]
+    beta = beta * float(beta_seasonality) * np.asarray(r0_scalars, np.float64)[:, None]
+    rate = beta / np.maximum(np.asarray(alive_counts, np.float64)[:, None], 1.0)
+    prob = np.maximum(1.0 - np.exp(-rate), 0.0)
+    P = np.zeros(prob.shape[0])
+    cdf = np.zeros_like(prob)
+    for s in range(prob.shape[1]):  # sequential sum, same association order as the device
+        P = P + prob[:, s]
+    run = np.zeros(prob.shape[0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for s in range(prob.shape[1]):
+            run = run + np.where(P > 0, prob[:, s] / P, 0.0)
+            cdf[:, s] = run
+    g = np.ones(prob.shape[0])
+    local = np.zeros(prob.shape[0])
+    for s in range(prob.shape[1]):
+        local = local + beta_pre[:, s]
+    r = max(1, int(np.round(dispersion)))
+    for n in np.nonzero((local == 0) & (P > 0))[0]:
+        g[n] = node_importation_multiplier(int(seed), int(n), int(tick), float(zero_inflation), r)
+    q = (P * g).astype(np.float32)
+    return q, cdf, prob, exposure * P
+
+
+def _node_u(seed, node, k, tick, pair):
+    x = philox4x32_10([node, k, tick, STAGE_NODE], [seed & 0xFFFFFFFF, seed >> 32])
+    hi, lo = (int(x[2]), int(x[3])) if pair else (int(x[0]), int(x[1]))
+    return float((((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0))
+
+
+def node_importation_multiplier(seed, node, tick, zi, r):
+    """g_n for an importation-only node; mirrors lpk's device function draw for draw."""
+    if zi >= 1.0:
+        return 0.0
+    if _node_u(seed, node, 0, tick, 0) < zi:
+        return 0.0
+    # Marsaglia-Tsang gamma(shape=r >= 1, scale=1); normals by Box-Muller on counter k = 1, 2, ...
+    d = r - 1.0 / 3.0
+    c = 1.0 / np.sqrt(9.0 * d)
+    k = 1
+    while True:
+        u1 = _node_u(seed, node, k, tick, 0)
+        u2 = _node_u(seed, node, k, tick, 1)
+        x = np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+        k += 1
+        v = 1.0 + c * x
+        if v <= 0:
+            continue
+        v = v * v * v
+        u = _node_u(seed, node, k, tick, 0)
+        k += 1
+        if np.log(1.0 - u) < 0.5 * x * x + d - d * v + d * np.log(v):
+            return (d * v) / r / (1.0 - zi)

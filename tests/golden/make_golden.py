@@ -1,0 +1,157 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE's own numba kernels.
+
+Runs only in the build container (needs /root/reference; the kernels are
+AST-loaded read-only by oracle/ref_loader.py, RNG call sites replaced by
+injected per-agent uniform arrays).  The fixtures are small .npz files holding
+the seeded inputs AND the reference outputs, so the tests that consume them
+(tests/test_oracle_golden.py on CPU, tests/test_gpu_parity.py on the B200) never
+need the reference checkout.
+
+    python tests/golden/make_golden.py
+
+Deterministic: the same command reproduces the same bytes (inputs come from
+numpy Generators with fixed seeds; the reference kernels are integer state
+machines once the uniforms are injected; the float32 tallies depend on the numba
+thread count, which is pinned to 4 here).
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+import numba as nb  # noqa: E402
+
+import laser_polio_b200.synth as synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+N_AGENTS, CAPACITY, N_NODES, N_STRAINS = 20_000, 20_480, 7, 3
+AGENT_COLS = list(synth.COLUMNS)
+
+
+def population(seed, **kw):
+    p = synth.synth_population(N_AGENTS, N_NODES, seed=seed, capacity=CAPACITY, f_exposed=0.08, f_infected=0.12,
+                               f_recovered=0.1, f_dead=0.03, **kw)
+    return p
+
+
+def save(name, **arrays):
+    np.savez_compressed(OUT / f"{name}.npz", **arrays)
+    print(f"wrote {name}.npz  ({(OUT / f'{name}.npz').stat().st_size / 1024:.0f} KiB)")
+
+
+def main():
+    nb.set_num_threads(4)
+    ref = ref_loader.load(inject_uniforms=True)
+    rng = np.random.default_rng(20261017)
+
+    # ---- D1: disease_state_step, 6 consecutive ticks, two paralysis probabilities ------------
+    for tag, p_par in (("ds_p03", 0.3), ("ds_p2000", 1 / 2000)):
+        p = population(11)
+        inputs = {f"in_{k}": p[k].copy() for k in AGENT_COLS}
+        ticks = 6
+        u = rng.random((ticks, CAPACITY))
+        new_pot = np.zeros((ticks, N_NODES), np.int32)
+        new_par = np.zeros((ticks, N_NODES), np.int32)
+        for t in range(ticks):
+            ref["disease_state_step"](
+                p["node_id"], N_NODES, p["disease_state"], p["strain"], p["count"], p["exposure_timer"],
+                p["infection_timer"], p["potentially_paralyzed"], p["paralyzed"], p["ipv_protected"],
+                p["paralysis_timer"], nb.float32(p_par), new_pot[t], new_par[t], u_inj=u[t],
+            )
+        save(tag, count=p["count"], n_nodes=N_NODES, p_paralysis=np.float32(p_par), u=u, new_potential=new_pot,
+             new_paralyzed=new_par, **inputs, **{f"out_{k}": p[k] for k in AGENT_COLS})
+
+    # ---- V1: get_deaths ---------------------------------------------------------------------
+    p = population(12)
+    p["date_of_death"][: p["count"]] = rng.integers(-5, 40, p["count"]).astype(np.int32)
+    inputs = {f"in_{k}": p[k].copy() for k in AGENT_COLS}
+    t = 21
+    tl = np.zeros((nb.get_num_threads(), N_NODES), np.int32)
+    dying = np.zeros(N_NODES, np.int32)
+    ref["get_deaths"](np.int32(N_NODES), np.int32(p["count"]), p["disease_state"], p["node_id"], p["date_of_death"],
+                      np.int32(t), tl, dying)
+    save("deaths", count=p["count"], n_nodes=N_NODES, t=t, num_dying=dying, **inputs,
+         out_disease_state=p["disease_state"])
+
+    # ---- R1: fast_ri on the first RI tick (closed window) and a later one (half-open) ---------
+    for tag, sim_t in (("ri_t14", 14), ("ri_t28", 28)):
+        p = population(13)
+        p["ri_timer"][: p["count"]] = rng.integers(-20, 40, p["count"]).astype(np.int16)
+        inputs = {f"in_{k}": p[k].copy() for k in AGENT_COLS}
+        pr = rng.uniform(0.2, 0.9, N_NODES)
+        pi = rng.uniform(0.2, 0.9, N_NODES)
+        u1, u2 = rng.random(CAPACITY), rng.random(CAPACITY)
+        nt = nb.get_num_threads()
+        c1, c2, c3 = (np.zeros((nt, N_NODES), np.int32) for _ in range(3))
+        ref["fast_ri"](np.int32(14), p["node_id"], p["disease_state"], p["strain"], p["ipv_protected"], p["ri_timer"],
+                       np.int32(sim_t), pr, pi, np.int32(p["count"]), c1, c2, c3, p["chronically_missed"], np.int8(1),
+                       u1, u2)
+        save(tag, count=p["count"], n_nodes=N_NODES, sim_t=sim_t, step_size=14, vx_prob_ri=pr, vx_prob_ipv=pi, u1=u1,
+             u2=u2, ri_counts=c1.sum(0), ri_protected=c2.sum(0), ipv_counts=c3.sum(0), vaccine_strain=1, **inputs,
+             **{f"out_{k}": p[k] for k in ("disease_state", "strain", "ipv_protected", "ri_timer")})
+
+    # ---- S1: fast_sia ---------------------------------------------------------------------------
+    p = population(14, max_age_days=8 * 365)
+    inputs = {f"in_{k}": p[k].copy() for k in AGENT_COLS}
+    vx = rng.uniform(0.3, 0.95, N_NODES).astype(np.float32)
+    targeted = np.array([1, 0, 1, 1, 0, 1, 1], np.uint8)
+    u = rng.random(CAPACITY)
+    nt = nb.get_num_threads()
+    lv, lp_ = np.zeros((nt, N_NODES), np.int32), np.zeros((nt, N_NODES), np.int32)
+    sim_t, vx_eff, amin, amax = 100, 0.7 * 0.8, 0, 5 * 365
+    ref["fast_sia"](p["node_id"], p["disease_state"], p["strain"], p["date_of_birth"], sim_t, vx, vx_eff, p["count"],
+                    targeted, amin, amax, lv, lp_, p["chronically_missed"], np.int8(2), u)
+    save("sia", count=p["count"], n_nodes=N_NODES, sim_t=sim_t, vx_prob=vx, vx_eff=vx_eff, nodes_to_vaccinate=targeted,
+         min_age=amin, max_age=amax, u=u, vaccinated=lv.sum(0), protected=lp_.sum(0), vaccine_strain=2, **inputs,
+         **{f"out_{k}": p[k] for k in ("disease_state", "strain")})
+
+    # ---- T1 + C1: tallies and census on one population ------------------------------------------
+    p = population(15)
+    srs = np.array([1.0, 0.25, 0.125])
+    n = p["count"]
+    beta, expo, sus = ref["tx_step_prep"](N_NODES, n, N_STRAINS, p["strain"][:n], srs, p["disease_state"][:n],
+                                          p["node_id"][:n], p["daily_infectivity"][:n], p["acq_risk_multiplier"][:n])
+    S, E, I, R, Ebs, Ibs, PP, P = ref["count_SEIRP"](p["node_id"], p["disease_state"], p["strain"],  # noqa: E741
+                                                      p["potentially_paralyzed"], p["paralyzed"], np.int32(N_NODES),
+                                                      np.int32(N_STRAINS), np.int32(n))
+    save("tally_census", count=n, n_nodes=N_NODES, n_strains=N_STRAINS, strain_r0_scalars=srs, beta=beta,
+         exposure=expo, sus=sus, S=S, E=E, I=I, R=R, E_by_strain=Ebs, I_by_strain=Ibs, POTP=PP, P=P,
+         **{f"in_{k}": p[k] for k in AGENT_COLS})
+
+    # ---- T3: tx_infect_nb statistics (distributional pin: it consumes its own numba RNG) ----------
+    # 400 repetitions on one small population: per-agent selection frequency and per-strain split.
+    p = population(16)
+    n = p["count"]
+    state0 = p["disease_state"][:n].copy()
+    sus_by_node = np.bincount(p["node_id"][:n][state0 == 0], minlength=N_NODES).astype(np.int64)
+    prob = np.tile(np.array([[0.02, 0.01, 0.005]]), (N_NODES, 1))
+    want = np.zeros((N_NODES, N_STRAINS), np.int32)
+    want[:, 0] = [60, 0, 40, 25, 80, 10, 5]
+    want[:, 1] = [20, 0, 10, 5, 10, 0, 5]
+    reps = 400
+    hits = np.zeros(n, np.int32)
+    by_strain = np.zeros((N_NODES, N_STRAINS), np.int64)
+    si = np.zeros(CAPACITY, np.int32)
+    sp = np.zeros(CAPACITY, np.float32)
+    for _ in range(reps):
+        st = state0.copy()
+        strain = p["strain"][:n].copy()
+        nn = ref["tx_infect_nb"](N_NODES, n, N_STRAINS, sus_by_node, p["node_id"][:n], strain, st, si, sp,
+                                 p["acq_risk_multiplier"][:n], prob, want)
+        hits += (st == 1) & (state0 == 0)
+        by_strain += nn
+    save("tx_infect_stats", count=n, n_nodes=N_NODES, n_strains=N_STRAINS, reps=reps, prob=prob, want=want,
+         sus_by_node=sus_by_node, hits=hits, new_by_strain=by_strain, **{f"in_{k}": p[k] for k in AGENT_COLS})
+
+
+if __name__ == "__main__":
+    if not ref_loader.available():
+        raise SystemExit("needs the reference checkout at /root/reference")
+    main()
