@@ -1,0 +1,158 @@
+/*
+ * lpk.h -- C ABI of liblpk.so, the B200 (sm_100a) kernels for laser-polio's
+ * per-tick agent update.
+ *
+ * Drop-in boundary: one entry point per free function of the reference's hot
+ * path.  Each declaration cites the reference
+ * signature it replaces (paths relative to the reference checkout,
+ * model.py = src/laser_polio/model.py).  Array arguments keep the reference's
+ * order, meaning and dtypes; they are DEVICE pointers into the structure-of-
+ * arrays agent table (owned by the caller -- PyTorch buffers in the shipped
+ * host code; the library borrows and never frees).  Per-node outputs are device
+ * pointers too.  `stream` is a cudaStream_t passed as void*.  No torch types
+ * cross this boundary.
+ *
+ * Every call is asynchronous on `stream` and returns a status:
+ *   0                      success (kernel enqueued)
+ *   LPK_ERR_ARG  (-1)      null pointer / negative size / unsupported n_strains
+ *   LPK_ERR_CUDA (-2)      a CUDA runtime error; text via lpk_last_error()
+ *
+ * Uniform source (`lpk_rng`).  The reference draws from numba's per-thread
+ * Mersenne streams (np.random.random() at model.py:441, np.random.rand() at
+ * :1845, :1852, :2049), which no parallel device schedule can reproduce.  Here
+ * every draw is Philox4x32-10 keyed on (seed, agent index, tick, stage), so a
+ * result depends neither on grid shape nor on GPU count.  For parity runs the
+ * optional u1/u2/x arrays inject the same per-agent uniforms the reference
+ * (RNG call sites textually replaced) and the oracle consume.
+ */
+#ifndef LPK_H
+#define LPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPK_OK 0
+#define LPK_ERR_ARG (-1)
+#define LPK_ERR_CUDA (-2)
+
+#define LPK_MAX_STRAINS 4
+#define LPK_FX_SCALE 1073741824.0 /* 2^30: fixed-point scale of the float tallies */
+
+/* Philox stage ids (counter word 3) */
+#define LPK_STAGE_PARALYSIS 0u
+#define LPK_STAGE_RI 1u
+#define LPK_STAGE_SIA 2u /* | event index << 8 */
+#define LPK_STAGE_EXPOSE 3u
+#define LPK_STAGE_STRAIN 4u
+#define LPK_STAGE_NODE 5u
+#define LPK_STAGE_BIRTH 6u
+#define LPK_STAGE_LIFESPAN 7u
+
+typedef struct lpk_rng {
+    uint64_t seed;      /* Philox key */
+    uint32_t tick;      /* Philox counter word 2 */
+    uint32_t _pad;
+    const double *u1;   /* optional injected per-agent uniforms (device), else NULL */
+    const double *u2;   /* second injected stream (fast_ri IPV draw; strain pick in tx_infect) */
+    const uint32_t *x;  /* optional injected per-agent 32-bit words for the exposure trial */
+} lpk_rng;
+
+const char *lpk_last_error(void);
+int lpk_version(void);
+/* Philox4x32-10 on the device for `n` (ctr,key) pairs -- known-answer testing only. */
+int lpk_philox_selftest(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n, void *stream);
+
+/* V1  replaces get_deaths(num_nodes, num_people, disease_state, node_id, date_of_death, t, tl_dying, num_dying)
+ *     model.py:1767-1781.  num_dying[n_nodes] is OVERWRITTEN (reference: num_dying[:] = tl_dying.sum(axis=0)).
+ *     The reference's thread-local scratch (tl_dying) has no device counterpart. */
+int lpk_get_deaths(int32_t num_nodes, int64_t num_people, int8_t *disease_state, const int16_t *node_id,
+                   const int32_t *date_of_death, int32_t t, int32_t *num_dying, void *stream);
+
+/* D1  replaces disease_state_step(node_id, n_nodes, disease_state, strain, active_count, exposure_timer,
+ *     infection_timer, potentially_paralyzed, paralyzed, ipv_protected, paralysis_timer, p_paralysis,
+ *     new_potential, new_paralyzed)  model.py:344-454.  new_potential/new_paralyzed[n_nodes] are ADDED to
+ *     (reference: new_potential[:] += ..., model.py:389-390). */
+int lpk_disease_state_step(const int16_t *node_id, int32_t n_nodes, int8_t *disease_state, const int8_t *strain,
+                           int64_t active_count, int8_t *exposure_timer, int8_t *infection_timer,
+                           int8_t *potentially_paralyzed, int8_t *paralyzed, const int8_t *ipv_protected,
+                           int8_t *paralysis_timer, float p_paralysis, int32_t *new_potential,
+                           int32_t *new_paralyzed, const lpk_rng *rng, void *stream);
+
+/* R1  replaces fast_ri(step_size, node_id, disease_state, strain, ipv_protected, ri_timer, sim_t, vx_prob_ri,
+ *     vx_prob_ipv, num_people, local_ri_counts, local_ri_protected, local_ipv_counts, chronically_missed,
+ *     ri_vaccine_strain)  model.py:1805-1855.  The three [threads, nodes] scratch arrays of the reference
+ *     become per-node outputs ri_counts/ri_protected/ipv_counts[n_nodes], OVERWRITTEN
+ *     (reference: results.ri_vaccinated[t] = local.sum(axis=0), model.py:1970-1983). */
+int lpk_fast_ri(int64_t step_size, const int16_t *node_id, int8_t *disease_state, int8_t *strain,
+                int8_t *ipv_protected, int16_t *ri_timer, int64_t sim_t, const double *vx_prob_ri,
+                const double *vx_prob_ipv, int64_t num_people, int32_t n_nodes, int32_t *ri_counts,
+                int32_t *ri_protected, int32_t *ipv_counts, const uint8_t *chronically_missed,
+                int8_t ri_vaccine_strain, const lpk_rng *rng, void *stream);
+
+/* S1  replaces fast_sia(node_ids, disease_states, strain, dobs, sim_t, vx_prob, vx_eff, count, nodes_to_vaccinate,
+ *     min_age, max_age, local_vaccinated, local_protected, chronically_missed, sia_vaccine_strain)
+ *     model.py:1995-2060.  vaccinated/protected_[n_nodes] OVERWRITTEN.  event_idx distinguishes several
+ *     campaigns on one day (each sees the previous one's state changes, model.py:2103). */
+int lpk_fast_sia(const int16_t *node_ids, int8_t *disease_states, int8_t *strain, const int32_t *dobs,
+                 int64_t sim_t, const float *vx_prob, double vx_eff, int64_t count,
+                 const uint8_t *nodes_to_vaccinate, int64_t min_age, int64_t max_age, int32_t n_nodes,
+                 int32_t *vaccinated, int32_t *protected_, const uint8_t *chronically_missed,
+                 int8_t sia_vaccine_strain, uint32_t event_idx, const lpk_rng *rng, void *stream);
+
+/* T1  replaces tx_step_prep(num_nodes, num_people, n_strains, strains, strain_r0_scalars, disease_states,
+ *     node_ids, daily_infectivity, risks)  model.py:932-1007.  Outputs OVERWRITTEN:
+ *       beta_fx[num_nodes * n_strains]  sum over infectious of infectivity * strain_r0_scalars[strain]
+ *       exposure_fx[num_nodes]          sum over susceptibles of acq_risk_multiplier
+ *       sus[num_nodes]                  susceptible count
+ *     The float sums are exact 2^30 fixed point in int64 (value = fx / LPK_FX_SCALE): order independent,
+ *     bitwise reproducible across launch shapes and GPU counts, within 1e-9 of the float64 sum (the
+ *     reference's per-thread float32 accumulation is itself ~5e-6 off it).  strain_r0_scalars: HOST double[n_strains]. */
+int lpk_tx_step_prep(int32_t num_nodes, int64_t num_people, int32_t n_strains, const int8_t *strains,
+                     const double *h_strain_r0_scalars, const int8_t *disease_states, const int16_t *node_ids,
+                     const float *daily_infectivity, const float *risks, int64_t *beta_fx, int64_t *exposure_fx,
+                     int64_t *sus, void *stream);
+
+/* T2  replaces the node-level block of Transmission_ABM.step, model.py:1332-1351 and 1362-1407:
+ *     network transfer beta += W^T beta - beta * rowsum(W), x seasonality x r0_scalars, / max(pop, 1),
+ *     p = max(1 - exp(-rate), 0).  Instead of an integer Poisson / ZINB count per node (host numpy RNG in the
+ *     reference) it emits the per-node multiplier of the per-agent Bernoulli scheme (SURVEY App. F, F1 +
+ *     importation gate):  q[n] = float(P_n * g_n), P_n = sum_s p[n,s]; g_n = 1 with local infectivity, else
+ *     0 w.p. zero_inflation, else Gamma(r, 1/r) / (1 - zero_inflation), r = max(1, round(dispersion)).
+ *       network        double[num_nodes * num_nodes] row-major, W[i,j] = fraction moving i -> j
+ *       r0_scalars     double[num_nodes]
+ *       alive_counts   int32[num_nodes]  (results.pop[t], model.py:1344)
+ *     outputs: q float[num_nodes], strain_cdf double[num_nodes * n_strains] (cumulative p[n,s]/P_n),
+ *              prob double[num_nodes * n_strains], expected double[num_nodes] (exposure[n] * P_n, model.py:1363).
+ *     rowsum_ws: caller-owned scratch, double[num_nodes] (row sums of W are recomputed every call because
+ *     the reference re-reads tx.network each tick, model.py:1335). */
+int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
+                     const double *network, double beta_seasonality, const double *r0_scalars,
+                     const int32_t *alive_counts, double zero_inflation, double dispersion, float *q,
+                     double *strain_cdf, double *prob, double *expected, double *rowsum_ws, const lpk_rng *rng,
+                     void *stream);
+
+/* T3  replaces tx_infect_nb(num_nodes, num_people, num_strains, sus_by_node, node_ids, strain, disease_state,
+ *     sus_indices_storage, sus_probs_storage, risks, prob_exp_by_node_strain, n_exposures_to_create_by_node_strain)
+ *     model.py:1010-1149.  Per-agent Bernoulli: susceptible i of node n is exposed iff
+ *     x_i < floor(risk_i * q[n] * 2^32) with x_i word (i & 3) of Philox(seed; i >> 2, tick, EXPOSE); strain by
+ *     the cumulative categorical of model.py:1127-1141.  No bucket pass, no scratch columns.
+ *     n_new[num_nodes * num_strains] OVERWRITTEN (the reference returns it). */
+int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_strains, const int16_t *node_ids,
+                  int8_t *strain, int8_t *disease_state, const float *risks, const float *q,
+                  const double *strain_cdf, int32_t *n_new, const lpk_rng *rng, void *stream);
+
+/* C1  replaces count_SEIRP(node_id, disease_state, strain, potentially_paralyzed, paralyzed, n_nodes, n_strains,
+ *     n_people)  model.py:869-929.  All eight outputs OVERWRITTEN (the reference returns fresh arrays):
+ *     S, E, I, R, POTP, P int32[n_nodes]; E_by_strain, I_by_strain int32[n_nodes * n_strains]. */
+int lpk_count_seirp(const int16_t *node_id, const int8_t *disease_state, const int8_t *strain,
+                    const int8_t *potentially_paralyzed, const int8_t *paralyzed, int32_t n_nodes,
+                    int32_t n_strains, int64_t n_people, int32_t *S, int32_t *E, int32_t *I, int32_t *R,
+                    int32_t *E_by_strain, int32_t *I_by_strain, int32_t *POTP, int32_t *P, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPK_H */

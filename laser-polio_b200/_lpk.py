@@ -1,0 +1,93 @@
+"""ctypes binding of liblpk.so (the C ABI declared in include/lpk.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There
+is NO fallback: if the shared object is missing or a call fails, this module raises.
+Device memory, streams and process groups come from PyTorch; this module only
+passes raw device pointers and the current stream handle across the C boundary.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+SO_PATH = _HERE / "liblpk.so"
+
+LPK_OK, LPK_ERR_ARG, LPK_ERR_CUDA = 0, -1, -2
+MAX_STRAINS = 4
+FX_SCALE = float(2**30)
+
+EXPORTS = (
+    "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
+    "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp",
+)
+
+
+class LpkError(RuntimeError):
+    pass
+
+
+class Rng(C.Structure):
+    """struct lpk_rng (include/lpk.h)."""
+
+    _fields_ = [
+        ("seed", C.c_uint64), ("tick", C.c_uint32), ("_pad", C.c_uint32),
+        ("u1", C.c_void_p), ("u2", C.c_void_p), ("x", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load liblpk.so; raise loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not SO_PATH.exists():
+            raise LpkError(
+                f"{SO_PATH} is missing: the CUDA extension has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback."
+            )
+        _lib = C.CDLL(str(SO_PATH))
+        _lib.lpk_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            if not hasattr(_lib, name):
+                raise LpkError(f"liblpk.so does not export {name}")
+    return _lib
+
+
+def check(status: int, where: str) -> None:
+    if status == LPK_OK:
+        return
+    msg = lib().lpk_last_error().decode()
+    if status == LPK_ERR_ARG:
+        raise ValueError(f"{where}: {msg}")
+    raise LpkError(f"{where}: {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LpkError("expected a CUDA tensor; the device path has no host fallback")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_handle():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_rng(seed=0, tick=0, u1=None, u2=None, x=None) -> Rng:
+    r = Rng()
+    r.seed, r.tick, r._pad = int(seed) & 0xFFFFFFFFFFFFFFFF, int(tick) & 0xFFFFFFFF, 0
+    r.u1 = u1.data_ptr() if u1 is not None else None
+    r.u2 = u2.data_ptr() if u2 is not None else None
+    r.x = x.data_ptr() if x is not None else None
+    r._keep = (u1, u2, x)  # the struct only holds raw pointers: keep the tensors alive with it
+    return r

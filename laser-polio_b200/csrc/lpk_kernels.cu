@@ -1,0 +1,743 @@
+// lpk_kernels.cu -- sm_100a kernels + C-ABI launchers, one per reference hot-path function
+// (include/lpk.h cites the reference signature each replaces).  All kernels are HBM-bound
+// streaming scans over the agent structure-of-arrays; see lpk_common.cuh for the quad tiling.
+#include <cstdio>
+#include <cstring>
+
+#include "lpk_common.cuh"
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[256] = "";
+static int set_cuda_err(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return LPK_ERR_CUDA;
+}
+static int set_arg_err(const char *what) {
+    snprintf(g_err, sizeof(g_err), "bad argument: %s", what);
+    return LPK_ERR_ARG;
+}
+extern "C" const char *lpk_last_error(void) { return g_err; }
+extern "C" int lpk_version(void) { return 1; }
+
+#define REQUIRE(cond, what) do { if (!(cond)) return set_arg_err(what); } while (0)
+#define ALIGNED(p, a) ((reinterpret_cast<uintptr_t>(p) & ((a) - 1)) == 0)
+#define CUDA_TRY(expr, where) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_cuda_err(e_, where); } while (0)
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+// persistent grid: a multiple of the SM count, never more blocks than there are tiles per warp-group
+static int agent_grid(int64_t n, int blocks_per_sm) {
+    const int64_t tiles = (n + LPK_TILE - 1) / LPK_TILE;
+    const int64_t want = (tiles + LPK_WARPS - 1) / LPK_WARPS;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+static cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct DevRng {
+    uint64_t seed;
+    uint32_t tick;
+    const double *u1;
+    const double *u2;
+    const uint32_t *x;
+};
+static DevRng dev_rng(const lpk_rng *r) {
+    DevRng d;
+    d.seed = r ? r->seed : 0; d.tick = r ? r->tick : 0;
+    d.u1 = r ? r->u1 : nullptr; d.u2 = r ? r->u2 : nullptr; d.x = r ? r->x : nullptr;
+    return d;
+}
+
+// ------------------------------------------------------------------ Philox self test
+__global__ void k_philox_selftest(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = o[k];
+}
+extern "C" int lpk_philox_selftest(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n, void *stream) {
+    REQUIRE(ctr4 && key2 && out4 && n >= 0, "philox_selftest");
+    if (n == 0) return LPK_OK;
+    k_philox_selftest<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(ctr4, key2, out4, n);
+    CUDA_TRY(cudaGetLastError(), "lpk_philox_selftest");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ V1 get_deaths
+__global__ void __launch_bounds__(LPK_BLOCK) k_get_deaths(int64_t n, int8_t *__restrict__ state,
+                                                           const int16_t *__restrict__ node_id,
+                                                           const int32_t *__restrict__ dod, int32_t t,
+                                                           int32_t *__restrict__ num_dying) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t base = quad_base(tile, j, lane);
+            const int valid = quad_valid(base, n);
+            if (valid == 0) continue;
+            const uint32_t w = load_b4(state, base, valid);
+            if ((w & 0x80808080u) == 0x80808080u) continue;  // whole quad dead / unborn
+            int d[4];
+            load_i4(dod, base, valid, d);
+            uint32_t nw = w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (byte_of(w, k) >= 0 && d[k] <= t) {
+                    nw = set_byte(nw, k, -1);
+                    atomicAdd(&num_dying[node_id[base + k]], 1);
+                }
+            }
+            if (nw != w) store_b4(state, base, valid, nw);
+        }
+    }
+}
+extern "C" int lpk_get_deaths(int32_t num_nodes, int64_t num_people, int8_t *disease_state, const int16_t *node_id,
+                              const int32_t *date_of_death, int32_t t, int32_t *num_dying, void *stream) {
+    REQUIRE(num_nodes > 0 && num_people >= 0, "get_deaths sizes");
+    REQUIRE(disease_state && node_id && date_of_death && num_dying, "get_deaths null pointer");
+    REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(date_of_death, 16), "get_deaths alignment");
+    CUDA_TRY(cudaMemsetAsync(num_dying, 0, sizeof(int32_t) * num_nodes, as_stream(stream)), "get_deaths memset");
+    if (num_people == 0) return LPK_OK;
+    k_get_deaths<<<agent_grid(num_people, 8), LPK_BLOCK, 0, as_stream(stream)>>>(num_people, disease_state, node_id,
+                                                                                 date_of_death, t, num_dying);
+    CUDA_TRY(cudaGetLastError(), "lpk_get_deaths");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ D1 disease_state_step
+// One agent of the state machine (reference model.py:419-452); returns the new state.
+__device__ __forceinline__ int8_t ds_agent(int64_t i, int8_t s, const int16_t *node_id, const int8_t *strain,
+                                           int8_t *etimer, int8_t *itimer, int8_t *pot_par, int8_t *paralyzed,
+                                           const int8_t *ipv, int8_t *ptimer, double p_paralysis, int32_t *new_pot,
+                                           int32_t *new_par, const DevRng &rng) {
+    if (s == 1) {
+        const int8_t e = etimer[i];
+        if (e <= 0) s = 2;
+        etimer[i] = (int8_t)(e - 1);
+    }
+    if (s == 2) {
+        const int8_t it = itimer[i];
+        if (it <= 0) s = 3;
+        itimer[i] = (int8_t)(it - 1);
+        if (strain[i] == 0) {
+            const int8_t pt = ptimer[i];
+            if (pt <= 0 && pot_par[i] == -1) {
+                if (ipv[i] == 0) {
+                    pot_par[i] = 1;
+                    const int nd = node_id[i];
+                    atomicAdd(&new_pot[nd], 1);
+                    double u;
+                    if (rng.u1) u = rng.u1[i];
+                    else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
+                    if (u < p_paralysis) { paralyzed[i] = 1; atomicAdd(&new_par[nd], 1); }
+                } else {
+                    pot_par[i] = 0;
+                }
+            }
+            ptimer[i] = (int8_t)(pt - 1);
+        }
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(LPK_BLOCK) k_disease_state(int64_t n, const int16_t *__restrict__ node_id,
+                                                              int8_t *__restrict__ state, const int8_t *__restrict__ strain,
+                                                              int8_t *etimer, int8_t *itimer, int8_t *pot_par,
+                                                              int8_t *paralyzed, const int8_t *__restrict__ ipv,
+                                                              int8_t *ptimer, double p_paralysis, int32_t *new_pot,
+                                                              int32_t *new_par, DevRng rng) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+        uint32_t w[4];
+        int64_t base[4];
+        int valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // all four state words in flight before any is used
+            base[j] = quad_base(tile, j, lane);
+            valid[j] = quad_valid(base[j], n);
+            w[j] = valid[j] ? load_b4(state, base[j], valid[j]) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!(any_byte_eq(w[j], 1u) || any_byte_eq(w[j], 2u))) continue;  // no E / I in this quad
+            uint32_t nw = w[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int8_t s = byte_of(w[j], k);
+                if (s == 1 || s == 2) {
+                    const int8_t ns = ds_agent(base[j] + k, s, node_id, strain, etimer, itimer, pot_par, paralyzed, ipv,
+                                               ptimer, p_paralysis, new_pot, new_par, rng);
+                    nw = set_byte(nw, k, ns);
+                }
+            }
+            if (nw != w[j]) store_b4(state, base[j], valid[j], nw);
+        }
+    }
+}
+extern "C" int lpk_disease_state_step(const int16_t *node_id, int32_t n_nodes, int8_t *disease_state,
+                                      const int8_t *strain, int64_t active_count, int8_t *exposure_timer,
+                                      int8_t *infection_timer, int8_t *potentially_paralyzed, int8_t *paralyzed,
+                                      const int8_t *ipv_protected, int8_t *paralysis_timer, float p_paralysis,
+                                      int32_t *new_potential, int32_t *new_paralyzed, const lpk_rng *rng, void *stream) {
+    REQUIRE(n_nodes > 0 && active_count >= 0, "disease_state_step sizes");
+    REQUIRE(node_id && disease_state && strain && exposure_timer && infection_timer && potentially_paralyzed &&
+                paralyzed && ipv_protected && paralysis_timer && new_potential && new_paralyzed,
+            "disease_state_step null pointer");
+    REQUIRE(ALIGNED(disease_state, 4), "disease_state_step alignment");
+    if (active_count == 0) return LPK_OK;
+    k_disease_state<<<agent_grid(active_count, 8), LPK_BLOCK, 0, as_stream(stream)>>>(
+        active_count, node_id, disease_state, strain, exposure_timer, infection_timer, potentially_paralyzed, paralyzed,
+        ipv_protected, paralysis_timer, (double)p_paralysis, new_potential, new_paralyzed, dev_rng(rng));
+    CUDA_TRY(cudaGetLastError(), "lpk_disease_state_step");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ R1 fast_ri
+__global__ void __launch_bounds__(LPK_BLOCK) k_fast_ri(int64_t n, int step, const int16_t *__restrict__ node_id,
+                                                        int8_t *__restrict__ state, int8_t *strain, int8_t *ipv,
+                                                        int16_t *__restrict__ ri_timer, int64_t sim_t,
+                                                        const double *__restrict__ prob_ri,
+                                                        const double *__restrict__ prob_ipv, int32_t *ri_counts,
+                                                        int32_t *ri_protected, int32_t *ipv_counts,
+                                                        const uint8_t *__restrict__ missed, int8_t vaccine_strain,
+                                                        DevRng rng) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    const bool first = (sim_t == step), later = (sim_t > step);
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t base = quad_base(tile, j, lane);
+            const int valid = quad_valid(base, n);
+            if (valid == 0) continue;
+            const uint32_t w = load_b4(state, base, valid);
+            if ((w & 0x80808080u) == 0x80808080u) continue;
+            const uint32_t m = load_b4(reinterpret_cast<const int8_t *>(missed), base, valid, 1);
+            int tm[4];
+            load_s4(ri_timer, base, valid, tm);
+            uint32_t nw = w;
+            bool touched = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int8_t s = byte_of(w, k);
+                if (s < 0 || byte_of(m, k) == 1) continue;
+                const int timer = tm[k] - step;  // eligibility uses the unwrapped value, the store wraps to int16
+                tm[k] = timer;
+                touched = true;
+                const bool eligible = first ? (timer <= 0 && timer >= -step) : (later && timer <= 0 && timer > -step);
+                if (!eligible) continue;
+                const int64_t i = base + k;
+                const int nd = node_id[i];
+                double u1, u2;
+                if (rng.u1) { u1 = rng.u1[i]; u2 = rng.u2[i]; }
+                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_RI, x); u1 = u53(x[0], x[1]); u2 = u53(x[2], x[3]); }
+                if (u1 < prob_ri[nd]) {
+                    atomicAdd(&ri_counts[nd], 1);
+                    if (s == 0) { nw = set_byte(nw, k, 1); strain[i] = vaccine_strain; atomicAdd(&ri_protected[nd], 1); }
+                }
+                if (u2 < prob_ipv[nd]) { atomicAdd(&ipv_counts[nd], 1); ipv[i] = 1; }
+            }
+            if (touched) {
+                if (valid == 4) *reinterpret_cast<short4 *>(ri_timer + base) = make_short4((short)tm[0], (short)tm[1], (short)tm[2], (short)tm[3]);
+                else for (int k = 0; k < valid; ++k) ri_timer[base + k] = (int16_t)tm[k];
+            }
+            if (nw != w) store_b4(state, base, valid, nw);
+        }
+    }
+}
+extern "C" int lpk_fast_ri(int64_t step_size, const int16_t *node_id, int8_t *disease_state, int8_t *strain,
+                           int8_t *ipv_protected, int16_t *ri_timer, int64_t sim_t, const double *vx_prob_ri,
+                           const double *vx_prob_ipv, int64_t num_people, int32_t n_nodes, int32_t *ri_counts,
+                           int32_t *ri_protected, int32_t *ipv_counts, const uint8_t *chronically_missed,
+                           int8_t ri_vaccine_strain, const lpk_rng *rng, void *stream) {
+    REQUIRE(n_nodes > 0 && num_people >= 0 && step_size > 0 && step_size < 32768, "fast_ri sizes");
+    REQUIRE(node_id && disease_state && strain && ipv_protected && ri_timer && vx_prob_ri && vx_prob_ipv && ri_counts &&
+                ri_protected && ipv_counts && chronically_missed, "fast_ri null pointer");
+    REQUIRE(!rng || !rng->u1 || rng->u2, "fast_ri needs both injected streams");
+    REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(chronically_missed, 4) && ALIGNED(ri_timer, 8), "fast_ri alignment");
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemsetAsync(ri_counts, 0, sizeof(int32_t) * n_nodes, st), "fast_ri memset");
+    CUDA_TRY(cudaMemsetAsync(ri_protected, 0, sizeof(int32_t) * n_nodes, st), "fast_ri memset");
+    CUDA_TRY(cudaMemsetAsync(ipv_counts, 0, sizeof(int32_t) * n_nodes, st), "fast_ri memset");
+    if (num_people == 0) return LPK_OK;
+    k_fast_ri<<<agent_grid(num_people, 8), LPK_BLOCK, 0, st>>>(num_people, (int)step_size, node_id, disease_state, strain,
+                                                               ipv_protected, ri_timer, sim_t, vx_prob_ri, vx_prob_ipv,
+                                                               ri_counts, ri_protected, ipv_counts, chronically_missed,
+                                                               ri_vaccine_strain, dev_rng(rng));
+    CUDA_TRY(cudaGetLastError(), "lpk_fast_ri");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ S1 fast_sia
+__global__ void __launch_bounds__(LPK_BLOCK) k_fast_sia(int64_t n, const int16_t *__restrict__ node_id,
+                                                         int8_t *__restrict__ state, int8_t *strain,
+                                                         const int32_t *__restrict__ dob, int64_t sim_t,
+                                                         const float *__restrict__ vx_prob, double vx_eff,
+                                                         const uint8_t *__restrict__ targeted, int64_t min_age,
+                                                         int64_t max_age, int32_t *vaccinated, int32_t *protected_,
+                                                         const uint8_t *__restrict__ missed, int8_t vaccine_strain,
+                                                         uint32_t stage, DevRng rng) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    NodeAcc<2, 0> acc;
+    acc.init();
+    auto flush = [&](int nd, const int *ci, const long long *) {
+        red_add(&vaccinated[nd], ci[0]);
+        red_add(&protected_[nd], ci[1]);
+    };
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t base = quad_base(tile, j, lane);
+            const int valid = quad_valid(base, n);
+            if (valid == 0) continue;
+            const uint32_t w = load_b4(state, base, valid);
+            if ((w & 0x80808080u) == 0x80808080u) continue;
+            const uint32_t m = load_b4(reinterpret_cast<const int8_t *>(missed), base, valid, 1);
+            int d[4];
+            load_i4(dob, base, valid, d);
+            bool elig[4];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t age = sim_t - d[k];
+                elig[k] = byte_of(w, k) >= 0 && byte_of(m, k) != 1 && min_age <= age && age <= max_age;
+                any |= elig[k];
+            }
+            if (!any) continue;
+            int nd[4];
+            load_s4(node_id, base, valid, nd);
+            uint32_t nw = w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!elig[k] || targeted[nd[k]] == 0) continue;
+                const int64_t i = base + k;
+                double r;
+                if (rng.u1) r = rng.u1[i];
+                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, stage, x); r = u53(x[0], x[1]); }
+                const double pv = (double)vx_prob[nd[k]];
+                if (r < pv) {
+                    acc.select(nd[k], flush);
+                    acc.ci[0] += 1;
+                    if (byte_of(w, k) == 0 && r < pv * vx_eff) {
+                        nw = set_byte(nw, k, 1);
+                        strain[i] = vaccine_strain;
+                        acc.ci[1] += 1;
+                    }
+                }
+            }
+            if (nw != w) store_b4(state, base, valid, nw);
+        }
+    }
+    acc.finish_warp(flush);
+}
+extern "C" int lpk_fast_sia(const int16_t *node_ids, int8_t *disease_states, int8_t *strain, const int32_t *dobs,
+                            int64_t sim_t, const float *vx_prob, double vx_eff, int64_t count,
+                            const uint8_t *nodes_to_vaccinate, int64_t min_age, int64_t max_age, int32_t n_nodes,
+                            int32_t *vaccinated, int32_t *protected_, const uint8_t *chronically_missed,
+                            int8_t sia_vaccine_strain, uint32_t event_idx, const lpk_rng *rng, void *stream) {
+    REQUIRE(n_nodes > 0 && count >= 0, "fast_sia sizes");
+    REQUIRE(node_ids && disease_states && strain && dobs && vx_prob && nodes_to_vaccinate && vaccinated && protected_ &&
+                chronically_missed, "fast_sia null pointer");
+    REQUIRE(ALIGNED(disease_states, 4) && ALIGNED(chronically_missed, 4) && ALIGNED(dobs, 16) && ALIGNED(node_ids, 8),
+            "fast_sia alignment");
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemsetAsync(vaccinated, 0, sizeof(int32_t) * n_nodes, st), "fast_sia memset");
+    CUDA_TRY(cudaMemsetAsync(protected_, 0, sizeof(int32_t) * n_nodes, st), "fast_sia memset");
+    if (count == 0) return LPK_OK;
+    k_fast_sia<<<agent_grid(count, 8), LPK_BLOCK, 0, st>>>(count, node_ids, disease_states, strain, dobs, sim_t, vx_prob,
+                                                           vx_eff, nodes_to_vaccinate, min_age, max_age, vaccinated,
+                                                           protected_, chronically_missed, sia_vaccine_strain,
+                                                           LPK_STAGE_SIA | (event_idx << 8), dev_rng(rng));
+    CUDA_TRY(cudaGetLastError(), "lpk_fast_sia");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ T1 tx_step_prep (tally)
+struct StrainScalars { double v[LPK_MAX_STRAINS]; };
+
+__global__ void __launch_bounds__(LPK_BLOCK) k_tx_step_prep(int64_t n, int n_strains, const int8_t *__restrict__ strain,
+                                                             StrainScalars srs, const int8_t *__restrict__ state,
+                                                             const int16_t *__restrict__ node_id,
+                                                             const float *__restrict__ infectivity,
+                                                             const float *__restrict__ risk, int64_t *beta_fx,
+                                                             int64_t *exposure_fx, int64_t *sus) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    NodeAcc<1, 1 + LPK_MAX_STRAINS> acc;
+    acc.init();
+    auto flush = [&](int nd, const int *ci, const long long *cl) {
+        if (ci[0]) atomicAdd(reinterpret_cast<unsigned long long *>(&sus[nd]), (unsigned long long)ci[0]);
+        red_add(&exposure_fx[nd], cl[0]);
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s)
+            if (s < n_strains) red_add(&beta_fx[(int64_t)nd * n_strains + s], cl[1 + s]);
+    };
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+        uint32_t w[4];
+        int64_t base[4];
+        int valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            base[j] = quad_base(tile, j, lane);
+            valid[j] = quad_valid(base[j], n);
+            w[j] = valid[j] ? load_b4(state, base[j], valid[j]) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool anyS = any_byte_eq(w[j], 0u), anyI = any_byte_eq(w[j], 2u);
+            if (!(anyS || anyI)) continue;
+            int nd[4];
+            load_s4(node_id, base[j], valid[j], nd);
+            float rk[4] = {0.f, 0.f, 0.f, 0.f};
+            if (anyS) load_f4(risk, base[j], valid[j], rk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int8_t s = byte_of(w[j], k);
+                if (s == 0) {
+                    acc.select(nd[k], flush);
+                    acc.ci[0] += 1;
+                    acc.cl[0] += to_fx((double)rk[k]);
+                } else if (s == 2) {
+                    acc.select(nd[k], flush);
+                    const int stn = strain[base[j] + k];
+                    const double v = (double)infectivity[base[j] + k] * srs.v[stn];
+                    const long long fx = to_fx(v);
+#pragma unroll
+                    for (int q = 0; q < LPK_MAX_STRAINS; ++q) acc.cl[1 + q] += (q == stn) ? fx : 0ll;
+                }
+            }
+        }
+    }
+    acc.finish_warp(flush);
+}
+extern "C" int lpk_tx_step_prep(int32_t num_nodes, int64_t num_people, int32_t n_strains, const int8_t *strains,
+                                const double *h_strain_r0_scalars, const int8_t *disease_states,
+                                const int16_t *node_ids, const float *daily_infectivity, const float *risks,
+                                int64_t *beta_fx, int64_t *exposure_fx, int64_t *sus, void *stream) {
+    REQUIRE(num_nodes > 0 && num_people >= 0, "tx_step_prep sizes");
+    REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "tx_step_prep n_strains");
+    REQUIRE(strains && h_strain_r0_scalars && disease_states && node_ids && daily_infectivity && risks && beta_fx &&
+                exposure_fx && sus, "tx_step_prep null pointer");
+    REQUIRE(ALIGNED(disease_states, 4) && ALIGNED(node_ids, 8) && ALIGNED(risks, 16), "tx_step_prep alignment");
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemsetAsync(beta_fx, 0, sizeof(int64_t) * num_nodes * n_strains, st), "tx_step_prep memset");
+    CUDA_TRY(cudaMemsetAsync(exposure_fx, 0, sizeof(int64_t) * num_nodes, st), "tx_step_prep memset");
+    CUDA_TRY(cudaMemsetAsync(sus, 0, sizeof(int64_t) * num_nodes, st), "tx_step_prep memset");
+    if (num_people == 0) return LPK_OK;
+    StrainScalars srs;
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) srs.v[s] = s < n_strains ? h_strain_r0_scalars[s] : 0.0;
+    k_tx_step_prep<<<agent_grid(num_people, 8), LPK_BLOCK, 0, st>>>(num_people, n_strains, strains, srs, disease_states,
+                                                                    node_ids, daily_infectivity, risks, beta_fx,
+                                                                    exposure_fx, sus);
+    CUDA_TRY(cudaGetLastError(), "lpk_tx_step_prep");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ C1 count_SEIRP (census)
+__global__ void __launch_bounds__(LPK_BLOCK) k_count_seirp(int64_t n, int n_strains, const int16_t *__restrict__ node_id,
+                                                            const int8_t *__restrict__ state,
+                                                            const int8_t *__restrict__ strain,
+                                                            const int8_t *__restrict__ pot_par,
+                                                            const int8_t *__restrict__ paralyzed, int32_t *S, int32_t *R,
+                                                            int32_t *Ebs, int32_t *Ibs, int32_t *POTP, int32_t *P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    // ci: 0 S, 1 R, 2 POTP, 3 P, 4.. E by strain, 4+MAX.. I by strain
+    NodeAcc<4 + 2 * LPK_MAX_STRAINS, 0> acc;
+    acc.init();
+    auto flush = [&](int nd, const int *ci, const long long *) {
+        red_add(&S[nd], ci[0]); red_add(&R[nd], ci[1]); red_add(&POTP[nd], ci[2]); red_add(&P[nd], ci[3]);
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s)
+            if (s < n_strains) {
+                red_add(&Ebs[(int64_t)nd * n_strains + s], ci[4 + s]);
+                red_add(&Ibs[(int64_t)nd * n_strains + s], ci[4 + LPK_MAX_STRAINS + s]);
+            }
+    };
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+        uint32_t w[4], pp[4], pz[4];
+        int64_t base[4];
+        int valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            base[j] = quad_base(tile, j, lane);
+            valid[j] = quad_valid(base[j], n);
+            w[j] = valid[j] ? load_b4(state, base[j], valid[j]) : 0xFFFFFFFFu;
+            pp[j] = valid[j] ? load_b4(pot_par, base[j], valid[j], 0) : 0u;
+            pz[j] = valid[j] ? load_b4(paralyzed, base[j], valid[j], 0) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((w[j] & 0x80808080u) == 0x80808080u) continue;
+            int nd[4];
+            load_s4(node_id, base[j], valid[j], nd);
+            const bool anyEI = any_byte_eq(w[j], 1u) || any_byte_eq(w[j], 2u);
+            const uint32_t sw = anyEI ? load_b4(strain, base[j], valid[j], 0) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int8_t s = byte_of(w[j], k);
+                if (s < 0) continue;
+                acc.select(nd[k], flush);
+                acc.ci[0] += (s == 0);
+                acc.ci[1] += (s == 3);
+                acc.ci[2] += (byte_of(pp[j], k) == 1);
+                acc.ci[3] += (byte_of(pz[j], k) == 1);
+                if (s == 1 || s == 2) {
+                    const int stn = byte_of(sw, k);
+#pragma unroll
+                    for (int q = 0; q < LPK_MAX_STRAINS; ++q) {
+                        acc.ci[4 + q] += (s == 1 && q == stn);
+                        acc.ci[4 + LPK_MAX_STRAINS + q] += (s == 2 && q == stn);
+                    }
+                }
+            }
+        }
+    }
+    acc.finish_warp(flush);
+}
+__global__ void k_sum_strains(int n_nodes, int n_strains, const int32_t *__restrict__ Ebs, const int32_t *__restrict__ Ibs,
+                              int32_t *E, int32_t *I) {
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= n_nodes) return;
+    int e = 0, i = 0;
+    for (int s = 0; s < n_strains; ++s) { e += Ebs[(int64_t)nd * n_strains + s]; i += Ibs[(int64_t)nd * n_strains + s]; }
+    E[nd] = e; I[nd] = i;
+}
+extern "C" int lpk_count_seirp(const int16_t *node_id, const int8_t *disease_state, const int8_t *strain,
+                               const int8_t *potentially_paralyzed, const int8_t *paralyzed, int32_t n_nodes,
+                               int32_t n_strains, int64_t n_people, int32_t *S, int32_t *E, int32_t *I, int32_t *R,
+                               int32_t *E_by_strain, int32_t *I_by_strain, int32_t *POTP, int32_t *P, void *stream) {
+    REQUIRE(n_nodes > 0 && n_people >= 0, "count_seirp sizes");
+    REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "count_seirp n_strains");
+    REQUIRE(node_id && disease_state && strain && potentially_paralyzed && paralyzed && S && E && I && R && E_by_strain &&
+                I_by_strain && POTP && P, "count_seirp null pointer");
+    REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(strain, 4) && ALIGNED(potentially_paralyzed, 4) && ALIGNED(paralyzed, 4) &&
+                ALIGNED(node_id, 8), "count_seirp alignment");
+    cudaStream_t st = as_stream(stream);
+    const size_t nb = sizeof(int32_t) * n_nodes;
+    CUDA_TRY(cudaMemsetAsync(S, 0, nb, st), "count_seirp memset");
+    CUDA_TRY(cudaMemsetAsync(R, 0, nb, st), "count_seirp memset");
+    CUDA_TRY(cudaMemsetAsync(POTP, 0, nb, st), "count_seirp memset");
+    CUDA_TRY(cudaMemsetAsync(P, 0, nb, st), "count_seirp memset");
+    CUDA_TRY(cudaMemsetAsync(E_by_strain, 0, nb * n_strains, st), "count_seirp memset");
+    CUDA_TRY(cudaMemsetAsync(I_by_strain, 0, nb * n_strains, st), "count_seirp memset");
+    if (n_people > 0) {
+        k_count_seirp<<<agent_grid(n_people, 8), LPK_BLOCK, 0, st>>>(n_people, n_strains, node_id, disease_state, strain,
+                                                                     potentially_paralyzed, paralyzed, S, R, E_by_strain,
+                                                                     I_by_strain, POTP, P);
+        CUDA_TRY(cudaGetLastError(), "lpk_count_seirp");
+    }
+    k_sum_strains<<<(n_nodes + 127) / 128, 128, 0, st>>>(n_nodes, n_strains, E_by_strain, I_by_strain, E, I);
+    CUDA_TRY(cudaGetLastError(), "lpk_count_seirp sum");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ T3 tx_infect (per-agent Bernoulli)
+__device__ __forceinline__ bool expose_hit(float p, uint32_t x) {
+    if (!(p > 0.f)) return false;
+    if (p >= 1.f) return true;
+    return x < (uint32_t)__float2uint_rz(p * 4294967296.0f);
+}
+
+__global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strains, const int16_t *__restrict__ node_id,
+                                                          int8_t *strain, int8_t *__restrict__ state,
+                                                          const float *__restrict__ risk, const float *__restrict__ q,
+                                                          const double *__restrict__ strain_cdf, int32_t *n_new,
+                                                          DevRng rng) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileRange tr = block_tiles(n);
+    NodeAcc<LPK_MAX_STRAINS, 0> acc;
+    acc.init();
+    auto flush = [&](int nd, const int *ci, const long long *) {
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s)
+            if (s < n_strains) red_add(&n_new[(int64_t)nd * n_strains + s], ci[s]);
+    };
+    for (int64_t tile = tr.lo + warp; tile < tr.hi; tile += LPK_WARPS) {
+        uint32_t w[4];
+        int64_t base[4];
+        int valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            base[j] = quad_base(tile, j, lane);
+            valid[j] = quad_valid(base[j], n);
+            w[j] = valid[j] ? load_b4(state, base[j], valid[j]) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!any_byte_eq(w[j], 0u)) continue;  // no susceptible in the quad
+            int nd[4];
+            load_s4(node_id, base[j], valid[j], nd);
+            float qn[4];
+            bool live = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                qn[k] = (byte_of(w[j], k) == 0) ? __ldg(&q[nd[k]]) : 0.f;
+                live |= qn[k] > 0.f;
+            }
+            if (!live) continue;  // no force of infection on this quad's nodes: risk is never read
+            float rk[4];
+            load_f4(risk, base[j], valid[j], rk);
+            uint32_t x[4];
+            if (rng.x) { for (int k = 0; k < 4; ++k) x[k] = (k < valid[j]) ? rng.x[base[j] + k] : 0u; }
+            else philox_agent(rng.seed, (uint64_t)base[j] >> 2, rng.tick, LPK_STAGE_EXPOSE, x);
+            uint32_t nw = w[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(qn[k] > 0.f)) continue;
+                if (!expose_hit(__fmul_rn(rk[k], qn[k]), x[k])) continue;
+                const int64_t i = base[j] + k;
+                double r;
+                if (rng.u2) r = rng.u2[i];
+                else { uint32_t y[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_STRAIN, y); r = u53(y[0], y[1]); }
+                int assigned = 0;
+                for (int s = 0; s < n_strains; ++s)
+                    if (r < strain_cdf[(int64_t)nd[k] * n_strains + s]) { assigned = s; break; }
+                nw = set_byte(nw, k, 1);
+                strain[i] = (int8_t)assigned;
+                acc.select(nd[k], flush);
+#pragma unroll
+                for (int s = 0; s < LPK_MAX_STRAINS; ++s) acc.ci[s] += (s == assigned);
+            }
+            if (nw != w[j]) store_b4(state, base[j], valid[j], nw);
+        }
+    }
+    acc.finish_warp(flush);
+}
+extern "C" int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_strains, const int16_t *node_ids,
+                             int8_t *strain, int8_t *disease_state, const float *risks, const float *q,
+                             const double *strain_cdf, int32_t *n_new, const lpk_rng *rng, void *stream) {
+    REQUIRE(num_nodes > 0 && num_people >= 0, "tx_infect sizes");
+    REQUIRE(num_strains >= 1 && num_strains <= LPK_MAX_STRAINS, "tx_infect n_strains");
+    REQUIRE(node_ids && strain && disease_state && risks && q && strain_cdf && n_new, "tx_infect null pointer");
+    REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(node_ids, 8) && ALIGNED(risks, 16), "tx_infect alignment");
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemsetAsync(n_new, 0, sizeof(int32_t) * num_nodes * num_strains, st), "tx_infect memset");
+    if (num_people == 0) return LPK_OK;
+    k_tx_infect<<<agent_grid(num_people, 8), LPK_BLOCK, 0, st>>>(num_people, num_strains, node_ids, strain, disease_state,
+                                                                 risks, q, strain_cdf, n_new, dev_rng(rng));
+    CUDA_TRY(cudaGetLastError(), "lpk_tx_infect");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ T2 node-level math
+// rowsum[i] = sum_j W[i, j]: one warp per row, coalesced.
+__global__ void k_row_sums(int n, const double *__restrict__ W, double *__restrict__ rowsum) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    double s = 0.0;
+    for (int j = threadIdx.x & 31; j < n; j += 32) s += W[(int64_t)row * n + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(LPK_FULL, s, o);
+    if ((threadIdx.x & 31) == 0) rowsum[row] = s;
+}
+
+__device__ double node_uniform(uint64_t seed, uint32_t node, uint32_t k, uint32_t tick, int pair) {
+    uint32_t x[4];
+    philox4x32_10(node, k, tick, LPK_STAGE_NODE, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    return pair ? u53(x[2], x[3]) : u53(x[0], x[1]);
+}
+// zero-inflated gamma multiplier of an importation-only node (see lpk.h T2); Marsaglia-Tsang, r >= 1
+__device__ double importation_multiplier(uint64_t seed, uint32_t node, uint32_t tick, double zi, double r) {
+    if (zi >= 1.0) return 0.0;
+    if (node_uniform(seed, node, 0, tick, 0) < zi) return 0.0;
+    const double d = r - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    uint32_t k = 1;
+    for (;;) {
+        const double u1 = node_uniform(seed, node, k, tick, 0), u2 = node_uniform(seed, node, k, tick, 1);
+        const double x = sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.14159265358979323846 * u2);
+        ++k;
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = node_uniform(seed, node, k, tick, 0);
+        ++k;
+        if (log(1.0 - u) < 0.5 * x * x + d - d * v + d * log(v)) return (d * v) / r / (1.0 - zi);
+    }
+}
+
+// block = 32 destination nodes x 8 source slices
+__global__ void __launch_bounds__(256) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
+                                                       const int64_t *__restrict__ exposure_fx,
+                                                       const double *__restrict__ W, const double *__restrict__ rowsum,
+                                                       double season, const double *__restrict__ r0_scalars,
+                                                       const int32_t *__restrict__ alive, double zi, double disp_r,
+                                                       float *q, double *strain_cdf, double *prob, double *expected,
+                                                       uint64_t seed, uint32_t tick) {
+    __shared__ double part[8][LPK_MAX_STRAINS][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
+    if (j < n) {
+        for (int i = ty; i < n; i += 8) {
+            long long b[LPK_MAX_STRAINS];
+            bool nz = false;
+#pragma unroll
+            for (int s = 0; s < LPK_MAX_STRAINS; ++s) { b[s] = (s < n_strains) ? beta_fx[(int64_t)i * n_strains + s] : 0; nz |= (b[s] != 0); }
+            if (!nz) continue;  // warp-uniform: rows without infectivity contribute nothing
+            const double w = W[(int64_t)i * n + j];
+#pragma unroll
+            for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += ((double)b[s] / LPK_FX_SCALE) * w;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[ty][s][tx] = in[s];
+    __syncthreads();
+    if (ty != 0 || j >= n) return;
+    double P = 0.0, local = 0.0, p[LPK_MAX_STRAINS];
+    const double popn = fmax((double)alive[j], 1.0);
+    for (int s = 0; s < n_strains; ++s) {
+        double inc = 0.0;
+        for (int y = 0; y < 8; ++y) inc += part[y][s][tx];
+        const double pre = (double)beta_fx[(int64_t)j * n_strains + s] / LPK_FX_SCALE;
+        local += pre;
+        double b = pre + inc - pre * rowsum[j];
+        b = b * season * r0_scalars[j];
+        const double rate = b / popn;
+        p[s] = fmax(1.0 - exp(-rate), 0.0);
+        prob[(int64_t)j * n_strains + s] = p[s];
+        P += p[s];
+    }
+    double run = 0.0;
+    for (int s = 0; s < n_strains; ++s) {
+        run += (P > 0.0) ? p[s] / P : 0.0;
+        strain_cdf[(int64_t)j * n_strains + s] = run;
+    }
+    expected[j] = ((double)exposure_fx[j] / LPK_FX_SCALE) * P;
+    double g = 1.0;
+    if (local == 0.0 && P > 0.0) g = importation_multiplier(seed, (uint32_t)j, tick, zi, disp_r);
+    q[j] = (float)(P * g);
+}
+
+extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
+                                const double *network, double beta_seasonality, const double *r0_scalars,
+                                const int32_t *alive_counts, double zero_inflation, double dispersion, float *q,
+                                double *strain_cdf, double *prob, double *expected, double *rowsum_ws, const lpk_rng *rng,
+                                void *stream) {
+    REQUIRE(num_nodes > 0, "tx_node_math sizes");
+    REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "tx_node_math n_strains");
+    REQUIRE(beta_fx && exposure_fx && network && r0_scalars && alive_counts && q && strain_cdf && prob && expected &&
+                rowsum_ws, "tx_node_math null pointer");
+    cudaStream_t st = as_stream(stream);
+    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum_ws);
+    CUDA_TRY(cudaGetLastError(), "lpk_tx_node_math rowsums");
+    double r = nearbyint(dispersion);
+    if (r < 1.0) r = 1.0;
+    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum_ws,
+                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, q,
+                                                          strain_cdf, prob, expected, rng ? rng->seed : 0,
+                                                          rng ? rng->tick : 0);
+    CUDA_TRY(cudaGetLastError(), "lpk_tx_node_math");
+    return LPK_OK;
+}

@@ -182,8 +182,8 @@ void orc_fast_ri(int64_t step_size, const int16_t *node_id, int8_t *state, int8_
         if (s < 0) continue;
         if (missed[i] == 1) continue;
         int32_t node = node_id[i];
-        int16_t timer = (int16_t)(ri_timer[i] - step_size);
-        ri_timer[i] = timer;
+        int64_t timer = (int64_t)ri_timer[i] - step_size; /* eligibility on the unwrapped value (numba int64) */
+        ri_timer[i] = (int16_t)timer;
         int eligible = 0;
         if (sim_t == step_size) eligible = (timer <= 0 && timer >= -step_size);
         else if (sim_t > step_size) eligible = (timer <= 0 && timer > -step_size);
