@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- agent-days/sec of the per-tick agent update on the Nigeria-774 shape (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--agents A] [--nodes M]
+
+A "step" is one simulated day over the whole population: every component's step() in the
+reference's run order (deaths/births every 7th tick, disease state, RI every 14th, SIA on campaign
+days, transmission) followed by the census, exactly what ``SEIR_ABM.run()`` does per tick.
+
+* value    whole-job agent-days/s with the agent table already resident in HBM (CUDA events, max over ranks)
+* e2e      the same K ticks through ``SEIR_ABM`` from HOST (pinned) columns: H2D of every agent column
+           and results array, the ticks, and D2H of everything back inside the timed region
+* roofline the dominant kernel's algorithmic bytes / its mean CUDA-event time inside the timed region
+* cpu_baseline  the CPU oracle (C + OpenMP restatement of the reference's numba kernels, "port") timed on
+           this box's host cores on a bounded sample (10 M agents) of the same workload
+
+N > 1 (torchrun, one rank per GPU): the population is sharded by node (contiguous node blocks, weak scaling:
+every rank holds --agents agents); the only per-tick exchange is the nodes x strains infectivity tally.
+
+--impl reference: the CPU leg alone, with every host thread, K ticks per run.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HBM_FALLBACK_GBS = 6650.0
+ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1
+
+# algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
+# (f_S = 0.93, f_E = f_I = 0.01 synthetic mix; derivations in DESIGN.md section 4)
+KERNEL_BYTES = {
+    "tx_step_prep": 1 + 2 + 4 * 0.93 + 5 * 0.01,          # state, node_id, risk (S), infectivity + strain (I)
+    "tx_infect": 1 + 2 + 4 * 0.93,                         # state, node_id, risk (S)
+    "count_SEIRP": 1 + 2 + 1 + 1 + 0.02,                   # state, node_id, potentially_paralyzed, paralyzed, strain (E/I)
+    "disease_state_step": 1 + 2 * 0.01 + 8 * 0.01,         # state; etimer r/w (E); itimer r/w, strain, ptimer r/w, pp, ipv (I)
+    "get_deaths": 1 + 4,                                   # state, date_of_death
+    "fast_ri": 1 + 1 + 2 + 2,                              # state, missed, ri_timer r/w
+    "fast_sia": 1 + 1 + 4 + 2 * 0.3,                       # state, missed, dob, node_id (eligible quads)
+}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:  # noqa: BLE001 - clocks are diagnostics
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ workload
+def sia_schedule(start, n_nodes, years, rng):
+    """~8 campaigns per year, under-5s, 30-100 % of nodes, mOPV2 then nOPV2 after year 3 (Nigeria)."""
+    import datetime as dt
+
+    events = []
+    for y in range(years + 1):
+        for k in range(8):
+            day = y * 365 + 20 + k * 44
+            frac = rng.uniform(0.3, 1.0)
+            nodes = np.sort(rng.choice(n_nodes, size=max(1, int(frac * n_nodes)), replace=False)).tolist()
+            events.append({"date": start + dt.timedelta(days=day), "nodes": nodes, "age_range": (0, 5 * 365),
+                           "vaccinetype": "mOPV2" if y < 3 else "nOPV2"})
+    return events
+
+
+def build_pars(lp, sizes, dur, seed, rng):
+    import datetime as dt
+
+    n = len(sizes)
+    xy = rng.uniform(0, 1000.0, (n, 2))  # synthetic node coordinates, km
+    dist = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+    dist[dist == 0] = 1.0
+    np.fill_diagonal(dist, 0.0)
+    start = dt.date(2017, 1, 1)
+    return lp.PropertySet({
+        "seed": seed, "start_date": start, "dur": dur, "init_pop": np.asarray(sizes), "cbr": np.full(n, 37.0),
+        "r0": 10, "r0_scalars": rng.uniform(0.5, 1.5, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
+        "distances": dist, "migration_method": "gravity", "gravity_k": 0.5, "gravity_k_exponent": -1.0, "gravity_c": 1.5,
+        "max_migr_frac": 0.1, "vx_prob_ri": rng.uniform(0.3, 0.8, n), "vx_prob_ipv": rng.uniform(0.3, 0.8, n),
+        "vx_prob_sia": rng.uniform(0.4, 0.9, n).tolist(), "sia_schedule": sia_schedule(start, n, dur // 365 + 1, rng),
+        "stop_if_no_cases": False, "verbose": 0, "node_seeding_zero_inflation": 0.0, "node_seeding_dispersion": 1000,
+    })
+
+
+def build_sim(lp, n_agents, n_nodes, dur, seed, device):
+    """Synthetic population generated in HBM, mirrored into pinned host columns (the reference-facing LaserFrame),
+    wrapped by SEIR_ABM.init_from_file + Component.init_from_file (the reference's route for a pre-built table)."""
+    import torch
+
+    from laser_polio_b200 import synth
+
+    births_room = 1.0 + 37.0 / 1000.0 * (dur + 100) / 365.0 * 1.15
+    capacity = int(n_agents * births_room) + 4096
+    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed, capacity=capacity, device=device)
+    people = lp.LaserFrame(capacity=capacity, initial_count=n_agents)
+    for name, dtype in synth.COLUMNS.items():
+        people.add_scalar_property(name, dtype=dtype, default=synth.COLUMN_DEFAULTS[name])
+        torch.from_numpy(getattr(people, name)).copy_(pop[name])
+    sizes = pop["node_sizes"]
+    del pop
+    torch.cuda.empty_cache()
+    rng = np.random.default_rng(seed + 1)
+    pars = build_pars(lp, sizes, dur, seed, rng)
+    sim = lp.SEIR_ABM.init_from_file(people, pars)
+    sim.verbose = 0
+    sim.nodes = np.arange(n_nodes)
+    sim._components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    sim.instances = [c.init_from_file(sim) for c in sim._components]
+    return sim
+
+
+# ------------------------------------------------------------------------------------------ CPU leg (oracle "port")
+def cpu_tick_loop(n_agents, n_nodes, ticks, warm, seed=5):
+    """The reference's per-tick call sequence on the CPU oracle; returns (agent_days_per_s, threads, per-stage seconds)."""
+    from laser_polio_b200 import synth
+    from oracle import oracle as orc
+
+    p = synth.synth_population(n_agents, n_nodes, seed=seed)
+    n, ns = n_agents, 3
+    srs = np.array([1.0, 0.25, 0.125])
+    rng = np.random.default_rng(seed)
+    W = rng.random((n_nodes, n_nodes)) * (0.1 / n_nodes)
+    np.fill_diagonal(W, 0.0)
+    r0s = rng.uniform(0.5, 1.5, n_nodes)
+    pr, pi = rng.uniform(0.3, 0.8, n_nodes), rng.uniform(0.3, 0.8, n_nodes)
+    vx = rng.uniform(0.4, 0.9, n_nodes).astype(np.float32)
+    targeted = (rng.random(n_nodes) < 0.6).astype(np.uint8)
+    pop = np.bincount(p["node_id"][:n], minlength=n_nodes).astype(np.int32)
+    si, sp = np.zeros(n, np.int32), np.zeros(n, np.float32)
+    rs = np.random.RandomState(seed)
+    stage = {}
+
+    def timed(name, fn):
+        t0 = time.perf_counter()
+        out = fn()
+        stage[name] = stage.get(name, 0.0) + (time.perf_counter() - t0 if measuring else 0.0)
+        return out
+
+    t_total, measuring = 0.0, False
+    first = 14 - warm  # so that the timed window contains a vital-dynamics tick and an RI tick (t = 14)
+    for k in range(warm + ticks):
+        t = first + k
+        measuring = k >= warm
+        t0 = time.perf_counter()
+        if t % 7 == 0:
+            dying = np.zeros(n_nodes, np.int32)
+            timed("get_deaths", lambda: orc.get_deaths(n_nodes, n, p["disease_state"], p["node_id"], p["date_of_death"], t, dying))
+        pot, par = np.zeros(n_nodes, np.int32), np.zeros(n_nodes, np.int32)
+        timed("disease_state_step", lambda: orc.disease_state_step(
+            p["node_id"], n_nodes, p["disease_state"], p["strain"], n, p["exposure_timer"], p["infection_timer"],
+            p["potentially_paralyzed"], p["paralyzed"], p["ipv_protected"], p["paralysis_timer"], 1 / 2000, pot, par, seed=seed, tick=t))
+        if t % 14 == 0:
+            c = [np.zeros(n_nodes, np.int32) for _ in range(3)]
+            timed("fast_ri", lambda: orc.fast_ri(14, p["node_id"], p["disease_state"], p["strain"], p["ipv_protected"], p["ri_timer"],
+                                                 t, pr, pi, n, c[0], c[1], c[2], p["chronically_missed"], 1, seed=seed, tick=t))
+        if t % 44 == 20 % 44 or k == warm + 1:  # ~8 campaigns / year; make sure one lands in a short window
+            v, pr_ = np.zeros(n_nodes, np.int32), np.zeros(n_nodes, np.int32)
+            timed("fast_sia", lambda: orc.fast_sia(p["node_id"], p["disease_state"], p["strain"], p["date_of_birth"], t, vx, 0.56, n,
+                                                   targeted, 0, 5 * 365, v, pr_, p["chronically_missed"], 2, seed=seed, tick=t))
+        beta, expo, sus, _, _ = timed("tx_step_prep", lambda: orc.tx_step_prep(
+            n_nodes, n, ns, p["strain"], srs, p["disease_state"], p["node_id"], p["daily_infectivity"], p["acq_risk_multiplier"], mode="f32"))
+        beta_pre, prob = timed("node_math", lambda: orc.tx_foi(beta.astype(np.float32), W, 1.05, r0s, pop))
+        want, _ = timed("node_math", lambda: orc.tx_draw_counts_ref(beta_pre, prob, expo, 0.0, 1000, rs=rs))
+        timed("tx_infect", lambda: orc.tx_infect_ref(n_nodes, n, ns, sus, p["node_id"], p["strain"], p["disease_state"], si, sp,
+                                                      p["acq_risk_multiplier"], prob, want, seed=seed, tick=t))
+        timed("count_SEIRP", lambda: orc.count_SEIRP(p["node_id"], p["disease_state"], p["strain"], p["potentially_paralyzed"],
+                                                      p["paralyzed"], n_nodes, ns, n))
+        if measuring:
+            t_total += time.perf_counter() - t0
+    return n * ticks / t_total, orc.num_threads(), stage, t_total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(args.agents or 220_000_000, args.cpu_agents)
+    nodes = args.nodes
+    value, threads, stage, secs = cpu_tick_loop(n, nodes, args.steps, max(1, min(args.warmup, 2)))
+    sample = f"{n} agents x {nodes} nodes (bounded sample of the {args.agents or 220_000_000}-agent workload), {args.steps} ticks"
+    line = {
+        "impl": "reference", "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8 state machine + f32/f64 tallies", "data": "synthetic",
+        "config": {"workload": f"nigeria-774 shape: {args.agents or 220_000_000} agents, {nodes} nodes", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "agent-days/s", "cores": threads, "kind": "port", "sample": sample,
+                         "stage_seconds": {k: round(v, 4) for k, v in stage.items()}},
+        "e2e": {"value": value, "unit": "agent-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU leg
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    import laser_polio_b200 as lp
+    from laser_polio_b200 import kernels as K
+
+    n_agents = args.agents or 220_000_000
+    n_nodes = args.nodes
+    K_, W_ = args.steps, max(args.warmup, 3)
+    dur = 2 * (K_ + W_) + 40
+    sim = build_sim(lp, n_agents, n_nodes, dur, seed=20261017 + rank, device=f"cuda:{local}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    sim.to_device()
+    live0 = int(sim.people.count)
+    for _ in range(W_):
+        sim.step_tick(sim.t)
+    K.STATS.reset()
+    K.STATS.timing = True
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K_):
+        sim.step_tick(sim.t)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    kstats = K.STATS.summary()
+    launches = K.STATS.launches
+    K.STATS.timing = False
+    sim.to_host()
+
+    # ---- end to end through the component API from host columns (H2D + ticks + D2H inside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    sim.to_device()
+    for _ in range(K_):
+        sim.step_tick(sim.t)
+    sim.to_host()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    h2d, d2h = sim.io_bytes
+
+    if rank != 0:
+        return
+    agents_total = live0 * world
+    value = agents_total * K_ / (ms / 1e3)
+    peak, peak_src = measured_peak()
+    top = max(kstats, key=lambda k: kstats[k][0] * kstats[k][1])
+    calls, mean_ms = kstats[top]
+    algo = KERNEL_BYTES[top] * live0
+    achieved = algo / (mean_ms / 1e3) / 1e9
+    kernel_share = {k: round(c * m / ms, 4) for k, (c, m) in kstats.items()}
+    cpu_n = min(n_agents, args.cpu_agents)
+    cpu_value, threads, stage, cpu_secs = cpu_tick_loop(cpu_n, n_nodes, args.cpu_ticks, 1)
+    line = {
+        "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": world, "steps": K_, "warmup": W_,
+        "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 state machine + int64 fixed-point tallies + f64 node math", "data": "synthetic",
+        "config": {"workload": f"nigeria-774 shape (examples/demo_nigeria.py): {n_agents} agents/GPU, {n_nodes} nodes, 3 strains, "
+                               "VD every 7, RI every 14, ~8 SIA/yr, daily transmission + census",
+                   "agents_per_gpu": n_agents, "nodes": n_nodes, "l2_policy": "inputs (>=1 GB per column) far larger than the 126 MB L2",
+                   "parallelism": f"node-sharded x{world}" if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
+                     "tick_frac_of_14B_roofline": (ALGO_BYTES_PER_AGENT_TICK * value / world) / (peak * 1e9),
+                     "kernel_share_of_step": kernel_share},
+        "cpu_baseline": {"value": cpu_value, "unit": "agent-days/s", "cores": threads, "kind": "port",
+                         "sample": f"{cpu_n} agents x {n_nodes} nodes, {args.cpu_ticks} ticks ({cpu_secs:.1f} s)",
+                         "stage_seconds": {k: round(v, 4) for k, v in stage.items()}},
+        "e2e": {"value": agents_total * K_ / e2e_s, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
+                "seconds": e2e_s, "note": "SEIR_ABM.to_device() + K step_tick() + to_host() from pinned host columns"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=28)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--agents", type=int, default=0, help="agents per GPU (default: 220M, the Nigeria config)")
+    ap.add_argument("--nodes", type=int, default=774)
+    ap.add_argument("--cpu-agents", type=int, default=10_000_000)
+    ap.add_argument("--cpu-ticks", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

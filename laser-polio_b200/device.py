@@ -1,0 +1,109 @@
+"""Device residency of the agent table and the results table.
+
+``sim.people`` (a :class:`core.LaserFrame`) keeps the reference's host-visible
+numpy columns -- tests and user scripts mutate them between construction and
+``run()`` and read them back afterwards by agent index.
+``DeviceState`` is the HBM twin those columns are copied into at ``run()``
+entry and copied back from at exit: one torch CUDA buffer per column, length
+``capacity``, reference dtypes, agents in the reference's order (initial
+population node-contiguous, newborn cohorts appended node-major), so a host
+index and a device slot are the same number and no permutation is needed.
+
+The ``[nt, nodes(, strains)]`` int32 result arrays live on the device for the
+whole run (kernels write row ``t`` directly) and come back in one bulk copy.
+
+PyTorch owns every allocation; liblpk only borrows raw pointers.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# results that are produced on the host (birth/death bookkeeping needs host-side draws) and never mirrored
+HOST_ONLY_RESULTS = ("pop", "births", "deaths", "network")
+
+
+def _to_dev(arr: np.ndarray, device) -> torch.Tensor:
+    t = torch.from_numpy(arr)
+    return t.to(device, non_blocking=t.is_pinned())
+
+
+class DeviceState:
+    def __init__(self, sim, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("laser_polio_b200 runs its per-tick path on a CUDA device; none is available (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.sim = sim
+        self.n_nodes = len(sim.nodes)
+        self.n_strains = len(sim.pars.strain_ids)
+        self.cols: dict[str, torch.Tensor] = {}
+        self.res: dict[str, torch.Tensor] = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.upload()
+
+    # ------------------------------------------------------------------ transfers
+    def upload(self):
+        people, results = self.sim.people, self.sim.results
+        for name, col in people.columns().items():
+            self.cols[name] = _to_dev(col, self.device)
+            self.h2d_bytes += col.nbytes
+        for name, arr in results.__dict__.items():
+            if isinstance(arr, np.ndarray) and arr.dtype == np.int32 and arr.ndim >= 2 and name not in HOST_ONLY_RESULTS:
+                self.res[name] = _to_dev(arr, self.device)
+                self.h2d_bytes += arr.nbytes
+        n, ns, dev = self.n_nodes, self.n_strains, self.device
+        self.pop_cur = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._pop_host = None
+        self.scratch_i32 = [torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(4)]
+        self.tally = (torch.zeros((n, ns), dtype=torch.int64, device=dev), torch.zeros(n, dtype=torch.int64, device=dev),
+                      torch.zeros(n, dtype=torch.int64, device=dev))
+        self.node_out = (torch.zeros(n, dtype=torch.float32, device=dev), torch.zeros((n, ns), dtype=torch.float64, device=dev),
+                         torch.zeros((n, ns), dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev),
+                         torch.zeros(n, dtype=torch.float64, device=dev))
+        self.n_new = torch.zeros((n, ns), dtype=torch.int32, device=dev)
+        mk = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
+        self.census = (mk(n), mk(n), mk(n), mk(n), mk(n, ns), mk(n, ns), mk(n), mk(n))
+        self._net_src = None
+        self.network = None
+
+    def download(self):
+        """Bulk D2H of every agent column and every device-resident results array, in place."""
+        people, results = self.sim.people, self.sim.results
+        torch.cuda.current_stream().synchronize()
+        for name, t in self.cols.items():
+            host = getattr(people, name)
+            torch.from_numpy(host).copy_(t, non_blocking=False)
+            self.d2h_bytes += host.nbytes
+        for name, t in self.res.items():
+            host = getattr(results, name)
+            torch.from_numpy(host).copy_(t, non_blocking=False)
+            self.d2h_bytes += host.nbytes
+
+    def push_rows(self, name: str, start: int, end: int):
+        """H2D of a slice of one agent column (newborn cohort written on the host)."""
+        host = getattr(self.sim.people, name)[start:end]
+        self.cols[name][start:end].copy_(torch.from_numpy(host), non_blocking=False)
+        self.h2d_bytes += host.nbytes
+
+    def pop_tensor(self, row: np.ndarray) -> torch.Tensor:
+        """Device copy of ``results.pop[t]``; re-uploaded only when the host row changed (births / deaths ticks)."""
+        row = np.ascontiguousarray(row, dtype=np.int32)
+        if self._pop_host is None or not np.array_equal(self._pop_host, row):
+            self._pop_host = row.copy()
+            self.pop_cur.copy_(torch.from_numpy(self._pop_host))
+            self.h2d_bytes += row.nbytes
+        return self.pop_cur
+
+    def network_tensor(self, host_network) -> torch.Tensor:
+        """Device copy of ``tx.network`` (float64, row-major); re-uploaded when the host object is replaced
+        (the reference re-reads the attribute every tick, model.py:1335, and tests overwrite it)."""
+        if self._net_src is not host_network:
+            arr = np.ascontiguousarray(np.asarray(host_network, dtype=np.float64))
+            if arr.shape != (self.n_nodes, self.n_nodes):
+                raise ValueError(f"network must be {self.n_nodes}x{self.n_nodes}, got {arr.shape}")
+            self.network = torch.from_numpy(arr).to(self.device)
+            self._net_src = host_network
+            self.h2d_bytes += arr.nbytes
+        return self.network

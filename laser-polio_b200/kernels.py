@@ -136,3 +136,55 @@ def count_SEIRP(node_id, disease_state, strain, potentially_paralyzed, paralyzed
         stream_handle(),
     ), "lpk_count_seirp")
     return out
+
+
+# ----------------------------------------------------------------------------- launch accounting / per-kernel timing
+class LaunchStats:
+    """Counts liblpk kernel launches and, when ``timing`` is on, brackets every call with CUDA events on the
+    launching stream so bench.py can report each kernel's average device time inside the timed region."""
+
+    KERNELS_PER_CALL = {"get_deaths": 1, "disease_state_step": 1, "fast_ri": 1, "fast_sia": 1, "tx_step_prep": 1,
+                        "tx_node_math": 2, "tx_infect": 1, "count_SEIRP": 2}
+
+    def __init__(self):
+        self.reset()
+        self.timing = False
+
+    def reset(self):
+        self.launches = 0
+        self.calls = {}
+        self.events = {}
+
+    def summary(self):
+        """{name: (calls, mean_ms)}; synchronises the device."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1)) for k, v in self.events.items()}
+
+
+STATS = LaunchStats()
+
+
+def _instrument(fn):
+    import functools
+
+    name = fn.__name__
+    per_call = LaunchStats.KERNELS_PER_CALL[name]
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        STATS.launches += per_call
+        STATS.calls[name] = STATS.calls.get(name, 0) + 1
+        if not STATS.timing:
+            return fn(*a, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **kw)
+        e1.record()
+        STATS.events.setdefault(name, []).append((e0, e1))
+        return out
+
+    return wrapper
+
+
+for _name in LaunchStats.KERNELS_PER_CALL:
+    globals()[_name] = _instrument(globals()[_name])

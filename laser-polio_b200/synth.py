@@ -151,3 +151,85 @@ def synth_population(
     out = {"count": n, "capacity": capacity, "n_nodes": int(n_nodes), "n_strains": int(n_strains), "node_sizes": sizes}
     out.update(cols)
     return out
+
+
+def synth_population_device(
+    n_agents: int,
+    n_nodes: int,
+    seed: int = 0,
+    capacity: int | None = None,
+    device="cuda",
+    f_exposed: float = 0.01,
+    f_infected: float = 0.01,
+    f_recovered: float = 0.05,
+    f_dead: float = 0.0,
+    r0: float = 14.0,
+    n_strains: int = 3,
+    missed_frac: float = 0.1,
+    ipv_frac: float = 0.3,
+    max_age_days: int = 15 * 365,
+) -> dict:
+    """Same distributions as :func:`synth_population`, generated directly in HBM with torch (seeded).
+
+    Used for the full-size configurations (2.2e8 .. 1.3e9 agents) where a host-side build would
+    dominate the run.  Values differ from the numpy generator (different RNG); shapes, dtypes and
+    distributions are the same.  Returns {"count", "capacity", "n_nodes", "n_strains", "node_sizes", column: tensor}.
+    """
+    import torch
+
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    capacity = int(capacity or n_agents)
+    n = int(n_agents)
+    sizes = node_sizes(n, n_nodes, np.random.default_rng(seed))
+    tdt = {np.int8: torch.int8, np.uint8: torch.uint8, np.int16: torch.int16, np.int32: torch.int32, np.float32: torch.float32}
+    cols = {k: torch.full((capacity,), COLUMN_DEFAULTS[k], dtype=tdt[d], device=dev) for k, d in COLUMNS.items()}
+
+    cols["node_id"][:n] = torch.repeat_interleave(
+        torch.arange(n_nodes, dtype=torch.int16, device=dev), torch.from_numpy(sizes).to(dev), output_size=n
+    )
+    u = torch.rand(n, generator=g, device=dev)
+    e = np.cumsum([f_dead, f_exposed, f_infected, f_recovered])
+    state = torch.zeros(n, dtype=torch.int8, device=dev)
+    state[u < e[0]] = -1
+    state[(u >= e[0]) & (u < e[1])] = 1
+    state[(u >= e[1]) & (u < e[2])] = 2
+    state[(u >= e[2]) & (u < e[3])] = 3
+    cols["disease_state"][:n] = state
+    ei = (state == 1) | (state == 2)
+    cols["strain"][:n] = torch.where(ei, torch.randint(0, n_strains, (n,), generator=g, device=dev), 0).to(torch.int8)
+    del u
+
+    et = torch.poisson(torch.full((capacity,), 3.0, device=dev), generator=g).clamp_(0, 127).to(torch.int8)
+    it = (torch._standard_gamma(torch.full((capacity,), 4.51, device=dev), generator=g) * 5.32).clamp_(0, 127).to(torch.int8)
+    mu = math.log(12.5**2 / math.sqrt(3.5**2 + 12.5**2))
+    sg = math.sqrt(math.log(3.5**2 / 12.5**2 + 1))
+    raw = torch.empty(capacity, device=dev).log_normal_(mu, sg, generator=g) - et
+    cols["paralysis_timer"][:] = torch.minimum(raw.clamp_(min=0), it.to(torch.float32)).to(torch.int8)
+    prog = torch.rand(n, generator=g, device=dev)
+    cols["exposure_timer"][:] = et
+    cols["infection_timer"][:] = it
+    cols["exposure_timer"][:n] = torch.where(state == 1, (et[:n] * prog).to(torch.int8), et[:n])
+    cols["infection_timer"][:n] = torch.where(state == 2, (it[:n] * prog).to(torch.int8), it[:n])
+    del raw, prog, et, it
+
+    rho = 2.0 * math.sin(math.pi * 0.8 / 6.0)
+    z1 = torch.randn(capacity, generator=g, device=dev)
+    z2 = rho * z1 + math.sqrt(1 - rho * rho) * torch.randn(capacity, generator=g, device=dev)
+    cols["acq_risk_multiplier"][:] = torch.exp(math.log(1.0 / math.sqrt(5.0)) + math.sqrt(math.log(5.0)) * z1)
+    mean_inf = r0 / (4.51 * 5.32)
+    cols["daily_infectivity"][:] = -mean_inf * torch.log1p(-torch.special.ndtr(z2.double()).clamp_(0.0, 1 - 1e-16)).float()
+    del z1, z2
+
+    age = torch.randint(1, max_age_days, (n,), generator=g, device=dev, dtype=torch.int32)
+    cols["date_of_birth"][:n] = -age
+    cols["date_of_death"][:n] = torch.empty(n, device=dev).exponential_(1.0 / (50 * 365.0), generator=g).to(torch.int32) + 1
+    cols["ri_timer"][:n] = (-age + (42 + 56 * torch.rand(n, generator=g, device=dev)).to(torch.int32)).to(torch.int16)
+    cols["chronically_missed"][:n] = (torch.rand(n, generator=g, device=dev) < missed_frac).to(torch.uint8)
+    cols["ipv_protected"][:n] = (torch.rand(n, generator=g, device=dev) < ipv_frac).to(torch.int8)
+    del age
+
+    out = {"count": n, "capacity": capacity, "n_nodes": int(n_nodes), "n_strains": int(n_strains), "node_sizes": sizes}
+    out.update(cols)
+    return out

@@ -17,6 +17,7 @@ gate-1 runs, else Philox keyed on ``(seed, tick)``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -43,6 +44,9 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
+        # sleeping (not spinning) idle OpenMP workers: on shared / oversubscribed hosts spinning workers steal the
+        # cores the working threads need (measured here: 4x slower with the default active policy)
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         _lib = C.CDLL(str(build()))
         _lib.orc_uniform53.restype = C.c_double
         _lib.orc_uniform53.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]

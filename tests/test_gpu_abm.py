@@ -1,0 +1,333 @@
+"""The reference's own integration tests for the per-tick path, re-pointed at this implementation.
+
+Each test builds a tiny real sim through the component API exactly as the reference's tests do
+(``lp.SEIR_ABM(PropertySet{...})`` + ``sim.components = [...]`` + ``sim.run()``), mutates
+``sim.people.<col>`` as host numpy before the run and reads columns / ``sim.results`` back afterwards.
+The reference test each one mirrors is cited (paths relative to the reference checkout).
+"""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def lp():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import laser_polio_b200 as lp
+
+    return lp
+
+
+@pytest.fixture(scope="module")
+def pyramid(tmp_path_factory):
+    """Synthetic 5-year-bin age pyramid in the reference's CSV format (Age,M,F; last row '100+')."""
+    path = tmp_path_factory.mktemp("data") / "pyramid.csv"
+    rows = ["Age,M,F"]
+    for k in range(20):
+        n = int(17_000_000 * np.exp(-0.16 * k))
+        rows.append(f"{5 * k}-{5 * k + 4},{n},{int(n * 0.97)}")
+    rows.append("100+,300,500")
+    path.write_text("\n".join(rows) + "\n")
+    return str(path)
+
+
+def base_pars(lp, pyramid, **over):
+    p = {
+        "start_date": lp.date("2020-01-01"), "dur": 30, "init_pop": np.array([1000, 500]), "cbr": np.array([30, 25]),
+        "r0_scalars": np.array([0.5, 2.0]), "age_pyramid_path": pyramid, "init_immun": 0.0, "init_prev": 0.0,
+        "stop_if_no_cases": False, "verbose": 0, "seed": 7,
+    }
+    p.update(over)
+    return lp.PropertySet(p)
+
+
+# ---------------------------------------------------------------- tests/test_diseasestate_abm.py:64-122
+def test_progression_without_transmission(lp, pyramid):
+    sims = []
+    for dur in (1, 2, 3):
+        sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=dur, dur_exp=lp.constant(value=1), dur_inf=lp.constant(value=1)))
+        sim.components = [lp.DiseaseState_ABM]
+        sims.append(sim)
+    n = 1500
+    assert np.all(sims[0].people.exposure_timer[:n] == 1) and np.all(sims[0].people.infection_timer[:n] == 1)
+    for sim, expect in zip(sims, (1, 2, 3)):  # all E after 1 day, all I after 2, all R after 3
+        sim.people.disease_state[:n] = 1
+        sim.run()
+        for state in (0, 1, 2, 3):
+            assert np.sum(sim.people.disease_state == state) == (n if state == expect else 0), (expect, state)
+
+
+# ---------------------------------------------------------------- tests/test_diseasestate_abm.py:258-351
+def test_disease_timers_with_trans_explicit(lp, pyramid):
+    dur_exp, dur_inf = 2, 3
+    pars = base_pars(
+        lp, pyramid, start_date=lp.date("2018-01-01"), dur=30, init_pop=np.array([1, 1]), cbr=np.array([0, 0]),
+        r0_scalars=np.array([1.0, 1.0]), init_prev=1, dur_exp=lp.constant(value=dur_exp), dur_inf=lp.constant(value=dur_inf),
+        t_to_paralysis=lp.constant(value=10), p_paralysis=1 / 2000, r0=999, distances=np.array([[0, 1], [1, 0]]),
+        individual_heterogeneity=False, seed=124,
+    )
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM, lp.VitalDynamics_ABM]
+    state = sim.people.disease_state[: sim.people.count]
+    assert (np.sum(state == 0), np.sum(state == 1), np.sum(state == 2), np.sum(state == 3)) == (1, 0, 1, 0)
+    assert np.all(sim.people.exposure_timer == dur_exp) and np.all(sim.people.infection_timer == dur_inf)
+    assert np.all(sim.people.paralysis_timer <= sim.people.infection_timer)
+    sim.run()
+    n_s, n_e, n_i, n_r = (np.sum(getattr(sim.results, k), axis=1) for k in "SEIR")
+    n_npp = np.sum(sim.results.new_potentially_paralyzed, axis=1)
+    zeros = np.zeros(sim.pars.dur + 1, int)
+    s_exp = zeros.copy(); s_exp[0] = 1  # noqa: E702
+    e_exp = zeros.copy(); e_exp[1 : 2 + dur_exp] = 1  # noqa: E702
+    i_exp = zeros.copy(); i_exp[0 : dur_inf + 1] += 1; i_exp[2 + dur_exp : 2 + dur_exp + dur_inf] += 1  # noqa: E702
+    r_exp = zeros.copy(); r_exp[1 + dur_inf :] += 1; r_exp[2 + dur_exp + dur_inf :] += 1  # noqa: E702
+    p_exp = zeros.copy(); p_exp[1 + dur_inf] += 1; p_exp[2 + dur_exp + dur_inf] += 1  # noqa: E702
+    assert np.all(n_s == s_exp) and np.all(n_e == e_exp) and np.all(n_i == i_exp) and np.all(n_r == r_exp)
+    assert np.all(n_npp == p_exp)
+
+
+# ---------------------------------------------------------------- tests/test_diseasestate_abm.py:497-541
+def test_paralysis_progression_manual(lp, pyramid):
+    pars = base_pars(lp, pyramid, dur=3, init_pop=np.array([4, 4]), cbr=np.array([0]), r0_scalars=np.array([0.0]),
+                     dur_exp=lp.constant(value=1), dur_inf=lp.constant(value=1), p_paralysis=1.0)
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM]
+    sim.people.disease_state[:] = np.array([0, 0, 1, 1, 2, 2, 3, 3])
+    sim.people.paralysis_timer[:] = 1
+    protected = np.array([1, 3, 5, 7])
+    unprotected = np.setdiff1d(np.arange(sim.people.count), protected)
+    sim.people.ipv_protected[:] = 0
+    sim.people.ipv_protected[protected] = 1
+    sim.run()
+    assert np.sum(sim.people.potentially_paralyzed[protected] <= 0) == 4
+    assert np.sum(sim.people.potentially_paralyzed[unprotected] > 0) == 2
+    assert np.sum(sim.people.paralyzed[protected] <= 0) == 4
+    assert np.sum(sim.people.paralyzed[unprotected] > 0) == 2
+    assert np.sum(sim.results.potentially_paralyzed[-1]) == 2 and np.sum(sim.results.paralyzed[-1]) == 2
+
+
+# ---------------------------------------------------------------- tests/test_transmission.py:63-113
+def tx_sim(lp, pyramid, dur=1, r0=14, r0_scalars=None, init_prev=0.01, seed=None, init_immun=0.8):
+    pars = base_pars(
+        lp, pyramid, dur=dur, init_pop=np.array([10000, 10000]),
+        r0_scalars=np.array([0.5, 2.0], dtype=np.float32) if r0_scalars is None else r0_scalars, init_immun=init_immun,
+        init_prev=init_prev, r0=r0, seasonal_amplitude=0.0, distances=np.array([[0, 1], [1, 0]]), migration_method="gravity",
+        gravity_k=0.5, max_migr_frac=0.01, seed=seed if seed is not None else 0,
+    )
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM, lp.VitalDynamics_ABM]
+    return sim
+
+
+def test_trans_default_mean_matches_force_of_infection(lp, pyramid):
+    exposures, sim = [], None
+    for rep in range(10):
+        sim = tx_sim(lp, pyramid, seed=100 + rep)
+        sim.run()
+        exposures.append(sim.results.E[1:].sum())
+    assert np.all(np.array(exposures) > 0)
+    D = np.mean(sim.pars["dur_inf"](1000))
+    S, E, I, R = (getattr(sim.results, k)[0] for k in "SEIR")  # noqa: E741
+    N = S + E + I + R
+    p_inf = 1 - np.exp(-(sim.pars["r0"] / D) * np.array(sim.pars["r0_scalars"]) * I / N)
+    exp_E = np.sum(S * p_inf)
+    stderr = np.sqrt(S * p_inf * (1 - p_inf)).sum()
+    assert abs(np.mean(exposures) - exp_E) < 2 * stderr, (np.mean(exposures), exp_E, stderr)
+
+
+def test_zero_trans(lp, pyramid):
+    for kw in ({"r0": 0}, {"r0_scalars": np.array([0.0, 0.0])}, {"init_prev": 0.0}):
+        sim = tx_sim(lp, pyramid, **kw)
+        sim.run()
+        assert sim.results.E[1:].sum() == 0, kw
+
+
+def test_linear_transmission_scaling(lp, pyramid):
+    def mean_E(**kw):
+        out = []
+        for seed in range(10):
+            sim = tx_sim(lp, pyramid, seed=seed, **kw)
+            sim.run()
+            out.append(sim.results.E[1:].sum())
+        return np.mean(out)
+
+    base = mean_E()
+    assert np.isclose(mean_E(r0=28), 2 * base, rtol=0.2)
+    assert np.isclose(mean_E(r0_scalars=np.array([1.0, 4.0])), 2 * base, rtol=0.2)
+    assert np.isclose(mean_E(init_prev=0.02), 2 * base, rtol=0.2)
+
+
+# ---------------------------------------------------------------- tests/test_strain_transmission.py:58-82, 283-290, 534
+def test_strain_result_shapes_and_totals(lp, pyramid):
+    sim = tx_sim(lp, pyramid, dur=20, init_prev=0.02)
+    sim.run()
+    nt, nn, ns = sim.pars.dur + 1, 2, 3
+    for k in ("E_by_strain", "I_by_strain", "new_exposed_by_strain"):
+        assert getattr(sim.results, k).shape == (nt, nn, ns) and getattr(sim.results, k).dtype == np.int32
+    assert np.array_equal(sim.results.E, sim.results.E_by_strain.sum(axis=2))
+    assert np.array_equal(sim.results.I, sim.results.I_by_strain.sum(axis=2))
+    assert np.array_equal(sim.results.new_exposed, sim.results.new_exposed_by_strain.sum(axis=2))
+    assert sim.results.new_exposed.sum() > 0
+    assert sim.results.E_by_strain[:, :, 1:].sum() == 0  # VDPV2 only without vaccination
+    # bookkeeping identity: no births here would be S[t] = S[t-1] - new_exposed[t] - deaths of S; with VD on, alive adds up
+    alive = np.sum(sim.people.disease_state[: sim.people.count] >= 0)
+    assert alive == sim.pars.init_pop.sum() + sim.results.births.sum() - sim.results.deaths.sum()
+    assert np.array_equal((sim.results.S + sim.results.E + sim.results.I + sim.results.R).sum(axis=1)[-1:], [alive])
+
+
+# ---------------------------------------------------------------- tests/test_interventions.py
+def vx_sim(lp, pyramid, dur=30, init_pop=None, vx_prob_ri=0.5, vx_prob_ipv=0.75, cbr=None, r0=14, new_pars=None, seed=123):
+    pars = base_pars(
+        lp, pyramid, start_date=lp.date("2019-01-01"), dur=dur, init_pop=np.array([50000, 50000]) if init_pop is None else init_pop,
+        cbr=np.array([30, 25]) if cbr is None else cbr, r0=r0, dur_exp=lp.constant(value=2), dur_inf=lp.constant(value=1),
+        vx_prob_ri=vx_prob_ri, vx_prob_ipv=vx_prob_ipv, seed=seed, strain_r0_scalars={0: 1.0, 1: 0.0, 2: 0.0},
+        r0_scalars=np.array([0.8, 1.2]),
+    )
+    pars += new_pars if new_pars is not None else {}
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    return sim
+
+
+def test_ri_manually_seeded(lp, pyramid):
+    n_vx, dur = 1000, 28
+    sim = vx_sim(lp, pyramid, dur=dur, vx_prob_ri=1.0, vx_prob_ipv=1.0)
+    sim.people.ri_timer[:n_vx] = np.random.randint(0, dur, n_vx)
+    sim.run()
+    assert sim.results.ri_vaccinated.sum() >= n_vx and sim.results.ipv_vaccinated.sum() >= n_vx
+
+
+def test_ri_zero(lp, pyramid):
+    sim = vx_sim(lp, pyramid, dur=365, cbr=np.array([0, 0]), vx_prob_ri=1.0, vx_prob_ipv=1.0)
+    sim.run()
+    assert sim.results.ri_vaccinated[:112].sum() > 0
+    assert sim.results.ri_vaccinated[98 + 14 :].sum() == 0 and sim.results.ipv_vaccinated[98 + 14 :].sum() == 0
+    sim = vx_sim(lp, pyramid, dur=120, cbr=np.array([300, 250]), vx_prob_ri=0.0, vx_prob_ipv=0.0)
+    sim.run()
+    assert sim.results.ri_vaccinated.sum() == 0 and sim.results.ipv_vaccinated.sum() == 0
+
+
+def test_ri_no_effect_on_non_susceptibles(lp, pyramid):
+    sim = vx_sim(lp, pyramid, init_pop=np.array([10, 10]), r0=0, vx_prob_ri=1.0)
+    sim.people.ri_timer[:20] = 0
+    sim.people.disease_state[:5] = 1
+    sim.people.disease_state[5:10] = 2
+    sim.people.disease_state[10:15] = 3
+    sim.run()
+    assert np.sum(sim.results.ri_vaccinated) == 20
+    assert np.sum(sim.results.new_exposed) == 5
+
+
+def test_sia_schedule(lp, pyramid):
+    sia = {"sia_schedule": [{"date": "2019-01-10", "nodes": [0], "age_range": (0, 5 * 365), "vaccinetype": "nOPV2"}],
+           "vx_prob_sia": [0.6, 0.8]}
+    sim = vx_sim(lp, pyramid, vx_prob_ri=0, new_pars=sia)
+    sim.run()
+    day10 = np.sum(sim.results.sia_vaccinated[9, :])
+    assert day10 > 0 and np.sum(sim.results.sia_vaccinated) == day10 and sim.results.sia_vaccinated[9, 1] == 0
+    assert np.isclose(np.sum(sim.results.sia_protected), day10 * 0.56, atol=100)
+    alive0 = (sim.people.node_id == 0) & (sim.people.disease_state >= 0)
+    age = sim.t - sim.people.date_of_birth[alive0]
+    assert np.isclose(day10, np.sum(age < 5 * 365) * 0.6, atol=500)
+    assert np.sum(sim.results.new_exposed) == np.sum(sim.results.sia_protected) > 0
+    exposed = sim.people.disease_state == 1
+    assert np.all(sim.t - sim.people.date_of_birth[exposed] <= 5 * 365 + 22)
+    assert sim.results.sia_new_exposed_by_strain[9, 0, 2] == sim.results.sia_protected[9, 0]
+
+
+def test_chronically_missed(lp, pyramid):
+    sia = {"sia_schedule": [{"date": "2019-01-10", "nodes": [0, 1], "age_range": (0, 5 * 365), "vaccinetype": "perfect"}],
+           "vx_prob_sia": [1.0, 1.0], "missed_frac": 0.2}
+    sim = vx_sim(lp, pyramid, vx_prob_ri=0, new_pars=sia)
+    sim.run()
+    missed = sim.people.chronically_missed[: sim.people.count].astype(bool)
+    assert np.isclose(missed.sum(), sim.pars.init_pop.sum() * 0.2, atol=100)
+    eir = np.isin(sim.people.disease_state[: sim.people.count], [1, 2, 3])
+    assert not np.any(eir & missed)
+    age = sim.t - sim.people.date_of_birth[: sim.people.count]
+    assert np.isclose(eir.sum(), np.sum(age < 5 * 365) * 0.8, atol=500)
+
+
+# ---------------------------------------------------------------- tests/test_vital_dynamics.py
+def vd_sim(lp, pyramid, step_size=1, cbr=None):
+    pars = base_pars(lp, pyramid, init_pop=np.array([10000, 5000]), step_size_VitalDynamics_ABM=step_size,
+                     cbr=np.array([30, 25]) if cbr is None else cbr)
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    return sim
+
+
+def _fold_day0(a):
+    a = a.copy()
+    a[1] += a[0]
+    return a[1:]
+
+
+def test_births_generated(lp, pyramid):
+    sim = vd_sim(lp, pyramid)
+    n0 = sim.people.count
+    sim.run()
+    assert sim.people.count > n0
+    assert n0 + sim.results.births.sum() - sim.results.deaths.sum() == np.sum(sim.people.disease_state > -1)
+    dobs = sim.people.date_of_birth[: sim.people.count]
+    expected = _fold_day0(np.bincount(dobs[dobs >= 0], minlength=sim.pars.dur + 1))
+    assert np.array_equal(expected, _fold_day0(np.sum(sim.results.births, axis=1)))
+    assert np.array_equal(sim.results.pop[-1], sim.results.pop[0] + sim.results.births.sum(0) - sim.results.deaths.sum(0))
+
+
+@pytest.mark.parametrize("step_size", [1, 7])
+def test_deaths_occur(lp, pyramid, step_size):
+    sim = vd_sim(lp, pyramid, step_size=step_size)
+    sim.people.date_of_death[:5] = 1
+    sim.run()
+    assert np.all(sim.people.date_of_death[:5] == 1) and np.all(sim.people.disease_state[:5] == -1)
+    dods = sim.people.date_of_death[: sim.people.count]
+    expected = np.bincount(dods[dods >= 0])[: sim.pars.dur + 1]
+    observed = np.sum(sim.results.deaths, axis=1)
+    if step_size == 1:
+        assert np.array_equal(_fold_day0(expected), _fold_day0(observed))
+    else:  # deaths are collected on the step days: compare per bin of `step_size` days
+        edges = np.arange(0, sim.pars.dur + 1, step_size)
+        assert np.array_equal(np.add.reduceat(_fold_day0(expected)[: edges[-1]], edges[:-1]),
+                              np.add.reduceat(_fold_day0(observed)[: edges[-1]], edges[:-1]))
+
+
+def test_no_births_with_zero_cbr(lp, pyramid):
+    sim = vd_sim(lp, pyramid, cbr=np.array([0, 0]))
+    n0 = sim.people.count
+    sim.run()
+    assert sim.people.count == n0 and sim.results.births.sum() == 0
+
+
+# ---------------------------------------------------------------- early stop + seed schedule (model.py:759-795)
+def test_seed_schedule_and_early_stop(lp, pyramid):
+    pars = base_pars(lp, pyramid, dur=60, init_pop=np.array([2000, 2000]), stop_if_no_cases=True, r0=0,
+                     seed_schedule=[{"timestep": 5, "node_id": 1, "prevalence": 50}, {"timestep": 9, "node_id": 0, "prevalence": 0.01}],
+                     dur_inf=lp.constant(value=4))
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    sim.run()
+    assert sim.results.I[4].sum() == 0 and sim.results.I[5, 1] == 50 and sim.results.I[5, 0] == 0
+    assert sim.results.I[9, 0] == 20
+    assert sim.should_stop and sim.t < sim.nt  # infections burn out (r0 = 0) -> stops early
+    assert sim.results.S[sim.t :].sum() == 0  # rows after the stop stay zero
+
+
+def test_same_seed_same_results(lp, pyramid):
+    """tests/test_prng_seeding.py:21-54 (on synthetic inputs): identical seeds give identical result arrays."""
+    outs = []
+    for seed in (11, 11, 12):
+        sim = vx_sim(lp, pyramid, dur=40, init_pop=np.array([20000, 10000]), seed=seed,
+                     new_pars={"sia_schedule": [{"date": "2019-01-20", "nodes": [0, 1], "age_range": (0, 5 * 365), "vaccinetype": "nOPV2"}],
+                               "vx_prob_sia": [0.5, 0.5]})
+        sim.people.disease_state[:200] = 2
+        sim.run()
+        outs.append({k: getattr(sim.results, k).copy() for k in ("births", "deaths", "paralyzed", "ri_vaccinated", "sia_protected",
+                                                                "sia_vaccinated", "S", "E", "I", "R", "new_exposed")})
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert any(not np.array_equal(outs[0][k], outs[2][k]) for k in outs[0])
