@@ -58,6 +58,8 @@ typedef struct lpk_rng {
     const double *u1;   /* optional injected per-agent uniforms (device), else NULL */
     const double *u2;   /* second injected stream (fast_ri IPV draw; strain pick in tx_infect) */
     const uint32_t *x;  /* optional injected per-agent 32-bit words for the exposure trial */
+    uint64_t id_base;   /* added to the agent index in every Philox counter: the global id of local agent 0 when the
+                           table is one node-shard of a larger population (multiple of 4); 0 on a single GPU */
 } lpk_rng;
 
 const char *lpk_last_error(void);
@@ -151,6 +153,103 @@ int lpk_count_seirp(const int16_t *node_id, const int8_t *disease_state, const i
                     const int8_t *potentially_paralyzed, const int8_t *paralyzed, int32_t n_nodes,
                     int32_t n_strains, int64_t n_people, int32_t *S, int32_t *E, int32_t *I, int32_t *R,
                     int32_t *E_by_strain, int32_t *I_by_strain, int32_t *POTP, int32_t *P, void *stream);
+
+/* =====================================================================================================
+ * Fused tick: the fast path behind SEIR_ABM.run() (reference model.py:246-289).
+ *
+ * One streaming pass over the agent table per simulated day instead of one per component.  Because every
+ * draw is keyed on (seed, agent, tick, stage), fusing changes no result: the pass for tick t executes, per
+ * agent and in the reference's order,
+ *     [pending from tick t-1]  tx_infect (model.py:1010-1149 replacement) and the census (model.py:869-929)
+ *     [tick t]                 get_deaths (1767-1781), disease_state_step (344-454), fast_ri (1805-1855),
+ *                              tx_step_prep tally (932-1007)
+ * and lpk_tick_node then does the node-level work of tick t (model.py:1332-1351 + population / paralysis
+ * bookkeeping), producing q / strain_cdf that the NEXT pass applies.  SIA days, seed_schedule days and the
+ * final tick are run through the per-function entry points above (the host drains the pending exposure first).
+ *
+ * All result rows are device pointers to row t (or t-1) of the [nt, nodes(, strains)] int32 arrays; counts are
+ * accumulated with atomics, so "=" rows must be zero beforehand (they are: fresh result arrays) and "+=" rows
+ * (R on top of pre-seeded immunes, new_exposed shared with RI/SIA) keep the reference's semantics for free.
+ * ===================================================================================================== */
+#define LPK_TILE_AGENTS 512
+
+typedef struct lpk_people {
+    int8_t *disease_state, *strain, *exposure_timer, *infection_timer, *paralysis_timer;
+    int8_t *potentially_paralyzed, *paralyzed, *ipv_protected;
+    const uint8_t *chronically_missed;
+    const int16_t *node_id;
+    int16_t *ri_timer;               /* NULL when RI_ABM is not a component */
+    const float *acq_risk_multiplier, *daily_infectivity;
+    const int32_t *date_of_birth;    /* unused by the pass (SIA days are unfused); kept for symmetry, may be NULL */
+    const int32_t *date_of_death;    /* NULL when VitalDynamics_ABM is not a component */
+    const int32_t *tile_node;        /* [ceil(capacity / 512)]: node id shared by every agent slot of the tile, or -1;
+                                        NULL = always read node_id (lpk_build_tile_nodes fills it) */
+    int64_t capacity;
+} lpk_people;
+
+#define LPK_F_PENDING 1u /* apply tick-1's exposure (q_prev / cdf_prev) and take tick-1's census */
+#define LPK_F_STAGES 2u  /* run tick t's own stages and tally */
+#define LPK_F_DEATHS 4u  /* tick t is a vital-dynamics tick: mark deaths (needs date_of_death) */
+#define LPK_F_RI 8u      /* tick t is a routine-immunisation tick (needs ri_timer) */
+
+typedef struct lpk_tick_args {
+    uint32_t flags;
+    int32_t tick; /* t */
+    int32_t n_nodes, n_strains;
+    uint64_t seed, id_base;
+    const int64_t *counts; /* device int64[2] = {agents alive-or-dead in the table when tick t-1 ended, agents now} */
+    /* ---- pending exposure + census of tick t-1 (LPK_F_PENDING) */
+    const float *q_prev;    /* [nodes]          from lpk_tick_node / lpk_tx_node_math of tick t-1 */
+    const double *cdf_prev; /* [nodes, strains] */
+    int32_t *new_exposed_prev, *new_exposed_by_strain_prev; /* rows t-1, += */
+    int32_t *S_prev, *R_prev, *E_by_strain_prev, *I_by_strain_prev; /* rows t-1, accumulate */
+    /* ---- stages of tick t (LPK_F_STAGES) */
+    float p_paralysis;
+    int32_t *new_potential, *new_paralyzed; /* rows t, += */
+    int32_t *deaths, *dead_pp, *dead_par;   /* [nodes] scratch, += : deaths, and how many of the dying had
+                                               potentially_paralyzed == 1 / paralyzed == 1 (census bookkeeping) */
+    int32_t ri_step;
+    int32_t ri_strain;
+    const double *vx_prob_ri, *vx_prob_ipv;                          /* [nodes] */
+    int32_t *ri_vaccinated, *ri_protected, *ipv_vaccinated;          /* rows t */
+    int32_t *new_exposed, *new_exposed_by_strain, *ri_new_exposed_by_strain; /* rows t */
+    double strain_r0_scalars[LPK_MAX_STRAINS];
+    int64_t *beta_fx, *exposure_fx, *sus; /* tally of tick t, += (lpk_tick_node zeroes the other parity buffer) */
+} lpk_tick_args;
+
+/* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
+ * tile's slots (unborn slots carry -1 and make a tile mixed), else -1. */
+int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, int64_t n_slots, int32_t *tile_node, void *stream);
+
+int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream);
+
+typedef struct lpk_node_args {
+    uint32_t flags; /* LPK_F_PENDING: finish rows t-1 (E, I totals); LPK_F_DEATHS: tick t is a vital-dynamics tick */
+    int32_t tick, n_nodes, n_strains;
+    uint64_t seed;
+    /* transmission node math of tick t (same meaning as lpk_tx_node_math) */
+    const int64_t *beta_fx, *exposure_fx;
+    const double *network, *r0_scalars;
+    double beta_seasonality, zero_inflation, dispersion;
+    float *q;
+    double *strain_cdf, *prob, *expected, *rowsum_ws;
+    /* population bookkeeping: pop[t] = pop[t-1] + births[t] - deaths (model.py:1751-1755); NULL pop rows = no VD */
+    const int32_t *pop_prev;
+    int32_t *pop, *births_row, *deaths_row;
+    int32_t *deaths, *dead_pp, *dead_par; /* consumed and zeroed */
+    /* paralysis census kept incrementally: cur += new - dead, row t = cur (model.py:1482-1483 equivalent) */
+    int32_t *cur_potp, *cur_p;
+    const int32_t *new_potential, *new_paralyzed; /* rows t */
+    int32_t *potp_row, *p_row;                     /* rows t */
+    /* totals of the census rows the pass just completed (t-1) */
+    const int32_t *E_by_strain_prev, *I_by_strain_prev;
+    int32_t *E_prev, *I_prev;
+    /* tallies of the other parity, zeroed for tick t+1 */
+    int64_t *next_beta_fx, *next_exposure_fx, *next_sus;
+    int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
+} lpk_node_args;
+
+int lpk_tick_node(const lpk_node_args *args, void *stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,8 @@ FX_SCALE = float(2**30)
 
 EXPORTS = (
     "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
-    "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp",
+    "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
+    "lpk_tick_pass", "lpk_tick_node",
 )
 
 
@@ -33,7 +34,7 @@ class Rng(C.Structure):
 
     _fields_ = [
         ("seed", C.c_uint64), ("tick", C.c_uint32), ("_pad", C.c_uint32),
-        ("u1", C.c_void_p), ("u2", C.c_void_p), ("x", C.c_void_p),
+        ("u1", C.c_void_p), ("u2", C.c_void_p), ("x", C.c_void_p), ("id_base", C.c_uint64),
     ]
 
 
@@ -83,11 +84,68 @@ def stream_handle():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def make_rng(seed=0, tick=0, u1=None, u2=None, x=None) -> Rng:
+def make_rng(seed=0, tick=0, u1=None, u2=None, x=None, id_base=0) -> Rng:
     r = Rng()
     r.seed, r.tick, r._pad = int(seed) & 0xFFFFFFFFFFFFFFFF, int(tick) & 0xFFFFFFFF, 0
     r.u1 = u1.data_ptr() if u1 is not None else None
     r.u2 = u2.data_ptr() if u2 is not None else None
     r.x = x.data_ptr() if x is not None else None
+    r.id_base = int(id_base)
     r._keep = (u1, u2, x)  # the struct only holds raw pointers: keep the tensors alive with it
     return r
+
+
+# ----------------------------------------------------------------------------- fused-tick structs (include/lpk.h)
+_VP = C.c_void_p
+
+
+class People(C.Structure):
+    """struct lpk_people"""
+
+    _fields_ = [(n, _VP) for n in (
+        "disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
+        "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
+        "daily_infectivity", "date_of_birth", "date_of_death", "tile_node")] + [("capacity", C.c_int64)]
+
+
+class TickArgs(C.Structure):
+    """struct lpk_tick_args"""
+
+    _fields_ = [
+        ("flags", C.c_uint32), ("tick", C.c_int32), ("n_nodes", C.c_int32), ("n_strains", C.c_int32),
+        ("seed", C.c_uint64), ("id_base", C.c_uint64), ("counts", _VP),
+        ("q_prev", _VP), ("cdf_prev", _VP), ("new_exposed_prev", _VP), ("new_exposed_by_strain_prev", _VP),
+        ("S_prev", _VP), ("R_prev", _VP), ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP),
+        ("p_paralysis", C.c_float), ("new_potential", _VP), ("new_paralyzed", _VP),
+        ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
+        ("ri_step", C.c_int32), ("ri_strain", C.c_int32), ("vx_prob_ri", _VP), ("vx_prob_ipv", _VP),
+        ("ri_vaccinated", _VP), ("ri_protected", _VP), ("ipv_vaccinated", _VP),
+        ("new_exposed", _VP), ("new_exposed_by_strain", _VP), ("ri_new_exposed_by_strain", _VP),
+        ("strain_r0_scalars", C.c_double * MAX_STRAINS),
+        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP),
+    ]
+
+
+class NodeArgs(C.Structure):
+    """struct lpk_node_args"""
+
+    _fields_ = [
+        ("flags", C.c_uint32), ("tick", C.c_int32), ("n_nodes", C.c_int32), ("n_strains", C.c_int32), ("seed", C.c_uint64),
+        ("beta_fx", _VP), ("exposure_fx", _VP), ("network", _VP), ("r0_scalars", _VP),
+        ("beta_seasonality", C.c_double), ("zero_inflation", C.c_double), ("dispersion", C.c_double),
+        ("q", _VP), ("strain_cdf", _VP), ("prob", _VP), ("expected", _VP), ("rowsum_ws", _VP),
+        ("pop_prev", _VP), ("pop", _VP), ("births_row", _VP), ("deaths_row", _VP),
+        ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
+        ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
+        ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
+        ("next_beta_fx", _VP), ("next_exposure_fx", _VP), ("next_sus", _VP), ("counts", _VP),
+    ]
+
+
+F_PENDING, F_STAGES, F_DEATHS, F_RI = 1, 2, 4, 8
+TILE_AGENTS = 512
+
+
+def dp(t):
+    """data_ptr of a tensor (None -> NULL) for struct fields."""
+    return None if t is None else t.data_ptr()

@@ -71,6 +71,9 @@ class SEIR_ABM:
         self.datevec = utils.daterange(pars["start_date"], days=self.nt)
         self.should_stop = False
         self.dev = None  # DeviceState while the agent table is resident in HBM
+        self._engine = None  # engine.FusedEngine while ticks are being fused
+        self.fused = True  # set False to force component-by-component ticks
+        self.id_base = 0  # global id of local agent 0 when this table is one node-shard of a larger population
         if self.verbose >= 1:
             _say("cyan", "Initializing simulation...")
 
@@ -148,24 +151,44 @@ class SEIR_ABM:
             from .device import DeviceState
 
             self.dev = DeviceState(self, device)
+            self._engine = None
         return self.dev
 
     def to_host(self):
-        """D2H of the agent columns and results into the host arrays (in place), then drop the device copy."""
+        """Finish any pipelined work, D2H the agent columns and results into the host arrays (in place), drop the device copy."""
         if self.dev is not None:
+            if self._engine is not None:
+                self._engine.drain()
+                self._engine = None
             self.dev.download()
             self.io_bytes = (self.dev.h2d_bytes, self.dev.d2h_bytes)
             self.dev = None
 
     # ------------------------------------------------------------------ tick loop
-    def step_tick(self, tick: int) -> None:
-        """One iteration of the reference's loop body (model.py:252-263); requires ``to_device()``."""
+    def _component_tick(self, tick: int) -> None:
+        """The reference's loop body verbatim (model.py:252-263): every step() in run order, then every log()."""
         if tick > 0:
             for component in self.instances:
                 with self.perf_stats.start(component.__class__.__name__ + ".step()"):
                     component.step()
         self.log_results(tick)
         self.t += 1
+
+    def step_tick(self, tick: int) -> None:
+        """Advance one tick on the device.  With the stock component list the day runs as the fused pass
+        (engine.FusedEngine: same results, one sweep over the agent table); otherwise component by component."""
+        self.to_device()
+        if getattr(self, "_engine", None) is None:
+            from . import engine
+
+            self._engine = engine.FusedEngine(self) if engine.eligible(self) else False
+        if self._engine is False:
+            self._component_tick(tick)
+        elif tick == 0:
+            self._component_tick(tick)
+            self._engine.after_component_tick(0)
+        else:
+            self._engine.tick(tick)
 
     def run(self):
         if self.verbose >= 1:
@@ -196,7 +219,7 @@ class SEIR_ABM:
     def rng(self, tick=None):
         from . import kernels
 
-        return kernels.make_rng(self.pars.seed, self.t if tick is None else tick)
+        return kernels.make_rng(self.pars.seed, self.t if tick is None else tick, id_base=self.id_base)
 
 
 def _need_dev(sim):

@@ -4,56 +4,24 @@
 #include <cstdio>
 #include <cstring>
 
-#include "lpk_common.cuh"
+#include "lpk_host.cuh"
+#include "lpk_stages.cuh"
 
 // ------------------------------------------------------------------ error plumbing
-static thread_local char g_err[256] = "";
-static int set_cuda_err(cudaError_t e, const char *where) {
-    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
-    return LPK_ERR_CUDA;
-}
-static int set_arg_err(const char *what) {
-    snprintf(g_err, sizeof(g_err), "bad argument: %s", what);
-    return LPK_ERR_ARG;
-}
-extern "C" const char *lpk_last_error(void) { return g_err; }
-extern "C" int lpk_version(void) { return 1; }
+thread_local char lpk_g_err[256] = "";
+extern "C" const char *lpk_last_error(void) { return lpk_g_err; }
+extern "C" int lpk_version(void) { return 2; }
 
-#define REQUIRE(cond, what) do { if (!(cond)) return set_arg_err(what); } while (0)
-#define ALIGNED(p, a) ((reinterpret_cast<uintptr_t>(p) & ((a) - 1)) == 0)
-#define CUDA_TRY(expr, where) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_cuda_err(e_, where); } while (0)
-
-static int g_sm_count = 0;
-static int sm_count() {
-    if (g_sm_count == 0) {
+int lpk_sm_count() {
+    static int count = 0;
+    if (count == 0) {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
-            g_sm_count = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || count <= 0)
+            count = 148;
     }
-    return g_sm_count;
+    return count;
 }
-// persistent grid: a multiple of the SM count, never more blocks than there are tiles per warp-group
-static int agent_grid(int64_t n, int blocks_per_sm) {
-    const int64_t tiles = (n + LPK_TILE - 1) / LPK_TILE;
-    const int64_t want = (tiles + LPK_WARPS - 1) / LPK_WARPS;
-    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
-    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
-}
-static cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
-
-struct DevRng {
-    uint64_t seed;
-    uint32_t tick;
-    const double *u1;
-    const double *u2;
-    const uint32_t *x;
-};
-static DevRng dev_rng(const lpk_rng *r) {
-    DevRng d;
-    d.seed = r ? r->seed : 0; d.tick = r ? r->tick : 0;
-    d.u1 = r ? r->u1 : nullptr; d.u2 = r ? r->u2 : nullptr; d.x = r ? r->x : nullptr;
-    return d;
-}
+#define agent_grid lpk_agent_grid
 
 // ------------------------------------------------------------------ Philox self test
 __global__ void k_philox_selftest(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n) {
@@ -114,41 +82,6 @@ extern "C" int lpk_get_deaths(int32_t num_nodes, int64_t num_people, int8_t *dis
 }
 
 // ------------------------------------------------------------------ D1 disease_state_step
-// One agent of the state machine (reference model.py:419-452); returns the new state.
-__device__ __forceinline__ int8_t ds_agent(int64_t i, int8_t s, const int16_t *node_id, const int8_t *strain,
-                                           int8_t *etimer, int8_t *itimer, int8_t *pot_par, int8_t *paralyzed,
-                                           const int8_t *ipv, int8_t *ptimer, double p_paralysis, int32_t *new_pot,
-                                           int32_t *new_par, const DevRng &rng) {
-    if (s == 1) {
-        const int8_t e = etimer[i];
-        if (e <= 0) s = 2;
-        etimer[i] = (int8_t)(e - 1);
-    }
-    if (s == 2) {
-        const int8_t it = itimer[i];
-        if (it <= 0) s = 3;
-        itimer[i] = (int8_t)(it - 1);
-        if (strain[i] == 0) {
-            const int8_t pt = ptimer[i];
-            if (pt <= 0 && pot_par[i] == -1) {
-                if (ipv[i] == 0) {
-                    pot_par[i] = 1;
-                    const int nd = node_id[i];
-                    atomicAdd(&new_pot[nd], 1);
-                    double u;
-                    if (rng.u1) u = rng.u1[i];
-                    else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
-                    if (u < p_paralysis) { paralyzed[i] = 1; atomicAdd(&new_par[nd], 1); }
-                } else {
-                    pot_par[i] = 0;
-                }
-            }
-            ptimer[i] = (int8_t)(pt - 1);
-        }
-    }
-    return s;
-}
-
 __global__ void __launch_bounds__(LPK_BLOCK) k_disease_state(int64_t n, const int16_t *__restrict__ node_id,
                                                               int8_t *__restrict__ state, const int8_t *__restrict__ strain,
                                                               int8_t *etimer, int8_t *itimer, int8_t *pot_par,
@@ -240,7 +173,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_fast_ri(int64_t n, int step, cons
                 const int nd = node_id[i];
                 double u1, u2;
                 if (rng.u1) { u1 = rng.u1[i]; u2 = rng.u2[i]; }
-                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_RI, x); u1 = u53(x[0], x[1]); u2 = u53(x[2], x[3]); }
+                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_RI, x); u1 = u53(x[0], x[1]); u2 = u53(x[2], x[3]); }
                 if (u1 < prob_ri[nd]) {
                     atomicAdd(&ri_counts[nd], 1);
                     if (s == 0) { nw = set_byte(nw, k, 1); strain[i] = vaccine_strain; atomicAdd(&ri_protected[nd], 1); }
@@ -324,7 +257,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_fast_sia(int64_t n, const int16_t
                 const int64_t i = base + k;
                 double r;
                 if (rng.u1) r = rng.u1[i];
-                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, stage, x); r = u53(x[0], x[1]); }
+                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, stage, x); r = u53(x[0], x[1]); }
                 const double pv = (double)vx_prob[nd[k]];
                 if (r < pv) {
                     acc.select(nd[k], flush);
@@ -544,12 +477,6 @@ extern "C" int lpk_count_seirp(const int16_t *node_id, const int8_t *disease_sta
 }
 
 // ------------------------------------------------------------------ T3 tx_infect (per-agent Bernoulli)
-__device__ __forceinline__ bool expose_hit(float p, uint32_t x) {
-    if (!(p > 0.f)) return false;
-    if (p >= 1.f) return true;
-    return x < (uint32_t)__float2uint_rz(p * 4294967296.0f);
-}
-
 __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strains, const int16_t *__restrict__ node_id,
                                                           int8_t *strain, int8_t *__restrict__ state,
                                                           const float *__restrict__ risk, const float *__restrict__ q,
@@ -591,7 +518,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strain
             load_f4(risk, base[j], valid[j], rk);
             uint32_t x[4];
             if (rng.x) { for (int k = 0; k < 4; ++k) x[k] = (k < valid[j]) ? rng.x[base[j] + k] : 0u; }
-            else philox_agent(rng.seed, (uint64_t)base[j] >> 2, rng.tick, LPK_STAGE_EXPOSE, x);
+            else philox_agent(rng.seed, ((uint64_t)base[j] + rng.id_base) >> 2, rng.tick, LPK_STAGE_EXPOSE, x);
             uint32_t nw = w[j];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -600,7 +527,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strain
                 const int64_t i = base[j] + k;
                 double r;
                 if (rng.u2) r = rng.u2[i];
-                else { uint32_t y[4]; philox_agent(rng.seed, (uint64_t)i, rng.tick, LPK_STAGE_STRAIN, y); r = u53(y[0], y[1]); }
+                else { uint32_t y[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_STRAIN, y); r = u53(y[0], y[1]); }
                 int assigned = 0;
                 for (int s = 0; s < n_strains; ++s)
                     if (r < strain_cdf[(int64_t)nd[k] * n_strains + s]) { assigned = s; break; }
@@ -622,6 +549,7 @@ extern "C" int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_
     REQUIRE(num_strains >= 1 && num_strains <= LPK_MAX_STRAINS, "tx_infect n_strains");
     REQUIRE(node_ids && strain && disease_state && risks && q && strain_cdf && n_new, "tx_infect null pointer");
     REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(node_ids, 8) && ALIGNED(risks, 16), "tx_infect alignment");
+    REQUIRE(!rng || (rng->id_base & 3) == 0, "tx_infect id_base must be a multiple of 4");
     cudaStream_t st = as_stream(stream);
     CUDA_TRY(cudaMemsetAsync(n_new, 0, sizeof(int32_t) * num_nodes * num_strains, st), "tx_infect memset");
     if (num_people == 0) return LPK_OK;
@@ -720,6 +648,21 @@ __global__ void __launch_bounds__(256) k_tx_node_math(int n, int n_strains, cons
     q[j] = (float)(P * g);
 }
 
+int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
+                         const double *network, double beta_seasonality, const double *r0_scalars, const int32_t *alive_counts,
+                         double zero_inflation, double dispersion, float *q, double *strain_cdf, double *prob, double *expected,
+                         double *rowsum_ws, uint64_t seed, uint32_t tick, cudaStream_t st) {
+    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum_ws);
+    CUDA_TRY(cudaGetLastError(), "node_math rowsums");
+    double r = nearbyint(dispersion);
+    if (r < 1.0) r = 1.0;
+    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum_ws,
+                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, q,
+                                                          strain_cdf, prob, expected, seed, tick);
+    CUDA_TRY(cudaGetLastError(), "node_math");
+    return LPK_OK;
+}
+
 extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                                 const double *network, double beta_seasonality, const double *r0_scalars,
                                 const int32_t *alive_counts, double zero_inflation, double dispersion, float *q,
@@ -729,15 +672,7 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
     REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "tx_node_math n_strains");
     REQUIRE(beta_fx && exposure_fx && network && r0_scalars && alive_counts && q && strain_cdf && prob && expected &&
                 rowsum_ws, "tx_node_math null pointer");
-    cudaStream_t st = as_stream(stream);
-    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum_ws);
-    CUDA_TRY(cudaGetLastError(), "lpk_tx_node_math rowsums");
-    double r = nearbyint(dispersion);
-    if (r < 1.0) r = 1.0;
-    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum_ws,
-                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, q,
-                                                          strain_cdf, prob, expected, rng ? rng->seed : 0,
-                                                          rng ? rng->tick : 0);
-    CUDA_TRY(cudaGetLastError(), "lpk_tx_node_math");
-    return LPK_OK;
+    return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, network, beta_seasonality, r0_scalars, alive_counts,
+                                zero_inflation, dispersion, q, strain_cdf, prob, expected, rowsum_ws, rng ? rng->seed : 0,
+                                rng ? rng->tick : 0, as_stream(stream));
 }

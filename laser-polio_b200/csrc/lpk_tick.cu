@@ -1,0 +1,418 @@
+// lpk_tick.cu -- the fused tick: ONE streaming pass over the agent table per simulated day.
+//
+// Pass for tick t, per agent, in the reference's order (include/lpk.h, "Fused tick"):
+//   pending tick t-1:  exposure trial (tx_infect)  ->  census (count_SEIRP: S, R, E/I by strain)
+//   tick t:            deaths (get_deaths) -> disease state (disease_state_step) -> RI (fast_ri) -> tally (tx_step_prep)
+// Every draw is Philox(seed; agent, tick, stage), so the fused pass reproduces the per-function kernels bit for bit
+// (tests/test_gpu_fused.py).  Design notes (profiles/r1_baseline_*: the unfused kernels were issue- and latency-bound
+// at ~16 % of HBM peak with `no_instruction` and `long_scoreboard` the top stalls):
+//   * all of a tile's loads (state of the NEXT tile, risk / node / date_of_death of this one) are issued before any is
+//     consumed, so each warp keeps ~3 KB in flight;
+//   * the byte columns are handled four agents at a time with SIMD-in-a-word compares / popcounts;
+//   * everything rare (a hit, an E/I agent, a death, an RI-eligible agent) lives in __noinline__ functions so the
+//     streaming loop stays a few KB of code;
+//   * node ids come from a per-tile table (one broadcast load per 512 agents) whenever the tile is node-uniform.
+#include "lpk_host.cuh"
+#include "lpk_stages.cuh"
+
+struct PassParams {
+    lpk_people P;
+    lpk_tick_args A;
+};
+
+// accumulator slots
+enum { CI_S = 0, CI_R = 1, CI_E = 2, CI_I = 2 + LPK_MAX_STRAINS, CI_NEW = 2 + 2 * LPK_MAX_STRAINS, CI_SUS = 2 + 3 * LPK_MAX_STRAINS, CI_N };
+enum { CL_EXPO = 0, CL_BETA = 1, CL_N = 1 + LPK_MAX_STRAINS };
+typedef NodeAcc<CI_N, CL_N> TickAcc;
+
+// ------------------------------------------------------------------ rare paths (out of line)
+__device__ __noinline__ int pick_strain(const PassParams &pp, int64_t i, int nd) {
+    uint32_t y[4];
+    philox_agent(pp.A.seed, (uint64_t)i + pp.A.id_base, (uint32_t)(pp.A.tick - 1), LPK_STAGE_STRAIN, y);
+    const double r = u53(y[0], y[1]);
+    const int ns = pp.A.n_strains;
+    int assigned = 0;
+    for (int s = 0; s < ns; ++s)
+        if (r < pp.A.cdf_prev[(int64_t)nd * ns + s]) { assigned = s; break; }
+    pp.P.strain[i] = (int8_t)assigned;
+    return assigned;
+}
+
+__device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd) {
+    atomicAdd(&pp.A.deaths[nd], 1);
+    if (pp.P.potentially_paralyzed[i] == 1) atomicAdd(&pp.A.dead_pp[nd], 1);
+    if (pp.P.paralyzed[i] == 1) atomicAdd(&pp.A.dead_par[nd], 1);
+}
+
+__device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8_t s) {
+    DevRng rng;
+    rng.seed = pp.A.seed; rng.tick = (uint32_t)pp.A.tick; rng.u1 = nullptr; rng.u2 = nullptr; rng.x = nullptr;
+    rng.id_base = pp.A.id_base;
+    const lpk_people &P = pp.P;
+    return ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
+                    P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed, rng);
+}
+
+// census / tally contribution of one E or I agent: returns its strain
+__device__ __noinline__ int strain_of(const PassParams &pp, int64_t i) { return pp.P.strain[i]; }
+
+__device__ __noinline__ long long infectious_fx(const PassParams &pp, int64_t i, int *strain_out) {
+    const int s = pp.P.strain[i];
+    *strain_out = s;
+    return to_fx((double)pp.P.daily_infectivity[i] * pp.A.strain_r0_scalars[s]);
+}
+
+// routine immunisation for one quad (reference model.py:1825-1854); returns the new state word
+__device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int valid, uint32_t w) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int step = A.ri_step;
+    const int64_t t = A.tick;
+    const bool first = (t == step), later = (t > step);
+    const uint32_t m = load_b4(reinterpret_cast<const int8_t *>(P.chronically_missed), base, valid, 1);
+    int tm[4];
+    load_s4(P.ri_timer, base, valid, tm);
+    bool touched = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int8_t s = byte_of(w, k);
+        if (s < 0 || byte_of(m, k) == 1) continue;
+        const int timer = tm[k] - step;
+        tm[k] = timer;
+        touched = true;
+        const bool eligible = first ? (timer <= 0 && timer >= -step) : (later && timer <= 0 && timer > -step);
+        if (!eligible) continue;
+        const int64_t i = base + k;
+        const int nd = P.node_id[i];
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
+        const double u1 = u53(x[0], x[1]), u2 = u53(x[2], x[3]);
+        if (u1 < A.vx_prob_ri[nd]) {
+            atomicAdd(&A.ri_vaccinated[nd], 1);
+            if (s == 0) {
+                w = set_byte(w, k, 1);
+                P.strain[i] = (int8_t)A.ri_strain;
+                const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
+                atomicAdd(&A.ri_protected[nd], 1);
+                atomicAdd(&A.new_exposed[nd], 1);
+                atomicAdd(&A.new_exposed_by_strain[c], 1);
+                atomicAdd(&A.ri_new_exposed_by_strain[c], 1);
+            }
+        }
+        if (u2 < A.vx_prob_ipv[nd]) { atomicAdd(&A.ipv_vaccinated[nd], 1); P.ipv_protected[i] = 1; }
+    }
+    if (touched) {
+        if (valid == 4) *reinterpret_cast<short4 *>(P.ri_timer + base) = make_short4((short)tm[0], (short)tm[1], (short)tm[2], (short)tm[3]);
+        else for (int k = 0; k < valid; ++k) P.ri_timer[base + k] = (int16_t)tm[k];
+    }
+    return w;
+}
+
+__device__ __forceinline__ void acc_add_strain(TickAcc &acc, int slot0, int strain, int v) {
+#pragma unroll
+    for (int q = 0; q < LPK_MAX_STRAINS; ++q) acc.ci[slot0 + q] += (q == strain) ? v : 0;
+}
+
+// ------------------------------------------------------------------ the pass
+template <bool kDeaths, bool kRI>
+__global__ void __launch_bounds__(LPK_BLOCK, 2) k_tick_pass(const __grid_constant__ PassParams pp) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t count_prev = A.counts[0], n = A.counts[1];
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    const int ns = A.n_strains;
+    const int tick = A.tick;
+    const TileRange tr = block_tiles(n);
+
+    TickAcc acc;
+    acc.init();
+    auto flush = [&](int nd, const int *ci, const long long *cl) {
+        red_add(&A.S_prev[nd], ci[CI_S]);
+        red_add(&A.R_prev[nd], ci[CI_R]);
+        int tot_new = 0;
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
+            if (s < ns) {
+                const int64_t c = (int64_t)nd * ns + s;
+                red_add(&A.E_by_strain_prev[c], ci[CI_E + s]);
+                red_add(&A.I_by_strain_prev[c], ci[CI_I + s]);
+                red_add(&A.new_exposed_by_strain_prev[c], ci[CI_NEW + s]);
+                red_add(&A.beta_fx[c], cl[CL_BETA + s]);
+                tot_new += ci[CI_NEW + s];
+            }
+        }
+        red_add(&A.new_exposed_prev[nd], tot_new);
+        if (ci[CI_SUS]) atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)ci[CI_SUS]);
+        red_add(&A.exposure_fx[nd], cl[CL_EXPO]);
+    };
+
+    int64_t tile = tr.lo + warp;
+    uint32_t wn[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (tile < tr.hi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t b = quad_base(tile, j, lane);
+            const int v = quad_valid(b, n);
+            if (v) wn[j] = load_b4(P.disease_state, b, v);
+        }
+    }
+    for (; tile < tr.hi; tile += LPK_WARPS) {
+        uint32_t w[4];
+        int64_t base[4];
+        int valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w[j] = wn[j];
+            base[j] = quad_base(tile, j, lane);
+            valid[j] = quad_valid(base[j], n);
+        }
+        // ---- issue every load of this tile (and the next tile's state words) before consuming any
+        const int64_t next = tile + LPK_WARPS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wn[j] = 0xFFFFFFFFu;
+            if (next < tr.hi) {
+                const int64_t b = quad_base(next, j, lane);
+                const int v = quad_valid(b, n);
+                if (v) wn[j] = load_b4(P.disease_state, b, v);
+            }
+        }
+        const int tn = P.tile_node ? __ldg(&P.tile_node[tile]) : -1;
+        float rk[4][4];
+        bool hasS[4];
+        uint2 ndraw[4];
+        int4 dd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hasS[j] = valid[j] && any_byte_eq(w[j], 0u);
+            if (hasS[j]) load_f4(P.acq_risk_multiplier, base[j], valid[j], rk[j]);
+            else { rk[j][0] = rk[j][1] = rk[j][2] = rk[j][3] = 0.f; }
+            const bool alive = valid[j] && (w[j] & 0x80808080u) != 0x80808080u;
+            ndraw[j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (tn < 0 && alive) {
+                if (valid[j] == 4) ndraw[j] = *reinterpret_cast<const uint2 *>(P.node_id + base[j]);
+                else {
+                    int t4[4];
+                    load_s4(P.node_id, base[j], valid[j], t4);
+                    ndraw[j] = make_uint2(((uint32_t)t4[0] & 0xFFFFu) | ((uint32_t)t4[1] << 16), ((uint32_t)t4[2] & 0xFFFFu) | ((uint32_t)t4[3] << 16));
+                }
+            }
+            if (kDeaths) {
+                dd[j] = make_int4(0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF);
+                if (alive) {
+                    int t4[4];
+                    load_i4(P.date_of_death, base[j], valid[j], t4);
+                    dd[j] = make_int4(t4[0], t4[1], t4[2], t4[3]);
+                }
+            }
+        }
+        // ---- consume, quad by quad
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t wj = w[j];
+            if (valid[j] == 0 || (wj & 0x80808080u) == 0x80808080u) continue;  // nobody alive here
+            const int64_t b = base[j];
+            int nq[4];
+            if (tn >= 0) { nq[0] = nq[1] = nq[2] = nq[3] = tn; }
+            else {
+                nq[0] = (int)(int16_t)(ndraw[j].x & 0xFFFFu); nq[1] = (int)(int16_t)(ndraw[j].x >> 16);
+                nq[2] = (int)(int16_t)(ndraw[j].y & 0xFFFFu); nq[3] = (int)(int16_t)(ndraw[j].y >> 16);
+            }
+            uint32_t nw = wj;
+            if (pending) {
+                // exposure trial of tick t-1 for the susceptibles that existed then
+                if (hasS[j]) {
+                    float qv[4];
+                    bool live = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        qv[k] = (byte_of(wj, k) == 0 && b + k < count_prev) ? __ldg(&A.q_prev[nq[k]]) : 0.f;
+                        live |= qv[k] > 0.f;
+                    }
+                    if (live) {
+                        uint32_t x[4];
+                        philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (qv[k] > 0.f && expose_hit(__fmul_rn(rk[j][k], qv[k]), x[k])) {
+                                const int s = pick_strain(pp, b + k, nq[k]);
+                                nw = set_byte(nw, k, 1);
+                                acc.select(nq[k], flush);
+                                acc_add_strain(acc, CI_NEW, s, 1);
+                            }
+                        }
+                    }
+                }
+                // census of tick t-1 on the post-exposure state
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int8_t s = byte_of(nw, k);
+                    if (s < 0 || b + k >= count_prev) continue;
+                    acc.select(nq[k], flush);
+                    acc.ci[CI_S] += (s == 0);
+                    acc.ci[CI_R] += (s == 3);
+                    if (s == 1 || s == 2) acc_add_strain(acc, s == 1 ? CI_E : CI_I, strain_of(pp, b + k), 1);
+                }
+            }
+            // ---- tick t
+            if (kDeaths) {
+                const int dq[4] = {dd[j].x, dd[j].y, dd[j].z, dd[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
+                        kill_agent(pp, b + k, nq[k]);
+                        nw = set_byte(nw, k, -1);
+                    }
+                }
+            }
+            if (any_byte_eq(nw, 1u) || any_byte_eq(nw, 2u)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int8_t s = byte_of(nw, k);
+                    if (s == 1 || s == 2) nw = set_byte(nw, k, ds_agent_ol(pp, b + k, s));
+                }
+            }
+            if (kRI) nw = ri_quad(pp, b, valid[j], nw);
+            // tally of tick t
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int8_t s = byte_of(nw, k);
+                if (s == 0) {
+                    acc.select(nq[k], flush);
+                    acc.ci[CI_SUS] += 1;
+                    acc.cl[CL_EXPO] += __float2ll_rn(rk[j][k] * 1073741824.0f);
+                } else if (s == 2) {
+                    acc.select(nq[k], flush);
+                    int st;
+                    const long long fx = infectious_fx(pp, b + k, &st);
+#pragma unroll
+                    for (int q = 0; q < LPK_MAX_STRAINS; ++q) acc.cl[CL_BETA + q] += (q == st) ? fx : 0ll;
+                }
+            }
+            if (nw != wj) store_b4(P.disease_state, b, valid[j], nw);
+        }
+    }
+    acc.finish_warp(flush);
+}
+
+extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream) {
+    REQUIRE(people && args, "tick_pass null struct");
+    const lpk_people &P = *people;
+    const lpk_tick_args &A = *args;
+    REQUIRE(A.n_nodes > 0 && A.n_strains >= 1 && A.n_strains <= LPK_MAX_STRAINS, "tick_pass sizes");
+    REQUIRE(P.capacity > 0 && A.counts, "tick_pass counts");
+    REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer && P.potentially_paralyzed &&
+                P.paralyzed && P.ipv_protected && P.node_id && P.acq_risk_multiplier && P.daily_infectivity, "tick_pass agent columns");
+    REQUIRE(ALIGNED(P.disease_state, 4) && ALIGNED(P.node_id, 8) && ALIGNED(P.acq_risk_multiplier, 16), "tick_pass alignment");
+    REQUIRE((A.flags & LPK_F_STAGES) != 0, "tick_pass always runs the stages of its tick (LPK_F_STAGES)");
+    REQUIRE((A.id_base & 3) == 0, "tick_pass id_base must be a multiple of 4");
+    REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus, "tick_pass stage outputs");
+    REQUIRE(A.S_prev && A.R_prev && A.E_by_strain_prev && A.I_by_strain_prev && A.new_exposed_prev && A.new_exposed_by_strain_prev,
+            "tick_pass census rows");
+    if (A.flags & LPK_F_PENDING) REQUIRE(A.q_prev && A.cdf_prev, "tick_pass pending exposure inputs");
+    const bool deaths = (A.flags & LPK_F_DEATHS) != 0, ri = (A.flags & LPK_F_RI) != 0;
+    if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && A.deaths && A.dead_pp && A.dead_par, "tick_pass deaths");
+    if (ri) REQUIRE(P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
+                        A.vx_prob_ipv && A.ri_vaccinated && A.ri_protected && A.ipv_vaccinated && A.new_exposed &&
+                        A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0, "tick_pass RI");
+    PassParams pp;
+    pp.P = P;
+    pp.A = A;
+    const int grid = lpk_agent_grid(P.capacity, 2);
+    cudaStream_t st = as_stream(stream);
+    if (deaths && ri) k_tick_pass<true, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
+    else if (deaths) k_tick_pass<true, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
+    else if (ri) k_tick_pass<false, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
+    else k_tick_pass<false, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
+    CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ tile -> node table
+__global__ void k_build_tile_nodes(const int16_t *__restrict__ node_id, int64_t first_tile, int64_t n_tiles, int64_t n_slots,
+                                   int32_t *__restrict__ tile_node) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = first_tile + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int64_t lo = tile * LPK_TILE;
+    const int first = node_id[lo];
+    bool same = true;
+    for (int k = lane; k < LPK_TILE; k += 32) {
+        const int64_t i = lo + k;
+        same &= (i < n_slots) && (node_id[i] == first);
+    }
+    same = __all_sync(LPK_FULL, same);
+    if (lane == 0) tile_node[tile] = (same && first >= 0) ? first : -1;
+}
+extern "C" int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, int64_t n_slots, int32_t *tile_node, void *stream) {
+    REQUIRE(node_id && tile_node && first_tile >= 0 && n_slots >= 0, "build_tile_nodes");
+    const int64_t n_tiles = (n_slots + LPK_TILE - 1) / LPK_TILE;
+    if (first_tile >= n_tiles) return LPK_OK;
+    const int64_t todo = n_tiles - first_tile;
+    k_build_tile_nodes<<<(unsigned)((todo + 7) / 8), 256, 0, as_stream(stream)>>>(node_id, first_tile, n_tiles, n_slots, tile_node);
+    CUDA_TRY(cudaGetLastError(), "lpk_build_tile_nodes");
+    return LPK_OK;
+}
+
+// ------------------------------------------------------------------ node-level epilogue of tick t
+__global__ void k_tick_epilogue(lpk_node_args a) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0 && a.counts) a.counts[0] = a.counts[1];
+    if (n >= a.n_nodes) return;
+    const int ns = a.n_strains;
+    int d = 0, dpp = 0, dpar = 0;
+    if (a.deaths) {
+        d = a.deaths[n]; dpp = a.dead_pp[n]; dpar = a.dead_par[n];
+        a.deaths[n] = 0; a.dead_pp[n] = 0; a.dead_par[n] = 0;
+    }
+    if (a.pop) {
+        const int births = a.births_row ? a.births_row[n] : 0;
+        if (a.flags & LPK_F_DEATHS) {
+            a.deaths_row[n] = d;  // "=": overwrites pre-modelled deaths of the non-agent immunes (model.py:1749)
+            a.pop[n] = a.pop_prev[n] + births - d;
+        } else {
+            a.pop[n] = a.pop_prev[n];
+        }
+    }
+    if (a.cur_potp) {
+        const int potp = a.cur_potp[n] + a.new_potential[n] - dpp;
+        const int par = a.cur_p[n] + a.new_paralyzed[n] - dpar;
+        a.cur_potp[n] = potp; a.cur_p[n] = par;
+        a.potp_row[n] = potp; a.p_row[n] = par;
+    }
+    if ((a.flags & LPK_F_PENDING) && a.E_prev) {
+        int e = 0, i = 0;
+        for (int s = 0; s < ns; ++s) { e += a.E_by_strain_prev[(int64_t)n * ns + s]; i += a.I_by_strain_prev[(int64_t)n * ns + s]; }
+        a.E_prev[n] = e; a.I_prev[n] = i;
+    }
+    if (a.next_beta_fx) {
+        for (int s = 0; s < ns; ++s) a.next_beta_fx[(int64_t)n * ns + s] = 0;
+        a.next_exposure_fx[n] = 0;
+        a.next_sus[n] = 0;
+    }
+}
+
+int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
+                         const double *network, double beta_seasonality, const double *r0_scalars, const int32_t *alive_counts,
+                         double zero_inflation, double dispersion, float *q, double *strain_cdf, double *prob, double *expected,
+                         double *rowsum_ws, uint64_t seed, uint32_t tick, cudaStream_t st);
+
+extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
+    REQUIRE(args, "tick_node null struct");
+    const lpk_node_args &a = *args;
+    REQUIRE(a.n_nodes > 0 && a.n_strains >= 1 && a.n_strains <= LPK_MAX_STRAINS, "tick_node sizes");
+    REQUIRE(a.beta_fx && a.exposure_fx && a.network && a.r0_scalars && a.q && a.strain_cdf && a.prob && a.expected && a.rowsum_ws,
+            "tick_node node-math pointers");
+    REQUIRE(!a.pop || (a.pop_prev && (!(a.flags & LPK_F_DEATHS) || (a.deaths_row && a.deaths))), "tick_node population rows");
+    REQUIRE(!a.cur_potp || (a.cur_p && a.new_potential && a.new_paralyzed && a.potp_row && a.p_row), "tick_node paralysis rows");
+    REQUIRE(!a.deaths || (a.dead_pp && a.dead_par), "tick_node death scratch");
+    REQUIRE(!a.next_beta_fx || (a.next_exposure_fx && a.next_sus), "tick_node next tallies");
+    REQUIRE(a.pop || a.pop_prev, "tick_node needs a population row for the rate denominator");
+    cudaStream_t st = as_stream(stream);
+    k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
+    return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.network, a.beta_seasonality, a.r0_scalars,
+                                a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob, a.expected,
+                                a.rowsum_ws, a.seed, (uint32_t)a.tick, st);
+}

@@ -1,0 +1,216 @@
+"""Fused-tick engine: what ``SEIR_ABM.run()`` drives when the component list is the stock one.
+
+The reference's loop body (model.py:252-263) calls every component's ``step()`` and then ``log(t)``; here the same
+work for a whole day is ONE streaming pass over the agent table (``lpk_tick_pass``) plus a node-level kernel
+(``lpk_tick_node``), software-pipelined by one tick: the pass for tick t first applies tick t-1's exposure trial and
+takes tick t-1's census, then runs tick t's deaths / disease-state / RI stages and tick t's infectivity tally.
+Results are identical to calling the components one by one (every draw is keyed on (seed, agent, tick, stage));
+``tests/test_gpu_fused.py`` asserts that bit for bit.
+
+Days that need something the pass does not fuse -- an SIA campaign, a ``seed_schedule`` injection, a
+vital-dynamics tick (births are drawn on the host) -- are run through the components after draining the pending
+exposure + census, so any schedule is legal.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lpk
+from . import kernels as K
+from ._lpk import F_DEATHS, F_PENDING, F_RI, F_STAGES, NodeArgs, People, TickArgs, check, dp, stream_handle
+
+STOCK = ("VitalDynamics_ABM", "DiseaseState_ABM", "RI_ABM", "SIA_ABM", "Transmission_ABM")
+
+
+def eligible(sim) -> bool:
+    """Fused path preconditions: stock components incl. disease state + transmission, no per-tick host decisions."""
+    from . import abm
+
+    names = [type(i).__name__ for i in sim.instances]
+    if not all(type(i) is getattr(abm, n, None) for i, n in zip(sim.instances, names)):
+        return False  # subclassed / foreign components: call their step() as written
+    if "DiseaseState_ABM" not in names or "Transmission_ABM" not in names:
+        return False
+    if sim.pars["stop_if_no_cases"]:  # the early-stop test needs tick t-1's census before tick t starts
+        return False
+    return getattr(sim, "fused", True) and sim.verbose < 3
+
+
+class FusedEngine:
+    def __init__(self, sim):
+        self.sim = sim
+        self.dev = dev = sim.dev
+        self.by_name = {type(i).__name__: i for i in sim.instances}
+        n, ns, d = dev.n_nodes, dev.n_strains, dev.device
+        c = dev.cols
+        self.pending = False
+        self.launches = 0
+        cap = sim.people.capacity
+        n_tiles = (cap + _lpk.TILE_AGENTS - 1) // _lpk.TILE_AGENTS
+        self.tile_node = torch.empty(n_tiles, dtype=torch.int32, device=d)
+        self.rebuild_tiles(0)
+        self.counts = torch.tensor([sim.people.count, sim.people.count], dtype=torch.int64, device=d)
+        self._count_host = sim.people.count
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=d)  # noqa: E731
+        i64 = lambda *s: torch.zeros(s, dtype=torch.int64, device=d)  # noqa: E731
+        self.tally = [(i64(n, ns), i64(n), i64(n)) for _ in range(2)]
+        self.deaths, self.dead_pp, self.dead_par = i32(n), i32(n), i32(n)
+        self.cur_potp, self.cur_p = i32(n), i32(n)
+        self.q = torch.zeros(n, dtype=torch.float32, device=d)
+        self.cdf = torch.zeros((n, ns), dtype=torch.float64, device=d)
+        self.prob = torch.zeros((n, ns), dtype=torch.float64, device=d)
+        self.expected = torch.zeros(n, dtype=torch.float64, device=d)
+        self.rowsum = torch.zeros(n, dtype=torch.float64, device=d)
+        self.dummy_row = i32(n * max(ns, 1))  # sink for rows of components that are absent
+        if sim.t > 0:  # resuming mid-run: re-base the incremental paralysis census on the last logged row
+            self.cur_potp.copy_(dev.res["potentially_paralyzed"][sim.t - 1])
+            self.cur_p.copy_(dev.res["paralyzed"][sim.t - 1])
+        P = People()
+        for name in ("disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
+                     "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
+                     "daily_infectivity", "date_of_birth", "date_of_death"):
+            setattr(P, name, dp(c.get(name)))
+        P.tile_node = dp(self.tile_node)
+        P.capacity = cap
+        self.P = P
+
+    # ------------------------------------------------------------------ helpers
+    def rebuild_tiles(self, first_agent: int):
+        first_tile = first_agent // _lpk.TILE_AGENTS
+        check(_lpk.lib().lpk_build_tile_nodes(dp(self.dev.cols["node_id"]), C.c_int64(first_tile),
+                                              C.c_int64(self.sim.people.capacity), dp(self.tile_node), stream_handle()),
+              "lpk_build_tile_nodes")
+
+    def _sync_count(self):
+        """Births were appended on the host (unfused vital-dynamics tick): refresh the device counters and tile table."""
+        count = self.sim.people.count
+        if count != self._count_host:
+            self.rebuild_tiles(self._count_host)
+            self._count_host = count
+        self.counts.copy_(torch.tensor([count, count], dtype=torch.int64), non_blocking=False)
+
+    def _row(self, name, t):
+        r = self.dev.res.get(name)
+        return self.dummy_row if r is None else r[t]
+
+    def needs_components(self, t) -> bool:
+        sim = self.sim
+        vd = self.by_name.get("VitalDynamics_ABM")
+        if vd is not None and t % vd.step_size == 0:
+            return True
+        sia = self.by_name.get("SIA_ABM")
+        if sia is not None and sia._by_tick.get(t) and sim.pars.vx_prob_sia is not None:
+            return True
+        ds = self.by_name["DiseaseState_ABM"]
+        return t in ds.seed_schedule
+
+    # ------------------------------------------------------------------ pipeline
+    def drain(self):
+        """Apply the pending exposure trial and census of the last fused tick with the per-function kernels."""
+        if not self.pending:
+            return
+        sim, dev = self.sim, self.dev
+        t = sim.t - 1  # the tick the pending work belongs to
+        c, r = dev.cols, dev.res
+        n, ns, count = dev.n_nodes, dev.n_strains, self._count_host
+        K.tx_infect(n, count, ns, c["node_id"], c["strain"], c["disease_state"], c["acq_risk_multiplier"], self.q, self.cdf,
+                    rng=K.make_rng(sim.pars.seed, t, id_base=sim.id_base), out=dev.n_new)
+        r["new_exposed"][t] += dev.n_new.sum(dim=1, dtype=torch.int32)
+        r["new_exposed_by_strain"][t] += dev.n_new
+        self.by_name["Transmission_ABM"].log(t)
+        self.cur_potp.copy_(r["potentially_paralyzed"][t])
+        self.cur_p.copy_(r["paralyzed"][t])
+        self.pending = False
+
+    def after_component_tick(self, t):
+        """An unfused tick left nothing pending; re-base the incremental paralysis census on its full census."""
+        r = self.dev.res
+        self.cur_potp.copy_(r["potentially_paralyzed"][t])
+        self.cur_p.copy_(r["paralyzed"][t])
+        self._sync_count()
+
+    def fused_tick(self, t):
+        sim, dev, pars = self.sim, self.dev, self.sim.pars
+        n, ns = dev.n_nodes, dev.n_strains
+        tx = self.by_name["Transmission_ABM"]
+        ri = self.by_name.get("RI_ABM")
+        res = sim.results
+        flags = F_STAGES | (F_PENDING if self.pending else 0)
+        A = TickArgs()
+        A.tick, A.n_nodes, A.n_strains = t, n, ns
+        A.seed, A.id_base = int(pars.seed) & 0xFFFFFFFFFFFFFFFF, sim.id_base
+        A.counts = dp(self.counts)
+        A.q_prev, A.cdf_prev = dp(self.q), dp(self.cdf)
+        tp = max(t - 1, 0)
+        A.new_exposed_prev, A.new_exposed_by_strain_prev = dp(self._row("new_exposed", tp)), dp(self._row("new_exposed_by_strain", tp))
+        A.S_prev, A.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
+        A.E_by_strain_prev, A.I_by_strain_prev = dp(self._row("E_by_strain", tp)), dp(self._row("I_by_strain", tp))
+        A.p_paralysis = float(np.float32(pars.p_paralysis))
+        A.new_potential, A.new_paralyzed = dp(self._row("new_potentially_paralyzed", t)), dp(self._row("new_paralyzed", t))
+        A.deaths, A.dead_pp, A.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
+        if ri is not None and pars["vx_prob_ri"] is not None and t % ri.step_size == 0:
+            flags |= F_RI
+            p_ri, p_ipv = ri._probs(dev)
+            A.ri_step = int(ri.step_size)
+            A.ri_strain = 2 if "nOPV" in getattr(pars, "ri_vaccine_type", "tOPV") else 1
+            A.vx_prob_ri, A.vx_prob_ipv = dp(p_ri), dp(p_ipv)
+            A.ri_vaccinated, A.ri_protected = dp(self._row("ri_vaccinated", t)), dp(self._row("ri_protected", t))
+            A.ipv_vaccinated = dp(self._row("ipv_vaccinated", t))
+            A.new_exposed, A.new_exposed_by_strain = dp(self._row("new_exposed", t)), dp(self._row("new_exposed_by_strain", t))
+            A.ri_new_exposed_by_strain = dp(self._row("ri_new_exposed_by_strain", t))
+        for s, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
+            A.strain_r0_scalars[s] = float(v)
+        beta_fx, exposure_fx, sus = self.tally[t & 1]
+        if not self.pending:  # the previous tick was not fused, so nobody zeroed this parity
+            beta_fx.zero_(), exposure_fx.zero_(), sus.zero_()
+        A.beta_fx, A.exposure_fx, A.sus = dp(beta_fx), dp(exposure_fx), dp(sus)
+        A.flags = flags
+        K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
+
+        # host-side population row: a fused tick is never a vital-dynamics tick, so pop[t] = pop[t-1] (model.py:1694)
+        if "VitalDynamics_ABM" in self.by_name:
+            res.pop[t, :] = res.pop[t - 1, :]
+        N = NodeArgs()
+        N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
+        N.seed = A.seed
+        N.beta_fx, N.exposure_fx = dp(beta_fx), dp(exposure_fx)
+        N.network, N.r0_scalars = dp(dev.network_tensor(tx.network)), dp(tx._r0_scalars_dev(dev))
+        N.beta_seasonality = float(self._seasonality(t))
+        N.zero_inflation, N.dispersion = float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion)
+        N.q, N.strain_cdf, N.prob, N.expected, N.rowsum_ws = dp(self.q), dp(self.cdf), dp(self.prob), dp(self.expected), dp(self.rowsum)
+        N.pop_prev, N.pop = dp(dev.pop_tensor(res.pop[t])), None
+        N.deaths, N.dead_pp, N.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
+        N.cur_potp, N.cur_p = dp(self.cur_potp), dp(self.cur_p)
+        N.new_potential, N.new_paralyzed = A.new_potential, A.new_paralyzed
+        N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
+        N.E_by_strain_prev, N.I_by_strain_prev = A.E_by_strain_prev, A.I_by_strain_prev
+        N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
+        nb, ne, nsus = self.tally[(t + 1) & 1]
+        N.next_beta_fx, N.next_exposure_fx, N.next_sus = dp(nb), dp(ne), dp(nsus)
+        N.counts = dp(self.counts)
+        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 3)
+        self.pending = True
+
+    def _seasonality(self, t):
+        from . import utils
+
+        return utils.get_seasonality(self.sim)
+
+    def tick(self, t):
+        """Tick t >= 1 (tick 0 only logs, through the components)."""
+        sim = self.sim
+        if self.needs_components(t):
+            self.drain()
+            for component in sim.instances:
+                with sim.perf_stats.start(component.__class__.__name__ + ".step()"):
+                    component.step()
+            sim.log_results(t)
+            self.after_component_tick(t)
+        else:
+            with sim.perf_stats.start("FusedTick.step()"):
+                self.fused_tick(t)
+        sim.t += 1

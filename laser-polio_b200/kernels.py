@@ -155,6 +155,19 @@ class LaunchStats:
         self.calls = {}
         self.events = {}
 
+    def record(self, name, fn, n_kernels):
+        """Run ``fn`` (a liblpk launch), counting it and, when timing is on, bracketing it with CUDA events."""
+        self.launches += n_kernels
+        self.calls[name] = self.calls.get(name, 0) + 1
+        if not self.timing:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.events.setdefault(name, []).append((e0, e1))
+        return out
+
     def summary(self):
         """{name: (calls, mean_ms)}; synchronises the device."""
         torch.cuda.synchronize()

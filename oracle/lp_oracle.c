@@ -126,7 +126,7 @@ void orc_get_deaths(int32_t n_nodes, int64_t n_people, int8_t *state, const int1
 void orc_disease_state_step(const int16_t *node_id, int32_t n_nodes, int8_t *state, const int8_t *strain,
                             int64_t count, int8_t *etimer, int8_t *itimer, int8_t *pot_par, int8_t *paralyzed,
                             const int8_t *ipv, int8_t *ptimer, float p_paralysis, int32_t *new_potential,
-                            int32_t *new_paralyzed, const double *u_inj, uint64_t seed, uint32_t tick) {
+                            int32_t *new_paralyzed, const double *u_inj, uint64_t seed, uint32_t tick, uint64_t id_base) {
     int nt = omp_get_max_threads();
     int32_t *tl_pot = tl_alloc(nt, n_nodes), *tl_par = tl_alloc(nt, n_nodes);
     const double p = (double)p_paralysis;
@@ -147,7 +147,7 @@ void orc_disease_state_step(const int16_t *node_id, int32_t n_nodes, int8_t *sta
                         tl_pot[(int64_t)tid * n_nodes + node_id[i]] += 1;
                         double u;
                         if (u_inj) u = u_inj[i];
-                        else { uint32_t x[4]; agent_block(seed, (uint64_t)i, tick, ORC_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
+                        else { uint32_t x[4]; agent_block(seed, (uint64_t)i + id_base, tick, ORC_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
                         if (u < p) {
                             paralyzed[i] = 1;
                             tl_par[(int64_t)tid * n_nodes + node_id[i]] += 1;
@@ -173,7 +173,7 @@ void orc_fast_ri(int64_t step_size, const int16_t *node_id, int8_t *state, int8_
                  int16_t *ri_timer, int64_t sim_t, const double *prob_ri, const double *prob_ipv,
                  int64_t num_people, int32_t n_nodes, int32_t *ri_counts, int32_t *ri_protected,
                  int32_t *ipv_counts, const uint8_t *missed, int8_t vaccine_strain, const double *u1_inj,
-                 const double *u2_inj, uint64_t seed, uint32_t tick) {
+                 const double *u2_inj, uint64_t seed, uint32_t tick, uint64_t id_base) {
     int nt = omp_get_max_threads();
     int32_t *tl_ri = tl_alloc(nt, n_nodes), *tl_pr = tl_alloc(nt, n_nodes), *tl_ipv = tl_alloc(nt, n_nodes);
 #pragma omp parallel for schedule(static)
@@ -190,7 +190,7 @@ void orc_fast_ri(int64_t step_size, const int16_t *node_id, int8_t *state, int8_
         if (!eligible) continue;
         double u1, u2;
         if (u1_inj) { u1 = u1_inj[i]; u2 = u2_inj[i]; }
-        else { uint32_t x[4]; agent_block(seed, (uint64_t)i, tick, ORC_STAGE_RI, x); u1 = u53(x[0], x[1]); u2 = u53(x[2], x[3]); }
+        else { uint32_t x[4]; agent_block(seed, (uint64_t)i + id_base, tick, ORC_STAGE_RI, x); u1 = u53(x[0], x[1]); u2 = u53(x[2], x[3]); }
         int64_t row = (int64_t)omp_get_thread_num() * n_nodes + node;
         if (u1 < prob_ri[node]) {
             tl_ri[row] += 1;
@@ -212,7 +212,7 @@ void orc_fast_sia(const int16_t *node_id, int8_t *state, int8_t *strain, const i
                   const float *vx_prob, double vx_eff, int64_t count, const uint8_t *nodes_to_vaccinate,
                   int64_t min_age, int64_t max_age, int32_t n_nodes, int32_t *vaccinated, int32_t *protected_,
                   const uint8_t *missed, int8_t vaccine_strain, const double *u_inj, uint64_t seed,
-                  uint32_t tick, uint32_t event_idx) {
+                  uint32_t tick, uint32_t event_idx, uint64_t id_base) {
     int nt = omp_get_max_threads();
     int32_t *tl_v = tl_alloc(nt, n_nodes), *tl_p = tl_alloc(nt, n_nodes);
 #pragma omp parallel for schedule(static)
@@ -225,7 +225,7 @@ void orc_fast_sia(const int16_t *node_id, int8_t *state, int8_t *strain, const i
         if (nodes_to_vaccinate[node] == 0) continue;
         double r;
         if (u_inj) r = u_inj[i];
-        else { uint32_t x[4]; agent_block(seed, (uint64_t)i, tick, ORC_STAGE_SIA | (event_idx << 8), x); r = u53(x[0], x[1]); }
+        else { uint32_t x[4]; agent_block(seed, (uint64_t)i + id_base, tick, ORC_STAGE_SIA | (event_idx << 8), x); r = u53(x[0], x[1]); }
         double pv = (double)vx_prob[node];
         if (r < pv) {
             int64_t row = (int64_t)omp_get_thread_num() * n_nodes + node;
@@ -451,7 +451,8 @@ static inline uint32_t expose_threshold(float p, int *always) {
 void orc_tx_infect_bernoulli(int32_t n_nodes, int64_t n_people, int32_t n_strains, const int16_t *node_id,
                              int8_t *strain, int8_t *state, const float *risk, const float *q /*[nodes]*/,
                              const double *strain_cdf /*[nodes,strains] cumulative*/, int32_t *n_new,
-                             const uint32_t *x_inj, const double *u_strain_inj, uint64_t seed, uint32_t tick) {
+                             const uint32_t *x_inj, const double *u_strain_inj, uint64_t seed, uint32_t tick,
+                             uint64_t id_base) {
     int nt = omp_get_max_threads();
     int64_t nb = (int64_t)n_nodes * n_strains;
     int32_t *tl = tl_alloc(nt, nb);
@@ -466,11 +467,11 @@ void orc_tx_infect_bernoulli(int32_t n_nodes, int64_t n_people, int32_t n_strain
         uint32_t thr = expose_threshold(p, &always);
         uint32_t x;
         if (x_inj) x = x_inj[i];
-        else { uint32_t b[4]; agent_block(seed, (uint64_t)i >> 2, tick, ORC_STAGE_EXPOSE, b); x = b[i & 3]; }
+        else { uint32_t b[4]; agent_block(seed, ((uint64_t)i + id_base) >> 2, tick, ORC_STAGE_EXPOSE, b); x = b[(i + id_base) & 3]; }
         if (!(always || x < thr)) continue;
         double r;
         if (u_strain_inj) r = u_strain_inj[i];
-        else { uint32_t b[4]; agent_block(seed, (uint64_t)i, tick, ORC_STAGE_STRAIN, b); r = u53(b[0], b[1]); }
+        else { uint32_t b[4]; agent_block(seed, (uint64_t)i + id_base, tick, ORC_STAGE_STRAIN, b); r = u53(b[0], b[1]); }
         int32_t assigned = 0;
         for (int32_t s = 0; s < n_strains; ++s) if (r < strain_cdf[(int64_t)nid * n_strains + s]) { assigned = s; break; }
         state[i] = 1;

@@ -93,6 +93,7 @@ def get_deaths(num_nodes, num_people, disease_state, node_id, date_of_death, t, 
 def disease_state_step(
     node_id, n_nodes, disease_state, strain, active_count, exposure_timer, infection_timer, potentially_paralyzed,
     paralyzed, ipv_protected, paralysis_timer, p_paralysis, new_potential, new_paralyzed, u_inj=None, seed=0, tick=0,
+    id_base=0,
 ):
     """reference model.py:344-454"""
     lib().orc_disease_state_step(
@@ -100,13 +101,14 @@ def disease_state_step(
         C.c_int64(active_count), _p(exposure_timer, np.int8), _p(infection_timer, np.int8),
         _p(potentially_paralyzed, np.int8), _p(paralyzed, np.int8), _p(ipv_protected, np.int8),
         _p(paralysis_timer, np.int8), C.c_float(np.float32(p_paralysis)), _p(new_potential, np.int32),
-        _p(new_paralyzed, np.int32), _p(u_inj, np.float64), C.c_uint64(seed), C.c_uint32(tick),
+        _p(new_paralyzed, np.int32), _p(u_inj, np.float64), C.c_uint64(seed), C.c_uint32(tick), C.c_uint64(id_base),
     )
 
 
 def fast_ri(
     step_size, node_id, disease_state, strain, ipv_protected, ri_timer, sim_t, vx_prob_ri, vx_prob_ipv, num_people,
     ri_counts, ri_protected, ipv_counts, chronically_missed, ri_vaccine_strain, u1_inj=None, u2_inj=None, seed=0, tick=0,
+    id_base=0,
 ):
     """reference model.py:1805-1855; the three count outputs are per-node int32 (already thread-reduced)."""
     n_nodes = len(vx_prob_ri)
@@ -116,13 +118,13 @@ def fast_ri(
         _p(vx_prob_ipv, np.float64), C.c_int64(num_people), C.c_int32(n_nodes), _p(ri_counts, np.int32),
         _p(ri_protected, np.int32), _p(ipv_counts, np.int32), _p(chronically_missed, np.uint8),
         C.c_int8(int(ri_vaccine_strain)), _p(u1_inj, np.float64), _p(u2_inj, np.float64), C.c_uint64(seed),
-        C.c_uint32(tick),
+        C.c_uint32(tick), C.c_uint64(id_base),
     )
 
 
 def fast_sia(
     node_ids, disease_states, strain, dobs, sim_t, vx_prob, vx_eff, count, nodes_to_vaccinate, min_age, max_age,
-    vaccinated, protected, chronically_missed, sia_vaccine_strain, u_inj=None, seed=0, tick=0, event_idx=0,
+    vaccinated, protected, chronically_missed, sia_vaccine_strain, u_inj=None, seed=0, tick=0, event_idx=0, id_base=0,
 ):
     """reference model.py:1995-2060; vaccinated/protected are per-node int32 (already thread-reduced)."""
     n_nodes = len(vx_prob)
@@ -132,7 +134,7 @@ def fast_sia(
         _p(nodes_to_vaccinate, np.uint8), C.c_int64(min_age), C.c_int64(max_age), C.c_int32(n_nodes),
         _p(vaccinated, np.int32), _p(protected, np.int32), _p(chronically_missed, np.uint8),
         C.c_int8(int(sia_vaccine_strain)), _p(u_inj, np.float64), C.c_uint64(seed), C.c_uint32(tick),
-        C.c_uint32(event_idx),
+        C.c_uint32(event_idx), C.c_uint64(id_base),
     )
 
 
@@ -186,14 +188,14 @@ def tx_infect_ref(num_nodes, num_people, num_strains, sus_by_node, node_ids, str
 
 
 def tx_infect_bernoulli(num_nodes, num_people, num_strains, node_ids, strain, disease_state, risks, q, strain_cdf,
-                        x_inj=None, u_strain_inj=None, seed=0, tick=0):
+                        x_inj=None, u_strain_inj=None, seed=0, tick=0, id_base=0):
     """Device exposure scheme (option F1 + importation gate): see lp_oracle.c."""
     n_new = np.zeros((num_nodes, num_strains), np.int32)
     lib().orc_tx_infect_bernoulli(
         C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(num_strains), _p(node_ids, np.int16),
         _p(strain, np.int8), _p(disease_state, np.int8), _p(risks, np.float32), _p(q, np.float32),
         _p(strain_cdf, np.float64), _p(n_new), _p(x_inj, np.uint32), _p(u_strain_inj, np.float64),
-        C.c_uint64(seed), C.c_uint32(tick),
+        C.c_uint64(seed), C.c_uint32(tick), C.c_uint64(id_base),
     )
     return n_new
 

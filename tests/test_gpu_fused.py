@@ -1,0 +1,130 @@
+"""The fused tick (lpk_tick_pass + lpk_tick_node, engine.FusedEngine) must reproduce the component-by-component
+path bit for bit: every results array and every agent column, on schedules that mix fused days with days the
+engine hands back to the components (vital dynamics, SIA campaigns, seed_schedule injections, RI)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def lp():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import laser_polio_b200 as lp
+
+    return lp
+
+
+@pytest.fixture(scope="module")
+def pyramid(tmp_path_factory):
+    path = tmp_path_factory.mktemp("data") / "pyramid.csv"
+    rows = ["Age,M,F"] + [f"{5 * k}-{5 * k + 4},{int(1.7e7 * np.exp(-0.16 * k))},{int(1.6e7 * np.exp(-0.16 * k))}" for k in range(20)]
+    rows.append("100+,300,500")
+    path.write_text("\n".join(rows) + "\n")
+    return str(path)
+
+
+def make(lp, pyramid, fused, components, **over):
+    n_nodes = over.pop("n_nodes", 5)
+    rs = np.random.RandomState(3)
+    init_pop = rs.randint(3000, 30000, n_nodes)
+    d = rs.uniform(5, 300, (n_nodes, n_nodes))
+    d = (d + d.T) / 2
+    np.fill_diagonal(d, 0)
+    p = {
+        "start_date": lp.date("2019-01-01"), "dur": 45, "init_pop": init_pop, "cbr": np.full(n_nodes, 35.0),
+        "r0_scalars": rs.uniform(0.5, 1.5, n_nodes), "age_pyramid_path": pyramid, "init_immun": 0.3,
+        "init_prev": [0.01] + [0.0] * (n_nodes - 1), "r0": 14, "distances": d, "stop_if_no_cases": False, "verbose": 0, "seed": 99,
+        "vx_prob_ri": rs.uniform(0.3, 0.9, n_nodes), "vx_prob_ipv": rs.uniform(0.3, 0.9, n_nodes), "missed_frac": 0.1,
+        "p_paralysis": 0.3, "node_seeding_zero_inflation": 0.2, "node_seeding_dispersion": 2,
+        "sia_schedule": [
+            {"date": "2019-01-10", "nodes": [0, 2], "age_range": (0, 5 * 365), "vaccinetype": "nOPV2"},
+            {"date": "2019-01-10", "nodes": [1, 2, 3], "age_range": (0, 10 * 365), "vaccinetype": "mOPV2"},
+            {"date": "2019-01-29", "nodes": list(range(n_nodes)), "age_range": (0, 5 * 365), "vaccinetype": "mOPV2"},
+        ],
+        "vx_prob_sia": rs.uniform(0.4, 0.9, n_nodes).tolist(),
+        "seed_schedule": [{"timestep": 12, "node_id": 3, "prevalence": 40}, {"timestep": 28, "node_id": 1, "prevalence": 0.002}],
+    }
+    p.update(over)
+    sim = lp.SEIR_ABM(lp.PropertySet(p))
+    sim.components = components
+    sim.fused = fused
+    return sim
+
+
+def run_pair(lp, pyramid, components, **over):
+    out = []
+    for fused in (False, True):
+        sim = make(lp, pyramid, fused, components, **over)
+        sim.people.ri_timer[: sim.people.count : 3] = np.random.RandomState(1).randint(-10, 40, len(sim.people.ri_timer[: sim.people.count : 3])) \
+            if hasattr(sim.people, "ri_timer") else 0
+        from laser_polio_b200 import kernels as K
+
+        K.STATS.reset()
+        sim.run()
+        out.append((sim, dict(K.STATS.calls)))
+    return out
+
+
+def assert_identical(a, b):
+    for name, arr in a.results.__dict__.items():
+        if isinstance(arr, np.ndarray):
+            assert np.array_equal(arr, getattr(b.results, name)), f"results.{name}"
+    assert a.people.count == b.people.count
+    for name, col in a.people.columns().items():
+        assert np.array_equal(col, getattr(b.people, name)), f"people.{name}"
+
+
+def test_fused_equals_components_full_feature_set(lp, pyramid):
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    (ref, calls_ref), (fus, calls_fus) = run_pair(lp, pyramid, comps)
+    assert calls_fus.get("tick_pass", 0) >= 30 and "tick_pass" not in calls_ref  # the fused path really ran
+    assert_identical(ref, fus)
+    r = fus.results
+    assert r.new_exposed.sum() > 500 and r.ri_vaccinated.sum() > 0 and r.sia_protected.sum() > 0 and r.new_potentially_paralyzed.sum() > 0
+    assert r.births.sum() > 0 and r.deaths.sum() > 0
+    assert np.array_equal(r.E, r.E_by_strain.sum(axis=2)) and np.array_equal(r.I, r.I_by_strain.sum(axis=2))
+    # incremental paralysis census == cumulative new minus the dead (cross-check against the agent table)
+    alive = fus.people.disease_state[: fus.people.count] >= 0
+    assert r.potentially_paralyzed[-1].sum() == np.sum((fus.people.potentially_paralyzed[: fus.people.count] == 1) & alive)
+    assert r.paralyzed[-1].sum() == np.sum((fus.people.paralyzed[: fus.people.count] == 1) & alive)
+
+
+def test_fused_equals_components_transmission_only_many_nodes(lp, pyramid):
+    # no vital dynamics: every tick after 0 is fused; pop[t] stays 0 so the rate denominator is max(0, 1) like the reference
+    comps = [lp.DiseaseState_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, n_nodes=40, dur=30, sia_schedule=None, seed_schedule=None, vx_prob_ri=None,
+                                      r0=0.002)
+    assert calls.get("tick_pass", 0) == 30
+    assert_identical(ref, fus)
+    assert fus.results.new_exposed.sum() > 100
+
+
+def test_fused_equals_components_ri_without_vd_or_sia(lp, pyramid):
+    comps = [lp.DiseaseState_ABM, lp.RI_ABM, lp.Transmission_ABM, lp.VitalDynamics_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, sia_schedule=None, seed_schedule=None, step_size_VitalDynamics_ABM=30,
+                                      cbr=np.zeros(5))
+    assert calls.get("tick_pass", 0) >= 40
+    assert_identical(ref, fus)
+    assert fus.results.ri_vaccinated.sum() > 0
+
+
+def test_step_tick_resume_after_to_host(lp, pyramid):
+    """to_host() mid-run drains the pipeline; resuming gives the same answer as one uninterrupted run."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    whole = make(lp, pyramid, True, comps)
+    whole.run()
+    parts = make(lp, pyramid, True, comps)
+    for t in range(0, 20):
+        parts.step_tick(t)
+    parts.to_host()
+    snapshot = parts.results.S[19].copy()
+    for t in range(20, parts.nt):
+        parts.step_tick(t)
+    parts.to_host()
+    assert np.array_equal(snapshot, whole.results.S[19])
+    assert_identical(whole, parts)

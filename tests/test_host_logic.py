@@ -186,3 +186,24 @@ def test_distributions(lp):
     u = lp.uniform(min=2, max=10)(10000)
     assert u.min() == 2 and u.max() == 9
     assert lp.exponential(scale=2.0)(10).shape == (10,)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The fused-tick argument structs are filled from Python: their layout must equal the C compiler's."""
+    import subprocess
+
+    from laser_polio_b200 import _lpk
+
+    src = tmp_path / "sz.cpp"
+    src.write_text(
+        '#include <cstdio>\n#include <cstddef>\n#include "lpk.h"\nint main(){'
+        'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lpk_rng), sizeof(lpk_people), sizeof(lpk_tick_args), sizeof(lpk_node_args),'
+        "offsetof(lpk_tick_args, strain_r0_scalars), offsetof(lpk_tick_args, ri_step), offsetof(lpk_node_args, counts),"
+        "offsetof(lpk_people, capacity));}\n"
+    )
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/g++", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(_lpk.Rng), ctypes.sizeof(_lpk.People), ctypes.sizeof(_lpk.TickArgs), ctypes.sizeof(_lpk.NodeArgs),
+            _lpk.TickArgs.strain_r0_scalars.offset, _lpk.TickArgs.ri_step.offset, _lpk.NodeArgs.counts.offset, _lpk.People.capacity.offset]
+    assert got == want
