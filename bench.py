@@ -42,6 +42,8 @@ ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I a
 # algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
 # (f_S = 0.93, f_E = f_I = 0.01 synthetic mix; derivations in DESIGN.md section 4)
 KERNEL_BYTES = {
+    "tick_pass": ALGO_BYTES_PER_AGENT_TICK,                # fused day: SURVEY 8(d) daily figure (pass A of t + pass B of t-1)
+    "tick_node": 0.0,                                      # node-level epilogue + node math: no per-agent traffic
     "tx_step_prep": 1 + 2 + 4 * 0.93 + 5 * 0.01,          # state, node_id, risk (S), infectivity + strain (I)
     "tx_infect": 1 + 2 + 4 * 0.93,                         # state, node_id, risk (S)
     "count_SEIRP": 1 + 2 + 1 + 1 + 0.02,                   # state, node_id, potentially_paralyzed, paralyzed, strain (E/I)
