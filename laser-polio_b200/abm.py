@@ -157,9 +157,9 @@ class SEIR_ABM:
     def to_host(self):
         """Finish any pipelined work, D2H the agent columns and results into the host arrays (in place), drop the device copy."""
         if self.dev is not None:
-            if self._engine is not None:
+            if self._engine:  # None: never started, False: components only
                 self._engine.drain()
-                self._engine = None
+            self._engine = None
             self.dev.download()
             self.io_bytes = (self.dev.h2d_bytes, self.dev.d2h_bytes)
             self.dev = None

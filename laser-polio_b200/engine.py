@@ -81,8 +81,8 @@ class FusedEngine:
     # ------------------------------------------------------------------ helpers
     def rebuild_tiles(self, first_agent: int):
         first_tile = first_agent // _lpk.TILE_AGENTS
-        check(_lpk.lib().lpk_build_tile_nodes(dp(self.dev.cols["node_id"]), C.c_int64(first_tile),
-                                              C.c_int64(self.sim.people.capacity), dp(self.tile_node), stream_handle()),
+        check(_lpk.lib().lpk_build_tile_nodes(_lpk.ptr(self.dev.cols["node_id"]), C.c_int64(first_tile),
+                                              C.c_int64(self.sim.people.capacity), _lpk.ptr(self.tile_node), stream_handle()),
               "lpk_build_tile_nodes")
 
     def _sync_count(self):
