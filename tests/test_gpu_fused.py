@@ -60,8 +60,9 @@ def run_pair(lp, pyramid, components, **over):
     out = []
     for fused in (False, True):
         sim = make(lp, pyramid, fused, components, **over)
-        sim.people.ri_timer[: sim.people.count : 3] = np.random.RandomState(1).randint(-10, 40, len(sim.people.ri_timer[: sim.people.count : 3])) \
-            if hasattr(sim.people, "ri_timer") else 0
+        if hasattr(sim.people, "ri_timer"):
+            k = len(sim.people.ri_timer[: sim.people.count : 3])
+            sim.people.ri_timer[: sim.people.count : 3] = np.random.RandomState(1).randint(-10, 40, k)
         from laser_polio_b200 import kernels as K
 
         K.STATS.reset()
