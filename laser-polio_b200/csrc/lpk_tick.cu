@@ -20,22 +20,38 @@ struct PassParams {
     lpk_tick_args A;
 };
 
-// accumulator slots
-enum { CI_S = 0, CI_R = 1, CI_E = 2, CI_I = 2 + LPK_MAX_STRAINS, CI_NEW = 2 + 2 * LPK_MAX_STRAINS, CI_SUS = 2 + 3 * LPK_MAX_STRAINS, CI_N };
-enum { CL_EXPO = 0, CL_BETA = 1, CL_N = 1 + LPK_MAX_STRAINS };
+// per-node partial sums a lane keeps in registers (everything else is rare and goes straight to atomics)
+enum { CI_S = 0, CI_R = 1, CI_SUS = 2, CI_N = 3 };
+enum { CL_EXPO = 0, CL_N = 1 };
 typedef NodeAcc<CI_N, CL_N> TickAcc;
 
-// ------------------------------------------------------------------ rare paths (out of line)
-__device__ __noinline__ int pick_strain(const PassParams &pp, int64_t i, int nd) {
+// ------------------------------------------------------------------ rare paths (out of line, direct atomics)
+__device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
+    DevRng rng;
+    rng.seed = pp.A.seed; rng.tick = (uint32_t)pp.A.tick; rng.u1 = nullptr; rng.u2 = nullptr; rng.x = nullptr;
+    rng.id_base = pp.A.id_base;
+    return rng;
+}
+
+// an exposure hit of tick t-1: categorical strain pick (model.py:1127-1141), bookkeeping rows t-1
+__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
+    const lpk_tick_args &A = pp.A;
     uint32_t y[4];
-    philox_agent(pp.A.seed, (uint64_t)i + pp.A.id_base, (uint32_t)(pp.A.tick - 1), LPK_STAGE_STRAIN, y);
+    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
     const double r = u53(y[0], y[1]);
-    const int ns = pp.A.n_strains;
+    const int ns = A.n_strains;
     int assigned = 0;
     for (int s = 0; s < ns; ++s)
-        if (r < pp.A.cdf_prev[(int64_t)nd * ns + s]) { assigned = s; break; }
+        if (r < A.cdf_prev[(int64_t)nd * ns + s]) { assigned = s; break; }
     pp.P.strain[i] = (int8_t)assigned;
-    return assigned;
+    atomicAdd(&A.new_exposed_prev[nd], 1);
+    atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
+}
+
+// census of one E or I agent (rows t-1)
+__device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, int8_t s) {
+    const int64_t c = (int64_t)nd * pp.A.n_strains + pp.P.strain[i];
+    atomicAdd(s == 1 ? &pp.A.E_by_strain_prev[c] : &pp.A.I_by_strain_prev[c], 1);
 }
 
 __device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd) {
@@ -45,21 +61,16 @@ __device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd)
 }
 
 __device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8_t s) {
-    DevRng rng;
-    rng.seed = pp.A.seed; rng.tick = (uint32_t)pp.A.tick; rng.u1 = nullptr; rng.u2 = nullptr; rng.x = nullptr;
-    rng.id_base = pp.A.id_base;
     const lpk_people &P = pp.P;
     return ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
-                    P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed, rng);
+                    P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed,
+                    stage_rng(pp));
 }
 
-// census / tally contribution of one E or I agent: returns its strain
-__device__ __noinline__ int strain_of(const PassParams &pp, int64_t i) { return pp.P.strain[i]; }
-
-__device__ __noinline__ long long infectious_fx(const PassParams &pp, int64_t i, int *strain_out) {
+// infectivity tally of one infectious agent (tick t)
+__device__ __noinline__ void tally_infectious(const PassParams &pp, int64_t i, int nd) {
     const int s = pp.P.strain[i];
-    *strain_out = s;
-    return to_fx((double)pp.P.daily_infectivity[i] * pp.A.strain_r0_scalars[s]);
+    red_add(&pp.A.beta_fx[(int64_t)nd * pp.A.n_strains + s], to_fx((double)pp.P.daily_infectivity[i] * pp.A.strain_r0_scalars[s]));
 }
 
 // routine immunisation for one quad (reference model.py:1825-1854); returns the new state word
@@ -73,7 +84,7 @@ __device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int
     int tm[4];
     load_s4(P.ri_timer, base, valid, tm);
     bool touched = false;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int8_t s = byte_of(w, k);
         if (s < 0 || byte_of(m, k) == 1) continue;
@@ -108,190 +119,202 @@ __device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int
     return w;
 }
 
-__device__ __forceinline__ void acc_add_strain(TickAcc &acc, int slot0, int strain, int v) {
-#pragma unroll
-    for (int q = 0; q < LPK_MAX_STRAINS; ++q) acc.ci[slot0 + q] += (q == strain) ? v : 0;
+// Generic quad: mixed node ids, the table's tail, or agents born after tick t-1's transmission.  One agent at a
+// time with direct atomics; reached for a few quads per node boundary, so its cost is irrelevant.
+__device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int valid, uint32_t w, bool deaths, bool ri,
+                                           int64_t count_prev) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    uint32_t nw = w;
+    uint32_t x[4] = {0u, 0u, 0u, 0u};
+    if (pending) philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE, x);
+#pragma unroll 1
+    for (int k = 0; k < valid; ++k) {
+        int8_t s = byte_of(nw, k);
+        if (s < 0) continue;
+        const int64_t i = b + k;
+        const int nd = P.node_id[i];
+        if (pending && i < count_prev) {
+            if (s == 0) {
+                const float q = A.q_prev[nd];
+                if (q > 0.f && expose_hit(__fmul_rn(P.acq_risk_multiplier[i], q), x[k])) { expose_agent(pp, i, nd); s = 1; }
+            }
+            if (s == 0) atomicAdd(&A.S_prev[nd], 1);
+            else if (s == 3) atomicAdd(&A.R_prev[nd], 1);
+            else census_ei(pp, i, nd, s);
+        }
+        if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd); s = -1; }
+        if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s);
+        nw = set_byte(nw, k, s);
+    }
+    if (ri) nw = ri_quad(pp, b, valid, nw);
+#pragma unroll 1
+    for (int k = 0; k < valid; ++k) {
+        const int8_t s = byte_of(nw, k);
+        const int64_t i = b + k;
+        if (s == 0) {
+            const int nd = P.node_id[i];
+            atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), 1ull);
+            red_add(&A.exposure_fx[nd], __float2ll_rn(P.acq_risk_multiplier[i] * 1073741824.0f));
+        } else if (s == 2) {
+            tally_infectious(pp, i, P.node_id[i]);
+        }
+    }
+    return nw;
 }
 
 // ------------------------------------------------------------------ the pass
+// A warp walks its rows of 128 agents (one quad per lane).  Software pipeline: the state word of row r+2, and the
+// risk / node / date_of_death words of row r+1 (predicated on its state, which arrived an iteration ago), are in
+// flight while row r is processed.
+struct RowData {
+    uint32_t w;      // 4 state bytes
+    float4 rk;       // acq_risk_multiplier of the quad (if it has a susceptible)
+    uint2 nd;        // 4 node ids (only when the tile is not node-uniform)
+    int4 dd;         // date_of_death (vital-dynamics ticks only)
+    int tn;          // tile's node or -1
+};
+
+template <bool kDeaths>
+__device__ __forceinline__ void issue_row_loads(const lpk_people &P, int64_t row, int lane, int64_t n, uint32_t w, RowData &d) {
+    const int64_t b = (row * 32 + lane) * 4;
+    d.w = w;
+    d.tn = P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
+    const bool full = b + 4 <= n;
+    const bool alive = (w & 0x80808080u) != 0x80808080u;
+    d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
+    d.nd = make_uint2(0u, 0u);
+    if (full && alive) {
+        if (any_byte_eq(w, 0u)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
+        if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
+        if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
+    }
+}
+
+__device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t row, int lane, int64_t n) {
+    const int64_t b = (row * 32 + lane) * 4;
+    const int v = quad_valid(b, n);
+    return v ? load_b4(P.disease_state, b, v) : 0xFFFFFFFFu;
+}
+
 template <bool kDeaths, bool kRI>
-__global__ void __launch_bounds__(LPK_BLOCK, 2) k_tick_pass(const __grid_constant__ PassParams pp) {
+__global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t count_prev = A.counts[0], n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    const int ns = A.n_strains;
     const int tick = A.tick;
-    const TileRange tr = block_tiles(n);
+    // rows of 128 agents; blocks own contiguous row ranges, warps interleave inside
+    const int64_t rows = (n + 127) >> 7;
+    const int64_t lo = rows * (int64_t)blockIdx.x / gridDim.x, hi = rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
 
     TickAcc acc;
     acc.init();
     auto flush = [&](int nd, const int *ci, const long long *cl) {
         red_add(&A.S_prev[nd], ci[CI_S]);
         red_add(&A.R_prev[nd], ci[CI_R]);
-        int tot_new = 0;
-#pragma unroll
-        for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
-            if (s < ns) {
-                const int64_t c = (int64_t)nd * ns + s;
-                red_add(&A.E_by_strain_prev[c], ci[CI_E + s]);
-                red_add(&A.I_by_strain_prev[c], ci[CI_I + s]);
-                red_add(&A.new_exposed_by_strain_prev[c], ci[CI_NEW + s]);
-                red_add(&A.beta_fx[c], cl[CL_BETA + s]);
-                tot_new += ci[CI_NEW + s];
-            }
-        }
-        red_add(&A.new_exposed_prev[nd], tot_new);
         if (ci[CI_SUS]) atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)ci[CI_SUS]);
         red_add(&A.exposure_fx[nd], cl[CL_EXPO]);
     };
 
-    int64_t tile = tr.lo + warp;
-    uint32_t wn[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (tile < tr.hi) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t b = quad_base(tile, j, lane);
-            const int v = quad_valid(b, n);
-            if (v) wn[j] = load_b4(P.disease_state, b, v);
-        }
+    int64_t row = lo + warp;
+    RowData cur, nxt;
+    uint32_t w2 = 0xFFFFFFFFu;  // state word two rows ahead
+    cur.w = 0xFFFFFFFFu;
+    if (row < hi) {
+        issue_row_loads<kDeaths>(P, row, lane, n, load_state_row(P, row, lane, n), cur);
+        if (row + LPK_WARPS < hi) w2 = load_state_row(P, row + LPK_WARPS, lane, n);
     }
-    for (; tile < tr.hi; tile += LPK_WARPS) {
-        uint32_t w[4];
-        int64_t base[4];
-        int valid[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            w[j] = wn[j];
-            base[j] = quad_base(tile, j, lane);
-            valid[j] = quad_valid(base[j], n);
-        }
-        // ---- issue every load of this tile (and the next tile's state words) before consuming any
-        const int64_t next = tile + LPK_WARPS;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            wn[j] = 0xFFFFFFFFu;
-            if (next < tr.hi) {
-                const int64_t b = quad_base(next, j, lane);
-                const int v = quad_valid(b, n);
-                if (v) wn[j] = load_b4(P.disease_state, b, v);
+#pragma unroll 1
+    for (; row < hi; row += LPK_WARPS) {
+        // ---- keep the pipeline full
+        const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
+        nxt.w = 0xFFFFFFFFu;
+        if (r1 < hi) issue_row_loads<kDeaths>(P, r1, lane, n, w2, nxt);
+        w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
+
+        // ---- row `row`
+        const uint32_t w = cur.w;
+        const int64_t b = (row * 32 + lane) * 4;
+        if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
+            const int valid = quad_valid(b, n);
+            int nd = cur.tn;
+            bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
+            if (nd < 0) {
+                nd = (int)(int16_t)(cur.nd.x & 0xFFFFu);
+                fast = fast && cur.nd.x == cur.nd.y && (cur.nd.x >> 16) == (cur.nd.x & 0xFFFFu) && nd >= 0;
             }
-        }
-        const int tn = P.tile_node ? __ldg(&P.tile_node[tile]) : -1;
-        float rk[4][4];
-        bool hasS[4];
-        uint2 ndraw[4];
-        int4 dd[4];
+            uint32_t nw;
+            if (!fast) {
+                nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
+            } else {
+                nw = w;
+                acc.select(nd, flush);
+                const float rk[4] = {cur.rk.x, cur.rk.y, cur.rk.z, cur.rk.w};
+                if (pending) {
+                    // exposure trial of tick t-1
+                    const uint32_t mS = __vcmpeq4(w, 0u);
+                    if (mS) {
+                        const float q = __ldg(&A.q_prev[nd]);
+                        if (q > 0.f) {
+                            uint32_t x[4];
+                            philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            hasS[j] = valid[j] && any_byte_eq(w[j], 0u);
-            if (hasS[j]) load_f4(P.acq_risk_multiplier, base[j], valid[j], rk[j]);
-            else { rk[j][0] = rk[j][1] = rk[j][2] = rk[j][3] = 0.f; }
-            const bool alive = valid[j] && (w[j] & 0x80808080u) != 0x80808080u;
-            ndraw[j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-            if (tn < 0 && alive) {
-                if (valid[j] == 4) ndraw[j] = *reinterpret_cast<const uint2 *>(P.node_id + base[j]);
-                else {
-                    int t4[4];
-                    load_s4(P.node_id, base[j], valid[j], t4);
-                    ndraw[j] = make_uint2(((uint32_t)t4[0] & 0xFFFFu) | ((uint32_t)t4[1] << 16), ((uint32_t)t4[2] & 0xFFFFu) | ((uint32_t)t4[3] << 16));
-                }
-            }
-            if (kDeaths) {
-                dd[j] = make_int4(0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF);
-                if (alive) {
-                    int t4[4];
-                    load_i4(P.date_of_death, base[j], valid[j], t4);
-                    dd[j] = make_int4(t4[0], t4[1], t4[2], t4[3]);
-                }
-            }
-        }
-        // ---- consume, quad by quad
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t wj = w[j];
-            if (valid[j] == 0 || (wj & 0x80808080u) == 0x80808080u) continue;  // nobody alive here
-            const int64_t b = base[j];
-            int nq[4];
-            if (tn >= 0) { nq[0] = nq[1] = nq[2] = nq[3] = tn; }
-            else {
-                nq[0] = (int)(int16_t)(ndraw[j].x & 0xFFFFu); nq[1] = (int)(int16_t)(ndraw[j].x >> 16);
-                nq[2] = (int)(int16_t)(ndraw[j].y & 0xFFFFu); nq[3] = (int)(int16_t)(ndraw[j].y >> 16);
-            }
-            uint32_t nw = wj;
-            if (pending) {
-                // exposure trial of tick t-1 for the susceptibles that existed then
-                if (hasS[j]) {
-                    float qv[4];
-                    bool live = false;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        qv[k] = (byte_of(wj, k) == 0 && b + k < count_prev) ? __ldg(&A.q_prev[nq[k]]) : 0.f;
-                        live |= qv[k] > 0.f;
-                    }
-                    if (live) {
-                        uint32_t x[4];
-                        philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (qv[k] > 0.f && expose_hit(__fmul_rn(rk[j][k], qv[k]), x[k])) {
-                                const int s = pick_strain(pp, b + k, nq[k]);
-                                nw = set_byte(nw, k, 1);
-                                acc.select(nq[k], flush);
-                                acc_add_strain(acc, CI_NEW, s, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                if (((mS >> (8 * k)) & 1u) && expose_hit(__fmul_rn(rk[k], q), x[k])) {
+                                    expose_agent(pp, b + k, nd);
+                                    nw = set_byte(nw, k, 1);
+                                }
                             }
                         }
                     }
-                }
-                // census of tick t-1 on the post-exposure state
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int8_t s = byte_of(nw, k);
-                    if (s < 0 || b + k >= count_prev) continue;
-                    acc.select(nq[k], flush);
-                    acc.ci[CI_S] += (s == 0);
-                    acc.ci[CI_R] += (s == 3);
-                    if (s == 1 || s == 2) acc_add_strain(acc, s == 1 ? CI_E : CI_I, strain_of(pp, b + k), 1);
-                }
-            }
-            // ---- tick t
-            if (kDeaths) {
-                const int dq[4] = {dd[j].x, dd[j].y, dd[j].z, dd[j].w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
-                        kill_agent(pp, b + k, nq[k]);
-                        nw = set_byte(nw, k, -1);
+                    // census of tick t-1 on the post-exposure state
+                    acc.ci[CI_S] += __popc(__vcmpeq4(nw, 0u)) >> 3;
+                    acc.ci[CI_R] += __popc(__vcmpeq4(nw, 0x03030303u)) >> 3;
+                    if (__vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u)) {
+#pragma unroll 1
+                        for (int k = 0; k < 4; ++k) {
+                            const int8_t s = byte_of(nw, k);
+                            if (s == 1 || s == 2) census_ei(pp, b + k, nd, s);
+                        }
                     }
                 }
-            }
-            if (any_byte_eq(nw, 1u) || any_byte_eq(nw, 2u)) {
+                // ---- tick t
+                if (kDeaths) {
+                    const int dq[4] = {cur.dd.x, cur.dd.y, cur.dd.z, cur.dd.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int8_t s = byte_of(nw, k);
-                    if (s == 1 || s == 2) nw = set_byte(nw, k, ds_agent_ol(pp, b + k, s));
+                    for (int k = 0; k < 4; ++k) {
+                        if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
+                            kill_agent(pp, b + k, nd);
+                            nw = set_byte(nw, k, -1);
+                        }
+                    }
+                }
+                if (__vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u)) {
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        const int8_t s = byte_of(nw, k);
+                        if (s == 1 || s == 2) nw = set_byte(nw, k, ds_agent_ol(pp, b + k, s));
+                    }
+                }
+                if (kRI) nw = ri_quad(pp, b, 4, nw);
+                // tally of tick t
+                const uint32_t mS2 = __vcmpeq4(nw, 0u);
+                acc.ci[CI_SUS] += __popc(mS2) >> 3;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc.cl[CL_EXPO] += ((mS2 >> (8 * k)) & 1u) ? __float2ll_rn(rk[k] * 1073741824.0f) : 0ll;
+                if (__vcmpeq4(nw, 0x02020202u)) {
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k)
+                        if (byte_of(nw, k) == 2) tally_infectious(pp, b + k, nd);
                 }
             }
-            if (kRI) nw = ri_quad(pp, b, valid[j], nw);
-            // tally of tick t
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int8_t s = byte_of(nw, k);
-                if (s == 0) {
-                    acc.select(nq[k], flush);
-                    acc.ci[CI_SUS] += 1;
-                    acc.cl[CL_EXPO] += __float2ll_rn(rk[j][k] * 1073741824.0f);
-                } else if (s == 2) {
-                    acc.select(nq[k], flush);
-                    int st;
-                    const long long fx = infectious_fx(pp, b + k, &st);
-#pragma unroll
-                    for (int q = 0; q < LPK_MAX_STRAINS; ++q) acc.cl[CL_BETA + q] += (q == st) ? fx : 0ll;
-                }
-            }
-            if (nw != wj) store_b4(P.disease_state, b, valid[j], nw);
+            if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
+        cur = nxt;
     }
     acc.finish_warp(flush);
 }
@@ -319,7 +342,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     PassParams pp;
     pp.P = P;
     pp.A = A;
-    const int grid = lpk_agent_grid(P.capacity, 2);
+    const int grid = lpk_agent_grid(P.capacity, 3);
     cudaStream_t st = as_stream(stream);
     if (deaths && ri) k_tick_pass<true, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
     else if (deaths) k_tick_pass<true, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
