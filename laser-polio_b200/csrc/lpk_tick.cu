@@ -198,17 +198,66 @@ __device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t 
     return v ? load_b4(P.disease_state, b, v) : 0xFFFFFFFFu;
 }
 
+// ---- active-agent queue -------------------------------------------------------------------------------------
+// E / I agents (and fresh exposure hits) are ~2 % of the table but sit in ~90 % of the 128-agent rows, so handling
+// them where they are found makes every warp walk the long disease-state path with one or two live lanes
+// (profiles/r1_fused2_*: 280 thread-instructions per agent, issue-bound).  Instead each warp appends them to a small
+// shared-memory ring and, whenever 32 have accumulated, processes them one per lane with all lanes busy.
+// An entry carries everything the handler needs; the handler owns the agent's state byte from then on (the owning
+// lane already stored the quad's word; both stores come from the same warp, ordered by __syncwarp()).
+#define QCAP 64
+__device__ __forceinline__ unsigned long long q_pack(int64_t i, int nd, int8_t s, bool hit) {
+    return (unsigned long long)i | ((unsigned long long)(uint16_t)nd << 40) | ((unsigned long long)(uint8_t)s << 56) |
+           ((unsigned long long)(hit ? 1 : 0) << 60);
+}
+
+// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent
+__device__ __noinline__ void active_agent(const PassParams &pp, unsigned long long e) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int64_t i = (int64_t)(e & 0xFFFFFFFFFFull);
+    const int nd = (int)(int16_t)((e >> 40) & 0xFFFFu);
+    int8_t s = (int8_t)((e >> 56) & 0xFu);
+    const int ns = A.n_strains;
+    if ((e >> 60) & 1ull) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
+        uint32_t y[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
+        const double r = u53(y[0], y[1]);
+        int assigned = 0;
+        for (int k = 0; k < ns; ++k)
+            if (r < A.cdf_prev[(int64_t)nd * ns + k]) { assigned = k; break; }
+        P.strain[i] = (int8_t)assigned;
+        atomicAdd(&A.new_exposed_prev[nd], 1);
+        atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
+    }
+    if (A.flags & LPK_F_PENDING) {
+        const int64_t c = (int64_t)nd * ns + P.strain[i];
+        atomicAdd(s == 1 ? &A.E_by_strain_prev[c] : &A.I_by_strain_prev[c], 1);
+    }
+    const int8_t s2 = ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
+                               P.ipv_protected, P.paralysis_timer, (double)A.p_paralysis, A.new_potential, A.new_paralyzed, stage_rng(pp));
+    if (s2 != s) P.disease_state[i] = s2;
+    if (s2 == 2) {
+        const int st = P.strain[i];
+        red_add(&A.beta_fx[(int64_t)nd * ns + st], to_fx((double)P.daily_infectivity[i] * A.strain_r0_scalars[st]));
+    }
+}
+
 template <bool kDeaths, bool kRI>
 __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
+    __shared__ unsigned long long queue[LPK_WARPS][QCAP];
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const int64_t count_prev = A.counts[0], n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick;
     // rows of 128 agents; blocks own contiguous row ranges, warps interleave inside
     const int64_t rows = (n + 127) >> 7;
     const int64_t lo = rows * (int64_t)blockIdx.x / gridDim.x, hi = rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    unsigned long long *q = queue[warp];
+    int q_head = 0, q_count = 0;  // warp-uniform
 
     TickAcc acc;
     acc.init();
@@ -238,48 +287,40 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         // ---- row `row`
         const uint32_t w = cur.w;
         const int64_t b = (row * 32 + lane) * 4;
+        uint32_t cand = 0u, hits = 0u, nw = w;  // cand/hits: bit k = agent k of the quad goes to the active queue
+        int nd = cur.tn;
         if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
             const int valid = quad_valid(b, n);
-            int nd = cur.tn;
             bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
             if (nd < 0) {
                 nd = (int)(int16_t)(cur.nd.x & 0xFFFFu);
                 fast = fast && cur.nd.x == cur.nd.y && (cur.nd.x >> 16) == (cur.nd.x & 0xFFFFu) && nd >= 0;
             }
-            uint32_t nw;
             if (!fast) {
                 nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
             } else {
-                nw = w;
                 acc.select(nd, flush);
                 const float rk[4] = {cur.rk.x, cur.rk.y, cur.rk.z, cur.rk.w};
                 if (pending) {
                     // exposure trial of tick t-1
                     const uint32_t mS = __vcmpeq4(w, 0u);
                     if (mS) {
-                        const float q = __ldg(&A.q_prev[nd]);
-                        if (q > 0.f) {
+                        const float qn = __ldg(&A.q_prev[nd]);
+                        if (qn > 0.f) {
                             uint32_t x[4];
                             philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (((mS >> (8 * k)) & 1u) && expose_hit(__fmul_rn(rk[k], q), x[k])) {
-                                    expose_agent(pp, b + k, nd);
+                                if (((mS >> (8 * k)) & 1u) && expose_hit(__fmul_rn(rk[k], qn), x[k])) {
+                                    hits |= 1u << k;
                                     nw = set_byte(nw, k, 1);
                                 }
                             }
                         }
                     }
-                    // census of tick t-1 on the post-exposure state
+                    // census of tick t-1 on the post-exposure state (E / I agents are counted by the queue handler)
                     acc.ci[CI_S] += __popc(__vcmpeq4(nw, 0u)) >> 3;
                     acc.ci[CI_R] += __popc(__vcmpeq4(nw, 0x03030303u)) >> 3;
-                    if (__vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u)) {
-#pragma unroll 1
-                        for (int k = 0; k < 4; ++k) {
-                            const int8_t s = byte_of(nw, k);
-                            if (s == 1 || s == 2) census_ei(pp, b + k, nd, s);
-                        }
-                    }
                 }
                 // ---- tick t
                 if (kDeaths) {
@@ -287,35 +328,48 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
+                            if ((hits >> k) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << k); }
+                            if (pending && (byte_of(nw, k) == 1 || byte_of(nw, k) == 2)) census_ei(pp, b + k, nd, byte_of(nw, k));
                             kill_agent(pp, b + k, nd);
                             nw = set_byte(nw, k, -1);
                         }
                     }
                 }
-                if (__vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u)) {
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {
-                        const int8_t s = byte_of(nw, k);
-                        if (s == 1 || s == 2) nw = set_byte(nw, k, ds_agent_ol(pp, b + k, s));
-                    }
-                }
+                const uint32_t mEI = __vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u);
+                cand = (mEI & 1u) | ((mEI >> 7) & 2u) | ((mEI >> 14) & 4u) | ((mEI >> 21) & 8u);
                 if (kRI) nw = ri_quad(pp, b, 4, nw);
-                // tally of tick t
+                // tally of tick t (susceptibles here, infectious agents in the queue handler)
                 const uint32_t mS2 = __vcmpeq4(nw, 0u);
                 acc.ci[CI_SUS] += __popc(mS2) >> 3;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     acc.cl[CL_EXPO] += ((mS2 >> (8 * k)) & 1u) ? __float2ll_rn(rk[k] * 1073741824.0f) : 0ll;
-                if (__vcmpeq4(nw, 0x02020202u)) {
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k)
-                        if (byte_of(nw, k) == 2) tally_infectious(pp, b + k, nd);
-                }
             }
             if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
+        // ---- append this row's active agents to the warp's ring; drain it 32 at a time (warp-uniform control flow)
+        if (__any_sync(LPK_FULL, cand != 0u)) {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const bool mine = (cand >> k) & 1u;
+                const uint32_t m = __ballot_sync(LPK_FULL, mine);
+                if (m == 0u) continue;
+                if (mine) q[(q_head + q_count + __popc(m & lt_mask)) & (QCAP - 1)] = q_pack(b + k, nd, byte_of(nw, k), (hits >> k) & 1u);
+                q_count += __popc(m);
+                __syncwarp();
+                if (q_count >= 32) {
+                    active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
+                    q_head = (q_head + 32) & (QCAP - 1);
+                    q_count -= 32;
+                    __syncwarp();
+                }
+            }
+        }
         cur = nxt;
     }
+    __syncwarp();
+    if (lane < q_count) active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
+    __syncwarp();
     acc.finish_warp(flush);
 }
 
