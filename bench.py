@@ -123,7 +123,10 @@ def build_pars(lp, sizes, dur, seed, rng):
     start = dt.date(2017, 1, 1)
     return lp.PropertySet({
         "seed": seed, "start_date": start, "dur": dur, "init_pop": np.asarray(sizes), "cbr": np.full(n, 37.0),
-        "r0": 10, "r0_scalars": rng.uniform(0.5, 1.5, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
+        # r0 chosen so that R_eff ~ 1 with 93 % susceptible agents: prevalence stays near the canonical mix of SURVEY 8(d)
+        # (f_S 0.93, f_E = f_I 0.01) for the whole timed window instead of exploding (the real Nigeria runs divide the force
+        # of infection by a population that is mostly non-agent immunes, model.py:1344-1347)
+        "r0": 1.1, "r0_scalars": rng.uniform(0.8, 1.2, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
         "distances": dist, "migration_method": "gravity", "gravity_k": 0.5, "gravity_k_exponent": -1.0, "gravity_c": 1.5,
         "max_migr_frac": 0.1, "vx_prob_ri": rng.uniform(0.3, 0.8, n), "vx_prob_ipv": rng.uniform(0.3, 0.8, n),
         "vx_prob_sia": rng.uniform(0.4, 0.9, n).tolist(), "sia_schedule": sia_schedule(start, n, dur // 365 + 1, rng),

@@ -206,20 +206,20 @@ __device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t 
 // An entry carries everything the handler needs; the handler owns the agent's state byte from then on (the owning
 // lane already stored the quad's word; both stores come from the same warp, ordered by __syncwarp()).
 #define QCAP 64
-__device__ __forceinline__ unsigned long long q_pack(int64_t i, int nd, int8_t s, bool hit) {
-    return (unsigned long long)i | ((unsigned long long)(uint16_t)nd << 40) | ((unsigned long long)(uint8_t)s << 56) |
-           ((unsigned long long)(hit ? 1 : 0) << 60);
+// entry = {agent index relative to the block's first agent, node | state << 16 | hit << 20}
+__device__ __forceinline__ uint2 q_pack(uint32_t rel, int nd, uint32_t s, uint32_t hit) {
+    return make_uint2(rel, ((uint32_t)nd & 0xFFFFu) | (s << 16) | (hit << 20));
 }
 
 // census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent
-__device__ __noinline__ void active_agent(const PassParams &pp, unsigned long long e) {
+__device__ __noinline__ void active_agent(const PassParams &pp, int64_t block_base, uint2 e) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
-    const int64_t i = (int64_t)(e & 0xFFFFFFFFFFull);
-    const int nd = (int)(int16_t)((e >> 40) & 0xFFFFu);
-    int8_t s = (int8_t)((e >> 56) & 0xFu);
+    const int64_t i = block_base + e.x;
+    const int nd = (int)(int16_t)(e.y & 0xFFFFu);
+    int8_t s = (int8_t)((e.y >> 16) & 0xFu);
     const int ns = A.n_strains;
-    if ((e >> 60) & 1ull) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
+    if ((e.y >> 20) & 1u) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
         uint32_t y[4];
         philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
         const double r = u53(y[0], y[1]);
@@ -245,7 +245,7 @@ __device__ __noinline__ void active_agent(const PassParams &pp, unsigned long lo
 
 template <bool kDeaths, bool kRI>
 __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
-    __shared__ unsigned long long queue[LPK_WARPS][QCAP];
+    __shared__ uint2 queue[LPK_WARPS][QCAP];
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
     // rows of 128 agents; blocks own contiguous row ranges, warps interleave inside
     const int64_t rows = (n + 127) >> 7;
     const int64_t lo = rows * (int64_t)blockIdx.x / gridDim.x, hi = rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    unsigned long long *q = queue[warp];
+    uint2 *q = queue[warp];
+    const int64_t block_base = lo << 7;
     int q_head = 0, q_count = 0;  // warp-uniform
 
     TickAcc acc;
@@ -309,13 +310,15 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                         if (qn > 0.f) {
                             uint32_t x[4];
                             philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
+                            // x < floor(risk * q * 2^32), saturating: the same predicate as expose_hit() (p >= 1 always
+                            // hits, p <= 0 / NaN never) in three instructions per agent; scaling q by 2^32 is exact
+                            const float q32 = qn * 4294967296.0f;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (((mS >> (8 * k)) & 1u) && expose_hit(__fmul_rn(rk[k], qn), x[k])) {
-                                    hits |= 1u << k;
-                                    nw = set_byte(nw, k, 1);
-                                }
+                                const bool hit = ((mS >> (8 * k)) & 1u) && ((unsigned long long)x[k] < __float2ull_rz(__fmul_rn(rk[k], q32)));
+                                hits |= hit ? (1u << k) : 0u;
                             }
+                            nw |= ((hits & 1u) | ((hits & 2u) << 7) | ((hits & 4u) << 14) | ((hits & 8u) << 21));  // S (0) -> E (1)
                         }
                     }
                     // census of tick t-1 on the post-exposure state (E / I agents are counted by the queue handler)
@@ -337,7 +340,22 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                 }
                 const uint32_t mEI = __vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u);
                 cand = (mEI & 1u) | ((mEI >> 7) & 2u) | ((mEI >> 14) & 4u) | ((mEI >> 21) & 8u);
-                if (kRI) nw = ri_quad(pp, b, 4, nw);
+                if (kRI) {
+                    // RI may set ipv_protected, which the disease-state step of the SAME tick must not see yet
+                    // (reference order: DiseaseState_ABM before RI_ABM), so nothing is deferred on RI ticks.
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        if (!((cand >> k) & 1u)) continue;
+                        if ((hits >> k) & 1u) expose_agent(pp, b + k, nd);
+                        int8_t sk = byte_of(nw, k);
+                        if (pending) census_ei(pp, b + k, nd, sk);
+                        sk = ds_agent_ol(pp, b + k, sk);
+                        nw = set_byte(nw, k, sk);
+                        if (sk == 2) tally_infectious(pp, b + k, nd);
+                    }
+                    cand = 0u;
+                    nw = ri_quad(pp, b, 4, nw);
+                }
                 // tally of tick t (susceptibles here, infectious agents in the queue handler)
                 const uint32_t mS2 = __vcmpeq4(nw, 0u);
                 acc.ci[CI_SUS] += __popc(mS2) >> 3;
@@ -347,28 +365,30 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
             }
             if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
-        // ---- append this row's active agents to the warp's ring; drain it 32 at a time (warp-uniform control flow)
-        if (__any_sync(LPK_FULL, cand != 0u)) {
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const bool mine = (cand >> k) & 1u;
-                const uint32_t m = __ballot_sync(LPK_FULL, mine);
-                if (m == 0u) continue;
-                if (mine) q[(q_head + q_count + __popc(m & lt_mask)) & (QCAP - 1)] = q_pack(b + k, nd, byte_of(nw, k), (hits >> k) & 1u);
-                q_count += __popc(m);
+        // ---- append this row's active agents to the warp's ring; drain it 32 at a time (warp-uniform control flow).
+        // One round per candidate of the busiest lane (almost always one round).
+        while (__any_sync(LPK_FULL, cand != 0u)) {
+            const bool mine = cand != 0u;
+            const int k = __ffs(cand) - 1;
+            const uint32_t m = __ballot_sync(LPK_FULL, mine);
+            if (mine) {
+                q[(q_head + q_count + __popc(m & lt_mask)) & (QCAP - 1)] =
+                    q_pack((uint32_t)(b + k - block_base), nd, (nw >> (8 * k)) & 0xFFu, (hits >> k) & 1u);
+                cand &= cand - 1u;
+            }
+            q_count += __popc(m);
+            __syncwarp();
+            if (q_count >= 32) {
+                active_agent(pp, block_base, q[(q_head + lane) & (QCAP - 1)]);
+                q_head = (q_head + 32) & (QCAP - 1);
+                q_count -= 32;
                 __syncwarp();
-                if (q_count >= 32) {
-                    active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
-                    q_head = (q_head + 32) & (QCAP - 1);
-                    q_count -= 32;
-                    __syncwarp();
-                }
             }
         }
         cur = nxt;
     }
     __syncwarp();
-    if (lane < q_count) active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
+    if (lane < q_count) active_agent(pp, block_base, q[(q_head + lane) & (QCAP - 1)]);
     __syncwarp();
     acc.finish_warp(flush);
 }
