@@ -37,6 +37,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 HBM_FALLBACK_GBS = 6650.0
+BENCH_R0 = 1.1  # sets daily_infectivity in the synthetic table; see build_pars
 ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1
 
 # algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
@@ -126,7 +127,7 @@ def build_pars(lp, sizes, dur, seed, rng):
         # r0 chosen so that R_eff ~ 1 with 93 % susceptible agents: prevalence stays near the canonical mix of SURVEY 8(d)
         # (f_S 0.93, f_E = f_I 0.01) for the whole timed window instead of exploding (the real Nigeria runs divide the force
         # of infection by a population that is mostly non-agent immunes, model.py:1344-1347)
-        "r0": 1.1, "r0_scalars": rng.uniform(0.8, 1.2, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
+        "r0": BENCH_R0, "r0_scalars": rng.uniform(0.8, 1.2, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
         "distances": dist, "migration_method": "gravity", "gravity_k": 0.5, "gravity_k_exponent": -1.0, "gravity_c": 1.5,
         "max_migr_frac": 0.1, "vx_prob_ri": rng.uniform(0.3, 0.8, n), "vx_prob_ipv": rng.uniform(0.3, 0.8, n),
         "vx_prob_sia": rng.uniform(0.4, 0.9, n).tolist(), "sia_schedule": sia_schedule(start, n, dur // 365 + 1, rng),
@@ -143,7 +144,7 @@ def build_sim(lp, n_agents, n_nodes, dur, seed, device):
 
     births_room = 1.0 + 37.0 / 1000.0 * (dur + 100) / 365.0 * 1.15
     capacity = int(n_agents * births_room) + 4096
-    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed, capacity=capacity, device=device)
+    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed, capacity=capacity, device=device, r0=BENCH_R0)
     people = lp.LaserFrame(capacity=capacity, initial_count=n_agents)
     for name, dtype in synth.COLUMNS.items():
         people.add_scalar_property(name, dtype=dtype, default=synth.COLUMN_DEFAULTS[name])
