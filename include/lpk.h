@@ -251,6 +251,38 @@ typedef struct lpk_node_args {
 
 int lpk_tick_node(const lpk_node_args *args, void *stream);
 
+/* V2  replaces the births block of VitalDynamics_ABM.step (model.py:1711-1734): per node
+ *     births = floor(e) + Bernoulli(e - floor(e)), e = step_size * birth_rate * pop[t-1]; the cohort is appended
+ *     node-major at [count, count + sum(births)) with date_of_birth = t, date_of_death = t + lifespan(age 0) drawn by
+ *     inverse CDF on cum_deaths (laser-core KaplanMeierEstimator.predict_age_at_death semantics: year by
+ *     searchsorted-left on the cumulative table, uniform day within the year), disease_state = 0.  Draws are
+ *     Philox(seed; node, tick, BIRTH) / Philox(seed; agent, tick, LIFESPAN) instead of the host numpy stream.
+ *     counts[1] += sum(births); if that would exceed capacity nobody is born and *status is set to 1 (the device
+ *     analogue of LaserFrame.add raising; the host raises when it next reads status). */
+typedef struct lpk_births_args {
+    int32_t tick, n_nodes;
+    uint64_t seed, id_base;
+    double step_size;            /* days covered by one vital-dynamics step (pars.step_size_VitalDynamics_ABM) */
+    const double *birth_rate;    /* [nodes] births per capita per day = cbr / (365 * 1000) */
+    const int32_t *pop_prev;     /* [nodes] results.pop[t-1] */
+    int32_t *births_row;         /* [nodes] results.births[t], overwritten */
+    int64_t *counts;             /* device int64[2], see lpk_tick_args.counts */
+    int64_t capacity;
+    const int64_t *cum_deaths;   /* [max_year + 2], cum_deaths[0] = 0 */
+    int32_t max_year;
+    int32_t ri_newborn_timer;    /* < 0: leave ri_timer as pre-set (reference behaviour); else value for newborns */
+    int32_t *node_offsets_ws;    /* scratch int32[nodes + 1] */
+    int64_t *cohort_ws;          /* scratch int64[2] = {first slot, size} of the cohort just created */
+    int32_t *status;             /* device int32 flag */
+    int8_t *disease_state;
+    int16_t *node_id;
+    int32_t *date_of_birth, *date_of_death;
+    int16_t *ri_timer;           /* may be NULL */
+    int32_t *tile_node;          /* may be NULL */
+} lpk_births_args;
+
+int lpk_vd_births(const lpk_births_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ FX_SCALE = float(2**30)
 EXPORTS = (
     "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
     "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
-    "lpk_tick_pass", "lpk_tick_node",
+    "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births",
 )
 
 
@@ -139,6 +139,18 @@ class NodeArgs(C.Structure):
         ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
         ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
         ("next_beta_fx", _VP), ("next_exposure_fx", _VP), ("next_sus", _VP), ("counts", _VP),
+    ]
+
+
+class BirthsArgs(C.Structure):
+    """struct lpk_births_args"""
+
+    _fields_ = [
+        ("tick", C.c_int32), ("n_nodes", C.c_int32), ("seed", C.c_uint64), ("id_base", C.c_uint64), ("step_size", C.c_double),
+        ("birth_rate", _VP), ("pop_prev", _VP), ("births_row", _VP), ("counts", _VP), ("capacity", C.c_int64),
+        ("cum_deaths", _VP), ("max_year", C.c_int32), ("ri_newborn_timer", C.c_int32), ("node_offsets_ws", _VP),
+        ("cohort_ws", _VP), ("status", _VP), ("disease_state", _VP), ("node_id", _VP), ("date_of_birth", _VP),
+        ("date_of_death", _VP), ("ri_timer", _VP), ("tile_node", _VP),
     ]
 
 

@@ -13,9 +13,9 @@ the reference.  ``run()`` copies the agent columns to HBM once, every ``componen
 columns and results come back in one bulk copy when the run ends.  There is no host compute
 fallback for the per-tick path: without a CUDA device or without liblpk.so, ``run()`` raises.
 
-Host-side on purpose (rare, tiny, or RNG-contract bound):
-births (per-node numpy draws + lifespans, every ``step_size_VitalDynamics_ABM`` ticks) and
-``seed_schedule`` injections (a handful of ticks per run).
+Host-side on purpose (rare and tiny): ``seed_schedule`` injections (a handful of ticks
+per run).  Births are drawn and appended on the device (include/lpk.h V2), so ``sim.people.count`` is refreshed
+from the device at the synchronisation points (``to_host()``, and every vital-dynamics tick in component mode).
 """
 
 from __future__ import annotations
@@ -367,9 +367,9 @@ class DiseaseState_ABM:
         """Scheduled importations (reference model.py:759-779): host picks, device state is patched in place."""
         import torch
 
-        count = self.people.count
+        count = dev.sync_count()  # cohorts born on the device are part of the candidate pool
         state = dev.cols["disease_state"][:count].cpu().numpy()
-        node_id = self.people.node_id[:count]  # node ids never change on the device
+        node_id = dev.cols["node_id"][:count].cpu().numpy()
         for node, value in self.seed_schedule[t]:
             pool = np.where((node_id == node) & (state >= 0))[0]
             if isinstance(value, float):
@@ -491,7 +491,7 @@ class Transmission_ABM:
         beta_fx, exposure_fx, _ = dev.tally
         r0s = self._r0_scalars_dev(dev)
         # results.pop[t] as it stands (all zeros when VitalDynamics_ABM is not a component -> divide by max(0, 1))
-        pop = dev.pop_tensor(self.results.pop[t])
+        pop = dev.pop_row(t)
         q, cdf, _, _ = K.tx_node_math(beta_fx, exposure_fx, dev.network_tensor(self.network), season, r0s, pop,
                                       float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion),
                                       rng=sim.rng(), out=dev.node_out)
@@ -615,40 +615,57 @@ class VitalDynamics_ABM:
         if cbr is not None:
             self.birth_rate[:] = (cbr[0] if (isinstance(cbr, (float, int)) or len(cbr) == 1) else np.array(cbr)) / (365 * 1000)
 
+    def births_args(self, dev, t, tile_node=None):
+        """Argument block of lpk_vd_births for tick t (device-side births, include/lpk.h V2)."""
+        import torch
+
+        from . import _lpk
+
+        if getattr(self, "_dev_owner", None) is not dev:
+            cd = np.ascontiguousarray(self.death_estimator._cd, dtype=np.int64)
+            self._cd_dev = torch.from_numpy(cd).to(dev.device)
+            self._rate_dev = torch.from_numpy(np.ascontiguousarray(self.birth_rate, dtype=np.float64)).to(dev.device)
+            self._dev_owner = dev
+        c, r, sim = dev.cols, dev.res, self.sim
+        a = _lpk.BirthsArgs()
+        a.tick, a.n_nodes = t, dev.n_nodes
+        a.seed, a.id_base = int(sim.pars.seed) & 0xFFFFFFFFFFFFFFFF, sim.id_base
+        a.step_size = float(self.step_size)
+        a.birth_rate, a.pop_prev, a.births_row = self._rate_dev.data_ptr(), r["pop"][t - 1].data_ptr(), r["births"][t].data_ptr()
+        a.counts, a.capacity = dev.counts.data_ptr(), self.people.capacity
+        a.cum_deaths, a.max_year = self._cd_dev.data_ptr(), min(100, len(self.death_estimator._cd) - 2)
+        a.ri_newborn_timer = 182 if (getattr(self.pars, "ri_newborn_timer", False) and "ri_timer" in c) else -1
+        a.node_offsets_ws, a.cohort_ws, a.status = dev.node_offsets_ws.data_ptr(), dev.cohort_ws.data_ptr(), dev.status.data_ptr()
+        a.disease_state, a.node_id = c["disease_state"].data_ptr(), c["node_id"].data_ptr()
+        a.date_of_birth, a.date_of_death = c["date_of_birth"].data_ptr(), c["date_of_death"].data_ptr()
+        a.ri_timer = c["ri_timer"].data_ptr() if "ri_timer" in c else None
+        a.tile_node = tile_node.data_ptr() if tile_node is not None else None
+        self._keep = (a,)
+        return a
+
     def step(self):
+        import ctypes as C
+
+        from . import _lpk
         from . import kernels as K
 
-        sim, people, res = self.sim, self.people, self.results
+        sim, people = self.sim, self.people
         dev = _need_dev(sim)
-        t = sim.t
+        t, r, c = sim.t, dev.res, dev.cols
         if t % self.step_size != 0:
-            res.pop[t, :] = res.pop[t - 1, :]
+            r["pop"][t] = r["pop"][t - 1]  # no births or deaths this tick (reference model.py:1691-1695)
             return
-        c = dev.cols
+        if self.pars.cbr is None:
+            raise ValueError("VitalDynamics_ABM needs pars.cbr")
         dying = dev.scratch_i32[0]
         K.get_deaths(dev.n_nodes, people.count, c["disease_state"], c["node_id"], c["date_of_death"], t, dying)
-        deaths = dying.cpu().numpy()  # stream sync: births need last step's population on the host
-        dev.d2h_bytes += deaths.nbytes
-        # births (reference model.py:1712-1734): floor + Bernoulli(frac) per node, host numpy stream
-        expected = self.step_size * self.birth_rate * res.pop[t - 1]
-        whole = expected.astype(np.int32)
-        births = whole + np.random.binomial(1, expected - whole)
-        total = int(births.sum())
-        if total > 0:
-            start, end = people.add(total)
-            people.date_of_birth[start:end] = t
-            people.date_of_death[start:end] = t + self.death_estimator.predict_age_at_death(np.zeros(total, np.int32), max_year=100)
-            people.disease_state[start:end] = 0
-            people.node_id[start:end] = np.repeat(np.arange(len(self.nodes)), births)
-            cols = ["date_of_birth", "date_of_death", "disease_state", "node_id"]
-            if getattr(self.pars, "ri_newborn_timer", False):
-                people.ri_timer[start:end] = 182  # the reference intends this but never applies it
-                cols.append("ri_timer")
-            for name in cols:
-                dev.push_rows(name, start, end)
-            res.births[t] = births
-        res.deaths[t] = deaths
-        res.pop[t, :] = res.pop[t - 1, :] + res.births[t, :] - res.deaths[t, :]
+        # births (reference model.py:1712-1734) are drawn and appended on the device: no host round trip per step
+        dev.set_count(people.count)
+        args = self.births_args(dev, t, dev.tile_node)
+        K.STATS.record("vd_births", lambda: _lpk.check(_lpk.lib().lpk_vd_births(C.byref(args), _lpk.stream_handle()), "lpk_vd_births"), 3)
+        r["deaths"][t] = dying  # "=": overwrites the pre-modelled deaths of non-agent immunes (model.py:1749)
+        r["pop"][t] = r["pop"][t - 1] + r["births"][t] - r["deaths"][t]
+        dev.sync_count()  # component-by-component mode launches with a host-side count
 
     def log(self, t):
         pass

@@ -20,8 +20,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-# results that are produced on the host (birth/death bookkeeping needs host-side draws) and never mirrored
-HOST_ONLY_RESULTS = ("pop", "births", "deaths", "network")
+# results entries that are not [nt, nodes(, strains)] int32 rows
+HOST_ONLY_RESULTS = ("network",)
 
 
 def _to_dev(arr: np.ndarray, device) -> torch.Tensor:
@@ -54,8 +54,13 @@ class DeviceState:
                 self.res[name] = _to_dev(arr, self.device)
                 self.h2d_bytes += arr.nbytes
         n, ns, dev = self.n_nodes, self.n_strains, self.device
-        self.pop_cur = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._pop_host = None
+        self.zero_pop = torch.zeros(n, dtype=torch.int32, device=dev)
+        # live-slot counters {agents when the previous tick ended, agents now}: births are created on the device
+        self.counts = torch.tensor([people.count, people.count], dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cohort_ws = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.node_offsets_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        self.tile_node = None  # owned by engine.FusedEngine when ticks are fused
         self.scratch_i32 = [torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(4)]
         self.tally = (torch.zeros((n, ns), dtype=torch.int64, device=dev), torch.zeros(n, dtype=torch.int64, device=dev),
                       torch.zeros(n, dtype=torch.int64, device=dev))
@@ -72,6 +77,7 @@ class DeviceState:
         """Bulk D2H of every agent column and every device-resident results array, in place."""
         people, results = self.sim.people, self.sim.results
         torch.cuda.current_stream().synchronize()
+        self.sync_count()
         for name, t in self.cols.items():
             host = getattr(people, name)
             torch.from_numpy(host).copy_(t, non_blocking=False)
@@ -87,14 +93,21 @@ class DeviceState:
         self.cols[name][start:end].copy_(torch.from_numpy(host), non_blocking=False)
         self.h2d_bytes += host.nbytes
 
-    def pop_tensor(self, row: np.ndarray) -> torch.Tensor:
-        """Device copy of ``results.pop[t]``; re-uploaded only when the host row changed (births / deaths ticks)."""
-        row = np.ascontiguousarray(row, dtype=np.int32)
-        if self._pop_host is None or not np.array_equal(self._pop_host, row):
-            self._pop_host = row.copy()
-            self.pop_cur.copy_(torch.from_numpy(self._pop_host))
-            self.h2d_bytes += row.nbytes
-        return self.pop_cur
+    def pop_row(self, t: int) -> torch.Tensor:
+        """results.pop[t] on the device (all zeros when nothing maintains it, like the reference's untouched rows)."""
+        pop = self.res.get("pop")
+        return self.zero_pop if pop is None else pop[t]
+
+    def sync_count(self) -> int:
+        """Device -> host: how many slots are in use (blocks on the stream), and whether a cohort overflowed capacity."""
+        count, status = int(self.counts[1].item()), int(self.status.item())
+        if status != 0:
+            raise ValueError(f"frame.add() exceeds capacity (capacity={self.sim.people.capacity}): births were dropped on the device")
+        self.sim.people._count = count
+        return count
+
+    def set_count(self, count: int):
+        self.counts.copy_(torch.tensor([count, count], dtype=torch.int64))
 
     def network_tensor(self, host_network) -> torch.Tensor:
         """Device copy of ``tx.network`` (float64, row-major); re-uploaded when the host object is replaced

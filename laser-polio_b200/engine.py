@@ -1,15 +1,15 @@
 """Fused-tick engine: what ``SEIR_ABM.run()`` drives when the component list is the stock one.
 
 The reference's loop body (model.py:252-263) calls every component's ``step()`` and then ``log(t)``; here the same
-work for a whole day is ONE streaming pass over the agent table (``lpk_tick_pass``) plus a node-level kernel
-(``lpk_tick_node``), software-pipelined by one tick: the pass for tick t first applies tick t-1's exposure trial and
-takes tick t-1's census, then runs tick t's deaths / disease-state / RI stages and tick t's infectivity tally.
-Results are identical to calling the components one by one (every draw is keyed on (seed, agent, tick, stage));
-``tests/test_gpu_fused.py`` asserts that bit for bit.
+work for a whole day is ONE streaming pass over the agent table (``lpk_tick_pass``) plus node-level kernels
+(``lpk_vd_births`` on vital-dynamics ticks, ``lpk_tick_node``), software-pipelined by one tick: the pass for tick t
+first applies tick t-1's exposure trial and takes tick t-1's census, then runs tick t's deaths / disease-state / RI
+stages and tick t's infectivity tally.  Results are identical to calling the components one by one (every draw is
+keyed on (seed, agent, tick, stage)); ``tests/test_gpu_fused.py`` asserts that bit for bit.
 
-Days that need something the pass does not fuse -- an SIA campaign, a ``seed_schedule`` injection, a
-vital-dynamics tick (births are drawn on the host) -- are run through the components after draining the pending
-exposure + census, so any schedule is legal.
+The host never waits for the device inside a fused day: births are created in HBM and the live-slot count stays
+there.  Days that need something the pass does not fuse -- an SIA campaign or a ``seed_schedule`` injection -- are
+run through the components after draining the pending exposure + census, so any schedule is legal.
 """
 
 from __future__ import annotations
@@ -22,8 +22,6 @@ import torch
 from . import _lpk
 from . import kernels as K
 from ._lpk import F_DEATHS, F_PENDING, F_RI, F_STAGES, NodeArgs, People, TickArgs, check, dp, stream_handle
-
-STOCK = ("VitalDynamics_ABM", "DiseaseState_ABM", "RI_ABM", "SIA_ABM", "Transmission_ABM")
 
 
 def eligible(sim) -> bool:
@@ -48,13 +46,11 @@ class FusedEngine:
         n, ns, d = dev.n_nodes, dev.n_strains, dev.device
         c = dev.cols
         self.pending = False
-        self.launches = 0
         cap = sim.people.capacity
         n_tiles = (cap + _lpk.TILE_AGENTS - 1) // _lpk.TILE_AGENTS
-        self.tile_node = torch.empty(n_tiles, dtype=torch.int32, device=d)
+        self.tile_node = dev.tile_node = torch.empty(n_tiles, dtype=torch.int32, device=d)
         self.rebuild_tiles(0)
-        self.counts = torch.tensor([sim.people.count, sim.people.count], dtype=torch.int64, device=d)
-        self._count_host = sim.people.count
+        dev.set_count(sim.people.count)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=d)  # noqa: E731
         i64 = lambda *s: torch.zeros(s, dtype=torch.int64, device=d)  # noqa: E731
         self.tally = [(i64(n, ns), i64(n), i64(n)) for _ in range(2)]
@@ -85,23 +81,12 @@ class FusedEngine:
                                               C.c_int64(self.sim.people.capacity), _lpk.ptr(self.tile_node), stream_handle()),
               "lpk_build_tile_nodes")
 
-    def _sync_count(self):
-        """Births were appended on the host (unfused vital-dynamics tick): refresh the device counters and tile table."""
-        count = self.sim.people.count
-        if count != self._count_host:
-            self.rebuild_tiles(self._count_host)
-            self._count_host = count
-        self.counts.copy_(torch.tensor([count, count], dtype=torch.int64), non_blocking=False)
-
     def _row(self, name, t):
         r = self.dev.res.get(name)
         return self.dummy_row if r is None else r[t]
 
     def needs_components(self, t) -> bool:
         sim = self.sim
-        vd = self.by_name.get("VitalDynamics_ABM")
-        if vd is not None and t % vd.step_size == 0:
-            return True
         sia = self.by_name.get("SIA_ABM")
         if sia is not None and sia._by_tick.get(t) and sim.pars.vx_prob_sia is not None:
             return True
@@ -116,7 +101,8 @@ class FusedEngine:
         sim, dev = self.sim, self.dev
         t = sim.t - 1  # the tick the pending work belongs to
         c, r = dev.cols, dev.res
-        n, ns, count = dev.n_nodes, dev.n_strains, self._count_host
+        n, ns = dev.n_nodes, dev.n_strains
+        count = dev.sync_count()  # births of fused vital-dynamics ticks happened on the device
         K.tx_infect(n, count, ns, c["node_id"], c["strain"], c["disease_state"], c["acq_risk_multiplier"], self.q, self.cdf,
                     rng=K.make_rng(sim.pars.seed, t, id_base=sim.id_base), out=dev.n_new)
         r["new_exposed"][t] += dev.n_new.sum(dim=1, dtype=torch.int32)
@@ -131,19 +117,25 @@ class FusedEngine:
         r = self.dev.res
         self.cur_potp.copy_(r["potentially_paralyzed"][t])
         self.cur_p.copy_(r["paralyzed"][t])
-        self._sync_count()
+        self.dev.set_count(self.sim.people.count)
 
     def fused_tick(self, t):
         sim, dev, pars = self.sim, self.dev, self.sim.pars
         n, ns = dev.n_nodes, dev.n_strains
         tx = self.by_name["Transmission_ABM"]
         ri = self.by_name.get("RI_ABM")
-        res = sim.results
-        flags = F_STAGES | (F_PENDING if self.pending else 0)
+        vd = self.by_name.get("VitalDynamics_ABM")
+        is_vd = vd is not None and t % vd.step_size == 0
+        flags = F_STAGES | (F_PENDING if self.pending else 0) | (F_DEATHS if is_vd else 0)
+        if is_vd:  # births first: the cohort takes part in this tick's tally (reference: VitalDynamics runs first)
+            if pars.cbr is None:
+                raise ValueError("VitalDynamics_ABM needs pars.cbr")
+            b = vd.births_args(dev, t, self.tile_node)
+            K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns
         A.seed, A.id_base = int(pars.seed) & 0xFFFFFFFFFFFFFFFF, sim.id_base
-        A.counts = dp(self.counts)
+        A.counts = dp(dev.counts)
         A.q_prev, A.cdf_prev = dp(self.q), dp(self.cdf)
         tp = max(t - 1, 0)
         A.new_exposed_prev, A.new_exposed_by_strain_prev = dp(self._row("new_exposed", tp)), dp(self._row("new_exposed_by_strain", tp))
@@ -171,18 +163,21 @@ class FusedEngine:
         A.flags = flags
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
 
-        # host-side population row: a fused tick is never a vital-dynamics tick, so pop[t] = pop[t-1] (model.py:1694)
-        if "VitalDynamics_ABM" in self.by_name:
-            res.pop[t, :] = res.pop[t - 1, :]
         N = NodeArgs()
         N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
         N.seed = A.seed
         N.beta_fx, N.exposure_fx = dp(beta_fx), dp(exposure_fx)
         N.network, N.r0_scalars = dp(dev.network_tensor(tx.network)), dp(tx._r0_scalars_dev(dev))
-        N.beta_seasonality = float(self._seasonality(t))
+        N.beta_seasonality = float(self._seasonality())
         N.zero_inflation, N.dispersion = float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion)
         N.q, N.strain_cdf, N.prob, N.expected, N.rowsum_ws = dp(self.q), dp(self.cdf), dp(self.prob), dp(self.expected), dp(self.rowsum)
-        N.pop_prev, N.pop = dp(dev.pop_tensor(res.pop[t])), None
+        if vd is not None:  # pop[t] = pop[t-1] (+ births[t] - deaths on vital-dynamics ticks), model.py:1694, 1751-1755
+            r = dev.res
+            N.pop_prev, N.pop = dp(r["pop"][t - 1]), dp(r["pop"][t])
+            if is_vd:
+                N.births_row, N.deaths_row = dp(r["births"][t]), dp(r["deaths"][t])
+        else:  # nobody maintains results.pop: rows after 0 stay zero, the rate is divided by max(0, 1)
+            N.pop_prev, N.pop = dp(dev.pop_row(t)), None
         N.deaths, N.dead_pp, N.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
         N.cur_potp, N.cur_p = dp(self.cur_potp), dp(self.cur_p)
         N.new_potential, N.new_paralyzed = A.new_potential, A.new_paralyzed
@@ -191,11 +186,11 @@ class FusedEngine:
         N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
         nb, ne, nsus = self.tally[(t + 1) & 1]
         N.next_beta_fx, N.next_exposure_fx, N.next_sus = dp(nb), dp(ne), dp(nsus)
-        N.counts = dp(self.counts)
+        N.counts = dp(dev.counts)
         K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 3)
         self.pending = True
 
-    def _seasonality(self, t):
+    def _seasonality(self):
         from . import utils
 
         return utils.get_seasonality(self.sim)
@@ -205,11 +200,14 @@ class FusedEngine:
         sim = self.sim
         if self.needs_components(t):
             self.drain()
+            old = self.dev.sync_count()
             for component in sim.instances:
                 with sim.perf_stats.start(component.__class__.__name__ + ".step()"):
                     component.step()
             sim.log_results(t)
             self.after_component_tick(t)
+            if sim.people.count != old and self.dev.tile_node is None:
+                self.rebuild_tiles(old)
         else:
             with sim.perf_stats.start("FusedTick.step()"):
                 self.fused_tick(t)

@@ -326,3 +326,42 @@ def node_importation_multiplier(seed, node, tick, zi, r):
         k += 1
         if np.log(1.0 - u) < 0.5 * x * x + d - d * v + d * np.log(v):
             return (d * v) / r / (1.0 - zi)
+
+
+# ------------------------------------------------------------------- births (device scheme, include/lpk.h V2)
+def _u53_pair(x, pair):
+    hi, lo = (int(x[2]), int(x[3])) if pair else (int(x[0]), int(x[1]))
+    return float((((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0))
+
+
+def vd_births_device(pop_prev, birth_rate, step_size, cum_deaths, count, capacity, seed, tick, id_base=0, max_year=100):
+    """Restatement of lpk_vd_births (reference model.py:1711-1734 with Philox draws instead of the host numpy stream).
+
+    Returns (births[nodes] int32, node_id[total] int16, date_of_death[total] int32, new_count, status); the cohort
+    occupies slots [count, count + total) node-major, date_of_birth = tick, disease_state = 0.
+    """
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    n = len(pop_prev)
+    births = np.zeros(n, np.int32)
+    for node in range(n):
+        expected = float(step_size) * float(birth_rate[node]) * float(pop_prev[node])
+        whole = int(expected)
+        x = philox4x32_10([node, 0, tick, STAGE_BIRTH], key)
+        births[node] = max(whole + (1 if _u53_pair(x, 0) < expected - whole else 0), 0)
+    total = int(births.sum())
+    if count + total > capacity:
+        return np.zeros(n, np.int32), np.zeros(0, np.int16), np.zeros(0, np.int32), count, 1
+    cd = np.asarray(cum_deaths, np.int64)
+    tot_deaths = max(int(cd[max_year + 1]), 1)
+    node_id = np.repeat(np.arange(n, dtype=np.int16), births)
+    dod = np.zeros(total, np.int32)
+    for k in range(total):
+        g = count + k + id_base
+        x = philox4x32_10([g & 0xFFFFFFFF, g >> 32, tick, STAGE_LIFESPAN], key)
+        draw = 1 + int(np.floor(_u53_pair(x, 0) * tot_deaths))
+        yod = int(np.searchsorted(cd[: max_year + 2], draw, side="left")) - 1
+        yod = min(max(yod, 0), max_year)
+        u2 = _u53_pair(x, 1)
+        doy = 1 + int(np.floor(u2 * 364.0)) if yod == 0 else int(np.floor(u2 * 365.0))
+        dod[k] = tick + yod * 365 + doy
+    return births, node_id, dod, count + total, 0

@@ -269,3 +269,59 @@ def test_empty_population_and_bad_arguments(K):
 
     with pytest.raises(_lpk.LpkError):  # host tensors are refused, there is no CPU fallback
         K.get_deaths(4, 8, z8.cpu(), z16, z32, 3, out)
+
+
+def test_device_births_vs_oracle(K, oracle):
+    """lpk_vd_births (reference model.py:1711-1734, Philox draws): births per node, node-major cohort, lifespans,
+    slot counter, tile table, and the capacity-overflow flag -- bit-exact against the numpy restatement."""
+    import ctypes as C
+
+    from laser_polio_b200 import _lpk, utils
+
+    n_nodes, count, cap, tick, seed, id_base = 37, 5_003, 9_000, 21, 0xABCDEF0123, 4096
+    rs = np.random.default_rng(4)
+    pop_prev = rs.integers(2_000, 400_000, n_nodes).astype(np.int32)
+    pop_prev[5] = 0
+    rate = rs.uniform(20, 45, n_nodes) / 365000.0
+    cd = np.insert(utils.create_cumulative_deaths(int(pop_prev.sum()), 100).astype(np.int64), 0, 0)
+    want = oracle.vd_births_device(pop_prev, rate, 7, cd, count, cap, seed, tick, id_base=id_base)
+    births_o, node_o, dod_o, new_count_o, status_o = want
+    assert status_o == 0 and births_o.sum() > 500 and births_o[5] == 0
+
+    def run(capacity):
+        d = {"state": torch.full((cap,), -1, dtype=torch.int8, device="cuda"), "node": torch.full((cap,), -1, dtype=torch.int16, device="cuda"),
+             "dob": torch.full((cap,), -1, dtype=torch.int32, device="cuda"), "dod": torch.zeros(cap, dtype=torch.int32, device="cuda"),
+             "births": torch.full((n_nodes,), 9, dtype=torch.int32, device="cuda"),
+             "counts": torch.tensor([count, count], dtype=torch.int64, device="cuda"), "status": torch.zeros(1, dtype=torch.int32, device="cuda"),
+             "off": torch.zeros(n_nodes + 1, dtype=torch.int32, device="cuda"), "coh": torch.zeros(2, dtype=torch.int64, device="cuda"),
+             "tiles": torch.full(((cap + 511) // 512,), -7, dtype=torch.int32, device="cuda"),
+             "rate": dev(rate), "pop": dev(pop_prev), "cd": dev(cd)}
+        d["node"][:count] = 3
+        a = _lpk.BirthsArgs()
+        a.tick, a.n_nodes, a.seed, a.id_base, a.step_size = tick, n_nodes, seed, id_base, 7.0
+        a.birth_rate, a.pop_prev, a.births_row = d["rate"].data_ptr(), d["pop"].data_ptr(), d["births"].data_ptr()
+        a.counts, a.capacity, a.cum_deaths, a.max_year, a.ri_newborn_timer = d["counts"].data_ptr(), capacity, d["cd"].data_ptr(), 100, -1
+        a.node_offsets_ws, a.cohort_ws, a.status = d["off"].data_ptr(), d["coh"].data_ptr(), d["status"].data_ptr()
+        a.disease_state, a.node_id, a.date_of_birth, a.date_of_death = (d[k].data_ptr() for k in ("state", "node", "dob", "dod"))
+        a.ri_timer, a.tile_node = None, d["tiles"].data_ptr()
+        _lpk.check(_lpk.lib().lpk_vd_births(C.byref(a), _lpk.stream_handle()), "lpk_vd_births")
+        torch.cuda.synchronize()
+        return d
+
+    d = run(cap)
+    total = int(births_o.sum())
+    assert np.array_equal(host(d["births"]), births_o)
+    assert host(d["counts"]).tolist() == [count, new_count_o] and int(d["status"].item()) == 0
+    assert np.array_equal(host(d["node"])[count:count + total], node_o)
+    assert np.array_equal(host(d["dod"])[count:count + total], dod_o)
+    assert np.all(host(d["dob"])[count:count + total] == tick) and np.all(host(d["state"])[count:count + total] == 0)
+    assert np.all(host(d["state"])[count + total:] == -1) and np.all(host(d["node"])[count + total:] == -1)
+    assert np.all(dod_o > tick)
+    tiles = host(d["tiles"])
+    node_all = host(d["node"])
+    for t_ in range(count // 512, (count + total - 1) // 512 + 1):
+        seg = node_all[t_ * 512:(t_ + 1) * 512]
+        assert tiles[t_] == (seg[0] if len(seg) == 512 and np.all(seg == seg[0]) and seg[0] >= 0 else -1)
+    assert np.all(tiles[: count // 512] == -7)  # untouched tiles keep their value
+    d = run(count + total - 1)  # one slot short: nobody is born, the flag is raised
+    assert int(d["status"].item()) == 1 and host(d["counts"]).tolist() == [count, count] and host(d["births"]).sum() == 0

@@ -199,11 +199,12 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         '#include <cstdio>\n#include <cstddef>\n#include "lpk.h"\nint main(){'
         'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lpk_rng), sizeof(lpk_people), sizeof(lpk_tick_args), sizeof(lpk_node_args),'
         "offsetof(lpk_tick_args, strain_r0_scalars), offsetof(lpk_tick_args, ri_step), offsetof(lpk_node_args, counts),"
-        "offsetof(lpk_people, capacity));}\n"
+        "offsetof(lpk_people, capacity)); printf(\"%zu %zu\\n\", sizeof(lpk_births_args), offsetof(lpk_births_args, tile_node));}\n"
     )
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/g++", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(_lpk.Rng), ctypes.sizeof(_lpk.People), ctypes.sizeof(_lpk.TickArgs), ctypes.sizeof(_lpk.NodeArgs),
-            _lpk.TickArgs.strain_r0_scalars.offset, _lpk.TickArgs.ri_step.offset, _lpk.NodeArgs.counts.offset, _lpk.People.capacity.offset]
+            _lpk.TickArgs.strain_r0_scalars.offset, _lpk.TickArgs.ri_step.offset, _lpk.NodeArgs.counts.offset, _lpk.People.capacity.offset,
+            ctypes.sizeof(_lpk.BirthsArgs), _lpk.BirthsArgs.tile_node.offset]
     assert got == want
