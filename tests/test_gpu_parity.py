@@ -278,7 +278,7 @@ def test_device_births_vs_oracle(K, oracle):
 
     from laser_polio_b200 import _lpk, utils
 
-    n_nodes, count, cap, tick, seed, id_base = 37, 5_003, 9_000, 21, 0xABCDEF0123, 4096
+    n_nodes, count, cap, tick, seed, id_base = 37, 5_003, 20_000, 21, 0xABCDEF0123, 4096
     rs = np.random.default_rng(4)
     pop_prev = rs.integers(2_000, 400_000, n_nodes).astype(np.int32)
     pop_prev[5] = 0
