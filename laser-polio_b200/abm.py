@@ -37,6 +37,11 @@ __all__ = ["SEIR_ABM", "DiseaseState_ABM", "Transmission_ABM", "VitalDynamics_AB
            "populate_heterogeneous_values"]
 
 
+# value an agent column holds in a slot nobody has been born into yet (reference model.py:144-162, 1550, 1603, 1891)
+_UNBORN_DEFAULTS = {"disease_state": -1, "potentially_paralyzed": -1, "paralyzed": 0, "ipv_protected": 0, "strain": 0,
+                    "chronically_missed": 0, "node_id": -1, "date_of_birth": -1, "date_of_death": 0, "ri_timer": -1}
+
+
 def _say(colour: str, msg: str) -> None:
     code = {"cyan": 36, "red": 31, "green": 32, "yellow": 33}[colour]
     print(f"\033[{code}m{msg}\033[0m")
@@ -74,6 +79,7 @@ class SEIR_ABM:
         self._engine = None  # engine.FusedEngine while ticks are being fused
         self.fused = True  # set False to force component-by-component ticks
         self.id_base = 0  # global id of local agent 0 when this table is one node-shard of a larger population
+        self.shard = None  # sharding.Shard when the population is split by node over several GPUs
         if self.verbose >= 1:
             _say("cyan", "Initializing simulation...")
 
@@ -143,6 +149,50 @@ class SEIR_ABM:
                 self.instances.append(c(self))
         if self.verbose >= 2:
             print(f"Initialized components: {self.instances}")
+
+    # ------------------------------------------------------------------ node sharding (one process per GPU)
+    def shard_to(self, rank: int, world: int, group=None):
+        """Keep only this rank's contiguous block of nodes: call on every rank after the components are
+        set and before ``run()``, on identically constructed sims (same pars / seed).  Node ids stay global; per-node
+        results are filled for owned nodes only.  Returns the :class:`sharding.Shard`."""
+        from . import sharding
+
+        if self.dev is not None:
+            raise RuntimeError("shard_to() must be called before the population is moved to the device")
+        people, n_nodes = self.people, len(self.nodes)
+        count = people.count
+        nid = people.node_id[:count]
+        if np.any(np.diff(nid.astype(np.int32)) < 0):
+            raise ValueError("shard_to() needs a node-contiguous agent table (true for a freshly constructed sim)")
+        sizes = np.bincount(nid, minlength=n_nodes)
+        blocks = sharding.plan_node_blocks(sizes, world)
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        spare = people.capacity - count
+        caps = []
+        for lo, hi in blocks:  # spare capacity (room for births) in proportion to the block's agents
+            n_r = int(starts[hi] - starts[lo])
+            caps.append(n_r + int(np.ceil(spare * n_r / max(count, 1))) + 16)
+        lo, hi = blocks[rank]
+        a0, a1 = int(starts[lo]), int(starts[hi])
+        n_r, cap_r = a1 - a0, caps[rank]
+        unborn0 = count + sum(c - int(starts[b[1]] - starts[b[0]]) for c, b in zip(caps[:rank], blocks[:rank]))
+        local = LaserFrame(capacity=cap_r, initial_count=n_r)
+        for name, col in people.columns().items():
+            local.add_scalar_property(name, dtype=col.dtype, default=0)
+            new = getattr(local, name)
+            new[:n_r] = col[a0:a1]
+            tail = col[unborn0 : unborn0 + (cap_r - n_r)]  # pre-drawn per-slot values of not-yet-born agents
+            new[n_r : n_r + len(tail)] = tail
+            if len(tail) < cap_r - n_r:  # more room than the original table had: state-like columns get their unborn default,
+                # pre-drawn per-slot columns (timers, risk, infectivity: iid draws) are recycled from the live slots
+                new[n_r + len(tail):] = (_UNBORN_DEFAULTS[name] if name in _UNBORN_DEFAULTS
+                                         else np.resize(col[:count], cap_r - n_r - len(tail)))
+        self.people = local
+        for inst in self.instances:
+            inst.people = local
+        self.id_base = sharding.id_bases(sizes, blocks, capacity_per_block=caps)[rank]
+        self.shard = sharding.Shard(rank=rank, world=world, node_lo=lo, node_hi=hi, group=group)
+        return self.shard
 
     # ------------------------------------------------------------------ device residency
     def to_device(self, device=None):
@@ -359,7 +409,12 @@ class DiseaseState_ABM:
             self._apply_seed_schedule(t, dev)
         if self.pars["stop_if_no_cases"]:
             # reference model.py:789-795: E/I of the previous tick and pending seeds decide; costs one device sync per tick
-            active = int(dev.res["E"][t - 1].sum().item()) > 0 or int(dev.res["I"][t - 1].sum().item()) > 0
+            ei = dev.res["E"][t - 1].sum() + dev.res["I"][t - 1].sum()
+            if sim.shard is not None and sim.shard.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(ei, group=sim.shard.group)
+            active = int(ei.item()) > 0
             if not (active or any(ts > t for ts in self.seed_schedule)):
                 sim.should_stop = True
 
@@ -371,6 +426,8 @@ class DiseaseState_ABM:
         state = dev.cols["disease_state"][:count].cpu().numpy()
         node_id = dev.cols["node_id"][:count].cpu().numpy()
         for node, value in self.seed_schedule[t]:
+            if self.sim.shard is not None and not self.sim.shard.owns(node):
+                continue  # another rank owns this node
             pool = np.where((node_id == node) & (state >= 0))[0]
             if isinstance(value, float):
                 k = int(len(pool) * value)
@@ -489,6 +546,10 @@ class Transmission_ABM:
         K.tx_step_prep(n, count, ns, c["strain"], srs, c["disease_state"], c["node_id"], c["daily_infectivity"],
                        c["acq_risk_multiplier"], out=dev.tally)
         beta_fx, exposure_fx, _ = dev.tally
+        if sim.shard is not None:  # the one per-tick exchange: every node's infectivity feeds the network transfer
+            from . import sharding
+
+            sharding.allreduce_tally(beta_fx, sim.shard)
         r0s = self._r0_scalars_dev(dev)
         # results.pop[t] as it stands (all zeros when VitalDynamics_ABM is not a component -> divide by max(0, 1))
         pop = dev.pop_row(t)
@@ -624,7 +685,10 @@ class VitalDynamics_ABM:
         if getattr(self, "_dev_owner", None) is not dev:
             cd = np.ascontiguousarray(self.death_estimator._cd, dtype=np.int64)
             self._cd_dev = torch.from_numpy(cd).to(dev.device)
-            self._rate_dev = torch.from_numpy(np.ascontiguousarray(self.birth_rate, dtype=np.float64)).to(dev.device)
+            rate = np.ascontiguousarray(self.birth_rate, dtype=np.float64).copy()
+            if self.sim.shard is not None:
+                rate[~self.sim.shard.owned_mask(len(rate))] = 0.0  # other ranks create the cohorts of their own nodes
+            self._rate_dev = torch.from_numpy(rate).to(dev.device)
             self._dev_owner = dev
         c, r, sim = dev.cols, dev.res, self.sim
         a = _lpk.BirthsArgs()

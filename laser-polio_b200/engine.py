@@ -163,6 +163,10 @@ class FusedEngine:
         A.flags = flags
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
 
+        if sim.shard is not None:  # the one per-tick exchange: sum of the nodes x strains infectivity tally
+            from . import sharding
+
+            sharding.allreduce_tally(beta_fx, sim.shard)
         N = NodeArgs()
         N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
         N.seed = A.seed
