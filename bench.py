@@ -135,30 +135,38 @@ def build_pars(lp, sizes, dur, seed, rng):
     })
 
 
-def build_sim(lp, n_agents, n_nodes, dur, seed, device):
+def build_sim(lp, n_agents, n_nodes, dur, seed, device, rank=0, world=1):
     """Synthetic population generated in HBM, mirrored into pinned host columns (the reference-facing LaserFrame),
-    wrapped by SEIR_ABM.init_from_file + Component.init_from_file (the reference's route for a pre-built table)."""
+    wrapped by SEIR_ABM.init_from_file + Component.init_from_file (the reference's route for a pre-built table).
+
+    With world > 1 every rank builds the shard it owns of a population of n_nodes * world nodes (weak scaling:
+    n_agents agents and n_nodes nodes per GPU, node ids global, network over all nodes)."""
     import torch
 
-    from laser_polio_b200 import synth
+    from laser_polio_b200 import sharding, synth
 
     births_room = 1.0 + 37.0 / 1000.0 * (dur + 100) / 365.0 * 1.15
     capacity = int(n_agents * births_room) + 4096
-    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed, capacity=capacity, device=device, r0=BENCH_R0)
+    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed + rank, capacity=capacity, device=device, r0=BENCH_R0)
+    if rank > 0:
+        live = pop["node_id"][:n_agents]
+        live += rank * n_nodes  # global node ids
     people = lp.LaserFrame(capacity=capacity, initial_count=n_agents)
     for name, dtype in synth.COLUMNS.items():
         people.add_scalar_property(name, dtype=dtype, default=synth.COLUMN_DEFAULTS[name])
         torch.from_numpy(getattr(people, name)).copy_(pop[name])
-    sizes = pop["node_sizes"]
     del pop
     torch.cuda.empty_cache()
-    rng = np.random.default_rng(seed + 1)
-    pars = build_pars(lp, sizes, dur, seed, rng)
+    sizes = np.concatenate([synth.node_sizes(n_agents, n_nodes, np.random.default_rng(seed + r)) for r in range(world)])
+    pars = build_pars(lp, sizes, dur, seed, np.random.default_rng(seed + 1000))
     sim = lp.SEIR_ABM.init_from_file(people, pars)
     sim.verbose = 0
-    sim.nodes = np.arange(n_nodes)
+    sim.nodes = np.arange(n_nodes * world)
     sim._components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
     sim.instances = [c.init_from_file(sim) for c in sim._components]
+    if world > 1:
+        sim.shard = sharding.Shard(rank=rank, world=world, node_lo=rank * n_nodes, node_hi=(rank + 1) * n_nodes)
+        sim.id_base = rank * ((capacity + 3) // 4 * 4)
     return sim
 
 
@@ -268,7 +276,7 @@ def run_b200(args):
     n_nodes = args.nodes
     K_, W_ = args.steps, max(args.warmup, 3)
     dur = 2 * (K_ + W_) + 40
-    sim = build_sim(lp, n_agents, n_nodes, dur, seed=20261017 + rank, device=f"cuda:{local}")
+    sim = build_sim(lp, n_agents, n_nodes, dur, seed=20261017, device=f"cuda:{local}", rank=rank, world=world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -333,10 +341,11 @@ def run_b200(args):
         "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8 state machine + int64 fixed-point tallies + f64 node math", "data": "synthetic",
-        "config": {"workload": f"nigeria-774 shape (examples/demo_nigeria.py): {n_agents} agents/GPU, {n_nodes} nodes, 3 strains, "
+        "config": {"workload": f"nigeria-774 shape (examples/demo_nigeria.py): {n_agents} agents/GPU, {n_nodes} nodes/GPU, 3 strains, "
                                "VD every 7, RI every 14, ~8 SIA/yr, daily transmission + census",
                    "agents_per_gpu": n_agents, "nodes": n_nodes, "l2_policy": "inputs (>=1 GB per column) far larger than the 126 MB L2",
-                   "parallelism": f"node-sharded x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"node-sharded x{world}: {n_nodes * world} nodes, one NCCL all-reduce of the nodes x strains tally per tick"
+                                   if world > 1 else "single GPU")},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
                      "tick_frac_of_14B_roofline": (ALGO_BYTES_PER_AGENT_TICK * value / world) / (peak * 1e9),
@@ -354,7 +363,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=28)
+    ap.add_argument("--steps", type=int, default=140)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="agents per GPU (default: 220M, the Nigeria config)")

@@ -567,7 +567,7 @@ class Transmission_ABM:
         src = self.r0_scalars
         if getattr(self, "_r0_src", None) is not src or getattr(self, "_r0_dev_owner", None) is not dev:
             # the reference broadcasts r0_scalars[:, None] against [nodes, strains] (model.py:1341): length 1 is legal
-            arr = np.ascontiguousarray(np.broadcast_to(np.asarray(src, dtype=np.float64), (dev.n_nodes,)))
+            arr = np.broadcast_to(np.asarray(src, dtype=np.float64), (dev.n_nodes,)).copy()
             self._r0_dev = torch.from_numpy(arr).to(dev.device)
             self._r0_src, self._r0_dev_owner = src, dev
         return self._r0_dev
