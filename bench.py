@@ -174,6 +174,9 @@ def build_sim(lp, n_agents, n_nodes, dur, seed, device, rank=0, world=1):
 def cpu_tick_loop(n_agents, n_nodes, ticks, warm, seed=5):
     """The reference's per-tick call sequence on the CPU oracle; returns (agent_days_per_s, threads, per-stage seconds)."""
     from laser_polio_b200 import synth
+
+    if "WORLD_SIZE" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())  # torchrun pins 1 thread per rank; the CPU leg uses every core
     from oracle import oracle as orc
 
     p = synth.synth_population(n_agents, n_nodes, seed=seed)
@@ -375,6 +378,10 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
