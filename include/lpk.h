@@ -40,6 +40,7 @@ extern "C" {
 
 #define LPK_MAX_STRAINS 4
 #define LPK_FX_SCALE 1073741824.0 /* 2^30: fixed-point scale of the float tallies */
+#define LPK_RISK_BINS 192          /* risk histogram: 8 bins per octave over [2^-12, 2^12) */
 
 /* Philox stage ids (counter word 3) */
 #define LPK_STAGE_PARALYSIS 0u
@@ -109,41 +110,47 @@ int lpk_fast_sia(const int16_t *node_ids, int8_t *disease_states, int8_t *strain
  *       beta_fx[num_nodes * n_strains]  sum over infectious of infectivity * strain_r0_scalars[strain]
  *       exposure_fx[num_nodes]          sum over susceptibles of acq_risk_multiplier
  *       sus[num_nodes]                  susceptible count
+ *       risk_hist[num_nodes * LPK_RISK_BINS]  histogram of the susceptibles' acq_risk_multiplier (log-spaced bins);
+ *                                       it replaces the reference's per-node sus_probs scratch (model.py:1055-1061):
+ *                                       lpk_tx_node_math solves the node's exposure scale on it
  *     The float sums are exact 2^30 fixed point in int64 (value = fx / LPK_FX_SCALE): order independent,
  *     bitwise reproducible across launch shapes and GPU counts, within 1e-9 of the float64 sum (the
  *     reference's per-thread float32 accumulation is itself ~5e-6 off it).  strain_r0_scalars: HOST double[n_strains]. */
 int lpk_tx_step_prep(int32_t num_nodes, int64_t num_people, int32_t n_strains, const int8_t *strains,
                      const double *h_strain_r0_scalars, const int8_t *disease_states, const int16_t *node_ids,
                      const float *daily_infectivity, const float *risks, int64_t *beta_fx, int64_t *exposure_fx,
-                     int64_t *sus, void *stream);
+                     int64_t *sus, int32_t *risk_hist, void *stream);
 
 /* T2  replaces the node-level block of Transmission_ABM.step, model.py:1332-1351 and 1362-1407:
  *     network transfer beta += W^T beta - beta * rowsum(W), x seasonality x r0_scalars, / max(pop, 1),
- *     p = max(1 - exp(-rate), 0).  Instead of an integer Poisson / ZINB count per node (host numpy RNG in the
- *     reference) it emits the per-node multiplier of the per-agent Bernoulli scheme (SURVEY App. F, F1 +
- *     importation gate):  q[n] = float(P_n * g_n), P_n = sum_s p[n,s]; g_n = 1 with local infectivity, else
- *     0 w.p. zero_inflation, else Gamma(r, 1/r) / (1 - zero_inflation), r = max(1, round(dispersion)).
+ *     p = max(1 - exp(-rate), 0), expected[n] = exposure[n] * sum_s p[n,s] (model.py:1363).
+ *     The reference then draws an integer count per node on the host (Poisson; zero-inflated NB for nodes without
+ *     local infectivity) and tx_infect_nb picks that many susceptibles by successive weighted sampling, which selects
+ *     agent i with probability 1 - exp(-w_i tau), tau fixed by the count.  Here the node's scale is solved for the
+ *     EXPECTED count instead:   sum_{i in S_n} (1 - exp(-w_i tau[n])) = expected[n] * g_n   (on risk_hist),
+ *     g_n = 1 with local infectivity, else 0 w.p. zero_inflation, else Gamma(r, 1/r) / (1 - zero_inflation),
+ *     r = max(1, round(dispersion)) (the ZINB as a zero-inflated gamma-Poisson mixture), so that independent per-agent
+ *     trials (lpk_tx_infect) have the reference's per-agent marginals and node means.  tau = 3e38 means "everybody"
+ *     (expected >= susceptibles - 0.5; the reference takes min(count, susceptibles)).
  *       network        double[num_nodes * num_nodes] row-major, W[i,j] = fraction moving i -> j
- *       r0_scalars     double[num_nodes]
- *       alive_counts   int32[num_nodes]  (results.pop[t], model.py:1344)
- *     outputs: q float[num_nodes], strain_cdf double[num_nodes * n_strains] (cumulative p[n,s]/P_n),
- *              prob double[num_nodes * n_strains], expected double[num_nodes] (exposure[n] * P_n, model.py:1363).
- *     rowsum_ws: caller-owned scratch, double[num_nodes] (row sums of W are recomputed every call because
- *     the reference re-reads tx.network each tick, model.py:1335). */
+ *       r0_scalars     double[num_nodes];  alive_counts int32[num_nodes] (results.pop[t], model.py:1344)
+ *     outputs: tau float[num_nodes], strain_cdf double[num_nodes * n_strains] (cumulative p[n,s] / P_n),
+ *              prob double[num_nodes * n_strains], expected double[num_nodes].
+ *     ws: caller-owned scratch, double[2 * num_nodes] (row sums of W, recomputed every call because the reference
+ *     re-reads tx.network each tick, model.py:1335; and the gated targets). */
 int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
-                     const double *network, double beta_seasonality, const double *r0_scalars,
-                     const int32_t *alive_counts, double zero_inflation, double dispersion, float *q,
-                     double *strain_cdf, double *prob, double *expected, double *rowsum_ws, const lpk_rng *rng,
-                     void *stream);
+                     const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
+                     const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau,
+                     double *strain_cdf, double *prob, double *expected, double *ws, const lpk_rng *rng, void *stream);
 
 /* T3  replaces tx_infect_nb(num_nodes, num_people, num_strains, sus_by_node, node_ids, strain, disease_state,
  *     sus_indices_storage, sus_probs_storage, risks, prob_exp_by_node_strain, n_exposures_to_create_by_node_strain)
  *     model.py:1010-1149.  Per-agent Bernoulli: susceptible i of node n is exposed iff
- *     x_i < floor(risk_i * q[n] * 2^32) with x_i word (i & 3) of Philox(seed; i >> 2, tick, EXPOSE); strain by
- *     the cumulative categorical of model.py:1127-1141.  No bucket pass, no scratch columns.
- *     n_new[num_nodes * num_strains] OVERWRITTEN (the reference returns it). */
+ *     x_i < floor(p_i * 2^32), p_i = 1 - exp(-risk_i * tau[n]) (evaluated by an exactly specified fmaf polynomial),
+ *     x_i = word (i & 3) of Philox(seed; i >> 2, tick, EXPOSE); strain by the cumulative categorical of
+ *     model.py:1127-1141.  No bucket pass, no scratch columns.  n_new[num_nodes * num_strains] OVERWRITTEN. */
 int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_strains, const int16_t *node_ids,
-                  int8_t *strain, int8_t *disease_state, const float *risks, const float *q,
+                  int8_t *strain, int8_t *disease_state, const float *risks, const float *tau,
                   const double *strain_cdf, int32_t *n_new, const lpk_rng *rng, void *stream);
 
 /* C1  replaces count_SEIRP(node_id, disease_state, strain, potentially_paralyzed, paralyzed, n_nodes, n_strains,
@@ -199,7 +206,7 @@ typedef struct lpk_tick_args {
     uint64_t seed, id_base;
     const int64_t *counts; /* device int64[2] = {agents alive-or-dead in the table when tick t-1 ended, agents now} */
     /* ---- pending exposure + census of tick t-1 (LPK_F_PENDING) */
-    const float *q_prev;    /* [nodes]          from lpk_tick_node / lpk_tx_node_math of tick t-1 */
+    const float *q_prev;    /* [nodes]  tau of tick t-1, from lpk_tick_node / lpk_tx_node_math */
     const double *cdf_prev; /* [nodes, strains] */
     int32_t *new_exposed_prev, *new_exposed_by_strain_prev; /* rows t-1, += */
     int32_t *S_prev, *R_prev, *E_by_strain_prev, *I_by_strain_prev; /* rows t-1, accumulate */
@@ -215,6 +222,7 @@ typedef struct lpk_tick_args {
     int32_t *new_exposed, *new_exposed_by_strain, *ri_new_exposed_by_strain; /* rows t */
     double strain_r0_scalars[LPK_MAX_STRAINS];
     int64_t *beta_fx, *exposure_fx, *sus; /* tally of tick t, += (lpk_tick_node zeroes the other parity buffer) */
+    int32_t *risk_hist;                   /* [nodes, LPK_RISK_BINS] of tick t, += (same) */
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
@@ -229,10 +237,11 @@ typedef struct lpk_node_args {
     uint64_t seed;
     /* transmission node math of tick t (same meaning as lpk_tx_node_math) */
     const int64_t *beta_fx, *exposure_fx;
+    const int32_t *risk_hist;
     const double *network, *r0_scalars;
     double beta_seasonality, zero_inflation, dispersion;
-    float *q;
-    double *strain_cdf, *prob, *expected, *rowsum_ws;
+    float *q; /* tau */
+    double *strain_cdf, *prob, *expected, *rowsum_ws; /* rowsum_ws: double[2 * nodes] */
     /* population bookkeeping: pop[t] = pop[t-1] + births[t] - deaths (model.py:1751-1755); NULL pop rows = no VD */
     const int32_t *pop_prev;
     int32_t *pop, *births_row, *deaths_row;
@@ -246,6 +255,7 @@ typedef struct lpk_node_args {
     int32_t *E_prev, *I_prev;
     /* tallies of the other parity, zeroed for tick t+1 */
     int64_t *next_beta_fx, *next_exposure_fx, *next_sus;
+    int32_t *next_risk_hist;
     int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
 } lpk_node_args;
 

@@ -16,6 +16,7 @@ SO_PATH = _HERE / "liblpk.so"
 
 LPK_OK, LPK_ERR_ARG, LPK_ERR_CUDA = 0, -1, -2
 MAX_STRAINS = 4
+RISK_BINS = 192
 FX_SCALE = float(2**30)
 
 EXPORTS = (
@@ -122,7 +123,7 @@ class TickArgs(C.Structure):
         ("ri_vaccinated", _VP), ("ri_protected", _VP), ("ipv_vaccinated", _VP),
         ("new_exposed", _VP), ("new_exposed_by_strain", _VP), ("ri_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
-        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP),
+        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP),
     ]
 
 
@@ -131,14 +132,14 @@ class NodeArgs(C.Structure):
 
     _fields_ = [
         ("flags", C.c_uint32), ("tick", C.c_int32), ("n_nodes", C.c_int32), ("n_strains", C.c_int32), ("seed", C.c_uint64),
-        ("beta_fx", _VP), ("exposure_fx", _VP), ("network", _VP), ("r0_scalars", _VP),
+        ("beta_fx", _VP), ("exposure_fx", _VP), ("risk_hist", _VP), ("network", _VP), ("r0_scalars", _VP),
         ("beta_seasonality", C.c_double), ("zero_inflation", C.c_double), ("dispersion", C.c_double),
         ("q", _VP), ("strain_cdf", _VP), ("prob", _VP), ("expected", _VP), ("rowsum_ws", _VP),
         ("pop_prev", _VP), ("pop", _VP), ("births_row", _VP), ("deaths_row", _VP),
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
         ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
-        ("next_beta_fx", _VP), ("next_exposure_fx", _VP), ("next_sus", _VP), ("counts", _VP),
+        ("next_beta_fx", _VP), ("next_exposure_fx", _VP), ("next_sus", _VP), ("next_risk_hist", _VP), ("counts", _VP),
     ]
 
 

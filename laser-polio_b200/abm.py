@@ -545,7 +545,7 @@ class Transmission_ABM:
         season = float(utils.get_seasonality(sim))
         K.tx_step_prep(n, count, ns, c["strain"], srs, c["disease_state"], c["node_id"], c["daily_infectivity"],
                        c["acq_risk_multiplier"], out=dev.tally)
-        beta_fx, exposure_fx, _ = dev.tally
+        beta_fx, exposure_fx, _, risk_hist = dev.tally
         if sim.shard is not None:  # the one per-tick exchange: every node's infectivity feeds the network transfer
             from . import sharding
 
@@ -553,7 +553,7 @@ class Transmission_ABM:
         r0s = self._r0_scalars_dev(dev)
         # results.pop[t] as it stands (all zeros when VitalDynamics_ABM is not a component -> divide by max(0, 1))
         pop = dev.pop_row(t)
-        q, cdf, _, _ = K.tx_node_math(beta_fx, exposure_fx, dev.network_tensor(self.network), season, r0s, pop,
+        q, cdf, _, _ = K.tx_node_math(beta_fx, exposure_fx, risk_hist, dev.network_tensor(self.network), season, r0s, pop,
                                       float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion),
                                       rng=sim.rng(), out=dev.node_out)
         K.tx_infect(n, count, ns, c["node_id"], c["strain"], c["disease_state"], c["acq_risk_multiplier"], q, cdf,

@@ -173,3 +173,71 @@ __device__ __forceinline__ void red_add(int64_t *p, long long v) {
 }
 
 __device__ __forceinline__ long long to_fx(double v) { return __double2ll_rn(v * LPK_FX_SCALE); }
+
+
+// ---------------------------------------------------------------- exposure probability and the risk histogram
+// Susceptible i of node n is exposed with probability p_i = 1 - exp(-risk_i * tau_n); tau_n solves
+// sum_i p_i = expected exposures of the node (include/lpk.h, T2/T3).  p_expose is specified with fmaf / floorf /
+// exact power-of-two scaling only, so a CPU restatement reproduces it bit for bit.
+__device__ __forceinline__ float p_expose(float x) {
+    if (!(x > 0.f)) return 0.f;
+    if (x < 0.0625f) {  // x - x^2/2 + x^3/6 - x^4/24 + x^5/120, relative error < 2e-9
+        float t = fmaf(-x, 0.008333333767950535f, 0.0416666679084301f);
+        t = fmaf(-x, t, 0.1666666716337204f);
+        t = fmaf(-x, t, 0.5f);
+        t = fmaf(-x, t, 1.0f);
+        return x * t;
+    }
+    if (x >= 17.f) return 1.f;
+    const float y = x * 1.4426950216293335f;  // log2(e)
+    const float n = floorf(y);
+    const float f = y - n;  // exact
+    float r = 0.00010938752529909834f;         // 2^-f on [0, 1), |error| < 8e-8
+    r = fmaf(r, f, -0.0012757162330672145f);
+    r = fmaf(r, f, 0.009580058045685291f);
+    r = fmaf(r, f, -0.05549103394150734f);
+    r = fmaf(r, f, 0.24022436141967773f);
+    r = fmaf(r, f, -0.6931470632553101f);
+    r = fmaf(r, f, 1.0f);
+    const float scale = __uint_as_float((uint32_t)(127 - (int)n) << 23);  // 2^-n, n in [0, 24]
+    return 1.f - r * scale;
+}
+// x < floor(p * 2^32) with p in [0, 1]; p == 1 always hits
+__device__ __forceinline__ bool expose_test(float p, uint32_t x) {
+    return (unsigned long long)x < __float2ull_rz(p * 4294967296.0f);
+}
+
+// risk histogram: 8 bins per octave over [2^-12, 2^12), clamped; non-positive / NaN weights fall in bin 0
+__device__ __forceinline__ int risk_bin(float w) {
+    if (!(w > 0.f)) return 0;
+    const int b = (int)(__float_as_uint(w) >> 20) - ((127 - 12) << 3);
+    return b < 0 ? 0 : (b >= LPK_RISK_BINS ? LPK_RISK_BINS - 1 : b);
+}
+__device__ __forceinline__ double risk_bin_weight(int b) {  // representative weight: middle of the bin
+    return ldexp(1.0 + ((double)(b & 7) + 0.5) / 8.0, (b >> 3) - 12);
+}
+
+// per-warp shared-memory histogram of the current node's susceptibles, flushed to global on node change
+struct WarpHist {
+    int *h;
+    int node;  // warp-uniform
+    __device__ __forceinline__ void init(int *smem, int lane) {
+        h = smem; node = -1;
+        for (int b = lane; b < LPK_RISK_BINS; b += 32) h[b] = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void flush(int32_t *g, int lane) {
+        __syncwarp();
+        if (node >= 0) {
+            for (int b = lane; b < LPK_RISK_BINS; b += 32) {
+                const int v = h[b];
+                if (v) { atomicAdd(&g[(int64_t)node * LPK_RISK_BINS + b], v); h[b] = 0; }
+            }
+        }
+        __syncwarp();
+    }
+    // make `nd` (warp-uniform) the current node
+    __device__ __forceinline__ void select(int nd, int32_t *g, int lane) {
+        if (nd != node) { flush(g, lane); node = nd; }
+    }
+};

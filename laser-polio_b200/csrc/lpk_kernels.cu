@@ -304,11 +304,14 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_step_prep(int64_t n, int n_str
                                                              const int16_t *__restrict__ node_id,
                                                              const float *__restrict__ infectivity,
                                                              const float *__restrict__ risk, int64_t *beta_fx,
-                                                             int64_t *exposure_fx, int64_t *sus) {
+                                                             int64_t *exposure_fx, int64_t *sus, int32_t *risk_hist) {
+    __shared__ int s_hist[LPK_WARPS][LPK_RISK_BINS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileRange tr = block_tiles(n);
     NodeAcc<1, 1 + LPK_MAX_STRAINS> acc;
     acc.init();
+    WarpHist wh;
+    wh.init(s_hist[warp], lane);
     auto flush = [&](int nd, const int *ci, const long long *cl) {
         if (ci[0]) atomicAdd(reinterpret_cast<unsigned long long *>(&sus[nd]), (unsigned long long)ci[0]);
         red_add(&exposure_fx[nd], cl[0]);
@@ -329,11 +332,22 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_step_prep(int64_t n, int n_str
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool anyS = any_byte_eq(w[j], 0u), anyI = any_byte_eq(w[j], 2u);
-            if (!(anyS || anyI)) continue;
-            int nd[4];
-            load_s4(node_id, base[j], valid[j], nd);
+            int nd[4] = {-1, -1, -1, -1};
             float rk[4] = {0.f, 0.f, 0.f, 0.f};
+            if (anyS || anyI) load_s4(node_id, base[j], valid[j], nd);
             if (anyS) load_f4(risk, base[j], valid[j], rk);
+            // the histogram of the susceptibles' risks goes through the warp's shared-memory bins when the whole warp is
+            // on one node (the common case); quads with mixed nodes fall back to global atomics
+            int mine = -1;  // -1: no susceptible in this quad, -2: its susceptibles sit in different nodes
+            if (anyS) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (byte_of(w[j], k) == 0) mine = (mine == -1 || mine == nd[k]) ? nd[k] : -2;
+            }
+            const int ref = __reduce_max_sync(LPK_FULL, mine);
+            const bool uni = ref >= 0 && __all_sync(LPK_FULL, mine == ref || mine == -1);
+            if (uni) wh.select(ref, risk_hist, lane);
+            if (!(anyS || anyI)) continue;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int8_t s = byte_of(w[j], k);
@@ -341,6 +355,8 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_step_prep(int64_t n, int n_str
                     acc.select(nd[k], flush);
                     acc.ci[0] += 1;
                     acc.cl[0] += to_fx((double)rk[k]);
+                    if (uni) atomicAdd(&wh.h[risk_bin(rk[k])], 1);
+                    else atomicAdd(&risk_hist[(int64_t)nd[k] * LPK_RISK_BINS + risk_bin(rk[k])], 1);
                 } else if (s == 2) {
                     acc.select(nd[k], flush);
                     const int stn = strain[base[j] + k];
@@ -352,27 +368,29 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_step_prep(int64_t n, int n_str
             }
         }
     }
+    wh.flush(risk_hist, lane);
     acc.finish_warp(flush);
 }
 extern "C" int lpk_tx_step_prep(int32_t num_nodes, int64_t num_people, int32_t n_strains, const int8_t *strains,
                                 const double *h_strain_r0_scalars, const int8_t *disease_states,
                                 const int16_t *node_ids, const float *daily_infectivity, const float *risks,
-                                int64_t *beta_fx, int64_t *exposure_fx, int64_t *sus, void *stream) {
+                                int64_t *beta_fx, int64_t *exposure_fx, int64_t *sus, int32_t *risk_hist, void *stream) {
     REQUIRE(num_nodes > 0 && num_people >= 0, "tx_step_prep sizes");
     REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "tx_step_prep n_strains");
     REQUIRE(strains && h_strain_r0_scalars && disease_states && node_ids && daily_infectivity && risks && beta_fx &&
-                exposure_fx && sus, "tx_step_prep null pointer");
+                exposure_fx && sus && risk_hist, "tx_step_prep null pointer");
     REQUIRE(ALIGNED(disease_states, 4) && ALIGNED(node_ids, 8) && ALIGNED(risks, 16), "tx_step_prep alignment");
     cudaStream_t st = as_stream(stream);
     CUDA_TRY(cudaMemsetAsync(beta_fx, 0, sizeof(int64_t) * num_nodes * n_strains, st), "tx_step_prep memset");
     CUDA_TRY(cudaMemsetAsync(exposure_fx, 0, sizeof(int64_t) * num_nodes, st), "tx_step_prep memset");
     CUDA_TRY(cudaMemsetAsync(sus, 0, sizeof(int64_t) * num_nodes, st), "tx_step_prep memset");
+    CUDA_TRY(cudaMemsetAsync(risk_hist, 0, sizeof(int32_t) * num_nodes * LPK_RISK_BINS, st), "tx_step_prep memset");
     if (num_people == 0) return LPK_OK;
     StrainScalars srs;
     for (int s = 0; s < LPK_MAX_STRAINS; ++s) srs.v[s] = s < n_strains ? h_strain_r0_scalars[s] : 0.0;
     k_tx_step_prep<<<agent_grid(num_people, 8), LPK_BLOCK, 0, st>>>(num_people, n_strains, strains, srs, disease_states,
                                                                     node_ids, daily_infectivity, risks, beta_fx,
-                                                                    exposure_fx, sus);
+                                                                    exposure_fx, sus, risk_hist);
     CUDA_TRY(cudaGetLastError(), "lpk_tx_step_prep");
     return LPK_OK;
 }
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strain
                                                           int8_t *strain, int8_t *__restrict__ state,
                                                           const float *__restrict__ risk, const float *__restrict__ q,
                                                           const double *__restrict__ strain_cdf, int32_t *n_new,
-                                                          DevRng rng) {
+                                                          DevRng rng) {  // q = tau[nodes]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileRange tr = block_tiles(n);
     NodeAcc<LPK_MAX_STRAINS, 0> acc;
@@ -523,7 +541,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strain
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!(qn[k] > 0.f)) continue;
-                if (!expose_hit(__fmul_rn(rk[k], qn[k]), x[k])) continue;
+                if (!expose_test(p_expose(__fmul_rn(rk[k], qn[k])), x[k])) continue;
                 const int64_t i = base[j] + k;
                 double r;
                 if (rng.u2) r = rng.u2[i];
@@ -601,7 +619,7 @@ __global__ void __launch_bounds__(256) k_tx_node_math(int n, int n_strains, cons
                                                        const double *__restrict__ W, const double *__restrict__ rowsum,
                                                        double season, const double *__restrict__ r0_scalars,
                                                        const int32_t *__restrict__ alive, double zi, double disp_r,
-                                                       float *q, double *strain_cdf, double *prob, double *expected,
+                                                       double *target, double *strain_cdf, double *prob, double *expected,
                                                        uint64_t seed, uint32_t tick) {
     __shared__ double part[8][LPK_MAX_STRAINS][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -642,37 +660,94 @@ __global__ void __launch_bounds__(256) k_tx_node_math(int n, int n_strains, cons
         run += (P > 0.0) ? p[s] / P : 0.0;
         strain_cdf[(int64_t)j * n_strains + s] = run;
     }
-    expected[j] = ((double)exposure_fx[j] / LPK_FX_SCALE) * P;
+    const double e = ((double)exposure_fx[j] / LPK_FX_SCALE) * P;  // model.py:1363
+    expected[j] = e;
     double g = 1.0;
     if (local == 0.0 && P > 0.0) g = importation_multiplier(seed, (uint32_t)j, tick, zi, disp_r);
-    q[j] = (float)(P * g);
+    target[j] = e * g;  // expected number of exposures the node's susceptibles must realise this tick
+}
+
+// tau[n]: sum over the node's susceptibles of (1 - exp(-risk * tau)) = target[n], on the risk histogram.
+// Successive weighted sampling without replacement of K agents (the reference, model.py:1096-1122) selects agent i with
+// probability 1 - exp(-w_i tau), tau fixed by the count; solving for the EXPECTED count gives independent per-agent
+// trials with the same marginals and the same node mean.  One warp per node, 6 bins per lane; Newton from the left of a
+// concave increasing function converges monotonically.
+__global__ void __launch_bounds__(256) k_tx_solve_tau(int n, const int32_t *__restrict__ hist, const double *__restrict__ target,
+                                                       float *__restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= n) return;
+    double h[LPK_RISK_BINS / 32], w[LPK_RISK_BINS / 32];
+    double S = 0.0, Wsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < LPK_RISK_BINS / 32; ++i) {
+        const int b = lane + 32 * i;
+        h[i] = (double)hist[(int64_t)j * LPK_RISK_BINS + b];
+        w[i] = risk_bin_weight(b);
+        S += h[i];
+        Wsum += h[i] * w[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { S += __shfl_xor_sync(LPK_FULL, S, o); Wsum += __shfl_xor_sync(LPK_FULL, Wsum, o); }
+    S = __shfl_sync(LPK_FULL, S, 0);
+    Wsum = __shfl_sync(LPK_FULL, Wsum, 0);
+    const double E = target[j];
+    double t = 0.0;
+    if (E > 0.0 && S > 0.0) {
+        if (E >= S - 0.5) {
+            t = 3.0e38;  // more exposures expected than susceptibles exist: everybody (reference: size = min(K, S))
+        } else {
+            t = E / Wsum;
+            for (int it = 0; it < 64; ++it) {
+                double F = 0.0, dF = 0.0;
+#pragma unroll
+                for (int i = 0; i < LPK_RISK_BINS / 32; ++i) {
+                    const double em = expm1(-w[i] * t);
+                    F -= h[i] * em;
+                    dF += h[i] * w[i] * (em + 1.0);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { F += __shfl_xor_sync(LPK_FULL, F, o); dF += __shfl_xor_sync(LPK_FULL, dF, o); }
+                F = __shfl_sync(LPK_FULL, F, 0);
+                dF = __shfl_sync(LPK_FULL, dF, 0);
+                const double step = (E - F) / dF;
+                if (!(step > 0.0)) break;
+                t += step;
+                if (step <= 1e-13 * t) break;
+            }
+        }
+    }
+    if (lane == 0) tau[j] = (float)(t > 3.0e38 ? 3.0e38 : t);
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
-                         const double *network, double beta_seasonality, const double *r0_scalars, const int32_t *alive_counts,
-                         double zero_inflation, double dispersion, float *q, double *strain_cdf, double *prob, double *expected,
-                         double *rowsum_ws, uint64_t seed, uint32_t tick, cudaStream_t st) {
-    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum_ws);
+                         const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
+                         const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st) {
+    double *rowsum = ws, *target = ws + num_nodes;
+    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
     CUDA_TRY(cudaGetLastError(), "node_math rowsums");
     double r = nearbyint(dispersion);
     if (r < 1.0) r = 1.0;
-    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum_ws,
-                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, q,
+    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
+                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
                                                           strain_cdf, prob, expected, seed, tick);
     CUDA_TRY(cudaGetLastError(), "node_math");
+    k_tx_solve_tau<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, risk_hist, target, tau);
+    CUDA_TRY(cudaGetLastError(), "node_math tau");
     return LPK_OK;
 }
 
 extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
-                                const double *network, double beta_seasonality, const double *r0_scalars,
-                                const int32_t *alive_counts, double zero_inflation, double dispersion, float *q,
-                                double *strain_cdf, double *prob, double *expected, double *rowsum_ws, const lpk_rng *rng,
-                                void *stream) {
+                                const int32_t *risk_hist, const double *network, double beta_seasonality,
+                                const double *r0_scalars, const int32_t *alive_counts, double zero_inflation,
+                                double dispersion, float *tau, double *strain_cdf, double *prob, double *expected,
+                                double *ws, const lpk_rng *rng, void *stream) {
     REQUIRE(num_nodes > 0, "tx_node_math sizes");
     REQUIRE(n_strains >= 1 && n_strains <= LPK_MAX_STRAINS, "tx_node_math n_strains");
-    REQUIRE(beta_fx && exposure_fx && network && r0_scalars && alive_counts && q && strain_cdf && prob && expected &&
-                rowsum_ws, "tx_node_math null pointer");
-    return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, network, beta_seasonality, r0_scalars, alive_counts,
-                                zero_inflation, dispersion, q, strain_cdf, prob, expected, rowsum_ws, rng ? rng->seed : 0,
-                                rng ? rng->tick : 0, as_stream(stream));
+    REQUIRE(beta_fx && exposure_fx && risk_hist && network && r0_scalars && alive_counts && tau && strain_cdf && prob &&
+                expected && ws, "tx_node_math null pointer");
+    return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
+                                alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream));
 }

@@ -137,8 +137,8 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
         const int nd = P.node_id[i];
         if (pending && i < count_prev) {
             if (s == 0) {
-                const float q = A.q_prev[nd];
-                if (q > 0.f && expose_hit(__fmul_rn(P.acq_risk_multiplier[i], q), x[k])) { expose_agent(pp, i, nd); s = 1; }
+                const float tau = A.q_prev[nd];
+                if (tau > 0.f && expose_test(p_expose(__fmul_rn(P.acq_risk_multiplier[i], tau)), x[k])) { expose_agent(pp, i, nd); s = 1; }
             }
             if (s == 0) atomicAdd(&A.S_prev[nd], 1);
             else if (s == 3) atomicAdd(&A.R_prev[nd], 1);
@@ -155,8 +155,10 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
         const int64_t i = b + k;
         if (s == 0) {
             const int nd = P.node_id[i];
+            const float rk = P.acq_risk_multiplier[i];
             atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), 1ull);
-            red_add(&A.exposure_fx[nd], __float2ll_rn(P.acq_risk_multiplier[i] * 1073741824.0f));
+            red_add(&A.exposure_fx[nd], __float2ll_rn(rk * 1073741824.0f));
+            atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], 1);
         } else if (s == 2) {
             tally_infectious(pp, i, P.node_id[i]);
         }
@@ -246,6 +248,7 @@ __device__ __noinline__ void active_agent(const PassParams &pp, int64_t block_ba
 template <bool kDeaths, bool kRI>
 __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
     __shared__ uint2 queue[LPK_WARPS][QCAP];
+    __shared__ int s_hist[LPK_WARPS][LPK_RISK_BINS];
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,6 +265,8 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
 
     TickAcc acc;
     acc.init();
+    WarpHist wh;
+    wh.init(s_hist[warp], lane);
     auto flush = [&](int nd, const int *ci, const long long *cl) {
         red_add(&A.S_prev[nd], ci[CI_S]);
         red_add(&A.R_prev[nd], ci[CI_R]);
@@ -290,6 +295,8 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         const int64_t b = (row * 32 + lane) * 4;
         uint32_t cand = 0u, hits = 0u, nw = w;  // cand/hits: bit k = agent k of the quad goes to the active queue
         int nd = cur.tn;
+        const bool row_uniform = cur.tn >= 0;  // warp-uniform: the row lies in one node-uniform tile
+        if (row_uniform) wh.select(cur.tn, A.risk_hist, lane);
         if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
             const int valid = quad_valid(b, n);
             bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
@@ -310,12 +317,10 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                         if (qn > 0.f) {
                             uint32_t x[4];
                             philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
-                            // x < floor(risk * q * 2^32), saturating: the same predicate as expose_hit() (p >= 1 always
-                            // hits, p <= 0 / NaN never) in three instructions per agent; scaling q by 2^32 is exact
-                            const float q32 = qn * 4294967296.0f;
+                            // p_i = 1 - exp(-risk_i * tau_n); hit iff x_i < floor(p_i * 2^32)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const bool hit = ((mS >> (8 * k)) & 1u) && ((unsigned long long)x[k] < __float2ull_rz(__fmul_rn(rk[k], q32)));
+                                const bool hit = ((mS >> (8 * k)) & 1u) && expose_test(p_expose(__fmul_rn(rk[k], qn)), x[k]);
                                 hits |= hit ? (1u << k) : 0u;
                             }
                             nw |= ((hits & 1u) | ((hits & 2u) << 7) | ((hits & 4u) << 14) | ((hits & 8u) << 21));  // S (0) -> E (1)
@@ -360,8 +365,13 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                 const uint32_t mS2 = __vcmpeq4(nw, 0u);
                 acc.ci[CI_SUS] += __popc(mS2) >> 3;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc.cl[CL_EXPO] += ((mS2 >> (8 * k)) & 1u) ? __float2ll_rn(rk[k] * 1073741824.0f) : 0ll;
+                for (int k = 0; k < 4; ++k) {
+                    if ((mS2 >> (8 * k)) & 1u) {
+                        acc.cl[CL_EXPO] += __float2ll_rn(rk[k] * 1073741824.0f);
+                        if (row_uniform) atomicAdd(&wh.h[risk_bin(rk[k])], 1);
+                        else atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk[k])], 1);
+                    }
+                }
             }
             if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
@@ -390,6 +400,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
     __syncwarp();
     if (lane < q_count) active_agent(pp, block_base, q[(q_head + lane) & (QCAP - 1)]);
     __syncwarp();
+    wh.flush(A.risk_hist, lane);
     acc.finish_warp(flush);
 }
 
@@ -404,7 +415,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     REQUIRE(ALIGNED(P.disease_state, 4) && ALIGNED(P.node_id, 8) && ALIGNED(P.acq_risk_multiplier, 16), "tick_pass alignment");
     REQUIRE((A.flags & LPK_F_STAGES) != 0, "tick_pass always runs the stages of its tick (LPK_F_STAGES)");
     REQUIRE((A.id_base & 3) == 0, "tick_pass id_base must be a multiple of 4");
-    REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus, "tick_pass stage outputs");
+    REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus && A.risk_hist, "tick_pass stage outputs");
     REQUIRE(A.S_prev && A.R_prev && A.E_by_strain_prev && A.I_by_strain_prev && A.new_exposed_prev && A.new_exposed_by_strain_prev,
             "tick_pass census rows");
     if (A.flags & LPK_F_PENDING) REQUIRE(A.q_prev && A.cdf_prev, "tick_pass pending exposure inputs");
@@ -491,25 +502,27 @@ __global__ void k_tick_epilogue(lpk_node_args a) {
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
-                         const double *network, double beta_seasonality, const double *r0_scalars, const int32_t *alive_counts,
-                         double zero_inflation, double dispersion, float *q, double *strain_cdf, double *prob, double *expected,
-                         double *rowsum_ws, uint64_t seed, uint32_t tick, cudaStream_t st);
+                         const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
+                         const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
     const lpk_node_args &a = *args;
     REQUIRE(a.n_nodes > 0 && a.n_strains >= 1 && a.n_strains <= LPK_MAX_STRAINS, "tick_node sizes");
-    REQUIRE(a.beta_fx && a.exposure_fx && a.network && a.r0_scalars && a.q && a.strain_cdf && a.prob && a.expected && a.rowsum_ws,
-            "tick_node node-math pointers");
+    REQUIRE(a.beta_fx && a.exposure_fx && a.risk_hist && a.network && a.r0_scalars && a.q && a.strain_cdf && a.prob && a.expected &&
+                a.rowsum_ws, "tick_node node-math pointers");
     REQUIRE(!a.pop || (a.pop_prev && (!(a.flags & LPK_F_DEATHS) || (a.deaths_row && a.deaths))), "tick_node population rows");
     REQUIRE(!a.cur_potp || (a.cur_p && a.new_potential && a.new_paralyzed && a.potp_row && a.p_row), "tick_node paralysis rows");
     REQUIRE(!a.deaths || (a.dead_pp && a.dead_par), "tick_node death scratch");
-    REQUIRE(!a.next_beta_fx || (a.next_exposure_fx && a.next_sus), "tick_node next tallies");
+    REQUIRE(!a.next_beta_fx || (a.next_exposure_fx && a.next_sus && a.next_risk_hist), "tick_node next tallies");
     REQUIRE(a.pop || a.pop_prev, "tick_node needs a population row for the rate denominator");
     cudaStream_t st = as_stream(stream);
     k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
-    return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.network, a.beta_seasonality, a.r0_scalars,
-                                a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob, a.expected,
-                                a.rowsum_ws, a.seed, (uint32_t)a.tick, st);
+    if (a.next_risk_hist)
+        CUDA_TRY(cudaMemsetAsync(a.next_risk_hist, 0, sizeof(int32_t) * (size_t)a.n_nodes * LPK_RISK_BINS, st), "lpk_tick_node hist");
+    return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
+                                a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
+                                a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st);
 }

@@ -62,11 +62,13 @@ class DeviceState:
         self.node_offsets_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)
         self.tile_node = None  # owned by engine.FusedEngine when ticks are fused
         self.scratch_i32 = [torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(4)]
+        from ._lpk import RISK_BINS
+
         self.tally = (torch.zeros((n, ns), dtype=torch.int64, device=dev), torch.zeros(n, dtype=torch.int64, device=dev),
-                      torch.zeros(n, dtype=torch.int64, device=dev))
+                      torch.zeros(n, dtype=torch.int64, device=dev), torch.zeros((n, RISK_BINS), dtype=torch.int32, device=dev))
         self.node_out = (torch.zeros(n, dtype=torch.float32, device=dev), torch.zeros((n, ns), dtype=torch.float64, device=dev),
                          torch.zeros((n, ns), dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev),
-                         torch.zeros(n, dtype=torch.float64, device=dev))
+                         torch.zeros(2 * n, dtype=torch.float64, device=dev))
         self.n_new = torch.zeros((n, ns), dtype=torch.int32, device=dev)
         mk = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
         self.census = (mk(n), mk(n), mk(n), mk(n), mk(n, ns), mk(n, ns), mk(n), mk(n))

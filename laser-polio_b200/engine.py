@@ -53,14 +53,14 @@ class FusedEngine:
         dev.set_count(sim.people.count)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=d)  # noqa: E731
         i64 = lambda *s: torch.zeros(s, dtype=torch.int64, device=d)  # noqa: E731
-        self.tally = [(i64(n, ns), i64(n), i64(n)) for _ in range(2)]
+        self.tally = [(i64(n, ns), i64(n), i64(n), i32(n, _lpk.RISK_BINS)) for _ in range(2)]
         self.deaths, self.dead_pp, self.dead_par = i32(n), i32(n), i32(n)
         self.cur_potp, self.cur_p = i32(n), i32(n)
         self.q = torch.zeros(n, dtype=torch.float32, device=d)
         self.cdf = torch.zeros((n, ns), dtype=torch.float64, device=d)
         self.prob = torch.zeros((n, ns), dtype=torch.float64, device=d)
         self.expected = torch.zeros(n, dtype=torch.float64, device=d)
-        self.rowsum = torch.zeros(n, dtype=torch.float64, device=d)
+        self.rowsum = torch.zeros(2 * n, dtype=torch.float64, device=d)
         self.dummy_row = i32(n * max(ns, 1))  # sink for rows of components that are absent
         if sim.t > 0:  # resuming mid-run: re-base the incremental paralysis census on the last logged row
             self.cur_potp.copy_(dev.res["potentially_paralyzed"][sim.t - 1])
@@ -156,10 +156,10 @@ class FusedEngine:
             A.ri_new_exposed_by_strain = dp(self._row("ri_new_exposed_by_strain", t))
         for s, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
             A.strain_r0_scalars[s] = float(v)
-        beta_fx, exposure_fx, sus = self.tally[t & 1]
+        beta_fx, exposure_fx, sus, risk_hist = self.tally[t & 1]
         if not self.pending:  # the previous tick was not fused, so nobody zeroed this parity
-            beta_fx.zero_(), exposure_fx.zero_(), sus.zero_()
-        A.beta_fx, A.exposure_fx, A.sus = dp(beta_fx), dp(exposure_fx), dp(sus)
+            beta_fx.zero_(), exposure_fx.zero_(), sus.zero_(), risk_hist.zero_()
+        A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
         A.flags = flags
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
 
@@ -170,7 +170,7 @@ class FusedEngine:
         N = NodeArgs()
         N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
         N.seed = A.seed
-        N.beta_fx, N.exposure_fx = dp(beta_fx), dp(exposure_fx)
+        N.beta_fx, N.exposure_fx, N.risk_hist = dp(beta_fx), dp(exposure_fx), dp(risk_hist)
         N.network, N.r0_scalars = dp(dev.network_tensor(tx.network)), dp(tx._r0_scalars_dev(dev))
         N.beta_seasonality = float(self._seasonality())
         N.zero_inflation, N.dispersion = float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion)
@@ -188,10 +188,10 @@ class FusedEngine:
         N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
         N.E_by_strain_prev, N.I_by_strain_prev = A.E_by_strain_prev, A.I_by_strain_prev
         N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
-        nb, ne, nsus = self.tally[(t + 1) & 1]
-        N.next_beta_fx, N.next_exposure_fx, N.next_sus = dp(nb), dp(ne), dp(nsus)
+        nb, ne, nsus, nh = self.tally[(t + 1) & 1]
+        N.next_beta_fx, N.next_exposure_fx, N.next_sus, N.next_risk_hist = dp(nb), dp(ne), dp(nsus), dp(nh)
         N.counts = dp(dev.counts)
-        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 3)
+        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 4)
         self.pending = True
 
     def _seasonality(self):

@@ -77,47 +77,49 @@ def fast_sia(node_ids, disease_states, strain, dobs, sim_t, vx_prob, vx_eff, cou
 
 def tx_step_prep(num_nodes, num_people, n_strains, strains, strain_r0_scalars, disease_states, node_ids,
                  daily_infectivity, risks, out=None):
-    """reference model.py:932-942.  Returns (beta_fx int64[nodes, strains], exposure_fx int64[nodes], sus int64[nodes]);
-    the float tallies are exact 2^30 fixed point (divide by ``FX_SCALE``)."""
+    """reference model.py:932-942.  Returns (beta_fx int64[nodes, strains], exposure_fx int64[nodes], sus int64[nodes],
+    risk_hist int32[nodes, RISK_BINS]); the float tallies are exact 2^30 fixed point (divide by ``FX_SCALE``)."""
     dev = disease_states.device
     if out is None:
         out = (torch.empty((num_nodes, n_strains), dtype=torch.int64, device=dev),
-               torch.empty(num_nodes, dtype=torch.int64, device=dev), torch.empty(num_nodes, dtype=torch.int64, device=dev))
-    beta_fx, exposure_fx, sus = out
+               torch.empty(num_nodes, dtype=torch.int64, device=dev), torch.empty(num_nodes, dtype=torch.int64, device=dev),
+               torch.empty((num_nodes, _lpk.RISK_BINS), dtype=torch.int32, device=dev))
+    beta_fx, exposure_fx, sus, risk_hist = out
     srs = (C.c_double * n_strains)(*[float(v) for v in strain_r0_scalars])
     check(_lpk.lib().lpk_tx_step_prep(
         C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(n_strains), ptr(strains), srs, ptr(disease_states),
-        ptr(node_ids), ptr(daily_infectivity), ptr(risks), ptr(beta_fx), ptr(exposure_fx), ptr(sus), stream_handle(),
+        ptr(node_ids), ptr(daily_infectivity), ptr(risks), ptr(beta_fx), ptr(exposure_fx), ptr(sus), ptr(risk_hist),
+        stream_handle(),
     ), "lpk_tx_step_prep")
-    return beta_fx, exposure_fx, sus
+    return beta_fx, exposure_fx, sus, risk_hist
 
 
-def tx_node_math(beta_fx, exposure_fx, network, beta_seasonality, r0_scalars, alive_counts, zero_inflation, dispersion,
-                 rng=None, out=None):
+def tx_node_math(beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars, alive_counts, zero_inflation,
+                 dispersion, rng=None, out=None):
     """Node-level block of Transmission_ABM.step (reference model.py:1332-1351, 1362-1407) on the device.
-    Returns (q float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected float64[nodes])."""
+    Returns (tau float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected float64[nodes])."""
     n, ns = beta_fx.shape
     dev = beta_fx.device
     if out is None:
         out = (torch.empty(n, dtype=torch.float32, device=dev), torch.empty((n, ns), dtype=torch.float64, device=dev),
                torch.empty((n, ns), dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev),
-               torch.empty(n, dtype=torch.float64, device=dev))
-    q, cdf, prob, expected, ws = out
+               torch.empty(2 * n, dtype=torch.float64, device=dev))
+    tau, cdf, prob, expected, ws = out
     check(_lpk.lib().lpk_tx_node_math(
-        C.c_int32(n), C.c_int32(ns), ptr(beta_fx), ptr(exposure_fx), ptr(network), C.c_double(beta_seasonality),
-        ptr(r0_scalars), ptr(alive_counts), C.c_double(zero_inflation), C.c_double(dispersion), ptr(q), ptr(cdf),
+        C.c_int32(n), C.c_int32(ns), ptr(beta_fx), ptr(exposure_fx), ptr(risk_hist), ptr(network), C.c_double(beta_seasonality),
+        ptr(r0_scalars), ptr(alive_counts), C.c_double(zero_inflation), C.c_double(dispersion), ptr(tau), ptr(cdf),
         ptr(prob), ptr(expected), ptr(ws), _rng_ref(rng), stream_handle(),
     ), "lpk_tx_node_math")
-    return q, cdf, prob, expected
+    return tau, cdf, prob, expected
 
 
-def tx_infect(num_nodes, num_people, num_strains, node_ids, strain, disease_state, risks, q, strain_cdf, rng=None,
+def tx_infect(num_nodes, num_people, num_strains, node_ids, strain, disease_state, risks, tau, strain_cdf, rng=None,
               out=None):
     """reference model.py:1011-1024 (per-agent Bernoulli scheme, see include/lpk.h T3); returns n_new int32[nodes, strains]."""
     n_new = out if out is not None else torch.empty((num_nodes, num_strains), dtype=torch.int32, device=disease_state.device)
     check(_lpk.lib().lpk_tx_infect(
         C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(num_strains), ptr(node_ids), ptr(strain),
-        ptr(disease_state), ptr(risks), ptr(q), ptr(strain_cdf), ptr(n_new), _rng_ref(rng), stream_handle(),
+        ptr(disease_state), ptr(risks), ptr(tau), ptr(strain_cdf), ptr(n_new), _rng_ref(rng), stream_handle(),
     ), "lpk_tx_infect")
     return n_new
 
@@ -144,7 +146,7 @@ class LaunchStats:
     launching stream so bench.py can report each kernel's average device time inside the timed region."""
 
     KERNELS_PER_CALL = {"get_deaths": 1, "disease_state_step": 1, "fast_ri": 1, "fast_sia": 1, "tx_step_prep": 1,
-                        "tx_node_math": 2, "tx_infect": 1, "count_SEIRP": 2}
+                        "tx_node_math": 3, "tx_infect": 1, "count_SEIRP": 2}
 
     def __init__(self):
         self.reset()

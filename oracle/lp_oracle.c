@@ -88,6 +88,46 @@ double orc_uniform53(uint64_t seed, uint64_t idx, uint32_t tick, uint32_t stage,
 }
 
 #define ORC_FX_SCALE 1073741824.0 /* 2^30 fixed-point scale of the float tallies */
+#define ORC_RISK_BINS 192         /* risk histogram: 8 bins per octave over [2^-12, 2^12) */
+
+/* bin of a susceptible's acq_risk_multiplier: (exponent, top three mantissa bits) relative to 2^-12, clamped */
+static inline int risk_bin(float w) {
+    if (!(w > 0.f)) return 0;
+    uint32_t bits;
+    memcpy(&bits, &w, 4);
+    int b = (int)(bits >> 20) - ((127 - 12) << 3);
+    return b < 0 ? 0 : (b >= ORC_RISK_BINS ? ORC_RISK_BINS - 1 : b);
+}
+
+/* 1 - exp(-x) for x >= 0 through fmaf / floorf / exact power-of-two scaling only (bit-identical on the device) */
+static inline float p_expose(float x) {
+    if (!(x > 0.f)) return 0.f;
+    if (x < 0.0625f) {
+        float t = fmaf(-x, 0.008333333767950535f, 0.0416666679084301f);
+        t = fmaf(-x, t, 0.1666666716337204f);
+        t = fmaf(-x, t, 0.5f);
+        t = fmaf(-x, t, 1.0f);
+        return x * t;
+    }
+    if (x >= 17.f) return 1.f;
+    const float y = x * 1.4426950216293335f;
+    const float n = floorf(y);
+    const float f = y - n;
+    float r = 0.00010938752529909834f;
+    r = fmaf(r, f, -0.0012757162330672145f);
+    r = fmaf(r, f, 0.009580058045685291f);
+    r = fmaf(r, f, -0.05549103394150734f);
+    r = fmaf(r, f, 0.24022436141967773f);
+    r = fmaf(r, f, -0.6931470632553101f);
+    r = fmaf(r, f, 1.0f);
+    uint32_t sb = (uint32_t)(127 - (int)n) << 23;
+    float scale;
+    memcpy(&scale, &sb, 4);
+    return 1.f - r * scale;
+}
+
+float orc_p_expose(float x) { return p_expose(x); }
+int orc_risk_bin(float w) { return risk_bin(w); }
 
 static int32_t *tl_alloc(int n_threads, int64_t n) {
     return (int32_t *)calloc((size_t)n_threads * (size_t)n, sizeof(int32_t));
@@ -247,7 +287,7 @@ void orc_fast_sia(const int16_t *node_id, int8_t *state, int8_t *strain, const i
 void orc_tx_step_prep(int32_t n_nodes, int64_t n_people, int32_t n_strains, const int8_t *strain,
                       const double *strain_r0_scalars, const int8_t *state, const int16_t *node_id,
                       const float *infectivity, const float *risk, int mode, double *beta_out,
-                      double *exposure_out, int64_t *sus_out, int64_t *beta_fx, int64_t *exposure_fx) {
+                      double *exposure_out, int64_t *sus_out, int64_t *beta_fx, int64_t *exposure_fx, int32_t *risk_hist) {
     int nt = omp_get_max_threads();
     int64_t nb = (int64_t)n_nodes * n_strains;
     float *f_beta = NULL, *f_exp = NULL;
@@ -257,6 +297,7 @@ void orc_tx_step_prep(int32_t n_nodes, int64_t n_people, int32_t n_strains, cons
     if (mode == 1) { d_beta = calloc((size_t)nt * nb, sizeof(double)); d_exp = calloc((size_t)nt * n_nodes, sizeof(double)); }
     if (mode == 2) { x_beta = calloc((size_t)nt * nb, sizeof(int64_t)); x_exp = calloc((size_t)nt * n_nodes, sizeof(int64_t)); }
     int32_t *tl_sus = tl_alloc(nt, n_nodes);
+    int32_t *tl_hist = risk_hist ? tl_alloc(nt, (int64_t)n_nodes * ORC_RISK_BINS) : NULL;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n_people; ++i) {
         int tid = omp_get_thread_num();
@@ -264,6 +305,7 @@ void orc_tx_step_prep(int32_t n_nodes, int64_t n_people, int32_t n_strains, cons
         int32_t nid = node_id[i];
         if (s == 0) {
             tl_sus[(int64_t)tid * n_nodes + nid] += 1;
+            if (tl_hist) tl_hist[((int64_t)tid * n_nodes + nid) * ORC_RISK_BINS + risk_bin(risk[i])] += 1;
             if (mode == 0) f_exp[(int64_t)tid * n_nodes + nid] += risk[i];
             else if (mode == 1) d_exp[(int64_t)tid * n_nodes + nid] += (double)risk[i];
             else x_exp[(int64_t)tid * n_nodes + nid] += llrint((double)risk[i] * ORC_FX_SCALE);
@@ -289,6 +331,7 @@ void orc_tx_step_prep(int32_t n_nodes, int64_t n_people, int32_t n_strains, cons
         for (int t = 0; t < nt; ++t) c += tl_sus[(int64_t)t * n_nodes + j];
         sus_out[j] = c;
     }
+    if (tl_hist) { tl_reduce_add(tl_hist, nt, (int64_t)n_nodes * ORC_RISK_BINS, risk_hist, 0); free(tl_hist); }
     free(f_beta); free(f_exp); free(d_beta); free(d_exp); free(x_beta); free(x_exp); free(tl_sus);
 }
 
@@ -462,7 +505,7 @@ void orc_tx_infect_bernoulli(int32_t n_nodes, int64_t n_people, int32_t n_strain
         int32_t nid = node_id[i];
         float qn = q[nid];
         if (!(qn > 0.f)) continue;
-        float p = risk[i] * qn;
+        float p = p_expose(risk[i] * qn); /* qn = tau[node] */
         int always;
         uint32_t thr = expose_threshold(p, &always);
         uint32_t x;

@@ -27,6 +27,7 @@ _HERE = Path(__file__).resolve().parent
 _SO = _HERE / "_build" / "liblp_oracle.so"
 
 FX_SCALE = float(2**30)
+RISK_BINS = 192
 
 STAGE_PARALYSIS, STAGE_RI, STAGE_SIA, STAGE_EXPOSE, STAGE_STRAIN, STAGE_NODE, STAGE_BIRTH, STAGE_LIFESPAN = range(8)
 
@@ -142,7 +143,9 @@ def tx_step_prep(num_nodes, num_people, n_strains, strains, strain_r0_scalars, d
                  daily_infectivity, risks, mode="fx"):
     """reference model.py:932-1007.  mode: 'f32' (reference-like), 'f64' (truth), 'fx' (device fixed point).
 
-    Returns (beta[nodes,strains] f64, exposure[nodes] f64, sus[nodes] i64, beta_fx i64, exposure_fx i64).
+    Returns (beta[nodes,strains] f64, exposure[nodes] f64, sus[nodes] i64, beta_fx i64, exposure_fx i64); the histogram of
+    the susceptibles' risks (int32[nodes, RISK_BINS], what the device's node step solves tau on) is kept in
+    ``tx_step_prep.last_hist``.
     """
     m = {"f32": 0, "f64": 1, "fx": 2}[mode]
     beta = np.zeros((num_nodes, n_strains), np.float64)
@@ -150,12 +153,14 @@ def tx_step_prep(num_nodes, num_people, n_strains, strains, strain_r0_scalars, d
     sus = np.zeros(num_nodes, np.int64)
     beta_fx = np.zeros((num_nodes, n_strains), np.int64)
     expo_fx = np.zeros(num_nodes, np.int64)
+    hist = np.zeros((num_nodes, RISK_BINS), np.int32)
     srs = np.ascontiguousarray(strain_r0_scalars, dtype=np.float64)
     lib().orc_tx_step_prep(
         C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(n_strains), _p(strains, np.int8), _p(srs),
         _p(disease_states, np.int8), _p(node_ids, np.int16), _p(daily_infectivity, np.float32),
-        _p(risks, np.float32), C.c_int(m), _p(beta), _p(expo), _p(sus), _p(beta_fx), _p(expo_fx),
+        _p(risks, np.float32), C.c_int(m), _p(beta), _p(expo), _p(sus), _p(beta_fx), _p(expo_fx), _p(hist),
     )
+    tx_step_prep.last_hist = hist
     return beta, expo, sus, beta_fx, expo_fx
 
 
@@ -189,7 +194,7 @@ def tx_infect_ref(num_nodes, num_people, num_strains, sus_by_node, node_ids, str
 
 def tx_infect_bernoulli(num_nodes, num_people, num_strains, node_ids, strain, disease_state, risks, q, strain_cdf,
                         x_inj=None, u_strain_inj=None, seed=0, tick=0, id_base=0):
-    """Device exposure scheme (option F1 + importation gate): see lp_oracle.c."""
+    """Device exposure scheme: susceptible i of node n is exposed w.p. 1 - exp(-risk_i * q[n]), q = tau (see lp_oracle.c)."""
     n_new = np.zeros((num_nodes, num_strains), np.int32)
     lib().orc_tx_infect_bernoulli(
         C.c_int32(num_nodes), C.c_int64(num_people), C.c_int32(num_strains), _p(node_ids, np.int16),
@@ -255,20 +260,42 @@ def seasonality(doy: int, days_in_year: int, amplitude: float, peak_doy: float) 
     return 1 + amplitude * np.cos(2 * np.pi * (doy - peak_doy) / days_in_year)
 
 
-def tx_node_math_device(beta_fx, exposure_fx, network, beta_seasonality, r0_scalars, alive_counts, zero_inflation,
+def risk_bin_weights():
+    b = np.arange(RISK_BINS)
+    return np.ldexp(1.0 + ((b & 7) + 0.5) / 8.0, (b >> 3) - 12)
+
+
+def solve_tau(hist_row, target):
+    """tau with sum_b hist[b] * (1 - exp(-w_b tau)) = target (Newton from the left; concave increasing -> monotone)."""
+    h = np.asarray(hist_row, np.float64)
+    w = risk_bin_weights()
+    S, Wsum = h.sum(), (h * w).sum()
+    if not (target > 0.0) or S <= 0:
+        return 0.0
+    if target >= S - 0.5:
+        return 3.0e38
+    t = target / Wsum
+    for _ in range(64):
+        em = np.expm1(-w * t)
+        F, dF = -(h * em).sum(), (h * w * (em + 1.0)).sum()
+        step = (target - F) / dF
+        if not step > 0.0:
+            break
+        t += step
+        if step <= 1e-13 * t:
+            break
+    return min(t, 3.0e38)
+
+
+def tx_node_math_device(beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars, alive_counts, zero_inflation,
                         dispersion, seed, tick):
-    """float64 restatement of the DEVICE node step (lpk_tx_node_math): same formulae as the
-    reference up to the probability (model.py:1332-1351), then instead of an integer count
-    draw it emits the per-node multiplier of the per-agent Bernoulli scheme:
+    """float64 restatement of the DEVICE node step (lpk_tx_node_math): the reference's formulae up to the probability
+    and the expected exposures per node (model.py:1332-1351, 1362-1363); then, instead of an integer count draw, the
+    node's exposure scale tau[n] with  sum_{i in S_n} (1 - exp(-w_i tau[n])) = expected[n] * g_n  on the risk histogram,
+    g_n = 1 when the node has local infectivity (sum_s beta_pre > 0), else 0 w.p. zi, else Gamma(r, 1/r) / (1 - zi)
+    (model.py:1381-1393's ZINB as a zero-inflated gamma-Poisson mixture), r = max(1, round(dispersion)).
 
-      q[n] = float32(P_n * g_n),  P_n = sum_s prob[n, s]
-      g_n  = 1                          if the node has local infectivity (sum_s beta_pre > 0)
-           = 0 w.p. zi, else Gamma(r, 1/r) / (1 - zi)    otherwise  (model.py:1381-1393's ZINB
-             as a zero-inflated gamma-Poisson mixture), r = max(1, round(dispersion)).
-
-    The gamma variate is drawn by Marsaglia-Tsang from the node's Philox stream
-    (counter = (node, k, tick, NODE)); restated in ``node_importation_multiplier``.
-    Returns (q float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected[nodes]).
+    Returns (tau float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected[nodes]).
     """
     beta_pre = np.asarray(beta_fx, np.float64) / FX_SCALE
     exposure = np.asarray(exposure_fx, np.float64) / FX_SCALE
@@ -293,8 +320,9 @@ def tx_node_math_device(beta_fx, exposure_fx, network, beta_seasonality, r0_scal
     r = max(1, int(np.round(dispersion)))
     for n in np.nonzero((local == 0) & (P > 0))[0]:
         g[n] = node_importation_multiplier(int(seed), int(n), int(tick), float(zero_inflation), r)
-    q = (P * g).astype(np.float32)
-    return q, cdf, prob, exposure * P
+    expected = exposure * P
+    tau = np.array([solve_tau(risk_hist[n], expected[n] * g[n]) for n in range(prob.shape[0])], np.float64).astype(np.float32)
+    return tau, cdf, prob, expected
 
 
 def _node_u(seed, node, k, tick, pair):

@@ -151,7 +151,65 @@ def main():
          sus_by_node=sus_by_node, hits=hits, new_by_strain=by_strain, **{f"in_{k}": p[k] for k in AGENT_COLS})
 
 
+def ensemble():
+    """Gate 3 fixture: 64-seed ensemble of per-node daily incidence from the REFERENCE's own transmission path --
+    its numba tx_step_prep / tx_infect_nb / disease_state_step (native numba RNG, no injection) with the node-level
+    block of Transmission_ABM.step (a method body, not extractable) restated by oracle.tx_foi + tx_draw_counts_ref
+    on numpy's global stream, exactly the calls model.py:1332-1407 makes.  Two configurations: Poisson-like
+    importation (defaults) and a calibrated-style zero-inflated, over-dispersed one."""
+    from oracle import oracle as orc
+
+    nb.set_num_threads(4)
+    ref = ref_loader.load(inject_uniforms=False)
+
+    @nb.njit(parallel=True)
+    def seed_threads(s):
+        for t in nb.prange(nb.get_num_threads()):
+            np.random.seed(s + 7919 * nb.get_thread_id())
+
+    n_agents, n_nodes, n_strains, ticks, seeds = 40_000, 5, 3, 30, 64
+    p0 = synth.synth_population(n_agents, n_nodes, seed=77, f_exposed=0.0, f_infected=0.0, f_recovered=0.2, f_dead=0.0)
+    n = p0["count"]
+    # infections seeded in nodes 0 and 1 only: nodes 2-4 are reached through the network (importation branch)
+    rs = np.random.default_rng(5)
+    in01 = np.where((p0["node_id"][:n] <= 1) & (p0["disease_state"][:n] == 0))[0]
+    p0["disease_state"][rs.choice(in01, 150, replace=False)] = 2
+    srs = np.array([1.0, 0.25, 0.125])
+    W = np.full((n_nodes, n_nodes), 0.01)
+    np.fill_diagonal(W, 0.0)
+    r0s = np.array([1.0, 0.8, 1.2, 1.0, 0.9])
+    pop = np.bincount(p0["node_id"][:n], minlength=n_nodes).astype(np.int32)
+    out = {}
+    for tag, zi, disp in (("poisson", 0.0, 1000), ("zinb", 0.5, 1)):
+        inc = np.zeros((seeds, ticks, n_nodes), np.int32)
+        for s in range(seeds):
+            np.random.seed(1000 + s)
+            seed_threads(5000 + 31 * s)
+            p = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p0.items()}
+            si, sp = np.zeros(len(p["disease_state"]), np.int32), np.zeros(len(p["disease_state"]), np.float32)
+            for t in range(1, ticks + 1):
+                a, b = np.zeros(n_nodes, np.int32), np.zeros(n_nodes, np.int32)
+                ref["disease_state_step"](p["node_id"], n_nodes, p["disease_state"], p["strain"], n, p["exposure_timer"],
+                                          p["infection_timer"], p["potentially_paralyzed"], p["paralyzed"], p["ipv_protected"],
+                                          p["paralysis_timer"], nb.float32(1 / 2000), a, b)
+                beta, expo, sus = ref["tx_step_prep"](n_nodes, n, n_strains, p["strain"][:n], srs, p["disease_state"][:n],
+                                                      p["node_id"][:n], p["daily_infectivity"][:n], p["acq_risk_multiplier"][:n])
+                beta_pre, prob = orc.tx_foi(beta, W, 1.0, r0s, pop)
+                want, _ = orc.tx_draw_counts_ref(beta_pre, prob, expo, zi, disp, rs=np.random)
+                new = ref["tx_infect_nb"](n_nodes, n, n_strains, sus, p["node_id"][:n], p["strain"][:n], p["disease_state"][:n],
+                                          si, sp, p["acq_risk_multiplier"][:n], prob, want)
+                inc[s, t - 1] = new.sum(axis=1)
+        out[f"incidence_{tag}"] = inc
+        print(tag, "mean cumulative incidence per node", inc.sum(1).mean(0))
+    save("ensemble_ref", count=n, n_nodes=n_nodes, n_strains=n_strains, ticks=ticks, strain_r0_scalars=srs, network=W, r0_scalars=r0s,
+         pop=pop, **out, **{f"in_{k}": p0[k] for k in AGENT_COLS})
+
+
 if __name__ == "__main__":
+    if "--ensemble" in sys.argv:
+        ensemble()
+        raise SystemExit(0)
     if not ref_loader.available():
         raise SystemExit("needs the reference checkout at /root/reference")
     main()
+    ensemble()

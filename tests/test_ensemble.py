@@ -1,0 +1,96 @@
+"""North-star gate 3: ensemble agreement of per-node incidence with the REFERENCE's transmission path.
+
+tests/golden/ensemble_ref.npz holds 64-seed ensembles produced by the reference's own numba kernels
+(tests/golden/make_golden.py --ensemble).  The device replaces the reference's "Poisson / ZINB count per node, then
+weighted sampling without replacement" by independent per-agent trials with probability 1 - exp(-risk * tau[node]), tau
+solved so that the node's expected count equals the reference's, so agreement is distributional: for every node, cumulative and daily incidence must pass a two-sample
+Kolmogorov-Smirnov test at p > 0.01 and have means within 2 standard errors, in both importation regimes
+(Poisson-like defaults; zero-inflated, over-dispersed calibrated style).
+
+The CPU test runs the device SCHEME through the oracle's restatement (bit-identical to the CUDA kernels,
+tests/test_gpu_parity.py); the GPU test runs the CUDA kernels themselves through the C ABI.
+"""
+
+import numpy as np
+import pytest
+from conftest import golden_inputs, load_golden
+from scipy import stats
+
+SEEDS = 64
+CONFIGS = (("poisson", 0.0, 1000.0), ("zinb", 0.5, 1.0))
+
+
+def oracle_backend(oracle, g, zi, disp, seed):
+    p = golden_inputs(g)
+    n, nn, ns, ticks = int(g["count"]), int(g["n_nodes"]), int(g["n_strains"]), int(g["ticks"])
+    inc = np.zeros((ticks, nn), np.int32)
+    for t in range(1, ticks + 1):
+        a, b = np.zeros(nn, np.int32), np.zeros(nn, np.int32)
+        oracle.disease_state_step(p["node_id"], nn, p["disease_state"], p["strain"], n, p["exposure_timer"], p["infection_timer"],
+                                  p["potentially_paralyzed"], p["paralyzed"], p["ipv_protected"], p["paralysis_timer"], 1 / 2000, a, b,
+                                  seed=seed, tick=t)
+        _, _, _, bfx, efx = oracle.tx_step_prep(nn, n, ns, p["strain"], g["strain_r0_scalars"], p["disease_state"], p["node_id"],
+                                                p["daily_infectivity"], p["acq_risk_multiplier"], mode="fx")
+        q, cdf, _, _ = oracle.tx_node_math_device(bfx, efx, oracle.tx_step_prep.last_hist, g["network"], 1.0, g["r0_scalars"], g["pop"],
+                                                  zi, disp, seed, t)
+        new = oracle.tx_infect_bernoulli(nn, n, ns, p["node_id"], p["strain"], p["disease_state"], p["acq_risk_multiplier"], q, cdf,
+                                         seed=seed, tick=t)
+        inc[t - 1] = new.sum(axis=1)
+    return inc
+
+
+def device_backend(K, torch, g, zi, disp, seed):
+    d = {k: torch.from_numpy(v).cuda() for k, v in golden_inputs(g).items()}
+    n, nn, ns, ticks = int(g["count"]), int(g["n_nodes"]), int(g["n_strains"]), int(g["ticks"])
+    W, r0s, pop = (torch.from_numpy(np.ascontiguousarray(g[k])).cuda() for k in ("network", "r0_scalars", "pop"))
+    inc = torch.zeros((ticks, nn), dtype=torch.int32, device="cuda")
+    a, b = torch.zeros(nn, dtype=torch.int32, device="cuda"), torch.zeros(nn, dtype=torch.int32, device="cuda")
+    for t in range(1, ticks + 1):
+        rng = K.make_rng(seed, t)
+        K.disease_state_step(d["node_id"], nn, d["disease_state"], d["strain"], n, d["exposure_timer"], d["infection_timer"],
+                             d["potentially_paralyzed"], d["paralyzed"], d["ipv_protected"], d["paralysis_timer"], 1 / 2000, a, b, rng=rng)
+        bfx, efx, _, hist = K.tx_step_prep(nn, n, ns, d["strain"], g["strain_r0_scalars"], d["disease_state"], d["node_id"],
+                                           d["daily_infectivity"], d["acq_risk_multiplier"])
+        q, cdf, _, _ = K.tx_node_math(bfx, efx, hist, W, 1.0, r0s, pop, zi, disp, rng=rng)
+        new = K.tx_infect(nn, n, ns, d["node_id"], d["strain"], d["disease_state"], d["acq_risk_multiplier"], q, cdf, rng=rng)
+        inc[t - 1] = new.sum(dim=1)
+    return inc.cpu().numpy()
+
+
+def check_agreement(ours, ref, tag):
+    """ours, ref: [seeds, ticks, nodes].  KS p > 0.01 and means within 2 s.e., per node, for cumulative incidence and for
+    daily incidence at one third, two thirds and the end of the window."""
+    views = {"cumulative": (ours.sum(1), ref.sum(1))}
+    for day in (ours.shape[1] // 3, 2 * ours.shape[1] // 3, ours.shape[1] - 1):
+        views[f"day {day + 1}"] = (ours[:, day], ref[:, day])
+    worst = 1.0
+    for what, (a, b) in views.items():
+        for node in range(a.shape[1]):
+            x, y = a[:, node].astype(float), b[:, node].astype(float)
+            p = stats.ks_2samp(x, y).pvalue
+            se = np.sqrt(x.var(ddof=1) / len(x) + y.var(ddof=1) / len(y))
+            assert p > 0.01, f"{tag} {what} node {node}: KS p = {p:.4f} (means {x.mean():.1f} vs {y.mean():.1f})"
+            assert abs(x.mean() - y.mean()) <= 2 * se + 0.5, f"{tag} {what} node {node}: means {x.mean():.2f} vs {y.mean():.2f}, s.e. {se:.2f}"
+            worst = min(worst, p)
+    return worst
+
+
+def test_bernoulli_scheme_matches_reference_ensemble_cpu(oracle):
+    g = load_golden("ensemble_ref")
+    for tag, zi, disp in CONFIGS:
+        ours = np.stack([oracle_backend(oracle, g, zi, disp, 9000 + s) for s in range(SEEDS)])
+        worst = check_agreement(ours, g[f"incidence_{tag}"], tag)
+        print(tag, "smallest KS p-value", worst)
+
+
+@pytest.mark.gpu
+def test_cuda_kernels_match_reference_ensemble():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from laser_polio_b200 import kernels as K
+
+    g = load_golden("ensemble_ref")
+    for tag, zi, disp in CONFIGS:
+        ours = np.stack([device_backend(K, torch, g, zi, disp, 9000 + s) for s in range(SEEDS)])
+        check_agreement(ours, g[f"incidence_{tag}"], tag)
