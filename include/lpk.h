@@ -221,8 +221,11 @@ typedef struct lpk_tick_args {
     int32_t *ri_vaccinated, *ri_protected, *ipv_vaccinated;          /* rows t */
     int32_t *new_exposed, *new_exposed_by_strain, *ri_new_exposed_by_strain; /* rows t */
     double strain_r0_scalars[LPK_MAX_STRAINS];
-    int64_t *beta_fx, *exposure_fx, *sus; /* tally of tick t, += (lpk_tick_node zeroes the other parity buffer) */
-    int32_t *risk_hist;                   /* [nodes, LPK_RISK_BINS] of tick t, += (same) */
+    int64_t *beta_fx;      /* infectivity tally of tick t, += (lpk_tick_node zeroes the other parity buffer) */
+    int64_t *exposure_fx, *sus; /* susceptible-side tallies, CARRIED from tick to tick: the pass only corrects them when */
+    int32_t *risk_hist;    /* an agent leaves the susceptible state (hit, RI exposure, death); lpk_vd_births adds cohorts.
+                              Exact integers, so they equal lpk_tx_step_prep's from-scratch values; the caller initialises
+                              them with lpk_tx_step_prep and re-initialises after any tick run outside the pass */
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
@@ -253,9 +256,7 @@ typedef struct lpk_node_args {
     /* totals of the census rows the pass just completed (t-1) */
     const int32_t *E_by_strain_prev, *I_by_strain_prev;
     int32_t *E_prev, *I_prev;
-    /* tallies of the other parity, zeroed for tick t+1 */
-    int64_t *next_beta_fx, *next_exposure_fx, *next_sus;
-    int32_t *next_risk_hist;
+    int64_t *next_beta_fx; /* infectivity tally of the other parity, zeroed for tick t+1 */
     int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
 } lpk_node_args;
 
@@ -289,6 +290,10 @@ typedef struct lpk_births_args {
     int32_t *date_of_birth, *date_of_death;
     int16_t *ri_timer;           /* may be NULL */
     int32_t *tile_node;          /* may be NULL */
+    /* optional (all or none): carried susceptible-side tallies to which the cohort is added, see lpk_tick_args */
+    const float *acq_risk_multiplier;
+    int64_t *sus, *exposure_fx;
+    int32_t *risk_hist;
 } lpk_births_args;
 
 int lpk_vd_births(const lpk_births_args *args, void *stream);

@@ -139,7 +139,7 @@ class NodeArgs(C.Structure):
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
         ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
-        ("next_beta_fx", _VP), ("next_exposure_fx", _VP), ("next_sus", _VP), ("next_risk_hist", _VP), ("counts", _VP),
+        ("next_beta_fx", _VP), ("counts", _VP),
     ]
 
 
@@ -152,6 +152,7 @@ class BirthsArgs(C.Structure):
         ("cum_deaths", _VP), ("max_year", C.c_int32), ("ri_newborn_timer", C.c_int32), ("node_offsets_ws", _VP),
         ("cohort_ws", _VP), ("status", _VP), ("disease_state", _VP), ("node_id", _VP), ("date_of_birth", _VP),
         ("date_of_death", _VP), ("ri_timer", _VP), ("tile_node", _VP),
+        ("acq_risk_multiplier", _VP), ("sus", _VP), ("exposure_fx", _VP), ("risk_hist", _VP),
     ]
 
 

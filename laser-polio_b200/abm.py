@@ -676,7 +676,7 @@ class VitalDynamics_ABM:
         if cbr is not None:
             self.birth_rate[:] = (cbr[0] if (isinstance(cbr, (float, int)) or len(cbr) == 1) else np.array(cbr)) / (365 * 1000)
 
-    def births_args(self, dev, t, tile_node=None):
+    def births_args(self, dev, t, tile_node=None, tallies=None):
         """Argument block of lpk_vd_births for tick t (device-side births, include/lpk.h V2)."""
         import torch
 
@@ -704,6 +704,10 @@ class VitalDynamics_ABM:
         a.date_of_birth, a.date_of_death = c["date_of_birth"].data_ptr(), c["date_of_death"].data_ptr()
         a.ri_timer = c["ri_timer"].data_ptr() if "ri_timer" in c else None
         a.tile_node = tile_node.data_ptr() if tile_node is not None else None
+        if tallies is not None:  # fused path: the cohort joins the carried susceptible-side tallies
+            sus, expo, hist = tallies
+            a.acq_risk_multiplier = c["acq_risk_multiplier"].data_ptr()
+            a.sus, a.exposure_fx, a.risk_hist = sus.data_ptr(), expo.data_ptr(), hist.data_ptr()
         self._keep = (a,)
         return a
 

@@ -21,9 +21,8 @@ struct PassParams {
 };
 
 // per-node partial sums a lane keeps in registers (everything else is rare and goes straight to atomics)
-enum { CI_S = 0, CI_R = 1, CI_SUS = 2, CI_N = 3 };
-enum { CL_EXPO = 0, CL_N = 1 };
-typedef NodeAcc<CI_N, CL_N> TickAcc;
+enum { CI_S = 0, CI_R = 1, CI_N = 2 };
+typedef NodeAcc<CI_N, 0> TickAcc;
 
 // ------------------------------------------------------------------ rare paths (out of line, direct atomics)
 __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
@@ -31,6 +30,18 @@ __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
     rng.seed = pp.A.seed; rng.tick = (uint32_t)pp.A.tick; rng.u1 = nullptr; rng.u2 = nullptr; rng.x = nullptr;
     rng.id_base = pp.A.id_base;
     return rng;
+}
+
+// The susceptible-side tallies (count, sum of risks, risk histogram per node) are carried from tick to tick and only
+// CORRECTED when an agent leaves the susceptible state (exposure hit, RI exposure, death) or is born; they are exact
+// integers, so the running values equal a from-scratch tally bit for bit (tests/test_gpu_fused.py) while the streaming
+// loop no longer converts and bins every susceptible every day.
+__device__ __noinline__ void leave_S(const PassParams &pp, int64_t i, int nd) {
+    const lpk_tick_args &A = pp.A;
+    const float rk = pp.P.acq_risk_multiplier[i];
+    atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)(-1ll));
+    red_add(&A.exposure_fx[nd], -__float2ll_rn(rk * 1073741824.0f));
+    atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
 }
 
 // an exposure hit of tick t-1: categorical strain pick (model.py:1127-1141), bookkeeping rows t-1
@@ -46,6 +57,7 @@ __device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int n
     pp.P.strain[i] = (int8_t)assigned;
     atomicAdd(&A.new_exposed_prev[nd], 1);
     atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
+    leave_S(pp, i, nd);
 }
 
 // census of one E or I agent (rows t-1)
@@ -54,7 +66,8 @@ __device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, 
     atomicAdd(s == 1 ? &pp.A.E_by_strain_prev[c] : &pp.A.I_by_strain_prev[c], 1);
 }
 
-__device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd) {
+__device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd, int8_t state_before) {
+    if (state_before == 0) leave_S(pp, i, nd);
     atomicAdd(&pp.A.deaths[nd], 1);
     if (pp.P.potentially_paralyzed[i] == 1) atomicAdd(&pp.A.dead_pp[nd], 1);
     if (pp.P.paralyzed[i] == 1) atomicAdd(&pp.A.dead_par[nd], 1);
@@ -103,6 +116,7 @@ __device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int
             if (s == 0) {
                 w = set_byte(w, k, 1);
                 P.strain[i] = (int8_t)A.ri_strain;
+                leave_S(pp, i, nd);
                 const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
                 atomicAdd(&A.ri_protected[nd], 1);
                 atomicAdd(&A.new_exposed[nd], 1);
@@ -144,25 +158,14 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
             else if (s == 3) atomicAdd(&A.R_prev[nd], 1);
             else census_ei(pp, i, nd, s);
         }
-        if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd); s = -1; }
+        if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd, s); s = -1; }
         if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s);
         nw = set_byte(nw, k, s);
     }
     if (ri) nw = ri_quad(pp, b, valid, nw);
 #pragma unroll 1
-    for (int k = 0; k < valid; ++k) {
-        const int8_t s = byte_of(nw, k);
-        const int64_t i = b + k;
-        if (s == 0) {
-            const int nd = P.node_id[i];
-            const float rk = P.acq_risk_multiplier[i];
-            atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), 1ull);
-            red_add(&A.exposure_fx[nd], __float2ll_rn(rk * 1073741824.0f));
-            atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], 1);
-        } else if (s == 2) {
-            tally_infectious(pp, i, P.node_id[i]);
-        }
-    }
+    for (int k = 0; k < valid; ++k)
+        if (byte_of(nw, k) == 2) tally_infectious(pp, b + k, P.node_id[b + k]);
     return nw;
 }
 
@@ -179,7 +182,8 @@ struct RowData {
 };
 
 template <bool kDeaths>
-__device__ __forceinline__ void issue_row_loads(const lpk_people &P, int64_t row, int lane, int64_t n, uint32_t w, RowData &d) {
+__device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
+                                                uint32_t w, RowData &d) {
     const int64_t b = (row * 32 + lane) * 4;
     d.w = w;
     d.tn = P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
@@ -188,7 +192,9 @@ __device__ __forceinline__ void issue_row_loads(const lpk_people &P, int64_t row
     d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
     d.nd = make_uint2(0u, 0u);
     if (full && alive) {
-        if (any_byte_eq(w, 0u)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
+        // risk is only needed for the exposure trial: skipped when nothing is pending or the tile's node has no force of infection
+        if (tau_prev && any_byte_eq(w, 0u) && (d.tn < 0 || __ldg(&tau_prev[d.tn]) > 0.f))
+            d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
         if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
         if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
     }
@@ -231,6 +237,7 @@ __device__ __noinline__ void active_agent(const PassParams &pp, int64_t block_ba
         P.strain[i] = (int8_t)assigned;
         atomicAdd(&A.new_exposed_prev[nd], 1);
         atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
+        leave_S(pp, i, nd);
     }
     if (A.flags & LPK_F_PENDING) {
         const int64_t c = (int64_t)nd * ns + P.strain[i];
@@ -248,13 +255,13 @@ __device__ __noinline__ void active_agent(const PassParams &pp, int64_t block_ba
 template <bool kDeaths, bool kRI>
 __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
     __shared__ uint2 queue[LPK_WARPS][QCAP];
-    __shared__ int s_hist[LPK_WARPS][LPK_RISK_BINS];
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int64_t count_prev = A.counts[0], n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    const float *tau_prev = pending ? A.q_prev : nullptr;
     const int tick = A.tick;
     // rows of 128 agents; blocks own contiguous row ranges, warps interleave inside
     const int64_t rows = (n + 127) >> 7;
@@ -265,13 +272,9 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
 
     TickAcc acc;
     acc.init();
-    WarpHist wh;
-    wh.init(s_hist[warp], lane);
-    auto flush = [&](int nd, const int *ci, const long long *cl) {
+    auto flush = [&](int nd, const int *ci, const long long *) {
         red_add(&A.S_prev[nd], ci[CI_S]);
         red_add(&A.R_prev[nd], ci[CI_R]);
-        if (ci[CI_SUS]) atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)ci[CI_SUS]);
-        red_add(&A.exposure_fx[nd], cl[CL_EXPO]);
     };
 
     int64_t row = lo + warp;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
     uint32_t w2 = 0xFFFFFFFFu;  // state word two rows ahead
     cur.w = 0xFFFFFFFFu;
     if (row < hi) {
-        issue_row_loads<kDeaths>(P, row, lane, n, load_state_row(P, row, lane, n), cur);
+        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), cur);
         if (row + LPK_WARPS < hi) w2 = load_state_row(P, row + LPK_WARPS, lane, n);
     }
 #pragma unroll 1
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         // ---- keep the pipeline full
         const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
         nxt.w = 0xFFFFFFFFu;
-        if (r1 < hi) issue_row_loads<kDeaths>(P, r1, lane, n, w2, nxt);
+        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, nxt);
         w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
 
         // ---- row `row`
@@ -295,8 +298,6 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         const int64_t b = (row * 32 + lane) * 4;
         uint32_t cand = 0u, hits = 0u, nw = w;  // cand/hits: bit k = agent k of the quad goes to the active queue
         int nd = cur.tn;
-        const bool row_uniform = cur.tn >= 0;  // warp-uniform: the row lies in one node-uniform tile
-        if (row_uniform) wh.select(cur.tn, A.risk_hist, lane);
         if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
             const int valid = quad_valid(b, n);
             bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                         if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
                             if ((hits >> k) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << k); }
                             if (pending && (byte_of(nw, k) == 1 || byte_of(nw, k) == 2)) census_ei(pp, b + k, nd, byte_of(nw, k));
-                            kill_agent(pp, b + k, nd);
+                            kill_agent(pp, b + k, nd, byte_of(nw, k));
                             nw = set_byte(nw, k, -1);
                         }
                     }
@@ -361,17 +362,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                     cand = 0u;
                     nw = ri_quad(pp, b, 4, nw);
                 }
-                // tally of tick t (susceptibles here, infectious agents in the queue handler)
-                const uint32_t mS2 = __vcmpeq4(nw, 0u);
-                acc.ci[CI_SUS] += __popc(mS2) >> 3;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((mS2 >> (8 * k)) & 1u) {
-                        acc.cl[CL_EXPO] += __float2ll_rn(rk[k] * 1073741824.0f);
-                        if (row_uniform) atomicAdd(&wh.h[risk_bin(rk[k])], 1);
-                        else atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk[k])], 1);
-                    }
-                }
+                // tick t's tally: infectious agents in the queue handler; the susceptible side is carried incrementally
             }
             if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
@@ -400,7 +391,6 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
     __syncwarp();
     if (lane < q_count) active_agent(pp, block_base, q[(q_head + lane) & (QCAP - 1)]);
     __syncwarp();
-    wh.flush(A.risk_hist, lane);
     acc.finish_warp(flush);
 }
 
@@ -494,11 +484,8 @@ __global__ void k_tick_epilogue(lpk_node_args a) {
         for (int s = 0; s < ns; ++s) { e += a.E_by_strain_prev[(int64_t)n * ns + s]; i += a.I_by_strain_prev[(int64_t)n * ns + s]; }
         a.E_prev[n] = e; a.I_prev[n] = i;
     }
-    if (a.next_beta_fx) {
+    if (a.next_beta_fx)
         for (int s = 0; s < ns; ++s) a.next_beta_fx[(int64_t)n * ns + s] = 0;
-        a.next_exposure_fx[n] = 0;
-        a.next_sus[n] = 0;
-    }
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
@@ -515,13 +502,10 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(!a.pop || (a.pop_prev && (!(a.flags & LPK_F_DEATHS) || (a.deaths_row && a.deaths))), "tick_node population rows");
     REQUIRE(!a.cur_potp || (a.cur_p && a.new_potential && a.new_paralyzed && a.potp_row && a.p_row), "tick_node paralysis rows");
     REQUIRE(!a.deaths || (a.dead_pp && a.dead_par), "tick_node death scratch");
-    REQUIRE(!a.next_beta_fx || (a.next_exposure_fx && a.next_sus && a.next_risk_hist), "tick_node next tallies");
     REQUIRE(a.pop || a.pop_prev, "tick_node needs a population row for the rate denominator");
     cudaStream_t st = as_stream(stream);
     k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
-    if (a.next_risk_hist)
-        CUDA_TRY(cudaMemsetAsync(a.next_risk_hist, 0, sizeof(int32_t) * (size_t)a.n_nodes * LPK_RISK_BINS, st), "lpk_tick_node hist");
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
                                 a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st);

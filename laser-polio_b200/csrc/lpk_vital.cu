@@ -99,6 +99,12 @@ __global__ void k_births_fill(lpk_births_args a) {
         a.date_of_death[slot] = a.tick + newborn_lifespan(a, (uint64_t)slot);
         a.disease_state[slot] = 0;
         if (a.ri_timer && a.ri_newborn_timer >= 0) a.ri_timer[slot] = (int16_t)a.ri_newborn_timer;
+        if (a.sus) {  // fused path: the susceptible-side tallies are carried incrementally (lpk_tick.cu)
+            const float rk = a.acq_risk_multiplier[slot];
+            atomicAdd(reinterpret_cast<unsigned long long *>(&a.sus[lo]), 1ull);
+            red_add(&a.exposure_fx[lo], __float2ll_rn(rk * 1073741824.0f));
+            atomicAdd(&a.risk_hist[(int64_t)lo * LPK_RISK_BINS + risk_bin(rk)], 1);
+        }
     }
 }
 

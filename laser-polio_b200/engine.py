@@ -53,7 +53,10 @@ class FusedEngine:
         dev.set_count(sim.people.count)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=d)  # noqa: E731
         i64 = lambda *s: torch.zeros(s, dtype=torch.int64, device=d)  # noqa: E731
-        self.tally = [(i64(n, ns), i64(n), i64(n), i32(n, _lpk.RISK_BINS)) for _ in range(2)]
+        self.beta = [i64(n, ns), i64(n, ns)]  # infectivity tally, recomputed every tick (ping-pong)
+        # susceptible-side tallies carried from tick to tick and corrected by the pass (include/lpk.h, lpk_tick_args)
+        self.expo, self.sus, self.hist = i64(n), i64(n), i32(n, _lpk.RISK_BINS)
+        self._beta_scratch = i64(n, ns)
         self.deaths, self.dead_pp, self.dead_par = i32(n), i32(n), i32(n)
         self.cur_potp, self.cur_p = i32(n), i32(n)
         self.q = torch.zeros(n, dtype=torch.float32, device=d)
@@ -73,6 +76,7 @@ class FusedEngine:
         P.tile_node = dp(self.tile_node)
         P.capacity = cap
         self.P = P
+        self.rebase_tallies()
 
     # ------------------------------------------------------------------ helpers
     def rebuild_tiles(self, first_agent: int):
@@ -80,6 +84,14 @@ class FusedEngine:
         check(_lpk.lib().lpk_build_tile_nodes(_lpk.ptr(self.dev.cols["node_id"]), C.c_int64(first_tile),
                                               C.c_int64(self.sim.people.capacity), _lpk.ptr(self.tile_node), stream_handle()),
               "lpk_build_tile_nodes")
+
+    def rebase_tallies(self):
+        """From-scratch susceptible-side tallies of the table as it stands (engine start, and after any tick that ran
+        through the components, whose kernels do not maintain the carried values)."""
+        sim, dev, c = self.sim, self.dev, self.dev.cols
+        K.tx_step_prep(dev.n_nodes, sim.people.count, dev.n_strains, c["strain"], list(sim.pars.strain_r0_scalars.values()),
+                       c["disease_state"], c["node_id"], c["daily_infectivity"], c["acq_risk_multiplier"],
+                       out=(self._beta_scratch, self.expo, self.sus, self.hist))
 
     def _row(self, name, t):
         r = self.dev.res.get(name)
@@ -118,6 +130,7 @@ class FusedEngine:
         self.cur_potp.copy_(r["potentially_paralyzed"][t])
         self.cur_p.copy_(r["paralyzed"][t])
         self.dev.set_count(self.sim.people.count)
+        self.rebase_tallies()
 
     def fused_tick(self, t):
         sim, dev, pars = self.sim, self.dev, self.sim.pars
@@ -130,7 +143,7 @@ class FusedEngine:
         if is_vd:  # births first: the cohort takes part in this tick's tally (reference: VitalDynamics runs first)
             if pars.cbr is None:
                 raise ValueError("VitalDynamics_ABM needs pars.cbr")
-            b = vd.births_args(dev, t, self.tile_node)
+            b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist))
             K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns
@@ -156,9 +169,9 @@ class FusedEngine:
             A.ri_new_exposed_by_strain = dp(self._row("ri_new_exposed_by_strain", t))
         for s, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
             A.strain_r0_scalars[s] = float(v)
-        beta_fx, exposure_fx, sus, risk_hist = self.tally[t & 1]
+        beta_fx, exposure_fx, sus, risk_hist = self.beta[t & 1], self.expo, self.sus, self.hist
         if not self.pending:  # the previous tick was not fused, so nobody zeroed this parity
-            beta_fx.zero_(), exposure_fx.zero_(), sus.zero_(), risk_hist.zero_()
+            beta_fx.zero_()
         A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
         A.flags = flags
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
@@ -188,8 +201,7 @@ class FusedEngine:
         N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
         N.E_by_strain_prev, N.I_by_strain_prev = A.E_by_strain_prev, A.I_by_strain_prev
         N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
-        nb, ne, nsus, nh = self.tally[(t + 1) & 1]
-        N.next_beta_fx, N.next_exposure_fx, N.next_sus, N.next_risk_hist = dp(nb), dp(ne), dp(nsus), dp(nh)
+        N.next_beta_fx = dp(self.beta[(t + 1) & 1])
         N.counts = dp(dev.counts)
         K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 4)
         self.pending = True
