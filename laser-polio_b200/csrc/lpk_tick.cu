@@ -183,10 +183,10 @@ struct RowData {
 
 template <bool kDeaths>
 __device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
-                                                uint32_t w, RowData &d) {
+                                                uint32_t w, int tn, RowData &d) {
     const int64_t b = (row * 32 + lane) * 4;
     d.w = w;
-    d.tn = P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
+    d.tn = tn;
     const bool full = b + 4 <= n;
     const bool alive = (w & 0x80808080u) != 0x80808080u;
     d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,6 +200,9 @@ __device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float
     }
 }
 
+__device__ __forceinline__ int load_tile_node(const lpk_people &P, int64_t row) {
+    return P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
+}
 __device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t row, int lane, int64_t n) {
     const int64_t b = (row * 32 + lane) * 4;
     const int v = quad_valid(b, n);
@@ -279,19 +282,21 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
 
     int64_t row = lo + warp;
     RowData cur, nxt;
-    uint32_t w2 = 0xFFFFFFFFu;  // state word two rows ahead
+    uint32_t w2 = 0xFFFFFFFFu;  // state word and tile node two rows ahead
+    int tn2 = -1;
     cur.w = 0xFFFFFFFFu;
     if (row < hi) {
-        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), cur);
-        if (row + LPK_WARPS < hi) w2 = load_state_row(P, row + LPK_WARPS, lane, n);
+        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), cur);
+        if (row + LPK_WARPS < hi) { w2 = load_state_row(P, row + LPK_WARPS, lane, n); tn2 = load_tile_node(P, row + LPK_WARPS); }
     }
 #pragma unroll 1
     for (; row < hi; row += LPK_WARPS) {
         // ---- keep the pipeline full
         const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
         nxt.w = 0xFFFFFFFFu;
-        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, nxt);
+        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, nxt);
         w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
+        tn2 = (r2 < hi) ? load_tile_node(P, r2) : -1;
 
         // ---- row `row`
         const uint32_t w = cur.w;
