@@ -20,7 +20,34 @@ static inline DevRng dev_rng(const lpk_rng *r) {
 }
 
 
-// One agent of the state machine (reference model.py:419-452); returns the new state.
+// Infected block of the state machine on register copies (reference model.py:425-452): recovery timer, then -- for the
+// paralytic strain 0 only -- the paralysis gate (once per agent: potentially_paralyzed leaves -1) with one uniform, and
+// the paralysis timer.  Returns the new state (2 or 3); flags bit 0 = newly potentially paralysed, bit 1 = newly paralysed.
+__device__ __forceinline__ int8_t ds_infected(int64_t i, int8_t st, int8_t ipvv, int8_t &it, int8_t &pt, int8_t &pq, int8_t &par,
+                                              double p_paralysis, const DevRng &rng, int &flags) {
+    int8_t s = 2;
+    flags = 0;
+    if (it <= 0) s = 3;
+    it = (int8_t)(it - 1);
+    if (st == 0) {
+        if (pt <= 0 && pq == -1) {
+            if (ipvv == 0) {
+                pq = 1;
+                flags |= 1;
+                double u;
+                if (rng.u1) u = rng.u1[i];
+                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
+                if (u < p_paralysis) { par = 1; flags |= 2; }
+            } else {
+                pq = 0;
+            }
+        }
+        pt = (int8_t)(pt - 1);
+    }
+    return s;
+}
+
+// One agent of the state machine (reference model.py:419-452) on the column arrays; returns the new state.
 __device__ __forceinline__ int8_t ds_agent(int64_t i, int8_t s, const int16_t *node_id, const int8_t *strain,
                                            int8_t *etimer, int8_t *itimer, int8_t *pot_par, int8_t *paralyzed,
                                            const int8_t *ipv, int8_t *ptimer, double p_paralysis, int32_t *new_pot,
@@ -31,25 +58,21 @@ __device__ __forceinline__ int8_t ds_agent(int64_t i, int8_t s, const int16_t *n
         etimer[i] = (int8_t)(e - 1);
     }
     if (s == 2) {
-        const int8_t it = itimer[i];
-        if (it <= 0) s = 3;
-        itimer[i] = (int8_t)(it - 1);
-        if (strain[i] == 0) {
-            const int8_t pt = ptimer[i];
-            if (pt <= 0 && pot_par[i] == -1) {
-                if (ipv[i] == 0) {
-                    pot_par[i] = 1;
-                    const int nd = node_id[i];
-                    atomicAdd(&new_pot[nd], 1);
-                    double u;
-                    if (rng.u1) u = rng.u1[i];
-                    else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
-                    if (u < p_paralysis) { paralyzed[i] = 1; atomicAdd(&new_par[nd], 1); }
-                } else {
-                    pot_par[i] = 0;
-                }
+        const int8_t st = strain[i];
+        int8_t it = itimer[i], pt = 0, pq = 0, par = 0, ipvv = 0;
+        if (st == 0) { pt = ptimer[i]; pq = pot_par[i]; ipvv = ipv[i]; }
+        const int8_t pq0 = pq;
+        int flags;
+        s = ds_infected(i, st, ipvv, it, pt, pq, par, p_paralysis, rng, flags);
+        itimer[i] = it;
+        if (st == 0) {
+            ptimer[i] = pt;
+            if (pq != pq0) pot_par[i] = pq;
+            if (flags) {
+                const int nd = node_id[i];
+                atomicAdd(&new_pot[nd], 1);
+                if (flags & 2) { paralyzed[i] = 1; atomicAdd(&new_par[nd], 1); }
             }
-            ptimer[i] = (int8_t)(pt - 1);
         }
     }
     return s;

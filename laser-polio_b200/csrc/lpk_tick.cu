@@ -223,37 +223,62 @@ __device__ __forceinline__ uint2 q_pack(uint32_t rel, int nd, uint32_t s, uint32
     return make_uint2(rel, ((uint32_t)nd & 0xFFFFu) | (s << 16) | (hit << 20));
 }
 
-// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent
+// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent.
+// Every column the agent can need is loaded up front, in one round trip, and the state machine runs on registers
+// (profiles/r1_fused_v6_postsia_*: a third of the stall samples sat on the serial etimer -> itimer -> strain -> ptimer
+// -> infectivity chain of dependent scattered loads).
 __device__ __noinline__ void active_agent(const PassParams &pp, uint2 e) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int64_t i = (int64_t)e.x;
     const int nd = (int)(int16_t)(e.y & 0xFFFFu);
-    int8_t s = (int8_t)((e.y >> 16) & 0xFu);
+    const int8_t s0 = (int8_t)((e.y >> 16) & 0xFu);
+    const bool hit = (e.y >> 20) & 1u;
     const int ns = A.n_strains;
-    if ((e.y >> 20) & 1u) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
+    int8_t st = hit ? (int8_t)0 : P.strain[i];
+    int8_t et = (s0 == 1) ? P.exposure_timer[i] : (int8_t)1;
+    int8_t it = P.infection_timer[i], pt = P.paralysis_timer[i], pq = P.potentially_paralyzed[i];
+    const int8_t ipvv = P.ipv_protected[i];
+    const float inf = P.daily_infectivity[i];
+    if (hit) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
         uint32_t y[4];
         philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
         const double r = u53(y[0], y[1]);
         int assigned = 0;
         for (int k = 0; k < ns; ++k)
             if (r < A.cdf_prev[(int64_t)nd * ns + k]) { assigned = k; break; }
-        P.strain[i] = (int8_t)assigned;
+        st = (int8_t)assigned;
+        P.strain[i] = st;
         atomicAdd(&A.new_exposed_prev[nd], 1);
         atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
         leave_S(pp, i, nd);
     }
     if (A.flags & LPK_F_PENDING) {
-        const int64_t c = (int64_t)nd * ns + P.strain[i];
-        atomicAdd(s == 1 ? &A.E_by_strain_prev[c] : &A.I_by_strain_prev[c], 1);
+        const int64_t c = (int64_t)nd * ns + st;
+        atomicAdd(s0 == 1 ? &A.E_by_strain_prev[c] : &A.I_by_strain_prev[c], 1);
     }
-    const int8_t s2 = ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
-                               P.ipv_protected, P.paralysis_timer, (double)A.p_paralysis, A.new_potential, A.new_paralyzed, stage_rng(pp));
-    if (s2 != s) P.disease_state[i] = s2;
-    if (s2 == 2) {
-        const int st = P.strain[i];
-        red_add(&A.beta_fx[(int64_t)nd * ns + st], to_fx((double)P.daily_infectivity[i] * A.strain_r0_scalars[st]));
+    int8_t s = s0;
+    if (s == 1) {  // model.py:419-422
+        if (et <= 0) s = 2;
+        P.exposure_timer[i] = (int8_t)(et - 1);
     }
+    if (s == 2) {
+        const int8_t pq0 = pq;
+        int8_t par = 0;
+        int flags;
+        s = ds_infected(i, st, ipvv, it, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
+        P.infection_timer[i] = it;
+        if (st == 0) {
+            P.paralysis_timer[i] = pt;
+            if (pq != pq0) P.potentially_paralyzed[i] = pq;
+            if (flags) {
+                atomicAdd(&A.new_potential[nd], 1);
+                if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
+            }
+        }
+    }
+    if (s != s0) P.disease_state[i] = s;
+    if (s == 2) red_add(&A.beta_fx[(int64_t)nd * ns + st], to_fx((double)inf * A.strain_r0_scalars[st]));
 }
 
 template <bool kDeaths, bool kRI>
