@@ -181,9 +181,12 @@ struct RowData {
     int tn;          // tile's node or -1
 };
 
+// (tau_tn, tau_val): the warp's one-entry cache of tau_prev[node] -- consecutive rows of a warp sit in the same node for
+// hundreds of rows, and a dependent tile_node -> tau -> risk load chain in the prefetch stage stalled the whole pipeline
+// (profiles/r1_fused_v7_postsia_*: 21 % of the stall samples)
 template <bool kDeaths>
 __device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
-                                                uint32_t w, int tn, RowData &d) {
+                                                uint32_t w, int tn, int &tau_tn, float &tau_val, RowData &d) {
     const int64_t b = (row * 32 + lane) * 4;
     d.w = w;
     d.tn = tn;
@@ -193,8 +196,12 @@ __device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float
     d.nd = make_uint2(0u, 0u);
     if (full && alive) {
         // risk is only needed for the exposure trial: skipped when nothing is pending or the tile's node has no force of infection
-        if (tau_prev && any_byte_eq(w, 0u) && (d.tn < 0 || __ldg(&tau_prev[d.tn]) > 0.f))
-            d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
+        bool live = tau_prev != nullptr;
+        if (live && d.tn >= 0) {
+            if (d.tn != tau_tn) { tau_tn = d.tn; tau_val = __ldg(&tau_prev[d.tn]); }  // warp-uniform branch
+            live = tau_val > 0.f;
+        }
+        if (live && any_byte_eq(w, 0u)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
         if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
         if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
     }
@@ -303,6 +310,10 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
 
     TickAcc acc;
     acc.init();
+    int tau_tn = -2;      // one-entry cache of tau_prev[node] (prefetch stage)
+    float tau_val = 0.f;
+    int q_nd = -2;        // and of the same value for the row being processed
+    float q_val = 0.f;
     auto flush = [&](int nd, const int *ci, const long long *) {
         red_add(&A.S_prev[nd], ci[CI_S]);
         red_add(&A.R_prev[nd], ci[CI_R]);
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
     int tn2 = -1;
     cur.w = 0xFFFFFFFFu;
     if (row < hi) {
-        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), cur);
+        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), tau_tn, tau_val, cur);
         if (row + LPK_WARPS < hi) { w2 = load_state_row(P, row + LPK_WARPS, lane, n); tn2 = load_tile_node(P, row + LPK_WARPS); }
     }
 #pragma unroll 1
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         // ---- keep the pipeline full
         const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
         nxt.w = 0xFFFFFFFFu;
-        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, nxt);
+        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, tau_tn, tau_val, nxt);
         w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
         tn2 = (r2 < hi) ? load_tile_node(P, r2) : -1;
 
@@ -350,7 +361,8 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
                     // exposure trial of tick t-1
                     const uint32_t mS = __vcmpeq4(w, 0u);
                     if (mS) {
-                        const float qn = __ldg(&A.q_prev[nd]);
+                        if (nd != q_nd) { q_nd = nd; q_val = __ldg(&A.q_prev[nd]); }
+                        const float qn = q_val;
                         if (qn > 0.f) {
                             uint32_t x[4];
                             philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
