@@ -166,7 +166,7 @@ def build_sim(lp, n_agents, n_nodes, dur, seed, device, rank=0, world=1):
     sim.instances = [c.init_from_file(sim) for c in sim._components]
     if world > 1:
         sim.shard = sharding.Shard(rank=rank, world=world, node_lo=rank * n_nodes, node_hi=(rank + 1) * n_nodes)
-        sim.id_base = rank * ((capacity + 3) // 4 * 4)
+        sim.id_base = rank * ((capacity + 255) // 256 * 256)
     return sim
 
 

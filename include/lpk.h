@@ -51,6 +51,7 @@ extern "C" {
 #define LPK_STAGE_NODE 5u
 #define LPK_STAGE_BIRTH 6u
 #define LPK_STAGE_LIFESPAN 7u
+#define LPK_STAGE_EXPOSE_LO 8u /* low half of the exposure word, generated only when the high half cannot decide */
 
 typedef struct lpk_rng {
     uint64_t seed;      /* Philox key */
@@ -60,7 +61,7 @@ typedef struct lpk_rng {
     const double *u2;   /* second injected stream (fast_ri IPV draw; strain pick in tx_infect) */
     const uint32_t *x;  /* optional injected per-agent 32-bit words for the exposure trial */
     uint64_t id_base;   /* added to the agent index in every Philox counter: the global id of local agent 0 when the
-                           table is one node-shard of a larger population (multiple of 4); 0 on a single GPU */
+                           table is one node-shard of a larger population (multiple of 256); 0 on a single GPU */
 } lpk_rng;
 
 const char *lpk_last_error(void);
@@ -147,8 +148,11 @@ int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_f
  *     sus_indices_storage, sus_probs_storage, risks, prob_exp_by_node_strain, n_exposures_to_create_by_node_strain)
  *     model.py:1010-1149.  Per-agent Bernoulli: susceptible i of node n is exposed iff
  *     x_i < floor(p_i * 2^32), p_i = 1 - exp(-risk_i * tau[n]) (evaluated by an exactly specified fmaf polynomial),
- *     x_i = word (i & 3) of Philox(seed; i >> 2, tick, EXPOSE); strain by the cumulative categorical of
- *     model.py:1127-1141.  No bucket pass, no scratch columns.  n_new[num_nodes * num_strains] OVERWRITTEN. */
+ *     x_i = h16 << 16 | l16, the half-words hw = ((i >> 7) & 1) * 4 + (i & 3) of the two blocks
+ *     Philox(seed; (i >> 8) * 32 + ((i >> 2) & 31), tick, EXPOSE / EXPOSE_LO) (i = agent index + id_base: one block
+ *     serves the 8 agents a lane owns in a pair of 128-agent rows; the fused pass generates the low block only when
+ *     the high half cannot decide); strain by the cumulative categorical of model.py:1127-1141.
+ *     No bucket pass, no scratch columns.  n_new[num_nodes * num_strains] OVERWRITTEN. */
 int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_strains, const int16_t *node_ids,
                   int8_t *strain, int8_t *disease_state, const float *risks, const float *tau,
                   const double *strain_cdf, int32_t *n_new, const lpk_rng *rng, void *stream);
@@ -209,7 +213,9 @@ typedef struct lpk_tick_args {
     const float *q_prev;    /* [nodes]  tau of tick t-1, from lpk_tick_node / lpk_tx_node_math */
     const double *cdf_prev; /* [nodes, strains] */
     int32_t *new_exposed_prev, *new_exposed_by_strain_prev; /* rows t-1, += */
-    int32_t *S_prev, *R_prev, *E_by_strain_prev, *I_by_strain_prev; /* rows t-1, accumulate */
+    int32_t *E_by_strain_prev, *I_by_strain_prev; /* rows t-1, accumulate (the S and R rows come from the carried counts
+                                                     below, see lpk_node_args) */
+    int32_t *tx_hits;       /* [nodes] scratch, += : exposures of tick t-1 found by this pass; consumed by lpk_tick_node */
     /* ---- stages of tick t (LPK_F_STAGES) */
     float p_paralysis;
     int32_t *new_potential, *new_paralyzed; /* rows t, += */
@@ -226,6 +232,8 @@ typedef struct lpk_tick_args {
     int32_t *risk_hist;    /* an agent leaves the susceptible state (hit, RI exposure, death); lpk_vd_births adds cohorts.
                               Exact integers, so they equal lpk_tx_step_prep's from-scratch values; the caller initialises
                               them with lpk_tx_step_prep and re-initialises after any tick run outside the pass */
+    int32_t *R_cur;        /* [nodes] recovered agents per node, carried the same way (+1 on recovery, -1 when a recovered
+                              agent dies); initialised / re-initialised from lpk_count_seirp's R */
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
@@ -256,6 +264,14 @@ typedef struct lpk_node_args {
     /* totals of the census rows the pass just completed (t-1) */
     const int32_t *E_by_strain_prev, *I_by_strain_prev;
     int32_t *E_prev, *I_prev;
+    /* S and R census from the carried per-node counts (model.py:1476-1481 equivalent): with LPK_F_PENDING,
+     *   S_prev[n] = S_snap[n] - tx_hits[n]   (susceptibles when tick t-1's stages ended, minus tick t-1's exposures)
+     *   R_prev[n] += R_snap[n]               ("+=": on top of the pre-seeded non-agent immunes, model.py:1481)
+     * then tx_hits is zeroed and the snapshots are retaken for tick t: S_snap = sus, R_snap = R_cur. */
+    const int64_t *sus;
+    const int32_t *R_cur;
+    int32_t *tx_hits, *S_snap, *R_snap;
+    int32_t *S_prev, *R_prev; /* rows t-1 */
     int64_t *next_beta_fx; /* infectivity tally of the other parity, zeroed for tick t+1 */
     int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
 } lpk_node_args;

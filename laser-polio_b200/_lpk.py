@@ -116,14 +116,14 @@ class TickArgs(C.Structure):
         ("flags", C.c_uint32), ("tick", C.c_int32), ("n_nodes", C.c_int32), ("n_strains", C.c_int32),
         ("seed", C.c_uint64), ("id_base", C.c_uint64), ("counts", _VP),
         ("q_prev", _VP), ("cdf_prev", _VP), ("new_exposed_prev", _VP), ("new_exposed_by_strain_prev", _VP),
-        ("S_prev", _VP), ("R_prev", _VP), ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP),
+        ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("tx_hits", _VP),
         ("p_paralysis", C.c_float), ("new_potential", _VP), ("new_paralyzed", _VP),
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("ri_step", C.c_int32), ("ri_strain", C.c_int32), ("vx_prob_ri", _VP), ("vx_prob_ipv", _VP),
         ("ri_vaccinated", _VP), ("ri_protected", _VP), ("ipv_vaccinated", _VP),
         ("new_exposed", _VP), ("new_exposed_by_strain", _VP), ("ri_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
-        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP),
+        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
     ]
 
 
@@ -139,6 +139,7 @@ class NodeArgs(C.Structure):
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
         ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
+        ("sus", _VP), ("R_cur", _VP), ("tx_hits", _VP), ("S_snap", _VP), ("R_snap", _VP), ("S_prev", _VP), ("R_prev", _VP),
         ("next_beta_fx", _VP), ("counts", _VP),
     ]
 

@@ -51,6 +51,35 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)v * (1.0 / 9007199254740992.0);
 }
 
+// ---------------------------------------------------------------- exposure draw
+// Agent `id` (= slot + id_base) owns one 32-bit word X = h16 << 16 | l16 per tick for its exposure trial.  The halves are
+// the same half-word `hw` of two Philox blocks (stages EXPOSE and EXPOSE_LO) shared by 8 agents -- the quads one lane owns
+// in an even / odd pair of 128-agent rows:
+//     ctr = (id >> 8) * 32 + ((id >> 2) & 31)        hw = ((id >> 7) & 1) * 4 + (id & 3)
+// so ONE Philox block serves 8 agents in the streaming pass: the high half alone decides > 99.9 % of the trials
+// (h16 >= risk * tau * 2^16 cannot be a hit) and the low-half block is generated only for the rest.  The trial itself is
+// unchanged: hit iff X < floor(p * 2^32).
+__device__ __forceinline__ uint64_t expose_ctr(uint64_t id) { return ((id >> 8) << 5) | ((id >> 2) & 31u); }
+__device__ __forceinline__ int expose_hw(uint64_t id) { return (int)(((id >> 7) & 1u) * 4u + (id & 3u)); }
+__device__ __forceinline__ uint32_t half_word(const uint32_t x[4], int hw) { return (x[hw >> 1] >> (16 * (hw & 1))) & 0xFFFFu; }
+// the four words of the aligned quad starting at agent id0 (id0 % 4 == 0)
+__device__ __forceinline__ void expose_words_quad(uint64_t seed, uint64_t id0, uint32_t tick, uint32_t out[4]) {
+    const uint64_t c = expose_ctr(id0);
+    const int hw0 = expose_hw(id0);
+    uint32_t h[4], l[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), tick, LPK_STAGE_EXPOSE, (uint32_t)seed, (uint32_t)(seed >> 32), h);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), tick, LPK_STAGE_EXPOSE_LO, (uint32_t)seed, (uint32_t)(seed >> 32), l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = (half_word(h, hw0 + k) << 16) | half_word(l, hw0 + k);
+}
+
+// ---------------------------------------------------------------- state-word masks
+// The four state bytes of a quad are 0xFF (dead / unborn), 0 (S), 1 (E), 2 (I), 3 (R); each mask has bit 0 of byte k set
+// when agent k is in the class.
+__device__ __forceinline__ uint32_t mask_S(uint32_t w) { return ~(w | (w >> 1) | (w >> 7)) & 0x01010101u; }
+__device__ __forceinline__ uint32_t mask_EI(uint32_t w) { return (w ^ (w >> 1)) & 0x01010101u; }
+__device__ __forceinline__ uint32_t mask_alive(uint32_t w) { return ~(w >> 7) & 0x01010101u; }
+
 // ---------------------------------------------------------------- byte-lane helpers
 __device__ __forceinline__ int8_t byte_of(uint32_t w, int k) { return (int8_t)((w >> (8 * k)) & 0xFFu); }
 __device__ __forceinline__ uint32_t set_byte(uint32_t w, int k, int8_t v) {

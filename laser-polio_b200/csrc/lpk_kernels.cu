@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(LPK_BLOCK) k_tx_infect(int64_t n, int n_strain
             load_f4(risk, base[j], valid[j], rk);
             uint32_t x[4];
             if (rng.x) { for (int k = 0; k < 4; ++k) x[k] = (k < valid[j]) ? rng.x[base[j] + k] : 0u; }
-            else philox_agent(rng.seed, ((uint64_t)base[j] + rng.id_base) >> 2, rng.tick, LPK_STAGE_EXPOSE, x);
+            else expose_words_quad(rng.seed, (uint64_t)base[j] + rng.id_base, rng.tick, x);
             uint32_t nw = w[j];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

@@ -1,17 +1,22 @@
 // lpk_tick.cu -- the fused tick: ONE streaming pass over the agent table per simulated day.
 //
 // Pass for tick t, per agent, in the reference's order (include/lpk.h, "Fused tick"):
-//   pending tick t-1:  exposure trial (tx_infect)  ->  census (count_SEIRP: S, R, E/I by strain)
+//   pending tick t-1:  exposure trial (tx_infect)  ->  census (count_SEIRP)
 //   tick t:            deaths (get_deaths) -> disease state (disease_state_step) -> RI (fast_ri) -> tally (tx_step_prep)
 // Every draw is Philox(seed; agent, tick, stage), so the fused pass reproduces the per-function kernels bit for bit
-// (tests/test_gpu_fused.py).  Design notes (profiles/r1_baseline_*: the unfused kernels were issue- and latency-bound
-// at ~16 % of HBM peak with `no_instruction` and `long_scoreboard` the top stalls):
-//   * all of a tile's loads (state of the NEXT tile, risk / node / date_of_death of this one) are issued before any is
-//     consumed, so each warp keeps ~3 KB in flight;
-//   * the byte columns are handled four agents at a time with SIMD-in-a-word compares / popcounts;
-//   * everything rare (a hit, an E/I agent, a death, an RI-eligible agent) lives in __noinline__ functions so the
-//     streaming loop stays a few KB of code;
-//   * node ids come from a per-tile table (one broadcast load per 512 agents) whenever the tile is node-uniform.
+// (tests/test_gpu_fused.py).
+//
+// The pass is instruction-issue bound, not bandwidth bound (profiles/r1_fused_v8_*: 534 warp-instructions per 128 agents
+// at 20 % of DRAM peak), so the design minimises instructions per agent:
+//   * per-node integer tallies (susceptibles, recovered, risk sum, risk histogram) are CARRIED from tick to tick and only
+//     corrected where an agent changes class, so the streaming loop counts nothing;
+//   * chunks of 32 K agents that lie in one node (nearly all of them) run a loop in which a lane owns 8 agents per
+//     iteration (its quads in an even / odd row pair) served by ONE Philox block: the 16-bit high halves reject > 99.9 %
+//     of the trials with 3 instructions per agent, the exact 32-bit test runs out of line for the rest;
+//   * the 2 % of agents that are exposed or infectious are pushed to a per-warp shared-memory ring and handled 32 at a
+//     time with all lanes busy (they sit in ~90 % of the 128-agent rows, so handling them in place made every warp walk
+//     the long disease-state path with one or two live lanes);
+//   * everything rare (a hit, a death, an RI-eligible agent, a node boundary) lives in __noinline__ functions.
 #include "lpk_host.cuh"
 #include "lpk_stages.cuh"
 
@@ -20,9 +25,12 @@ struct PassParams {
     lpk_tick_args A;
 };
 
-// per-node partial sums a lane keeps in registers (everything else is rare and goes straight to atomics)
-enum { CI_S = 0, CI_R = 1, CI_N = 2 };
-typedef NodeAcc<CI_N, 0> TickAcc;
+#define QCAP 512             // ring entries per warp: 31 left over + the 256 agents of one iteration fit
+#define LPK_CHUNK_ROWS 256   // rows of 128 agents per chunk (32 K agents), dealt round-robin to the blocks
+#define LPK_CHUNK_AGENTS (LPK_CHUNK_ROWS * 128)
+#ifndef LPK_PASS_BLOCKS_PER_SM
+#define LPK_PASS_BLOCKS_PER_SM 2
+#endif
 
 // ------------------------------------------------------------------ rare paths (out of line, direct atomics)
 __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
@@ -34,8 +42,7 @@ __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
 
 // The susceptible-side tallies (count, sum of risks, risk histogram per node) are carried from tick to tick and only
 // CORRECTED when an agent leaves the susceptible state (exposure hit, RI exposure, death) or is born; they are exact
-// integers, so the running values equal a from-scratch tally bit for bit (tests/test_gpu_fused.py) while the streaming
-// loop no longer converts and bins every susceptible every day.
+// integers, so the running values equal a from-scratch tally bit for bit (tests/test_gpu_fused.py).
 __device__ __noinline__ void leave_S(const PassParams &pp, int64_t i, int nd) {
     const lpk_tick_args &A = pp.A;
     const float rk = pp.P.acq_risk_multiplier[i];
@@ -44,8 +51,8 @@ __device__ __noinline__ void leave_S(const PassParams &pp, int64_t i, int nd) {
     atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
 }
 
-// an exposure hit of tick t-1: categorical strain pick (model.py:1127-1141), bookkeeping rows t-1
-__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
+// bookkeeping of an exposure hit of tick t-1: categorical strain pick (model.py:1127-1141), rows t-1; returns the strain
+__device__ __forceinline__ int8_t expose_bookkeeping(const PassParams &pp, int64_t i, int nd) {
     const lpk_tick_args &A = pp.A;
     uint32_t y[4];
     philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
@@ -57,8 +64,11 @@ __device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int n
     pp.P.strain[i] = (int8_t)assigned;
     atomicAdd(&A.new_exposed_prev[nd], 1);
     atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
+    atomicAdd(&A.tx_hits[nd], 1);
     leave_S(pp, i, nd);
+    return (int8_t)assigned;
 }
+__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) { expose_bookkeeping(pp, i, nd); }
 
 // census of one E or I agent (rows t-1)
 __device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, int8_t s) {
@@ -68,16 +78,19 @@ __device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, 
 
 __device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd, int8_t state_before) {
     if (state_before == 0) leave_S(pp, i, nd);
+    if (state_before == 3) atomicAdd(&pp.A.R_cur[nd], -1);
     atomicAdd(&pp.A.deaths[nd], 1);
     if (pp.P.potentially_paralyzed[i] == 1) atomicAdd(&pp.A.dead_pp[nd], 1);
     if (pp.P.paralyzed[i] == 1) atomicAdd(&pp.A.dead_par[nd], 1);
 }
 
-__device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8_t s) {
+__device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8_t s, int nd) {
     const lpk_people &P = pp.P;
-    return ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
-                    P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed,
-                    stage_rng(pp));
+    const int8_t s2 = ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
+                               P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed,
+                               stage_rng(pp));
+    if (s2 == 3) atomicAdd(&pp.A.R_cur[nd], 1);  // s was E or I: a recovery
+    return s2;
 }
 
 // infectivity tally of one infectious agent (tick t)
@@ -142,7 +155,7 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     uint32_t nw = w;
     uint32_t x[4] = {0u, 0u, 0u, 0u};
-    if (pending) philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE, x);
+    if (pending) expose_words_quad(A.seed, (uint64_t)b + A.id_base, (uint32_t)(A.tick - 1), x);
 #pragma unroll 1
     for (int k = 0; k < valid; ++k) {
         int8_t s = byte_of(nw, k);
@@ -154,12 +167,10 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
                 const float tau = A.q_prev[nd];
                 if (tau > 0.f && expose_test(p_expose(__fmul_rn(P.acq_risk_multiplier[i], tau)), x[k])) { expose_agent(pp, i, nd); s = 1; }
             }
-            if (s == 0) atomicAdd(&A.S_prev[nd], 1);
-            else if (s == 3) atomicAdd(&A.R_prev[nd], 1);
-            else census_ei(pp, i, nd, s);
+            if (s == 1 || s == 2) census_ei(pp, i, nd, s);
         }
         if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd, s); s = -1; }
-        if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s);
+        if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s, nd);
         nw = set_byte(nw, k, s);
     }
     if (ri) nw = ri_quad(pp, b, valid, nw);
@@ -169,66 +180,47 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
     return nw;
 }
 
-// ------------------------------------------------------------------ the pass
-// A warp walks its rows of 128 agents (one quad per lane).  Software pipeline: the state word of row r+2, and the
-// risk / node / date_of_death words of row r+1 (predicated on its state, which arrived an iteration ago), are in
-// flight while row r is processed.
-struct RowData {
-    uint32_t w;      // 4 state bytes
-    float4 rk;       // acq_risk_multiplier of the quad (if it has a susceptible)
-    uint2 nd;        // 4 node ids (only when the tile is not node-uniform)
-    int4 dd;         // date_of_death (vital-dynamics ticks only)
-    int tn;          // tile's node or -1
-};
-
-// (tau_tn, tau_val): the warp's one-entry cache of tau_prev[node] -- consecutive rows of a warp sit in the same node for
-// hundreds of rows, and a dependent tile_node -> tau -> risk load chain in the prefetch stage stalled the whole pipeline
-// (profiles/r1_fused_v7_postsia_*: 21 % of the stall samples)
-template <bool kDeaths>
-__device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
-                                                uint32_t w, int tn, int &tau_tn, float &tau_val, RowData &d) {
-    const int64_t b = (row * 32 + lane) * 4;
-    d.w = w;
-    d.tn = tn;
-    const bool full = b + 4 <= n;
-    const bool alive = (w & 0x80808080u) != 0x80808080u;
-    d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
-    d.nd = make_uint2(0u, 0u);
-    if (full && alive) {
-        // risk is only needed for the exposure trial: skipped when nothing is pending or the tile's node has no force of infection
-        bool live = tau_prev != nullptr;
-        if (live && d.tn >= 0) {
-            if (d.tn != tau_tn) { tau_tn = d.tn; tau_val = __ldg(&tau_prev[d.tn]); }  // warp-uniform branch
-            live = tau_val > 0.f;
-        }
-        if (live && any_byte_eq(w, 0u)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
-        if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
-        if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
-    }
+// ------------------------------------------------------------------ exposure trial of a quad
+// High halves of the quad's four draws: x[2 * par], x[2 * par + 1] of the pair's EXPOSE block (par = row parity).
+// Pre-test, 3 instructions per agent: U = 2^23 + h16 as a float (one PRMT), T = fma(risk, tau * 2^16, 2^23 + 1); a hit needs
+// X < floor(p * 2^32) with p <= risk * tau, hence h16 < risk * tau * 2^16, hence U < T (the + 1 covers both roundings).
+__device__ __forceinline__ bool pretest_quad(uint32_t xa, uint32_t xb, const float4 &rk, float tau16) {
+    const uint32_t k23 = 0x4B000000u;
+    const float c = 8388609.0f;
+    return (__uint_as_float(__byte_perm(xa, k23, 0x7610)) < fmaf(rk.x, tau16, c)) |
+           (__uint_as_float(__byte_perm(xa, k23, 0x7632)) < fmaf(rk.y, tau16, c)) |
+           (__uint_as_float(__byte_perm(xb, k23, 0x7610)) < fmaf(rk.z, tau16, c)) |
+           (__uint_as_float(__byte_perm(xb, k23, 0x7632)) < fmaf(rk.w, tau16, c));
 }
-
-__device__ __forceinline__ int load_tile_node(const lpk_people &P, int64_t row) {
-    return P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
-}
-__device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t row, int lane, int64_t n) {
-    const int64_t b = (row * 32 + lane) * 4;
-    const int v = quad_valid(b, n);
-    return v ? load_b4(P.disease_state, b, v) : 0xFFFFFFFFu;
+// The exact trial for the susceptibles of the quad (state word w): generates the low halves; returns the hit mask.
+__device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, uint32_t c1, int par, uint32_t xa, uint32_t xb, uint32_t w,
+                                            float4 rk, float tau) {
+    uint32_t l[4];
+    philox4x32_10(c0, c1, (uint32_t)(pp.A.tick - 1), LPK_STAGE_EXPOSE_LO, (uint32_t)pp.A.seed, (uint32_t)(pp.A.seed >> 32), l);
+    const uint32_t la = par ? l[2] : l[0], lb = par ? l[3] : l[1];
+    const uint32_t X[4] = {(xa << 16) | (la & 0xFFFFu), (xa & 0xFFFF0000u) | (la >> 16), (xb << 16) | (lb & 0xFFFFu),
+                           (xb & 0xFFFF0000u) | (lb >> 16)};
+    const float r[4] = {rk.x, rk.y, rk.z, rk.w};
+    const uint32_t mS = mask_S(w);
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (((mS >> (8 * k)) & 1u) && expose_test(p_expose(__fmul_rn(r[k], tau)), X[k])) hits |= 1u << (8 * k);
+    return hits;
 }
 
 // ---- active-agent queue -------------------------------------------------------------------------------------
-// E / I agents (and fresh exposure hits) are ~2 % of the table but sit in ~90 % of the 128-agent rows, so handling
-// them where they are found makes every warp walk the long disease-state path with one or two live lanes
-// (profiles/r1_fused2_*: 280 thread-instructions per agent, issue-bound).  Instead each warp appends them to a small
-// shared-memory ring and, whenever 32 have accumulated, processes them one per lane with all lanes busy.
-// An entry carries everything the handler needs; the handler owns the agent's state byte from then on (the owning
-// lane already stored the quad's word; both stores come from the same warp, ordered by __syncwarp()).
-#define QCAP 64
-#define LPK_CHUNK_ROWS 256
+// E / I agents (and fresh exposure hits) are appended to the warp's shared-memory ring and, whenever 32 have
+// accumulated, processed one per lane with all lanes busy.  An entry carries everything the handler needs; the handler
+// owns the agent's state byte from then on (the owning lane already stored the quad's word; both stores come from the
+// same warp, ordered by the warp-wide reduction in q_commit).
 // entry = {agent index (tables hold < 2^32 slots), node | state << 16 | hit << 20}
-__device__ __forceinline__ uint2 q_pack(uint32_t rel, int nd, uint32_t s, uint32_t hit) {
-    return make_uint2(rel, ((uint32_t)nd & 0xFFFFu) | (s << 16) | (hit << 20));
-}
+struct WarpQueue {
+    uint2 *q;
+    uint32_t *tail;  // shared, monotonic
+    uint32_t head;   // warp-uniform
+    int count;       // warp-uniform
+};
 
 // census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent.
 // Every column the agent can need is loaded up front, in one round trip, and the state machine runs on registers
@@ -247,19 +239,7 @@ __device__ __noinline__ void active_agent(const PassParams &pp, uint2 e) {
     int8_t it = P.infection_timer[i], pt = P.paralysis_timer[i], pq = P.potentially_paralyzed[i];
     const int8_t ipvv = P.ipv_protected[i];
     const float inf = P.daily_infectivity[i];
-    if (hit) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
-        uint32_t y[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
-        const double r = u53(y[0], y[1]);
-        int assigned = 0;
-        for (int k = 0; k < ns; ++k)
-            if (r < A.cdf_prev[(int64_t)nd * ns + k]) { assigned = k; break; }
-        st = (int8_t)assigned;
-        P.strain[i] = st;
-        atomicAdd(&A.new_exposed_prev[nd], 1);
-        atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
-        leave_S(pp, i, nd);
-    }
+    if (hit) st = expose_bookkeeping(pp, i, nd);  // exposure hit of tick t-1
     if (A.flags & LPK_F_PENDING) {
         const int64_t c = (int64_t)nd * ns + st;
         atomicAdd(s0 == 1 ? &A.E_by_strain_prev[c] : &A.I_by_strain_prev[c], 1);
@@ -286,49 +266,182 @@ __device__ __noinline__ void active_agent(const PassParams &pp, uint2 e) {
     }
     if (s != s0) P.disease_state[i] = s;
     if (s == 2) red_add(&A.beta_fx[(int64_t)nd * ns + st], to_fx((double)inf * A.strain_r0_scalars[st]));
+    if (s == 3) atomicAdd(&A.R_cur[nd], 1);
+}
+
+// append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; returns how many
+__device__ __forceinline__ int q_push(WarpQueue &Q, uint32_t idx0, int nd, uint32_t nw, uint32_t hits, uint32_t m) {
+    const uint32_t comb = nw | (hits << 4);
+    const int cnt = __popc(m);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        const uint32_t pos = atomicAdd(Q.tail, 1u) & (QCAP - 1);
+        Q.q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((comb >> bit) & 0xFFu) << 16));
+    }
+    return cnt;
+}
+// every lane pushed `mine` entries: drain the ring 32 at a time (warp-uniform control flow)
+__device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int mine, int lane) {
+    Q.count += __reduce_add_sync(LPK_FULL, mine);
+    while (Q.count >= 32) {
+        __syncwarp();
+        active_agent(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        Q.head += 32;
+        Q.count -= 32;
+    }
+}
+
+// out-of-line part of a death in a fast chunk: the quad's agents in mask dm die on tick t (after tick t-1's pending
+// exposure + census); returns {new state word, remaining hits}
+__device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t dm) {
+    const bool pending = (pp.A.flags & LPK_F_PENDING) != 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        if (!((dm >> (8 * k)) & 1u)) continue;
+        const int8_t s = byte_of(nw, k);
+        if ((hits >> (8 * k)) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << (8 * k)); }
+        if (pending && (s == 1 || s == 2)) census_ei(pp, b + k, nd, s);
+        kill_agent(pp, b + k, nd, s);
+        nw = set_byte(nw, k, -1);
+    }
+    return make_uint2(nw, hits);
+}
+__device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick, uint32_t w) {
+    return ((d.x <= tick ? 1u : 0u) | (d.y <= tick ? 0x100u : 0u) | (d.z <= tick ? 0x10000u : 0u) | (d.w <= tick ? 0x1000000u : 0u)) &
+           mask_alive(w);
+}
+
+// ------------------------------------------------------------------ fast chunk: 32 K agents of ONE node, all of them
+// present at tick t-1.  A warp takes every 8th row pair; a lane owns its quad in the even row (A) and in the odd row (B).
+struct PairData {
+    uint32_t wA, wB;
+    float4 rA, rB;
+    int4 dA, dB;
+};
+template <bool kDeaths>
+__device__ __forceinline__ void fast_chunk(const PassParams &pp, WarpQueue &Q, int64_t base, int nd, int lane, int warp) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    const float tau = pending ? __ldg(&A.q_prev[nd]) : 0.f;
+    const bool expose = tau > 0.f;  // no force of infection on the node: neither risk nor random numbers are needed
+    const float tau16 = tau * 65536.0f;
+    const int tick = A.tick;
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const int64_t lane_base = base + lane * 4;
+    const uint64_t ctr_base = ((((uint64_t)base + A.id_base) >> 8) << 5) + (uint64_t)lane;
+    const int8_t *sp = P.disease_state + lane_base;
+    const float *rp = P.acq_risk_multiplier + lane_base;
+    const int32_t *dp = kDeaths ? P.date_of_death + lane_base : nullptr;
+    auto load = [&](int p, PairData &d) {
+        const int o = p * 256;
+        d.wA = *reinterpret_cast<const uint32_t *>(sp + o);
+        d.wB = *reinterpret_cast<const uint32_t *>(sp + o + 128);
+        if (expose) {
+            d.rA = __ldg(reinterpret_cast<const float4 *>(rp + o));
+            d.rB = __ldg(reinterpret_cast<const float4 *>(rp + o + 128));
+        }
+        if (kDeaths) {
+            d.dA = __ldg(reinterpret_cast<const int4 *>(dp + o));
+            d.dB = __ldg(reinterpret_cast<const int4 *>(dp + o + 128));
+        }
+    };
+    PairData cur, nxt;
+    load(warp, cur);
+#pragma unroll 2
+    for (int p = warp; p < LPK_CHUNK_ROWS / 2; p += LPK_WARPS) {
+        if (p + LPK_WARPS < LPK_CHUNK_ROWS / 2) load(p + LPK_WARPS, nxt);
+        const int64_t bA = lane_base + p * 256, bB = bA + 128;
+        uint32_t nwA = cur.wA, nwB = cur.wB, hA = 0u, hB = 0u;
+        if (expose) {  // exposure trial of tick t-1
+            const uint64_t c = ctr_base + (uint64_t)(p * 32);
+            uint32_t x[4];
+            philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
+            if (pretest_quad(x[0], x[1], cur.rA, tau16) | pretest_quad(x[2], x[3], cur.rB, tau16)) {
+                hA = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 0, x[0], x[1], nwA, cur.rA, tau);
+                hB = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 1, x[2], x[3], nwB, cur.rB, tau);
+                nwA |= hA;  // S (0) -> E (1)
+                nwB |= hB;
+            }
+        }
+        if (kDeaths) {  // tick t
+            const uint32_t dmA = death_mask(cur.dA, tick, nwA), dmB = death_mask(cur.dB, tick, nwB);
+            if (dmA) { const uint2 r = death_quad(pp, bA, nd, nwA, hA, dmA); nwA = r.x; hA = r.y; }
+            if (dmB) { const uint2 r = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = r.x; hB = r.y; }
+        }
+        if (nwA != cur.wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
+        if (nwB != cur.wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
+        // exposed / infectious agents (fresh hits included): census of t-1, disease state and tally of t in the handler
+        int mine = q_push(Q, (uint32_t)bA, nd, nwA, hA, mask_EI(nwA));
+        mine += q_push(Q, (uint32_t)bB, nd, nwB, hB, mask_EI(nwB));
+        q_commit(pp, Q, mine, lane);
+        cur = nxt;
+    }
+}
+
+// ------------------------------------------------------------------ general rows: node boundaries, newborn cohorts, the
+// table's tail, RI ticks.  A warp walks rows of 128 agents (one quad per lane).  Software pipeline: the state word of row
+// r+2, and the risk / node / date_of_death words of row r+1 (predicated on its state, which arrived an iteration ago),
+// are in flight while row r is processed.
+struct RowData {
+    uint32_t w;      // 4 state bytes
+    float4 rk;       // acq_risk_multiplier of the quad (if it has a susceptible)
+    uint2 nd;        // 4 node ids (only when the tile is not node-uniform)
+    int4 dd;         // date_of_death (vital-dynamics ticks only)
+    int tn;          // tile's node or -1
+};
+struct TauCache {
+    int node;
+    float tau;
+};
+
+template <bool kDeaths>
+__device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
+                                                uint32_t w, int tn, TauCache &tc, RowData &d) {
+    const int64_t b = (row * 32 + lane) * 4;
+    d.w = w;
+    d.tn = tn;
+    const bool full = b + 4 <= n;
+    const bool alive = (w & 0x80808080u) != 0x80808080u;
+    d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
+    d.nd = make_uint2(0u, 0u);
+    if (full && alive) {
+        // risk is only needed for the exposure trial: skipped when nothing is pending or the tile's node has no force of infection
+        bool live = tau_prev != nullptr;
+        if (live && d.tn >= 0) {
+            if (d.tn != tc.node) { tc.node = d.tn; tc.tau = __ldg(&tau_prev[d.tn]); }  // warp-uniform branch
+            live = tc.tau > 0.f;
+        }
+        if (live && mask_S(w)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
+        if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
+        if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
+    }
+}
+__device__ __forceinline__ int load_tile_node(const lpk_people &P, int64_t row) {
+    return P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
+}
+__device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t row, int lane, int64_t n) {
+    const int64_t b = (row * 32 + lane) * 4;
+    const int v = quad_valid(b, n);
+    return v ? load_b4(P.disease_state, b, v) : 0xFFFFFFFFu;
 }
 
 template <bool kDeaths, bool kRI>
-__global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constant__ PassParams pp) {
-    __shared__ uint2 queue[LPK_WARPS][QCAP];
+__device__ __forceinline__ void general_rows(const PassParams &pp, WarpQueue &Q, int64_t lo, int64_t hi, int64_t n, int64_t count_prev,
+                                             TauCache &tc_load, TauCache &tc_use, int lane, int warp) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int64_t count_prev = A.counts[0], n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const float *tau_prev = pending ? A.q_prev : nullptr;
     const int tick = A.tick;
-    // rows of 128 agents, grouped in chunks of LPK_CHUNK_ROWS rows (32 K agents) dealt round-robin to the blocks: a
-    // chunk is long enough for per-node partial sums to stay in registers, short enough that regions dense in E / I
-    // agents (an SIA wave hits whole nodes) spread over all SMs instead of making a few blocks the tail
-    // (profiles/r1_fused_v6_postsia_*: 2.2x the time for 1.16x the instructions with contiguous block ranges)
-    const int64_t rows = (n + 127) >> 7;
-    const int64_t n_chunks = (rows + LPK_CHUNK_ROWS - 1) / LPK_CHUNK_ROWS;
-    uint2 *q = queue[warp];
-    int q_head = 0, q_count = 0;  // warp-uniform
-
-    TickAcc acc;
-    acc.init();
-    int tau_tn = -2;      // one-entry cache of tau_prev[node] (prefetch stage)
-    float tau_val = 0.f;
-    int q_nd = -2;        // and of the same value for the row being processed
-    float q_val = 0.f;
-    auto flush = [&](int nd, const int *ci, const long long *) {
-        red_add(&A.S_prev[nd], ci[CI_S]);
-        red_add(&A.R_prev[nd], ci[CI_R]);
-    };
-
-  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int64_t lo = chunk * LPK_CHUNK_ROWS;
-    const int64_t hi = (lo + LPK_CHUNK_ROWS < rows) ? lo + LPK_CHUNK_ROWS : rows;
     int64_t row = lo + warp;
     RowData cur, nxt;
     uint32_t w2 = 0xFFFFFFFFu;  // state word and tile node two rows ahead
     int tn2 = -1;
     cur.w = 0xFFFFFFFFu;
     if (row < hi) {
-        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), tau_tn, tau_val, cur);
+        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), tc_load, cur);
         if (row + LPK_WARPS < hi) { w2 = load_state_row(P, row + LPK_WARPS, lane, n); tn2 = load_tile_node(P, row + LPK_WARPS); }
     }
 #pragma unroll 1
@@ -336,14 +449,14 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
         // ---- keep the pipeline full
         const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
         nxt.w = 0xFFFFFFFFu;
-        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, tau_tn, tau_val, nxt);
+        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, tc_load, nxt);
         w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
         tn2 = (r2 < hi) ? load_tile_node(P, r2) : -1;
 
         // ---- row `row`
         const uint32_t w = cur.w;
         const int64_t b = (row * 32 + lane) * 4;
-        uint32_t cand = 0u, hits = 0u, nw = w;  // cand/hits: bit k = agent k of the quad goes to the active queue
+        uint32_t cand = 0u, hits = 0u, nw = w;  // cand: agents that go to the active queue
         int nd = cur.tn;
         if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
             const int valid = quad_valid(b, n);
@@ -355,92 +468,91 @@ __global__ void __launch_bounds__(LPK_BLOCK, 3) k_tick_pass(const __grid_constan
             if (!fast) {
                 nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
             } else {
-                acc.select(nd, flush);
-                const float rk[4] = {cur.rk.x, cur.rk.y, cur.rk.z, cur.rk.w};
-                if (pending) {
-                    // exposure trial of tick t-1
-                    const uint32_t mS = __vcmpeq4(w, 0u);
-                    if (mS) {
-                        if (nd != q_nd) { q_nd = nd; q_val = __ldg(&A.q_prev[nd]); }
-                        const float qn = q_val;
-                        if (qn > 0.f) {
-                            uint32_t x[4];
-                            philox_agent(A.seed, ((uint64_t)b + A.id_base) >> 2, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
-                            // p_i = 1 - exp(-risk_i * tau_n); hit iff x_i < floor(p_i * 2^32)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const bool hit = ((mS >> (8 * k)) & 1u) && expose_test(p_expose(__fmul_rn(rk[k], qn)), x[k]);
-                                hits |= hit ? (1u << k) : 0u;
-                            }
-                            nw |= ((hits & 1u) | ((hits & 2u) << 7) | ((hits & 4u) << 14) | ((hits & 8u) << 21));  // S (0) -> E (1)
+                if (pending && mask_S(w)) {  // exposure trial of tick t-1
+                    if (nd != tc_use.node) { tc_use.node = nd; tc_use.tau = __ldg(&A.q_prev[nd]); }
+                    const float tau = tc_use.tau;
+                    if (tau > 0.f) {
+                        const uint64_t id0 = (uint64_t)b + A.id_base;
+                        const uint64_t c = expose_ctr(id0);
+                        const int par = (int)((id0 >> 7) & 1u);
+                        uint32_t x[4];
+                        philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
+                                      (uint32_t)(A.seed >> 32), x);
+                        const uint32_t xa = par ? x[2] : x[0], xb = par ? x[3] : x[1];
+                        if (pretest_quad(xa, xb, cur.rk, tau * 65536.0f)) {
+                            hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, xa, xb, w, cur.rk, tau);
+                            nw |= hits;  // S (0) -> E (1)
                         }
                     }
-                    // census of tick t-1 on the post-exposure state (E / I agents are counted by the queue handler)
-                    acc.ci[CI_S] += __popc(__vcmpeq4(nw, 0u)) >> 3;
-                    acc.ci[CI_R] += __popc(__vcmpeq4(nw, 0x03030303u)) >> 3;
                 }
                 // ---- tick t
                 if (kDeaths) {
-                    const int dq[4] = {cur.dd.x, cur.dd.y, cur.dd.z, cur.dd.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (byte_of(nw, k) >= 0 && dq[k] <= tick) {
-                            if ((hits >> k) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << k); }
-                            if (pending && (byte_of(nw, k) == 1 || byte_of(nw, k) == 2)) census_ei(pp, b + k, nd, byte_of(nw, k));
-                            kill_agent(pp, b + k, nd, byte_of(nw, k));
-                            nw = set_byte(nw, k, -1);
-                        }
-                    }
+                    const uint32_t dm = death_mask(cur.dd, tick, nw);
+                    if (dm) { const uint2 r = death_quad(pp, b, nd, nw, hits, dm); nw = r.x; hits = r.y; }
                 }
-                const uint32_t mEI = __vcmpeq4(nw, 0x01010101u) | __vcmpeq4(nw, 0x02020202u);
-                cand = (mEI & 1u) | ((mEI >> 7) & 2u) | ((mEI >> 14) & 4u) | ((mEI >> 21) & 8u);
+                cand = mask_EI(nw);
                 if (kRI) {
                     // RI may set ipv_protected, which the disease-state step of the SAME tick must not see yet
                     // (reference order: DiseaseState_ABM before RI_ABM), so nothing is deferred on RI ticks.
 #pragma unroll 1
                     for (int k = 0; k < 4; ++k) {
-                        if (!((cand >> k) & 1u)) continue;
-                        if ((hits >> k) & 1u) expose_agent(pp, b + k, nd);
+                        if (!((cand >> (8 * k)) & 1u)) continue;
+                        if ((hits >> (8 * k)) & 1u) expose_agent(pp, b + k, nd);
                         int8_t sk = byte_of(nw, k);
                         if (pending) census_ei(pp, b + k, nd, sk);
-                        sk = ds_agent_ol(pp, b + k, sk);
+                        sk = ds_agent_ol(pp, b + k, sk, nd);
                         nw = set_byte(nw, k, sk);
                         if (sk == 2) tally_infectious(pp, b + k, nd);
                     }
                     cand = 0u;
                     nw = ri_quad(pp, b, 4, nw);
                 }
-                // tick t's tally: infectious agents in the queue handler; the susceptible side is carried incrementally
             }
             if (nw != w) store_b4(P.disease_state, b, valid, nw);
         }
-        // ---- append this row's active agents to the warp's ring; drain it 32 at a time (warp-uniform control flow).
-        // One round per candidate of the busiest lane (almost always one round).
-        while (__any_sync(LPK_FULL, cand != 0u)) {
-            const bool mine = cand != 0u;
-            const int k = __ffs(cand) - 1;
-            const uint32_t m = __ballot_sync(LPK_FULL, mine);
-            if (mine) {
-                q[(q_head + q_count + __popc(m & lt_mask)) & (QCAP - 1)] =
-                    q_pack((uint32_t)(b + k), nd, (nw >> (8 * k)) & 0xFFu, (hits >> k) & 1u);
-                cand &= cand - 1u;
-            }
-            q_count += __popc(m);
-            __syncwarp();
-            if (q_count >= 32) {
-                active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
-                q_head = (q_head + 32) & (QCAP - 1);
-                q_count -= 32;
-                __syncwarp();
-            }
-        }
+        q_commit(pp, Q, q_push(Q, (uint32_t)b, nd, nw, hits, cand), lane);
         cur = nxt;
     }
-    acc.finish_warp(flush);
-  }
+}
+
+template <bool kDeaths, bool kRI>
+__global__ void __launch_bounds__(LPK_BLOCK, LPK_PASS_BLOCKS_PER_SM) k_tick_pass(const __grid_constant__ PassParams pp) {
+    __shared__ uint2 queue[LPK_WARPS][QCAP];
+    __shared__ uint32_t q_tail[LPK_WARPS];
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t count_prev = A.counts[0], n = A.counts[1];
+    const int64_t rows = (n + 127) >> 7;
+    const int64_t n_chunks = (rows + LPK_CHUNK_ROWS - 1) / LPK_CHUNK_ROWS;
+    WarpQueue Q;
+    Q.q = queue[warp];
+    Q.tail = &q_tail[warp];
+    Q.head = 0u;
+    Q.count = 0;
+    if (lane == 0) q_tail[warp] = 0u;
     __syncwarp();
-    if (lane < q_count) active_agent(pp, q[(q_head + lane) & (QCAP - 1)]);
+    TauCache tc_load = {-2, 0.f}, tc_use = {-2, 0.f};
+
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t base = chunk * LPK_CHUNK_AGENTS;
+        // one node, every slot occupied since before tick t-1's transmission?  (64 tiles of 512 agents)
+        int cn = -1;
+        if (!kRI && P.tile_node && base + LPK_CHUNK_AGENTS <= count_prev) {
+            const int t0 = __ldg(&P.tile_node[chunk * 64 + lane]), t1 = __ldg(&P.tile_node[chunk * 64 + 32 + lane]);
+            const int first = __shfl_sync(LPK_FULL, t0, 0);
+            if (__all_sync(LPK_FULL, t0 == first && t1 == first)) cn = first;
+        }
+        if (cn >= 0) {
+            fast_chunk<kDeaths>(pp, Q, base, cn, lane, warp);
+        } else {
+            const int64_t lo = chunk * LPK_CHUNK_ROWS;
+            const int64_t hi = (lo + LPK_CHUNK_ROWS < rows) ? lo + LPK_CHUNK_ROWS : rows;
+            general_rows<kDeaths, kRI>(pp, Q, lo, hi, n, count_prev, tc_load, tc_use, lane, warp);
+        }
+    }
     __syncwarp();
+    if (lane < Q.count) active_agent(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
 }
 
 extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream) {
@@ -453,10 +565,10 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
                 P.paralyzed && P.ipv_protected && P.node_id && P.acq_risk_multiplier && P.daily_infectivity, "tick_pass agent columns");
     REQUIRE(ALIGNED(P.disease_state, 4) && ALIGNED(P.node_id, 8) && ALIGNED(P.acq_risk_multiplier, 16), "tick_pass alignment");
     REQUIRE((A.flags & LPK_F_STAGES) != 0, "tick_pass always runs the stages of its tick (LPK_F_STAGES)");
-    REQUIRE((A.id_base & 3) == 0, "tick_pass id_base must be a multiple of 4");
-    REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus && A.risk_hist, "tick_pass stage outputs");
-    REQUIRE(A.S_prev && A.R_prev && A.E_by_strain_prev && A.I_by_strain_prev && A.new_exposed_prev && A.new_exposed_by_strain_prev,
-            "tick_pass census rows");
+    REQUIRE((A.id_base & 255) == 0, "tick_pass id_base must be a multiple of 256");
+    REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus && A.risk_hist && A.R_cur && A.tx_hits,
+            "tick_pass stage outputs");
+    REQUIRE(A.E_by_strain_prev && A.I_by_strain_prev && A.new_exposed_prev && A.new_exposed_by_strain_prev, "tick_pass census rows");
     if (A.flags & LPK_F_PENDING) REQUIRE(A.q_prev && A.cdf_prev, "tick_pass pending exposure inputs");
     const bool deaths = (A.flags & LPK_F_DEATHS) != 0, ri = (A.flags & LPK_F_RI) != 0;
     if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && A.deaths && A.dead_pp && A.dead_par, "tick_pass deaths");
@@ -466,7 +578,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     PassParams pp;
     pp.P = P;
     pp.A = A;
-    const int grid = lpk_agent_grid(P.capacity, 3);
+    const int grid = lpk_agent_grid(P.capacity, LPK_PASS_BLOCKS_PER_SM);
     cudaStream_t st = as_stream(stream);
     if (deaths && ri) k_tick_pass<true, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
     else if (deaths) k_tick_pass<true, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
@@ -528,6 +640,15 @@ __global__ void k_tick_epilogue(lpk_node_args a) {
         a.cur_potp[n] = potp; a.cur_p[n] = par;
         a.potp_row[n] = potp; a.p_row[n] = par;
     }
+    if (a.S_snap) {
+        if (a.flags & LPK_F_PENDING) {
+            a.S_prev[n] = a.S_snap[n] - a.tx_hits[n];  // "=" (model.py:1476)
+            a.R_prev[n] += a.R_snap[n];                // "+=" on top of the pre-seeded immunes (model.py:1481)
+        }
+        a.tx_hits[n] = 0;
+        a.S_snap[n] = (int32_t)a.sus[n];
+        a.R_snap[n] = a.R_cur[n];
+    }
     if ((a.flags & LPK_F_PENDING) && a.E_prev) {
         int e = 0, i = 0;
         for (int s = 0; s < ns; ++s) { e += a.E_by_strain_prev[(int64_t)n * ns + s]; i += a.I_by_strain_prev[(int64_t)n * ns + s]; }
@@ -551,6 +672,8 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(!a.pop || (a.pop_prev && (!(a.flags & LPK_F_DEATHS) || (a.deaths_row && a.deaths))), "tick_node population rows");
     REQUIRE(!a.cur_potp || (a.cur_p && a.new_potential && a.new_paralyzed && a.potp_row && a.p_row), "tick_node paralysis rows");
     REQUIRE(!a.deaths || (a.dead_pp && a.dead_par), "tick_node death scratch");
+    REQUIRE(!a.S_snap || (a.R_snap && a.sus && a.R_cur && a.tx_hits && (!(a.flags & LPK_F_PENDING) || (a.S_prev && a.R_prev))),
+            "tick_node carried census");
     REQUIRE(a.pop || a.pop_prev, "tick_node needs a population row for the rate denominator");
     cudaStream_t st = as_stream(stream);
     k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);

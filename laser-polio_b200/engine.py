@@ -56,6 +56,9 @@ class FusedEngine:
         self.beta = [i64(n, ns), i64(n, ns)]  # infectivity tally, recomputed every tick (ping-pong)
         # susceptible-side tallies carried from tick to tick and corrected by the pass (include/lpk.h, lpk_tick_args)
         self.expo, self.sus, self.hist = i64(n), i64(n), i32(n, _lpk.RISK_BINS)
+        # recovered per node, carried the same way; per-node exposures found by a pass; census snapshots (lpk_node_args)
+        self.R_cur, self.tx_hits, self.S_snap, self.R_snap = i32(n), i32(n), i32(n), i32(n)
+        self._census_scratch = [i32(n) for _ in range(6)] + [i32(n, ns), i32(n, ns)]
         self._beta_scratch = i64(n, ns)
         self.deaths, self.dead_pp, self.dead_par = i32(n), i32(n), i32(n)
         self.cur_potp, self.cur_p = i32(n), i32(n)
@@ -92,6 +95,10 @@ class FusedEngine:
         K.tx_step_prep(dev.n_nodes, sim.people.count, dev.n_strains, c["strain"], list(sim.pars.strain_r0_scalars.values()),
                        c["disease_state"], c["node_id"], c["daily_infectivity"], c["acq_risk_multiplier"],
                        out=(self._beta_scratch, self.expo, self.sus, self.hist))
+        S, E, I, R, POTP, Pz, Es, Is = self._census_scratch
+        K.count_SEIRP(c["node_id"], c["disease_state"], c["strain"], c["potentially_paralyzed"], c["paralyzed"], dev.n_nodes,
+                      dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, Es, Is, POTP, Pz))
+        self.tx_hits.zero_()
 
     def _row(self, name, t):
         r = self.dev.res.get(name)
@@ -152,8 +159,8 @@ class FusedEngine:
         A.q_prev, A.cdf_prev = dp(self.q), dp(self.cdf)
         tp = max(t - 1, 0)
         A.new_exposed_prev, A.new_exposed_by_strain_prev = dp(self._row("new_exposed", tp)), dp(self._row("new_exposed_by_strain", tp))
-        A.S_prev, A.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
         A.E_by_strain_prev, A.I_by_strain_prev = dp(self._row("E_by_strain", tp)), dp(self._row("I_by_strain", tp))
+        A.tx_hits, A.R_cur = dp(self.tx_hits), dp(self.R_cur)
         A.p_paralysis = float(np.float32(pars.p_paralysis))
         A.new_potential, A.new_paralyzed = dp(self._row("new_potentially_paralyzed", t)), dp(self._row("new_paralyzed", t))
         A.deaths, A.dead_pp, A.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
@@ -201,6 +208,8 @@ class FusedEngine:
         N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
         N.E_by_strain_prev, N.I_by_strain_prev = A.E_by_strain_prev, A.I_by_strain_prev
         N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
+        N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
+        N.S_prev, N.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
         N.next_beta_fx = dp(self.beta[(t + 1) & 1])
         N.counts = dp(dev.counts)
         K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 4)

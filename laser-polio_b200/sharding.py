@@ -59,14 +59,14 @@ def plan_node_blocks(node_agents, world: int):
 
 
 def id_bases(node_agents, blocks, capacity_per_block=None):
-    """Global id of each shard's first agent: the running sum of shard sizes rounded up to a multiple of 4
-    (exposure draws are made per aligned group of four agents)."""
+    """Global id of each shard's first agent: the running sum of shard sizes rounded up to a multiple of 256
+    (exposure draws are made per aligned group of 256 agents: one Philox block per lane and pair of 128-agent rows)."""
     sizes = np.asarray(node_agents, dtype=np.int64)
     bases, run = [], 0
     for k, (lo, hi) in enumerate(blocks):
         bases.append(run)
         span = int(sizes[lo:hi].sum()) if capacity_per_block is None else int(capacity_per_block[k])
-        run += (span + 3) // 4 * 4
+        run += (span + 255) // 256 * 256
     return bases
 
 

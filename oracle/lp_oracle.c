@@ -66,7 +66,8 @@ enum {
     ORC_STAGE_STRAIN = 4,
     ORC_STAGE_NODE = 5,
     ORC_STAGE_BIRTH = 6,
-    ORC_STAGE_LIFESPAN = 7
+    ORC_STAGE_LIFESPAN = 7,
+    ORC_STAGE_EXPOSE_LO = 8
 };
 
 static inline void agent_block(uint64_t seed, uint64_t idx, uint32_t tick, uint32_t stage, uint32_t out[4]) {
@@ -479,11 +480,26 @@ void orc_tx_infect_ref(int32_t n_nodes, int64_t n_people, int32_t n_strains, con
 /* ------------------------------- T3 (device scheme: per-agent Bernoulli) */
 /* SURVEY Appendix F option F1 + importation gate, the scheme the north star
  * prescribes for the device: susceptible agent i of node n is exposed iff
- * x_i < thr(risk_i * q[n]) with x_i the (i & 3)-th word of the Philox block
- * (seed, i >> 2, tick, EXPOSE) and q[n] = float(P_n * g_n); strain by the cumulative
+ * x_i < thr(risk_i * q[n]) with x_i = expose_word(seed, i, tick) (below) and
+ * q[n] = tau[n] (oracle.py: tx_node_math); strain by the cumulative
  * categorical of model.py:1127-1141 on a second block (seed, i, tick, STRAIN).
  * Marginal exposure probability w_i * P_n and node mean exposure[n] * P_n equal the
  * reference's (model.py:1362-1363, 1087). */
+/* The 32-bit exposure word of agent id (= index + id_base): X = h16 << 16 | l16, the half-words
+ * hw = ((id >> 7) & 1) * 4 + (id & 3) of the two Philox blocks (seed; ctr, tick, EXPOSE / EXPOSE_LO),
+ * ctr = (id >> 8) * 32 + ((id >> 2) & 31): one block serves the 8 agents a device lane owns in a pair of
+ * 128-agent rows, and the device generates the low block only when the high half cannot decide the trial
+ * (include/lpk.h, T3). */
+static inline uint32_t expose_word(uint64_t seed, uint64_t id, uint32_t tick) {
+    uint64_t ctr = ((id >> 8) << 5) | ((id >> 2) & 31u);
+    int hw = (int)(((id >> 7) & 1u) * 4u + (id & 3u));
+    uint32_t h[4], l[4];
+    agent_block(seed, ctr, tick, ORC_STAGE_EXPOSE, h);
+    agent_block(seed, ctr, tick, ORC_STAGE_EXPOSE_LO, l);
+    uint32_t h16 = (h[hw >> 1] >> (16 * (hw & 1))) & 0xFFFFu, l16 = (l[hw >> 1] >> (16 * (hw & 1))) & 0xFFFFu;
+    return (h16 << 16) | l16;
+}
+
 static inline uint32_t expose_threshold(float p, int *always) {
     *always = 0;
     if (!(p > 0.f)) return 0u;
@@ -510,7 +526,7 @@ void orc_tx_infect_bernoulli(int32_t n_nodes, int64_t n_people, int32_t n_strain
         uint32_t thr = expose_threshold(p, &always);
         uint32_t x;
         if (x_inj) x = x_inj[i];
-        else { uint32_t b[4]; agent_block(seed, ((uint64_t)i + id_base) >> 2, tick, ORC_STAGE_EXPOSE, b); x = b[(i + id_base) & 3]; }
+        else x = expose_word(seed, (uint64_t)i + id_base, tick);
         if (!(always || x < thr)) continue;
         double r;
         if (u_strain_inj) r = u_strain_inj[i];

@@ -30,8 +30,9 @@ def pyramid(tmp_path_factory):
 
 def make(lp, pyramid, fused, components, **over):
     n_nodes = over.pop("n_nodes", 5)
+    pop_lo, pop_hi = over.pop("pop_range", (3000, 30000))
     rs = np.random.RandomState(3)
-    init_pop = rs.randint(3000, 30000, n_nodes)
+    init_pop = rs.randint(pop_lo, pop_hi, n_nodes)
     d = rs.uniform(5, 300, (n_nodes, n_nodes))
     d = (d + d.T) / 2
     np.fill_diagonal(d, 0)
@@ -93,6 +94,29 @@ def test_fused_equals_components_full_feature_set(lp, pyramid):
     alive = fus.people.disease_state[: fus.people.count] >= 0
     assert r.potentially_paralyzed[-1].sum() == np.sum((fus.people.potentially_paralyzed[: fus.people.count] == 1) & alive)
     assert r.paralyzed[-1].sum() == np.sum((fus.people.paralyzed[: fus.people.count] == 1) & alive)
+
+
+def test_fused_equals_components_large_nodes(lp, pyramid):
+    """Nodes of 120-260 K agents: most 32 K-agent chunks lie inside one node and take the pass's single-node loop (one
+    Philox block per 8 agents, high-half pre-test); node boundaries, newborn cohorts and RI ticks take the general rows."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, n_nodes=4, pop_range=(120_000, 260_000), dur=40, r0=6,
+                                      init_prev=[0.004, 0.0, 0.001, 0.0])
+    assert calls.get("tick_pass", 0) >= 30
+    assert_identical(ref, fus)
+    r = fus.results
+    assert r.new_exposed.sum() > 20_000 and r.deaths.sum() > 0 and r.births.sum() > 0 and r.ri_vaccinated.sum() > 0
+    assert (r.R[-1] > r.R[0]).all() and np.array_equal(r.E, r.E_by_strain.sum(axis=2))
+
+
+def test_fused_equals_components_saturating_force_of_infection(lp, pyramid):
+    """r0 = 999 (the reference's own 'everybody gets exposed' regime, tests/test_diseasestate_abm.py:258): tau is huge or
+    'everybody', so the high-half pre-test passes for every susceptible and the exact path decides."""
+    comps = [lp.DiseaseState_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, _) = run_pair(lp, pyramid, comps, n_nodes=3, pop_range=(70_000, 90_000), dur=12, r0=999, sia_schedule=None,
+                                  seed_schedule=None, vx_prob_ri=None, init_immun=0.0, init_prev=[0.01, 0.01, 0.01])
+    assert_identical(ref, fus)
+    assert fus.results.S[-1].sum() < 0.005 * fus.results.S[0].sum()  # all but a few agents of negligible risk
 
 
 def test_fused_equals_components_transmission_only_many_nodes(lp, pyramid):

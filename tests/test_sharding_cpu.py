@@ -52,7 +52,7 @@ def test_shard_to_partitions_the_agent_table(tmp_path):
             assert np.array_equal(getattr(p, name)[: p.count], col[:count][own]), name
         assert np.all(p.disease_state[p.count:] == -1) and np.all(p.node_id[p.count:] == -1)
         assert all(inst.people is p for inst in sim.instances)
-        assert sim.id_base % 4 == 0
+        assert sim.id_base % 256 == 0
         id_ranges.append((sim.id_base, sim.id_base + p.capacity))
         seen += p.count
         assert np.array_equal(sim.results.pop[0], whole.results.pop[0])  # per-node arrays keep the global length
