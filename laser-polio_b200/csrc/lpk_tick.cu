@@ -17,6 +17,8 @@
 //     time with all lanes busy (they sit in ~90 % of the 128-agent rows, so handling them in place made every warp walk
 //     the long disease-state path with one or two live lanes);
 //   * everything rare (a hit, a death, an RI-eligible agent, a node boundary) lives in __noinline__ functions.
+#include <cstdlib>
+
 #include "lpk_host.cuh"
 #include "lpk_stages.cuh"
 
@@ -26,11 +28,8 @@ struct PassParams {
 };
 
 #define QCAP 512             // ring entries per warp: 31 left over + the 256 agents of one iteration fit
-#define LPK_CHUNK_ROWS 256   // rows of 128 agents per chunk (32 K agents), dealt round-robin to the blocks
-#define LPK_CHUNK_AGENTS (LPK_CHUNK_ROWS * 128)
-#ifndef LPK_PASS_BLOCKS_PER_SM
-#define LPK_PASS_BLOCKS_PER_SM 2
-#endif
+#define LPK_CHUNK_PAIRS 192  // pairs of 128-agent rows per chunk (48 K agents), dealt round-robin to the blocks
+#define LPK_CHUNK_ITERS (LPK_CHUNK_PAIRS / LPK_WARPS)  // a warp's pairs per chunk: a multiple of the pipeline depth 4
 
 // ------------------------------------------------------------------ rare paths (out of line, direct atomics)
 __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
@@ -270,14 +269,31 @@ __device__ __noinline__ void active_agent(const PassParams &pp, uint2 e) {
 }
 
 // append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; returns how many
-__device__ __forceinline__ int q_push(WarpQueue &Q, uint32_t idx0, int nd, uint32_t nw, uint32_t hits, uint32_t m) {
+__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t nw, uint32_t hits, uint32_t m) {
     const uint32_t comb = nw | (hits << 4);
     const int cnt = __popc(m);
     while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
-        const uint32_t pos = atomicAdd(Q.tail, 1u) & (QCAP - 1);
-        Q.q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((comb >> bit) & 0xFFu) << 16));
+        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
+        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((comb >> bit) & 0xFFu) << 16));
+    }
+    return cnt;
+}
+// the same for the two quads a lane owns in a row pair (B = A + 128 agents): one loop for both
+__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t nwA, uint32_t hA, uint32_t mA,
+                                           uint32_t nwB, uint32_t hB, uint32_t mB) {
+    const uint32_t combA = nwA | (hA << 4), combB = nwB | (hB << 4);
+    uint32_t m = mA | (mB << 4);
+    const int cnt = __popc(m);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        const bool rowB = (bit & 4) != 0;
+        const uint32_t comb = rowB ? combB : combA;
+        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
+        q[pos] = make_uint2(idxA + (uint32_t)(bit >> 3) + (rowB ? 128u : 0u),
+                            ((uint32_t)nd & 0xFFFFu) | (((comb >> (bit & 24)) & 0xFFu) << 16));
     }
     return cnt;
 }
@@ -292,7 +308,7 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
     }
 }
 
-// out-of-line part of a death in a fast chunk: the quad's agents in mask dm die on tick t (after tick t-1's pending
+// out-of-line part of a death in a node-uniform quad: the agents in mask dm die on tick t (after tick t-1's pending
 // exposure + census); returns {new state word, remaining hits}
 __device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t dm) {
     const bool pending = (pp.A.flags & LPK_F_PENDING) != 0;
@@ -312,247 +328,364 @@ __device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick, uint32_t
            mask_alive(w);
 }
 
-// ------------------------------------------------------------------ fast chunk: 32 K agents of ONE node, all of them
-// present at tick t-1.  A warp takes every 8th row pair; a lane owns its quad in the even row (A) and in the odd row (B).
-struct PairData {
-    uint32_t wA, wB;
-    float4 rA, rB;
-    int4 dA, dB;
-};
-template <bool kDeaths>
-__device__ __forceinline__ void fast_chunk(const PassParams &pp, WarpQueue &Q, int64_t base, int nd, int lane, int warp) {
+// ---- routine immunisation in a node-uniform quad (reference model.py:1825-1854) -----------------------------------
+// Every alive, not chronically missed agent's ri_timer goes down by the step (four int16 lanes at a time); an agent is
+// eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Eligible agents are the few in
+// the age window, handled out of line.
+__device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t b, uint32_t w, uint32_t missed, uint2 tm) {
+    const int step = pp.A.ri_step;
+    const uint32_t ok8 = mask_alive(w) & ~missed;  // missed bytes are 0 / 1
+    if (!ok8) return 0u;
+    const uint2 tn = make_uint2(__vsub2(tm.x, __byte_perm(ok8, 0u, 0x4140) * (uint32_t)step),
+                                __vsub2(tm.y, __byte_perm(ok8, 0u, 0x4342) * (uint32_t)step));
+    *reinterpret_cast<uint2 *>(pp.P.ri_timer + b) = tn;
+    const int lo = (pp.A.tick == step) ? -step : 1 - step;  // eligible: lo <= timer <= 0
+    const uint32_t lo2 = ((uint32_t)lo & 0xFFFFu) * 0x10001u, span2 = ((uint32_t)(-lo) & 0xFFFFu) * 0x10001u;
+    const uint32_t ex = __vcmpleu2(__vsub2(tn.x, lo2), span2), ey = __vcmpleu2(__vsub2(tn.y, lo2), span2);
+    return __byte_perm(ex, ey, 0x6420) & ok8;
+}
+// the eligible agents (mask elig) of the quad: disease state first where the agent is E / I (RI may set ipv_protected,
+// which the disease-state step of the SAME tick must not see: reference order DiseaseState_ABM before RI_ABM), then the
+// two draws.  Returns {new state word, cand | hits << 1} with the agents handled here removed from cand / hits.
+__device__ __noinline__ uint2 ri_eligible_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t cand,
+                                               uint32_t elig) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    const float tau = pending ? __ldg(&A.q_prev[nd]) : 0.f;
-    const bool expose = tau > 0.f;  // no force of infection on the node: neither risk nor random numbers are needed
-    const float tau16 = tau * 65536.0f;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t bit = 1u << (8 * k);
+        if (!(elig & bit)) continue;
+        const int64_t i = b + k;
+        int8_t s = byte_of(nw, k);
+        if (cand & bit) {
+            if (hits & bit) expose_agent(pp, i, nd);
+            if (pending) census_ei(pp, i, nd, s);
+            s = ds_agent_ol(pp, i, s, nd);
+            nw = set_byte(nw, k, s);
+            if (s == 2) tally_infectious(pp, i, nd);
+            cand &= ~bit;
+            hits &= ~bit;
+        }
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
+        const double u1 = u53(x[0], x[1]), u2 = u53(x[2], x[3]);
+        if (u1 < A.vx_prob_ri[nd]) {
+            atomicAdd(&A.ri_vaccinated[nd], 1);
+            if (s == 0) {
+                nw = set_byte(nw, k, 1);
+                P.strain[i] = (int8_t)A.ri_strain;
+                leave_S(pp, i, nd);
+                const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
+                atomicAdd(&A.ri_protected[nd], 1);
+                atomicAdd(&A.new_exposed[nd], 1);
+                atomicAdd(&A.new_exposed_by_strain[c], 1);
+                atomicAdd(&A.ri_new_exposed_by_strain[c], 1);
+            }
+        }
+        if (u2 < A.vx_prob_ipv[nd]) { atomicAdd(&A.ipv_vaccinated[nd], 1); P.ipv_protected[i] = 1; }
+    }
+    return make_uint2(nw, cand | (hits << 1));
+}
+
+// ------------------------------------------------------------------ general pair (out of line): 256 agents that are not
+// all in one node or were not all present at tick t-1 (node boundaries, newborn cohorts, the table's tail).  One row at a
+// time, no software pipeline.  Returns how many agents this lane appended to the ring.
+template <bool kDeaths, bool kRI>
+__device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_t *q_tail, int64_t gp, int64_t n, int64_t count_prev,
+                                         int lane) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    const int tick = A.tick;
+    int mine = 0;
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        const int64_t b = gp * 256 + r * 128 + lane * 4;
+        const int valid = quad_valid(b, n);
+        if (!valid) continue;
+        const uint32_t w = load_b4(P.disease_state, b, valid);
+        if ((w & 0x80808080u) == 0x80808080u) continue;  // nobody alive
+        uint32_t nw = w, hits = 0u, cand = 0u;
+        int nd = -1;
+        bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
+        if (fast) {
+            const uint2 ids = *reinterpret_cast<const uint2 *>(P.node_id + b);
+            nd = (int)(int16_t)(ids.x & 0xFFFFu);
+            fast = ids.x == ids.y && (ids.x >> 16) == (ids.x & 0xFFFFu) && nd >= 0;
+        }
+        if (!fast) {
+            nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
+        } else {
+            if (pending && mask_S(w)) {  // exposure trial of tick t-1
+                const float tau = __ldg(&A.q_prev[nd]);
+                if (tau > 0.f) {
+                    const uint64_t id0 = (uint64_t)b + A.id_base;
+                    const uint64_t c = expose_ctr(id0);
+                    const int par = (int)((id0 >> 7) & 1u);
+                    uint32_t x[4];
+                    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
+                                  (uint32_t)(A.seed >> 32), x);
+                    const float4 rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
+                    hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, par ? x[2] : x[0], par ? x[3] : x[1], w, rk, tau);
+                    nw |= hits;  // S (0) -> E (1)
+                }
+            }
+            if (kDeaths) {
+                const int4 dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
+                const uint32_t dm = death_mask(dd, tick, nw);
+                if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, dm); nw = o.x; hits = o.y; }
+            }
+            cand = mask_EI(nw);
+            if (kRI) {
+                const uint32_t missed = *reinterpret_cast<const uint32_t *>(P.chronically_missed + b);
+                const uint2 tm = *reinterpret_cast<const uint2 *>(P.ri_timer + b);
+                const uint32_t elig = ri_timers_quad(pp, b, nw, missed, tm);
+                if (elig) { const uint2 o = ri_eligible_quad(pp, b, nd, nw, hits, cand, elig); nw = o.x; cand = o.y & 0x01010101u; hits = (o.y >> 1) & 0x01010101u; }
+            }
+        }
+        if (nw != w) store_b4(P.disease_state, b, valid, nw);
+        mine += q_push(q, q_tail, (uint32_t)b, nd, nw, hits, cand);
+    }
+    return mine;
+}
+
+// ------------------------------------------------------------------ the pass
+// Unit of work: a PAIR of 128-agent rows (256 consecutive agents); a lane owns its quad in the even row (A) and in the
+// odd row (B).  Pairs are grouped in chunks of LPK_CHUNK_PAIRS dealt round-robin to the blocks (a chunk is short enough
+// that regions dense in E / I agents -- an SIA wave hits whole nodes -- spread over all SMs); inside a chunk a warp takes
+// every 8th pair.  A warp's pairs form one sequence s = 0, 1, ... served by the warp's PRIVATE ring of kStages
+// shared-memory slots: one elected lane asks the TMA engine for the pair's columns (cp.async.bulk: 256 B of state, 1 KB
+// of risk, + date_of_death / chronically_missed / ri_timer on vital-dynamics / RI ticks) kStages iterations ahead, the
+// bytes land on the slot's mbarrier, and the warp reads its quads from shared memory.  The copies cost no registers and
+// no per-lane load instructions, so the depth of the memory pipeline is set by shared memory (40 KB per block), not by
+// occupancy.  The pair's node (tile table) and the node's exposure scale tau are looked up at issue time: with no force
+// of infection on the node neither risk nor random numbers are touched.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 26)) __trap();  // a lost copy would otherwise hang the device; this turns it into an error
+}
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool kDeaths, bool kRI>
+struct PassSmem {
+    static constexpr int kStages = (kDeaths || kRI) ? 3 : 4;
+    static constexpr int kOffRisk = 256, kOffDod = 1280, kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
+    static constexpr int kStageBytes = kOffMissed + (kRI ? 768 : 0);
+    static constexpr int kOffQueue = 0;
+    static constexpr int kOffSlots = kOffQueue + LPK_WARPS * QCAP * 8;
+    static constexpr int kOffBars = kOffSlots + LPK_WARPS * kStages * kStageBytes;
+    static constexpr int kOffMeta = kOffBars + LPK_WARPS * kStages * 8;
+    static constexpr int kOffTail = kOffMeta + LPK_WARPS * kStages * 8;
+    static constexpr int kBytes = kOffTail + LPK_WARPS * 4 + 32;
+};
+
+template <bool kDeaths, bool kRI, int kOcc>
+__global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_constant__ PassParams pp) {
+    typedef PassSmem<kDeaths, kRI> L;
+    constexpr int NST = L::kStages;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t count_prev = A.counts[0], n = A.counts[1];
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick;
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
-    const int64_t lane_base = base + lane * 4;
-    const uint64_t ctr_base = ((((uint64_t)base + A.id_base) >> 8) << 5) + (uint64_t)lane;
-    const int8_t *sp = P.disease_state + lane_base;
-    const float *rp = P.acq_risk_multiplier + lane_base;
-    const int32_t *dp = kDeaths ? P.date_of_death + lane_base : nullptr;
-    auto load = [&](int p, PairData &d) {
-        const int o = p * 256;
-        d.wA = *reinterpret_cast<const uint32_t *>(sp + o);
-        d.wB = *reinterpret_cast<const uint32_t *>(sp + o + 128);
-        if (expose) {
-            d.rA = __ldg(reinterpret_cast<const float4 *>(rp + o));
-            d.rB = __ldg(reinterpret_cast<const float4 *>(rp + o + 128));
+    const int64_t total_pairs = (n + 255) >> 8;
+    const int64_t full_pairs = P.tile_node ? (count_prev >> 8) : 0;  // pairs whose 256 agents all existed at tick t-1
+    const int64_t n_chunks = (total_pairs + LPK_CHUNK_PAIRS - 1) / LPK_CHUNK_PAIRS;
+    const int64_t my_chunks = (int64_t)blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int S = (int)(my_chunks * LPK_CHUNK_ITERS);
+
+    unsigned char *slots = smem + L::kOffSlots + warp * NST * L::kStageBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBars) + warp * NST;
+    int2 *meta = reinterpret_cast<int2 *>(smem + L::kOffMeta) + warp * NST;
+    WarpQueue Q;
+    Q.q = reinterpret_cast<uint2 *>(smem + L::kOffQueue) + warp * QCAP;
+    Q.tail = reinterpret_cast<uint32_t *>(smem + L::kOffTail) + warp;
+    Q.head = 0u;
+    Q.count = 0;
+    if (lane == 0) {
+        *Q.tail = 0u;
+        for (int k = 0; k < NST; ++k) mbar_init(&bars[k], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto pair_of = [&](int s) -> int64_t {
+        const int c = s / LPK_CHUNK_ITERS, it = s - c * LPK_CHUNK_ITERS;
+        return ((int64_t)blockIdx.x + (int64_t)c * gridDim.x) * LPK_CHUNK_PAIRS + it * LPK_WARPS + warp;
+    };
+    // node of pair s: >= 0 all 256 agents in that node and present at tick t-1; -1 general handling; -2 nothing to do
+    auto node_of = [&](int s) -> int {
+        const int64_t gp = pair_of(s);
+        if (s >= S || gp >= total_pairs) return -2;
+        return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
+    };
+    int tc_node = -2;  // one-entry cache of tau per node (a warp stays in one node for hundreds of pairs)
+    float tc_tau = 0.f;
+    int tn_next = node_of(0);  // node of the next pair to be requested, loaded one request ahead
+    // request pair s into slot (warp-uniform; the elected lane talks to the TMA engine)
+    auto produce = [&](int s, int slot) {
+        const int tn = tn_next;
+        tn_next = node_of(s + 1);
+        float tau = 0.f;
+        if (tn >= 0) {
+            if (tn != tc_node) { tc_node = tn; tc_tau = pending ? __ldg(&A.q_prev[tn]) : 0.f; }
+            tau = tc_tau;
         }
-        if (kDeaths) {
-            d.dA = __ldg(reinterpret_cast<const int4 *>(dp + o));
-            d.dB = __ldg(reinterpret_cast<const int4 *>(dp + o + 128));
+        if (lane == 0) {
+            meta[slot] = make_int2(tn, __float_as_int(tau));
+            uint64_t *bar = &bars[slot];
+            if (tn >= 0) {
+                const int64_t a0 = pair_of(s) * 256;
+                unsigned char *dst = slots + slot * L::kStageBytes;
+                const bool risk = tau > 0.f;
+                fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
+                mbar_arrive_expect_tx(bar, 256u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (kRI ? 768u : 0u));
+                tma_load(dst, P.disease_state + a0, 256u, bar);
+                if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
+                if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
+                if (kRI) {
+                    tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
+                    tma_load(dst + L::kOffTimer, P.ri_timer + a0, 512u, bar);
+                }
+            } else {
+                mbar_arrive(bar);
+            }
         }
     };
-    PairData cur, nxt;
-    load(warp, cur);
-#pragma unroll 2
-    for (int p = warp; p < LPK_CHUNK_ROWS / 2; p += LPK_WARPS) {
-        if (p + LPK_WARPS < LPK_CHUNK_ROWS / 2) load(p + LPK_WARPS, nxt);
-        const int64_t bA = lane_base + p * 256, bB = bA + 128;
-        uint32_t nwA = cur.wA, nwB = cur.wB, hA = 0u, hB = 0u;
-        if (expose) {  // exposure trial of tick t-1
-            const uint64_t c = ctr_base + (uint64_t)(p * 32);
+
+    // process pair s from slot, then re-arm the slot with pair s + NST
+    auto consume = [&](int s, int slot, uint32_t parity) {
+        mbar_wait(&bars[slot], parity);
+        const int2 mt = meta[slot];
+        const int tn = mt.x;
+        const float tau = __int_as_float(mt.y);
+        const unsigned char *src = slots + slot * L::kStageBytes;
+        uint32_t wA = 0u, wB = 0u, mA = 0u, mB = 0u;
+        float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA;
+        int4 dA = make_int4(0, 0, 0, 0), dB = dA;
+        uint2 tA = make_uint2(0u, 0u), tB = tA;
+        if (tn >= 0) {
+            wA = *reinterpret_cast<const uint32_t *>(src + lane * 4);
+            wB = *reinterpret_cast<const uint32_t *>(src + 128 + lane * 4);
+            if (tau > 0.f) {
+                rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
+                rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
+            }
+            if (kDeaths) {
+                dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
+                dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
+            }
+            if (kRI) {
+                mA = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + lane * 4);
+                mB = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + 128 + lane * 4);
+                tA = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + lane * 8);
+                tB = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + 256 + lane * 8);
+            }
+        }
+        __syncwarp();
+        produce(s + NST, slot);
+        if (tn == -2) return;
+        const int64_t gp = pair_of(s);
+        if (tn < 0) {
+            q_commit(pp, Q, general_pair<kDeaths, kRI>(pp, Q.q, Q.tail, gp, n, count_prev, lane), lane);
+            return;
+        }
+        const int nd = tn;
+        const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
+        uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u;
+        if (tau > 0.f) {  // exposure trial of tick t-1
+            const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
             uint32_t x[4];
             philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
-            if (pretest_quad(x[0], x[1], cur.rA, tau16) | pretest_quad(x[2], x[3], cur.rB, tau16)) {
-                hA = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 0, x[0], x[1], nwA, cur.rA, tau);
-                hB = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 1, x[2], x[3], nwB, cur.rB, tau);
+            const float tau16 = tau * 65536.0f;
+            if (pretest_quad(x[0], x[1], rA, tau16) | pretest_quad(x[2], x[3], rB, tau16)) {
+                hA = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 0, x[0], x[1], nwA, rA, tau);
+                hB = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 1, x[2], x[3], nwB, rB, tau);
                 nwA |= hA;  // S (0) -> E (1)
                 nwB |= hB;
             }
         }
         if (kDeaths) {  // tick t
-            const uint32_t dmA = death_mask(cur.dA, tick, nwA), dmB = death_mask(cur.dB, tick, nwB);
-            if (dmA) { const uint2 r = death_quad(pp, bA, nd, nwA, hA, dmA); nwA = r.x; hA = r.y; }
-            if (dmB) { const uint2 r = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = r.x; hB = r.y; }
+            const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
+            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, hA, dmA); nwA = o.x; hA = o.y; }
+            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = o.x; hB = o.y; }
         }
-        if (nwA != cur.wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
-        if (nwB != cur.wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
         // exposed / infectious agents (fresh hits included): census of t-1, disease state and tally of t in the handler
-        int mine = q_push(Q, (uint32_t)bA, nd, nwA, hA, mask_EI(nwA));
-        mine += q_push(Q, (uint32_t)bB, nd, nwB, hB, mask_EI(nwB));
-        q_commit(pp, Q, mine, lane);
-        cur = nxt;
-    }
-}
-
-// ------------------------------------------------------------------ general rows: node boundaries, newborn cohorts, the
-// table's tail, RI ticks.  A warp walks rows of 128 agents (one quad per lane).  Software pipeline: the state word of row
-// r+2, and the risk / node / date_of_death words of row r+1 (predicated on its state, which arrived an iteration ago),
-// are in flight while row r is processed.
-struct RowData {
-    uint32_t w;      // 4 state bytes
-    float4 rk;       // acq_risk_multiplier of the quad (if it has a susceptible)
-    uint2 nd;        // 4 node ids (only when the tile is not node-uniform)
-    int4 dd;         // date_of_death (vital-dynamics ticks only)
-    int tn;          // tile's node or -1
-};
-struct TauCache {
-    int node;
-    float tau;
-};
-
-template <bool kDeaths>
-__device__ __forceinline__ void issue_row_loads(const lpk_people &P, const float *tau_prev, int64_t row, int lane, int64_t n,
-                                                uint32_t w, int tn, TauCache &tc, RowData &d) {
-    const int64_t b = (row * 32 + lane) * 4;
-    d.w = w;
-    d.tn = tn;
-    const bool full = b + 4 <= n;
-    const bool alive = (w & 0x80808080u) != 0x80808080u;
-    d.rk = make_float4(0.f, 0.f, 0.f, 0.f);
-    d.nd = make_uint2(0u, 0u);
-    if (full && alive) {
-        // risk is only needed for the exposure trial: skipped when nothing is pending or the tile's node has no force of infection
-        bool live = tau_prev != nullptr;
-        if (live && d.tn >= 0) {
-            if (d.tn != tc.node) { tc.node = d.tn; tc.tau = __ldg(&tau_prev[d.tn]); }  // warp-uniform branch
-            live = tc.tau > 0.f;
+        uint32_t cA = mask_EI(nwA), cB = mask_EI(nwB);
+        if (kRI) {
+            const uint32_t eA = ri_timers_quad(pp, bA, nwA, mA, tA), eB = ri_timers_quad(pp, bB, nwB, mB, tB);
+            if (eA) { const uint2 o = ri_eligible_quad(pp, bA, nd, nwA, hA, cA, eA); nwA = o.x; cA = o.y & 0x01010101u; hA = (o.y >> 1) & 0x01010101u; }
+            if (eB) { const uint2 o = ri_eligible_quad(pp, bB, nd, nwB, hB, cB, eB); nwB = o.x; cB = o.y & 0x01010101u; hB = (o.y >> 1) & 0x01010101u; }
         }
-        if (live && mask_S(w)) d.rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
-        if (d.tn < 0) d.nd = *reinterpret_cast<const uint2 *>(P.node_id + b);
-        if (kDeaths) d.dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
-    }
-}
-__device__ __forceinline__ int load_tile_node(const lpk_people &P, int64_t row) {
-    return P.tile_node ? __ldg(&P.tile_node[row >> 2]) : -1;
-}
-__device__ __forceinline__ uint32_t load_state_row(const lpk_people &P, int64_t row, int lane, int64_t n) {
-    const int64_t b = (row * 32 + lane) * 4;
-    const int v = quad_valid(b, n);
-    return v ? load_b4(P.disease_state, b, v) : 0xFFFFFFFFu;
-}
+        if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
+        if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
+        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, nwA, hA, cA, nwB, hB, cB), lane);
+    };
 
-template <bool kDeaths, bool kRI>
-__device__ __forceinline__ void general_rows(const PassParams &pp, WarpQueue &Q, int64_t lo, int64_t hi, int64_t n, int64_t count_prev,
-                                             TauCache &tc_load, TauCache &tc_use, int lane, int warp) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    const float *tau_prev = pending ? A.q_prev : nullptr;
-    const int tick = A.tick;
-    int64_t row = lo + warp;
-    RowData cur, nxt;
-    uint32_t w2 = 0xFFFFFFFFu;  // state word and tile node two rows ahead
-    int tn2 = -1;
-    cur.w = 0xFFFFFFFFu;
-    if (row < hi) {
-        issue_row_loads<kDeaths>(P, tau_prev, row, lane, n, load_state_row(P, row, lane, n), load_tile_node(P, row), tc_load, cur);
-        if (row + LPK_WARPS < hi) { w2 = load_state_row(P, row + LPK_WARPS, lane, n); tn2 = load_tile_node(P, row + LPK_WARPS); }
-    }
+    // one copy of the loop body (runtime slot index): the unrolled variant was 100 KB of code and stalled on instruction
+    // fetch (profiles/r1_fused_v10_*: no_instruction 8.4 per issue)
+    if (S > 0) {
 #pragma unroll 1
-    for (; row < hi; row += LPK_WARPS) {
-        // ---- keep the pipeline full
-        const int64_t r1 = row + LPK_WARPS, r2 = row + 2 * LPK_WARPS;
-        nxt.w = 0xFFFFFFFFu;
-        if (r1 < hi) issue_row_loads<kDeaths>(P, tau_prev, r1, lane, n, w2, tn2, tc_load, nxt);
-        w2 = (r2 < hi) ? load_state_row(P, r2, lane, n) : 0xFFFFFFFFu;
-        tn2 = (r2 < hi) ? load_tile_node(P, r2) : -1;
-
-        // ---- row `row`
-        const uint32_t w = cur.w;
-        const int64_t b = (row * 32 + lane) * 4;
-        uint32_t cand = 0u, hits = 0u, nw = w;  // cand: agents that go to the active queue
-        int nd = cur.tn;
-        if ((w & 0x80808080u) != 0x80808080u) {  // somebody alive in the quad
-            const int valid = quad_valid(b, n);
-            bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
-            if (nd < 0) {
-                nd = (int)(int16_t)(cur.nd.x & 0xFFFFu);
-                fast = fast && cur.nd.x == cur.nd.y && (cur.nd.x >> 16) == (cur.nd.x & 0xFFFFu) && nd >= 0;
-            }
-            if (!fast) {
-                nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
-            } else {
-                if (pending && mask_S(w)) {  // exposure trial of tick t-1
-                    if (nd != tc_use.node) { tc_use.node = nd; tc_use.tau = __ldg(&A.q_prev[nd]); }
-                    const float tau = tc_use.tau;
-                    if (tau > 0.f) {
-                        const uint64_t id0 = (uint64_t)b + A.id_base;
-                        const uint64_t c = expose_ctr(id0);
-                        const int par = (int)((id0 >> 7) & 1u);
-                        uint32_t x[4];
-                        philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
-                                      (uint32_t)(A.seed >> 32), x);
-                        const uint32_t xa = par ? x[2] : x[0], xb = par ? x[3] : x[1];
-                        if (pretest_quad(xa, xb, cur.rk, tau * 65536.0f)) {
-                            hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, xa, xb, w, cur.rk, tau);
-                            nw |= hits;  // S (0) -> E (1)
-                        }
-                    }
-                }
-                // ---- tick t
-                if (kDeaths) {
-                    const uint32_t dm = death_mask(cur.dd, tick, nw);
-                    if (dm) { const uint2 r = death_quad(pp, b, nd, nw, hits, dm); nw = r.x; hits = r.y; }
-                }
-                cand = mask_EI(nw);
-                if (kRI) {
-                    // RI may set ipv_protected, which the disease-state step of the SAME tick must not see yet
-                    // (reference order: DiseaseState_ABM before RI_ABM), so nothing is deferred on RI ticks.
+        for (int k = 0; k < NST; ++k) produce(k, k);
+        uint32_t parity = 0u;
+        int slot = 0;
 #pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {
-                        if (!((cand >> (8 * k)) & 1u)) continue;
-                        if ((hits >> (8 * k)) & 1u) expose_agent(pp, b + k, nd);
-                        int8_t sk = byte_of(nw, k);
-                        if (pending) census_ei(pp, b + k, nd, sk);
-                        sk = ds_agent_ol(pp, b + k, sk, nd);
-                        nw = set_byte(nw, k, sk);
-                        if (sk == 2) tally_infectious(pp, b + k, nd);
-                    }
-                    cand = 0u;
-                    nw = ri_quad(pp, b, 4, nw);
-                }
-            }
-            if (nw != w) store_b4(P.disease_state, b, valid, nw);
-        }
-        q_commit(pp, Q, q_push(Q, (uint32_t)b, nd, nw, hits, cand), lane);
-        cur = nxt;
-    }
-}
-
-template <bool kDeaths, bool kRI>
-__global__ void __launch_bounds__(LPK_BLOCK, LPK_PASS_BLOCKS_PER_SM) k_tick_pass(const __grid_constant__ PassParams pp) {
-    __shared__ uint2 queue[LPK_WARPS][QCAP];
-    __shared__ uint32_t q_tail[LPK_WARPS];
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t count_prev = A.counts[0], n = A.counts[1];
-    const int64_t rows = (n + 127) >> 7;
-    const int64_t n_chunks = (rows + LPK_CHUNK_ROWS - 1) / LPK_CHUNK_ROWS;
-    WarpQueue Q;
-    Q.q = queue[warp];
-    Q.tail = &q_tail[warp];
-    Q.head = 0u;
-    Q.count = 0;
-    if (lane == 0) q_tail[warp] = 0u;
-    __syncwarp();
-    TauCache tc_load = {-2, 0.f}, tc_use = {-2, 0.f};
-
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int64_t base = chunk * LPK_CHUNK_AGENTS;
-        // one node, every slot occupied since before tick t-1's transmission?  (64 tiles of 512 agents)
-        int cn = -1;
-        if (!kRI && P.tile_node && base + LPK_CHUNK_AGENTS <= count_prev) {
-            const int t0 = __ldg(&P.tile_node[chunk * 64 + lane]), t1 = __ldg(&P.tile_node[chunk * 64 + 32 + lane]);
-            const int first = __shfl_sync(LPK_FULL, t0, 0);
-            if (__all_sync(LPK_FULL, t0 == first && t1 == first)) cn = first;
-        }
-        if (cn >= 0) {
-            fast_chunk<kDeaths>(pp, Q, base, cn, lane, warp);
-        } else {
-            const int64_t lo = chunk * LPK_CHUNK_ROWS;
-            const int64_t hi = (lo + LPK_CHUNK_ROWS < rows) ? lo + LPK_CHUNK_ROWS : rows;
-            general_rows<kDeaths, kRI>(pp, Q, lo, hi, n, count_prev, tc_load, tc_use, lane, warp);
+        for (int s = 0; s < S; ++s) {
+            consume(s, slot, parity);
+            if (++slot == NST) { slot = 0; parity ^= 1u; }
         }
     }
     __syncwarp();
     if (lane < Q.count) active_agent(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+}
+
+template <bool kDeaths, bool kRI, int kOcc>
+static int launch_pass(const PassParams &pp, cudaStream_t st) {
+    typedef PassSmem<kDeaths, kRI> L;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
+                 "tick_pass smem");
+        configured = true;
+    }
+    const int grid = lpk_agent_grid(pp.P.capacity, kOcc);
+    k_tick_pass<kDeaths, kRI, kOcc><<<grid, LPK_BLOCK, L::kBytes, st>>>(pp);
+    return LPK_OK;
+}
+// blocks per SM of the plain-day pass: 2 (no register cap, 100 KB of L1 left beside the rings) or 3 (80 registers: measured
+// 2x slower, diag_v10b); LPK_PASS_OCC overrides for experiments
+static int pass_occupancy() {
+    static int occ = 0;
+    if (!occ) {
+        const char *e = getenv("LPK_PASS_OCC");
+        occ = (e && e[0] == '3') ? 3 : 2;
+    }
+    return occ;
 }
 
 extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream) {
@@ -578,12 +711,16 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     PassParams pp;
     pp.P = P;
     pp.A = A;
-    const int grid = lpk_agent_grid(P.capacity, LPK_PASS_BLOCKS_PER_SM);
+    REQUIRE(ALIGNED(P.disease_state, 16) && (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
+            "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
-    if (deaths && ri) k_tick_pass<true, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
-    else if (deaths) k_tick_pass<true, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
-    else if (ri) k_tick_pass<false, true><<<grid, LPK_BLOCK, 0, st>>>(pp);
-    else k_tick_pass<false, false><<<grid, LPK_BLOCK, 0, st>>>(pp);
+    int rc;
+    if (deaths && ri) rc = launch_pass<true, true, 2>(pp, st);
+    else if (deaths) rc = launch_pass<true, false, 2>(pp, st);
+    else if (ri) rc = launch_pass<false, true, 2>(pp, st);
+    else if (pass_occupancy() == 2) rc = launch_pass<false, false, 2>(pp, st);
+    else rc = launch_pass<false, false, 3>(pp, st);
+    if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
     return LPK_OK;
 }
