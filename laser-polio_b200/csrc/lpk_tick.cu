@@ -25,11 +25,12 @@
 struct PassParams {
     lpk_people P;
     lpk_tick_args A;
+    uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
 };
 
-#define QCAP 512             // ring entries per warp: 31 left over + the 256 agents of one iteration fit
-#define LPK_CHUNK_PAIRS 192  // pairs of 128-agent rows per chunk (48 K agents), dealt round-robin to the blocks
-#define LPK_CHUNK_ITERS (LPK_CHUNK_PAIRS / LPK_WARPS)  // a warp's pairs per chunk: a multiple of the pipeline depth 4
+#define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one iteration fit
+#define LPK_UNIT_LOG 3   // a work unit = 8 consecutive pairs of 128-agent rows (2048 agents), claimed by one warp at a time
+#define LPK_UNIT_PAIRS (1 << LPK_UNIT_LOG)
 
 // ------------------------------------------------------------------ rare paths (out of line, direct atomics)
 __device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
@@ -50,8 +51,9 @@ __device__ __noinline__ void leave_S(const PassParams &pp, int64_t i, int nd) {
     atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
 }
 
-// bookkeeping of an exposure hit of tick t-1: categorical strain pick (model.py:1127-1141), rows t-1; returns the strain
-__device__ __forceinline__ int8_t expose_bookkeeping(const PassParams &pp, int64_t i, int nd) {
+// bookkeeping of an exposure hit of tick t-1 (the agent's risk already in a register): categorical strain pick
+// (model.py:1127-1141), rows t-1, susceptible-side tallies; returns the strain
+__device__ __noinline__ int8_t expose_bookkeeping_rk(const PassParams &pp, int64_t i, int nd, float rk) {
     const lpk_tick_args &A = pp.A;
     uint32_t y[4];
     philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
@@ -64,10 +66,14 @@ __device__ __forceinline__ int8_t expose_bookkeeping(const PassParams &pp, int64
     atomicAdd(&A.new_exposed_prev[nd], 1);
     atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
     atomicAdd(&A.tx_hits[nd], 1);
-    leave_S(pp, i, nd);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)(-1ll));
+    red_add(&A.exposure_fx[nd], -__float2ll_rn(rk * 1073741824.0f));
+    atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
     return (int8_t)assigned;
 }
-__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) { expose_bookkeeping(pp, i, nd); }
+__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
+    expose_bookkeeping_rk(pp, i, nd, pp.P.acq_risk_multiplier[i]);
+}
 
 // census of one E or I agent (rows t-1)
 __device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, int8_t s) {
@@ -214,58 +220,159 @@ __device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, u
 // owns the agent's state byte from then on (the owning lane already stored the quad's word; both stores come from the
 // same warp, ordered by the warp-wide reduction in q_commit).
 // entry = {agent index (tables hold < 2^32 slots), node | state << 16 | hit << 20}
+struct ActiveRegs {
+    uint2 e;
+    int8_t st, et, it, pt, pq, ipvv;
+    float inf, rk;
+};
+struct WarpAcc;
 struct WarpQueue {
     uint2 *q;
     uint32_t *tail;  // shared, monotonic
     uint32_t head;   // warp-uniform
     int count;       // warp-uniform
+    bool loaded;     // warp-uniform: `pend` holds a batch whose loads are in flight
+    ActiveRegs pend;
+    WarpAcc *acc;
 };
 
-// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent.
-// Every column the agent can need is loaded up front, in one round trip, and the state machine runs on registers
-// (profiles/r1_fused_v6_postsia_*: a third of the stall samples sat on the serial etimer -> itimer -> strain -> ptimer
-// -> infectivity chain of dependent scattered loads).
-__device__ __noinline__ void active_agent(const PassParams &pp, uint2 e) {
+// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent, in two phases a ring
+// batch apart: active_load issues every load the agent can need (one round trip, nothing dependent), active_process runs
+// the state machine on those registers when the NEXT batch is loaded, so the scattered-load latency is spent streaming
+// (profiles/r1_fused_v10_postsia_*: 35 % of the stall samples sat in the handler waiting for its own loads).  Between the
+// two phases nobody else touches the agent: it is pushed once per pass, and the death / RI paths never push what they
+// handle themselves.
+__device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
+    const lpk_people &P = pp.P;
+    const int64_t i = (int64_t)e.x;
+    const bool hit = (e.y >> 20) & 1u;
+    ActiveRegs r;
+    r.e = e;
+    r.st = hit ? (int8_t)0 : P.strain[i];
+    r.et = (((e.y >> 16) & 0xFu) == 1u) ? P.exposure_timer[i] : (int8_t)1;
+    r.it = P.infection_timer[i];
+    r.pt = P.paralysis_timer[i];
+    r.pq = P.potentially_paralyzed[i];
+    r.ipvv = P.ipv_protected[i];
+    r.inf = P.daily_infectivity[i];
+    r.rk = hit ? P.acq_risk_multiplier[i] : 0.f;
+    return r;
+}
+// Per-warp accumulators of the handler's node-level counts (shared memory, read and written by lane 0 only).  The
+// agents of a warp come from one node for hundreds of batches and all SMs work in the same few nodes at a time, so
+// per-agent atomics on E_by_strain / I_by_strain / beta_fx land on a handful of addresses from every SM at once and
+// serialise in L2 (diag_v11: a tighter work window made the post-SIA pass 2x slower).  Counts are therefore reduced
+// across the batch with ballots / REDUX, added here, and flushed with one atomic per counter when the node changes.
+struct WarpAcc {
+    int node;
+    int E[LPK_MAX_STRAINS], I[LPK_MAX_STRAINS], H[LPK_MAX_STRAINS];  // census of t-1 (E, I) and exposure hits of t-1 per strain
+    int R;                                                            // recoveries of tick t
+    long long beta[LPK_MAX_STRAINS];                                  // infectivity tally of tick t (fixed point)
+    long long expo;                                                   // risk (fixed point) of the agents that left S
+};
+__device__ __forceinline__ void acc_clear(WarpAcc *a) {
+#pragma unroll
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) { a->E[s] = 0; a->I[s] = 0; a->H[s] = 0; a->beta[s] = 0; }
+    a->R = 0;
+    a->expo = 0;
+}
+// lane 0 only
+__device__ __noinline__ void acc_flush(const PassParams &pp, WarpAcc *a) {
+    const lpk_tick_args &A = pp.A;
+    const int nd = a->node, ns = A.n_strains;
+    if (nd < 0) return;
+    int hits = 0;
+    for (int s = 0; s < ns; ++s) {
+        const int64_t c = (int64_t)nd * ns + s;
+        red_add(&A.E_by_strain_prev[c], a->E[s]);
+        red_add(&A.I_by_strain_prev[c], a->I[s]);
+        red_add(&A.new_exposed_by_strain_prev[c], a->H[s]);
+        red_add(&A.beta_fx[c], a->beta[s]);
+        hits += a->H[s];
+    }
+    if (hits) {
+        atomicAdd(&A.new_exposed_prev[nd], hits);
+        atomicAdd(&A.tx_hits[nd], hits);
+        red_add(&A.sus[nd], -(long long)hits);
+        red_add(&A.exposure_fx[nd], -a->expo);
+    }
+    red_add(&A.R_cur[nd], a->R);
+    acc_clear(a);
+}
+// warp-wide sum of a 64-bit fixed-point value (|v| < 2^55) as two 32-bit REDUX
+__device__ __forceinline__ long long warp_sum_fx(long long v) {
+    const int lo = (int)(v & 0xFFFFFF), hi = (int)(v >> 24);
+    return ((long long)__reduce_add_sync(LPK_FULL, hi) << 24) + (long long)__reduce_add_sync(LPK_FULL, lo);
+}
+
+// warp-collective: every lane calls it; `valid` lanes carry an agent
+__device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, bool valid, WarpAcc *acc, int lane) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
-    const int64_t i = (int64_t)e.x;
-    const int nd = (int)(int16_t)(e.y & 0xFFFFu);
-    const int8_t s0 = (int8_t)((e.y >> 16) & 0xFu);
-    const bool hit = (e.y >> 20) & 1u;
+    const int64_t i = (int64_t)r.e.x;
+    const int nd = (int)(int16_t)(r.e.y & 0xFFFFu);
+    const int8_t s0 = (int8_t)((r.e.y >> 16) & 0xFu);
+    const bool hit = valid && ((r.e.y >> 20) & 1u);
     const int ns = A.n_strains;
-    int8_t st = hit ? (int8_t)0 : P.strain[i];
-    int8_t et = (s0 == 1) ? P.exposure_timer[i] : (int8_t)1;
-    int8_t it = P.infection_timer[i], pt = P.paralysis_timer[i], pq = P.potentially_paralyzed[i];
-    const int8_t ipvv = P.ipv_protected[i];
-    const float inf = P.daily_infectivity[i];
-    if (hit) st = expose_bookkeeping(pp, i, nd);  // exposure hit of tick t-1
-    if (A.flags & LPK_F_PENDING) {
-        const int64_t c = (int64_t)nd * ns + st;
-        atomicAdd(s0 == 1 ? &A.E_by_strain_prev[c] : &A.I_by_strain_prev[c], 1);
-    }
-    int8_t s = s0;
-    if (s == 1) {  // model.py:419-422
-        if (et <= 0) s = 2;
-        P.exposure_timer[i] = (int8_t)(et - 1);
-    }
-    if (s == 2) {
-        const int8_t pq0 = pq;
-        int8_t par = 0;
-        int flags;
-        s = ds_infected(i, st, ipvv, it, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
-        P.infection_timer[i] = it;
-        if (st == 0) {
-            P.paralysis_timer[i] = pt;
-            if (pq != pq0) P.potentially_paralyzed[i] = pq;
-            if (flags) {
-                atomicAdd(&A.new_potential[nd], 1);
-                if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
+    const bool pending = (A.flags & LPK_F_PENDING) != 0;
+    int8_t st = r.st, s = s0;
+    long long fx = 0, efx = 0;
+    if (valid) {
+        if (hit) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
+            uint32_t y[4];
+            philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
+            const double u = u53(y[0], y[1]);
+            st = 0;
+            for (int k = 0; k < ns; ++k)
+                if (u < A.cdf_prev[(int64_t)nd * ns + k]) { st = (int8_t)k; break; }
+            P.strain[i] = st;
+            efx = __float2ll_rn(r.rk * 1073741824.0f);
+            atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
+        }
+        int8_t it = r.it, pt = r.pt, pq = r.pq;
+        if (s == 1) {  // model.py:419-422
+            if (r.et <= 0) s = 2;
+            P.exposure_timer[i] = (int8_t)(r.et - 1);
+        }
+        if (s == 2) {
+            const int8_t pq0 = pq;
+            int8_t par = 0;
+            int flags;
+            s = ds_infected(i, st, r.ipvv, it, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
+            P.infection_timer[i] = it;
+            if (st == 0) {
+                P.paralysis_timer[i] = pt;
+                if (pq != pq0) P.potentially_paralyzed[i] = pq;
+                if (flags) {
+                    atomicAdd(&A.new_potential[nd], 1);
+                    if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
+                }
             }
         }
+        if (s != s0) P.disease_state[i] = s;
+        if (s == 2) fx = to_fx((double)r.inf * A.strain_r0_scalars[st]);
     }
-    if (s != s0) P.disease_state[i] = s;
-    if (s == 2) red_add(&A.beta_fx[(int64_t)nd * ns + st], to_fx((double)inf * A.strain_r0_scalars[st]));
-    if (s == 3) atomicAdd(&A.R_cur[nd], 1);
+    // node-level counts, one group of same-node lanes at a time (one group except at a node boundary)
+    uint32_t todo = __ballot_sync(LPK_FULL, valid);
+    while (todo) {
+        const int nd0 = __shfl_sync(LPK_FULL, nd, __ffs(todo) - 1);
+        const bool mine = valid && nd == nd0;
+        if (lane == 0 && acc->node != nd0) { acc_flush(pp, acc); acc->node = nd0; }
+        for (int k = 0; k < ns; ++k) {
+            const bool mk = mine && st == k;
+            const int cE = __popc(__ballot_sync(LPK_FULL, mk && pending && s0 == 1));
+            const int cI = __popc(__ballot_sync(LPK_FULL, mk && pending && s0 == 2));
+            const int cH = __popc(__ballot_sync(LPK_FULL, mk && hit));
+            const uint32_t tallied = __ballot_sync(LPK_FULL, mk && s == 2);
+            const long long b = tallied ? warp_sum_fx(mk && s == 2 ? fx : 0ll) : 0ll;
+            if (lane == 0) { acc->E[k] += cE; acc->I[k] += cI; acc->H[k] += cH; acc->beta[k] += b; }
+        }
+        const int cR = __popc(__ballot_sync(LPK_FULL, mine && s == 3));
+        const uint32_t anyhit = __ballot_sync(LPK_FULL, mine && hit);
+        const long long e = anyhit ? warp_sum_fx(mine && hit ? efx : 0ll) : 0ll;
+        if (lane == 0) { acc->R += cR; acc->expo += e; }
+        todo &= ~__ballot_sync(LPK_FULL, mine);
+    }
 }
 
 // append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; returns how many
@@ -302,7 +409,10 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
     Q.count += __reduce_add_sync(LPK_FULL, mine);
     while (Q.count >= 32) {
         __syncwarp();
-        active_agent(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        const ActiveRegs nxt = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        if (Q.loaded) active_process(pp, Q.pend, true, Q.acc, lane);
+        Q.pend = nxt;
+        Q.loaded = true;
         Q.head += 32;
         Q.count -= 32;
     }
@@ -452,9 +562,8 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
 
 // ------------------------------------------------------------------ the pass
 // Unit of work: a PAIR of 128-agent rows (256 consecutive agents); a lane owns its quad in the even row (A) and in the
-// odd row (B).  Pairs are grouped in chunks of LPK_CHUNK_PAIRS dealt round-robin to the blocks (a chunk is short enough
-// that regions dense in E / I agents -- an SIA wave hits whole nodes -- spread over all SMs); inside a chunk a warp takes
-// every 8th pair.  A warp's pairs form one sequence s = 0, 1, ... served by the warp's PRIVATE ring of kStages
+// odd row (B).  Warps claim units of LPK_UNIT_PAIRS consecutive pairs from a global counter (see the kernel body).  A
+// warp's pairs form one sequence s = 0, 1, ... served by the warp's PRIVATE ring of kStages
 // shared-memory slots: one elected lane asks the TMA engine for the pair's columns (cp.async.bulk: 256 B of state, 1 KB
 // of risk, + date_of_death / chronically_missed / ri_timer on vital-dynamics / RI ticks) kStages iterations ahead, the
 // bytes land on the slot's mbarrier, and the warp reads its quads from shared memory.  The copies cost no registers and
@@ -498,7 +607,8 @@ struct PassSmem {
     static constexpr int kOffBars = kOffSlots + LPK_WARPS * kStages * kStageBytes;
     static constexpr int kOffMeta = kOffBars + LPK_WARPS * kStages * 8;
     static constexpr int kOffTail = kOffMeta + LPK_WARPS * kStages * 8;
-    static constexpr int kBytes = kOffTail + LPK_WARPS * 4 + 32;
+    static constexpr int kOffAcc = (kOffTail + LPK_WARPS * 4 + 15) & ~15;
+    static constexpr int kBytes = kOffAcc + LPK_WARPS * (int)sizeof(WarpAcc) + 32;
 };
 
 template <bool kDeaths, bool kRI, int kOcc>
@@ -513,11 +623,9 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick;
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
-    const int64_t total_pairs = (n + 255) >> 8;
-    const int64_t full_pairs = P.tile_node ? (count_prev >> 8) : 0;  // pairs whose 256 agents all existed at tick t-1
-    const int64_t n_chunks = (total_pairs + LPK_CHUNK_PAIRS - 1) / LPK_CHUNK_PAIRS;
-    const int64_t my_chunks = (int64_t)blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int S = (int)(my_chunks * LPK_CHUNK_ITERS);
+    const uint32_t total_pairs = (uint32_t)((n + 255) >> 8);
+    const uint32_t full_pairs = P.tile_node ? (uint32_t)(count_prev >> 8) : 0u;  // pairs whose 256 agents all existed at tick t-1
+    const uint32_t n_units = (total_pairs + LPK_UNIT_PAIRS - 1) >> LPK_UNIT_LOG;
 
     unsigned char *slots = smem + L::kOffSlots + warp * NST * L::kStageBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBars) + warp * NST;
@@ -527,21 +635,42 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     Q.tail = reinterpret_cast<uint32_t *>(smem + L::kOffTail) + warp;
     Q.head = 0u;
     Q.count = 0;
+    Q.loaded = false;
+    Q.acc = reinterpret_cast<WarpAcc *>(smem + L::kOffAcc) + warp;
     if (lane == 0) {
+        Q.acc->node = -1;
+        acc_clear(Q.acc);
         *Q.tail = 0u;
         for (int k = 0; k < NST; ++k) mbar_init(&bars[k], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    auto pair_of = [&](int s) -> int64_t {
-        const int c = s / LPK_CHUNK_ITERS, it = s - c * LPK_CHUNK_ITERS;
-        return ((int64_t)blockIdx.x + (int64_t)c * gridDim.x) * LPK_CHUNK_PAIRS + it * LPK_WARPS + warp;
+    // Work distribution: units of LPK_UNIT_PAIRS consecutive pairs are claimed warp by warp from a global counter, so a
+    // warp that meets regions dense in E / I agents (an SIA wave hits whole nodes) simply claims fewer units
+    // (profiles/r1_fused_v10_*: with static round-robin chunks the average SM was busy 58-66 % of the kernel's duration).
+    // A warp's pairs form one sequence s = 0, 1, ...; the unit of sequence position s sits in register ua / ub (parity of
+    // s >> LPK_UNIT_LOG); the producer runs at most kStages + 1 <= LPK_UNIT_PAIRS positions ahead of the consumer, so two
+    // registers suffice.  The claim for the unit after next is issued one unit early (its latency is never waited for).
+    const uint32_t kNoUnit = 0xFFFFFFFFu;
+    uint32_t ua = kNoUnit, ub = kNoUnit;
+    uint32_t claim = 0u;  // lane 0: the prefetched claim
+    if (lane == 0) claim = atomicAdd(pp.unit_ctr, 1u);
+    auto pair_of = [&](int s) -> uint32_t {
+        const uint32_t u = ((s >> LPK_UNIT_LOG) & 1) ? ub : ua;
+        return u == kNoUnit ? kNoUnit : (u << LPK_UNIT_LOG) + (uint32_t)(s & (LPK_UNIT_PAIRS - 1));
     };
-    // node of pair s: >= 0 all 256 agents in that node and present at tick t-1; -1 general handling; -2 nothing to do
+    // node of the pair at position s (called once per s, in order): >= 0 all 256 agents in that node and present at tick
+    // t-1; -1 general handling; -2 no more work for this warp
     auto node_of = [&](int s) -> int {
-        const int64_t gp = pair_of(s);
-        if (s >= S || gp >= total_pairs) return -2;
+        if ((s & (LPK_UNIT_PAIRS - 1)) == 0) {
+            uint32_t u = __shfl_sync(LPK_FULL, claim, 0);
+            if (u >= n_units) u = kNoUnit;
+            else if (lane == 0) claim = atomicAdd(pp.unit_ctr, 1u);
+            if ((s >> LPK_UNIT_LOG) & 1) ub = u; else ua = u;
+        }
+        const uint32_t gp = pair_of(s);
+        if (gp >= total_pairs) return -2;  // kNoUnit included
         return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
     };
     int tc_node = -2;  // one-entry cache of tau per node (a warp stays in one node for hundreds of pairs)
@@ -560,7 +689,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
             meta[slot] = make_int2(tn, __float_as_int(tau));
             uint64_t *bar = &bars[slot];
             if (tn >= 0) {
-                const int64_t a0 = pair_of(s) * 256;
+                const int64_t a0 = (int64_t)pair_of(s) * 256;
                 unsigned char *dst = slots + slot * L::kStageBytes;
                 const bool risk = tau > 0.f;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
@@ -579,7 +708,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     };
 
     // process pair s from slot, then re-arm the slot with pair s + NST
-    auto consume = [&](int s, int slot, uint32_t parity) {
+    auto consume = [&](int s, int slot, uint32_t parity) -> bool {
         mbar_wait(&bars[slot], parity);
         const int2 mt = meta[slot];
         const int tn = mt.x;
@@ -609,11 +738,11 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         }
         __syncwarp();
         produce(s + NST, slot);
-        if (tn == -2) return;
-        const int64_t gp = pair_of(s);
+        if (tn == -2) return false;
+        const int64_t gp = (int64_t)pair_of(s);
         if (tn < 0) {
             q_commit(pp, Q, general_pair<kDeaths, kRI>(pp, Q.q, Q.tail, gp, n, count_prev, lane), lane);
-            return;
+            return true;
         }
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
@@ -645,23 +774,32 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
         if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
         q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, nwA, hA, cA, nwB, hB, cB), lane);
+        return true;
     };
 
     // one copy of the loop body (runtime slot index): the unrolled variant was 100 KB of code and stalled on instruction
-    // fetch (profiles/r1_fused_v10_*: no_instruction 8.4 per issue)
-    if (S > 0) {
+    // fetch (profiles/r1_fused_v10_*: no_instruction 8.4 per issue).  Once a position has no work none after it has, and
+    // nothing was requested from the TMA engine for those, so the warp can leave at the first one.
+    {
 #pragma unroll 1
         for (int k = 0; k < NST; ++k) produce(k, k);
         uint32_t parity = 0u;
         int slot = 0;
 #pragma unroll 1
-        for (int s = 0; s < S; ++s) {
-            consume(s, slot, parity);
+        for (int s = 0;; ++s) {
+            if (!consume(s, slot, parity)) break;
             if (++slot == NST) { slot = 0; parity ^= 1u; }
         }
     }
     __syncwarp();
-    if (lane < Q.count) active_agent(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+    if (Q.loaded) active_process(pp, Q.pend, true, Q.acc, lane);
+    {
+        const bool valid = lane < Q.count;
+        ActiveRegs last = {};
+        if (valid) last = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        active_process(pp, last, valid, Q.acc, lane);
+    }
+    if (lane == 0) acc_flush(pp, Q.acc);
 }
 
 template <bool kDeaths, bool kRI, int kOcc>
@@ -674,8 +812,17 @@ static int launch_pass(const PassParams &pp, cudaStream_t st) {
         configured = true;
     }
     const int grid = lpk_agent_grid(pp.P.capacity, kOcc);
+    CUDA_TRY(cudaMemsetAsync(pp.unit_ctr, 0, sizeof(uint32_t), st), "tick_pass work counter");
     k_tick_pass<kDeaths, kRI, kOcc><<<grid, LPK_BLOCK, L::kBytes, st>>>(pp);
     return LPK_OK;
+}
+// one 4-byte work counter per device, allocated on first use (the pass is launched on one stream per device)
+static uint32_t *pass_unit_counter() {
+    static uint32_t *ctr[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ctr[dev] && cudaMalloc(&ctr[dev], 256) != cudaSuccess) ctr[dev] = nullptr;
+    return ctr[dev];
 }
 // blocks per SM of the plain-day pass: 2 (no register cap, 100 KB of L1 left beside the rings) or 3 (80 registers: measured
 // 2x slower, diag_v10b); LPK_PASS_OCC overrides for experiments
@@ -711,6 +858,8 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     PassParams pp;
     pp.P = P;
     pp.A = A;
+    pp.unit_ctr = pass_unit_counter();
+    REQUIRE(pp.unit_ctr, "tick_pass work counter allocation");
     REQUIRE(ALIGNED(P.disease_state, 16) && (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
             "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
