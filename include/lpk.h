@@ -173,10 +173,11 @@ int lpk_count_seirp(const int16_t *node_id, const int8_t *disease_state, const i
  * agent and in the reference's order,
  *     [pending from tick t-1]  tx_infect (model.py:1010-1149 replacement) and the census (model.py:869-929)
  *     [tick t]                 get_deaths (1767-1781), disease_state_step (344-454), fast_ri (1805-1855),
- *                              tx_step_prep tally (932-1007)
+ *                              fast_sia (1994-2060; one campaign event per tick), tx_step_prep tally (932-1007)
  * and lpk_tick_node then does the node-level work of tick t (model.py:1332-1351 + population / paralysis
- * bookkeeping), producing q / strain_cdf that the NEXT pass applies.  SIA days, seed_schedule days and the
- * final tick are run through the per-function entry points above (the host drains the pending exposure first).
+ * bookkeeping), producing q / strain_cdf that the NEXT pass applies.  seed_schedule days, days with several
+ * campaign events and the final tick are run through the per-function entry points above (the host drains the
+ * pending exposure first).
  *
  * All result rows are device pointers to row t (or t-1) of the [nt, nodes(, strains)] int32 arrays; counts are
  * accumulated with atomics, so "=" rows must be zero beforehand (they are: fresh result arrays) and "+=" rows
@@ -191,7 +192,7 @@ typedef struct lpk_people {
     const int16_t *node_id;
     int16_t *ri_timer;               /* NULL when RI_ABM is not a component */
     const float *acq_risk_multiplier, *daily_infectivity;
-    const int32_t *date_of_birth;    /* unused by the pass (SIA days are unfused); kept for symmetry, may be NULL */
+    const int32_t *date_of_birth;    /* read on SIA days only (LPK_F_SIA); may be NULL otherwise */
     const int32_t *date_of_death;    /* NULL when VitalDynamics_ABM is not a component */
     const int32_t *tile_node;        /* [ceil(capacity / 512)]: node id shared by every agent slot of the tile, or -1;
                                         NULL = always read node_id (lpk_build_tile_nodes fills it) */
@@ -202,6 +203,7 @@ typedef struct lpk_people {
 #define LPK_F_STAGES 2u  /* run tick t's own stages and tally */
 #define LPK_F_DEATHS 4u  /* tick t is a vital-dynamics tick: mark deaths (needs date_of_death) */
 #define LPK_F_RI 8u      /* tick t is a routine-immunisation tick (needs ri_timer) */
+#define LPK_F_SIA 16u    /* tick t carries ONE campaign event (needs date_of_birth and the sia_* fields) */
 
 typedef struct lpk_tick_args {
     uint32_t flags;
@@ -212,10 +214,10 @@ typedef struct lpk_tick_args {
     /* ---- pending exposure + census of tick t-1 (LPK_F_PENDING) */
     const float *q_prev;    /* [nodes]  tau of tick t-1, from lpk_tick_node / lpk_tx_node_math */
     const double *cdf_prev; /* [nodes, strains] */
-    int32_t *new_exposed_prev, *new_exposed_by_strain_prev; /* rows t-1, += */
-    int32_t *E_by_strain_prev, *I_by_strain_prev; /* rows t-1, accumulate (the S and R rows come from the carried counts
-                                                     below, see lpk_node_args) */
-    int32_t *tx_hits;       /* [nodes] scratch, += : exposures of tick t-1 found by this pass; consumed by lpk_tick_node */
+    int32_t *new_exposed_prev, *new_exposed_by_strain_prev; /* rows t-1, += (the S / E / I / R rows of t-1 are written by
+                                                               lpk_tick_node from the carried counts below) */
+    int32_t *tx_hits;           /* [nodes] scratch, += : exposures of tick t-1 found by this pass; consumed by lpk_tick_node */
+    int32_t *tx_hits_by_strain; /* [nodes, strains] scratch, += : the same per strain */
     /* ---- stages of tick t (LPK_F_STAGES) */
     float p_paralysis;
     int32_t *new_potential, *new_paralyzed; /* rows t, += */
@@ -225,9 +227,22 @@ typedef struct lpk_tick_args {
     int32_t ri_strain;
     const double *vx_prob_ri, *vx_prob_ipv;                          /* [nodes] */
     int32_t *ri_vaccinated, *ri_protected, *ipv_vaccinated;          /* rows t */
-    int32_t *new_exposed, *new_exposed_by_strain, *ri_new_exposed_by_strain; /* rows t */
+    int32_t *new_exposed, *new_exposed_by_strain, *ri_new_exposed_by_strain; /* rows t (new_exposed* shared with SIA) */
+    /* ---- one SIA campaign event on tick t (LPK_F_SIA), same meaning as lpk_fast_sia's arguments; an agent's draw is
+     *      Philox(seed; agent, tick, SIA | event_idx << 8) exactly as there.  Rows t, += (zero beforehand). */
+    const uint8_t *sia_targeted;   /* [nodes] nodes_to_vaccinate */
+    const float *vx_prob_sia;      /* [nodes] */
+    double sia_vx_eff;
+    int32_t sia_min_age, sia_max_age, sia_strain;
+    uint32_t sia_event_idx;
+    int32_t *sia_vaccinated, *sia_protected, *sia_new_exposed_by_strain;
     double strain_r0_scalars[LPK_MAX_STRAINS];
-    int64_t *beta_fx;      /* infectivity tally of tick t, += (lpk_tick_node zeroes the other parity buffer) */
+    int64_t *beta_fx;      /* [nodes, strains] infectivity tally, CARRIED: sum over the infectious agents of
+                              round(infectivity * strain_r0_scalar * 2^30); the pass adds an agent's term when it turns
+                              infectious and subtracts it when it recovers or dies (exact integers: equals
+                              lpk_tx_step_prep's from-scratch tally bit for bit) */
+    int32_t *E_cur, *I_cur; /* [nodes, strains] exposed / infectious agents per strain, carried the same way; initialised
+                               from lpk_count_seirp's E_by_strain / I_by_strain */
     int64_t *exposure_fx, *sus; /* susceptible-side tallies, CARRIED from tick to tick: the pass only corrects them when */
     int32_t *risk_hist;    /* an agent leaves the susceptible state (hit, RI exposure, death); lpk_vd_births adds cohorts.
                               Exact integers, so they equal lpk_tx_step_prep's from-scratch values; the caller initialises
@@ -261,9 +276,13 @@ typedef struct lpk_node_args {
     int32_t *cur_potp, *cur_p;
     const int32_t *new_potential, *new_paralyzed; /* rows t */
     int32_t *potp_row, *p_row;                     /* rows t */
-    /* totals of the census rows the pass just completed (t-1) */
-    const int32_t *E_by_strain_prev, *I_by_strain_prev;
-    int32_t *E_prev, *I_prev;
+    /* exposed / infectious census of t-1 from the carried counts (model.py:1477-1480 equivalent): with LPK_F_PENDING,
+     *   E_by_strain_prev = E_snap + tx_hits_by_strain, I_by_strain_prev = I_snap ("="), E_prev / I_prev their sums;
+     * then tx_hits_by_strain is zeroed and the snapshots are retaken for tick t: E_snap = E_cur, I_snap = I_cur. */
+    int32_t *E_by_strain_prev, *I_by_strain_prev; /* rows t-1 */
+    int32_t *E_prev, *I_prev;                     /* rows t-1 */
+    const int32_t *E_cur, *I_cur;
+    int32_t *E_snap, *I_snap, *tx_hits_by_strain;
     /* S and R census from the carried per-node counts (model.py:1476-1481 equivalent): with LPK_F_PENDING,
      *   S_prev[n] = S_snap[n] - tx_hits[n]   (susceptibles when tick t-1's stages ended, minus tick t-1's exposures)
      *   R_prev[n] += R_snap[n]               ("+=": on top of the pre-seeded non-agent immunes, model.py:1481)
@@ -272,7 +291,6 @@ typedef struct lpk_node_args {
     const int32_t *R_cur;
     int32_t *tx_hits, *S_snap, *R_snap;
     int32_t *S_prev, *R_prev; /* rows t-1 */
-    int64_t *next_beta_fx; /* infectivity tally of the other parity, zeroed for tick t+1 */
     int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
 } lpk_node_args;
 

@@ -116,14 +116,17 @@ class TickArgs(C.Structure):
         ("flags", C.c_uint32), ("tick", C.c_int32), ("n_nodes", C.c_int32), ("n_strains", C.c_int32),
         ("seed", C.c_uint64), ("id_base", C.c_uint64), ("counts", _VP),
         ("q_prev", _VP), ("cdf_prev", _VP), ("new_exposed_prev", _VP), ("new_exposed_by_strain_prev", _VP),
-        ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("tx_hits", _VP),
+        ("tx_hits", _VP), ("tx_hits_by_strain", _VP),
         ("p_paralysis", C.c_float), ("new_potential", _VP), ("new_paralyzed", _VP),
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("ri_step", C.c_int32), ("ri_strain", C.c_int32), ("vx_prob_ri", _VP), ("vx_prob_ipv", _VP),
         ("ri_vaccinated", _VP), ("ri_protected", _VP), ("ipv_vaccinated", _VP),
         ("new_exposed", _VP), ("new_exposed_by_strain", _VP), ("ri_new_exposed_by_strain", _VP),
+        ("sia_targeted", _VP), ("vx_prob_sia", _VP), ("sia_vx_eff", C.c_double),
+        ("sia_min_age", C.c_int32), ("sia_max_age", C.c_int32), ("sia_strain", C.c_int32), ("sia_event_idx", C.c_uint32),
+        ("sia_vaccinated", _VP), ("sia_protected", _VP), ("sia_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
-        ("beta_fx", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
+        ("beta_fx", _VP), ("E_cur", _VP), ("I_cur", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
     ]
 
 
@@ -139,8 +142,9 @@ class NodeArgs(C.Structure):
         ("deaths", _VP), ("dead_pp", _VP), ("dead_par", _VP),
         ("cur_potp", _VP), ("cur_p", _VP), ("new_potential", _VP), ("new_paralyzed", _VP), ("potp_row", _VP), ("p_row", _VP),
         ("E_by_strain_prev", _VP), ("I_by_strain_prev", _VP), ("E_prev", _VP), ("I_prev", _VP),
+        ("E_cur", _VP), ("I_cur", _VP), ("E_snap", _VP), ("I_snap", _VP), ("tx_hits_by_strain", _VP),
         ("sus", _VP), ("R_cur", _VP), ("tx_hits", _VP), ("S_snap", _VP), ("R_snap", _VP), ("S_prev", _VP), ("R_prev", _VP),
-        ("next_beta_fx", _VP), ("counts", _VP),
+        ("counts", _VP),
     ]
 
 
@@ -157,7 +161,7 @@ class BirthsArgs(C.Structure):
     ]
 
 
-F_PENDING, F_STAGES, F_DEATHS, F_RI = 1, 2, 4, 8
+F_PENDING, F_STAGES, F_DEATHS, F_RI, F_SIA = 1, 2, 4, 8, 16
 TILE_AGENTS = 512
 
 

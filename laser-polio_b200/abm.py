@@ -837,9 +837,25 @@ class SIA_ABM:
     def init_from_file(cls, sim):
         return cls(sim)
 
-    def step(self):
+    def event_args(self, dev, event):
+        """Device-side arguments of one campaign event (model.py:2106-2140): targeted-node mask (uploaded once per
+        event), per-node vaccination probability, efficacy, age window in days, vaccine strain."""
         import torch
 
+        if self._vx_cache is None or self._vx_cache[0] is not dev:
+            vx = np.ascontiguousarray(np.array(self.pars["vx_prob_sia"], dtype=np.float32))
+            self._vx_cache = (dev, torch.from_numpy(vx).to(dev.device), {})
+        _, vx_prob, masks = self._vx_cache
+        targeted = masks.get(id(event))
+        if targeted is None:
+            host = np.zeros(len(self.sim.nodes), np.uint8)
+            host[event["nodes"]] = 1
+            targeted = masks[id(event)] = torch.from_numpy(host).to(dev.device)
+        vtype = event["vaccinetype"]
+        lo, hi = event["age_range"]
+        return targeted, vx_prob, self.pars["vx_efficacy"][vtype], lo, hi, (2 if "nOPV" in vtype else 1)
+
+    def step(self):
         from . import kernels as K
 
         sim, pars = self.sim, self.pars
@@ -849,20 +865,11 @@ class SIA_ABM:
             return
         dev = _need_dev(sim)
         c, r = dev.cols, dev.res
-        if self._vx_cache is None or self._vx_cache[0] is not dev:
-            vx = np.ascontiguousarray(np.array(pars["vx_prob_sia"], dtype=np.float32))
-            self._vx_cache = (dev, torch.from_numpy(vx).to(dev.device))
-        vx_prob = self._vx_cache[1]
         vacc, prot = dev.scratch_i32[1], dev.scratch_i32[2]
         for k, event in enumerate(events):
-            targeted = np.zeros(len(sim.nodes), np.uint8)
-            targeted[event["nodes"]] = 1
-            vtype = event["vaccinetype"]
-            vx_eff = pars["vx_efficacy"][vtype]
-            lo, hi = event["age_range"]
-            vstrain = 2 if "nOPV" in vtype else 1
+            targeted, vx_prob, vx_eff, lo, hi, vstrain = self.event_args(dev, event)
             K.fast_sia(c["node_id"], c["disease_state"], c["strain"], c["date_of_birth"], t, vx_prob, float(vx_eff),
-                       self.people.count, torch.from_numpy(targeted).to(dev.device), int(lo), int(hi), vacc, prot,
+                       self.people.count, targeted, int(lo), int(hi), vacc, prot,
                        c["chronically_missed"], vstrain, event_idx=k, rng=sim.rng())
             r["sia_vaccinated"][t] = vacc  # overwritten per event, like the reference (model.py:2142-2145)
             r["sia_protected"][t] = prot

@@ -26,6 +26,7 @@ struct PassParams {
     lpk_people P;
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
+    uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches, 2 = skip the exposure trial
 };
 
 #define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one iteration fit
@@ -71,19 +72,38 @@ __device__ __noinline__ int8_t expose_bookkeeping_rk(const PassParams &pp, int64
     atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
     return (int8_t)assigned;
 }
-__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
-    expose_bookkeeping_rk(pp, i, nd, pp.P.acq_risk_multiplier[i]);
+// The exposed / infectious census by strain and the infectivity tally are CARRIED like the susceptible-side tallies:
+// E_cur / I_cur / beta_fx change only when an agent changes class, so the pass does nothing for an agent that merely
+// counts a timer down.  Slow-path form (direct atomics): the agent moves from class `from` to class `to` (-1 dead, 0 S,
+// 1 E, 2 I, 3 R); its strain must already be final.
+__device__ __noinline__ void carried_move(const PassParams &pp, int64_t i, int nd, int8_t from, int8_t to) {
+    const lpk_tick_args &A = pp.A;
+    if (from == to) return;
+    const bool ei = from == 1 || from == 2 || to == 1 || to == 2;
+    if (ei) {
+        const int st = pp.P.strain[i];
+        const int64_t c = (int64_t)nd * A.n_strains + st;
+        if (from == 1) atomicAdd(&A.E_cur[c], -1);
+        if (to == 1) atomicAdd(&A.E_cur[c], 1);
+        if (from == 2 || to == 2) {
+            const long long fx = to_fx((double)pp.P.daily_infectivity[i] * A.strain_r0_scalars[st]);
+            atomicAdd(&A.I_cur[c], to == 2 ? 1 : -1);
+            red_add(&A.beta_fx[c], to == 2 ? fx : -fx);
+        }
+    }
+    if (to == 3) atomicAdd(&A.R_cur[nd], 1);
+    if (from == 3) atomicAdd(&A.R_cur[nd], -1);
 }
-
-// census of one E or I agent (rows t-1)
-__device__ __noinline__ void census_ei(const PassParams &pp, int64_t i, int nd, int8_t s) {
-    const int64_t c = (int64_t)nd * pp.A.n_strains + pp.P.strain[i];
-    atomicAdd(s == 1 ? &pp.A.E_by_strain_prev[c] : &pp.A.I_by_strain_prev[c], 1);
+__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
+    const int st = expose_bookkeeping_rk(pp, i, nd, pp.P.acq_risk_multiplier[i]);
+    const int64_t c = (int64_t)nd * pp.A.n_strains + st;
+    atomicAdd(&pp.A.tx_hits_by_strain[c], 1);
+    atomicAdd(&pp.A.E_cur[c], 1);
 }
 
 __device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd, int8_t state_before) {
     if (state_before == 0) leave_S(pp, i, nd);
-    if (state_before == 3) atomicAdd(&pp.A.R_cur[nd], -1);
+    else carried_move(pp, i, nd, state_before, -1);
     atomicAdd(&pp.A.deaths[nd], 1);
     if (pp.P.potentially_paralyzed[i] == 1) atomicAdd(&pp.A.dead_pp[nd], 1);
     if (pp.P.paralyzed[i] == 1) atomicAdd(&pp.A.dead_par[nd], 1);
@@ -94,14 +114,8 @@ __device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8
     const int8_t s2 = ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
                                P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed,
                                stage_rng(pp));
-    if (s2 == 3) atomicAdd(&pp.A.R_cur[nd], 1);  // s was E or I: a recovery
+    carried_move(pp, i, nd, s, s2);
     return s2;
-}
-
-// infectivity tally of one infectious agent (tick t)
-__device__ __noinline__ void tally_infectious(const PassParams &pp, int64_t i, int nd) {
-    const int s = pp.P.strain[i];
-    red_add(&pp.A.beta_fx[(int64_t)nd * pp.A.n_strains + s], to_fx((double)pp.P.daily_infectivity[i] * pp.A.strain_r0_scalars[s]));
 }
 
 // routine immunisation for one quad (reference model.py:1825-1854); returns the new state word
@@ -136,6 +150,7 @@ __device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int
                 P.strain[i] = (int8_t)A.ri_strain;
                 leave_S(pp, i, nd);
                 const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
+                atomicAdd(&A.E_cur[c], 1);
                 atomicAdd(&A.ri_protected[nd], 1);
                 atomicAdd(&A.new_exposed[nd], 1);
                 atomicAdd(&A.new_exposed_by_strain[c], 1);
@@ -147,6 +162,44 @@ __device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int
     if (touched) {
         if (valid == 4) *reinterpret_cast<short4 *>(P.ri_timer + base) = make_short4((short)tm[0], (short)tm[1], (short)tm[2], (short)tm[3]);
         else for (int k = 0; k < valid; ++k) P.ri_timer[base + k] = (int16_t)tm[k];
+    }
+    return w;
+}
+
+// one campaign event for one quad (reference model.py:2030-2059), direct atomics; returns the new state word
+__device__ __forceinline__ uint32_t sia_age_mask(const int4 &d, int tick, int lo, uint32_t span) {
+    return ((uint32_t)(tick - d.x - lo) <= span ? 1u : 0u) | ((uint32_t)(tick - d.y - lo) <= span ? 0x100u : 0u) |
+           ((uint32_t)(tick - d.z - lo) <= span ? 0x10000u : 0u) | ((uint32_t)(tick - d.w - lo) <= span ? 0x1000000u : 0u);
+}
+__device__ __noinline__ uint32_t sia_quad(const PassParams &pp, int64_t base, int valid, uint32_t w) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const uint32_t span = (uint32_t)(A.sia_max_age - A.sia_min_age);
+#pragma unroll 1
+    for (int k = 0; k < valid; ++k) {
+        const int8_t s = byte_of(w, k);
+        const int64_t i = base + k;
+        if (s < 0 || P.chronically_missed[i] == 1) continue;
+        if ((uint32_t)(A.tick - P.date_of_birth[i] - A.sia_min_age) > span) continue;
+        const int nd = P.node_id[i];
+        if (A.sia_targeted[nd] == 0) continue;
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
+        const double r = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
+        if (r < pv) {
+            atomicAdd(&A.sia_vaccinated[nd], 1);
+            if (s == 0 && r < pv * A.sia_vx_eff) {
+                w = set_byte(w, k, 1);
+                P.strain[i] = (int8_t)A.sia_strain;
+                leave_S(pp, i, nd);
+                const int64_t c = (int64_t)nd * A.n_strains + A.sia_strain;
+                atomicAdd(&A.E_cur[c], 1);
+                atomicAdd(&A.sia_protected[nd], 1);
+                atomicAdd(&A.new_exposed[nd], 1);
+                atomicAdd(&A.new_exposed_by_strain[c], 1);
+                atomicAdd(&A.sia_new_exposed_by_strain[c], 1);
+            }
+        }
     }
     return w;
 }
@@ -172,16 +225,13 @@ __device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int 
                 const float tau = A.q_prev[nd];
                 if (tau > 0.f && expose_test(p_expose(__fmul_rn(P.acq_risk_multiplier[i], tau)), x[k])) { expose_agent(pp, i, nd); s = 1; }
             }
-            if (s == 1 || s == 2) census_ei(pp, i, nd, s);
         }
         if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd, s); s = -1; }
         if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s, nd);
         nw = set_byte(nw, k, s);
     }
     if (ri) nw = ri_quad(pp, b, valid, nw);
-#pragma unroll 1
-    for (int k = 0; k < valid; ++k)
-        if (byte_of(nw, k) == 2) tally_infectious(pp, b + k, P.node_id[b + k]);
+    if (A.flags & LPK_F_SIA) nw = sia_quad(pp, b, valid, nw);
     return nw;
 }
 
@@ -242,38 +292,43 @@ struct WarpQueue {
 // (profiles/r1_fused_v10_postsia_*: 35 % of the stall samples sat in the handler waiting for its own loads).  Between the
 // two phases nobody else touches the agent: it is pushed once per pass, and the death / RI paths never push what they
 // handle themselves.
+// entry.y = node | state << 16 | hit << 20 | RI-eligible << 21 | SIA-eligible << 22
 __device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
     const lpk_people &P = pp.P;
     const int64_t i = (int64_t)e.x;
-    const bool hit = (e.y >> 20) & 1u;
+    const uint32_t s0 = (e.y >> 16) & 0xFu;
+    const bool hit = (e.y >> 20) & 1u, ei = (s0 == 1u || s0 == 2u);
     ActiveRegs r;
     r.e = e;
-    r.st = hit ? (int8_t)0 : P.strain[i];
-    r.et = (((e.y >> 16) & 0xFu) == 1u) ? P.exposure_timer[i] : (int8_t)1;
-    r.it = P.infection_timer[i];
-    r.pt = P.paralysis_timer[i];
-    r.pq = P.potentially_paralyzed[i];
-    r.ipvv = P.ipv_protected[i];
-    r.inf = P.daily_infectivity[i];
-    r.rk = hit ? P.acq_risk_multiplier[i] : 0.f;
+    r.st = (ei && !hit) ? P.strain[i] : (int8_t)0;
+    r.et = (s0 == 1u) ? P.exposure_timer[i] : (int8_t)1;
+    r.it = ei ? P.infection_timer[i] : (int8_t)0;
+    r.pt = ei ? P.paralysis_timer[i] : (int8_t)0;
+    r.pq = ei ? P.potentially_paralyzed[i] : (int8_t)0;
+    r.ipvv = ei ? P.ipv_protected[i] : (int8_t)0;
+    r.inf = ei ? P.daily_infectivity[i] : 0.f;
+    r.rk = (hit || s0 == 0u) ? P.acq_risk_multiplier[i] : 0.f;  // a susceptible is here for RI / SIA and may leave S
     return r;
 }
-// Per-warp accumulators of the handler's node-level counts (shared memory, read and written by lane 0 only).  The
-// agents of a warp come from one node for hundreds of batches and all SMs work in the same few nodes at a time, so
-// per-agent atomics on E_by_strain / I_by_strain / beta_fx land on a handful of addresses from every SM at once and
-// serialise in L2 (diag_v11: a tighter work window made the post-SIA pass 2x slower).  Counts are therefore reduced
-// across the batch with ballots / REDUX, added here, and flushed with one atomic per counter when the node changes.
+// Per-warp accumulators of the handler's node-level counts (shared memory; lanes add with shared-memory atomics, lane 0
+// flushes).  The agents of a warp come from one node for many batches and all SMs work in few nodes at a time, so
+// per-agent global atomics land on a handful of addresses from every SM at once and serialise in L2 (diag_v11: a tighter
+// work window made the post-SIA pass 2x slower).  Counts are collected here and flushed with one global atomic per
+// counter when the warp's node changes.
 struct WarpAcc {
     int node;
-    int E[LPK_MAX_STRAINS], I[LPK_MAX_STRAINS], H[LPK_MAX_STRAINS];  // census of t-1 (E, I) and exposure hits of t-1 per strain
-    int R;                                                            // recoveries of tick t
-    long long beta[LPK_MAX_STRAINS];                                  // infectivity tally of tick t (fixed point)
-    long long expo;                                                   // risk (fixed point) of the agents that left S
+    int E[LPK_MAX_STRAINS], I[LPK_MAX_STRAINS];  // changes of the carried exposed / infectious counts
+    int H[LPK_MAX_STRAINS];                      // exposure hits of t-1 per strain (already included in E)
+    int R;                                       // recoveries of tick t
+    int riV, riP, ipvV, siaV, siaP;              // RI / SIA of tick t: vaccinated, protected (S -> E)
+    long long beta[LPK_MAX_STRAINS];             // change of the carried infectivity tally (fixed point)
+    long long expo;                              // risk (fixed point) of the agents that left S
 };
 __device__ __forceinline__ void acc_clear(WarpAcc *a) {
 #pragma unroll
     for (int s = 0; s < LPK_MAX_STRAINS; ++s) { a->E[s] = 0; a->I[s] = 0; a->H[s] = 0; a->beta[s] = 0; }
     a->R = 0;
+    a->riV = a->riP = a->ipvV = a->siaV = a->siaP = 0;
     a->expo = 0;
 }
 // lane 0 only
@@ -282,27 +337,82 @@ __device__ __noinline__ void acc_flush(const PassParams &pp, WarpAcc *a) {
     const int nd = a->node, ns = A.n_strains;
     if (nd < 0) return;
     int hits = 0;
+    if (a->riP) a->E[A.ri_strain] += a->riP;
+    if (a->siaP) a->E[A.sia_strain] += a->siaP;
     for (int s = 0; s < ns; ++s) {
         const int64_t c = (int64_t)nd * ns + s;
-        red_add(&A.E_by_strain_prev[c], a->E[s]);
-        red_add(&A.I_by_strain_prev[c], a->I[s]);
+        red_add(&A.E_cur[c], a->E[s]);
+        red_add(&A.I_cur[c], a->I[s]);
         red_add(&A.new_exposed_by_strain_prev[c], a->H[s]);
+        red_add(&A.tx_hits_by_strain[c], a->H[s]);
         red_add(&A.beta_fx[c], a->beta[s]);
         hits += a->H[s];
     }
     if (hits) {
         atomicAdd(&A.new_exposed_prev[nd], hits);
         atomicAdd(&A.tx_hits[nd], hits);
-        red_add(&A.sus[nd], -(long long)hits);
-        red_add(&A.exposure_fx[nd], -a->expo);
     }
+    if (a->riV) atomicAdd(&A.ri_vaccinated[nd], a->riV);
+    if (a->ipvV) atomicAdd(&A.ipv_vaccinated[nd], a->ipvV);
+    if (a->riP) {
+        const int64_t c = (int64_t)nd * ns + A.ri_strain;
+        atomicAdd(&A.ri_protected[nd], a->riP);
+        atomicAdd(&A.new_exposed[nd], a->riP);
+        atomicAdd(&A.new_exposed_by_strain[c], a->riP);
+        atomicAdd(&A.ri_new_exposed_by_strain[c], a->riP);
+    }
+    if (a->siaV) atomicAdd(&A.sia_vaccinated[nd], a->siaV);
+    if (a->siaP) {
+        const int64_t c = (int64_t)nd * ns + A.sia_strain;
+        atomicAdd(&A.sia_protected[nd], a->siaP);
+        atomicAdd(&A.new_exposed[nd], a->siaP);
+        atomicAdd(&A.new_exposed_by_strain[c], a->siaP);
+        atomicAdd(&A.sia_new_exposed_by_strain[c], a->siaP);
+    }
+    red_add(&A.sus[nd], -(long long)(hits + a->riP + a->siaP));
+    red_add(&A.exposure_fx[nd], -a->expo);
     red_add(&A.R_cur[nd], a->R);
     acc_clear(a);
 }
-// warp-wide sum of a 64-bit fixed-point value (|v| < 2^55) as two 32-bit REDUX
-__device__ __forceinline__ long long warp_sum_fx(long long v) {
-    const int lo = (int)(v & 0xFFFFFF), hi = (int)(v >> 24);
-    return ((long long)__reduce_add_sync(LPK_FULL, hi) << 24) + (long long)__reduce_add_sync(LPK_FULL, lo);
+__device__ __forceinline__ void acc_add(long long *p, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
+
+// the rare draws of the handler, out of line so that the common path stays compact
+__device__ __noinline__ int8_t pick_strain(const PassParams &pp, int64_t i, int nd) {  // model.py:1127-1141
+    const lpk_tick_args &A = pp.A;
+    uint32_t y[4];
+    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
+    const double u = u53(y[0], y[1]);
+    const int ns = A.n_strains;
+    for (int k = 0; k < ns; ++k)
+        if (u < A.cdf_prev[(int64_t)nd * ns + k]) return (int8_t)k;
+    return 0;
+}
+// routine immunisation (model.py:1825-1854) and the campaign (model.py:2030-2059) for one agent in state s (after this
+// tick's disease-state step); returns s | vx << 8, vx bit 0 RI vaccinated, 1 RI protected, 2 IPV vaccinated, 3 SIA
+// vaccinated, 4 SIA protected
+__device__ __noinline__ uint32_t vaccine_draws(const PassParams &pp, int64_t i, int nd, int8_t s, uint32_t ey) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    uint32_t vx = 0u;
+    if ((ey >> 21) & 1u) {
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
+        if (u53(x[0], x[1]) < A.vx_prob_ri[nd]) {
+            vx |= 1u;
+            if (s == 0) { s = 1; P.strain[i] = (int8_t)A.ri_strain; vx |= 2u; }
+        }
+        if (u53(x[2], x[3]) < A.vx_prob_ipv[nd]) { vx |= 4u; P.ipv_protected[i] = 1; }
+    }
+    if ((ey >> 22) & 1u) {
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
+        const double u = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
+        if (u < pv) {
+            vx |= 8u;
+            if (s == 0 && u < pv * A.sia_vx_eff) { s = 1; P.strain[i] = (int8_t)A.sia_strain; vx |= 16u; }
+        }
+    }
+    return (uint32_t)(uint8_t)s | (vx << 8);
 }
 
 // warp-collective: every lane calls it; `valid` lanes carry an agent
@@ -313,18 +423,12 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
     const int nd = (int)(int16_t)(r.e.y & 0xFFFFu);
     const int8_t s0 = (int8_t)((r.e.y >> 16) & 0xFu);
     const bool hit = valid && ((r.e.y >> 20) & 1u);
-    const int ns = A.n_strains;
-    const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    int8_t st = r.st, s = s0;
-    long long fx = 0, efx = 0;
+    int8_t st = r.st, s = s0, sd = s0;  // sd: state after this tick's disease-state step, s: after the vaccines
+    long long efx = 0;
+    uint32_t vx = 0u;
     if (valid) {
-        if (hit) {  // exposure hit of tick t-1: categorical strain pick (model.py:1127-1141)
-            uint32_t y[4];
-            philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
-            const double u = u53(y[0], y[1]);
-            st = 0;
-            for (int k = 0; k < ns; ++k)
-                if (u < A.cdf_prev[(int64_t)nd * ns + k]) { st = (int8_t)k; break; }
+        if (hit) {  // exposure hit of tick t-1
+            st = pick_strain(pp, i, nd);
             P.strain[i] = st;
             efx = __float2ll_rn(r.rk * 1073741824.0f);
             atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
@@ -349,35 +453,54 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
                 }
             }
         }
+        sd = s;
+        if (r.e.y & (3u << 21)) {  // after the disease-state step (the reference's run order; it used the ipv_protected loaded before)
+            const uint32_t o = vaccine_draws(pp, i, nd, s, r.e.y);
+            s = (int8_t)(o & 0xFFu);
+            vx = o >> 8;
+            if (vx & 18u) {  // left S through a vaccine
+                efx = __float2ll_rn(r.rk * 1073741824.0f);
+                atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
+            }
+        }
         if (s != s0) P.disease_state[i] = s;
-        if (s == 2) fx = to_fx((double)r.inf * A.strain_r0_scalars[st]);
     }
-    // node-level counts, one group of same-node lanes at a time (one group except at a node boundary)
+    // node-level counts, one group of same-node lanes at a time (one group except at a node boundary): only lanes whose
+    // agent changed class today have anything to add
     uint32_t todo = __ballot_sync(LPK_FULL, valid);
     while (todo) {
         const int nd0 = __shfl_sync(LPK_FULL, nd, __ffs(todo) - 1);
         const bool mine = valid && nd == nd0;
         if (lane == 0 && acc->node != nd0) { acc_flush(pp, acc); acc->node = nd0; }
-        for (int k = 0; k < ns; ++k) {
-            const bool mk = mine && st == k;
-            const int cE = __popc(__ballot_sync(LPK_FULL, mk && pending && s0 == 1));
-            const int cI = __popc(__ballot_sync(LPK_FULL, mk && pending && s0 == 2));
-            const int cH = __popc(__ballot_sync(LPK_FULL, mk && hit));
-            const uint32_t tallied = __ballot_sync(LPK_FULL, mk && s == 2);
-            const long long b = tallied ? warp_sum_fx(mk && s == 2 ? fx : 0ll) : 0ll;
-            if (lane == 0) { acc->E[k] += cE; acc->I[k] += cI; acc->H[k] += cH; acc->beta[k] += b; }
+        __syncwarp();
+        if (mine) {
+            if (hit) { atomicAdd(&acc->H[st], 1); atomicAdd(&acc->E[st], 1); }
+            if (sd != s0) {  // s0 is E or I here
+                const long long fx = to_fx((double)r.inf * A.strain_r0_scalars[st]);
+                if (s0 == 1) atomicAdd(&acc->E[st], -1);
+                else { atomicAdd(&acc->I[st], -1); acc_add(&acc->beta[st], -fx); }
+                if (sd == 2) { atomicAdd(&acc->I[st], 1); acc_add(&acc->beta[st], fx); }
+                else atomicAdd(&acc->R, 1);
+            }
+            if (efx) acc_add(&acc->expo, efx);
+            if (vx) {
+                if (vx & 1u) atomicAdd(&acc->riV, 1);
+                if (vx & 2u) atomicAdd(&acc->riP, 1);
+                if (vx & 4u) atomicAdd(&acc->ipvV, 1);
+                if (vx & 8u) atomicAdd(&acc->siaV, 1);
+                if (vx & 16u) atomicAdd(&acc->siaP, 1);
+            }
         }
-        const int cR = __popc(__ballot_sync(LPK_FULL, mine && s == 3));
-        const uint32_t anyhit = __ballot_sync(LPK_FULL, mine && hit);
-        const long long e = anyhit ? warp_sum_fx(mine && hit ? efx : 0ll) : 0ll;
-        if (lane == 0) { acc->R += cR; acc->expo += e; }
+        __syncwarp();
         todo &= ~__ballot_sync(LPK_FULL, mine);
     }
 }
 
-// append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; returns how many
-__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t nw, uint32_t hits, uint32_t m) {
-    const uint32_t comb = nw | (hits << 4);
+// append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; f carries the agents' flag bits (hit
+// << 4 | RI-eligible << 5 | SIA-eligible << 6 in byte k); returns how many
+__device__ __forceinline__ uint32_t entry_flags(uint32_t hits, uint32_t ri, uint32_t sia) { return (hits << 4) | (ri << 5) | (sia << 6); }
+__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t nw, uint32_t f, uint32_t m) {
+    const uint32_t comb = (nw & 0x0F0F0F0Fu) | f;
     const int cnt = __popc(m);
     while (m) {
         const int bit = __ffs(m) - 1;
@@ -388,9 +511,9 @@ __device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, i
     return cnt;
 }
 // the same for the two quads a lane owns in a row pair (B = A + 128 agents): one loop for both
-__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t nwA, uint32_t hA, uint32_t mA,
-                                           uint32_t nwB, uint32_t hB, uint32_t mB) {
-    const uint32_t combA = nwA | (hA << 4), combB = nwB | (hB << 4);
+__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t nwA, uint32_t fA, uint32_t mA,
+                                           uint32_t nwB, uint32_t fB, uint32_t mB) {
+    const uint32_t combA = (nwA & 0x0F0F0F0Fu) | fA, combB = (nwB & 0x0F0F0F0Fu) | fB;
     uint32_t m = mA | (mB << 4);
     const int cnt = __popc(m);
     while (m) {
@@ -409,9 +532,12 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
     Q.count += __reduce_add_sync(LPK_FULL, mine);
     while (Q.count >= 32) {
         __syncwarp();
-        const ActiveRegs nxt = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        if (pp.debug & 1u) { Q.head += 32; Q.count -= 32; continue; }
+        // process the batch loaded a commit ago FIRST: a call boundary waits for every load in flight, so the new batch's
+        // loads are issued after it and land while the warp streams the next pair (profiles/r1_fused_v12_*: with the
+        // loads issued before the call, 8 % of all stall samples sat on the call instruction)
         if (Q.loaded) active_process(pp, Q.pend, true, Q.acc, lane);
-        Q.pend = nxt;
+        Q.pend = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
         Q.loaded = true;
         Q.head += 32;
         Q.count -= 32;
@@ -421,13 +547,11 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
 // out-of-line part of a death in a node-uniform quad: the agents in mask dm die on tick t (after tick t-1's pending
 // exposure + census); returns {new state word, remaining hits}
 __device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t dm) {
-    const bool pending = (pp.A.flags & LPK_F_PENDING) != 0;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         if (!((dm >> (8 * k)) & 1u)) continue;
         const int8_t s = byte_of(nw, k);
         if ((hits >> (8 * k)) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << (8 * k)); }
-        if (pending && (s == 1 || s == 2)) census_ei(pp, b + k, nd, s);
         kill_agent(pp, b + k, nd, s);
         nw = set_byte(nw, k, -1);
     }
@@ -441,7 +565,7 @@ __device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick, uint32_t
 // ---- routine immunisation in a node-uniform quad (reference model.py:1825-1854) -----------------------------------
 // Every alive, not chronically missed agent's ri_timer goes down by the step (four int16 lanes at a time); an agent is
 // eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Eligible agents are the few in
-// the age window, handled out of line.
+// the age window; they go to the ring and take their two draws in the handler, after their disease-state step.
 __device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t b, uint32_t w, uint32_t missed, uint2 tm) {
     const int step = pp.A.ri_step;
     const uint32_t ok8 = mask_alive(w) & ~missed;  // missed bytes are 0 / 1
@@ -454,54 +578,10 @@ __device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t
     const uint32_t ex = __vcmpleu2(__vsub2(tn.x, lo2), span2), ey = __vcmpleu2(__vsub2(tn.y, lo2), span2);
     return __byte_perm(ex, ey, 0x6420) & ok8;
 }
-// the eligible agents (mask elig) of the quad: disease state first where the agent is E / I (RI may set ipv_protected,
-// which the disease-state step of the SAME tick must not see: reference order DiseaseState_ABM before RI_ABM), then the
-// two draws.  Returns {new state word, cand | hits << 1} with the agents handled here removed from cand / hits.
-__device__ __noinline__ uint2 ri_eligible_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t cand,
-                                               uint32_t elig) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const bool pending = (A.flags & LPK_F_PENDING) != 0;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t bit = 1u << (8 * k);
-        if (!(elig & bit)) continue;
-        const int64_t i = b + k;
-        int8_t s = byte_of(nw, k);
-        if (cand & bit) {
-            if (hits & bit) expose_agent(pp, i, nd);
-            if (pending) census_ei(pp, i, nd, s);
-            s = ds_agent_ol(pp, i, s, nd);
-            nw = set_byte(nw, k, s);
-            if (s == 2) tally_infectious(pp, i, nd);
-            cand &= ~bit;
-            hits &= ~bit;
-        }
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
-        const double u1 = u53(x[0], x[1]), u2 = u53(x[2], x[3]);
-        if (u1 < A.vx_prob_ri[nd]) {
-            atomicAdd(&A.ri_vaccinated[nd], 1);
-            if (s == 0) {
-                nw = set_byte(nw, k, 1);
-                P.strain[i] = (int8_t)A.ri_strain;
-                leave_S(pp, i, nd);
-                const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
-                atomicAdd(&A.ri_protected[nd], 1);
-                atomicAdd(&A.new_exposed[nd], 1);
-                atomicAdd(&A.new_exposed_by_strain[c], 1);
-                atomicAdd(&A.ri_new_exposed_by_strain[c], 1);
-            }
-        }
-        if (u2 < A.vx_prob_ipv[nd]) { atomicAdd(&A.ipv_vaccinated[nd], 1); P.ipv_protected[i] = 1; }
-    }
-    return make_uint2(nw, cand | (hits << 1));
-}
-
 // ------------------------------------------------------------------ general pair (out of line): 256 agents that are not
 // all in one node or were not all present at tick t-1 (node boundaries, newborn cohorts, the table's tail).  One row at a
 // time, no software pipeline.  Returns how many agents this lane appended to the ring.
-template <bool kDeaths, bool kRI>
+template <bool kDeaths, bool kRI, bool kSIA>
 __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_t *q_tail, int64_t gp, int64_t n, int64_t count_prev,
                                          int lane) {
     const lpk_people &P = pp.P;
@@ -516,7 +596,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
         if (!valid) continue;
         const uint32_t w = load_b4(P.disease_state, b, valid);
         if ((w & 0x80808080u) == 0x80808080u) continue;  // nobody alive
-        uint32_t nw = w, hits = 0u, cand = 0u;
+        uint32_t nw = w, hits = 0u, cand = 0u, elig = 0u, camp = 0u;
         int nd = -1;
         bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
         if (fast) {
@@ -547,15 +627,15 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
                 if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, dm); nw = o.x; hits = o.y; }
             }
             cand = mask_EI(nw);
-            if (kRI) {
-                const uint32_t missed = *reinterpret_cast<const uint32_t *>(P.chronically_missed + b);
-                const uint2 tm = *reinterpret_cast<const uint2 *>(P.ri_timer + b);
-                const uint32_t elig = ri_timers_quad(pp, b, nw, missed, tm);
-                if (elig) { const uint2 o = ri_eligible_quad(pp, b, nd, nw, hits, cand, elig); nw = o.x; cand = o.y & 0x01010101u; hits = (o.y >> 1) & 0x01010101u; }
-            }
+            uint32_t missed = 0u;
+            if (kRI || kSIA) missed = *reinterpret_cast<const uint32_t *>(P.chronically_missed + b);
+            if (kRI) elig = ri_timers_quad(pp, b, nw, missed, *reinterpret_cast<const uint2 *>(P.ri_timer + b));
+            if (kSIA && A.sia_targeted[nd])
+                camp = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + b)), tick, A.sia_min_age,
+                                    (uint32_t)(A.sia_max_age - A.sia_min_age)) & mask_alive(nw) & ~missed;
         }
         if (nw != w) store_b4(P.disease_state, b, valid, nw);
-        mine += q_push(q, q_tail, (uint32_t)b, nd, nw, hits, cand);
+        mine += q_push(q, q_tail, (uint32_t)b, nd, nw, entry_flags(hits, elig, camp), cand | elig | camp);
     }
     return mine;
 }
@@ -597,11 +677,12 @@ __device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool kDeaths, bool kRI>
+template <bool kDeaths, bool kRI, bool kSIA>
 struct PassSmem {
-    static constexpr int kStages = (kDeaths || kRI) ? 3 : 4;
+    static constexpr int kStages = kSIA ? ((kDeaths || kRI) ? 2 : 3) : ((kDeaths || kRI) ? 3 : 4);
     static constexpr int kOffRisk = 256, kOffDod = 1280, kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
-    static constexpr int kStageBytes = kOffMissed + (kRI ? 768 : 0);
+    static constexpr int kOffDob = kOffMissed + ((kRI || kSIA) ? 256 : 0) + (kRI ? 512 : 0);
+    static constexpr int kStageBytes = kOffDob + (kSIA ? 1024 : 0);
     static constexpr int kOffQueue = 0;
     static constexpr int kOffSlots = kOffQueue + LPK_WARPS * QCAP * 8;
     static constexpr int kOffBars = kOffSlots + LPK_WARPS * kStages * kStageBytes;
@@ -609,11 +690,13 @@ struct PassSmem {
     static constexpr int kOffTail = kOffMeta + LPK_WARPS * kStages * 8;
     static constexpr int kOffAcc = (kOffTail + LPK_WARPS * 4 + 15) & ~15;
     static constexpr int kBytes = kOffAcc + LPK_WARPS * (int)sizeof(WarpAcc) + 32;
+    static_assert(kStages + 1 <= LPK_UNIT_PAIRS, "the producer may not run further ahead than one work unit");
+    static_assert(2 * kBytes <= 227 * 1024, "two blocks per SM");
 };
 
-template <bool kDeaths, bool kRI, int kOcc>
+template <bool kDeaths, bool kRI, bool kSIA, int kOcc>
 __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_constant__ PassParams pp) {
-    typedef PassSmem<kDeaths, kRI> L;
+    typedef PassSmem<kDeaths, kRI, kSIA> L;
     constexpr int NST = L::kStages;
     extern __shared__ __align__(128) unsigned char smem[];
     const lpk_people &P = pp.P;
@@ -646,16 +729,31 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     }
     __syncwarp();
 
-    // Work distribution: units of LPK_UNIT_PAIRS consecutive pairs are claimed warp by warp from a global counter, so a
-    // warp that meets regions dense in E / I agents (an SIA wave hits whole nodes) simply claims fewer units
+    // Work distribution: a warp claims RUNS of consecutive units (LPK_UNIT_PAIRS pairs each) from a global counter, so a
+    // warp that meets regions dense in E / I agents (an SIA wave hits whole nodes) simply claims less
     // (profiles/r1_fused_v10_*: with static round-robin chunks the average SM was busy 58-66 % of the kernel's duration).
+    // Guided self-scheduling: a run is 1 / (3 x warps in the grid) of the units still unclaimed (at most 64, at least 1) --
+    // long runs while there is plenty of work, so that a warp stays in one node and its per-node accumulators are flushed
+    // rarely, single units at the end for balance.
     // A warp's pairs form one sequence s = 0, 1, ...; the unit of sequence position s sits in register ua / ub (parity of
     // s >> LPK_UNIT_LOG); the producer runs at most kStages + 1 <= LPK_UNIT_PAIRS positions ahead of the consumer, so two
-    // registers suffice.  The claim for the unit after next is issued one unit early (its latency is never waited for).
+    // registers suffice.  The next run is claimed when the last unit of the current one is taken, a unit's worth of time
+    // before it is needed, from a counter value read another unit earlier: no claim latency is ever waited for.
     const uint32_t kNoUnit = 0xFFFFFFFFu;
+    const uint32_t guide = 3u * gridDim.x * LPK_WARPS;
     uint32_t ua = kNoUnit, ub = kNoUnit;
-    uint32_t claim = 0u;  // lane 0: the prefetched claim
-    if (lane == 0) claim = atomicAdd(pp.unit_ctr, 1u);
+    uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: the units of the current run not yet taken
+    bool exhausted = false;                // warp-uniform: a claim came back beyond the last unit
+    uint32_t claim_first = 0u, claim_cnt = 0u, seen = 0u;  // lane 0: the prefetched claim, the counter as last read
+    auto run_length = [&](uint32_t ctr) -> uint32_t {
+        const uint32_t left = ctr < n_units ? n_units - ctr : 0u;
+        const uint32_t r = left / guide;
+        return r < 1u ? 1u : (r > 64u ? 64u : r);
+    };
+    if (lane == 0) {
+        claim_cnt = run_length(0u);
+        claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
+    }
     auto pair_of = [&](int s) -> uint32_t {
         const uint32_t u = ((s >> LPK_UNIT_LOG) & 1) ? ub : ua;
         return u == kNoUnit ? kNoUnit : (u << LPK_UNIT_LOG) + (uint32_t)(s & (LPK_UNIT_PAIRS - 1));
@@ -664,17 +762,33 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     // t-1; -1 general handling; -2 no more work for this warp
     auto node_of = [&](int s) -> int {
         if ((s & (LPK_UNIT_PAIRS - 1)) == 0) {
-            uint32_t u = __shfl_sync(LPK_FULL, claim, 0);
-            if (u >= n_units) u = kNoUnit;
-            else if (lane == 0) claim = atomicAdd(pp.unit_ctr, 1u);
+            uint32_t u = kNoUnit;
+            if (!exhausted) {
+                if (run_next >= run_end) {  // take the prefetched claim
+                    const uint32_t first = __shfl_sync(LPK_FULL, claim_first, 0), cnt = __shfl_sync(LPK_FULL, claim_cnt, 0);
+                    if (first >= n_units) exhausted = true;
+                    else { run_next = first; run_end = first + cnt < n_units ? first + cnt : n_units; }
+                }
+                if (!exhausted) {
+                    u = run_next++;
+                    if (run_next >= run_end && lane == 0) {  // the run's last unit: claim the next run now
+                        claim_cnt = run_length(seen);
+                        claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
+                    }
+                    if (lane == 0) seen = *reinterpret_cast<volatile uint32_t *>(pp.unit_ctr);
+                }
+            }
             if ((s >> LPK_UNIT_LOG) & 1) ub = u; else ua = u;
         }
         const uint32_t gp = pair_of(s);
         if (gp >= total_pairs) return -2;  // kNoUnit included
         return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
     };
-    int tc_node = -2;  // one-entry cache of tau per node (a warp stays in one node for hundreds of pairs)
+    int tc_node = -2;  // one-entry cache of tau (and the campaign's target flag) per node: a warp stays in one node for long
     float tc_tau = 0.f;
+    bool tc_sia = false;
+    const int sia_lo = kSIA ? A.sia_min_age : 0;
+    const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
     int tn_next = node_of(0);  // node of the next pair to be requested, loaded one request ahead
     // request pair s into slot (warp-uniform; the elected lane talks to the TMA engine)
     auto produce = [&](int s, int slot) {
@@ -682,25 +796,31 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         tn_next = node_of(s + 1);
         float tau = 0.f;
         if (tn >= 0) {
-            if (tn != tc_node) { tc_node = tn; tc_tau = pending ? __ldg(&A.q_prev[tn]) : 0.f; }
+            if (tn != tc_node) {
+                tc_node = tn;
+                tc_tau = pending ? __ldg(&A.q_prev[tn]) : 0.f;
+                if (kSIA) tc_sia = __ldg(&A.sia_targeted[tn]) != 0;
+            }
             tau = tc_tau;
         }
+        const bool camp = kSIA && tn >= 0 && tc_sia;
         if (lane == 0) {
-            meta[slot] = make_int2(tn, __float_as_int(tau));
+            meta[slot] = make_int2(tn, __float_as_int(tau) | (camp ? (int)0x80000000u : 0));  // tau >= 0: the sign bit is free
             uint64_t *bar = &bars[slot];
             if (tn >= 0) {
                 const int64_t a0 = (int64_t)pair_of(s) * 256;
                 unsigned char *dst = slots + slot * L::kStageBytes;
                 const bool risk = tau > 0.f;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
-                mbar_arrive_expect_tx(bar, 256u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (kRI ? 768u : 0u));
+                const bool missed = kRI || camp;
+                mbar_arrive_expect_tx(bar, 256u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
+                                               (camp ? 1024u : 0u));
                 tma_load(dst, P.disease_state + a0, 256u, bar);
                 if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
                 if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
-                if (kRI) {
-                    tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
-                    tma_load(dst + L::kOffTimer, P.ri_timer + a0, 512u, bar);
-                }
+                if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
+                if (kRI) tma_load(dst + L::kOffTimer, P.ri_timer + a0, 512u, bar);
+                if (camp) tma_load(dst + L::kOffDob, P.date_of_birth + a0, 1024u, bar);
             } else {
                 mbar_arrive(bar);
             }
@@ -712,11 +832,12 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         mbar_wait(&bars[slot], parity);
         const int2 mt = meta[slot];
         const int tn = mt.x;
-        const float tau = __int_as_float(mt.y);
+        const float tau = __int_as_float(mt.y & 0x7FFFFFFF);
+        const bool camp = kSIA && mt.y < 0;
         const unsigned char *src = slots + slot * L::kStageBytes;
         uint32_t wA = 0u, wB = 0u, mA = 0u, mB = 0u;
         float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA;
-        int4 dA = make_int4(0, 0, 0, 0), dB = dA;
+        int4 dA = make_int4(0, 0, 0, 0), dB = dA, bA4 = dA, bB4 = dA;
         uint2 tA = make_uint2(0u, 0u), tB = tA;
         if (tn >= 0) {
             wA = *reinterpret_cast<const uint32_t *>(src + lane * 4);
@@ -729,11 +850,17 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
                 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
                 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
             }
-            if (kRI) {
+            if (kRI || camp) {
                 mA = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + lane * 4);
                 mB = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + 128 + lane * 4);
+            }
+            if (kRI) {
                 tA = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + lane * 8);
                 tB = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + 256 + lane * 8);
+            }
+            if (camp) {
+                bA4 = *reinterpret_cast<const int4 *>(src + L::kOffDob + lane * 16);
+                bB4 = *reinterpret_cast<const int4 *>(src + L::kOffDob + 512 + lane * 16);
             }
         }
         __syncwarp();
@@ -741,13 +868,13 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         if (tn == -2) return false;
         const int64_t gp = (int64_t)pair_of(s);
         if (tn < 0) {
-            q_commit(pp, Q, general_pair<kDeaths, kRI>(pp, Q.q, Q.tail, gp, n, count_prev, lane), lane);
+            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, gp, n, count_prev, lane), lane);
             return true;
         }
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
         uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u;
-        if (tau > 0.f) {  // exposure trial of tick t-1
+        if (tau > 0.f && !(pp.debug & 2u)) {  // exposure trial of tick t-1
             const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
             uint32_t x[4];
             philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
@@ -765,15 +892,18 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
             if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = o.x; hB = o.y; }
         }
         // exposed / infectious agents (fresh hits included): census of t-1, disease state and tally of t in the handler
-        uint32_t cA = mask_EI(nwA), cB = mask_EI(nwB);
-        if (kRI) {
-            const uint32_t eA = ri_timers_quad(pp, bA, nwA, mA, tA), eB = ri_timers_quad(pp, bB, nwB, mB, tB);
-            if (eA) { const uint2 o = ri_eligible_quad(pp, bA, nd, nwA, hA, cA, eA); nwA = o.x; cA = o.y & 0x01010101u; hA = (o.y >> 1) & 0x01010101u; }
-            if (eB) { const uint2 o = ri_eligible_quad(pp, bB, nd, nwB, hB, cB, eB); nwB = o.x; cB = o.y & 0x01010101u; hB = (o.y >> 1) & 0x01010101u; }
+        // and so are the agents eligible for routine immunisation or the campaign: their draws follow their own disease-state step
+        const uint32_t cA = mask_EI(nwA), cB = mask_EI(nwB);
+        uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
+        if (kRI) { eA = ri_timers_quad(pp, bA, nwA, mA, tA); eB = ri_timers_quad(pp, bB, nwB, mB, tB); }
+        if (camp) {
+            sA = sia_age_mask(bA4, tick, sia_lo, sia_span) & mask_alive(nwA) & ~mA;
+            sB = sia_age_mask(bB4, tick, sia_lo, sia_span) & mask_alive(nwB) & ~mB;
         }
         if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
         if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
-        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, nwA, hA, cA, nwB, hB, cB), lane);
+        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, nwA, entry_flags(hA, eA, sA), cA | eA | sA, nwB,
+                                    entry_flags(hB, eB, sB), cB | eB | sB), lane);
         return true;
     };
 
@@ -802,18 +932,18 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     if (lane == 0) acc_flush(pp, Q.acc);
 }
 
-template <bool kDeaths, bool kRI, int kOcc>
+template <bool kDeaths, bool kRI, bool kSIA, int kOcc>
 static int launch_pass(const PassParams &pp, cudaStream_t st) {
-    typedef PassSmem<kDeaths, kRI> L;
+    typedef PassSmem<kDeaths, kRI, kSIA> L;
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
+        CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kSIA, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
                  "tick_pass smem");
         configured = true;
     }
     const int grid = lpk_agent_grid(pp.P.capacity, kOcc);
     CUDA_TRY(cudaMemsetAsync(pp.unit_ctr, 0, sizeof(uint32_t), st), "tick_pass work counter");
-    k_tick_pass<kDeaths, kRI, kOcc><<<grid, LPK_BLOCK, L::kBytes, st>>>(pp);
+    k_tick_pass<kDeaths, kRI, kSIA, kOcc><<<grid, LPK_BLOCK, L::kBytes, st>>>(pp);
     return LPK_OK;
 }
 // one 4-byte work counter per device, allocated on first use (the pass is launched on one stream per device)
@@ -848,27 +978,42 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     REQUIRE((A.id_base & 255) == 0, "tick_pass id_base must be a multiple of 256");
     REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus && A.risk_hist && A.R_cur && A.tx_hits,
             "tick_pass stage outputs");
-    REQUIRE(A.E_by_strain_prev && A.I_by_strain_prev && A.new_exposed_prev && A.new_exposed_by_strain_prev, "tick_pass census rows");
+    REQUIRE(A.E_cur && A.I_cur && A.tx_hits_by_strain && A.new_exposed_prev && A.new_exposed_by_strain_prev, "tick_pass census");
     if (A.flags & LPK_F_PENDING) REQUIRE(A.q_prev && A.cdf_prev, "tick_pass pending exposure inputs");
-    const bool deaths = (A.flags & LPK_F_DEATHS) != 0, ri = (A.flags & LPK_F_RI) != 0;
+    const bool deaths = (A.flags & LPK_F_DEATHS) != 0, ri = (A.flags & LPK_F_RI) != 0, sia = (A.flags & LPK_F_SIA) != 0;
+    if (sia) REQUIRE(P.date_of_birth && ALIGNED(P.date_of_birth, 16) && P.chronically_missed && ALIGNED(P.chronically_missed, 16) &&
+                         A.sia_targeted && A.vx_prob_sia && A.sia_vaccinated && A.sia_protected && A.sia_new_exposed_by_strain &&
+                         A.new_exposed && A.new_exposed_by_strain && A.sia_max_age >= A.sia_min_age && A.sia_strain >= 0 &&
+                         A.sia_strain < A.n_strains, "tick_pass SIA");
     if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && A.deaths && A.dead_pp && A.dead_par, "tick_pass deaths");
     if (ri) REQUIRE(P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
                         A.vx_prob_ipv && A.ri_vaccinated && A.ri_protected && A.ipv_vaccinated && A.new_exposed &&
-                        A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0, "tick_pass RI");
+                        A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0 && A.ri_strain >= 0 &&
+                        A.ri_strain < A.n_strains, "tick_pass RI");
     PassParams pp;
     pp.P = P;
     pp.A = A;
     pp.unit_ctr = pass_unit_counter();
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("LPK_PASS_DEBUG"); dbg = e ? atoi(e) : 0; }
+        pp.debug = (uint32_t)dbg;
+    }
     REQUIRE(pp.unit_ctr, "tick_pass work counter allocation");
     REQUIRE(ALIGNED(P.disease_state, 16) && (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
             "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
     int rc;
-    if (deaths && ri) rc = launch_pass<true, true, 2>(pp, st);
-    else if (deaths) rc = launch_pass<true, false, 2>(pp, st);
-    else if (ri) rc = launch_pass<false, true, 2>(pp, st);
-    else if (pass_occupancy() == 2) rc = launch_pass<false, false, 2>(pp, st);
-    else rc = launch_pass<false, false, 3>(pp, st);
+    if (sia) {
+        if (deaths && ri) rc = launch_pass<true, true, true, 2>(pp, st);
+        else if (deaths) rc = launch_pass<true, false, true, 2>(pp, st);
+        else if (ri) rc = launch_pass<false, true, true, 2>(pp, st);
+        else rc = launch_pass<false, false, true, 2>(pp, st);
+    } else if (deaths && ri) rc = launch_pass<true, true, false, 2>(pp, st);
+    else if (deaths) rc = launch_pass<true, false, false, 2>(pp, st);
+    else if (ri) rc = launch_pass<false, true, false, 2>(pp, st);
+    else if (pass_occupancy() == 2) rc = launch_pass<false, false, false, 2>(pp, st);
+    else rc = launch_pass<false, false, false, 3>(pp, st);
     if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
     return LPK_OK;
@@ -935,13 +1080,24 @@ __global__ void k_tick_epilogue(lpk_node_args a) {
         a.S_snap[n] = (int32_t)a.sus[n];
         a.R_snap[n] = a.R_cur[n];
     }
-    if ((a.flags & LPK_F_PENDING) && a.E_prev) {
+    // exposed / infectious census of tick t-1 from the carried counts: the snapshot taken when tick t-1's stages ended,
+    // plus tick t-1's exposures (found by this pass); "=" like Transmission_ABM.log (model.py:1477-1480)
+    if (a.flags & LPK_F_PENDING) {
         int e = 0, i = 0;
-        for (int s = 0; s < ns; ++s) { e += a.E_by_strain_prev[(int64_t)n * ns + s]; i += a.I_by_strain_prev[(int64_t)n * ns + s]; }
+        for (int s = 0; s < ns; ++s) {
+            const int64_t c = (int64_t)n * ns + s;
+            const int es = a.E_snap[c] + a.tx_hits_by_strain[c], is = a.I_snap[c];
+            a.E_by_strain_prev[c] = es; a.I_by_strain_prev[c] = is;
+            e += es; i += is;
+        }
         a.E_prev[n] = e; a.I_prev[n] = i;
     }
-    if (a.next_beta_fx)
-        for (int s = 0; s < ns; ++s) a.next_beta_fx[(int64_t)n * ns + s] = 0;
+    for (int s = 0; s < ns; ++s) {
+        const int64_t c = (int64_t)n * ns + s;
+        a.tx_hits_by_strain[c] = 0;
+        a.E_snap[c] = a.E_cur[c];
+        a.I_snap[c] = a.I_cur[c];
+    }
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
@@ -961,6 +1117,8 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(!a.S_snap || (a.R_snap && a.sus && a.R_cur && a.tx_hits && (!(a.flags & LPK_F_PENDING) || (a.S_prev && a.R_prev))),
             "tick_node carried census");
     REQUIRE(a.pop || a.pop_prev, "tick_node needs a population row for the rate denominator");
+    REQUIRE(a.E_cur && a.I_cur && a.E_snap && a.I_snap && a.tx_hits_by_strain &&
+                (!(a.flags & LPK_F_PENDING) || (a.E_by_strain_prev && a.I_by_strain_prev && a.E_prev && a.I_prev)), "tick_node E / I census");
     cudaStream_t st = as_stream(stream);
     k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");

@@ -21,7 +21,7 @@ import torch
 
 from . import _lpk
 from . import kernels as K
-from ._lpk import F_DEATHS, F_PENDING, F_RI, F_STAGES, NodeArgs, People, TickArgs, check, dp, stream_handle
+from ._lpk import F_DEATHS, F_PENDING, F_RI, F_SIA, F_STAGES, NodeArgs, People, TickArgs, check, dp, stream_handle
 
 
 def eligible(sim) -> bool:
@@ -53,13 +53,16 @@ class FusedEngine:
         dev.set_count(sim.people.count)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=d)  # noqa: E731
         i64 = lambda *s: torch.zeros(s, dtype=torch.int64, device=d)  # noqa: E731
-        self.beta = [i64(n, ns), i64(n, ns)]  # infectivity tally, recomputed every tick (ping-pong)
-        # susceptible-side tallies carried from tick to tick and corrected by the pass (include/lpk.h, lpk_tick_args)
+        # tallies carried from tick to tick and corrected by the pass where an agent changes class (include/lpk.h,
+        # lpk_tick_args): infectivity per node and strain, susceptibles / their risk sum / risk histogram per node,
+        # exposed / infectious per node and strain, recovered per node
+        self.beta, self.beta_sum = i64(n, ns), i64(n, ns)  # beta_sum: the all-reduced copy of a sharded run
         self.expo, self.sus, self.hist = i64(n), i64(n), i32(n, _lpk.RISK_BINS)
-        # recovered per node, carried the same way; per-node exposures found by a pass; census snapshots (lpk_node_args)
-        self.R_cur, self.tx_hits, self.S_snap, self.R_snap = i32(n), i32(n), i32(n), i32(n)
-        self._census_scratch = [i32(n) for _ in range(6)] + [i32(n, ns), i32(n, ns)]
-        self._beta_scratch = i64(n, ns)
+        self.E_cur, self.I_cur, self.R_cur = i32(n, ns), i32(n, ns), i32(n)
+        # exposures of the pending tick found by a pass; census snapshots (lpk_node_args)
+        self.tx_hits, self.tx_hits_s, self.S_snap, self.R_snap = i32(n), i32(n, ns), i32(n), i32(n)
+        self.E_snap, self.I_snap = i32(n, ns), i32(n, ns)
+        self._census_scratch = [i32(n) for _ in range(6)]
         self.deaths, self.dead_pp, self.dead_par = i32(n), i32(n), i32(n)
         self.cur_potp, self.cur_p = i32(n), i32(n)
         self.q = torch.zeros(n, dtype=torch.float32, device=d)
@@ -94,20 +97,28 @@ class FusedEngine:
         sim, dev, c = self.sim, self.dev, self.dev.cols
         K.tx_step_prep(dev.n_nodes, sim.people.count, dev.n_strains, c["strain"], list(sim.pars.strain_r0_scalars.values()),
                        c["disease_state"], c["node_id"], c["daily_infectivity"], c["acq_risk_multiplier"],
-                       out=(self._beta_scratch, self.expo, self.sus, self.hist))
-        S, E, I, R, POTP, Pz, Es, Is = self._census_scratch
+                       out=(self.beta, self.expo, self.sus, self.hist))
+        S, E, I, R, POTP, Pz = self._census_scratch
         K.count_SEIRP(c["node_id"], c["disease_state"], c["strain"], c["potentially_paralyzed"], c["paralyzed"], dev.n_nodes,
-                      dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, Es, Is, POTP, Pz))
+                      dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, self.E_cur, self.I_cur, POTP, Pz))
         self.tx_hits.zero_()
+        self.tx_hits_s.zero_()
 
     def _row(self, name, t):
         r = self.dev.res.get(name)
         return self.dummy_row if r is None else r[t]
 
-    def needs_components(self, t) -> bool:
-        sim = self.sim
+    def sia_events(self, t):
         sia = self.by_name.get("SIA_ABM")
-        if sia is not None and sia._by_tick.get(t) and sim.pars.vx_prob_sia is not None:
+        if sia is None or self.sim.pars.vx_prob_sia is None:
+            return []
+        return sia._by_tick.get(t) or []
+
+    def needs_components(self, t) -> bool:
+        """Days the pass does not fuse: seed_schedule injections, several campaign events on one day (the reference
+        overwrites sia_vaccinated / sia_protected per event, model.py:2142-2145), a campaign with an empty age window."""
+        events = self.sia_events(t)
+        if len(events) > 1 or (events and not (int(events[0]["age_range"][0]) <= int(events[0]["age_range"][1]))):
             return True
         ds = self.by_name["DiseaseState_ABM"]
         return t in ds.seed_schedule
@@ -159,8 +170,8 @@ class FusedEngine:
         A.q_prev, A.cdf_prev = dp(self.q), dp(self.cdf)
         tp = max(t - 1, 0)
         A.new_exposed_prev, A.new_exposed_by_strain_prev = dp(self._row("new_exposed", tp)), dp(self._row("new_exposed_by_strain", tp))
-        A.E_by_strain_prev, A.I_by_strain_prev = dp(self._row("E_by_strain", tp)), dp(self._row("I_by_strain", tp))
-        A.tx_hits, A.R_cur = dp(self.tx_hits), dp(self.R_cur)
+        A.tx_hits, A.tx_hits_by_strain, A.R_cur = dp(self.tx_hits), dp(self.tx_hits_s), dp(self.R_cur)
+        A.E_cur, A.I_cur = dp(self.E_cur), dp(self.I_cur)
         A.p_paralysis = float(np.float32(pars.p_paralysis))
         A.new_potential, A.new_paralyzed = dp(self._row("new_potentially_paralyzed", t)), dp(self._row("new_paralyzed", t))
         A.deaths, A.dead_pp, A.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
@@ -174,11 +185,18 @@ class FusedEngine:
             A.ipv_vaccinated = dp(self._row("ipv_vaccinated", t))
             A.new_exposed, A.new_exposed_by_strain = dp(self._row("new_exposed", t)), dp(self._row("new_exposed_by_strain", t))
             A.ri_new_exposed_by_strain = dp(self._row("ri_new_exposed_by_strain", t))
+        events = self.sia_events(t)
+        if events:  # exactly one (needs_components): the campaign runs inside the pass, after RI, like SIA_ABM.step
+            flags |= F_SIA
+            targeted, vx_prob, vx_eff, lo, hi, vstrain = self.by_name["SIA_ABM"].event_args(dev, events[0])
+            A.sia_targeted, A.vx_prob_sia, A.sia_vx_eff = dp(targeted), dp(vx_prob), float(vx_eff)
+            A.sia_min_age, A.sia_max_age, A.sia_strain, A.sia_event_idx = int(lo), int(hi), int(vstrain), 0
+            A.sia_vaccinated, A.sia_protected = dp(self._row("sia_vaccinated", t)), dp(self._row("sia_protected", t))
+            A.sia_new_exposed_by_strain = dp(self._row("sia_new_exposed_by_strain", t))
+            A.new_exposed, A.new_exposed_by_strain = dp(self._row("new_exposed", t)), dp(self._row("new_exposed_by_strain", t))
         for s, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
             A.strain_r0_scalars[s] = float(v)
-        beta_fx, exposure_fx, sus, risk_hist = self.beta[t & 1], self.expo, self.sus, self.hist
-        if not self.pending:  # the previous tick was not fused, so nobody zeroed this parity
-            beta_fx.zero_()
+        beta_fx, exposure_fx, sus, risk_hist = self.beta, self.expo, self.sus, self.hist
         A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
         A.flags = flags
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
@@ -186,6 +204,8 @@ class FusedEngine:
         if sim.shard is not None:  # the one per-tick exchange: sum of the nodes x strains infectivity tally
             from . import sharding
 
+            self.beta_sum.copy_(self.beta)  # the carried tally stays local; the node math sees the sum over ranks
+            beta_fx = self.beta_sum
             sharding.allreduce_tally(beta_fx, sim.shard)
         N = NodeArgs()
         N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
@@ -206,11 +226,12 @@ class FusedEngine:
         N.cur_potp, N.cur_p = dp(self.cur_potp), dp(self.cur_p)
         N.new_potential, N.new_paralyzed = A.new_potential, A.new_paralyzed
         N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
-        N.E_by_strain_prev, N.I_by_strain_prev = A.E_by_strain_prev, A.I_by_strain_prev
+        N.E_by_strain_prev, N.I_by_strain_prev = dp(self._row("E_by_strain", tp)), dp(self._row("I_by_strain", tp))
         N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
+        N.E_cur, N.I_cur, N.E_snap, N.I_snap = dp(self.E_cur), dp(self.I_cur), dp(self.E_snap), dp(self.I_snap)
+        N.tx_hits_by_strain = dp(self.tx_hits_s)
         N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
         N.S_prev, N.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
-        N.next_beta_fx = dp(self.beta[(t + 1) & 1])
         N.counts = dp(dev.counts)
         K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 4)
         self.pending = True

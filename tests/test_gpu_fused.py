@@ -109,6 +109,36 @@ def test_fused_equals_components_large_nodes(lp, pyramid):
     assert (r.R[-1] > r.R[0]).all() and np.array_equal(r.E, r.E_by_strain.sum(axis=2))
 
 
+SIA_DAYS = [  # single-event days: fused inside the pass; tick 7 = vital dynamics, tick 14 = vital dynamics + RI, tick 19 plain
+    {"date": "2019-01-08", "nodes": [0, 2], "age_range": (0, 5 * 365), "vaccinetype": "nOPV2"},
+    {"date": "2019-01-15", "nodes": [1, 2, 3], "age_range": (200, 10 * 365), "vaccinetype": "mOPV2"},
+    {"date": "2019-01-20", "nodes": [0, 1, 2, 3], "age_range": (0, 15 * 365), "vaccinetype": "nOPV2"},
+    {"date": "2019-01-24", "nodes": [3], "age_range": (0, 5 * 365), "vaccinetype": "mOPV2"},   # two events on one day:
+    {"date": "2019-01-24", "nodes": [0, 3], "age_range": (0, 5 * 365), "vaccinetype": "nOPV2"},  # handed to the components
+]
+
+
+def test_fused_sia_days_small_nodes(lp, pyramid):
+    """Campaign days run inside the pass (LPK_F_SIA) on nodes of a few thousand agents: general rows and mixed quads."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, sia_schedule=[dict(e) for e in SIA_DAYS], dur=35)
+    assert calls.get("tick_pass", 0) >= 30 and calls.get("fast_sia", 0) == 2  # only the two-event day left the pass
+    assert_identical(ref, fus)
+    r = fus.results
+    assert (r.sia_protected[[7, 14, 19]].sum(axis=1) > 0).all() and r.sia_vaccinated.sum() > r.sia_protected.sum()
+
+
+def test_fused_sia_days_large_nodes(lp, pyramid):
+    """The same on nodes of 120-260 K agents: the streaming loop's SIA rows (TMA-staged date_of_birth, ring entries)."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, n_nodes=4, pop_range=(120_000, 260_000), dur=30, r0=6,
+                                      init_prev=[0.004, 0.0, 0.001, 0.0], sia_schedule=[dict(e) for e in SIA_DAYS], seed_schedule=None)
+    assert calls.get("tick_pass", 0) >= 28
+    assert_identical(ref, fus)
+    r = fus.results
+    assert r.sia_protected.sum() > 50_000 and r.ri_vaccinated.sum() > 0 and r.deaths.sum() > 0
+
+
 def test_fused_equals_components_saturating_force_of_infection(lp, pyramid):
     """r0 = 999 (the reference's own 'everybody gets exposed' regime, tests/test_diseasestate_abm.py:258): tau is huge or
     'everybody', so the high-half pre-test passes for every susceptible and the exact path decides."""
