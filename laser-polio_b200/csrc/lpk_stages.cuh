@@ -20,30 +20,35 @@ static inline DevRng dev_rng(const lpk_rng *r) {
 }
 
 
-// Infected block of the state machine on register copies (reference model.py:425-452): recovery timer, then -- for the
-// paralytic strain 0 only -- the paralysis gate (once per agent: potentially_paralyzed leaves -1) with one uniform, and
-// the paralysis timer.  Returns the new state (2 or 3); flags bit 0 = newly potentially paralysed, bit 1 = newly paralysed.
+// Paralysis part of the infected block (reference model.py:432-452), paralytic strain 0 only: the gate fires once per
+// agent (potentially_paralyzed leaves -1) with one uniform; then the paralysis timer counts down.  flags bit 0 = newly
+// potentially paralysed, bit 1 = newly paralysed.
+__device__ __forceinline__ void paralysis_step(int64_t i, int8_t ipvv, int8_t &pt, int8_t &pq, int8_t &par, double p_paralysis,
+                                               const DevRng &rng, int &flags) {
+    if (pt <= 0 && pq == -1) {
+        if (ipvv == 0) {
+            pq = 1;
+            flags |= 1;
+            double u;
+            if (rng.u1) u = rng.u1[i];
+            else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
+            if (u < p_paralysis) { par = 1; flags |= 2; }
+        } else {
+            pq = 0;
+        }
+    }
+    pt = (int8_t)(pt - 1);
+}
+
+// Infected block of the state machine on register copies (reference model.py:425-452): recovery timer, then the
+// paralysis part for strain 0.  Returns the new state (2 or 3).
 __device__ __forceinline__ int8_t ds_infected(int64_t i, int8_t st, int8_t ipvv, int8_t &it, int8_t &pt, int8_t &pq, int8_t &par,
                                               double p_paralysis, const DevRng &rng, int &flags) {
     int8_t s = 2;
     flags = 0;
     if (it <= 0) s = 3;
     it = (int8_t)(it - 1);
-    if (st == 0) {
-        if (pt <= 0 && pq == -1) {
-            if (ipvv == 0) {
-                pq = 1;
-                flags |= 1;
-                double u;
-                if (rng.u1) u = rng.u1[i];
-                else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
-                if (u < p_paralysis) { par = 1; flags |= 2; }
-            } else {
-                pq = 0;
-            }
-        }
-        pt = (int8_t)(pt - 1);
-    }
+    if (st == 0) paralysis_step(i, ipvv, pt, pq, par, p_paralysis, rng, flags);
     return s;
 }
 

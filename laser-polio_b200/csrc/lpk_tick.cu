@@ -272,7 +272,7 @@ __device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, u
 // entry = {agent index (tables hold < 2^32 slots), node | state << 16 | hit << 20}
 struct ActiveRegs {
     uint2 e;
-    int8_t st, et, it, pt, pq, ipvv;
+    int8_t pt, pq, ipvv;
     float inf, rk;
 };
 struct WarpAcc;
@@ -292,22 +292,29 @@ struct WarpQueue {
 // (profiles/r1_fused_v10_postsia_*: 35 % of the stall samples sat in the handler waiting for its own loads).  Between the
 // two phases nobody else touches the agent: it is pushed once per pass, and the death / RI paths never push what they
 // handle themselves.
-// entry.y = node | state << 16 | hit << 20 | RI-eligible << 21 | SIA-eligible << 22
+// Ring entry: x = agent index, y = node | F << 16 | strain << 24 with the flag byte
+//   F = state before tick t's disease-state step (bits 0-1) | E -> I today << 2 | I -> R today << 3 | exposure hit of t-1 << 4
+//       | RI-eligible << 5 | SIA-eligible << 6 | paralytic strain in the infected block today << 7
+// The streaming loop has already counted the timers down and written the new state (ds_quad): the handler only does what
+// needs scattered columns -- class-change bookkeeping, the paralysis step, the strain pick of a hit, the vaccine draws.
+#define EF_TE (1u << 18)
+#define EF_TI (1u << 19)
+#define EF_HIT (1u << 20)
+#define EF_RI (1u << 21)
+#define EF_SIA (1u << 22)
+#define EF_WILD (1u << 23)
 __device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
     const lpk_people &P = pp.P;
     const int64_t i = (int64_t)e.x;
-    const uint32_t s0 = (e.y >> 16) & 0xFu;
-    const bool hit = (e.y >> 20) & 1u, ei = (s0 == 1u || s0 == 2u);
+    const bool wild = (e.y & EF_WILD) != 0u;
     ActiveRegs r;
     r.e = e;
-    r.st = (ei && !hit) ? P.strain[i] : (int8_t)0;
-    r.et = (s0 == 1u) ? P.exposure_timer[i] : (int8_t)1;
-    r.it = ei ? P.infection_timer[i] : (int8_t)0;
-    r.pt = ei ? P.paralysis_timer[i] : (int8_t)0;
-    r.pq = ei ? P.potentially_paralyzed[i] : (int8_t)0;
-    r.ipvv = ei ? P.ipv_protected[i] : (int8_t)0;
-    r.inf = ei ? P.daily_infectivity[i] : 0.f;
-    r.rk = (hit || s0 == 0u) ? P.acq_risk_multiplier[i] : 0.f;  // a susceptible is here for RI / SIA and may leave S
+    r.pt = wild ? P.paralysis_timer[i] : (int8_t)0;
+    r.pq = wild ? P.potentially_paralyzed[i] : (int8_t)0;
+    r.ipvv = wild ? P.ipv_protected[i] : (int8_t)0;
+    r.inf = (e.y & (EF_TE | EF_TI)) ? P.daily_infectivity[i] : 0.f;
+    // a hit left S; a susceptible that is here for RI / SIA may leave it
+    r.rk = ((e.y & EF_HIT) || ((e.y >> 16) & 3u) == 0u) ? P.acq_risk_multiplier[i] : 0.f;
     return r;
 }
 // Per-warp accumulators of the handler's node-level counts (shared memory; lanes add with shared-memory atomics, lane 0
@@ -415,15 +422,33 @@ __device__ __noinline__ uint32_t vaccine_draws(const PassParams &pp, int64_t i, 
     return (uint32_t)(uint8_t)s | (vx << 8);
 }
 
+// the paralysis step of one agent of the paralytic strain that is in the infected block today (out of line: rare)
+__device__ __noinline__ void paralysis_agent(const PassParams &pp, int64_t i, int nd, int8_t ipvv, int8_t pt, int8_t pq) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int8_t pq0 = pq;
+    int8_t par = 0;
+    int flags = 0;
+    paralysis_step(i, ipvv, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
+    P.paralysis_timer[i] = pt;
+    if (pq != pq0) P.potentially_paralyzed[i] = pq;
+    if (flags) {
+        atomicAdd(&A.new_potential[nd], 1);
+        if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
+    }
+}
+
 // warp-collective: every lane calls it; `valid` lanes carry an agent
 __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, bool valid, WarpAcc *acc, int lane) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int64_t i = (int64_t)r.e.x;
-    const int nd = (int)(int16_t)(r.e.y & 0xFFFFu);
-    const int8_t s0 = (int8_t)((r.e.y >> 16) & 0xFu);
-    const bool hit = valid && ((r.e.y >> 20) & 1u);
-    int8_t st = r.st, s = s0, sd = s0;  // sd: state after this tick's disease-state step, s: after the vaccines
+    const uint32_t ey = valid ? r.e.y : 0u;
+    const int nd = (int)(int16_t)(ey & 0xFFFFu);
+    const int8_t s0 = (int8_t)((ey >> 16) & 3u);
+    const int8_t sd = (int8_t)(s0 + ((ey >> 18) & 1u) + ((ey >> 19) & 1u));  // state after this tick's disease-state step
+    const bool hit = (ey & EF_HIT) != 0u;
+    int8_t st = (int8_t)((ey >> 24) & 3u), s = sd;
     long long efx = 0;
     uint32_t vx = 0u;
     if (valid) {
@@ -432,41 +457,22 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
             P.strain[i] = st;
             efx = __float2ll_rn(r.rk * 1073741824.0f);
             atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
+            if (st == 0 && (ey & EF_TE))  // infectious on the day after exposure, paralytic strain: its columns were not preloaded
+                paralysis_agent(pp, i, nd, P.ipv_protected[i], P.paralysis_timer[i], P.potentially_paralyzed[i]);
         }
-        int8_t it = r.it, pt = r.pt, pq = r.pq;
-        if (s == 1) {  // model.py:419-422
-            if (r.et <= 0) s = 2;
-            P.exposure_timer[i] = (int8_t)(r.et - 1);
-        }
-        if (s == 2) {
-            const int8_t pq0 = pq;
-            int8_t par = 0;
-            int flags;
-            s = ds_infected(i, st, r.ipvv, it, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
-            P.infection_timer[i] = it;
-            if (st == 0) {
-                P.paralysis_timer[i] = pt;
-                if (pq != pq0) P.potentially_paralyzed[i] = pq;
-                if (flags) {
-                    atomicAdd(&A.new_potential[nd], 1);
-                    if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
-                }
-            }
-        }
-        sd = s;
-        if (r.e.y & (3u << 21)) {  // after the disease-state step (the reference's run order; it used the ipv_protected loaded before)
-            const uint32_t o = vaccine_draws(pp, i, nd, s, r.e.y);
+        if (ey & EF_WILD) paralysis_agent(pp, i, nd, r.ipvv, r.pt, r.pq);
+        if (ey & (EF_RI | EF_SIA)) {  // after the disease-state step (the reference's run order; it used the ipv_protected loaded before)
+            const uint32_t o = vaccine_draws(pp, i, nd, s, ey);
             s = (int8_t)(o & 0xFFu);
             vx = o >> 8;
             if (vx & 18u) {  // left S through a vaccine
                 efx = __float2ll_rn(r.rk * 1073741824.0f);
                 atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
+                P.disease_state[i] = s;
             }
         }
-        if (s != s0) P.disease_state[i] = s;
     }
-    // node-level counts, one group of same-node lanes at a time (one group except at a node boundary): only lanes whose
-    // agent changed class today have anything to add
+    // node-level counts, one group of same-node lanes at a time (one group except at a node boundary)
     uint32_t todo = __ballot_sync(LPK_FULL, valid);
     while (todo) {
         const int nd0 = __shfl_sync(LPK_FULL, nd, __ffs(todo) - 1);
@@ -496,34 +502,61 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
     }
 }
 
-// append the agents of mask m (bit 0 of byte k = agent idx0 + k) of state word nw; f carries the agents' flag bits (hit
-// << 4 | RI-eligible << 5 | SIA-eligible << 6 in byte k); returns how many
-__device__ __forceinline__ uint32_t entry_flags(uint32_t hits, uint32_t ri, uint32_t sia) { return (hits << 4) | (ri << 5) | (sia << 6); }
-__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t nw, uint32_t f, uint32_t m) {
-    const uint32_t comb = (nw & 0x0F0F0F0Fu) | f;
+// Disease-state step of a node-uniform quad on byte lanes (reference model.py:419-431): every exposed agent's timer
+// counts down and those at <= 0 turn infectious; every agent in the infected block (infectious before, or just turned)
+// counts its timer down and those at <= 0 recover.  nw0: state word after tick t-1's hits and tick t's deaths; et / it /
+// sw: the quad's exposure_timer, infection_timer and strain words.  Timers are written back here.
+struct DsQuad {
+    uint32_t nw, f, m;  // new state word; flag bytes of the agents that need the handler; their mask (bit 0 per byte)
+};
+// byte lanes by hand (the __v*4 intrinsics are emulated with ~10 instructions each): masks carry bit 0 of each byte
+__device__ __forceinline__ uint32_t bytes_le0(uint32_t x) {  // per byte, signed: byte <= 0  (zero, or bit 7 set)
+    const uint32_t nz = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 set iff the byte is not zero
+    return ((~nz | x) >> 7) & 0x01010101u;
+}
+__device__ __forceinline__ uint32_t bytes_dec(uint32_t x, uint32_t m) {  // per byte: x - m (m is 0 / 1), wrapping like int8
+    const uint32_t t = (x | 0x80808080u) - m;  // bit 7 forced: no borrow leaves a byte
+    return (t & 0x7F7F7F7Fu) | ((x ^ ~t) & 0x80808080u);
+}
+__device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t hits, uint32_t et, uint32_t it, uint32_t sw) {
+    const uint32_t K1 = 0x01010101u;
+    const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;  // state bytes are 0, 1, 2, 3 or 0xFF
+    const uint32_t tE = mE & bytes_le0(et);
+    const uint32_t mJ = mI | tE;
+    const uint32_t tI = mJ & bytes_le0(it);
+    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = bytes_dec(et, mE);
+    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = bytes_dec(it, mJ);
+    const uint32_t wild = mJ & ~(sw | (sw >> 1)) & ~hits;  // strain 0 of 0..3; a hit's strain is picked by the handler
+    DsQuad o;
+    o.nw = nw0 + tE + tI;
+    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (hits << 4) | (wild << 7);
+    o.m = tE | tI | wild | hits;
+    return o;
+}
+// append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain bytes; returns how many
+__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t f, uint32_t g, uint32_t m) {
     const int cnt = __popc(m);
     while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
         const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
-        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((comb >> bit) & 0xFFu) << 16));
+        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((f >> bit) & 0xFFu) << 16) | (((g >> bit) & 3u) << 24));
     }
     return cnt;
 }
 // the same for the two quads a lane owns in a row pair (B = A + 128 agents): one loop for both
-__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t nwA, uint32_t fA, uint32_t mA,
-                                           uint32_t nwB, uint32_t fB, uint32_t mB) {
-    const uint32_t combA = (nwA & 0x0F0F0F0Fu) | fA, combB = (nwB & 0x0F0F0F0Fu) | fB;
+__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t fA, uint32_t gA, uint32_t mA,
+                                           uint32_t fB, uint32_t gB, uint32_t mB) {
     uint32_t m = mA | (mB << 4);
     const int cnt = __popc(m);
     while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
         const bool rowB = (bit & 4) != 0;
-        const uint32_t comb = rowB ? combB : combA;
+        const uint32_t f = rowB ? fB : fA, g = rowB ? gB : gA;
         const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
         q[pos] = make_uint2(idxA + (uint32_t)(bit >> 3) + (rowB ? 128u : 0u),
-                            ((uint32_t)nd & 0xFFFFu) | (((comb >> (bit & 24)) & 0xFFu) << 16));
+                            ((uint32_t)nd & 0xFFFFu) | (((f >> (bit & 24)) & 0xFFu) << 16) | (((g >> (bit & 24)) & 3u) << 24));
     }
     return cnt;
 }
@@ -596,7 +629,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
         if (!valid) continue;
         const uint32_t w = load_b4(P.disease_state, b, valid);
         if ((w & 0x80808080u) == 0x80808080u) continue;  // nobody alive
-        uint32_t nw = w, hits = 0u, cand = 0u, elig = 0u, camp = 0u;
+        uint32_t nw = w, hits = 0u, cand = 0u, elig = 0u, camp = 0u, fl = 0u, sw = 0u;
         int nd = -1;
         bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
         if (fast) {
@@ -626,7 +659,13 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
                 const uint32_t dm = death_mask(dd, tick, nw);
                 if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, dm); nw = o.x; hits = o.y; }
             }
-            cand = mask_EI(nw);
+            if (mask_EI(nw)) {  // disease-state step of tick t on byte lanes
+                const DsQuad d = ds_quad(P, b, nw, hits, *reinterpret_cast<const uint32_t *>(P.exposure_timer + b),
+                                         *reinterpret_cast<const uint32_t *>(P.infection_timer + b), sw = *reinterpret_cast<const uint32_t *>(P.strain + b));
+                nw = d.nw; fl = d.f; cand = d.m;
+            } else {
+                fl = (nw & 0x03030303u) | (hits << 4);  // no E / I in the quad: no hit either
+            }
             uint32_t missed = 0u;
             if (kRI || kSIA) missed = *reinterpret_cast<const uint32_t *>(P.chronically_missed + b);
             if (kRI) elig = ri_timers_quad(pp, b, nw, missed, *reinterpret_cast<const uint2 *>(P.ri_timer + b));
@@ -635,7 +674,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
                                     (uint32_t)(A.sia_max_age - A.sia_min_age)) & mask_alive(nw) & ~missed;
         }
         if (nw != w) store_b4(P.disease_state, b, valid, nw);
-        mine += q_push(q, q_tail, (uint32_t)b, nd, nw, entry_flags(hits, elig, camp), cand | elig | camp);
+        mine += q_push(q, q_tail, (uint32_t)b, nd, fl | (elig << 5) | (camp << 6), sw, cand | elig | camp);
     }
     return mine;
 }
@@ -679,10 +718,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 template <bool kDeaths, bool kRI, bool kSIA>
 struct PassSmem {
-    static constexpr int kStages = kSIA ? ((kDeaths || kRI) ? 2 : 3) : ((kDeaths || kRI) ? 3 : 4);
-    static constexpr int kOffRisk = 256, kOffDod = 1280, kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
+    // a stage: state 256 | risk 1024 | exposure_timer 256 | infection_timer 256 | strain 256 | [date_of_death 1024]
+    //          | [chronically_missed 256] | [ri_timer 512] | [date_of_birth 1024]
+    static constexpr int kOffRisk = 256, kOffEt = 1280, kOffIt = 1536, kOffSt = 1792, kOffDod = 2048;
+    static constexpr int kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
     static constexpr int kOffDob = kOffMissed + ((kRI || kSIA) ? 256 : 0) + (kRI ? 512 : 0);
     static constexpr int kStageBytes = kOffDob + (kSIA ? 1024 : 0);
+    static constexpr int kFit = (113 * 1024 - LPK_WARPS * QCAP * 8 - 2048) / (LPK_WARPS * kStageBytes);  // two blocks per SM
+    static constexpr int kStages = kFit >= 4 ? 4 : (kFit < 1 ? 1 : kFit);
     static constexpr int kOffQueue = 0;
     static constexpr int kOffSlots = kOffQueue + LPK_WARPS * QCAP * 8;
     static constexpr int kOffBars = kOffSlots + LPK_WARPS * kStages * kStageBytes;
@@ -813,9 +856,12 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
                 const bool risk = tau > 0.f;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
                 const bool missed = kRI || camp;
-                mbar_arrive_expect_tx(bar, 256u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
+                mbar_arrive_expect_tx(bar, 1024u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
                                                (camp ? 1024u : 0u));
                 tma_load(dst, P.disease_state + a0, 256u, bar);
+                tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
+                tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
+                tma_load(dst + L::kOffSt, P.strain + a0, 256u, bar);
                 if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
                 if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
                 if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
@@ -835,46 +881,25 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         const float tau = __int_as_float(mt.y & 0x7FFFFFFF);
         const bool camp = kSIA && mt.y < 0;
         const unsigned char *src = slots + slot * L::kStageBytes;
-        uint32_t wA = 0u, wB = 0u, mA = 0u, mB = 0u;
-        float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA;
-        int4 dA = make_int4(0, 0, 0, 0), dB = dA, bA4 = dA, bB4 = dA;
-        uint2 tA = make_uint2(0u, 0u), tB = tA;
+        uint32_t wA = 0u, wB = 0u;
         if (tn >= 0) {
             wA = *reinterpret_cast<const uint32_t *>(src + lane * 4);
             wB = *reinterpret_cast<const uint32_t *>(src + 128 + lane * 4);
-            if (tau > 0.f) {
-                rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
-                rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
-            }
-            if (kDeaths) {
-                dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
-                dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
-            }
-            if (kRI || camp) {
-                mA = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + lane * 4);
-                mB = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + 128 + lane * 4);
-            }
-            if (kRI) {
-                tA = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + lane * 8);
-                tB = *reinterpret_cast<const uint2 *>(src + L::kOffTimer + 256 + lane * 8);
-            }
-            if (camp) {
-                bA4 = *reinterpret_cast<const int4 *>(src + L::kOffDob + lane * 16);
-                bB4 = *reinterpret_cast<const int4 *>(src + L::kOffDob + 512 + lane * 16);
-            }
         }
-        __syncwarp();
-        produce(s + NST, slot);
-        if (tn == -2) return false;
-        const int64_t gp = (int64_t)pair_of(s);
-        if (tn < 0) {
-            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, gp, n, count_prev, lane), lane);
+        if (tn < 0) {  // nothing was copied for this position
+            __syncwarp();
+            produce(s + NST, slot);
+            if (tn == -2) return false;
+            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)pair_of(s), n, count_prev, lane), lane);
             return true;
         }
+        const int64_t gp = (int64_t)pair_of(s);
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
         uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u;
         if (tau > 0.f && !(pp.debug & 2u)) {  // exposure trial of tick t-1
+            const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
+            const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
             const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
             uint32_t x[4];
             philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
@@ -887,23 +912,46 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
             }
         }
         if (kDeaths) {  // tick t
+            const int4 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
+            const int4 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
             const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
             if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, hA, dmA); nwA = o.x; hA = o.y; }
             if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = o.x; hB = o.y; }
         }
-        // exposed / infectious agents (fresh hits included): census of t-1, disease state and tally of t in the handler
-        // and so are the agents eligible for routine immunisation or the campaign: their draws follow their own disease-state step
-        const uint32_t cA = mask_EI(nwA), cB = mask_EI(nwB);
-        uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
-        if (kRI) { eA = ri_timers_quad(pp, bA, nwA, mA, tA); eB = ri_timers_quad(pp, bB, nwB, mB, tB); }
-        if (camp) {
-            sA = sia_age_mask(bA4, tick, sia_lo, sia_span) & mask_alive(nwA) & ~mA;
-            sB = sia_age_mask(bB4, tick, sia_lo, sia_span) & mask_alive(nwB) & ~mB;
+        // disease-state step of tick t on byte lanes; only class changes, the paralytic strain's daily step, fresh hits and
+        // vaccine-eligible agents go to the ring (their draws follow their own disease-state step)
+        uint32_t fA = (nwA & 0x03030303u) | (hA << 4), fB = (nwB & 0x03030303u) | (hB << 4), gA = 0u, gB = 0u, cA = hA, cB = hB;
+        if (mask_EI(nwA)) {
+            gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
+            const DsQuad d = ds_quad(P, bA, nwA, hA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA);
+            nwA = d.nw; fA = d.f; cA = d.m;
         }
+        if (mask_EI(nwB)) {
+            gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
+            const DsQuad d = ds_quad(P, bB, nwB, hB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB);
+            nwB = d.nw; fB = d.f; cB = d.m;
+        }
+        uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
+        if (kRI || camp) {
+            const uint32_t mA = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + lane * 4);
+            const uint32_t mB = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + 128 + lane * 4);
+            if (kRI) {
+                eA = ri_timers_quad(pp, bA, nwA, mA, *reinterpret_cast<const uint2 *>(src + L::kOffTimer + lane * 8));
+                eB = ri_timers_quad(pp, bB, nwB, mB, *reinterpret_cast<const uint2 *>(src + L::kOffTimer + 256 + lane * 8));
+            }
+            if (camp) {
+                sA = sia_age_mask(*reinterpret_cast<const int4 *>(src + L::kOffDob + lane * 16), tick, sia_lo, sia_span) & mask_alive(nwA) & ~mA;
+                sB = sia_age_mask(*reinterpret_cast<const int4 *>(src + L::kOffDob + 512 + lane * 16), tick, sia_lo, sia_span) & mask_alive(nwB) & ~mB;
+            }
+        }
+        __syncwarp();
+        produce(s + NST, slot);  // every read of the slot is done: re-arm it
         if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
         if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
-        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, nwA, entry_flags(hA, eA, sA), cA | eA | sA, nwB,
-                                    entry_flags(hB, eB, sB), cB | eB | sB), lane);
+        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, fA | (eA << 5) | (sA << 6), gA, cA | eA | sA,
+                                    fB | (eB << 5) | (sB << 6), gB, cB | eB | sB), lane);
         return true;
     };
 
@@ -1000,7 +1048,8 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
         pp.debug = (uint32_t)dbg;
     }
     REQUIRE(pp.unit_ctr, "tick_pass work counter allocation");
-    REQUIRE(ALIGNED(P.disease_state, 16) && (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
+    REQUIRE(ALIGNED(P.disease_state, 16) && ALIGNED(P.exposure_timer, 16) && ALIGNED(P.infection_timer, 16) && ALIGNED(P.strain, 16) &&
+                (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
             "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
     int rc;
