@@ -371,8 +371,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="agents per GPU (default: 220M, the Nigeria config)")
     ap.add_argument("--nodes", type=int, default=774)
-    ap.add_argument("--cpu-agents", type=int, default=10_000_000)
-    ap.add_argument("--cpu-ticks", type=int, default=4)
+    ap.add_argument("--cpu-agents", type=int, default=20_000_000)
+    ap.add_argument("--cpu-ticks", type=int, default=60)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,22 +21,24 @@ static inline DevRng dev_rng(const lpk_rng *r) {
 
 
 // Paralysis part of the infected block (reference model.py:432-452), paralytic strain 0 only: the gate fires once per
-// agent (potentially_paralyzed leaves -1) with one uniform; then the paralysis timer counts down.  flags bit 0 = newly
-// potentially paralysed, bit 1 = newly paralysed.
+// agent (when the paralysis timer has run out and potentially_paralyzed is still -1) with one uniform; then the
+// paralysis timer counts down.  flags bit 0 = newly potentially paralysed, bit 1 = newly paralysed.
+__device__ __forceinline__ void paralysis_gate(int64_t i, int8_t ipvv, int8_t &pq, int8_t &par, double p_paralysis, const DevRng &rng,
+                                               int &flags) {
+    if (ipvv == 0) {
+        pq = 1;
+        flags |= 1;
+        double u;
+        if (rng.u1) u = rng.u1[i];
+        else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
+        if (u < p_paralysis) { par = 1; flags |= 2; }
+    } else {
+        pq = 0;
+    }
+}
 __device__ __forceinline__ void paralysis_step(int64_t i, int8_t ipvv, int8_t &pt, int8_t &pq, int8_t &par, double p_paralysis,
                                                const DevRng &rng, int &flags) {
-    if (pt <= 0 && pq == -1) {
-        if (ipvv == 0) {
-            pq = 1;
-            flags |= 1;
-            double u;
-            if (rng.u1) u = rng.u1[i];
-            else { uint32_t x[4]; philox_agent(rng.seed, (uint64_t)i + rng.id_base, rng.tick, LPK_STAGE_PARALYSIS, x); u = u53(x[0], x[1]); }
-            if (u < p_paralysis) { par = 1; flags |= 2; }
-        } else {
-            pq = 0;
-        }
-    }
+    if (pt <= 0 && pq == -1) paralysis_gate(i, ipvv, pq, par, p_paralysis, rng, flags);
     pt = (int8_t)(pt - 1);
 }
 

@@ -272,7 +272,7 @@ __device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, u
 // entry = {agent index (tables hold < 2^32 slots), node | state << 16 | hit << 20}
 struct ActiveRegs {
     uint2 e;
-    int8_t pt, pq, ipvv;
+    int8_t ipvv;
     float inf, rk;
 };
 struct WarpAcc;
@@ -294,24 +294,21 @@ struct WarpQueue {
 // handle themselves.
 // Ring entry: x = agent index, y = node | F << 16 | strain << 24 with the flag byte
 //   F = state before tick t's disease-state step (bits 0-1) | E -> I today << 2 | I -> R today << 3 | exposure hit of t-1 << 4
-//       | RI-eligible << 5 | SIA-eligible << 6 | paralytic strain in the infected block today << 7
+//       | RI-eligible << 5 | SIA-eligible << 6 | paralysis gate fires today << 7
 // The streaming loop has already counted the timers down and written the new state (ds_quad): the handler only does what
-// needs scattered columns -- class-change bookkeeping, the paralysis step, the strain pick of a hit, the vaccine draws.
+// needs scattered columns -- class-change bookkeeping, the paralysis gate, the strain pick of a hit, the vaccine draws.
 #define EF_TE (1u << 18)
 #define EF_TI (1u << 19)
 #define EF_HIT (1u << 20)
 #define EF_RI (1u << 21)
 #define EF_SIA (1u << 22)
-#define EF_WILD (1u << 23)
+#define EF_GATE (1u << 23)
 __device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
     const lpk_people &P = pp.P;
     const int64_t i = (int64_t)e.x;
-    const bool wild = (e.y & EF_WILD) != 0u;
     ActiveRegs r;
     r.e = e;
-    r.pt = wild ? P.paralysis_timer[i] : (int8_t)0;
-    r.pq = wild ? P.potentially_paralyzed[i] : (int8_t)0;
-    r.ipvv = wild ? P.ipv_protected[i] : (int8_t)0;
+    r.ipvv = (e.y & EF_GATE) ? P.ipv_protected[i] : (int8_t)0;
     r.inf = (e.y & (EF_TE | EF_TI)) ? P.daily_infectivity[i] : 0.f;
     // a hit left S; a susceptible that is here for RI / SIA may leave it
     r.rk = ((e.y & EF_HIT) || ((e.y >> 16) & 3u) == 0u) ? P.acq_risk_multiplier[i] : 0.f;
@@ -422,16 +419,24 @@ __device__ __noinline__ uint32_t vaccine_draws(const PassParams &pp, int64_t i, 
     return (uint32_t)(uint8_t)s | (vx << 8);
 }
 
-// the paralysis step of one agent of the paralytic strain that is in the infected block today (out of line: rare)
-__device__ __noinline__ void paralysis_agent(const PassParams &pp, int64_t i, int nd, int8_t ipvv, int8_t pt, int8_t pq) {
+// paralysis of one agent of the paralytic strain in the infected block (out of line: rare).  gate_only: the streaming loop
+// found the gate open (timer run out, potentially_paralyzed still -1) and has counted the timer down itself; else the whole
+// step on the agent's columns (an agent exposed yesterday that is infectious today: its strain was not known there).
+__device__ __noinline__ void paralysis_agent(const PassParams &pp, int64_t i, int nd, int8_t ipvv, bool gate_only) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
-    const int8_t pq0 = pq;
-    int8_t par = 0;
+    int8_t pq = -1, par = 0;
     int flags = 0;
-    paralysis_step(i, ipvv, pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
-    P.paralysis_timer[i] = pt;
-    if (pq != pq0) P.potentially_paralyzed[i] = pq;
+    if (gate_only) {
+        paralysis_gate(i, ipvv, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
+        P.potentially_paralyzed[i] = pq;
+    } else {
+        int8_t pt = P.paralysis_timer[i];
+        const int8_t pq0 = pq = P.potentially_paralyzed[i];
+        paralysis_step(i, P.ipv_protected[i], pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
+        P.paralysis_timer[i] = pt;
+        if (pq != pq0) P.potentially_paralyzed[i] = pq;
+    }
     if (flags) {
         atomicAdd(&A.new_potential[nd], 1);
         if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
@@ -457,10 +462,9 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
             P.strain[i] = st;
             efx = __float2ll_rn(r.rk * 1073741824.0f);
             atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
-            if (st == 0 && (ey & EF_TE))  // infectious on the day after exposure, paralytic strain: its columns were not preloaded
-                paralysis_agent(pp, i, nd, P.ipv_protected[i], P.paralysis_timer[i], P.potentially_paralyzed[i]);
+            if (st == 0 && (ey & EF_TE)) paralysis_agent(pp, i, nd, 0, false);  // infectious on the day after exposure
         }
-        if (ey & EF_WILD) paralysis_agent(pp, i, nd, r.ipvv, r.pt, r.pq);
+        if (ey & EF_GATE) paralysis_agent(pp, i, nd, r.ipvv, true);
         if (ey & (EF_RI | EF_SIA)) {  // after the disease-state step (the reference's run order; it used the ipv_protected loaded before)
             const uint32_t o = vaccine_draws(pp, i, nd, s, ey);
             s = (int8_t)(o & 0xFFu);
@@ -505,7 +509,8 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
 // Disease-state step of a node-uniform quad on byte lanes (reference model.py:419-431): every exposed agent's timer
 // counts down and those at <= 0 turn infectious; every agent in the infected block (infectious before, or just turned)
 // counts its timer down and those at <= 0 recover.  nw0: state word after tick t-1's hits and tick t's deaths; et / it /
-// sw: the quad's exposure_timer, infection_timer and strain words.  Timers are written back here.
+// sw / pt / pq: the quad's exposure_timer, infection_timer, strain, paralysis_timer and potentially_paralyzed words.  Timers
+// are written back here.
 struct DsQuad {
     uint32_t nw, f, m;  // new state word; flag bytes of the agents that need the handler; their mask (bit 0 per byte)
 };
@@ -518,7 +523,8 @@ __device__ __forceinline__ uint32_t bytes_dec(uint32_t x, uint32_t m) {  // per 
     const uint32_t t = (x | 0x80808080u) - m;  // bit 7 forced: no borrow leaves a byte
     return (t & 0x7F7F7F7Fu) | ((x ^ ~t) & 0x80808080u);
 }
-__device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t hits, uint32_t et, uint32_t it, uint32_t sw) {
+__device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t hits, uint32_t et, uint32_t it, uint32_t sw,
+                                          uint32_t pt, uint32_t pq) {
     const uint32_t K1 = 0x01010101u;
     const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;  // state bytes are 0, 1, 2, 3 or 0xFF
     const uint32_t tE = mE & bytes_le0(et);
@@ -526,11 +532,19 @@ __device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32
     const uint32_t tI = mJ & bytes_le0(it);
     if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = bytes_dec(et, mE);
     if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = bytes_dec(it, mJ);
-    const uint32_t wild = mJ & ~(sw | (sw >> 1)) & ~hits;  // strain 0 of 0..3; a hit's strain is picked by the handler
+    // the paralytic strain (0 of 0..3) in the infected block: its paralysis timer counts down here too, and the agents whose
+    // gate opens today (timer run out, potentially_paralyzed still -1 = 0xFF) go to the handler.  A hit's strain is picked by
+    // the handler, which then runs the whole step.
+    const uint32_t wild = mJ & ~(sw | (sw >> 1)) & ~hits;
+    uint32_t gate = 0u;
+    if (wild) {
+        gate = wild & bytes_le0(pt) & (pq >> 7);
+        *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = bytes_dec(pt, wild);
+    }
     DsQuad o;
     o.nw = nw0 + tE + tI;
-    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (hits << 4) | (wild << 7);
-    o.m = tE | tI | wild | hits;
+    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (hits << 4) | (gate << 7);
+    o.m = tE | tI | gate | hits;
     return o;
 }
 // append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain bytes; returns how many
@@ -660,8 +674,11 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
                 if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, dm); nw = o.x; hits = o.y; }
             }
             if (mask_EI(nw)) {  // disease-state step of tick t on byte lanes
+                sw = *reinterpret_cast<const uint32_t *>(P.strain + b);
                 const DsQuad d = ds_quad(P, b, nw, hits, *reinterpret_cast<const uint32_t *>(P.exposure_timer + b),
-                                         *reinterpret_cast<const uint32_t *>(P.infection_timer + b), sw = *reinterpret_cast<const uint32_t *>(P.strain + b));
+                                         *reinterpret_cast<const uint32_t *>(P.infection_timer + b), sw,
+                                         *reinterpret_cast<const uint32_t *>(P.paralysis_timer + b),
+                                         *reinterpret_cast<const uint32_t *>(P.potentially_paralyzed + b));
                 nw = d.nw; fl = d.f; cand = d.m;
             } else {
                 fl = (nw & 0x03030303u) | (hits << 4);  // no E / I in the quad: no hit either
@@ -716,30 +733,30 @@ __device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool kDeaths, bool kRI, bool kSIA>
+template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
 struct PassSmem {
-    // a stage: state 256 | risk 1024 | exposure_timer 256 | infection_timer 256 | strain 256 | [date_of_death 1024]
-    //          | [chronically_missed 256] | [ri_timer 512] | [date_of_birth 1024]
-    static constexpr int kOffRisk = 256, kOffEt = 1280, kOffIt = 1536, kOffSt = 1792, kOffDod = 2048;
+    // a stage: state 256 | risk 1024 | exposure_timer 256 | infection_timer 256 | strain 256 | paralysis_timer 256
+    //          | potentially_paralyzed 256 | [date_of_death 1024] | [chronically_missed 256] | [ri_timer 512] | [date_of_birth 1024]
+    static constexpr int kOffRisk = 256, kOffEt = 1280, kOffIt = 1536, kOffSt = 1792, kOffPt = 2048, kOffPq = 2304, kOffDod = 2560;
     static constexpr int kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
     static constexpr int kOffDob = kOffMissed + ((kRI || kSIA) ? 256 : 0) + (kRI ? 512 : 0);
     static constexpr int kStageBytes = kOffDob + (kSIA ? 1024 : 0);
-    static constexpr int kFit = (113 * 1024 - LPK_WARPS * QCAP * 8 - 2048) / (LPK_WARPS * kStageBytes);  // two blocks per SM
+    static constexpr int kFit = (227 * 1024 / kOcc - 1024 - kWarps * QCAP * 8 - 2048) / (kWarps * kStageBytes);  // kOcc blocks per SM
     static constexpr int kStages = kFit >= 4 ? 4 : (kFit < 1 ? 1 : kFit);
     static constexpr int kOffQueue = 0;
-    static constexpr int kOffSlots = kOffQueue + LPK_WARPS * QCAP * 8;
-    static constexpr int kOffBars = kOffSlots + LPK_WARPS * kStages * kStageBytes;
-    static constexpr int kOffMeta = kOffBars + LPK_WARPS * kStages * 8;
-    static constexpr int kOffTail = kOffMeta + LPK_WARPS * kStages * 8;
-    static constexpr int kOffAcc = (kOffTail + LPK_WARPS * 4 + 15) & ~15;
-    static constexpr int kBytes = kOffAcc + LPK_WARPS * (int)sizeof(WarpAcc) + 32;
+    static constexpr int kOffSlots = kOffQueue + kWarps * QCAP * 8;
+    static constexpr int kOffBars = kOffSlots + kWarps * kStages * kStageBytes;
+    static constexpr int kOffMeta = kOffBars + kWarps * kStages * 8;
+    static constexpr int kOffTail = kOffMeta + kWarps * kStages * 8;
+    static constexpr int kOffAcc = (kOffTail + kWarps * 4 + 15) & ~15;
+    static constexpr int kBytes = kOffAcc + kWarps * (int)sizeof(WarpAcc) + 32;
     static_assert(kStages + 1 <= LPK_UNIT_PAIRS, "the producer may not run further ahead than one work unit");
-    static_assert(2 * kBytes <= 227 * 1024, "two blocks per SM");
+    static_assert(kOcc * (kBytes + 1024) <= 228 * 1024, "kOcc blocks per SM");
 };
 
-template <bool kDeaths, bool kRI, bool kSIA, int kOcc>
-__global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_constant__ PassParams pp) {
-    typedef PassSmem<kDeaths, kRI, kSIA> L;
+template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
+__global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_constant__ PassParams pp) {
+    typedef PassSmem<kDeaths, kRI, kSIA, kWarps, kOcc> L;
     constexpr int NST = L::kStages;
     extern __shared__ __align__(128) unsigned char smem[];
     const lpk_people &P = pp.P;
@@ -783,7 +800,7 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     // registers suffice.  The next run is claimed when the last unit of the current one is taken, a unit's worth of time
     // before it is needed, from a counter value read another unit earlier: no claim latency is ever waited for.
     const uint32_t kNoUnit = 0xFFFFFFFFu;
-    const uint32_t guide = 3u * gridDim.x * LPK_WARPS;
+    const uint32_t guide = 3u * gridDim.x * kWarps;
     uint32_t ua = kNoUnit, ub = kNoUnit;
     uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: the units of the current run not yet taken
     bool exhausted = false;                // warp-uniform: a claim came back beyond the last unit
@@ -856,12 +873,14 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
                 const bool risk = tau > 0.f;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
                 const bool missed = kRI || camp;
-                mbar_arrive_expect_tx(bar, 1024u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
+                mbar_arrive_expect_tx(bar, 1536u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
                                                (camp ? 1024u : 0u));
                 tma_load(dst, P.disease_state + a0, 256u, bar);
                 tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
                 tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
                 tma_load(dst + L::kOffSt, P.strain + a0, 256u, bar);
+                tma_load(dst + L::kOffPt, P.paralysis_timer + a0, 256u, bar);
+                tma_load(dst + L::kOffPq, P.potentially_paralyzed + a0, 256u, bar);
                 if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
                 if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
                 if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
@@ -924,13 +943,17 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
         if (mask_EI(nwA)) {
             gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
             const DsQuad d = ds_quad(P, bA, nwA, hA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA);
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA,
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPt + lane * 4),
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPq + lane * 4));
             nwA = d.nw; fA = d.f; cA = d.m;
         }
         if (mask_EI(nwB)) {
             gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
             const DsQuad d = ds_quad(P, bB, nwB, hB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB);
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB,
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPt + 128 + lane * 4),
+                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
             nwB = d.nw; fB = d.f; cB = d.m;
         }
         uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
@@ -980,18 +1003,18 @@ __global__ void __launch_bounds__(LPK_BLOCK, kOcc) k_tick_pass(const __grid_cons
     if (lane == 0) acc_flush(pp, Q.acc);
 }
 
-template <bool kDeaths, bool kRI, bool kSIA, int kOcc>
+template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
 static int launch_pass(const PassParams &pp, cudaStream_t st) {
-    typedef PassSmem<kDeaths, kRI, kSIA> L;
+    typedef PassSmem<kDeaths, kRI, kSIA, kWarps, kOcc> L;
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kSIA, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
+        CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kSIA, kWarps, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
                  "tick_pass smem");
         configured = true;
     }
-    const int grid = lpk_agent_grid(pp.P.capacity, kOcc);
+    const int grid = lpk_sm_count() * kOcc;
     CUDA_TRY(cudaMemsetAsync(pp.unit_ctr, 0, sizeof(uint32_t), st), "tick_pass work counter");
-    k_tick_pass<kDeaths, kRI, kSIA, kOcc><<<grid, LPK_BLOCK, L::kBytes, st>>>(pp);
+    k_tick_pass<kDeaths, kRI, kSIA, kWarps, kOcc><<<grid, kWarps * 32, L::kBytes, st>>>(pp);
     return LPK_OK;
 }
 // one 4-byte work counter per device, allocated on first use (the pass is launched on one stream per device)
@@ -1002,8 +1025,7 @@ static uint32_t *pass_unit_counter() {
     if (!ctr[dev] && cudaMalloc(&ctr[dev], 256) != cudaSuccess) ctr[dev] = nullptr;
     return ctr[dev];
 }
-// blocks per SM of the plain-day pass: 2 (no register cap, 100 KB of L1 left beside the rings) or 3 (80 registers: measured
-// 2x slower, diag_v10b); LPK_PASS_OCC overrides for experiments
+// shape of the plain-day pass: 2 blocks of 8 warps per SM, or (LPK_PASS_OCC=3, experiments) 3 blocks of 6 warps at <= 112 registers
 static int pass_occupancy() {
     static int occ = 0;
     if (!occ) {
@@ -1049,20 +1071,21 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     }
     REQUIRE(pp.unit_ctr, "tick_pass work counter allocation");
     REQUIRE(ALIGNED(P.disease_state, 16) && ALIGNED(P.exposure_timer, 16) && ALIGNED(P.infection_timer, 16) && ALIGNED(P.strain, 16) &&
+                ALIGNED(P.paralysis_timer, 16) && ALIGNED(P.potentially_paralyzed, 16) &&
                 (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
             "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
     int rc;
     if (sia) {
-        if (deaths && ri) rc = launch_pass<true, true, true, 2>(pp, st);
-        else if (deaths) rc = launch_pass<true, false, true, 2>(pp, st);
-        else if (ri) rc = launch_pass<false, true, true, 2>(pp, st);
-        else rc = launch_pass<false, false, true, 2>(pp, st);
-    } else if (deaths && ri) rc = launch_pass<true, true, false, 2>(pp, st);
-    else if (deaths) rc = launch_pass<true, false, false, 2>(pp, st);
-    else if (ri) rc = launch_pass<false, true, false, 2>(pp, st);
-    else if (pass_occupancy() == 2) rc = launch_pass<false, false, false, 2>(pp, st);
-    else rc = launch_pass<false, false, false, 3>(pp, st);
+        if (deaths && ri) rc = launch_pass<true, true, true, 8, 2>(pp, st);
+        else if (deaths) rc = launch_pass<true, false, true, 8, 2>(pp, st);
+        else if (ri) rc = launch_pass<false, true, true, 8, 2>(pp, st);
+        else rc = launch_pass<false, false, true, 8, 2>(pp, st);
+    } else if (deaths && ri) rc = launch_pass<true, true, false, 8, 2>(pp, st);
+    else if (deaths) rc = launch_pass<true, false, false, 8, 2>(pp, st);
+    else if (ri) rc = launch_pass<false, true, false, 8, 2>(pp, st);
+    else if (pass_occupancy() == 2) rc = launch_pass<false, false, false, 8, 2>(pp, st);
+    else rc = launch_pass<false, false, false, 6, 3>(pp, st);
     if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
     return LPK_OK;
