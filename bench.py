@@ -39,6 +39,9 @@ sys.path.insert(0, str(ROOT))
 HBM_FALLBACK_GBS = 6650.0
 BENCH_R0 = 1.1  # sets daily_infectivity in the synthetic table; see build_pars
 ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1
+# DRAM bytes per agent of one tick_pass launch from the committed ncu --set full capture of this workload at 2.2e8 agents
+# (profiles/r1_fused_v18_220M_summary.csv: dram__bytes_read.sum 2.321 GB + dram__bytes_write.sum 0.254 GB, tick 34)
+NCU_TRAFFIC_BYTES_PER_AGENT = (2.321415e9 + 0.254483e9) / 220_000_000
 
 # algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
 # (f_S = 0.93, f_E = f_I = 0.01 synthetic mix; derivations in DESIGN.md section 4)
@@ -63,38 +66,52 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every 5 ms through NVML while the timed region runs (nvidia-smi's own loop is
+    too coarse for a region of a few hundred ms; it is the fallback when NVML cannot be loaded)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz, self._stop_evt, self.source = index, [], set(), None, threading.Event(), "nvml"
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop_evt.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
         except Exception:  # noqa: BLE001 - clocks are diagnostics
-            pass
+            self.source = "nvidia-smi"
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                while not self._stop_evt.is_set():
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                    if len(out) >= 6:
+                        self.sm.append(float(out[0]))
+                        self.max_mhz = float(out[1])
+                        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                            if v.strip().lower().startswith("active"):
+                                self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop_evt.set()
+        self.join(timeout=15)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -339,7 +356,12 @@ def run_b200(args):
     achieved = algo / (mean_ms / 1e3) / 1e9
     kernel_share = {k: round(c * m / ms, 4) for k, (c, m) in kstats.items()}
     cpu_n = min(n_agents, args.cpu_agents)
-    cpu_value, threads, stage, cpu_secs = cpu_tick_loop(cpu_n, n_nodes, args.cpu_ticks, 1)
+    cpu_base = None
+    if world == 1:  # the CPU leg is reported at N = 1 only (rank 0's host cores)
+        cpu_value, threads, stage, cpu_secs = cpu_tick_loop(cpu_n, n_nodes, args.cpu_ticks, 1)
+        cpu_base = {"value": cpu_value, "unit": "agent-days/s", "cores": threads, "kind": "port",
+                    "sample": f"{cpu_n} agents x {n_nodes} nodes, {args.cpu_ticks} ticks ({cpu_secs:.1f} s)",
+                    "stage_seconds": {k: round(v, 4) for k, v in stage.items()}}
     line = {
         "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -350,12 +372,12 @@ def run_b200(args):
                    "parallelism": (f"node-sharded x{world}: {n_nodes * world} nodes, one NCCL all-reduce of the nodes x strains tally per tick"
                                    if world > 1 else "single GPU")},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
+                     "traffic": (NCU_TRAFFIC_BYTES_PER_AGENT * live0) if top == "tick_pass" else None,
+                     "traffic_source": "ncu --set full capture of one launch at 2.2e8 agents (profiles/r1_fused_v18_220M_summary.csv), scaled per agent",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
                      "tick_frac_of_14B_roofline": (ALGO_BYTES_PER_AGENT_TICK * value / world) / (peak * 1e9),
                      "kernel_share_of_step": kernel_share},
-        "cpu_baseline": {"value": cpu_value, "unit": "agent-days/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_n} agents x {n_nodes} nodes, {args.cpu_ticks} ticks ({cpu_secs:.1f} s)",
-                         "stage_seconds": {k: round(v, 4) for k, v in stage.items()}},
+        "cpu_baseline": cpu_base,
         "e2e": {"value": agents_total * K_ / e2e_s, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
                 "seconds": e2e_s, "note": "SEIR_ABM.to_device() + K step_tick() + to_host() from pinned host columns"},
         "gpu_launches": launches, "clocks": clocks,

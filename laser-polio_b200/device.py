@@ -22,6 +22,9 @@ import torch
 
 # results entries that are not [nt, nodes(, strains)] int32 rows
 HOST_ONLY_RESULTS = ("network",)
+# agent columns no kernel writes (the host copy stays current), and columns only births write (appended cohorts)
+READ_ONLY_COLUMNS = frozenset({"chronically_missed", "acq_risk_multiplier", "daily_infectivity"})
+APPEND_ONLY_COLUMNS = frozenset({"node_id", "date_of_birth", "date_of_death"})
 
 
 def _to_dev(arr: np.ndarray, device) -> torch.Tensor:
@@ -41,11 +44,13 @@ class DeviceState:
         self.res: dict[str, torch.Tensor] = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.dirty: set[str] = set()  # columns a custom component wrote on the device although the stock kernels never do
         self.upload()
 
     # ------------------------------------------------------------------ transfers
     def upload(self):
         people, results = self.sim.people, self.sim.results
+        self.count0 = int(people.count)  # slots in use at upload: append-only columns come back from here on
         for name, col in people.columns().items():
             self.cols[name] = _to_dev(col, self.device)
             self.h2d_bytes += col.nbytes
@@ -75,13 +80,30 @@ class DeviceState:
         self._net_src = None
         self.network = None
 
+    def mark_dirty(self, name: str):
+        """A custom component wrote column ``name`` on the device: bring it back whole at download()."""
+        self.dirty.add(name)
+
     def download(self):
-        """Bulk D2H of every agent column and every device-resident results array, in place."""
+        """Bulk D2H of every agent column the device may have changed and every device-resident results array, in
+        place.  Columns no kernel writes (risk, infectivity, chronically_missed) are not copied -- the host arrays
+        they were uploaded from are still current -- and columns only births write (node_id, date_of_birth,
+        date_of_death) come back for the cohorts appended since upload()."""
         people, results = self.sim.people, self.sim.results
         torch.cuda.current_stream().synchronize()
-        self.sync_count()
+        count = self.sync_count()
         for name, t in self.cols.items():
             host = getattr(people, name)
+            if name in self.dirty:
+                pass
+            elif name in READ_ONLY_COLUMNS:
+                continue
+            elif name in APPEND_ONLY_COLUMNS:
+                lo, hi = min(self.count0, count), count
+                if hi > lo:
+                    torch.from_numpy(host[lo:hi]).copy_(t[lo:hi], non_blocking=False)
+                    self.d2h_bytes += host[lo:hi].nbytes
+                continue
             torch.from_numpy(host).copy_(t, non_blocking=False)
             self.d2h_bytes += host.nbytes
         for name, t in self.res.items():
