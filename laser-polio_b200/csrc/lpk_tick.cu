@@ -264,6 +264,35 @@ __device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, u
     return hits;
 }
 
+// per-agent form of the pre-test: bit 0 of byte k set when agent k of the quad passes it
+__device__ __forceinline__ uint32_t pretest_mask(uint32_t xa, uint32_t xb, const float4 &rk, float tau16) {
+    const uint32_t k23 = 0x4B000000u;
+    const float c = 8388609.0f;
+    return ((__uint_as_float(__byte_perm(xa, k23, 0x7610)) < fmaf(rk.x, tau16, c)) ? 1u : 0u) |
+           ((__uint_as_float(__byte_perm(xa, k23, 0x7632)) < fmaf(rk.y, tau16, c)) ? 0x100u : 0u) |
+           ((__uint_as_float(__byte_perm(xb, k23, 0x7610)) < fmaf(rk.z, tau16, c)) ? 0x10000u : 0u) |
+           ((__uint_as_float(__byte_perm(xb, k23, 0x7632)) < fmaf(rk.w, tau16, c)) ? 0x1000000u : 0u);
+}
+// The exact exposure trial of tick t-1 for ONE susceptible agent (both Philox blocks regenerated): the streaming loop only
+// pre-tests and sends the few candidates to the ring, where 32 of them are decided at a time with all lanes busy
+// (profiles/r1_fused_v17_late_*: run in place it was 1-2 live lanes in 40 % of the iterations).
+__device__ __noinline__ bool exact_agent(const PassParams &pp, int64_t i, int nd, float rk) {
+    const lpk_tick_args &A = pp.A;
+    const float tau = __ldg(&A.q_prev[nd]);
+    if (!(tau > 0.f)) return false;
+    const uint64_t id = (uint64_t)i + A.id_base;
+    const uint64_t c = expose_ctr(id);
+    const int hw = expose_hw(id);
+    uint32_t h[4], l[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), h);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE_LO, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), l);
+    const uint32_t hs = (hw & 2) ? ((hw & 4) ? h[3] : h[1]) : ((hw & 4) ? h[2] : h[0]);
+    const uint32_t ls = (hw & 2) ? ((hw & 4) ? l[3] : l[1]) : ((hw & 4) ? l[2] : l[0]);
+    const uint32_t sh = 16u * (uint32_t)(hw & 1);
+    const uint32_t X = (((hs >> sh) & 0xFFFFu) << 16) | ((ls >> sh) & 0xFFFFu);
+    return expose_test(p_expose(__fmul_rn(rk, tau)), X);
+}
+
 // ---- active-agent queue -------------------------------------------------------------------------------------
 // E / I agents (and fresh exposure hits) are appended to the warp's shared-memory ring and, whenever 32 have
 // accumulated, processed one per lane with all lanes busy.  An entry carries everything the handler needs; the handler
@@ -292,7 +321,7 @@ struct WarpQueue {
 // (profiles/r1_fused_v10_postsia_*: 35 % of the stall samples sat in the handler waiting for its own loads).  Between the
 // two phases nobody else touches the agent: it is pushed once per pass, and the death / RI paths never push what they
 // handle themselves.
-// Ring entry: x = agent index, y = node | F << 16 | strain << 24 with the flag byte
+// Ring entry: x = agent index, y = node | F << 16 | strain << 24 | exposure candidate << 26 with the flag byte
 //   F = state before tick t's disease-state step (bits 0-1) | E -> I today << 2 | I -> R today << 3 | exposure hit of t-1 << 4
 //       | RI-eligible << 5 | SIA-eligible << 6 | paralysis gate fires today << 7
 // The streaming loop has already counted the timers down and written the new state (ds_quad): the handler only does what
@@ -303,6 +332,7 @@ struct WarpQueue {
 #define EF_RI (1u << 21)
 #define EF_SIA (1u << 22)
 #define EF_GATE (1u << 23)
+#define EF_CAND (1u << 26)  // susceptible that passed the pre-test of tick t-1's exposure trial: the handler decides
 __device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
     const lpk_people &P = pp.P;
     const int64_t i = (int64_t)e.x;
@@ -448,8 +478,24 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int64_t i = (int64_t)r.e.x;
-    const uint32_t ey = valid ? r.e.y : 0u;
+    uint32_t ey = valid ? r.e.y : 0u;
     const int nd = (int)(int16_t)(ey & 0xFFFFu);
+    if (ey & EF_CAND) {  // a susceptible that passed the pre-test of tick t-1's exposure trial
+        if (exact_agent(pp, i, nd, r.rk)) {
+            // exposed yesterday: the streaming loop saw a susceptible, so today's disease-state step (model.py:419-431) runs here
+            const int8_t et = P.exposure_timer[i];
+            uint32_t f = EF_HIT | (1u << 16);
+            if (et <= 0) {
+                const int8_t it = P.infection_timer[i];
+                f |= EF_TE | (it <= 0 ? EF_TI : 0u);
+                P.infection_timer[i] = (int8_t)(it - 1);
+                r.inf = P.daily_infectivity[i];
+            }
+            P.exposure_timer[i] = (int8_t)(et - 1);
+            ey |= f;
+            P.disease_state[i] = (int8_t)(1 + ((f >> 18) & 1u) + ((f >> 19) & 1u));
+        }
+    }
     const int8_t s0 = (int8_t)((ey >> 16) & 3u);
     const int8_t sd = (int8_t)(s0 + ((ey >> 18) & 1u) + ((ey >> 19) & 1u));  // state after this tick's disease-state step
     const bool hit = (ey & EF_HIT) != 0u;
@@ -547,14 +593,15 @@ __device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32
     o.m = tE | tI | gate | hits;
     return o;
 }
-// append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain bytes; returns how many
+// append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain (bits 0-1) and
+// exposure-candidate (bit 2) bytes; returns how many
 __device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t f, uint32_t g, uint32_t m) {
     const int cnt = __popc(m);
     while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
         const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
-        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((f >> bit) & 0xFFu) << 16) | (((g >> bit) & 3u) << 24));
+        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((f >> bit) & 0xFFu) << 16) | (((g >> bit) & 7u) << 24));
     }
     return cnt;
 }
@@ -570,7 +617,7 @@ __device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t id
         const uint32_t f = rowB ? fB : fA, g = rowB ? gB : gA;
         const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
         q[pos] = make_uint2(idxA + (uint32_t)(bit >> 3) + (rowB ? 128u : 0u),
-                            ((uint32_t)nd & 0xFFFFu) | (((f >> (bit & 24)) & 0xFFu) << 16) | (((g >> (bit & 24)) & 3u) << 24));
+                            ((uint32_t)nd & 0xFFFFu) | (((f >> (bit & 24)) & 0xFFu) << 16) | (((g >> (bit & 24)) & 7u) << 24));
     }
     return cnt;
 }
@@ -592,17 +639,22 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
 }
 
 // out-of-line part of a death in a node-uniform quad: the agents in mask dm die on tick t (after tick t-1's pending
-// exposure + census); returns {new state word, remaining hits}
-__device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t dm) {
+// exposure); returns {new state word, remaining hits | remaining exposure candidates << 1}
+__device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t cand, uint32_t dm) {
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        if (!((dm >> (8 * k)) & 1u)) continue;
-        const int8_t s = byte_of(nw, k);
-        if ((hits >> (8 * k)) & 1u) { expose_agent(pp, b + k, nd); hits &= ~(1u << (8 * k)); }
+        const uint32_t bit = 1u << (8 * k);
+        if (!(dm & bit)) continue;
+        int8_t s = byte_of(nw, k);
+        if (cand & bit) {  // the exposure trial of t-1 comes before the death of t: decide it now
+            cand &= ~bit;
+            if (exact_agent(pp, b + k, nd, pp.P.acq_risk_multiplier[b + k])) { hits |= bit; s = 1; }
+        }
+        if (hits & bit) { expose_agent(pp, b + k, nd); hits &= ~bit; }
         kill_agent(pp, b + k, nd, s);
         nw = set_byte(nw, k, -1);
     }
-    return make_uint2(nw, hits);
+    return make_uint2(nw, hits | (cand << 1));
 }
 __device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick, uint32_t w) {
     return ((d.x <= tick ? 1u : 0u) | (d.y <= tick ? 0x100u : 0u) | (d.z <= tick ? 0x10000u : 0u) | (d.w <= tick ? 0x1000000u : 0u)) &
@@ -671,7 +723,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
             if (kDeaths) {
                 const int4 dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
                 const uint32_t dm = death_mask(dd, tick, nw);
-                if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, dm); nw = o.x; hits = o.y; }
+                if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, 0u, dm); nw = o.x; hits = o.y; }
             }
             if (mask_EI(nw)) {  // disease-state step of tick t on byte lanes
                 sw = *reinterpret_cast<const uint32_t *>(P.strain + b);
@@ -915,8 +967,8 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         const int64_t gp = (int64_t)pair_of(s);
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
-        uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u;
-        if (tau > 0.f && !(pp.debug & 2u)) {  // exposure trial of tick t-1
+        uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u, xcA = 0u, xcB = 0u;
+        if (tau > 0.f && !(pp.debug & 2u)) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
             const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
             const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
             const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
@@ -924,18 +976,16 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
             const float tau16 = tau * 65536.0f;
             if (pretest_quad(x[0], x[1], rA, tau16) | pretest_quad(x[2], x[3], rB, tau16)) {
-                hA = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 0, x[0], x[1], nwA, rA, tau);
-                hB = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), 1, x[2], x[3], nwB, rB, tau);
-                nwA |= hA;  // S (0) -> E (1)
-                nwB |= hB;
+                xcA = pretest_mask(x[0], x[1], rA, tau16) & mask_S(nwA);
+                xcB = pretest_mask(x[2], x[3], rB, tau16) & mask_S(nwB);
             }
         }
         if (kDeaths) {  // tick t
             const int4 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
             const int4 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
             const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
-            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, hA, dmA); nwA = o.x; hA = o.y; }
-            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, hB, dmB); nwB = o.x; hB = o.y; }
+            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, 0u, xcA, dmA); nwA = o.x; xcA = (o.y >> 1) & 0x01010101u; }
+            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, 0u, xcB, dmB); nwB = o.x; xcB = (o.y >> 1) & 0x01010101u; }
         }
         // disease-state step of tick t on byte lanes; only class changes, the paralytic strain's daily step, fresh hits and
         // vaccine-eligible agents go to the ring (their draws follow their own disease-state step)
@@ -973,8 +1023,8 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         produce(s + NST, slot);  // every read of the slot is done: re-arm it
         if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
         if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
-        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, fA | (eA << 5) | (sA << 6), gA, cA | eA | sA,
-                                    fB | (eB << 5) | (sB << 6), gB, cB | eB | sB), lane);
+        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, fA | (eA << 5) | (sA << 6), (gA & 0x03030303u) | (xcA << 2),
+                                    cA | eA | sA | xcA, fB | (eB << 5) | (sB << 6), (gB & 0x03030303u) | (xcB << 2), cB | eB | sB | xcB), lane);
         return true;
     };
 
