@@ -613,70 +613,12 @@ __device__ double importation_multiplier(uint64_t seed, uint32_t node, uint32_t 
     }
 }
 
-// block = 32 destination nodes x 8 source slices
-__global__ void __launch_bounds__(256) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
-                                                       const int64_t *__restrict__ exposure_fx,
-                                                       const double *__restrict__ W, const double *__restrict__ rowsum,
-                                                       double season, const double *__restrict__ r0_scalars,
-                                                       const int32_t *__restrict__ alive, double zi, double disp_r,
-                                                       double *target, double *strain_cdf, double *prob, double *expected,
-                                                       uint64_t seed, uint32_t tick) {
-    __shared__ double part[8][LPK_MAX_STRAINS][32];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx;
-    double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
-    if (j < n) {
-        for (int i = ty; i < n; i += 8) {
-            long long b[LPK_MAX_STRAINS];
-            bool nz = false;
-#pragma unroll
-            for (int s = 0; s < LPK_MAX_STRAINS; ++s) { b[s] = (s < n_strains) ? beta_fx[(int64_t)i * n_strains + s] : 0; nz |= (b[s] != 0); }
-            if (!nz) continue;  // warp-uniform: rows without infectivity contribute nothing
-            const double w = W[(int64_t)i * n + j];
-#pragma unroll
-            for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += ((double)b[s] / LPK_FX_SCALE) * w;
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[ty][s][tx] = in[s];
-    __syncthreads();
-    if (ty != 0 || j >= n) return;
-    double P = 0.0, local = 0.0, p[LPK_MAX_STRAINS];
-    const double popn = fmax((double)alive[j], 1.0);
-    for (int s = 0; s < n_strains; ++s) {
-        double inc = 0.0;
-        for (int y = 0; y < 8; ++y) inc += part[y][s][tx];
-        const double pre = (double)beta_fx[(int64_t)j * n_strains + s] / LPK_FX_SCALE;
-        local += pre;
-        double b = pre + inc - pre * rowsum[j];
-        b = b * season * r0_scalars[j];
-        const double rate = b / popn;
-        p[s] = fmax(1.0 - exp(-rate), 0.0);
-        prob[(int64_t)j * n_strains + s] = p[s];
-        P += p[s];
-    }
-    double run = 0.0;
-    for (int s = 0; s < n_strains; ++s) {
-        run += (P > 0.0) ? p[s] / P : 0.0;
-        strain_cdf[(int64_t)j * n_strains + s] = run;
-    }
-    const double e = ((double)exposure_fx[j] / LPK_FX_SCALE) * P;  // model.py:1363
-    expected[j] = e;
-    double g = 1.0;
-    if (local == 0.0 && P > 0.0) g = importation_multiplier(seed, (uint32_t)j, tick, zi, disp_r);
-    target[j] = e * g;  // expected number of exposures the node's susceptibles must realise this tick
-}
-
-// tau[n]: sum over the node's susceptibles of (1 - exp(-risk * tau)) = target[n], on the risk histogram.
+// tau[j]: sum over the node's susceptibles of (1 - exp(-risk * tau)) = E, on the risk histogram.
 // Successive weighted sampling without replacement of K agents (the reference, model.py:1096-1122) selects agent i with
 // probability 1 - exp(-w_i tau), tau fixed by the count; solving for the EXPECTED count gives independent per-agent
 // trials with the same marginals and the same node mean.  One warp per node, 6 bins per lane; Newton from the left of a
 // concave increasing function converges monotonically.
-__global__ void __launch_bounds__(256) k_tx_solve_tau(int n, const int32_t *__restrict__ hist, const double *__restrict__ target,
-                                                       float *__restrict__ tau) {
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= n) return;
+__device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double E, int lane) {
     double h[LPK_RISK_BINS / 32], w[LPK_RISK_BINS / 32];
     double S = 0.0, Wsum = 0.0;
 #pragma unroll
@@ -691,7 +633,6 @@ __global__ void __launch_bounds__(256) k_tx_solve_tau(int n, const int32_t *__re
     for (int o = 16; o > 0; o >>= 1) { S += __shfl_xor_sync(LPK_FULL, S, o); Wsum += __shfl_xor_sync(LPK_FULL, Wsum, o); }
     S = __shfl_sync(LPK_FULL, S, 0);
     Wsum = __shfl_sync(LPK_FULL, Wsum, 0);
-    const double E = target[j];
     double t = 0.0;
     if (E > 0.0 && S > 0.0) {
         if (E >= S - 0.5) {
@@ -717,24 +658,110 @@ __global__ void __launch_bounds__(256) k_tx_solve_tau(int n, const int32_t *__re
             }
         }
     }
-    if (lane == 0) tau[j] = (float)(t > 3.0e38 ? 3.0e38 : t);
+    return (float)(t > 3.0e38 ? 3.0e38 : t);
+}
+
+// One block = 32 destination nodes x 32 source slices (1024 threads).  The infectivity tally is staged through shared
+// memory 1024 source rows at a time (the previous version re-read it from global in a dependent loop and took 41 us at 774
+// nodes: profiles/r1_v18_launches.csv); the block's 32 warps then solve tau for its 32 nodes.
+#define NM_ROWS 1024
+__global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
+                                                        const int64_t *__restrict__ exposure_fx,
+                                                        const double *__restrict__ W, const double *__restrict__ rowsum,
+                                                        double season, const double *__restrict__ r0_scalars,
+                                                        const int32_t *__restrict__ alive, double zi, double disp_r,
+                                                        double *target, double *strain_cdf, double *prob, double *expected,
+                                                        const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
+                                                        uint32_t tick) {
+    __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
+    __shared__ unsigned char snz[NM_ROWS];
+    __shared__ double stgt[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
+    for (int base = 0; base < n; base += NM_ROWS) {
+        const int rows = min(NM_ROWS, n - base);
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            bool nz = false;
+#pragma unroll
+            for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
+                const long long b = (s < n_strains) ? beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s] : 0;
+                nz |= (b != 0);
+                sbeta[s][threadIdx.x] = (double)b / LPK_FX_SCALE;
+            }
+            snz[threadIdx.x] = nz ? 1 : 0;
+        }
+        __syncthreads();
+        if (j < n) {
+#pragma unroll 4
+            for (int i = ty; i < rows; i += 32) {
+                if (!snz[i]) continue;  // warp-uniform: rows without infectivity contribute nothing
+                const double w = W[(int64_t)(base + i) * n + j];
+#pragma unroll
+                for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += sbeta[s][i] * w;
+            }
+        }
+    }
+    __syncthreads();
+    double *part = &sbeta[0][0];  // [ty][s][tx], 32 * 4 * 32 doubles = 32 KB
+#pragma unroll
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[(ty * LPK_MAX_STRAINS + s) * 32 + tx] = in[s];
+    __syncthreads();
+    if (ty == 0) {
+        double tgt = 0.0;
+        if (j < n) {
+            double P = 0.0, local = 0.0, p[LPK_MAX_STRAINS];
+            const double popn = fmax((double)alive[j], 1.0);
+            for (int s = 0; s < n_strains; ++s) {
+                double inc = 0.0;
+                for (int y = 0; y < 32; ++y) inc += part[(y * LPK_MAX_STRAINS + s) * 32 + tx];
+                const double pre = (double)beta_fx[(int64_t)j * n_strains + s] / LPK_FX_SCALE;
+                local += pre;
+                double b = pre + inc - pre * rowsum[j];
+                b = b * season * r0_scalars[j];
+                const double rate = b / popn;
+                p[s] = fmax(1.0 - exp(-rate), 0.0);
+                prob[(int64_t)j * n_strains + s] = p[s];
+                P += p[s];
+            }
+            double run = 0.0;
+            for (int s = 0; s < n_strains; ++s) {
+                run += (P > 0.0) ? p[s] / P : 0.0;
+                strain_cdf[(int64_t)j * n_strains + s] = run;
+            }
+            const double e = ((double)exposure_fx[j] / LPK_FX_SCALE) * P;  // model.py:1363
+            expected[j] = e;
+            double g = 1.0;
+            if (local == 0.0 && P > 0.0) g = importation_multiplier(seed, (uint32_t)j, tick, zi, disp_r);
+            tgt = e * g;  // expected number of exposures the node's susceptibles must realise this tick
+            target[j] = tgt;
+        }
+        stgt[tx] = tgt;
+    }
+    __syncthreads();
+    const int jn = blockIdx.x * 32 + ty;  // warp ty solves node jn
+    if (jn < n) {
+        const float t = solve_tau_warp(jn, hist, stgt[ty], tx);
+        if (tx == 0) tau[jn] = t;
+    }
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
-                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st) {
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done) {
     double *rowsum = ws, *target = ws + num_nodes;
-    k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
-    CUDA_TRY(cudaGetLastError(), "node_math rowsums");
+    if (!rowsums_done) {
+        k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
+        CUDA_TRY(cudaGetLastError(), "node_math rowsums");
+    }
     double r = nearbyint(dispersion);
     if (r < 1.0) r = 1.0;
-    k_tx_node_math<<<(num_nodes + 31) / 32, 256, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
-                                                          beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
-                                                          strain_cdf, prob, expected, seed, tick);
+    k_tx_node_math<<<(num_nodes + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
+                                                           beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
+                                                           strain_cdf, prob, expected, risk_hist, tau, seed, tick);
     CUDA_TRY(cudaGetLastError(), "node_math");
-    k_tx_solve_tau<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, risk_hist, target, tau);
-    CUDA_TRY(cudaGetLastError(), "node_math tau");
     return LPK_OK;
 }
 
@@ -749,5 +776,5 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
                 expected && ws, "tx_node_math null pointer");
     return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
                                 alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
-                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream));
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false);
 }

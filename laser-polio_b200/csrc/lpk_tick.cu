@@ -26,7 +26,7 @@ struct PassParams {
     lpk_people P;
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
-    uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches, 2 = skip the exposure trial
+    uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
 };
 
 #define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one iteration fit
@@ -798,8 +798,8 @@ struct PassSmem {
     static constexpr int kOffQueue = 0;
     static constexpr int kOffSlots = kOffQueue + kWarps * QCAP * 8;
     static constexpr int kOffBars = kOffSlots + kWarps * kStages * kStageBytes;
-    static constexpr int kOffMeta = kOffBars + kWarps * kStages * 8;
-    static constexpr int kOffTail = kOffMeta + kWarps * kStages * 8;
+    static constexpr int kOffMeta = (kOffBars + kWarps * kStages * 8 + 15) & ~15;
+    static constexpr int kOffTail = kOffMeta + kWarps * kStages * 16;
     static constexpr int kOffAcc = (kOffTail + kWarps * 4 + 15) & ~15;
     static constexpr int kBytes = kOffAcc + kWarps * (int)sizeof(WarpAcc) + 32;
     static_assert(kStages + 1 <= LPK_UNIT_PAIRS, "the producer may not run further ahead than one work unit");
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
 
     unsigned char *slots = smem + L::kOffSlots + warp * NST * L::kStageBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBars) + warp * NST;
-    int2 *meta = reinterpret_cast<int2 *>(smem + L::kOffMeta) + warp * NST;
+    int4 *meta = reinterpret_cast<int4 *>(smem + L::kOffMeta) + warp * NST;
     WarpQueue Q;
     Q.q = reinterpret_cast<uint2 *>(smem + L::kOffQueue) + warp * QCAP;
     Q.tail = reinterpret_cast<uint32_t *>(smem + L::kOffTail) + warp;
@@ -866,6 +866,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         claim_cnt = run_length(0u);
         claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
     }
+    uint32_t gp_looked = 0u;  // pair index of the position node_of looked up last
     auto pair_of = [&](int s) -> uint32_t {
         const uint32_t u = ((s >> LPK_UNIT_LOG) & 1) ? ub : ua;
         return u == kNoUnit ? kNoUnit : (u << LPK_UNIT_LOG) + (uint32_t)(s & (LPK_UNIT_PAIRS - 1));
@@ -893,6 +894,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             if ((s >> LPK_UNIT_LOG) & 1) ub = u; else ua = u;
         }
         const uint32_t gp = pair_of(s);
+        gp_looked = gp;
         if (gp >= total_pairs) return -2;  // kNoUnit included
         return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
     };
@@ -901,11 +903,14 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     bool tc_sia = false;
     const int sia_lo = kSIA ? A.sia_min_age : 0;
     const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
-    int tn_next = node_of(0);  // node of the next pair to be requested, loaded one request ahead
+    int tn_next = node_of(0);  // node (and pair index) of the next pair to be requested, looked up one request ahead
+    uint32_t gp_next = gp_looked;
     // request pair s into slot (warp-uniform; the elected lane talks to the TMA engine)
     auto produce = [&](int s, int slot) {
         const int tn = tn_next;
+        const uint32_t gp_req = gp_next;
         tn_next = node_of(s + 1);
+        gp_next = gp_looked;
         float tau = 0.f;
         if (tn >= 0) {
             if (tn != tc_node) {
@@ -917,10 +922,10 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         }
         const bool camp = kSIA && tn >= 0 && tc_sia;
         if (lane == 0) {
-            meta[slot] = make_int2(tn, __float_as_int(tau) | (camp ? (int)0x80000000u : 0));  // tau >= 0: the sign bit is free
+            meta[slot] = make_int4(tn, __float_as_int(tau) | (camp ? (int)0x80000000u : 0), (int)gp_req, 0);  // tau >= 0: the sign bit is free
             uint64_t *bar = &bars[slot];
             if (tn >= 0) {
-                const int64_t a0 = (int64_t)pair_of(s) * 256;
+                const int64_t a0 = (int64_t)gp_req * 256;
                 unsigned char *dst = slots + slot * L::kStageBytes;
                 const bool risk = tau > 0.f;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
@@ -947,7 +952,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     // process pair s from slot, then re-arm the slot with pair s + NST
     auto consume = [&](int s, int slot, uint32_t parity) -> bool {
         mbar_wait(&bars[slot], parity);
-        const int2 mt = meta[slot];
+        const int4 mt = meta[slot];
         const int tn = mt.x;
         const float tau = __int_as_float(mt.y & 0x7FFFFFFF);
         const bool camp = kSIA && mt.y < 0;
@@ -961,14 +966,14 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             __syncwarp();
             produce(s + NST, slot);
             if (tn == -2) return false;
-            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)pair_of(s), n, count_prev, lane), lane);
+            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)(uint32_t)mt.z, n, count_prev, lane), lane);
             return true;
         }
-        const int64_t gp = (int64_t)pair_of(s);
+        const int64_t gp = (int64_t)(uint32_t)mt.z;
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
         uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u, xcA = 0u, xcB = 0u;
-        if (tau > 0.f && !(pp.debug & 2u)) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
+        if (tau > 0.f) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
             const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
             const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
             const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
@@ -1168,10 +1173,19 @@ extern "C" int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, 
 }
 
 // ------------------------------------------------------------------ node-level epilogue of tick t
-__global__ void k_tick_epilogue(lpk_node_args a) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n == 0 && a.counts) a.counts[0] = a.counts[1];
+// one warp per node: the row sum of the network (coalesced) by all lanes, the node's bookkeeping by lane 0
+__global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ lpk_node_args a) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= a.n_nodes) return;
+    {
+        double sum = 0.0;
+        for (int j = lane; j < a.n_nodes; j += 32) sum += a.network[(int64_t)n * a.n_nodes + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(LPK_FULL, sum, o);
+        if (lane == 0) a.rowsum_ws[n] = sum;
+    }
+    if (lane != 0) return;
+    if (n == 0 && a.counts) a.counts[0] = a.counts[1];
     const int ns = a.n_strains;
     int d = 0, dpp = 0, dpar = 0;
     if (a.deaths) {
@@ -1225,7 +1239,7 @@ __global__ void k_tick_epilogue(lpk_node_args a) {
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
-                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st);
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
@@ -1242,9 +1256,9 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(a.E_cur && a.I_cur && a.E_snap && a.I_snap && a.tx_hits_by_strain &&
                 (!(a.flags & LPK_F_PENDING) || (a.E_by_strain_prev && a.I_by_strain_prev && a.E_prev && a.I_prev)), "tick_node E / I census");
     cudaStream_t st = as_stream(stream);
-    k_tick_epilogue<<<(a.n_nodes + 127) / 128, 128, 0, st>>>(a);
+    k_tick_epilogue<<<(a.n_nodes + 7) / 8, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
-                                a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st);
+                                a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true);
 }

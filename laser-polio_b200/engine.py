@@ -233,7 +233,7 @@ class FusedEngine:
         N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
         N.S_prev, N.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
         N.counts = dp(dev.counts)
-        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 4)
+        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 2)
         self.pending = True
 
     def _seasonality(self):

@@ -146,7 +146,7 @@ class LaunchStats:
     launching stream so bench.py can report each kernel's average device time inside the timed region."""
 
     KERNELS_PER_CALL = {"get_deaths": 1, "disease_state_step": 1, "fast_ri": 1, "fast_sia": 1, "tx_step_prep": 1,
-                        "tx_node_math": 3, "tx_infect": 1, "count_SEIRP": 2}
+                        "tx_node_math": 2, "tx_infect": 1, "count_SEIRP": 2}
 
     def __init__(self):
         self.reset()
