@@ -283,6 +283,8 @@ typedef struct lpk_node_args {
     int32_t *E_prev, *I_prev;                     /* rows t-1 */
     const int32_t *E_cur, *I_cur;
     int32_t *E_snap, *I_snap, *tx_hits_by_strain;
+    int32_t *any_cases; /* optional: one int32, set to 1 when some node still has an exposed or infectious agent after
+                           tick t's stages (the early-stop test of the next tick, model.py:789-795, reads it) */
     /* S and R census from the carried per-node counts (model.py:1476-1481 equivalent): with LPK_F_PENDING,
      *   S_prev[n] = S_snap[n] - tx_hits[n]   (susceptibles when tick t-1's stages ended, minus tick t-1's exposures)
      *   R_prev[n] += R_snap[n]               ("+=": on top of the pre-seeded non-agent immunes, model.py:1481)

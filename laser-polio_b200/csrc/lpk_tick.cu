@@ -1228,12 +1228,16 @@ __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ l
         }
         a.E_prev[n] = e; a.I_prev[n] = i;
     }
+    int cases = 0;
     for (int s = 0; s < ns; ++s) {
         const int64_t c = (int64_t)n * ns + s;
         a.tx_hits_by_strain[c] = 0;
-        a.E_snap[c] = a.E_cur[c];
-        a.I_snap[c] = a.I_cur[c];
+        const int e = a.E_cur[c], i = a.I_cur[c];
+        a.E_snap[c] = e;
+        a.I_snap[c] = i;
+        cases |= e | i;
     }
+    if (cases && a.any_cases) *a.any_cases = 1;
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,

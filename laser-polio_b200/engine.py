@@ -33,8 +33,6 @@ def eligible(sim) -> bool:
         return False  # subclassed / foreign components: call their step() as written
     if "DiseaseState_ABM" not in names or "Transmission_ABM" not in names:
         return False
-    if sim.pars["stop_if_no_cases"]:  # the early-stop test needs tick t-1's census before tick t starts
-        return False
     return getattr(sim, "fused", True) and sim.verbose < 3
 
 
@@ -71,6 +69,13 @@ class FusedEngine:
         self.expected = torch.zeros(n, dtype=torch.float64, device=d)
         self.rowsum = torch.zeros(2 * n, dtype=torch.float64, device=d)
         self.dummy_row = i32(n * max(ns, 1))  # sink for rows of components that are absent
+        # early stop (pars.stop_if_no_cases): "somebody is still exposed or infectious after tick t", one flag per tick,
+        # mirrored into pinned host memory with an event so that the host never waits for more than one tick
+        self.stop_rule = bool(sim.pars["stop_if_no_cases"])
+        if self.stop_rule:
+            self.cases_dev = i32(sim.nt + 1)
+            self.cases_host = torch.zeros(sim.nt + 1, dtype=torch.int32).pin_memory()
+            self.cases_evt = {}
         if sim.t > 0:  # resuming mid-run: re-base the incremental paralysis census on the last logged row
             self.cur_potp.copy_(dev.res["potentially_paralyzed"][sim.t - 1])
             self.cur_p.copy_(dev.res["paralyzed"][sim.t - 1])
@@ -122,6 +127,31 @@ class FusedEngine:
             return True
         ds = self.by_name["DiseaseState_ABM"]
         return t in ds.seed_schedule
+
+    def early_stop_rule(self, t):
+        """DiseaseState_ABM.step's early-stop test for tick t (reference model.py:789-795): nobody exposed or infectious
+        in tick t-1's census and no seed_schedule event left -> tick t is the last one.  After a fused tick t-1 the
+        census of t-1 is still in flight, but it has E or I agents exactly when some node had any after tick t-1's stages
+        (with nobody infectious there is no force of infection, so tick t-1's transmission adds nobody): the flag
+        lpk_tick_node(t-1) left, copied to pinned memory behind an event.  The host therefore runs at most one tick ahead
+        of the device instead of synchronising every tick."""
+        sim = self.sim
+        ds = self.by_name["DiseaseState_ABM"]
+        if any(ts > t for ts in ds.seed_schedule):
+            return
+        evt = self.cases_evt.get(t - 1)
+        if evt is not None:
+            evt.synchronize()
+            active = int(self.cases_host[t - 1]) > 0
+        else:  # tick t-1 ran through the components (or was tick 0): its census rows are complete on the device
+            ei = self.dev.res["E"][t - 1].sum() + self.dev.res["I"][t - 1].sum()
+            if sim.shard is not None and sim.shard.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(ei, group=sim.shard.group)
+            active = int(ei.item()) > 0
+        if not active:
+            sim.should_stop = True
 
     # ------------------------------------------------------------------ pipeline
     def drain(self):
@@ -233,7 +263,19 @@ class FusedEngine:
         N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
         N.S_prev, N.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
         N.counts = dp(dev.counts)
+        if self.stop_rule:
+            N.any_cases = self.cases_dev[t:].data_ptr()
         K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 2)
+        if self.stop_rule:
+            flag = self.cases_dev[t:t + 1]
+            if sim.shard is not None and sim.shard.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=sim.shard.group)
+            self.cases_host[t:t + 1].copy_(flag, non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record()
+            self.cases_evt = {t: evt}
         self.pending = True
 
     def _seasonality(self):
@@ -255,6 +297,8 @@ class FusedEngine:
             if sim.people.count != old and self.dev.tile_node is None:
                 self.rebuild_tiles(old)
         else:
+            if self.stop_rule:
+                self.early_stop_rule(t)
             with sim.perf_stats.start("FusedTick.step()"):
                 self.fused_tick(t)
         sim.t += 1

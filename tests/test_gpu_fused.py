@@ -168,6 +168,24 @@ def test_fused_equals_components_ri_without_vd_or_sia(lp, pyramid):
     assert fus.results.ri_vaccinated.sum() > 0
 
 
+def test_fused_early_stop_rule(lp, pyramid):
+    """pars.stop_if_no_cases (the reference's default, model.py:789-795): the fused engine stops on the same tick as the
+    component path -- the tick after the last exposed / infectious agent is gone -- without a device sync per tick."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    (ref, _), (fus, calls) = run_pair(lp, pyramid, comps, n_nodes=3, dur=200, r0=0.0001, sia_schedule=None, seed_schedule=None,
+                                      vx_prob_ri=None, init_prev=[0.003, 0.0, 0.001], stop_if_no_cases=True)
+    assert calls.get("tick_pass", 0) >= 20
+    assert ref.should_stop and fus.should_stop and ref.t == fus.t and 20 < fus.t < fus.nt
+    assert_identical(ref, fus)
+    assert fus.results.E[fus.t - 2].sum() + fus.results.I[fus.t - 2].sum() == 0  # the census that triggered the stop
+    # a pending seed_schedule event keeps the run alive past the extinction
+    (ref2, _), (fus2, _) = run_pair(lp, pyramid, comps, n_nodes=3, dur=200, r0=0.0001, sia_schedule=None, vx_prob_ri=None,
+                                    seed_schedule=[{"timestep": 190, "node_id": 1, "prevalence": 5}], init_prev=[0.003, 0.0, 0.001],
+                                    stop_if_no_cases=True)
+    assert ref2.t == fus2.t and fus2.t > 190
+    assert_identical(ref2, fus2)
+
+
 def test_step_tick_resume_after_to_host(lp, pyramid):
     """to_host() mid-run drains the pipeline; resuming gives the same answer as one uninterrupted run."""
     comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
