@@ -762,11 +762,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -779,9 +779,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 26)) __trap();  // a lost copy would otherwise hang the device; this turns it into an error
 }
-__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -921,17 +927,24 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             tau = tc_tau;
         }
         const bool camp = kSIA && tn >= 0 && tc_sia;
-        if (lane == 0) {
+        // What the copy engine needs goes through ONE warp reduction: its result lives in a uniform register, so the bulk
+        // copies below are issued straight from the uniform datapath by the elected lane.  With the operands in ordinary
+        // registers the compiler wraps every copy in an ELECT / R2UR x 4 / branch loop: 13 instructions per copy, 7-11
+        // copies per pair -- a third of the plain day's instructions (SASS of v19).
+        const uint32_t u = __reduce_max_sync(LPK_FULL, (gp_req & 0xFFFFFFu) | (tau > 0.f ? 1u << 24 : 0u) | (tn >= 0 ? 1u << 25 : 0u) |
+                                                           (camp ? 1u << 26 : 0u) | ((uint32_t)slot << 28));
+        if (elect_one()) {
             meta[slot] = make_int4(tn, __float_as_int(tau) | (camp ? (int)0x80000000u : 0), (int)gp_req, 0);  // tau >= 0: the sign bit is free
-            uint64_t *bar = &bars[slot];
-            if (tn >= 0) {
-                const int64_t a0 = (int64_t)gp_req * 256;
-                unsigned char *dst = slots + slot * L::kStageBytes;
-                const bool risk = tau > 0.f;
+            const uint32_t uslot = u >> 28;
+            const uint32_t bar = smem_u32(bars) + uslot * 8u;
+            if (u & (1u << 25)) {
+                const int64_t a0 = (int64_t)(u & 0xFFFFFFu) * 256;
+                const uint32_t dst = smem_u32(slots) + uslot * (uint32_t)L::kStageBytes;
+                const bool risk = (u & (1u << 24)) != 0u, ucamp = kSIA && (u & (1u << 26)) != 0u;
                 fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
-                const bool missed = kRI || camp;
+                const bool missed = kRI || ucamp;
                 mbar_arrive_expect_tx(bar, 1536u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
-                                               (camp ? 1024u : 0u));
+                                               (ucamp ? 1024u : 0u));
                 tma_load(dst, P.disease_state + a0, 256u, bar);
                 tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
                 tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
@@ -942,7 +955,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                 if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
                 if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
                 if (kRI) tma_load(dst + L::kOffTimer, P.ri_timer + a0, 512u, bar);
-                if (camp) tma_load(dst + L::kOffDob, P.date_of_birth + a0, 1024u, bar);
+                if (ucamp) tma_load(dst + L::kOffDob, P.date_of_birth + a0, 1024u, bar);
             } else {
                 mbar_arrive(bar);
             }
