@@ -593,6 +593,27 @@ __device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32
     o.m = tE | tI | gate | hits;
     return o;
 }
+// The same step without a branch, for the streaming loop: the two quads a lane owns run through it back to back, so the
+// compiler interleaves two independent dependency chains (the pass is bound by fixed-latency dependencies, not by issue
+// slots: profiles/r1_fused_v19_220M_*: stall_wait 2.2 cycles per instruction at 4 warps per scheduler).  No hits here.
+__device__ __forceinline__ DsQuad ds_quad_flat(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t et, uint32_t it, uint32_t sw,
+                                               uint32_t pt, uint32_t pq) {
+    const uint32_t K1 = 0x01010101u;
+    const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;
+    const uint32_t tE = mE & bytes_le0(et);
+    const uint32_t mJ = mI | tE;
+    const uint32_t tI = mJ & bytes_le0(it);
+    const uint32_t wild = mJ & ~(sw | (sw >> 1));
+    const uint32_t gate = wild & bytes_le0(pt) & (pq >> 7);
+    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = bytes_dec(et, mE);
+    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = bytes_dec(it, mJ);
+    if (wild) *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = bytes_dec(pt, wild);
+    DsQuad o;
+    o.nw = nw0 + tE + tI;
+    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (gate << 7);
+    o.m = tE | tI | gate;
+    return o;
+}
 // append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain (bits 0-1) and
 // exposure-candidate (bit 2) bytes; returns how many
 __device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t f, uint32_t g, uint32_t m) {
@@ -985,7 +1006,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         const int64_t gp = (int64_t)(uint32_t)mt.z;
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
-        uint32_t nwA = wA, nwB = wB, hA = 0u, hB = 0u, xcA = 0u, xcB = 0u;
+        uint32_t nwA = wA, nwB = wB, xcA = 0u, xcB = 0u;
         if (tau > 0.f) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
             const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
             const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
@@ -1007,22 +1028,20 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         }
         // disease-state step of tick t on byte lanes; only class changes, the paralytic strain's daily step, fresh hits and
         // vaccine-eligible agents go to the ring (their draws follow their own disease-state step)
-        uint32_t fA = (nwA & 0x03030303u) | (hA << 4), fB = (nwB & 0x03030303u) | (hB << 4), gA = 0u, gB = 0u, cA = hA, cB = hB;
-        if (mask_EI(nwA)) {
+        uint32_t fA = nwA & 0x03030303u, fB = nwB & 0x03030303u, gA = 0u, gB = 0u, cA = 0u, cB = 0u;
+        if (mask_EI(nwA) | mask_EI(nwB)) {
             gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
-            const DsQuad d = ds_quad(P, bA, nwA, hA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA,
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPt + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPq + lane * 4));
-            nwA = d.nw; fA = d.f; cA = d.m;
-        }
-        if (mask_EI(nwB)) {
             gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
-            const DsQuad d = ds_quad(P, bB, nwB, hB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB,
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPt + 128 + lane * 4),
-                                     *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
-            nwB = d.nw; fB = d.f; cB = d.m;
+            const DsQuad dA = ds_quad_flat(P, bA, nwA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA,
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPt + lane * 4),
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPq + lane * 4));
+            const DsQuad dB = ds_quad_flat(P, bB, nwB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB,
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPt + 128 + lane * 4),
+                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
+            nwA = dA.nw; fA = dA.f; cA = dA.m;
+            nwB = dB.nw; fB = dB.f; cB = dB.m;
         }
         uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
         if (kRI || camp) {
