@@ -1007,29 +1007,12 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         const int nd = tn;
         const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
         uint32_t nwA = wA, nwB = wB, xcA = 0u, xcB = 0u;
-        if (tau > 0.f) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
-            const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
-            const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
-            const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
-            uint32_t x[4];
-            philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
-            const float tau16 = tau * 65536.0f;
-            if (pretest_quad(x[0], x[1], rA, tau16) | pretest_quad(x[2], x[3], rB, tau16)) {
-                xcA = pretest_mask(x[0], x[1], rA, tau16) & mask_S(nwA);
-                xcB = pretest_mask(x[2], x[3], rB, tau16) & mask_S(nwB);
-            }
-        }
-        if (kDeaths) {  // tick t
-            const int4 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
-            const int4 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
-            const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
-            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, 0u, xcA, dmA); nwA = o.x; xcA = (o.y >> 1) & 0x01010101u; }
-            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, 0u, xcB, dmB); nwB = o.x; xcB = (o.y >> 1) & 0x01010101u; }
-        }
-        // disease-state step of tick t on byte lanes; only class changes, the paralytic strain's daily step, fresh hits and
-        // vaccine-eligible agents go to the ring (their draws follow their own disease-state step)
-        uint32_t fA = nwA & 0x03030303u, fB = nwB & 0x03030303u, gA = 0u, gB = 0u, cA = 0u, cB = 0u;
-        if (mask_EI(nwA) | mask_EI(nwB)) {
+        uint32_t fA = 0u, fB = 0u, gA = 0u, gB = 0u, cA = 0u, cB = 0u;
+        // disease-state step of tick t on byte lanes, both rows back to back and without a branch, in the same basic block
+        // as the Philox rounds of the exposure trial: the pass is bound by fixed-latency dependencies (stall_wait 2.2 cycles
+        // per instruction at 4 warps per scheduler), and these are three independent chains.  Only class changes, the
+        // paralytic strain's gate and vaccine-eligible agents go to the ring (their draws follow their own step).
+        auto ds_both = [&]() {
             gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
             gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
             const DsQuad dA = ds_quad_flat(P, bA, nwA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
@@ -1042,6 +1025,30 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
             nwA = dA.nw; fA = dA.f; cA = dA.m;
             nwB = dB.nw; fB = dB.f; cB = dB.m;
+        };
+        if (tau > 0.f) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
+            const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
+            const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
+            const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
+            uint32_t x[4];
+            philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
+            const uint32_t sA0 = mask_S(nwA), sB0 = mask_S(nwB);  // susceptible at the end of tick t-1
+            if (!kDeaths) ds_both();
+            const float tau16 = tau * 65536.0f;
+            if (pretest_quad(x[0], x[1], rA, tau16) | pretest_quad(x[2], x[3], rB, tau16)) {
+                xcA = pretest_mask(x[0], x[1], rA, tau16) & sA0;
+                xcB = pretest_mask(x[2], x[3], rB, tau16) & sB0;
+            }
+        } else if (!kDeaths) {
+            ds_both();
+        }
+        if (kDeaths) {  // tick t
+            const int4 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
+            const int4 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
+            const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
+            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, 0u, xcA, dmA); nwA = o.x; xcA = (o.y >> 1) & 0x01010101u; }
+            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, 0u, xcB, dmB); nwB = o.x; xcB = (o.y >> 1) & 0x01010101u; }
+            ds_both();
         }
         uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
         if (kRI || camp) {
