@@ -19,14 +19,18 @@
 //   * everything rare (a hit, a death, an RI-eligible agent, a node boundary) lives in __noinline__ functions.
 #include <cstdlib>
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched from the driver at run time, liblpk does not link libcuda)
+
 #include "lpk_host.cuh"
 #include "lpk_stages.cuh"
 
 struct PassParams {
+    CUtensorMap tmap;    // the six byte columns of the disease state as ONE 2-D tensor [column, agent] (use_tmap)
     lpk_people P;
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
     uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
+    uint32_t use_tmap;   // the byte columns lie at one constant stride (device.DeviceState's arena): one tensor copy per pair
 };
 
 #define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one iteration fit
@@ -804,6 +808,11 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// [6 columns, 256 agents] of the byte-column tensor starting at agent a0 -> 1536 contiguous bytes
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *map, uint32_t a0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(a0), "r"(0), "r"(bar) : "memory");
+}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -814,9 +823,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
 struct PassSmem {
-    // a stage: state 256 | risk 1024 | exposure_timer 256 | infection_timer 256 | strain 256 | paralysis_timer 256
-    //          | potentially_paralyzed 256 | [date_of_death 1024] | [chronically_missed 256] | [ri_timer 512] | [date_of_birth 1024]
-    static constexpr int kOffRisk = 256, kOffEt = 1280, kOffIt = 1536, kOffSt = 1792, kOffPt = 2048, kOffPq = 2304, kOffDod = 2560;
+    // a stage: state 256 | exposure_timer 256 | infection_timer 256 | strain 256 | paralysis_timer 256 | potentially_paralyzed 256
+    //          (= the [6, 256] box of the tensor copy) | risk 1024 | [date_of_death 1024] | [chronically_missed 256] | [ri_timer 512]
+    //          | [date_of_birth 1024]
+    static constexpr int kOffEt = 256, kOffIt = 512, kOffSt = 768, kOffPt = 1024, kOffPq = 1280, kOffRisk = 1536, kOffDod = 2560;
     static constexpr int kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
     static constexpr int kOffDob = kOffMissed + ((kRI || kSIA) ? 256 : 0) + (kRI ? 512 : 0);
     static constexpr int kStageBytes = kOffDob + (kSIA ? 1024 : 0);
@@ -966,12 +976,16 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                 const bool missed = kRI || ucamp;
                 mbar_arrive_expect_tx(bar, 1536u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
                                                (ucamp ? 1024u : 0u));
-                tma_load(dst, P.disease_state + a0, 256u, bar);
-                tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
-                tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
-                tma_load(dst + L::kOffSt, P.strain + a0, 256u, bar);
-                tma_load(dst + L::kOffPt, P.paralysis_timer + a0, 256u, bar);
-                tma_load(dst + L::kOffPq, P.potentially_paralyzed + a0, 256u, bar);
+                if (pp.use_tmap) {
+                    tma_load_box(dst, &pp.tmap, (u & 0xFFFFFFu) << 8, bar);
+                } else {
+                    tma_load(dst, P.disease_state + a0, 256u, bar);
+                    tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
+                    tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
+                    tma_load(dst + L::kOffSt, P.strain + a0, 256u, bar);
+                    tma_load(dst + L::kOffPt, P.paralysis_timer + a0, 256u, bar);
+                    tma_load(dst + L::kOffPq, P.potentially_paralyzed + a0, 256u, bar);
+                }
                 if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
                 if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
                 if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
@@ -1119,6 +1133,47 @@ static uint32_t *pass_unit_counter() {
     if (!ctr[dev] && cudaMalloc(&ctr[dev], 256) != cudaSuccess) ctr[dev] = nullptr;
     return ctr[dev];
 }
+// The byte columns of the disease state as one 2-D uint8 tensor [6 columns, capacity agents]: possible when the caller
+// allocated them at one constant stride, in this order (device.DeviceState does); one tensor copy per pair then replaces six
+// bulk copies.  Encoded once per (base, stride, capacity); any failure just leaves the per-column copies in charge.
+typedef CUresult (*lpk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool pass_tensor_map(const lpk_people &P, CUtensorMap *out) {
+    static lpk_encode_tiled_fn encode = nullptr;
+    static bool looked = false;
+    static struct { const void *base; int64_t stride, capacity; CUtensorMap map; bool ok; } cache = {nullptr, 0, 0, {}, false};
+    const char *env = getenv("LPK_PASS_TMAP");
+    if (env && env[0] == '0') return false;
+    const int8_t *cols[6] = {P.disease_state, P.exposure_timer, P.infection_timer, P.strain, P.paralysis_timer, P.potentially_paralyzed};
+    const int64_t stride = cols[1] - cols[0];
+    if (stride < P.capacity || (stride & 15) || P.capacity >= (1ll << 31)) return false;
+    for (int k = 1; k < 6; ++k)
+        if (cols[k] - cols[k - 1] != stride) return false;
+    if (cache.base == cols[0] && cache.stride == stride && cache.capacity == P.capacity) {
+        if (cache.ok) *out = cache.map;
+        return cache.ok;
+    }
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<lpk_encode_tiled_fn>(fn);
+        else
+            (void)cudaGetLastError();
+    }
+    cache.base = cols[0]; cache.stride = stride; cache.capacity = P.capacity; cache.ok = false;
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)P.capacity, 6}, strides[1] = {(cuuint64_t)stride};
+    const cuuint32_t box[2] = {256, 6}, estr[2] = {1, 1};
+    cache.ok = encode(&cache.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(cols[0]), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (cache.ok) *out = cache.map;
+    return cache.ok;
+}
+
 // shape of the plain-day pass: 2 blocks of 8 warps per SM, or (LPK_PASS_OCC=3, experiments) 3 blocks of 6 warps at <= 112 registers
 static int pass_occupancy() {
     static int occ = 0;
@@ -1158,6 +1213,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     pp.P = P;
     pp.A = A;
     pp.unit_ctr = pass_unit_counter();
+    pp.use_tmap = pass_tensor_map(P, &pp.tmap) ? 1u : 0u;
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("LPK_PASS_DEBUG"); dbg = e ? atoi(e) : 0; }
