@@ -334,6 +334,70 @@ typedef struct lpk_births_args {
 
 int lpk_vd_births(const lpk_births_args *args, void *stream);
 
+/* ---- Population initialisation in HBM -------------------------------------------------------
+ * The reference draws every per-agent column on the host at construction.  Each entry below replaces one of those
+ * blocks with a kernel whose output is a pure function of (seed, agent id = slot + id_base, stage): Philox4x32-10,
+ * counter = (id, block, stage), 53-bit uniforms taken two words at a time.  Slices [start, end) can be drawn in any
+ * order and on any number of GPUs with the same result.  oracle/lp_oracle_init.c restates every sampler. */
+#define LPK_STAGE_INIT_HET 16u
+#define LPK_STAGE_INIT_EXP 17u
+#define LPK_STAGE_INIT_INF 18u
+#define LPK_STAGE_INIT_PAR 19u
+#define LPK_STAGE_INIT_AGE 20u
+#define LPK_STAGE_INIT_LIFE 21u
+#define LPK_STAGE_INIT_RI 22u
+#define LPK_STAGE_INIT_MISSED 23u
+
+/* the lp.* distributions of reference distributions.py:17-135 (host objects ``Distribution(dist_type, **pars)``) */
+#define LPK_DIST_CONSTANT 0    /* a = value */
+#define LPK_DIST_EXPONENTIAL 1 /* a = scale */
+#define LPK_DIST_GAMMA 2       /* a = shape, b = scale */
+#define LPK_DIST_LOGNORMAL 3   /* a, b = mu, sigma of the underlying normal (the host converts lp.lognormal's mean / sigma) */
+#define LPK_DIST_NORMAL 4      /* a = mean, b = std */
+#define LPK_DIST_POISSON 5     /* a = lam */
+#define LPK_DIST_UNIFORM 6     /* integers in [a, b)  (np.random.randint) */
+typedef struct lpk_dist {
+    int32_t kind;
+    double a, b;
+} lpk_dist;
+
+/* populate_heterogeneous_values(start, end, acq_risk_out, infectivity_out, pars), reference model.py:816-866:
+ * (z0, z1) standard normal, zc = rho * z0 + sqrt(1 - rho^2) * z1;  acq_risk = exp(mu_ln + sigma_ln * z0);
+ * infectivity = gamma.ppf(norm.cdf(zc), a = 1, scale = scale_gamma) = -scale_gamma * log(erfc(zc / sqrt 2) / 2).
+ * heterogeneity == 0: acq_risk = 1, infectivity = mean_gamma (pars.individual_heterogeneity False). */
+int lpk_init_heterogeneity(int64_t start, int64_t end, float *acq_risk_out, float *infectivity_out, double mu_ln, double sigma_ln,
+                           double scale_gamma, double rho, int32_t heterogeneity, double mean_gamma, uint64_t seed, uint64_t id_base,
+                           void *stream);
+
+/* DiseaseState_ABM.__init__ timers, reference model.py:571-587: exposure_timer = clip(int8(dur_exp), 0, 127),
+ * infection_timer likewise, paralysis_timer = int8(clip(t_to_paralysis - exposure_timer, 0, min(infection_timer, 127))). */
+int lpk_init_timers(int64_t start, int64_t end, int8_t *exposure_timer, int8_t *infection_timer, int8_t *paralysis_timer,
+                    const lpk_dist *dur_exp, const lpk_dist *dur_inf, const lpk_dist *t_to_paralysis, uint64_t seed, uint64_t id_base,
+                    void *stream);
+
+/* VitalDynamics_ABM._initialize_ages_and_births / _initialize_deaths and RI_ABM._initialize_people_fields, reference
+ * model.py:1578-1596, 1605-1611, 1893-1894, fused: age bin ~ pyramid counts (inverse CDF), age = randint(lo, hi) days
+ * (0 -> 1), date_of_birth = -age; date_of_death = KaplanMeier age at death given the age (laser-core, restated in
+ * core.py) - age; ri_timer = int16(int32(date_of_birth + U(42, 98))).  date_of_death / ri_timer may be NULL. */
+typedef struct lpk_demog_args {
+    int64_t start, end;
+    int32_t *date_of_birth, *date_of_death;
+    int16_t *ri_timer;
+    const double *bin_cdf;             /* device [n_bins] cumulative pyramid counts */
+    const int32_t *bin_lo, *bin_hi;    /* device [n_bins] age range of the bin in days: [lo, hi) */
+    int32_t n_bins;
+    const int64_t *cum_deaths;         /* device [max_year + 2]: cum_deaths[y] = deaths before age y (leading 0) */
+    int32_t max_year;
+    uint64_t seed, id_base;
+} lpk_demog_args;
+int lpk_init_demography(const lpk_demog_args *args, void *stream);
+
+/* chronically_missed, reference model.py:154-159: exactly n_missed of the n agents, uniformly without replacement
+ * (the n_missed smallest 64-bit Philox keys; found by a 4-pass radix select that never stores the keys).
+ * ws: device scratch of LPK_MISSED_WS_WORDS uint32, 8-byte aligned. */
+#define LPK_MISSED_WS_WORDS (65536 + 4)
+int lpk_init_missed(int64_t n, int64_t n_missed, uint8_t *chronically_missed, uint64_t seed, uint64_t id_base, uint32_t *ws, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ EXPORTS = (
     "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
     "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
     "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births",
+    "lpk_init_heterogeneity", "lpk_init_timers", "lpk_init_demography", "lpk_init_missed",
 )
 
 
@@ -160,6 +161,25 @@ class BirthsArgs(C.Structure):
         ("acq_risk_multiplier", _VP), ("sus", _VP), ("exposure_fx", _VP), ("risk_hist", _VP),
     ]
 
+
+class Dist(C.Structure):
+    """struct lpk_dist"""
+
+    _fields_ = [("kind", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
+class DemogArgs(C.Structure):
+    """struct lpk_demog_args"""
+
+    _fields_ = [
+        ("start", C.c_int64), ("end", C.c_int64), ("date_of_birth", _VP), ("date_of_death", _VP), ("ri_timer", _VP),
+        ("bin_cdf", _VP), ("bin_lo", _VP), ("bin_hi", _VP), ("n_bins", C.c_int32), ("cum_deaths", _VP), ("max_year", C.c_int32),
+        ("seed", C.c_uint64), ("id_base", C.c_uint64),
+    ]
+
+
+DIST_KINDS = {"constant": 0, "exponential": 1, "gamma": 2, "lognormal": 3, "normal": 4, "poisson": 5, "uniform": 6}
+MISSED_WS_WORDS = 65536 + 4
 
 F_PENDING, F_STAGES, F_DEATHS, F_RI, F_SIA = 1, 2, 4, 8, 16
 TILE_AGENTS = 512

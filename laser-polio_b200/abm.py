@@ -28,7 +28,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import core, pars as _pars, utils
+from . import core, pars as _pars, popinit, utils
 from .core import LaserFrame, PropertySet
 
 logger = logging.getLogger("laser-polio-b200")
@@ -45,6 +45,12 @@ _UNBORN_DEFAULTS = {"disease_state": -1, "potentially_paralyzed": -1, "paralyzed
 def _say(colour: str, msg: str) -> None:
     code = {"cyan": 36, "red": 31, "green": 32, "yellow": 33}[colour]
     print(f"\033[{code}m{msg}\033[0m")
+
+
+def _device_init(pars) -> bool:
+    """``pars.device_init`` (an extension key, default False): draw the per-agent columns in HBM (popinit / lpk_init.cu)
+    instead of with the host's numpy stream.  Same distributions, Philox streams keyed on (seed, agent, stage)."""
+    return bool(pars["device_init"]) if "device_init" in pars else False
 
 
 def _verbosity(pars) -> int:
@@ -111,7 +117,10 @@ class SEIR_ABM:
         people.add_scalar_property("strain", dtype=np.int8, default=0)
         people.add_scalar_property("chronically_missed", dtype=np.uint8, default=0)
         n_missed = int(pars.missed_frac * people.count)
-        people.chronically_missed[np.random.choice(people.count, size=n_missed, replace=False)] = 1
+        if _device_init(pars):
+            popinit.init_frame_device(people, pars, {"missed"})
+        else:
+            people.chronically_missed[np.random.choice(people.count, size=n_missed, replace=False)] = 1
         people.add_scalar_property("node_id", dtype=np.int16, default=-1)
         self.nodes = np.arange(len(pars.init_pop))
         by_node = pars.init_sus if pars.init_sus_by_age is not None else pars.init_pop
@@ -318,12 +327,15 @@ class DiseaseState_ABM:
         # timers for every slot, born or not (reference model.py:571-587): int8, truncation before the clip
         for name in ("exposure_timer", "infection_timer", "paralysis_timer"):
             people.add_scalar_property(name, dtype=np.int8, default=0)
-        people.exposure_timer[:] = pars.dur_exp(cap)
-        people.infection_timer[:] = pars.dur_inf(cap)
-        people.exposure_timer[:] = np.clip(people.exposure_timer, 0, 127)
-        people.infection_timer[:] = np.clip(people.infection_timer, 0, 127)
-        remaining = pars.t_to_paralysis(cap) - people.exposure_timer  # onset measured from exposure
-        people.paralysis_timer[:] = np.clip(remaining, 0, np.minimum(people.infection_timer, 127)).astype(np.int8)
+        if _device_init(pars):
+            popinit.init_frame_device(people, pars, {"timers"})
+        else:
+            people.exposure_timer[:] = pars.dur_exp(cap)
+            people.infection_timer[:] = pars.dur_inf(cap)
+            people.exposure_timer[:] = np.clip(people.exposure_timer, 0, 127)
+            people.infection_timer[:] = np.clip(people.infection_timer, 0, 127)
+            remaining = pars.t_to_paralysis(cap) - people.exposure_timer  # onset measured from exposure
+            people.paralysis_timer[:] = np.clip(remaining, 0, np.minimum(people.infection_timer, 127)).astype(np.int8)
         self._init_immunity()
         self._seed_initial_infections()
 
@@ -494,7 +506,10 @@ class Transmission_ABM:
         cap = self.people.capacity
         self.people.add_scalar_property("acq_risk_multiplier", dtype=np.float32, default=1.0)
         self.people.add_scalar_property("daily_infectivity", dtype=np.float32, default=1.0)
-        populate_heterogeneous_values(0, cap, self.people.acq_risk_multiplier, self.people.daily_infectivity, self.pars)
+        if _device_init(self.pars):
+            popinit.init_frame_device(self.people, self.pars, {"heterogeneity"})
+        else:
+            populate_heterogeneous_values(0, cap, self.people.acq_risk_multiplier, self.people.daily_infectivity, self.pars)
         self._init_common()
 
     @classmethod
@@ -632,6 +647,10 @@ class VitalDynamics_ABM:
                 ages = np.random.randint(lo[bins], hi[bins]).astype(np.int32)
                 ages[ages <= 0] = 1
                 people.date_of_birth[np.where(people.node_id[: people.count] == node)[0]] = -ages
+        elif _device_init(pars):
+            self._pyramid = core.load_pyramid_csv(pars.age_pyramid_path)
+            popinit.init_frame_device(people, pars, {"demography"}, pyramid=self._pyramid)
+            self.sim._device_demography = True  # date_of_death / ri_timer continue the same per-agent streams
         else:
             pyr = core.load_pyramid_csv(pars.age_pyramid_path)
             bins = core.AliasedDistribution(pyr[:, 2] + pyr[:, 3]).sample(people.count)
@@ -651,8 +670,14 @@ class VitalDynamics_ABM:
         people.add_scalar_property("date_of_death", dtype=np.int32, default=0)
         self.death_estimator = core.KaplanMeierEstimator(utils.create_cumulative_deaths(np.sum(pars.init_pop), max_age_years=100))
         ages = -people.date_of_birth[: people.count]
-        lifespans = self.death_estimator.predict_age_at_death(ages, max_year=100)
-        people.date_of_death[: people.count] = lifespans - ages
+        if getattr(self.sim, "_device_demography", False):
+            self._cum_deaths = utils.create_cumulative_deaths(np.sum(pars.init_pop), max_age_years=100)
+            popinit.init_frame_device(people, pars, {"demography"}, pyramid=self._pyramid, cum_deaths=self._cum_deaths)
+            self.sim._device_cum_deaths = self._cum_deaths
+            lifespans = people.date_of_death[: people.count] + ages
+        else:
+            lifespans = self.death_estimator.predict_age_at_death(ages, max_year=100)
+            people.date_of_death[: people.count] = lifespans - ages
         nid = people.node_id[: people.count]
         cnt = np.bincount(nid, minlength=nn)
         life = np.zeros(nn)
@@ -761,7 +786,15 @@ class RI_ABM:
         people = self.people
         people.add_scalar_property("ri_timer", dtype=np.int16, default=-1)
         dob = people.date_of_birth[: people.count]
-        people.ri_timer[: people.count] = (dob + np.random.uniform(42, 98, people.count)).astype(np.int32)
+        if getattr(sim, "_device_demography", False):
+            vd = next((i for i in getattr(sim, "instances", []) if isinstance(i, VitalDynamics_ABM)), None)
+            pyramid = getattr(vd, "_pyramid", None) if vd is not None else None
+            if pyramid is None:
+                pyramid = core.load_pyramid_csv(sim.pars.age_pyramid_path)
+            popinit.init_frame_device(people, sim.pars, {"demography"}, pyramid=pyramid,
+                                      cum_deaths=getattr(sim, "_device_cum_deaths", None))
+        else:
+            people.ri_timer[: people.count] = (dob + np.random.uniform(42, 98, people.count)).astype(np.int32)
 
     @classmethod
     def init_from_file(cls, sim):

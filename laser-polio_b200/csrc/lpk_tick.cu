@@ -1179,7 +1179,7 @@ static int pass_occupancy() {
     static int occ = 0;
     if (!occ) {
         const char *e = getenv("LPK_PASS_OCC");
-        occ = (e && e[0] == '3') ? 3 : 2;
+        occ = (e && e[0] == '3') ? 3 : ((e && e[0] == '5') ? 5 : 2);
     }
     return occ;
 }
@@ -1235,6 +1235,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     else if (deaths) rc = launch_pass<true, false, false, 8, 2>(pp, st);
     else if (ri) rc = launch_pass<false, true, false, 8, 2>(pp, st);
     else if (pass_occupancy() == 2) rc = launch_pass<false, false, false, 8, 2>(pp, st);
+    else if (pass_occupancy() == 5) rc = launch_pass<false, false, false, 10, 2>(pp, st);
     else rc = launch_pass<false, false, false, 6, 3>(pp, st);
     if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");

@@ -77,6 +77,7 @@ default_pars = PropertySet(
         "summary_config": None,
         "verbose": 1,
         "stop_if_no_cases": True,
+        "device_init": False,  # extension (not a reference key): draw the per-agent columns on the GPU (popinit.py)
     }
 )
 

@@ -33,8 +33,8 @@ STAGE_PARALYSIS, STAGE_RI, STAGE_SIA, STAGE_EXPOSE, STAGE_STRAIN, STAGE_NODE, ST
 
 
 def build(force: bool = False) -> Path:
-    src = _HERE / "lp_oracle.c"
-    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+    newest = max((_HERE / f).stat().st_mtime for f in ("lp_oracle.c", "lp_oracle_init.c"))
+    if force or not _SO.exists() or _SO.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []), check=True, capture_output=True)
     return _SO
 
@@ -393,3 +393,53 @@ def vd_births_device(pop_prev, birth_rate, step_size, cum_deaths, count, capacit
         doy = 1 + int(np.floor(u2 * 364.0)) if yod == 0 else int(np.floor(u2 * 365.0))
         dod[k] = tick + yod * 365 + doy
     return births, node_id, dod, count + total, 0
+
+
+# ------------------------------------------------------------------------------------------ population initialisers
+# (lp_oracle_init.c; checker for laser-polio_b200/csrc/lpk_init.cu)
+DIST_KINDS = {"constant": 0, "exponential": 1, "gamma": 2, "lognormal": 3, "normal": 4, "poisson": 5, "uniform": 6}
+
+
+class Dist(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
+def dist(kind: str, a: float = 0.0, b: float = 0.0) -> Dist:
+    """kind / a / b as in include/lpk.h (lognormal takes mu, sigma of the underlying normal)."""
+    return Dist(DIST_KINDS[kind], float(a), float(b))
+
+
+def lognormal_mu_sigma(mean: float, sigma: float):
+    """lp.lognormal(mean, sigma) -> parameters of the underlying normal (reference distributions.py:73-87)."""
+    return float(np.log(mean**2 / np.sqrt(sigma**2 + mean**2))), float(np.sqrt(np.log(sigma**2 / mean**2 + 1)))
+
+
+def init_draw(n: int, d: Dist, seed: int, stage: int = 17) -> np.ndarray:
+    out = np.zeros(n, np.float64)
+    lib().orc_init_draw(C.c_int64(n), C.byref(d), C.c_uint64(seed), C.c_uint32(stage), _p(out))
+    return out
+
+
+def init_heterogeneity(start, end, acq_risk_out, infectivity_out, mu_ln, sigma_ln, scale_gamma, rho, heterogeneity, mean_gamma,
+                       seed, id_base=0):
+    lib().orc_init_heterogeneity(C.c_int64(start), C.c_int64(end), _p(acq_risk_out, np.float32), _p(infectivity_out, np.float32),
+                                 C.c_double(mu_ln), C.c_double(sigma_ln), C.c_double(scale_gamma), C.c_double(rho),
+                                 C.c_int32(int(bool(heterogeneity))), C.c_double(mean_gamma), C.c_uint64(seed), C.c_uint64(id_base))
+
+
+def init_timers(start, end, exposure_timer, infection_timer, paralysis_timer, dur_exp: Dist, dur_inf: Dist, t_to_paralysis: Dist,
+                seed, id_base=0):
+    lib().orc_init_timers(C.c_int64(start), C.c_int64(end), _p(exposure_timer, np.int8), _p(infection_timer, np.int8),
+                          _p(paralysis_timer, np.int8), C.byref(dur_exp), C.byref(dur_inf), C.byref(t_to_paralysis),
+                          C.c_uint64(seed), C.c_uint64(id_base))
+
+
+def init_demography(start, end, date_of_birth, date_of_death, ri_timer, bin_cdf, bin_lo, bin_hi, cum_deaths, max_year, seed, id_base=0):
+    lib().orc_init_demography(C.c_int64(start), C.c_int64(end), _p(date_of_birth, np.int32), _p(date_of_death, np.int32),
+                              _p(ri_timer, np.int16), _p(bin_cdf, np.float64), _p(bin_lo, np.int32), _p(bin_hi, np.int32),
+                              C.c_int32(len(bin_cdf)), _p(cum_deaths, np.int64), C.c_int32(max_year), C.c_uint64(seed),
+                              C.c_uint64(id_base))
+
+
+def init_missed(n, n_missed, chronically_missed, seed, id_base=0):
+    lib().orc_init_missed(C.c_int64(n), C.c_int64(n_missed), _p(chronically_missed, np.uint8), C.c_uint64(seed), C.c_uint64(id_base))
