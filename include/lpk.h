@@ -398,6 +398,20 @@ int lpk_init_demography(const lpk_demog_args *args, void *stream);
 #define LPK_MISSED_WS_WORDS (65536 + 4)
 int lpk_init_missed(int64_t n, int64_t n_missed, uint8_t *chronically_missed, uint64_t seed, uint64_t id_base, uint32_t *ws, void *stream);
 
+/* ---- The infection-migration network in HBM ---------------------------------------------------
+ * Transmission_ABM._initialize_common, reference model.py:1216-1258; laser-core's gravity / radiation / row_normalizer /
+ * distance (~=0.6, not in the checkout) as restated in laser-polio_b200/core.py.  All matrices device float64 [n, n]. */
+/* all-pairs Haversine (km, R = 6371); d == 0 off the diagonal -> epsilon (model.py:1232-1238) */
+int lpk_net_haversine(const double *lat_deg, const double *lon_deg, int32_t n, double epsilon, double *dist, void *stream);
+/* net[i, j] = k * p_i^a * p_j^b * d_ij^-c / norm, zero diagonal; norm = (sum p)^c (model.py:1243-1251) */
+int lpk_net_gravity(const double *pops, const double *dist, int32_t n, double k, double a, double b, double c, double norm, double *net,
+                    void *stream);
+/* T_ij = k p_i p_j / ((p_i + s_ij)(p_i + p_j + s_ij)), s_ij = population within d_ij of i without j (and without i unless
+ * include_home); n <= 8192 (model.py:1252-1254) */
+int lpk_net_radiation(const double *pops, const double *dist, int32_t n, double k, int32_t include_home, double *net, void *stream);
+/* rows whose sum exceeds max_rowsum are rescaled to it, in place (model.py:1258) */
+int lpk_net_row_normalize(double *net, int32_t n, double max_rowsum, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

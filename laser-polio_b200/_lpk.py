@@ -24,6 +24,7 @@ EXPORTS = (
     "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
     "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births",
     "lpk_init_heterogeneity", "lpk_init_timers", "lpk_init_demography", "lpk_init_missed",
+    "lpk_net_haversine", "lpk_net_gravity", "lpk_net_radiation", "lpk_net_row_normalize",
 )
 
 

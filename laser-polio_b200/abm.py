@@ -28,7 +28,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import core, pars as _pars, popinit, utils
+from . import core, netbuild, pars as _pars, popinit, utils
 from .core import LaserFrame, PropertySet
 
 logger = logging.getLogger("laser-polio-b200")
@@ -525,6 +525,10 @@ class Transmission_ABM:
     def _init_common(self):
         pars, n = self.pars, len(self.sim.nodes)
         init_pops = np.asarray(pars.init_pop)
+        if _device_init(pars) and n <= 8192:  # distances, gravity / radiation, row normalisation on the GPU (netbuild.py)
+            self.network = netbuild.build_network(pars, init_pops).cpu().numpy()
+            self._init_results_rows()
+            return
         if pars.distances is not None:
             dist = np.asarray(pars.distances)
         else:  # Haversine all-pairs from node_lookup (reference model.py:1224-1240), vectorised
@@ -544,6 +548,10 @@ class Transmission_ABM:
         else:
             raise ValueError(f"Unknown migration method: {pars.migration_method}")
         self.network = core.row_normalizer(net, pars.max_migr_frac)
+        self._init_results_rows()
+
+    def _init_results_rows(self):
+        pars = self.pars
         nt, ns = self.sim.nt, len(pars.strain_ids)
         self.results.add_array_property("new_exposed", shape=(nt, len(self.nodes)), dtype=np.int32)
         self.results.add_array_property("new_exposed_by_strain", shape=(nt, len(self.nodes), ns), dtype=np.int32)

@@ -443,3 +443,58 @@ def init_demography(start, end, date_of_birth, date_of_death, ri_timer, bin_cdf,
 
 def init_missed(n, n_missed, chronically_missed, seed, id_base=0):
     lib().orc_init_missed(C.c_int64(n), C.c_int64(n_missed), _p(chronically_missed, np.uint8), C.c_uint64(seed), C.c_uint64(id_base))
+
+
+# ------------------------------------------------------------------------------------------ network construction
+# (checker for laser-polio_b200/csrc/lpk_net.cu; reference model.py:1216-1258.  laser-core ~=0.6 is not in the checkout:
+# gravity follows the in-tree evidence scripts/sandbox/debug_negative_network.py:74, row_normalizer debug_row_normalizer.py:30-33,
+# radiation the published model -- parity unpinned for radiation and distance.)
+def net_haversine(lat, lon, epsilon=1.0):
+    """The reference's double loop (model.py:1231-1240) with laser-core's Haversine ``distance`` (km, R = 6371)."""
+    lat, lon = np.radians(np.asarray(lat, np.float64)), np.radians(np.asarray(lon, np.float64))
+    n = len(lat)
+    out = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            a = np.sin((lat[j] - lat[i]) / 2) ** 2 + np.cos(lat[i]) * np.cos(lat[j]) * np.sin((lon[j] - lon[i]) / 2) ** 2
+            d = 6371.0 * 2 * np.arcsin(np.sqrt(a))
+            if d == 0:
+                d = epsilon
+            out[i, j] = out[j, i] = d
+    return out
+
+
+def net_gravity(pops, dist, k, a, b, c, norm=1.0):
+    pops, dist = np.asarray(pops, np.float64), np.asarray(dist, np.float64)
+    n = len(pops)
+    out = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                out[i, j] = k * pops[i] ** a * pops[j] ** b / dist[i, j] ** c / norm
+    return out
+
+
+def net_radiation(pops, dist, k, include_home=False):
+    """From the definition: s_ij = population at distance <= d_ij from i, without j, without i unless include_home."""
+    pops, dist = np.asarray(pops, np.float64), np.asarray(dist, np.float64)
+    n = len(pops)
+    out = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                continue
+            inside = dist[i] <= dist[i, j]
+            s = pops[inside].sum() - pops[j] - (0.0 if include_home else pops[i])
+            s = max(s, 0.0)
+            out[i, j] = k * pops[i] * pops[j] / ((pops[i] + s) * (pops[i] + pops[j] + s))
+    return out
+
+
+def net_row_normalize(net, max_rowsum):
+    net = np.array(net, np.float64, copy=True)
+    for i in range(len(net)):
+        rs = net[i].sum()
+        if rs > max_rowsum:
+            net[i] *= max_rowsum / rs
+    return net
