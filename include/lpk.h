@@ -294,6 +294,9 @@ typedef struct lpk_node_args {
     int32_t *tx_hits, *S_snap, *R_snap;
     int32_t *S_prev, *R_prev; /* rows t-1 */
     int64_t *counts; /* counts[0] = counts[1] once tick t is complete */
+    /* node shard: only nodes [node_lo, node_hi) are this rank's -- their rows are written, their columns of
+     * the network are read (1 / world of the matrix per tick); node_hi == 0 means every node */
+    int32_t node_lo, node_hi;
 } lpk_node_args;
 
 int lpk_tick_node(const lpk_node_args *args, void *stream);

@@ -672,12 +672,12 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
                                                         const int32_t *__restrict__ alive, double zi, double disp_r,
                                                         double *target, double *strain_cdf, double *prob, double *expected,
                                                         const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
-                                                        uint32_t tick) {
+                                                        uint32_t tick, int j_lo, int j_hi) {
     __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
     __shared__ unsigned char snz[NM_ROWS];
     __shared__ double stgt[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx;
+    const int j = j_lo + blockIdx.x * 32 + tx;  // destination nodes [j_lo, j_hi): all of them, or this rank's shard
     double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
     for (int base = 0; base < n; base += NM_ROWS) {
         const int rows = min(NM_ROWS, n - base);
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
             snz[threadIdx.x] = nz ? 1 : 0;
         }
         __syncthreads();
-        if (j < n) {
+        if (j < j_hi) {
 #pragma unroll 4
             for (int i = ty; i < rows; i += 32) {
                 if (!snz[i]) continue;  // warp-uniform: rows without infectivity contribute nothing
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
     __syncthreads();
     if (ty == 0) {
         double tgt = 0.0;
-        if (j < n) {
+        if (j < j_hi) {
             double P = 0.0, local = 0.0, p[LPK_MAX_STRAINS];
             const double popn = fmax((double)alive[j], 1.0);
             for (int s = 0; s < n_strains; ++s) {
@@ -740,8 +740,8 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
         stgt[tx] = tgt;
     }
     __syncthreads();
-    const int jn = blockIdx.x * 32 + ty;  // warp ty solves node jn
-    if (jn < n) {
+    const int jn = j_lo + blockIdx.x * 32 + ty;  // warp ty solves node jn
+    if (jn < j_hi) {
         const float t = solve_tau_warp(jn, hist, stgt[ty], tx);
         if (tx == 0) tau[jn] = t;
     }
@@ -750,7 +750,8 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
-                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done) {
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
+                         int32_t node_lo, int32_t node_hi) {
     double *rowsum = ws, *target = ws + num_nodes;
     if (!rowsums_done) {
         k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
@@ -758,9 +759,9 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
     }
     double r = nearbyint(dispersion);
     if (r < 1.0) r = 1.0;
-    k_tx_node_math<<<(num_nodes + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
-                                                           beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
-                                                           strain_cdf, prob, expected, risk_hist, tau, seed, tick);
+    k_tx_node_math<<<(node_hi - node_lo + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
+                                                                   beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
+                                                                   strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi);
     CUDA_TRY(cudaGetLastError(), "node_math");
     return LPK_OK;
 }
@@ -776,5 +777,5 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
                 expected && ws, "tx_node_math null pointer");
     return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
                                 alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
-                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false);
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes);
 }

@@ -1271,8 +1271,9 @@ extern "C" int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, 
 // ------------------------------------------------------------------ node-level epilogue of tick t
 // one warp per node: the row sum of the network (coalesced) by all lanes, the node's bookkeeping by lane 0
 __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ lpk_node_args a) {
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (n >= a.n_nodes) return;
+    const int n_lo = a.node_hi > 0 ? a.node_lo : 0, n_hi = a.node_hi > 0 ? a.node_hi : a.n_nodes;
+    const int n = n_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= n_hi) return;
     {
         double sum = 0.0;
         for (int j = lane; j < a.n_nodes; j += 32) sum += a.network[(int64_t)n * a.n_nodes + j];
@@ -1281,7 +1282,7 @@ __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ l
         if (lane == 0) a.rowsum_ws[n] = sum;
     }
     if (lane != 0) return;
-    if (n == 0 && a.counts) a.counts[0] = a.counts[1];
+    if (n == n_lo && a.counts) a.counts[0] = a.counts[1];
     const int ns = a.n_strains;
     int d = 0, dpp = 0, dpar = 0;
     if (a.deaths) {
@@ -1339,7 +1340,8 @@ __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ l
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
-                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done);
+                         double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
+                         int32_t node_lo, int32_t node_hi);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
@@ -1356,9 +1358,12 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(a.E_cur && a.I_cur && a.E_snap && a.I_snap && a.tx_hits_by_strain &&
                 (!(a.flags & LPK_F_PENDING) || (a.E_by_strain_prev && a.I_by_strain_prev && a.E_prev && a.I_prev)), "tick_node E / I census");
     cudaStream_t st = as_stream(stream);
-    k_tick_epilogue<<<(a.n_nodes + 7) / 8, 256, 0, st>>>(a);
+    REQUIRE(a.node_hi == 0 || (a.node_lo >= 0 && a.node_lo < a.node_hi && a.node_hi <= a.n_nodes), "tick_node node shard");
+    const int owned = a.node_hi > 0 ? a.node_hi - a.node_lo : a.n_nodes;
+    k_tick_epilogue<<<(owned + 7) / 8, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
-                                a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true);
+                                a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true, a.node_hi > 0 ? a.node_lo : 0,
+                                a.node_hi > 0 ? a.node_hi : a.n_nodes);
 }

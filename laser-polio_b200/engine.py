@@ -239,6 +239,8 @@ class FusedEngine:
             sharding.allreduce_tally(beta_fx, sim.shard)
         N = NodeArgs()
         N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
+        if sim.shard is not None:  # the node kernels touch this rank's nodes only: 1 / world of the network per tick
+            N.node_lo, N.node_hi = int(sim.shard.node_lo), int(sim.shard.node_hi)
         N.seed = A.seed
         N.beta_fx, N.exposure_fx, N.risk_hist = dp(beta_fx), dp(exposure_fx), dp(risk_hist)
         N.network, N.r0_scalars = dp(dev.network_tensor(tx.network)), dp(tx._r0_scalars_dev(dev))
