@@ -600,21 +600,27 @@ __device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32
 // The same step without a branch, for the streaming loop: the two quads a lane owns run through it back to back, so the
 // compiler interleaves two independent dependency chains (the pass is bound by fixed-latency dependencies, not by issue
 // slots: profiles/r1_fused_v19_220M_*: stall_wait 2.2 cycles per instruction at 4 warps per scheduler).  No hits here.
-__device__ __forceinline__ DsQuad ds_quad_flat(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t et, uint32_t it, uint32_t sw,
+__device__ __forceinline__ DsQuad ds_quad_flat(const lpk_people &P, uint32_t b, uint32_t nw0, uint32_t et, uint32_t it, uint32_t sw,
                                                uint32_t pt, uint32_t pq) {
-    const uint32_t K1 = 0x01010101u;
+    const uint32_t K1 = 0x01010101u, K80 = 0x80808080u, K7F = 0x7F7F7F7Fu;
     const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;
-    const uint32_t tE = mE & bytes_le0(et);
+    // count down and test in one go: t = (x | 0x80) - m never borrows across bytes; where m = 1, bit 7 of t is clear iff the
+    // low 7 bits of x were zero, so "x <= 0" (zero, or bit 7 set) is (~t | x) >> 7; the decremented byte keeps t's low 7 bits
+    // and takes bit 7 from x ^ ~t
+    const uint32_t te = (et | K80) - mE;
+    const uint32_t tE = mE & ((~te | et) >> 7);
     const uint32_t mJ = mI | tE;
-    const uint32_t tI = mJ & bytes_le0(it);
+    const uint32_t ti = (it | K80) - mJ;
+    const uint32_t tI = mJ & ((~ti | it) >> 7);
     const uint32_t wild = mJ & ~(sw | (sw >> 1));
-    const uint32_t gate = wild & bytes_le0(pt) & (pq >> 7);
-    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = bytes_dec(et, mE);
-    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = bytes_dec(it, mJ);
-    if (wild) *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = bytes_dec(pt, wild);
+    const uint32_t tp = (pt | K80) - wild;
+    const uint32_t gate = wild & ((~tp | pt) >> 7) & (pq >> 7);
+    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = (te & K7F) | ((et ^ ~te) & K80);
+    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = (ti & K7F) | ((it ^ ~ti) & K80);
+    if (wild) *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = (tp & K7F) | ((pt ^ ~tp) & K80);
     DsQuad o;
     o.nw = nw0 + tE + tI;
-    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (gate << 7);
+    o.f = nw0 | (tE << 2) | (tI << 3) | (gate << 7);  // flag bytes are read for the agents of o.m only (state byte 1 or 2)
     o.m = tE | tI | gate;
     return o;
 }
@@ -1029,11 +1035,11 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         auto ds_both = [&]() {
             gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
             gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
-            const DsQuad dA = ds_quad_flat(P, bA, nwA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
+            const DsQuad dA = ds_quad_flat(P, (uint32_t)bA, nwA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA,
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffPt + lane * 4),
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffPq + lane * 4));
-            const DsQuad dB = ds_quad_flat(P, bB, nwB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
+            const DsQuad dB = ds_quad_flat(P, (uint32_t)bB, nwB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB,
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffPt + 128 + lane * 4),
                                            *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
