@@ -204,6 +204,8 @@ typedef struct lpk_people {
 #define LPK_F_DEATHS 4u  /* tick t is a vital-dynamics tick: mark deaths (needs date_of_death) */
 #define LPK_F_RI 8u      /* tick t is a routine-immunisation tick (needs ri_timer) */
 #define LPK_F_SIA 16u    /* tick t carries ONE campaign event (needs date_of_birth and the sia_* fields) */
+#define LPK_F_ROWSUMS 32u /* lpk_tick_node only: rowsum_ws[0 .. nodes) already holds the row sums of `network` (the caller
+                             sets it from the second tick on while the network is unchanged; saves re-reading the matrix) */
 
 typedef struct lpk_tick_args {
     uint32_t flags;

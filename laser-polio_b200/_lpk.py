@@ -182,7 +182,7 @@ class DemogArgs(C.Structure):
 DIST_KINDS = {"constant": 0, "exponential": 1, "gamma": 2, "lognormal": 3, "normal": 4, "poisson": 5, "uniform": 6}
 MISSED_WS_WORDS = 65536 + 4
 
-F_PENDING, F_STAGES, F_DEATHS, F_RI, F_SIA = 1, 2, 4, 8, 16
+F_PENDING, F_STAGES, F_DEATHS, F_RI, F_SIA, F_ROWSUMS = 1, 2, 4, 8, 16, 32
 TILE_AGENTS = 512
 
 

@@ -68,6 +68,7 @@ class FusedEngine:
         self.prob = torch.zeros((n, ns), dtype=torch.float64, device=d)
         self.expected = torch.zeros(n, dtype=torch.float64, device=d)
         self.rowsum = torch.zeros(2 * n, dtype=torch.float64, device=d)
+        self._rowsum_of = None  # the network tensor whose row sums self.rowsum[:n] holds
         self.dummy_row = i32(n * max(ns, 1))  # sink for rows of components that are absent
         # early stop (pars.stop_if_no_cases): "somebody is still exposed or infectious after tick t", one flag per tick,
         # mirrored into pinned host memory with an event so that the host never waits for more than one tick
@@ -243,7 +244,11 @@ class FusedEngine:
             N.node_lo, N.node_hi = int(sim.shard.node_lo), int(sim.shard.node_hi)
         N.seed = A.seed
         N.beta_fx, N.exposure_fx, N.risk_hist = dp(beta_fx), dp(exposure_fx), dp(risk_hist)
-        N.network, N.r0_scalars = dp(dev.network_tensor(tx.network)), dp(tx._r0_scalars_dev(dev))
+        net = dev.network_tensor(tx.network)
+        N.network, N.r0_scalars = dp(net), dp(tx._r0_scalars_dev(dev))
+        if self._rowsum_of is net:  # the row sums in self.rowsum belong to this very matrix: do not re-read it
+            N.flags |= _lpk.F_ROWSUMS
+        self._rowsum_of = net
         N.beta_seasonality = float(self._seasonality())
         N.zero_inflation, N.dispersion = float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion)
         N.q, N.strain_cdf, N.prob, N.expected, N.rowsum_ws = dp(self.q), dp(self.cdf), dp(self.prob), dp(self.expected), dp(self.rowsum)
