@@ -251,6 +251,9 @@ typedef struct lpk_tick_args {
                               them with lpk_tx_step_prep and re-initialises after any tick run outside the pass */
     int32_t *R_cur;        /* [nodes] recovered agents per node, carried the same way (+1 on recovery, -1 when a recovered
                               agent dies); initialised / re-initialised from lpk_count_seirp's R */
+    /* scheduling hint (results do not depend on it): slots [0, uniform_agents) hold the node-contiguous initial population,
+     * slots beyond it appended newborn cohorts; the pass hands the cohort region out first.  0 = unknown */
+    int64_t uniform_agents;
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the

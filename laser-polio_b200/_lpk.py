@@ -129,6 +129,7 @@ class TickArgs(C.Structure):
         ("sia_vaccinated", _VP), ("sia_protected", _VP), ("sia_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
         ("beta_fx", _VP), ("E_cur", _VP), ("I_cur", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
+        ("uniform_agents", C.c_int64),
     ]
 
 

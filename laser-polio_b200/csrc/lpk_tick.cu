@@ -747,7 +747,10 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
                     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
                                   (uint32_t)(A.seed >> 32), x);
                     const float4 rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
-                    hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, par ? x[2] : x[0], par ? x[3] : x[1], w, rk, tau);
+                    // the 16-bit pre-test first, as in the streaming loop: newborn cohorts are all susceptible and never leave
+                    // this path (their 512-agent tiles span several nodes), and the exact trial is ~200 instructions
+                    const uint32_t xa = par ? x[2] : x[0], xb = par ? x[3] : x[1];
+                    if (pretest_quad(xa, xb, rk, tau * 65536.0f)) hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, xa, xb, w, rk, tau);
                     nw |= hits;  // S (0) -> E (1)
                 }
             }
@@ -900,7 +903,10 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: the units of the current run not yet taken
     bool exhausted = false;                // warp-uniform: a claim came back beyond the last unit
     uint32_t claim_first = 0u, claim_cnt = 0u, seen = 0u;  // lane 0: the prefetched claim, the counter as last read
+    const uint32_t stream_units = A.uniform_agents > 0 ? (uint32_t)(A.uniform_agents >> (8 + LPK_UNIT_LOG)) : n_units;
+    const uint32_t tail_units = n_units - (stream_units < n_units ? stream_units : n_units);  // warp-uniform
     auto run_length = [&](uint32_t ctr) -> uint32_t {
+        if (ctr < tail_units) return 1u;
         const uint32_t left = ctr < n_units ? n_units - ctr : 0u;
         const uint32_t r = left / guide;
         return r < 1u ? 1u : (r > 64u ? 64u : r);
@@ -915,7 +921,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         return u == kNoUnit ? kNoUnit : (u << LPK_UNIT_LOG) + (uint32_t)(s & (LPK_UNIT_PAIRS - 1));
     };
     // node of the pair at position s (called once per s, in order): >= 0 all 256 agents in that node and present at tick
-    // t-1; -1 general handling; -2 no more work for this warp
+    // t-1; -1 general handling; -2 no more work for this warp; -3 no such pair (past the end of the table)
     auto node_of = [&](int s) -> int {
         if ((s & (LPK_UNIT_PAIRS - 1)) == 0) {
             uint32_t u = kNoUnit;
@@ -926,7 +932,12 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                     else { run_next = first; run_end = first + cnt < n_units ? first + cnt : n_units; }
                 }
                 if (!exhausted) {
-                    u = run_next++;
+                    // claim index -> unit: the units behind the node-contiguous initial population (appended newborn cohorts:
+                    // their tiles span several nodes, so they run through the general path, ~50 us of a warp's time per unit)
+                    // are handed out FIRST, one per claim; claimed last they formed a tail of that length on every day
+                    // after the first births (plain day 0.54 -> 0.59 ms).  The streaming part follows in ascending order.
+                    const uint32_t c = run_next++;
+                    u = c < tail_units ? n_units - 1u - c : c - tail_units;
                     if (run_next >= run_end && lane == 0) {  // the run's last unit: claim the next run now
                         claim_cnt = run_length(seen);
                         claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
@@ -938,7 +949,8 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         }
         const uint32_t gp = pair_of(s);
         gp_looked = gp;
-        if (gp >= total_pairs) return -2;  // kNoUnit included
+        if (gp == kNoUnit) return -2;
+        if (gp >= total_pairs) return -3;  // beyond the table inside the last unit: nothing to do, but the warp goes on
         return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
     };
     int tc_node = -2;  // one-entry cache of tau (and the campaign's target flag) per node: a warp stays in one node for long
@@ -1020,7 +1032,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             __syncwarp();
             produce(s + NST, slot);
             if (tn == -2) return false;
-            q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)(uint32_t)mt.z, n, count_prev, lane), lane);
+            if (tn == -1) q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)(uint32_t)mt.z, n, count_prev, lane), lane);
             return true;
         }
         const int64_t gp = (int64_t)(uint32_t)mt.z;

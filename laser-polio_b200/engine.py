@@ -69,6 +69,9 @@ class FusedEngine:
         self.expected = torch.zeros(n, dtype=torch.float64, device=d)
         self.rowsum = torch.zeros(2 * n, dtype=torch.float64, device=d)
         self._rowsum_of = None  # the network tensor whose row sums self.rowsum[:n] holds
+        # scheduling hint for the pass: the node-contiguous initial population ends here, appended cohorts follow
+        init_total = int(np.sum(np.asarray(sim.pars.init_pop))) if "init_pop" in sim.pars else 0
+        self.uniform_agents = init_total if 0 < init_total <= dev.count0 else int(dev.count0)
         self.dummy_row = i32(n * max(ns, 1))  # sink for rows of components that are absent
         # early stop (pars.stop_if_no_cases): "somebody is still exposed or infectious after tick t", one flag per tick,
         # mirrored into pinned host memory with an event so that the host never waits for more than one tick
@@ -230,6 +233,7 @@ class FusedEngine:
         beta_fx, exposure_fx, sus, risk_hist = self.beta, self.expo, self.sus, self.hist
         A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
         A.flags = flags
+        A.uniform_agents = self.uniform_agents
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
 
         if sim.shard is not None:  # the one per-tick exchange: sum of the nodes x strains infectivity tally
