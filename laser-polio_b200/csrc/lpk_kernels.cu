@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "lpk_host.cuh"
 #include "lpk_stages.cuh"
 
@@ -665,6 +667,53 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
 // memory 1024 source rows at a time (the previous version re-read it from global in a dependent loop and took 41 us at 774
 // nodes: profiles/r1_v18_launches.csv); the block's 32 warps then solve tau for its 32 nodes.
 #define NM_ROWS 1024
+// Many nodes (continental config; 8 x 774 in the weak-scaling bench): one block per 32 destination nodes walking every source
+// row leaves most SMs idle (25 blocks for 38 MB of network at 6192 nodes, 50 us).  The transfer is then summed per chunk of
+// 1024 source rows by a 2-D grid (destinations x chunks) and k_tx_node_math adds the chunks in index order, so the result
+// does not depend on which block finishes first.
+__global__ void __launch_bounds__(1024) k_node_matvec_partial(int n, int n_strains, const int64_t *__restrict__ beta_fx,
+                                                               const double *__restrict__ W, int j_lo, int j_hi,
+                                                               double *__restrict__ partial) {
+    __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];
+    __shared__ unsigned char snz[NM_ROWS];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = j_lo + blockIdx.x * 32 + tx, base = blockIdx.y * NM_ROWS;
+    const int rows = min(NM_ROWS, n - base);
+    if ((int)threadIdx.x < rows) {
+        bool nz = false;
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
+            const long long b = (s < n_strains) ? beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s] : 0;
+            nz |= (b != 0);
+            sbeta[s][threadIdx.x] = (double)b / LPK_FX_SCALE;
+        }
+        snz[threadIdx.x] = nz ? 1 : 0;
+    }
+    __syncthreads();
+    double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
+    if (j < j_hi) {
+#pragma unroll 4
+        for (int i = ty; i < rows; i += 32) {
+            if (!snz[i]) continue;
+            const double w = W[(int64_t)(base + i) * n + j];
+#pragma unroll
+            for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += sbeta[s][i] * w;
+        }
+    }
+    __syncthreads();
+    double *part = &sbeta[0][0];
+#pragma unroll
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[(ty * LPK_MAX_STRAINS + s) * 32 + tx] = in[s];
+    __syncthreads();
+    if (ty == 0 && j < j_hi) {
+#pragma unroll
+        for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
+            double acc = 0.0;
+            for (int y = 0; y < 32; ++y) acc += part[(y * LPK_MAX_STRAINS + s) * 32 + tx];
+            partial[((int64_t)blockIdx.y * LPK_MAX_STRAINS + s) * n + j] = acc;
+        }
+    }
+}
 __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
                                                         const int64_t *__restrict__ exposure_fx,
                                                         const double *__restrict__ W, const double *__restrict__ rowsum,
@@ -672,13 +721,21 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
                                                         const int32_t *__restrict__ alive, double zi, double disp_r,
                                                         double *target, double *strain_cdf, double *prob, double *expected,
                                                         const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
-                                                        uint32_t tick, int j_lo, int j_hi) {
+                                                        uint32_t tick, int j_lo, int j_hi, const double *__restrict__ partial,
+                                                        int n_chunks) {
     __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
     __shared__ unsigned char snz[NM_ROWS];
     __shared__ double stgt[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = j_lo + blockIdx.x * 32 + tx;  // destination nodes [j_lo, j_hi): all of them, or this rank's shard
     double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
+    if (partial) {  // the transfer was summed per chunk of source rows by k_node_matvec_partial: add the chunks in order
+        if (ty == 0 && j < j_hi) {
+            for (int c = 0; c < n_chunks; ++c)
+#pragma unroll
+                for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += partial[((int64_t)c * LPK_MAX_STRAINS + s) * n + j];
+        }
+    } else
     for (int base = 0; base < n; base += NM_ROWS) {
         const int rows = min(NM_ROWS, n - base);
         __syncthreads();
@@ -759,9 +816,33 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
     }
     double r = nearbyint(dispersion);
     if (r < 1.0) r = 1.0;
+    const double *partial = nullptr;
+    const int n_chunks = (num_nodes + NM_ROWS - 1) / NM_ROWS;
+    static int split = -1;  // LPK_NODE_SPLIT=0: experiments only (single-block form for any size)
+    if (split < 0) { const char *e = getenv("LPK_NODE_SPLIT"); split = (e && e[0] == '0') ? 0 : 1; }
+    if (n_chunks > 1 && split) {  // library-owned scratch, one per device, grown on demand (chunks x strains x nodes doubles: 1.4 MB at 6192 nodes)
+        static double *scratch[64] = {nullptr};
+        static size_t scratch_bytes[64] = {0};
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev), "node_math device");
+        REQUIRE(dev >= 0 && dev < 64, "node_math device index");
+        const size_t need = (size_t)n_chunks * LPK_MAX_STRAINS * num_nodes * sizeof(double);
+        if (scratch_bytes[dev] < need) {
+            CUDA_TRY(cudaStreamSynchronize(st), "node_math scratch");
+            if (scratch[dev]) cudaFree(scratch[dev]);
+            scratch[dev] = nullptr; scratch_bytes[dev] = 0;
+            CUDA_TRY(cudaMalloc(&scratch[dev], need), "node_math scratch");
+            scratch_bytes[dev] = need;
+        }
+        k_node_matvec_partial<<<dim3((node_hi - node_lo + 31) / 32, n_chunks), 1024, 0, st>>>(num_nodes, n_strains, beta_fx, network, node_lo,
+                                                                                             node_hi, scratch[dev]);
+        CUDA_TRY(cudaGetLastError(), "node_math matvec");
+        partial = scratch[dev];
+    }
     k_tx_node_math<<<(node_hi - node_lo + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
                                                                    beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
-                                                                   strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi);
+                                                                   strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi,
+                                                                   partial, n_chunks);
     CUDA_TRY(cudaGetLastError(), "node_math");
     return LPK_OK;
 }

@@ -253,6 +253,32 @@ def test_all_stages_vs_oracle_philox(K, oracle, n, cap, nodes, srt):
         assert (p["disease_state"][:n] == 1).sum() > 0 and new_o.sum() > 0
 
 
+def test_node_math_many_nodes(K, oracle):
+    """More than 1024 nodes: the network transfer is summed per chunk of 1024 source rows by a 2-D grid and the chunks are
+    added in index order (lpk_kernels.cu, k_node_matvec_partial) -- same tolerances as the single-block form, and the same
+    bits from run to run."""
+    nodes, ns, seed, tick = 2600, 3, 11, 9
+    rs = np.random.default_rng(3)
+    bfx = (rs.random((nodes, ns)) * (rs.random((nodes, ns)) < 0.7) * 5.0 * 2**30).astype(np.int64)
+    hist = rs.integers(0, 40, (nodes, 192)).astype(np.int32)
+    hist[rs.random(nodes) < 0.05] = 0
+    efx = (hist.sum(1) * 1.1 * 2**30).astype(np.int64)
+    W = rs.random((nodes, nodes)) * (0.1 / nodes)
+    np.fill_diagonal(W, 0.0)
+    r0s = rs.uniform(0.5, 2.0, nodes)
+    pop = rs.integers(5_000, 50_000, nodes).astype(np.int32)
+    args = (dev(bfx), dev(efx), dev(hist), dev(W), 1.07, dev(r0s), dev(pop), 0.3, 2.0)
+    q, cdf, prob, expd = K.tx_node_math(*args, rng=K.make_rng(seed, tick))
+    q_o, cdf_o, prob_o, exp_o = oracle.tx_node_math_device(bfx, efx, hist, W, 1.07, r0s, pop, 0.3, 2.0, seed, tick)
+    np.testing.assert_allclose(host(prob), prob_o, rtol=1e-6, atol=1e-15)
+    np.testing.assert_allclose(host(cdf), cdf_o, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(host(expd), exp_o, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(host(q), q_o, rtol=2e-6, atol=1e-30)
+    q1, cdf1 = host(q).copy(), host(cdf).copy()
+    q2, cdf2, _, _ = K.tx_node_math(*args, rng=K.make_rng(seed, tick))
+    assert np.array_equal(q1, host(q2)) and np.array_equal(cdf1, host(cdf2))
+
+
 def test_empty_population_and_bad_arguments(K):
     z8 = torch.zeros(16, dtype=torch.int8, device="cuda")
     z16 = torch.zeros(16, dtype=torch.int16, device="cuda")
