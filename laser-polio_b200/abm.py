@@ -317,6 +317,28 @@ class DiseaseState_ABM:
         self = cls.__new__(cls)
         self._common_init(sim)
         self._init_results()
+        people, pars = self.people, self.pars
+        lo, cap = getattr(people, "_unborn_from", None), people.capacity
+        if lo is not None and lo < cap:
+            # a table loaded from a snapshot holds the live prefix only: draw the columns of the slots future newborns will
+            # take, as the reference does at this point (model.py:506-524, including its -1 defaults for the three flags)
+            if _device_init(pars):  # (the device kernels apply the constructor's clipped paralysis-timer rule here too)
+                popinit.init_frame_device(people, pars, {"heterogeneity", "timers"}, start=lo)
+            else:
+                populate_heterogeneous_values(lo, cap, people.acq_risk_multiplier, people.daily_infectivity, pars)
+                people.exposure_timer[lo:cap] = pars.dur_exp(cap - lo)
+                people.infection_timer[lo:cap] = pars.dur_inf(cap - lo)
+                people.paralysis_timer[lo:cap] = pars.t_to_paralysis(cap - lo)
+            people.potentially_paralyzed[lo:cap] = -1
+            people.paralyzed[lo:cap] = -1
+            people.ipv_protected[lo:cap] = -1
+            people.disease_state[lo:cap] = -1
+            people.node_id[lo:cap] = -1
+            if hasattr(people, "ri_timer"):
+                people.ri_timer[lo:cap] = -1
+            if hasattr(people, "date_of_birth"):
+                people.date_of_birth[lo:cap] = -1
+            people._unborn_from = None
         return self
 
     def __init__(self, sim):

@@ -168,6 +168,92 @@ class LaserFrame:
         self._count += count
         return start, self._count
 
+    # ------------------------------------------------------------------ snapshots
+    # laser-core's LaserFrame.save_snapshot / load_snapshot as the reference uses them (run_sim.py:388-409, 431, 457): the
+    # live prefix [0, count) of every per-agent column, the recovered-by-node results array and the parameters that
+    # produced the table; on load the frame gets room for the births of the run to come.  laser-core writes HDF5 through
+    # h5py, which is not installed here: the container is HDF5 when h5py can be imported and the path ends in .h5 / .hdf5,
+    # otherwise a numpy .npz archive with the same entries (a path given as "init_pop.h5" is honoured as the file name).
+    _SNAPSHOT_SCALARS = (int, float, str, bool, np.integer, np.floating, np.bool_)
+
+    def save_snapshot(self, path, results_r=None, pars=None) -> None:
+        import json
+
+        cols = {k: np.ascontiguousarray(v[: self._count]) for k, v in self.columns().items()}
+        meta = {"count": int(self._count), "capacity": int(self._capacity)}
+        if pars is not None:
+            src = pars.to_dict() if hasattr(pars, "to_dict") else dict(pars)
+            keep = {}
+            for k, v in src.items():
+                if isinstance(v, self._SNAPSHOT_SCALARS):
+                    keep[k] = v.item() if isinstance(v, np.generic) else v
+                elif isinstance(v, (list, tuple, np.ndarray)) and np.asarray(v).dtype.kind in "iuf" and np.asarray(v).size <= 100_000:
+                    keep[k] = np.asarray(v).tolist()
+            meta["pars"] = keep
+        path = str(path)
+        if path.endswith((".h5", ".hdf5")):
+            try:
+                import h5py
+
+                with h5py.File(path, "w") as f:
+                    g = f.create_group("people")
+                    for k, v in cols.items():
+                        g.create_dataset(k, data=v)
+                    if results_r is not None:
+                        f.create_dataset("recovered", data=np.asarray(results_r))
+                    f.attrs["meta"] = json.dumps(meta)
+                return
+            except ImportError:
+                pass
+        arrays = {f"people/{k}": v for k, v in cols.items()}
+        if results_r is not None:
+            arrays["recovered"] = np.asarray(results_r)
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        with open(path, "wb") as fh:  # np.savez would append ".npz" to a path ending in ".h5"
+            np.savez(fh, **arrays)
+
+    @classmethod
+    def load_snapshot(cls, path, n_ppl=None, cbr=None, nt=None):
+        """-> (frame, results_r or None, pars dict or None).  With ``n_ppl`` / ``cbr`` / ``nt`` the capacity is sized for the
+        births of an ``nt``-day run (``calc_capacity`` plus the reference's 4 / sqrt(births) safety margin, model.py:124-137);
+        otherwise it is the live count."""
+        import json
+
+        path = str(path)
+        cols, recovered, meta = {}, None, None
+        loaded = False
+        if path.endswith((".h5", ".hdf5")):
+            try:
+                import h5py
+
+                if h5py.is_hdf5(path):
+                    with h5py.File(path, "r") as f:
+                        cols = {k: f["people"][k][...] for k in f["people"]}
+                        recovered = f["recovered"][...] if "recovered" in f else None
+                        meta = json.loads(f.attrs["meta"])
+                    loaded = True
+            except ImportError:
+                pass
+        if not loaded:
+            with np.load(path, allow_pickle=False) as z:
+                cols = {k[len("people/"):]: z[k] for k in z.files if k.startswith("people/")}
+                recovered = z["recovered"] if "recovered" in z.files else None
+                meta = json.loads(bytes(z["meta"]).decode())
+        count = int(meta["count"])
+        capacity = count
+        if n_ppl is not None and cbr is not None and nt is not None:
+            total = float(np.sum(n_ppl))
+            rate = float(np.mean(np.atleast_1d(cbr)))
+            births = float(calc_capacity(total, int(nt), rate)) - total
+            fudge = 1 + 4 / np.sqrt(births) if births > 0 else 1
+            capacity = max(count, int(fudge * (count + max(births, 0.0))))
+        frame = cls(capacity=capacity, initial_count=count)
+        for name, arr in cols.items():
+            frame.add_scalar_property(name, dtype=arr.dtype, default=0)
+            getattr(frame, name)[:count] = arr
+        frame._unborn_from = count  # slots [count, capacity) hold defaults: DiseaseState_ABM.init_from_file draws them (model.py:506-524)
+        return frame, recovered, meta.get("pars")
+
     def columns(self) -> dict:
         """name -> 1-D per-agent numpy column (length == capacity)."""
         return {k: v for k, v in self.__dict__.items()

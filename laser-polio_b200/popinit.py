@@ -128,24 +128,25 @@ def init_missed(n, n_missed, chronically_missed, seed, id_base=0):
     torch.cuda.current_stream().synchronize()
 
 
-def init_frame_device(people, pars, columns, device=None, pyramid=None, cum_deaths=None, chunk=1 << 26):
+def init_frame_device(people, pars, columns, device=None, pyramid=None, cum_deaths=None, chunk=1 << 26, start=0):
     """Fill the host columns of ``people`` (a LaserFrame) named in ``columns`` by drawing them on the GPU, ``chunk`` agents
     at a time (kernels + one D2H per column and chunk): what the components do when ``pars.device_init`` is set.
 
-    ``columns`` is any subset of {"heterogeneity", "timers", "demography", "missed"}."""
+    ``columns`` is any subset of {"heterogeneity", "timers", "demography", "missed"}; ``start`` restricts "heterogeneity" and
+    "timers" to the slots [start, capacity) (the unborn tail of a table loaded from a snapshot)."""
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     cap, count, seed = int(people.capacity), int(people.count), int(pars.seed)
     out = lambda name, lo, hi: torch.from_numpy(getattr(people, name)[lo:hi])  # noqa: E731
     if "heterogeneity" in columns:
         mean_dur = float(np.mean(pars.dur_inf(1000)))
-        for lo in range(0, cap, chunk):
+        for lo in range(int(start), cap, chunk):
             hi = min(cap, lo + chunk)
             r, f = (torch.empty(hi - lo, dtype=torch.float32, device=device) for _ in range(2))
             populate_heterogeneous_values(0, hi - lo, r, f, pars, seed=seed, id_base=lo, mean_dur_inf=mean_dur)
             out("acq_risk_multiplier", lo, hi).copy_(r)
             out("daily_infectivity", lo, hi).copy_(f)
     if "timers" in columns:
-        for lo in range(0, cap, chunk):
+        for lo in range(int(start), cap, chunk):
             hi = min(cap, lo + chunk)
             e, i, p = (torch.empty(hi - lo, dtype=torch.int8, device=device) for _ in range(3))
             init_timers(0, hi - lo, e, i, p, pars, seed=seed, id_base=lo)
