@@ -9,7 +9,8 @@ from time import perf_counter_ns
 
 import numpy as np
 
-__all__ = ["date", "daterange", "get_doy", "get_seasonality", "create_cumulative_deaths", "TimingStats"]
+__all__ = ["date", "daterange", "get_doy", "get_seasonality", "create_cumulative_deaths", "TimingStats", "save_sim_results",
+           "add_temporal_groupings", "results_long_table"]
 
 
 def date(value):
@@ -85,3 +86,61 @@ class TimingStats:
         width = max(map(len, self.stats))
         for label, ns in self.stats.items():
             logger.info(f"{label:<{width}} : {round(ns / 1000):11,} µsecs")
+
+
+# --------------------------------------------------------------------------- results long table
+RESULT_COLUMNS = (("S", "S"), ("E", "E"), ("I", "I"), ("R", "R"), ("P", "paralyzed"), ("births", "births"), ("deaths", "deaths"),
+                  ("new_exposed", "new_exposed"), ("potentially_paralyzed", "potentially_paralyzed"),
+                  ("new_potentially_paralyzed", "new_potentially_paralyzed"), ("new_paralyzed", "new_paralyzed"))
+
+
+def results_long_table(sim) -> dict:
+    """The columns of the reference's long results table (utils.py:716-747), one row per (timestep, node), time-major: the
+    ``[nt, nodes]`` results arrays are already laid out that way (on the device too), so every column is a flat view."""
+    nt, nodes = int(sim.nt), len(sim.nodes)
+    lookup = getattr(sim.pars, "node_lookup", None) or {}
+    names = np.array([lookup.get(n, {}).get("dot_name", "UNKNOWN") for n in range(nodes)], dtype=object)
+    data = {"timestep": np.repeat(np.arange(nt), nodes), "date": np.repeat(np.asarray(sim.datevec), nodes),
+            "node": np.tile(np.arange(nodes), nt), "dot_name": np.tile(names, nt)}
+    for column, attr in RESULT_COLUMNS:
+        arr = getattr(sim.results, attr, None)
+        data[column] = np.zeros(nt * nodes, np.int32) if arr is None else np.asarray(arr).reshape(nt * nodes)
+    return data
+
+
+def add_temporal_groupings(df, time_config):
+    """``time_period`` column from ``{"bins": [dates], "labels": [...]}`` (reference utils.py:1040-1073): left-closed periods."""
+    import pandas as pd
+
+    df = df.copy()
+    if "bins" in time_config and "labels" in time_config:
+        edges = [pd.Timestamp.min, *[pd.Timestamp(d) for d in time_config["bins"]], pd.Timestamp.max]
+        df["time_period"] = pd.cut(df["date"], bins=edges, labels=time_config["labels"], right=False)
+    return df
+
+
+def save_sim_results(sim, filename="simulation_results.h5", summary_config=None):
+    """Reference ``save_sim_results`` (utils.py:690-786): the long table as a DataFrame, written as HDF5 (key "results") when
+    pandas can (PyTables present) and the name ends in .h5, else as CSV next to it.  Temporal groupings are applied;
+    regional groupings need the reference's region YAMLs and are left to the caller (``dot_name`` is in the table)."""
+    from pathlib import Path
+
+    import pandas as pd
+
+    df = pd.DataFrame(results_long_table(sim))
+    df["dot_name"] = df["dot_name"].astype("category")
+    if summary_config is not None:
+        df["date"] = pd.to_datetime(df["date"])
+        if "time_periods" in summary_config:
+            df = add_temporal_groupings(df, summary_config["time_periods"])
+    path = Path(filename)
+    if path.suffix == ".h5":
+        try:
+            out = df.copy()
+            out["date"] = pd.to_datetime(out["date"])
+            out.to_hdf(path, key="results", mode="w", format="table", complevel=5)
+            return df
+        except ImportError:  # PyTables is not installed: keep the data, as CSV
+            path = path.with_suffix(".csv")
+    df.to_csv(path, index=False)
+    return df
