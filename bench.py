@@ -41,8 +41,8 @@ E2E_REPS = 3
 BENCH_R0 = 1.1  # sets daily_infectivity in the synthetic table; see build_pars
 ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1
 # DRAM bytes per agent of one tick_pass launch from the committed ncu --set full capture of this workload at 2.2e8 agents
-# (profiles/r1_fused_v23_220M_summary.csv: dram__bytes_read.sum 2.390 GB + dram__bytes_write.sum 0.274 GB, tick 40)
-NCU_TRAFFIC_BYTES_PER_AGENT = (2.390115e9 + 0.274141e9) / 220_000_000
+# (profiles/r1_fused_v25_220M_summary.csv: dram__bytes_read.sum 2.391 GB + dram__bytes_write.sum 0.275 GB, tick 40)
+NCU_TRAFFIC_BYTES_PER_AGENT = (2.391031e9 + 0.274833e9) / 220_000_000
 
 # algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
 # (f_S = 0.93, f_E = f_I = 0.01 synthetic mix; derivations in DESIGN.md section 4)
@@ -379,7 +379,7 @@ def run_b200(args):
                                    if world > 1 else "single GPU")},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC_BYTES_PER_AGENT * live0) if top == "tick_pass" else None,
-                     "traffic_source": "ncu --set full capture of one launch at 2.2e8 agents (profiles/r1_fused_v23_220M_summary.csv), scaled per agent",
+                     "traffic_source": "ncu --set full capture of one launch at 2.2e8 agents (profiles/r1_fused_v25_220M_summary.csv), scaled per agent",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
                      "tick_frac_of_14B_roofline": (ALGO_BYTES_PER_AGENT_TICK * value / world) / (peak * 1e9),
                      "kernel_share_of_step": kernel_share},
