@@ -197,6 +197,11 @@ typedef struct lpk_people {
     const int32_t *tile_node;        /* [ceil(capacity / 512)]: node id shared by every agent slot of the tile, or -1;
                                         NULL = always read node_id (lpk_build_tile_nodes fills it) */
     int64_t capacity;
+    /* device-only companions of the table, owned by the caller, filled by lpk_hot_build (see "Agenda bytes" below) */
+    uint8_t *hot;                    /* [lpk_hot_padded(capacity)] one agenda byte per slot, 16-byte aligned */
+    int32_t *pair_min_dod;           /* [lpk_hot_padded(capacity) / 256] earliest date_of_death among the alive agents of
+                                        each 256-slot pair (INT32_MAX: nobody); NULL when there is no date_of_death */
+    int32_t risk_e0;                 /* exponent bias of the 6-bit risk code: lpk_hot_risk_e0(largest finite risk in the table) */
 } lpk_people;
 
 #define LPK_F_PENDING 1u /* apply tick-1's exposure (q_prev / cdf_prev) and take tick-1's census */
@@ -254,6 +259,8 @@ typedef struct lpk_tick_args {
     /* scheduling hint (results do not depend on it): slots [0, uniform_agents) hold the node-contiguous initial population,
      * slots beyond it appended newborn cohorts; the pass hands the cohort region out first.  0 = unknown */
     int64_t uniform_agents;
+    uint32_t *work_counter; /* caller-owned device uint32 (one per table / stream): the pass zeroes it on `stream` and claims
+                               work units from it, so two tables on one device never share scheduling state */
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
@@ -261,6 +268,26 @@ typedef struct lpk_tick_args {
 int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, int64_t n_slots, int32_t *tile_node, void *stream);
 
 int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream);
+
+/* ---- Agenda bytes: what the pass streams (csrc/lpk_hot.cuh) ----------------------------------------------------------
+ * lpk_tick_pass reads ONE byte per agent per day, people->hot[i]:
+ *   bits 7:6 class: 00 susceptible, 01 inactive (payload 0 recovered, 1 dead / unborn), 10 exposed, 11 infectious
+ *   bits 5:0 susceptible: 6-bit upper bound of acq_risk_multiplier (4 steps per octave; 2^(e - risk_e0) * (1 + m / 4));
+ *            exposed / infectious: day of the agent's next event (E -> I, paralysis gate, I -> R) modulo 64
+ * and touches the reference's full-width columns only for agents with an event.  While an agent is exposed / infectious
+ * its countdown columns hold DEADLINES, (timer + tick) mod 256 -- exposure_timer while disease_state == 1,
+ * infection_timer while == 2, paralysis_timer while == 2 and strain == 0 -- so nothing is decremented on the days in
+ * between (the reference decrements daily, model.py:419-452; the tested values are identical, int8 wrap-around included).
+ *   lpk_hot_build   canonical columns (as every per-function entry point above reads them) -> agenda bytes + deadlines
+ *                   + pair_min_dod, for the table as it stands BEFORE tick `tick_next`.  *status = 2 if a risk exceeds the
+ *                   range of the code (risk_e0 too large); slots >= n_slots and the padding read as dead.
+ *   lpk_hot_settle  the inverse for the timers (deadline -> the value tick `tick_next` would test): call before handing
+ *                   the table to the per-function entry points or to the host.  disease_state, strain and every other
+ *                   column are kept canonical by the pass at all times. */
+int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t *status, void *stream);
+int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, void *stream);
+int64_t lpk_hot_padded(int64_t capacity); /* capacity rounded up to the pass's work unit (2048 agents) */
+int32_t lpk_hot_risk_e0(float max_risk);
 
 typedef struct lpk_node_args {
     uint32_t flags; /* LPK_F_PENDING: finish rows t-1 (E, I totals); LPK_F_DEATHS: tick t is a vital-dynamics tick */
@@ -338,6 +365,10 @@ typedef struct lpk_births_args {
     const float *acq_risk_multiplier;
     int64_t *sus, *exposure_fx;
     int32_t *risk_hist;
+    /* optional: agenda bytes of the table (lpk_people.hot / pair_min_dod / risk_e0); newborns enter as susceptibles */
+    uint8_t *hot;
+    int32_t *pair_min_dod;
+    int32_t risk_e0;
 } lpk_births_args;
 
 int lpk_vd_births(const lpk_births_args *args, void *stream);

@@ -22,7 +22,7 @@ FX_SCALE = float(2**30)
 EXPORTS = (
     "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
     "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
-    "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births",
+    "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births", "lpk_hot_build", "lpk_hot_settle", "lpk_hot_padded", "lpk_hot_risk_e0",
     "lpk_init_heterogeneity", "lpk_init_timers", "lpk_init_demography", "lpk_init_missed",
     "lpk_net_haversine", "lpk_net_gravity", "lpk_net_radiation", "lpk_net_row_normalize",
 )
@@ -55,6 +55,10 @@ def lib() -> C.CDLL:
             )
         _lib = C.CDLL(str(SO_PATH))
         _lib.lpk_last_error.restype = C.c_char_p
+        _lib.lpk_hot_padded.restype = C.c_int64
+        _lib.lpk_hot_padded.argtypes = [C.c_int64]
+        _lib.lpk_hot_risk_e0.restype = C.c_int32
+        _lib.lpk_hot_risk_e0.argtypes = [C.c_float]
         for name in EXPORTS:
             if not hasattr(_lib, name):
                 raise LpkError(f"liblpk.so does not export {name}")
@@ -108,7 +112,8 @@ class People(C.Structure):
     _fields_ = [(n, _VP) for n in (
         "disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
         "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
-        "daily_infectivity", "date_of_birth", "date_of_death", "tile_node")] + [("capacity", C.c_int64)]
+        "daily_infectivity", "date_of_birth", "date_of_death", "tile_node")] + [
+            ("capacity", C.c_int64), ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32)]
 
 
 class TickArgs(C.Structure):
@@ -129,7 +134,7 @@ class TickArgs(C.Structure):
         ("sia_vaccinated", _VP), ("sia_protected", _VP), ("sia_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
         ("beta_fx", _VP), ("E_cur", _VP), ("I_cur", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
-        ("uniform_agents", C.c_int64),
+        ("uniform_agents", C.c_int64), ("work_counter", _VP),
     ]
 
 
@@ -161,6 +166,7 @@ class BirthsArgs(C.Structure):
         ("cohort_ws", _VP), ("status", _VP), ("disease_state", _VP), ("node_id", _VP), ("date_of_birth", _VP),
         ("date_of_death", _VP), ("ri_timer", _VP), ("tile_node", _VP),
         ("acq_risk_multiplier", _VP), ("sus", _VP), ("exposure_fx", _VP), ("risk_hist", _VP),
+        ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32),
     ]
 
 

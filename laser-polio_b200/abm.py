@@ -731,7 +731,7 @@ class VitalDynamics_ABM:
         if cbr is not None:
             self.birth_rate[:] = (cbr[0] if (isinstance(cbr, (float, int)) or len(cbr) == 1) else np.array(cbr)) / (365 * 1000)
 
-    def births_args(self, dev, t, tile_node=None, tallies=None):
+    def births_args(self, dev, t, tile_node=None, tallies=None, hot=None):
         """Argument block of lpk_vd_births for tick t (device-side births, include/lpk.h V2)."""
         import torch
 
@@ -763,6 +763,11 @@ class VitalDynamics_ABM:
             sus, expo, hist = tallies
             a.acq_risk_multiplier = c["acq_risk_multiplier"].data_ptr()
             a.sus, a.exposure_fx, a.risk_hist = sus.data_ptr(), expo.data_ptr(), hist.data_ptr()
+        if hot is not None:  # fused path: newborns get their agenda byte (csrc/lpk_hot.cuh)
+            hot_bytes, pair_min_dod, e0 = hot
+            a.hot = hot_bytes.data_ptr()
+            a.pair_min_dod = pair_min_dod.data_ptr() if pair_min_dod is not None else None
+            a.risk_e0 = e0
         self._keep = (a,)
         return a
 

@@ -24,13 +24,38 @@
 #define LPK_WARPS (LPK_BLOCK / 32)
 #define LPK_FULL 0xFFFFFFFFu
 
+// Functions marked LPK_HD also compile for the host: tests/hot_model builds the per-agent logic of the fused pass
+// (lpk_hot.cuh) as a plain CPU program and holds it to the oracle without a GPU.
+#define LPK_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define LPK_MULHI(a, b) __umulhi((a), (b))
+#else
+#include <cmath>
+#include <cstring>
+#define LPK_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#endif
+LPK_HD uint32_t lpk_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+LPK_HD float lpk_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
 // ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+LPK_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t hi0 = LPK_MULHI(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = LPK_MULHI(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;
@@ -41,12 +66,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ void philox_agent(uint64_t seed, uint64_t idx, uint32_t tick, uint32_t stage,
+LPK_HD void philox_agent(uint64_t seed, uint64_t idx, uint32_t tick, uint32_t stage,
                                              uint32_t out[4]) {
     philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), tick, stage, (uint32_t)seed, (uint32_t)(seed >> 32), out);
 }
 
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+LPK_HD double u53(uint32_t hi, uint32_t lo) {
     const unsigned long long v = (((unsigned long long)hi << 32) | lo) >> 11;
     return (double)v * (1.0 / 9007199254740992.0);
 }
@@ -59,11 +84,11 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 // so ONE Philox block serves 8 agents in the streaming pass: the high half alone decides > 99.9 % of the trials
 // (h16 >= risk * tau * 2^16 cannot be a hit) and the low-half block is generated only for the rest.  The trial itself is
 // unchanged: hit iff X < floor(p * 2^32).
-__device__ __forceinline__ uint64_t expose_ctr(uint64_t id) { return ((id >> 8) << 5) | ((id >> 2) & 31u); }
-__device__ __forceinline__ int expose_hw(uint64_t id) { return (int)(((id >> 7) & 1u) * 4u + (id & 3u)); }
-__device__ __forceinline__ uint32_t half_word(const uint32_t x[4], int hw) { return (x[hw >> 1] >> (16 * (hw & 1))) & 0xFFFFu; }
+LPK_HD uint64_t expose_ctr(uint64_t id) { return ((id >> 8) << 5) | ((id >> 2) & 31u); }
+LPK_HD int expose_hw(uint64_t id) { return (int)(((id >> 7) & 1u) * 4u + (id & 3u)); }
+LPK_HD uint32_t half_word(const uint32_t x[4], int hw) { return (x[hw >> 1] >> (16 * (hw & 1))) & 0xFFFFu; }
 // the four words of the aligned quad starting at agent id0 (id0 % 4 == 0)
-__device__ __forceinline__ void expose_words_quad(uint64_t seed, uint64_t id0, uint32_t tick, uint32_t out[4]) {
+LPK_HD void expose_words_quad(uint64_t seed, uint64_t id0, uint32_t tick, uint32_t out[4]) {
     const uint64_t c = expose_ctr(id0);
     const int hw0 = expose_hw(id0);
     uint32_t h[4], l[4];
@@ -201,14 +226,28 @@ __device__ __forceinline__ void red_add(int64_t *p, long long v) {
     if (v) atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
 }
 
-__device__ __forceinline__ long long to_fx(double v) { return __double2ll_rn(v * LPK_FX_SCALE); }
+LPK_HD long long to_fx(double v) {
+#ifdef __CUDA_ARCH__
+    return __double2ll_rn(v * LPK_FX_SCALE);
+#else
+    return llrint(v * LPK_FX_SCALE);
+#endif
+}
+// a float weight (risk) in the 2^30 fixed point of the carried tallies
+LPK_HD long long risk_fx(float rk) {
+#ifdef __CUDA_ARCH__
+    return __float2ll_rn(rk * 1073741824.0f);
+#else
+    return llrintf(rk * 1073741824.0f);
+#endif
+}
 
 
 // ---------------------------------------------------------------- exposure probability and the risk histogram
 // Susceptible i of node n is exposed with probability p_i = 1 - exp(-risk_i * tau_n); tau_n solves
 // sum_i p_i = expected exposures of the node (include/lpk.h, T2/T3).  p_expose is specified with fmaf / floorf /
 // exact power-of-two scaling only, so a CPU restatement reproduces it bit for bit.
-__device__ __forceinline__ float p_expose(float x) {
+LPK_HD float p_expose(float x) {
     if (!(x > 0.f)) return 0.f;
     if (x < 0.0625f) {  // x - x^2/2 + x^3/6 - x^4/24 + x^5/120, relative error < 2e-9
         float t = fmaf(-x, 0.008333333767950535f, 0.0416666679084301f);
@@ -228,18 +267,22 @@ __device__ __forceinline__ float p_expose(float x) {
     r = fmaf(r, f, 0.24022436141967773f);
     r = fmaf(r, f, -0.6931470632553101f);
     r = fmaf(r, f, 1.0f);
-    const float scale = __uint_as_float((uint32_t)(127 - (int)n) << 23);  // 2^-n, n in [0, 24]
+    const float scale = lpk_u2f((uint32_t)(127 - (int)n) << 23);  // 2^-n, n in [0, 24]
     return 1.f - r * scale;
 }
 // x < floor(p * 2^32) with p in [0, 1]; p == 1 always hits
-__device__ __forceinline__ bool expose_test(float p, uint32_t x) {
+LPK_HD bool expose_test(float p, uint32_t x) {
+#ifdef __CUDA_ARCH__
     return (unsigned long long)x < __float2ull_rz(p * 4294967296.0f);
+#else
+    return (unsigned long long)x < (unsigned long long)(p * 4294967296.0f);
+#endif
 }
 
 // risk histogram: 8 bins per octave over [2^-12, 2^12), clamped; non-positive / NaN weights fall in bin 0
-__device__ __forceinline__ int risk_bin(float w) {
+LPK_HD int risk_bin(float w) {
     if (!(w > 0.f)) return 0;
-    const int b = (int)(__float_as_uint(w) >> 20) - ((127 - 12) << 3);
+    const int b = (int)(lpk_f2u(w) >> 20) - ((127 - 12) << 3);
     return b < 0 ? 0 : (b >= LPK_RISK_BINS ? LPK_RISK_BINS - 1 : b);
 }
 __device__ __forceinline__ double risk_bin_weight(int b) {  // representative weight: middle of the bin

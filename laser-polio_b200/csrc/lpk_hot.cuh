@@ -1,0 +1,340 @@
+// lpk_hot.cuh -- the "agenda" representation of the fused pass and the per-agent event logic on it.
+//
+// What an agent needs from the daily sweep depends on its class only:
+//   susceptible   one exposure trial (its risk against the node's tau)
+//   exposed       nothing until the day it turns infectious
+//   infectious    nothing until the day its paralysis gate opens (paralytic strain) or it recovers
+//   recovered / dead / unborn   nothing
+// so the sweep reads ONE byte per agent, the agenda byte `hot[i]`:
+//   bits 7:6  class   00 susceptible   01 inactive (payload 0 recovered, 1 dead / unborn)   10 exposed   11 infectious
+//   bits 5:0  payload susceptible: a 6-bit upper bound of acq_risk_multiplier (4 steps per octave, see risk_code)
+//                     exposed / infectious: the day of the agent's next event, modulo 64
+// and everything else is event driven: an agent whose payload equals today (or that passes the pre-test of the exposure
+// trial) is handed to hot_event, which works on the full-width columns of the reference.
+//
+// Deadline timers.  The reference tests a countdown timer and then decrements it on every step the agent spends in the
+// state that owns the timer (model.py:419-452), with int8 wrap-around; the value tested on tick t is timer0 - (t - t0).
+// While an agent is exposed / infectious the owning column therefore holds the DEADLINE  d = (timer + t) mod 256  (t = the
+// tick whose test would see `timer`), the value tested on any tick t is (int8)(d - t), and nothing is written on the days in
+// between.  Columns are converted back at the state's exit, at death, and by hot_settle_agent whenever the table leaves the
+// fused path (to_host(), a day run through the component kernels):
+//   exposure_timer    deadline form while disease_state == 1
+//   infection_timer   deadline form while disease_state == 2
+//   paralysis_timer   deadline form while disease_state == 2 and strain == 0 (the only strain whose timer runs, model.py:447)
+// All of it is exact modular arithmetic, so the columns the host reads back equal the reference's bit for bit
+// (tests/test_hot_model.py on the CPU, tests/test_gpu_fused.py on the device).
+#pragma once
+#include "lpk_common.cuh"
+
+#define HOT_S 0x00u
+#define HOT_R 0x40u
+#define HOT_DEAD 0x41u
+#define HOT_E 0x80u
+#define HOT_I 0xC0u
+#define HOT_LOOKAHEAD 63  // an event further away is reached through check-in events every 63 days
+
+// ring / event flags (bits 16+ of the second entry word; bits 0-15 carry the node)
+#define EV_CAND (1u << 16)   // susceptible that passed the pre-test of tick t-1's exposure trial
+#define EV_FIRE (1u << 17)   // exposed / infectious agent whose agenda day is today
+#define EV_DEATH (1u << 18)  // date_of_death <= t on a vital-dynamics tick
+#define EV_RI (1u << 19)     // routine-immunisation eligible today
+#define EV_SIA (1u << 20)    // inside today's campaign (node, age window, not chronically missed)
+
+// ---------------------------------------------------------------- risk code
+// 6-bit code c = e * 4 + m of the smallest value  ub(c) = 2^(e - e0) * (1 + m / 4)  that is >= risk.  e0 is a per-table
+// constant chosen so that the largest risk in the table fits (hot_risk_e0).  Non-positive / NaN risks never hit
+// (p_expose) and take code 0.  *over is set when the risk exceeds ub(63).
+LPK_HD int risk_code(float rk, int e0, bool *over) {
+    if (!(rk > 0.f)) return 0;
+    const uint32_t b = lpk_f2u(rk);
+    const int c = ((int)(b >> 23) - 127 + e0) * 4 + (int)((b >> 21) & 3u) + ((b & 0x1FFFFFu) ? 1 : 0);
+    if (c > 63) { if (over) *over = true; return 63; }
+    return c < 0 ? 0 : c;
+}
+LPK_HD float risk_code_ub(int c, int e0) { return ldexpf(1.0f + 0.25f * (float)(c & 3), (c >> 2) - e0); }
+// e0 for a table whose largest finite risk is rmax: ub(63) = 1.75 * 2^(15 - e0) >= rmax
+LPK_HD int hot_risk_e0(float rmax) {
+    if (!(rmax > 0.f)) return 0;
+    int ex;
+    const float fr = frexpf(rmax, &ex);  // rmax = fr * 2^ex, fr in [0.5, 1)
+    const int need = (fr > 0.875f) ? ex : ex - 1;  // smallest k with 1.75 * 2^k >= rmax
+    int e0 = 15 - need;
+    return e0 < -60 ? -60 : (e0 > 60 ? 60 : e0);
+}
+// In the sweep the code is decoded without arithmetic: (hot ^ 0xC0) placed at bits 21-28 of a float is
+// 2^(48 + e - 127) * (1 + m / 4) for a susceptible and at most 2^(33 - 127) for every other class, so
+//     U < fma(decoded, tau * 2^(95 - e0), 2^23 + 1),   U = 2^23 + h16
+// is the 16-bit pre-test of lpk_tick.cu with the agent's risk replaced by its upper bound.
+LPK_HD float hot_tau_scale(float tau, int e0) { return ldexpf(tau, 95 - e0); }
+
+LPK_HD uint8_t hot_due(int tick, int days) {
+    const int d = days < 0 ? 0 : (days > HOT_LOOKAHEAD ? HOT_LOOKAHEAD : days);
+    return (uint8_t)((tick + d) & 63);
+}
+
+// ---- byte-lane helpers (masks carry bit 0 of each byte) ------------------------------------------------------------
+LPK_HD uint32_t zero_bytes(uint32_t v) {  // exact, per byte: v == 0
+    return (~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) >> 7) & 0x01010101u;
+}
+LPK_HD uint32_t hot_mask_S(uint32_t h) { return (~(h | (h << 1)) >> 7) & 0x01010101u; }
+LPK_HD uint32_t hot_mask_alive(uint32_t h) { return zero_bytes(h ^ (HOT_DEAD * 0x01010101u)) ^ 0x01010101u; }
+// agents of the quad whose agenda day is today: class 1x and payload == tick mod 64.  today = (0xC0 | tick & 63) * 0x01010101
+LPK_HD uint32_t hot_due_word(uint32_t h, uint32_t today) { return (h | 0x40404040u) ^ today; }
+LPK_HD uint32_t any_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }  // != 0 iff some byte is 0
+
+// Pre-test of the exposure trial for the four agents of agenda word h (lpk_hot.cuh, risk code): bit 0 of byte k set when
+// agent k's 16-bit high half can still be a hit.  xa / xb: the quad's two words of the EXPOSE block (high halves of the
+// draws: agent 0 = low half of xa, 1 = high half of xa, 2 = low half of xb, 3 = high half of xb).  Six instructions per
+// agent; classes other than susceptible decode to < 2^-16 of the smallest susceptible bound and pass with probability
+// ~2^-16 (the caller masks with hot_mask_S when anything passed).
+LPK_HD uint32_t hot_pretest(uint32_t h, uint32_t xa, uint32_t xb, float tauS) {
+    const uint32_t KX = 0x18000000u, KM = 0x1FFFFFFFu, k23 = 0x4B000000u;
+    const float c = 8388609.0f;
+    const float d0 = lpk_u2f(((h << 21) ^ KX) & KM), d1 = lpk_u2f(((h << 13) ^ KX) & KM);
+    const float d2 = lpk_u2f(((h << 5) ^ KX) & KM), d3 = lpk_u2f((h >> 3) ^ KX);
+#ifdef __CUDA_ARCH__
+    const float u0 = __uint_as_float(__byte_perm(xa, k23, 0x7610)), u1 = __uint_as_float(__byte_perm(xa, k23, 0x7632));
+    const float u2 = __uint_as_float(__byte_perm(xb, k23, 0x7610)), u3 = __uint_as_float(__byte_perm(xb, k23, 0x7632));
+#else
+    const float u0 = lpk_u2f(k23 | (xa & 0xFFFFu)), u1 = lpk_u2f(k23 | (xa >> 16));
+    const float u2 = lpk_u2f(k23 | (xb & 0xFFFFu)), u3 = lpk_u2f(k23 | (xb >> 16));
+#endif
+    return ((u0 < fmaf(d0, tauS, c)) ? 1u : 0u) | ((u1 < fmaf(d1, tauS, c)) ? 0x100u : 0u) |
+           ((u2 < fmaf(d2, tauS, c)) ? 0x10000u : 0u) | ((u3 < fmaf(d3, tauS, c)) ? 0x1000000u : 0u);
+}
+
+
+// ---------------------------------------------------------------- canonical <-> agenda
+// Agenda byte of agent i as the table stands before tick t_next runs, converting the timers of exposed / infectious
+// agents to deadline form.  Returns the byte; *over: risk beyond the code range.
+LPK_HD uint8_t hot_build_agent(const lpk_people &P, int64_t i, int t_next, int e0, bool *over) {
+    const int8_t s = P.disease_state[i];
+    const uint8_t t8 = (uint8_t)t_next;
+    if (s == 0) return (uint8_t)(HOT_S | risk_code(P.acq_risk_multiplier[i], e0, over));
+    if (s == 1) {
+        const int8_t et = P.exposure_timer[i];
+        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)et + t8);
+        return (uint8_t)(HOT_E | hot_due(t_next, et));
+    }
+    if (s == 2) {
+        const int8_t it = P.infection_timer[i];
+        P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)it + t8);
+        int next = it < 0 ? 0 : it;
+        if (P.strain[i] == 0) {
+            const int8_t pt = P.paralysis_timer[i];
+            P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)pt + t8);
+            if (P.potentially_paralyzed[i] == -1) { const int g = pt < 0 ? 0 : pt; if (g < next) next = g; }
+        }
+        return (uint8_t)(HOT_I | hot_due(t_next, next));
+    }
+    return s == 3 ? (uint8_t)HOT_R : (uint8_t)HOT_DEAD;
+}
+// The inverse for the timers: deadline -> the value tick t_next would test.
+LPK_HD void hot_settle_agent(const lpk_people &P, int64_t i, int t_next) {
+    const int8_t s = P.disease_state[i];
+    const uint8_t t8 = (uint8_t)t_next;
+    if (s == 1) {
+        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)P.exposure_timer[i] - t8);
+    } else if (s == 2) {
+        P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)P.infection_timer[i] - t8);
+        if (P.strain[i] == 0) P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)P.paralysis_timer[i] - t8);
+    }
+}
+
+// ---------------------------------------------------------------- the event
+// What hot_event needs from the agent's columns, loaded one ring batch ahead of its use on the device.
+struct HotPre {
+    int8_t state, et, it;
+    float rk, inf;
+};
+LPK_HD HotPre hot_preload(const lpk_people &P, int64_t i, uint32_t fl) {
+    HotPre r;
+    r.state = P.disease_state[i];
+    r.et = P.exposure_timer[i];
+    r.it = P.infection_timer[i];
+    r.inf = P.daily_infectivity[i];
+    r.rk = (fl & (EV_CAND | EV_RI | EV_SIA | EV_DEATH)) ? P.acq_risk_multiplier[i] : 0.f;
+    return r;
+}
+// Node-level consequences of one event, applied by the caller (per-warp shared-memory accumulators on the device,
+// plain arrays in the host model).
+struct HotDelta {
+    int nd;
+    int8_t st;      // strain of the hit / the E, I and infectivity changes
+    int8_t dE, dI, dR;
+    uint8_t hit;    // exposure hit of tick t-1
+    uint8_t vx;     // 1 RI vaccinated, 2 RI protected, 4 IPV vaccinated, 8 SIA vaccinated, 16 SIA protected
+    uint8_t gate;   // 1 newly potentially paralysed, 2 newly paralysed
+    uint8_t died;   // 1 died, 2 was potentially paralysed, 4 was paralysed, 8 died susceptible
+    long long dbeta;  // change of the infectivity tally (2^30 fixed point)
+    long long efx;    // risk (fixed point) of an agent that left the susceptible class; hbin its histogram bin, else -1
+    int hbin;
+};
+
+// the exact exposure trial of tick t-1 for one susceptible (both Philox blocks; the sweep only pre-tests)
+LPK_HD bool hot_exact_trial(const lpk_tick_args &A, int64_t i, int nd, float rk) {
+    const float tau = A.q_prev[nd];
+    if (!(tau > 0.f)) return false;
+    const uint64_t id = (uint64_t)i + A.id_base;
+    const uint64_t c = expose_ctr(id);
+    const int hw = expose_hw(id);
+    uint32_t h[4], l[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), h);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE_LO, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), l);
+    const uint32_t X = (half_word(h, hw) << 16) | half_word(l, hw);
+#ifdef __CUDA_ARCH__
+    const float x = __fmul_rn(rk, tau);
+#else
+    const float x = rk * tau;
+#endif
+    return expose_test(p_expose(x), X);
+}
+LPK_HD int8_t hot_pick_strain(const lpk_tick_args &A, int64_t i, int nd) {  // model.py:1127-1141
+    uint32_t y[4];
+    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
+    const double u = u53(y[0], y[1]);
+    const int ns = A.n_strains;
+    for (int k = 0; k < ns; ++k)
+        if (u < A.cdf_prev[(int64_t)nd * ns + k]) return (int8_t)k;
+    return 0;
+}
+
+// One agent with something to do in the pass of tick t, in the reference's order: pending exposure trial of t-1
+// (model.py:1010-1149 replacement) -> death (1767-1781) -> disease-state step (419-452) -> RI draws (1825-1854) -> campaign
+// draws (2030-2059).  `fl` says why the sweep sent it; every condition is re-checked against the full-width columns.
+LPK_HD HotDelta hot_event(const lpk_people &P, const lpk_tick_args &A, int64_t i, int nd, uint32_t fl, const HotPre &pre) {
+    HotDelta d;
+    d.nd = nd; d.st = 0; d.dE = d.dI = d.dR = 0; d.hit = d.vx = d.gate = d.died = 0; d.dbeta = 0; d.efx = 0; d.hbin = -1;
+    const int tick = A.tick;
+    const uint8_t t8 = (uint8_t)tick;
+    const int8_t s_in = pre.state;
+    int8_t s = s_in, st = 0;
+    bool st_known = false, hot_set = false, fresh = false;
+    uint8_t hot_new = 0;
+    uint8_t etd = (uint8_t)pre.et;  // deadline of an exposed agent; the pre-drawn duration of a susceptible
+
+    // ---- 1. exposure trial of tick t-1 (agents born today were not there)
+    if ((fl & EV_CAND) && s == 0 && (A.flags & LPK_F_PENDING)) {
+        const bool born_today = (A.flags & LPK_F_DEATHS) && P.date_of_birth && P.date_of_birth[i] == tick;
+        if (!born_today && hot_exact_trial(A, i, nd, pre.rk)) {
+            s = 1;
+            st = hot_pick_strain(A, i, nd);
+            st_known = true;
+            P.strain[i] = st;
+            d.hit = 1; d.dE = 1;
+            d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk);
+            etd = (uint8_t)(etd + t8);  // the first step that tests the exposure timer is today's
+            fresh = true;
+        }
+    }
+    // ---- 2. death
+    if ((fl & EV_DEATH) && s >= 0 && P.date_of_death[i] <= tick) {
+        d.died = 1;
+        if (s == 0) { d.died |= 8; d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk); }
+        if (s == 1) {
+            if (!st_known) st = P.strain[i];
+            d.dE -= 1;
+            if (!fresh) P.exposure_timer[i] = (int8_t)(uint8_t)(etd - t8);
+        } else if (s == 2) {
+            st = P.strain[i];
+            d.dI -= 1;
+            d.dbeta -= to_fx((double)pre.inf * A.strain_r0_scalars[st]);
+            P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)pre.it - t8);
+            if (st == 0) P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)P.paralysis_timer[i] - t8);
+        } else if (s == 3) {
+            d.dR -= 1;
+        }
+        d.st = st;
+        if (P.potentially_paralyzed[i] == 1) d.died |= 2;
+        if (P.paralyzed[i] == 1) d.died |= 4;
+        P.disease_state[i] = -1;
+        P.hot[i] = HOT_DEAD;
+        return d;
+    }
+    // ---- 3. disease-state step of tick t
+    bool turned = false;
+    if (s == 1) {
+        const int8_t etv = (int8_t)(uint8_t)(etd - t8);  // the value today's step tests
+        if (etv <= 0) {
+            P.exposure_timer[i] = (int8_t)(etv - 1);
+            s = 2; turned = true;
+        } else {
+            if (fresh) P.exposure_timer[i] = (int8_t)etd;
+            hot_new = (uint8_t)(HOT_E | hot_due(tick, etv)); hot_set = true;
+        }
+    }
+    if (s == 2) {
+        if (!st_known) { st = P.strain[i]; st_known = true; }
+        const uint8_t itd = turned ? (uint8_t)((uint8_t)pre.it + t8) : (uint8_t)pre.it;
+        const int8_t itv = (int8_t)(uint8_t)(itd - t8);
+        const long long fxv = to_fx((double)pre.inf * A.strain_r0_scalars[st]);
+        if (turned) { d.dE -= 1; d.dI += 1; d.dbeta += fxv; }
+        const bool recover = itv <= 0;
+        const bool wild = st == 0;
+        uint8_t ptd = 0;
+        int8_t ptv = 0, pq = 0;
+        if (wild) {  // paralysis part, model.py:432-452
+            const uint8_t ptc = (uint8_t)P.paralysis_timer[i];
+            ptd = turned ? (uint8_t)(ptc + t8) : ptc;
+            ptv = (int8_t)(uint8_t)(ptd - t8);
+            pq = P.potentially_paralyzed[i];
+            if (ptv <= 0 && pq == -1) {
+                if (P.ipv_protected[i] == 0) {
+                    pq = 1;
+                    d.gate = 1;
+                    uint32_t x[4];
+                    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_PARALYSIS, x);
+                    if (u53(x[0], x[1]) < (double)A.p_paralysis) { P.paralyzed[i] = 1; d.gate = 3; }
+                } else {
+                    pq = 0;
+                }
+                P.potentially_paralyzed[i] = pq;
+            }
+        }
+        if (recover) {
+            P.infection_timer[i] = (int8_t)(itv - 1);
+            if (wild) P.paralysis_timer[i] = (int8_t)(ptv - 1);
+            d.dI -= 1; d.dbeta -= fxv; d.dR += 1;
+            s = 3;
+            hot_new = HOT_R; hot_set = true;
+        } else {
+            if (turned) {
+                P.infection_timer[i] = (int8_t)itd;
+                if (wild) P.paralysis_timer[i] = (int8_t)ptd;
+            }
+            int next = itv;
+            if (wild && pq == -1 && ptv < next) next = ptv;  // the gate is still closed: ptv > 0
+            hot_new = (uint8_t)(HOT_I | hot_due(tick, next)); hot_set = true;
+        }
+    }
+    // ---- 4. vaccine draws, after the agent's own disease-state step (the reference's run order)
+    if ((fl & EV_RI) && (A.flags & LPK_F_RI)) {
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_RI, x);
+        if (u53(x[0], x[1]) < A.vx_prob_ri[nd]) {
+            d.vx |= 1;
+            if (s == 0) { s = 1; st = (int8_t)A.ri_strain; d.vx |= 2; }
+        }
+        if (u53(x[2], x[3]) < A.vx_prob_ipv[nd]) { d.vx |= 4; P.ipv_protected[i] = 1; }
+    }
+    if ((fl & EV_SIA) && (A.flags & LPK_F_SIA)) {
+        uint32_t x[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
+        const double u = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
+        if (u < pv) {
+            d.vx |= 8;
+            if (s == 0 && u < pv * A.sia_vx_eff) { s = 1; st = (int8_t)A.sia_strain; d.vx |= 16; }
+        }
+    }
+    if (d.vx & 18) {  // left S through a vaccine: exposed from tomorrow's step on
+        P.strain[i] = st;
+        d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk);
+        const int8_t et0 = pre.et;
+        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)et0 + t8 + 1u);
+        hot_new = (uint8_t)(HOT_E | hot_due(tick, 1 + (et0 < 0 ? 0 : et0))); hot_set = true;
+    }
+    d.st = st;
+    if (s != s_in) P.disease_state[i] = s;
+    if (hot_set) P.hot[i] = hot_new;
+    return d;
+}

@@ -1,364 +1,56 @@
-// lpk_tick.cu -- the fused tick: ONE streaming pass over the agent table per simulated day.
+// lpk_tick.cu -- the fused tick: ONE sweep over the agent table per simulated day, reading one byte per agent.
 //
 // Pass for tick t, per agent, in the reference's order (include/lpk.h, "Fused tick"):
 //   pending tick t-1:  exposure trial (tx_infect)  ->  census (count_SEIRP)
-//   tick t:            deaths (get_deaths) -> disease state (disease_state_step) -> RI (fast_ri) -> tally (tx_step_prep)
+//   tick t:            deaths (get_deaths) -> disease state (disease_state_step) -> RI (fast_ri) -> SIA (fast_sia) -> tally
 // Every draw is Philox(seed; agent, tick, stage), so the fused pass reproduces the per-function kernels bit for bit
 // (tests/test_gpu_fused.py).
 //
-// The pass is instruction-issue bound, not bandwidth bound (profiles/r1_fused_v8_*: 534 warp-instructions per 128 agents
-// at 20 % of DRAM peak), so the design minimises instructions per agent:
-//   * per-node integer tallies (susceptibles, recovered, risk sum, risk histogram) are CARRIED from tick to tick and only
-//     corrected where an agent changes class, so the streaming loop counts nothing;
-//   * chunks of 32 K agents that lie in one node (nearly all of them) run a loop in which a lane owns 8 agents per
-//     iteration (its quads in an even / odd row pair) served by ONE Philox block: the 16-bit high halves reject > 99.9 %
-//     of the trials with 3 instructions per agent, the exact 32-bit test runs out of line for the rest;
-//   * the 2 % of agents that are exposed or infectious are pushed to a per-warp shared-memory ring and handled 32 at a
-//     time with all lanes busy (they sit in ~90 % of the 128-agent rows, so handling them in place made every warp walk
-//     the long disease-state path with one or two live lanes);
-//   * everything rare (a hit, a death, an RI-eligible agent, a node boundary) lives in __noinline__ functions.
+// Round 1's pass streamed 12 B per agent (state, five timer / flag byte columns, risk) and spent a third of its
+// instructions counting three timers down on byte lanes (profiles/r1_fused_v25_*: 389 M warp-instructions, 630 us at
+// 2.2e8 agents, issue bound).  This one keeps an AGENDA BYTE per agent (lpk_hot.cuh): class + either a 6-bit upper bound of
+// the agent's risk (susceptibles) or the day of its next event (exposed / infectious; timers are deadlines, nothing counts
+// down).  The sweep reads that byte only:
+//   * susceptibles: one Philox block per 8 agents, U = 2^23 + h16 against fma(decoded bound, tau', 2^23 + 1) -- the
+//     16-bit pre-test of round 1 with the risk replaced by its bound, so the candidates are a superset of the hits;
+//   * exposed / infectious: one byte-equality test of the payload against today (SWAR, 7 instructions per 8 agents);
+//   * recovered / dead / unborn slots: nothing.
+// Candidates and agents whose day has come (~1 % of the table per day) go to the warp's shared-memory ring and are
+// handled 32 at a time by hot_event on the full-width columns (exact trial, strain pick, state change, paralysis gate,
+// vaccine draws), with the node-level counts collected in per-warp accumulators.  Tallies (susceptibles, risk sums,
+// risk histogram, E / I / R census, infectivity) are CARRIED from tick to tick and only corrected by events.
+// Vital-dynamics days read date_of_death only for pairs whose earliest death date has come (pair_min_dod); RI days add
+// chronically_missed + ri_timer, campaign days chronically_missed + date_of_birth in targeted nodes.
+#include <climits>
 #include <cstdlib>
 
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched from the driver at run time, liblpk does not link libcuda)
-
 #include "lpk_host.cuh"
-#include "lpk_stages.cuh"
+#include "lpk_hot.cuh"
 
 struct PassParams {
-    CUtensorMap tmap;    // the six byte columns of the disease state as ONE 2-D tensor [column, agent] (use_tmap)
     lpk_people P;
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
     uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
-    uint32_t use_tmap;   // the byte columns lie at one constant stride (device.DeviceState's arena): one tensor copy per pair
 };
 
-#define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one iteration fit
-#define LPK_UNIT_LOG 3   // a work unit = 8 consecutive pairs of 128-agent rows (2048 agents), claimed by one warp at a time
+#define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one pair fit
+#define LPK_UNIT_LOG 3   // a work unit = 8 consecutive pairs of 128-agent rows (2048 agents = 2 KB of agenda bytes)
 #define LPK_UNIT_PAIRS (1 << LPK_UNIT_LOG)
+#define LPK_UNIT_AGENTS (256 << LPK_UNIT_LOG)
 
-// ------------------------------------------------------------------ rare paths (out of line, direct atomics)
-__device__ __forceinline__ DevRng stage_rng(const PassParams &pp) {
-    DevRng rng;
-    rng.seed = pp.A.seed; rng.tick = (uint32_t)pp.A.tick; rng.u1 = nullptr; rng.u2 = nullptr; rng.x = nullptr;
-    rng.id_base = pp.A.id_base;
-    return rng;
-}
-
-// The susceptible-side tallies (count, sum of risks, risk histogram per node) are carried from tick to tick and only
-// CORRECTED when an agent leaves the susceptible state (exposure hit, RI exposure, death) or is born; they are exact
-// integers, so the running values equal a from-scratch tally bit for bit (tests/test_gpu_fused.py).
-__device__ __noinline__ void leave_S(const PassParams &pp, int64_t i, int nd) {
-    const lpk_tick_args &A = pp.A;
-    const float rk = pp.P.acq_risk_multiplier[i];
-    atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)(-1ll));
-    red_add(&A.exposure_fx[nd], -__float2ll_rn(rk * 1073741824.0f));
-    atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
-}
-
-// bookkeeping of an exposure hit of tick t-1 (the agent's risk already in a register): categorical strain pick
-// (model.py:1127-1141), rows t-1, susceptible-side tallies; returns the strain
-__device__ __noinline__ int8_t expose_bookkeeping_rk(const PassParams &pp, int64_t i, int nd, float rk) {
-    const lpk_tick_args &A = pp.A;
-    uint32_t y[4];
-    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
-    const double r = u53(y[0], y[1]);
-    const int ns = A.n_strains;
-    int assigned = 0;
-    for (int s = 0; s < ns; ++s)
-        if (r < A.cdf_prev[(int64_t)nd * ns + s]) { assigned = s; break; }
-    pp.P.strain[i] = (int8_t)assigned;
-    atomicAdd(&A.new_exposed_prev[nd], 1);
-    atomicAdd(&A.new_exposed_by_strain_prev[(int64_t)nd * ns + assigned], 1);
-    atomicAdd(&A.tx_hits[nd], 1);
-    atomicAdd(reinterpret_cast<unsigned long long *>(&A.sus[nd]), (unsigned long long)(-1ll));
-    red_add(&A.exposure_fx[nd], -__float2ll_rn(rk * 1073741824.0f));
-    atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(rk)], -1);
-    return (int8_t)assigned;
-}
-// The exposed / infectious census by strain and the infectivity tally are CARRIED like the susceptible-side tallies:
-// E_cur / I_cur / beta_fx change only when an agent changes class, so the pass does nothing for an agent that merely
-// counts a timer down.  Slow-path form (direct atomics): the agent moves from class `from` to class `to` (-1 dead, 0 S,
-// 1 E, 2 I, 3 R); its strain must already be final.
-__device__ __noinline__ void carried_move(const PassParams &pp, int64_t i, int nd, int8_t from, int8_t to) {
-    const lpk_tick_args &A = pp.A;
-    if (from == to) return;
-    const bool ei = from == 1 || from == 2 || to == 1 || to == 2;
-    if (ei) {
-        const int st = pp.P.strain[i];
-        const int64_t c = (int64_t)nd * A.n_strains + st;
-        if (from == 1) atomicAdd(&A.E_cur[c], -1);
-        if (to == 1) atomicAdd(&A.E_cur[c], 1);
-        if (from == 2 || to == 2) {
-            const long long fx = to_fx((double)pp.P.daily_infectivity[i] * A.strain_r0_scalars[st]);
-            atomicAdd(&A.I_cur[c], to == 2 ? 1 : -1);
-            red_add(&A.beta_fx[c], to == 2 ? fx : -fx);
-        }
-    }
-    if (to == 3) atomicAdd(&A.R_cur[nd], 1);
-    if (from == 3) atomicAdd(&A.R_cur[nd], -1);
-}
-__device__ __noinline__ void expose_agent(const PassParams &pp, int64_t i, int nd) {
-    const int st = expose_bookkeeping_rk(pp, i, nd, pp.P.acq_risk_multiplier[i]);
-    const int64_t c = (int64_t)nd * pp.A.n_strains + st;
-    atomicAdd(&pp.A.tx_hits_by_strain[c], 1);
-    atomicAdd(&pp.A.E_cur[c], 1);
-}
-
-__device__ __noinline__ void kill_agent(const PassParams &pp, int64_t i, int nd, int8_t state_before) {
-    if (state_before == 0) leave_S(pp, i, nd);
-    else carried_move(pp, i, nd, state_before, -1);
-    atomicAdd(&pp.A.deaths[nd], 1);
-    if (pp.P.potentially_paralyzed[i] == 1) atomicAdd(&pp.A.dead_pp[nd], 1);
-    if (pp.P.paralyzed[i] == 1) atomicAdd(&pp.A.dead_par[nd], 1);
-}
-
-__device__ __noinline__ int8_t ds_agent_ol(const PassParams &pp, int64_t i, int8_t s, int nd) {
-    const lpk_people &P = pp.P;
-    const int8_t s2 = ds_agent(i, s, P.node_id, P.strain, P.exposure_timer, P.infection_timer, P.potentially_paralyzed, P.paralyzed,
-                               P.ipv_protected, P.paralysis_timer, (double)pp.A.p_paralysis, pp.A.new_potential, pp.A.new_paralyzed,
-                               stage_rng(pp));
-    carried_move(pp, i, nd, s, s2);
-    return s2;
-}
-
-// routine immunisation for one quad (reference model.py:1825-1854); returns the new state word
-__device__ __noinline__ uint32_t ri_quad(const PassParams &pp, int64_t base, int valid, uint32_t w) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const int step = A.ri_step;
-    const int64_t t = A.tick;
-    const bool first = (t == step), later = (t > step);
-    const uint32_t m = load_b4(reinterpret_cast<const int8_t *>(P.chronically_missed), base, valid, 1);
-    int tm[4];
-    load_s4(P.ri_timer, base, valid, tm);
-    bool touched = false;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int8_t s = byte_of(w, k);
-        if (s < 0 || byte_of(m, k) == 1) continue;
-        const int timer = tm[k] - step;
-        tm[k] = timer;
-        touched = true;
-        const bool eligible = first ? (timer <= 0 && timer >= -step) : (later && timer <= 0 && timer > -step);
-        if (!eligible) continue;
-        const int64_t i = base + k;
-        const int nd = P.node_id[i];
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
-        const double u1 = u53(x[0], x[1]), u2 = u53(x[2], x[3]);
-        if (u1 < A.vx_prob_ri[nd]) {
-            atomicAdd(&A.ri_vaccinated[nd], 1);
-            if (s == 0) {
-                w = set_byte(w, k, 1);
-                P.strain[i] = (int8_t)A.ri_strain;
-                leave_S(pp, i, nd);
-                const int64_t c = (int64_t)nd * A.n_strains + A.ri_strain;
-                atomicAdd(&A.E_cur[c], 1);
-                atomicAdd(&A.ri_protected[nd], 1);
-                atomicAdd(&A.new_exposed[nd], 1);
-                atomicAdd(&A.new_exposed_by_strain[c], 1);
-                atomicAdd(&A.ri_new_exposed_by_strain[c], 1);
-            }
-        }
-        if (u2 < A.vx_prob_ipv[nd]) { atomicAdd(&A.ipv_vaccinated[nd], 1); P.ipv_protected[i] = 1; }
-    }
-    if (touched) {
-        if (valid == 4) *reinterpret_cast<short4 *>(P.ri_timer + base) = make_short4((short)tm[0], (short)tm[1], (short)tm[2], (short)tm[3]);
-        else for (int k = 0; k < valid; ++k) P.ri_timer[base + k] = (int16_t)tm[k];
-    }
-    return w;
-}
-
-// one campaign event for one quad (reference model.py:2030-2059), direct atomics; returns the new state word
-__device__ __forceinline__ uint32_t sia_age_mask(const int4 &d, int tick, int lo, uint32_t span) {
-    return ((uint32_t)(tick - d.x - lo) <= span ? 1u : 0u) | ((uint32_t)(tick - d.y - lo) <= span ? 0x100u : 0u) |
-           ((uint32_t)(tick - d.z - lo) <= span ? 0x10000u : 0u) | ((uint32_t)(tick - d.w - lo) <= span ? 0x1000000u : 0u);
-}
-__device__ __noinline__ uint32_t sia_quad(const PassParams &pp, int64_t base, int valid, uint32_t w) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const uint32_t span = (uint32_t)(A.sia_max_age - A.sia_min_age);
-#pragma unroll 1
-    for (int k = 0; k < valid; ++k) {
-        const int8_t s = byte_of(w, k);
-        const int64_t i = base + k;
-        if (s < 0 || P.chronically_missed[i] == 1) continue;
-        if ((uint32_t)(A.tick - P.date_of_birth[i] - A.sia_min_age) > span) continue;
-        const int nd = P.node_id[i];
-        if (A.sia_targeted[nd] == 0) continue;
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
-        const double r = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
-        if (r < pv) {
-            atomicAdd(&A.sia_vaccinated[nd], 1);
-            if (s == 0 && r < pv * A.sia_vx_eff) {
-                w = set_byte(w, k, 1);
-                P.strain[i] = (int8_t)A.sia_strain;
-                leave_S(pp, i, nd);
-                const int64_t c = (int64_t)nd * A.n_strains + A.sia_strain;
-                atomicAdd(&A.E_cur[c], 1);
-                atomicAdd(&A.sia_protected[nd], 1);
-                atomicAdd(&A.new_exposed[nd], 1);
-                atomicAdd(&A.new_exposed_by_strain[c], 1);
-                atomicAdd(&A.sia_new_exposed_by_strain[c], 1);
-            }
-        }
-    }
-    return w;
-}
-
-// Generic quad: mixed node ids, the table's tail, or agents born after tick t-1's transmission.  One agent at a
-// time with direct atomics; reached for a few quads per node boundary, so its cost is irrelevant.
-__device__ __noinline__ uint32_t slow_quad(const PassParams &pp, int64_t b, int valid, uint32_t w, bool deaths, bool ri,
-                                           int64_t count_prev) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    uint32_t nw = w;
-    uint32_t x[4] = {0u, 0u, 0u, 0u};
-    if (pending) expose_words_quad(A.seed, (uint64_t)b + A.id_base, (uint32_t)(A.tick - 1), x);
-#pragma unroll 1
-    for (int k = 0; k < valid; ++k) {
-        int8_t s = byte_of(nw, k);
-        if (s < 0) continue;
-        const int64_t i = b + k;
-        const int nd = P.node_id[i];
-        if (pending && i < count_prev) {
-            if (s == 0) {
-                const float tau = A.q_prev[nd];
-                if (tau > 0.f && expose_test(p_expose(__fmul_rn(P.acq_risk_multiplier[i], tau)), x[k])) { expose_agent(pp, i, nd); s = 1; }
-            }
-        }
-        if (deaths && P.date_of_death[i] <= A.tick) { kill_agent(pp, i, nd, s); s = -1; }
-        if (s == 1 || s == 2) s = ds_agent_ol(pp, i, s, nd);
-        nw = set_byte(nw, k, s);
-    }
-    if (ri) nw = ri_quad(pp, b, valid, nw);
-    if (A.flags & LPK_F_SIA) nw = sia_quad(pp, b, valid, nw);
-    return nw;
-}
-
-// ------------------------------------------------------------------ exposure trial of a quad
-// High halves of the quad's four draws: x[2 * par], x[2 * par + 1] of the pair's EXPOSE block (par = row parity).
-// Pre-test, 3 instructions per agent: U = 2^23 + h16 as a float (one PRMT), T = fma(risk, tau * 2^16, 2^23 + 1); a hit needs
-// X < floor(p * 2^32) with p <= risk * tau, hence h16 < risk * tau * 2^16, hence U < T (the + 1 covers both roundings).
-__device__ __forceinline__ bool pretest_quad(uint32_t xa, uint32_t xb, const float4 &rk, float tau16) {
-    const uint32_t k23 = 0x4B000000u;
-    const float c = 8388609.0f;
-    return (__uint_as_float(__byte_perm(xa, k23, 0x7610)) < fmaf(rk.x, tau16, c)) |
-           (__uint_as_float(__byte_perm(xa, k23, 0x7632)) < fmaf(rk.y, tau16, c)) |
-           (__uint_as_float(__byte_perm(xb, k23, 0x7610)) < fmaf(rk.z, tau16, c)) |
-           (__uint_as_float(__byte_perm(xb, k23, 0x7632)) < fmaf(rk.w, tau16, c));
-}
-// The exact trial for the susceptibles of the quad (state word w): generates the low halves; returns the hit mask.
-__device__ __noinline__ uint32_t exact_quad(const PassParams &pp, uint32_t c0, uint32_t c1, int par, uint32_t xa, uint32_t xb, uint32_t w,
-                                            float4 rk, float tau) {
-    uint32_t l[4];
-    philox4x32_10(c0, c1, (uint32_t)(pp.A.tick - 1), LPK_STAGE_EXPOSE_LO, (uint32_t)pp.A.seed, (uint32_t)(pp.A.seed >> 32), l);
-    const uint32_t la = par ? l[2] : l[0], lb = par ? l[3] : l[1];
-    const uint32_t X[4] = {(xa << 16) | (la & 0xFFFFu), (xa & 0xFFFF0000u) | (la >> 16), (xb << 16) | (lb & 0xFFFFu),
-                           (xb & 0xFFFF0000u) | (lb >> 16)};
-    const float r[4] = {rk.x, rk.y, rk.z, rk.w};
-    const uint32_t mS = mask_S(w);
-    uint32_t hits = 0u;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (((mS >> (8 * k)) & 1u) && expose_test(p_expose(__fmul_rn(r[k], tau)), X[k])) hits |= 1u << (8 * k);
-    return hits;
-}
-
-// per-agent form of the pre-test: bit 0 of byte k set when agent k of the quad passes it
-__device__ __forceinline__ uint32_t pretest_mask(uint32_t xa, uint32_t xb, const float4 &rk, float tau16) {
-    const uint32_t k23 = 0x4B000000u;
-    const float c = 8388609.0f;
-    return ((__uint_as_float(__byte_perm(xa, k23, 0x7610)) < fmaf(rk.x, tau16, c)) ? 1u : 0u) |
-           ((__uint_as_float(__byte_perm(xa, k23, 0x7632)) < fmaf(rk.y, tau16, c)) ? 0x100u : 0u) |
-           ((__uint_as_float(__byte_perm(xb, k23, 0x7610)) < fmaf(rk.z, tau16, c)) ? 0x10000u : 0u) |
-           ((__uint_as_float(__byte_perm(xb, k23, 0x7632)) < fmaf(rk.w, tau16, c)) ? 0x1000000u : 0u);
-}
-// The exact exposure trial of tick t-1 for ONE susceptible agent (both Philox blocks regenerated): the streaming loop only
-// pre-tests and sends the few candidates to the ring, where 32 of them are decided at a time with all lanes busy
-// (profiles/r1_fused_v17_late_*: run in place it was 1-2 live lanes in 40 % of the iterations).
-__device__ __noinline__ bool exact_agent(const PassParams &pp, int64_t i, int nd, float rk) {
-    const lpk_tick_args &A = pp.A;
-    const float tau = __ldg(&A.q_prev[nd]);
-    if (!(tau > 0.f)) return false;
-    const uint64_t id = (uint64_t)i + A.id_base;
-    const uint64_t c = expose_ctr(id);
-    const int hw = expose_hw(id);
-    uint32_t h[4], l[4];
-    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), h);
-    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(A.tick - 1), LPK_STAGE_EXPOSE_LO, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), l);
-    const uint32_t hs = (hw & 2) ? ((hw & 4) ? h[3] : h[1]) : ((hw & 4) ? h[2] : h[0]);
-    const uint32_t ls = (hw & 2) ? ((hw & 4) ? l[3] : l[1]) : ((hw & 4) ? l[2] : l[0]);
-    const uint32_t sh = 16u * (uint32_t)(hw & 1);
-    const uint32_t X = (((hs >> sh) & 0xFFFFu) << 16) | ((ls >> sh) & 0xFFFFu);
-    return expose_test(p_expose(__fmul_rn(rk, tau)), X);
-}
-
-// ---- active-agent queue -------------------------------------------------------------------------------------
-// E / I agents (and fresh exposure hits) are appended to the warp's shared-memory ring and, whenever 32 have
-// accumulated, processed one per lane with all lanes busy.  An entry carries everything the handler needs; the handler
-// owns the agent's state byte from then on (the owning lane already stored the quad's word; both stores come from the
-// same warp, ordered by the warp-wide reduction in q_commit).
-// entry = {agent index (tables hold < 2^32 slots), node | state << 16 | hit << 20}
-struct ActiveRegs {
-    uint2 e;
-    int8_t ipvv;
-    float inf, rk;
-};
-struct WarpAcc;
-struct WarpQueue {
-    uint2 *q;
-    uint32_t *tail;  // shared, monotonic
-    uint32_t head;   // warp-uniform
-    int count;       // warp-uniform
-    bool loaded;     // warp-uniform: `pend` holds a batch whose loads are in flight
-    ActiveRegs pend;
-    WarpAcc *acc;
-};
-
-// census (rows t-1) -> disease state (tick t) -> infectivity tally (tick t) for one active agent, in two phases a ring
-// batch apart: active_load issues every load the agent can need (one round trip, nothing dependent), active_process runs
-// the state machine on those registers when the NEXT batch is loaded, so the scattered-load latency is spent streaming
-// (profiles/r1_fused_v10_postsia_*: 35 % of the stall samples sat in the handler waiting for its own loads).  Between the
-// two phases nobody else touches the agent: it is pushed once per pass, and the death / RI paths never push what they
-// handle themselves.
-// Ring entry: x = agent index, y = node | F << 16 | strain << 24 | exposure candidate << 26 with the flag byte
-//   F = state before tick t's disease-state step (bits 0-1) | E -> I today << 2 | I -> R today << 3 | exposure hit of t-1 << 4
-//       | RI-eligible << 5 | SIA-eligible << 6 | paralysis gate fires today << 7
-// The streaming loop has already counted the timers down and written the new state (ds_quad): the handler only does what
-// needs scattered columns -- class-change bookkeeping, the paralysis gate, the strain pick of a hit, the vaccine draws.
-#define EF_TE (1u << 18)
-#define EF_TI (1u << 19)
-#define EF_HIT (1u << 20)
-#define EF_RI (1u << 21)
-#define EF_SIA (1u << 22)
-#define EF_GATE (1u << 23)
-#define EF_CAND (1u << 26)  // susceptible that passed the pre-test of tick t-1's exposure trial: the handler decides
-__device__ __forceinline__ ActiveRegs active_load(const PassParams &pp, uint2 e) {
-    const lpk_people &P = pp.P;
-    const int64_t i = (int64_t)e.x;
-    ActiveRegs r;
-    r.e = e;
-    r.ipvv = (e.y & EF_GATE) ? P.ipv_protected[i] : (int8_t)0;
-    r.inf = (e.y & (EF_TE | EF_TI)) ? P.daily_infectivity[i] : 0.f;
-    // a hit left S; a susceptible that is here for RI / SIA may leave it
-    r.rk = ((e.y & EF_HIT) || ((e.y >> 16) & 3u) == 0u) ? P.acq_risk_multiplier[i] : 0.f;
-    return r;
-}
-// Per-warp accumulators of the handler's node-level counts (shared memory; lanes add with shared-memory atomics, lane 0
-// flushes).  The agents of a warp come from one node for many batches and all SMs work in few nodes at a time, so
-// per-agent global atomics land on a handful of addresses from every SM at once and serialise in L2 (diag_v11: a tighter
-// work window made the post-SIA pass 2x slower).  Counts are collected here and flushed with one global atomic per
-// counter when the warp's node changes.
+// ------------------------------------------------------------------ per-warp accumulators of the node-level counts
+// The agents of a warp come from one node for many ring batches and all SMs work in few nodes at a time, so per-agent
+// global atomics land on a handful of addresses from every SM at once and serialise in L2 (round 1, diag_v11).  Counts
+// are collected here (shared memory; lanes add with shared-memory atomics) and flushed by lane 0 with one global atomic
+// per counter when the warp's node changes.
 struct WarpAcc {
     int node;
     int E[LPK_MAX_STRAINS], I[LPK_MAX_STRAINS];  // changes of the carried exposed / infectious counts
     int H[LPK_MAX_STRAINS];                      // exposure hits of t-1 per strain (already included in E)
-    int R;                                       // recoveries of tick t
+    int R;                                       // change of the carried recovered count
     int riV, riP, ipvV, siaV, siaP;              // RI / SIA of tick t: vaccinated, protected (S -> E)
+    int Sdead;                                   // susceptibles that died
     long long beta[LPK_MAX_STRAINS];             // change of the carried infectivity tally (fixed point)
     long long expo;                              // risk (fixed point) of the agents that left S
 };
@@ -366,7 +58,7 @@ __device__ __forceinline__ void acc_clear(WarpAcc *a) {
 #pragma unroll
     for (int s = 0; s < LPK_MAX_STRAINS; ++s) { a->E[s] = 0; a->I[s] = 0; a->H[s] = 0; a->beta[s] = 0; }
     a->R = 0;
-    a->riV = a->riP = a->ipvV = a->siaV = a->siaP = 0;
+    a->riV = a->riP = a->ipvV = a->siaV = a->siaP = a->Sdead = 0;
     a->expo = 0;
 }
 // lane 0 only
@@ -407,148 +99,71 @@ __device__ __noinline__ void acc_flush(const PassParams &pp, WarpAcc *a) {
         atomicAdd(&A.new_exposed_by_strain[c], a->siaP);
         atomicAdd(&A.sia_new_exposed_by_strain[c], a->siaP);
     }
-    red_add(&A.sus[nd], -(long long)(hits + a->riP + a->siaP));
+    red_add(&A.sus[nd], -(long long)(hits + a->riP + a->siaP + a->Sdead));
     red_add(&A.exposure_fx[nd], -a->expo);
     red_add(&A.R_cur[nd], a->R);
     acc_clear(a);
 }
 __device__ __forceinline__ void acc_add(long long *p, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
 
-// the rare draws of the handler, out of line so that the common path stays compact
-__device__ __noinline__ int8_t pick_strain(const PassParams &pp, int64_t i, int nd) {  // model.py:1127-1141
-    const lpk_tick_args &A = pp.A;
-    uint32_t y[4];
-    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)(A.tick - 1), LPK_STAGE_STRAIN, y);
-    const double u = u53(y[0], y[1]);
-    const int ns = A.n_strains;
-    for (int k = 0; k < ns; ++k)
-        if (u < A.cdf_prev[(int64_t)nd * ns + k]) return (int8_t)k;
-    return 0;
-}
-// routine immunisation (model.py:1825-1854) and the campaign (model.py:2030-2059) for one agent in state s (after this
-// tick's disease-state step); returns s | vx << 8, vx bit 0 RI vaccinated, 1 RI protected, 2 IPV vaccinated, 3 SIA
-// vaccinated, 4 SIA protected
-__device__ __noinline__ uint32_t vaccine_draws(const PassParams &pp, int64_t i, int nd, int8_t s, uint32_t ey) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    uint32_t vx = 0u;
-    if ((ey >> 21) & 1u) {
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_RI, x);
-        if (u53(x[0], x[1]) < A.vx_prob_ri[nd]) {
-            vx |= 1u;
-            if (s == 0) { s = 1; P.strain[i] = (int8_t)A.ri_strain; vx |= 2u; }
-        }
-        if (u53(x[2], x[3]) < A.vx_prob_ipv[nd]) { vx |= 4u; P.ipv_protected[i] = 1; }
-    }
-    if ((ey >> 22) & 1u) {
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)A.tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
-        const double u = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
-        if (u < pv) {
-            vx |= 8u;
-            if (s == 0 && u < pv * A.sia_vx_eff) { s = 1; P.strain[i] = (int8_t)A.sia_strain; vx |= 16u; }
-        }
-    }
-    return (uint32_t)(uint8_t)s | (vx << 8);
-}
-
-// paralysis of one agent of the paralytic strain in the infected block (out of line: rare).  gate_only: the streaming loop
-// found the gate open (timer run out, potentially_paralyzed still -1) and has counted the timer down itself; else the whole
-// step on the agent's columns (an agent exposed yesterday that is infectious today: its strain was not known there).
-__device__ __noinline__ void paralysis_agent(const PassParams &pp, int64_t i, int nd, int8_t ipvv, bool gate_only) {
-    const lpk_people &P = pp.P;
-    const lpk_tick_args &A = pp.A;
-    int8_t pq = -1, par = 0;
-    int flags = 0;
-    if (gate_only) {
-        paralysis_gate(i, ipvv, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
-        P.potentially_paralyzed[i] = pq;
-    } else {
-        int8_t pt = P.paralysis_timer[i];
-        const int8_t pq0 = pq = P.potentially_paralyzed[i];
-        paralysis_step(i, P.ipv_protected[i], pt, pq, par, (double)A.p_paralysis, stage_rng(pp), flags);
-        P.paralysis_timer[i] = pt;
-        if (pq != pq0) P.potentially_paralyzed[i] = pq;
-    }
-    if (flags) {
-        atomicAdd(&A.new_potential[nd], 1);
-        if (flags & 2) { P.paralyzed[i] = 1; atomicAdd(&A.new_paralyzed[nd], 1); }
-    }
-}
+// ---- event ring ----------------------------------------------------------------------------------------------
+// Agents with something to do are appended to the warp's shared-memory ring and, whenever 32 have accumulated, handled
+// one per lane with all lanes busy (they sit in most 256-agent pairs, so handling them in place would make every warp
+// walk the long event path with one or two live lanes).  entry = {agent index (tables hold < 2^32 slots),
+// node | EV_* flags}.  The handler runs in two phases a ring batch apart: active_load issues the scattered loads,
+// active_process runs hot_event on those registers when the NEXT batch is loaded, so the load latency is spent sweeping.
+struct WarpQueue {
+    uint2 *q;
+    uint32_t *tail;  // shared, monotonic
+    uint32_t head;   // warp-uniform
+    int count;       // warp-uniform
+    bool loaded;     // warp-uniform: `pend` holds a batch whose loads are in flight
+    uint2 pend_e;
+    HotPre pend;
+    WarpAcc *acc;
+};
 
 // warp-collective: every lane calls it; `valid` lanes carry an agent
-__device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, bool valid, WarpAcc *acc, int lane) {
-    const lpk_people &P = pp.P;
+__device__ __noinline__ void active_process(const PassParams &pp, uint2 e, HotPre pre, bool valid, WarpAcc *acc, int lane) {
     const lpk_tick_args &A = pp.A;
-    const int64_t i = (int64_t)r.e.x;
-    uint32_t ey = valid ? r.e.y : 0u;
-    const int nd = (int)(int16_t)(ey & 0xFFFFu);
-    if (ey & EF_CAND) {  // a susceptible that passed the pre-test of tick t-1's exposure trial
-        if (exact_agent(pp, i, nd, r.rk)) {
-            // exposed yesterday: the streaming loop saw a susceptible, so today's disease-state step (model.py:419-431) runs here
-            const int8_t et = P.exposure_timer[i];
-            uint32_t f = EF_HIT | (1u << 16);
-            if (et <= 0) {
-                const int8_t it = P.infection_timer[i];
-                f |= EF_TE | (it <= 0 ? EF_TI : 0u);
-                P.infection_timer[i] = (int8_t)(it - 1);
-                r.inf = P.daily_infectivity[i];
-            }
-            P.exposure_timer[i] = (int8_t)(et - 1);
-            ey |= f;
-            P.disease_state[i] = (int8_t)(1 + ((f >> 18) & 1u) + ((f >> 19) & 1u));
-        }
-    }
-    const int8_t s0 = (int8_t)((ey >> 16) & 3u);
-    const int8_t sd = (int8_t)(s0 + ((ey >> 18) & 1u) + ((ey >> 19) & 1u));  // state after this tick's disease-state step
-    const bool hit = (ey & EF_HIT) != 0u;
-    int8_t st = (int8_t)((ey >> 24) & 3u), s = sd;
-    long long efx = 0;
-    uint32_t vx = 0u;
+    HotDelta d;
+    d.nd = -1; d.st = 0; d.dE = d.dI = d.dR = 0; d.hit = d.vx = d.gate = d.died = 0; d.dbeta = 0; d.efx = 0; d.hbin = -1;
     if (valid) {
-        if (hit) {  // exposure hit of tick t-1
-            st = pick_strain(pp, i, nd);
-            P.strain[i] = st;
-            efx = __float2ll_rn(r.rk * 1073741824.0f);
-            atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
-            if (st == 0 && (ey & EF_TE)) paralysis_agent(pp, i, nd, 0, false);  // infectious on the day after exposure
+        d = hot_event(pp.P, A, (int64_t)e.x, (int)(int16_t)(e.y & 0xFFFFu), e.y, pre);
+        // rare bookkeeping: direct atomics
+        if (d.hbin >= 0) atomicAdd(&A.risk_hist[(int64_t)d.nd * LPK_RISK_BINS + d.hbin], -1);
+        if (d.gate) {
+            atomicAdd(&A.new_potential[d.nd], 1);
+            if (d.gate & 2) atomicAdd(&A.new_paralyzed[d.nd], 1);
         }
-        if (ey & EF_GATE) paralysis_agent(pp, i, nd, r.ipvv, true);
-        if (ey & (EF_RI | EF_SIA)) {  // after the disease-state step (the reference's run order; it used the ipv_protected loaded before)
-            const uint32_t o = vaccine_draws(pp, i, nd, s, ey);
-            s = (int8_t)(o & 0xFFu);
-            vx = o >> 8;
-            if (vx & 18u) {  // left S through a vaccine
-                efx = __float2ll_rn(r.rk * 1073741824.0f);
-                atomicAdd(&A.risk_hist[(int64_t)nd * LPK_RISK_BINS + risk_bin(r.rk)], -1);
-                P.disease_state[i] = s;
-            }
+        if (d.died) {
+            atomicAdd(&A.deaths[d.nd], 1);
+            if (d.died & 2) atomicAdd(&A.dead_pp[d.nd], 1);
+            if (d.died & 4) atomicAdd(&A.dead_par[d.nd], 1);
         }
     }
+    const bool any = valid && (d.hit | d.dE | d.dI | d.dR | d.vx | (d.died & 8) | (d.efx != 0) | (d.dbeta != 0));
     // node-level counts, one group of same-node lanes at a time (one group except at a node boundary)
-    uint32_t todo = __ballot_sync(LPK_FULL, valid);
+    uint32_t todo = __ballot_sync(LPK_FULL, any);
     while (todo) {
-        const int nd0 = __shfl_sync(LPK_FULL, nd, __ffs(todo) - 1);
-        const bool mine = valid && nd == nd0;
+        const int nd0 = __shfl_sync(LPK_FULL, d.nd, __ffs(todo) - 1);
+        const bool mine = any && d.nd == nd0;
         if (lane == 0 && acc->node != nd0) { acc_flush(pp, acc); acc->node = nd0; }
         __syncwarp();
         if (mine) {
-            if (hit) { atomicAdd(&acc->H[st], 1); atomicAdd(&acc->E[st], 1); }
-            if (sd != s0) {  // s0 is E or I here
-                const long long fx = to_fx((double)r.inf * A.strain_r0_scalars[st]);
-                if (s0 == 1) atomicAdd(&acc->E[st], -1);
-                else { atomicAdd(&acc->I[st], -1); acc_add(&acc->beta[st], -fx); }
-                if (sd == 2) { atomicAdd(&acc->I[st], 1); acc_add(&acc->beta[st], fx); }
-                else atomicAdd(&acc->R, 1);
-            }
-            if (efx) acc_add(&acc->expo, efx);
-            if (vx) {
-                if (vx & 1u) atomicAdd(&acc->riV, 1);
-                if (vx & 2u) atomicAdd(&acc->riP, 1);
-                if (vx & 4u) atomicAdd(&acc->ipvV, 1);
-                if (vx & 8u) atomicAdd(&acc->siaV, 1);
-                if (vx & 16u) atomicAdd(&acc->siaP, 1);
+            if (d.hit) atomicAdd(&acc->H[d.st], 1);
+            if (d.dE) atomicAdd(&acc->E[d.st], (int)d.dE);
+            if (d.dI) atomicAdd(&acc->I[d.st], (int)d.dI);
+            if (d.dR) atomicAdd(&acc->R, (int)d.dR);
+            if (d.dbeta) acc_add(&acc->beta[d.st], d.dbeta);
+            if (d.efx) acc_add(&acc->expo, d.efx);
+            if (d.died & 8) atomicAdd(&acc->Sdead, 1);
+            if (d.vx) {
+                if (d.vx & 1u) atomicAdd(&acc->riV, 1);
+                if (d.vx & 2u) atomicAdd(&acc->riP, 1);
+                if (d.vx & 4u) atomicAdd(&acc->ipvV, 1);
+                if (d.vx & 8u) atomicAdd(&acc->siaV, 1);
+                if (d.vx & 16u) atomicAdd(&acc->siaP, 1);
             }
         }
         __syncwarp();
@@ -556,102 +171,6 @@ __device__ __noinline__ void active_process(const PassParams &pp, ActiveRegs r, 
     }
 }
 
-// Disease-state step of a node-uniform quad on byte lanes (reference model.py:419-431): every exposed agent's timer
-// counts down and those at <= 0 turn infectious; every agent in the infected block (infectious before, or just turned)
-// counts its timer down and those at <= 0 recover.  nw0: state word after tick t-1's hits and tick t's deaths; et / it /
-// sw / pt / pq: the quad's exposure_timer, infection_timer, strain, paralysis_timer and potentially_paralyzed words.  Timers
-// are written back here.
-struct DsQuad {
-    uint32_t nw, f, m;  // new state word; flag bytes of the agents that need the handler; their mask (bit 0 per byte)
-};
-// byte lanes by hand (the __v*4 intrinsics are emulated with ~10 instructions each): masks carry bit 0 of each byte
-__device__ __forceinline__ uint32_t bytes_le0(uint32_t x) {  // per byte, signed: byte <= 0  (zero, or bit 7 set)
-    const uint32_t nz = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 set iff the byte is not zero
-    return ((~nz | x) >> 7) & 0x01010101u;
-}
-__device__ __forceinline__ uint32_t bytes_dec(uint32_t x, uint32_t m) {  // per byte: x - m (m is 0 / 1), wrapping like int8
-    const uint32_t t = (x | 0x80808080u) - m;  // bit 7 forced: no borrow leaves a byte
-    return (t & 0x7F7F7F7Fu) | ((x ^ ~t) & 0x80808080u);
-}
-__device__ __forceinline__ DsQuad ds_quad(const lpk_people &P, int64_t b, uint32_t nw0, uint32_t hits, uint32_t et, uint32_t it, uint32_t sw,
-                                          uint32_t pt, uint32_t pq) {
-    const uint32_t K1 = 0x01010101u;
-    const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;  // state bytes are 0, 1, 2, 3 or 0xFF
-    const uint32_t tE = mE & bytes_le0(et);
-    const uint32_t mJ = mI | tE;
-    const uint32_t tI = mJ & bytes_le0(it);
-    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = bytes_dec(et, mE);
-    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = bytes_dec(it, mJ);
-    // the paralytic strain (0 of 0..3) in the infected block: its paralysis timer counts down here too, and the agents whose
-    // gate opens today (timer run out, potentially_paralyzed still -1 = 0xFF) go to the handler.  A hit's strain is picked by
-    // the handler, which then runs the whole step.
-    const uint32_t wild = mJ & ~(sw | (sw >> 1)) & ~hits;
-    uint32_t gate = 0u;
-    if (wild) {
-        gate = wild & bytes_le0(pt) & (pq >> 7);
-        *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = bytes_dec(pt, wild);
-    }
-    DsQuad o;
-    o.nw = nw0 + tE + tI;
-    o.f = (nw0 & 0x03030303u) | (tE << 2) | (tI << 3) | (hits << 4) | (gate << 7);
-    o.m = tE | tI | gate | hits;
-    return o;
-}
-// The same step without a branch, for the streaming loop: the two quads a lane owns run through it back to back, so the
-// compiler interleaves two independent dependency chains (the pass is bound by fixed-latency dependencies, not by issue
-// slots: profiles/r1_fused_v19_220M_*: stall_wait 2.2 cycles per instruction at 4 warps per scheduler).  No hits here.
-__device__ __forceinline__ DsQuad ds_quad_flat(const lpk_people &P, uint32_t b, uint32_t nw0, uint32_t et, uint32_t it, uint32_t sw,
-                                               uint32_t pt, uint32_t pq) {
-    const uint32_t K1 = 0x01010101u, K80 = 0x80808080u, K7F = 0x7F7F7F7Fu;
-    const uint32_t mE = nw0 & ~(nw0 >> 1) & K1, mI = (nw0 >> 1) & ~nw0 & K1;
-    // count down and test in one go: t = (x | 0x80) - m never borrows across bytes; where m = 1, bit 7 of t is clear iff the
-    // low 7 bits of x were zero, so "x <= 0" (zero, or bit 7 set) is (~t | x) >> 7; the decremented byte keeps t's low 7 bits
-    // and takes bit 7 from x ^ ~t
-    const uint32_t te = (et | K80) - mE;
-    const uint32_t tE = mE & ((~te | et) >> 7);
-    const uint32_t mJ = mI | tE;
-    const uint32_t ti = (it | K80) - mJ;
-    const uint32_t tI = mJ & ((~ti | it) >> 7);
-    const uint32_t wild = mJ & ~(sw | (sw >> 1));
-    const uint32_t tp = (pt | K80) - wild;
-    const uint32_t gate = wild & ((~tp | pt) >> 7) & (pq >> 7);
-    if (mE) *reinterpret_cast<uint32_t *>(P.exposure_timer + b) = (te & K7F) | ((et ^ ~te) & K80);
-    if (mJ) *reinterpret_cast<uint32_t *>(P.infection_timer + b) = (ti & K7F) | ((it ^ ~ti) & K80);
-    if (wild) *reinterpret_cast<uint32_t *>(P.paralysis_timer + b) = (tp & K7F) | ((pt ^ ~tp) & K80);
-    DsQuad o;
-    o.nw = nw0 + tE + tI;
-    o.f = nw0 | (tE << 2) | (tI << 3) | (gate << 7);  // flag bytes are read for the agents of o.m only (state byte 1 or 2)
-    o.m = tE | tI | gate;
-    return o;
-}
-// append the agents of mask m (bit 0 of byte k = agent idx0 + k); f = their flag bytes, g = their strain (bits 0-1) and
-// exposure-candidate (bit 2) bytes; returns how many
-__device__ __forceinline__ int q_push(uint2 *q, uint32_t *tail, uint32_t idx0, int nd, uint32_t f, uint32_t g, uint32_t m) {
-    const int cnt = __popc(m);
-    while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1u;
-        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
-        q[pos] = make_uint2(idx0 + (uint32_t)(bit >> 3), ((uint32_t)nd & 0xFFFFu) | (((f >> bit) & 0xFFu) << 16) | (((g >> bit) & 7u) << 24));
-    }
-    return cnt;
-}
-// the same for the two quads a lane owns in a row pair (B = A + 128 agents): one loop for both
-__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t fA, uint32_t gA, uint32_t mA,
-                                           uint32_t fB, uint32_t gB, uint32_t mB) {
-    uint32_t m = mA | (mB << 4);
-    const int cnt = __popc(m);
-    while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1u;
-        const bool rowB = (bit & 4) != 0;
-        const uint32_t f = rowB ? fB : fA, g = rowB ? gB : gA;
-        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
-        q[pos] = make_uint2(idxA + (uint32_t)(bit >> 3) + (rowB ? 128u : 0u),
-                            ((uint32_t)nd & 0xFFFFu) | (((f >> (bit & 24)) & 0xFFu) << 16) | (((g >> (bit & 24)) & 7u) << 24));
-    }
-    return cnt;
-}
 // every lane pushed `mine` entries: drain the ring 32 at a time (warp-uniform control flow)
 __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int mine, int lane) {
     Q.count += __reduce_add_sync(LPK_FULL, mine);
@@ -659,46 +178,38 @@ __device__ __forceinline__ void q_commit(const PassParams &pp, WarpQueue &Q, int
         __syncwarp();
         if (pp.debug & 1u) { Q.head += 32; Q.count -= 32; continue; }
         // process the batch loaded a commit ago FIRST: a call boundary waits for every load in flight, so the new batch's
-        // loads are issued after it and land while the warp streams the next pair (profiles/r1_fused_v12_*: with the
-        // loads issued before the call, 8 % of all stall samples sat on the call instruction)
-        if (Q.loaded) active_process(pp, Q.pend, true, Q.acc, lane);
-        Q.pend = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
+        // loads are issued after it and land while the warp sweeps the next pairs
+        if (Q.loaded) active_process(pp, Q.pend_e, Q.pend, true, Q.acc, lane);
+        Q.pend_e = Q.q[(Q.head + lane) & (QCAP - 1)];
+        Q.pend = hot_preload(pp.P, (int64_t)Q.pend_e.x, Q.pend_e.y);
         Q.loaded = true;
         Q.head += 32;
         Q.count -= 32;
     }
 }
 
-// out-of-line part of a death in a node-uniform quad: the agents in mask dm die on tick t (after tick t-1's pending
-// exposure); returns {new state word, remaining hits | remaining exposure candidates << 1}
-__device__ __noinline__ uint2 death_quad(const PassParams &pp, int64_t b, int nd, uint32_t nw, uint32_t hits, uint32_t cand, uint32_t dm) {
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t bit = 1u << (8 * k);
-        if (!(dm & bit)) continue;
-        int8_t s = byte_of(nw, k);
-        if (cand & bit) {  // the exposure trial of t-1 comes before the death of t: decide it now
-            cand &= ~bit;
-            if (exact_agent(pp, b + k, nd, pp.P.acq_risk_multiplier[b + k])) { hits |= bit; s = 1; }
-        }
-        if (hits & bit) { expose_agent(pp, b + k, nd); hits &= ~bit; }
-        kill_agent(pp, b + k, nd, s);
-        nw = set_byte(nw, k, -1);
-    }
-    return make_uint2(nw, hits | (cand << 1));
+__device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick) {
+    return (d.x <= tick ? 1u : 0u) | (d.y <= tick ? 0x100u : 0u) | (d.z <= tick ? 0x10000u : 0u) | (d.w <= tick ? 0x1000000u : 0u);
 }
-__device__ __forceinline__ uint32_t death_mask(const int4 &d, int tick, uint32_t w) {
-    return ((d.x <= tick ? 1u : 0u) | (d.y <= tick ? 0x100u : 0u) | (d.z <= tick ? 0x10000u : 0u) | (d.w <= tick ? 0x1000000u : 0u)) &
-           mask_alive(w);
+__device__ __forceinline__ int min_dod_left(const int4 &d, uint32_t keep) {  // earliest date of death among the agents in mask `keep`
+    int m = INT_MAX;
+    if (keep & 1u) m = min(m, d.x);
+    if (keep & 0x100u) m = min(m, d.y);
+    if (keep & 0x10000u) m = min(m, d.z);
+    if (keep & 0x1000000u) m = min(m, d.w);
+    return m;
 }
-
-// ---- routine immunisation in a node-uniform quad (reference model.py:1825-1854) -----------------------------------
+__device__ __forceinline__ uint32_t sia_age_mask(const int4 &d, int tick, int lo, uint32_t span) {
+    return ((uint32_t)(tick - d.x - lo) <= span ? 1u : 0u) | ((uint32_t)(tick - d.y - lo) <= span ? 0x100u : 0u) |
+           ((uint32_t)(tick - d.z - lo) <= span ? 0x10000u : 0u) | ((uint32_t)(tick - d.w - lo) <= span ? 0x1000000u : 0u);
+}
+// ---- routine immunisation in a quad (reference model.py:1825-1854) -----------------------------------------------
 // Every alive, not chronically missed agent's ri_timer goes down by the step (four int16 lanes at a time); an agent is
 // eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Eligible agents are the few in
 // the age window; they go to the ring and take their two draws in the handler, after their disease-state step.
-__device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t b, uint32_t w, uint32_t missed, uint2 tm) {
+__device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t b, uint32_t alive, uint32_t missed, uint2 tm) {
     const int step = pp.A.ri_step;
-    const uint32_t ok8 = mask_alive(w) & ~missed;  // missed bytes are 0 / 1
+    const uint32_t ok8 = alive & ~missed;  // missed bytes are 0 / 1
     if (!ok8) return 0u;
     const uint2 tn = make_uint2(__vsub2(tm.x, __byte_perm(ok8, 0u, 0x4140) * (uint32_t)step),
                                 __vsub2(tm.y, __byte_perm(ok8, 0u, 0x4342) * (uint32_t)step));
@@ -708,96 +219,96 @@ __device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t
     const uint32_t ex = __vcmpleu2(__vsub2(tn.x, lo2), span2), ey = __vcmpleu2(__vsub2(tn.y, lo2), span2);
     return __byte_perm(ex, ey, 0x6420) & ok8;
 }
+
+// append the agents of the two quads a lane owns in a row pair (B = A + 128 agents); F = per-agent flag bytes
+// (bit 0 candidate, 1 agenda day, 2 death, 3 RI, 4 SIA); returns how many
+__device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t FA, uint32_t FB) {
+    uint32_t m = (zero_bytes(FA) ^ 0x01010101u) | ((zero_bytes(FB) ^ 0x01010101u) << 4);
+    const int cnt = __popc(m);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        const bool rowB = (bit & 4) != 0;
+        const uint32_t f = ((rowB ? FB : FA) >> (bit & 24)) & 0x1Fu;
+        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
+        q[pos] = make_uint2(idxA + (uint32_t)(bit >> 3) + (rowB ? 128u : 0u), ((uint32_t)nd & 0xFFFFu) | (f << 16));
+    }
+    return cnt;
+}
+
 // ------------------------------------------------------------------ general pair (out of line): 256 agents that are not
-// all in one node or were not all present at tick t-1 (node boundaries, newborn cohorts, the table's tail).  One row at a
-// time, no software pipeline.  Returns how many agents this lane appended to the ring.
+// all in one node (node boundaries, appended cohorts, the table's tail).  One agent at a time; every agent with
+// something to do goes to the ring with its own node.  h: the lane's agenda words of the two rows.
 template <bool kDeaths, bool kRI, bool kSIA>
-__device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_t *q_tail, int64_t gp, int64_t n, int64_t count_prev,
+__device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_t *q_tail, int64_t gp, int64_t n, uint32_t hA, uint32_t hB,
                                          int lane) {
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    const int tick = A.tick;
+    const int tick = A.tick, e0 = P.risk_e0;
+    const uint32_t today = 0xC0u | ((uint32_t)tick & 63u);
     int mine = 0;
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
         const int64_t b = gp * 256 + r * 128 + lane * 4;
         const int valid = quad_valid(b, n);
-        if (!valid) continue;
-        const uint32_t w = load_b4(P.disease_state, b, valid);
-        if ((w & 0x80808080u) == 0x80808080u) continue;  // nobody alive
-        uint32_t nw = w, hits = 0u, cand = 0u, elig = 0u, camp = 0u, fl = 0u, sw = 0u;
-        int nd = -1;
-        bool fast = (valid == 4) && (!pending || b + 4 <= count_prev);
-        if (fast) {
-            const uint2 ids = *reinterpret_cast<const uint2 *>(P.node_id + b);
-            nd = (int)(int16_t)(ids.x & 0xFFFFu);
-            fast = ids.x == ids.y && (ids.x >> 16) == (ids.x & 0xFFFFu) && nd >= 0;
-        }
-        if (!fast) {
-            nw = slow_quad(pp, b, valid, w, kDeaths, kRI, count_prev);
-        } else {
-            if (pending && mask_S(w)) {  // exposure trial of tick t-1
+        const uint32_t h = r ? hB : hA;
+        if (!valid || h == HOT_DEAD * 0x01010101u) continue;
+        uint32_t x[4];
+        bool have_x = false;
+#pragma unroll 1
+        for (int k = 0; k < valid; ++k) {
+            const uint32_t hb = (h >> (8 * k)) & 0xFFu;
+            if (hb == HOT_DEAD) continue;
+            const int64_t i = b + k;
+            const int nd = P.node_id[i];
+            uint32_t fl = 0u;
+            if (pending && (hb >> 6) == 0u) {  // susceptible: pre-test of tick t-1's exposure trial
                 const float tau = __ldg(&A.q_prev[nd]);
                 if (tau > 0.f) {
-                    const uint64_t id0 = (uint64_t)b + A.id_base;
-                    const uint64_t c = expose_ctr(id0);
-                    const int par = (int)((id0 >> 7) & 1u);
-                    uint32_t x[4];
-                    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
-                                  (uint32_t)(A.seed >> 32), x);
-                    const float4 rk = __ldg(reinterpret_cast<const float4 *>(P.acq_risk_multiplier + b));
-                    // the 16-bit pre-test first, as in the streaming loop: newborn cohorts are all susceptible and never leave
-                    // this path (their 512-agent tiles span several nodes), and the exact trial is ~200 instructions
-                    const uint32_t xa = par ? x[2] : x[0], xb = par ? x[3] : x[1];
-                    if (pretest_quad(xa, xb, rk, tau * 65536.0f)) hits = exact_quad(pp, (uint32_t)c, (uint32_t)(c >> 32), par, xa, xb, w, rk, tau);
-                    nw |= hits;  // S (0) -> E (1)
+                    if (!have_x) {
+                        const uint64_t c = expose_ctr((uint64_t)b + A.id_base);
+                        philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, (uint32_t)A.seed,
+                                      (uint32_t)(A.seed >> 32), x);
+                        have_x = true;
+                    }
+                    const float U = 8388608.0f + (float)half_word(x, expose_hw((uint64_t)i + A.id_base));
+                    if (U < fmaf(risk_code_ub((int)(hb & 63u), e0), tau * 65536.0f, 8388609.0f)) fl |= EV_CAND;
                 }
             }
-            if (kDeaths) {
-                const int4 dd = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + b));
-                const uint32_t dm = death_mask(dd, tick, nw);
-                if (dm) { const uint2 o = death_quad(pp, b, nd, nw, hits, 0u, dm); nw = o.x; hits = o.y; }
+            if ((hb | 0x40u) == today) fl |= EV_FIRE;
+            bool dying = false;
+            if (kDeaths && P.date_of_death[i] <= tick) { fl |= EV_DEATH; dying = true; }
+            if ((kRI || kSIA) && !dying && P.chronically_missed[i] != 1) {
+                if (kRI) {
+                    const int step = A.ri_step;
+                    const int timer = (int)P.ri_timer[i] - step;
+                    P.ri_timer[i] = (int16_t)timer;
+                    const bool first = (tick == step);
+                    if (first ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step)) fl |= EV_RI;
+                }
+                if (kSIA && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age) &&
+                    A.sia_targeted[nd] != 0)
+                    fl |= EV_SIA;
             }
-            if (mask_EI(nw)) {  // disease-state step of tick t on byte lanes
-                sw = *reinterpret_cast<const uint32_t *>(P.strain + b);
-                const DsQuad d = ds_quad(P, b, nw, hits, *reinterpret_cast<const uint32_t *>(P.exposure_timer + b),
-                                         *reinterpret_cast<const uint32_t *>(P.infection_timer + b), sw,
-                                         *reinterpret_cast<const uint32_t *>(P.paralysis_timer + b),
-                                         *reinterpret_cast<const uint32_t *>(P.potentially_paralyzed + b));
-                nw = d.nw; fl = d.f; cand = d.m;
-            } else {
-                fl = (nw & 0x03030303u) | (hits << 4);  // no E / I in the quad: no hit either
+            if (fl) {
+                const uint32_t pos = atomicAdd(q_tail, 1u) & (QCAP - 1);
+                q[pos] = make_uint2((uint32_t)i, ((uint32_t)nd & 0xFFFFu) | fl);
+                ++mine;
             }
-            uint32_t missed = 0u;
-            if (kRI || kSIA) missed = *reinterpret_cast<const uint32_t *>(P.chronically_missed + b);
-            if (kRI) elig = ri_timers_quad(pp, b, nw, missed, *reinterpret_cast<const uint2 *>(P.ri_timer + b));
-            if (kSIA && A.sia_targeted[nd])
-                camp = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + b)), tick, A.sia_min_age,
-                                    (uint32_t)(A.sia_max_age - A.sia_min_age)) & mask_alive(nw) & ~missed;
         }
-        if (nw != w) store_b4(P.disease_state, b, valid, nw);
-        mine += q_push(q, q_tail, (uint32_t)b, nd, fl | (elig << 5) | (camp << 6), sw, cand | elig | camp);
     }
     return mine;
 }
 
 // ------------------------------------------------------------------ the pass
-// Unit of work: a PAIR of 128-agent rows (256 consecutive agents); a lane owns its quad in the even row (A) and in the
-// odd row (B).  Warps claim units of LPK_UNIT_PAIRS consecutive pairs from a global counter (see the kernel body).  A
-// warp's pairs form one sequence s = 0, 1, ... served by the warp's PRIVATE ring of kStages
-// shared-memory slots: one elected lane asks the TMA engine for the pair's columns (cp.async.bulk: 256 B of state, 1 KB
-// of risk, + date_of_death / chronically_missed / ri_timer on vital-dynamics / RI ticks) kStages iterations ahead, the
-// bytes land on the slot's mbarrier, and the warp reads its quads from shared memory.  The copies cost no registers and
-// no per-lane load instructions, so the depth of the memory pipeline is set by shared memory (40 KB per block), not by
-// occupancy.  The pair's node (tile table) and the node's exposure scale tau are looked up at issue time: with no force
-// of infection on the node neither risk nor random numbers are touched.
+// Unit of work: 8 consecutive PAIRS of 128-agent rows (2048 agents); a lane owns its quad in the even row (A) and in the
+// odd row (B) of every pair -- also the unit of the exposure RNG (one Philox block = 8 x 16-bit high halves).  Warps claim
+// runs of units from a global counter (guided self-scheduling) and fetch a unit's 2 KB of agenda bytes with ONE bulk copy
+// (cp.async.bulk on an mbarrier, issued by an elected lane one unit ahead) into a private double-buffered stage.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -817,11 +328,6 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// [6 columns, 256 agents] of the byte-column tensor starting at agent a0 -> 1536 contiguous bytes
-__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *map, uint32_t a0, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(a0), "r"(0), "r"(bar) : "memory");
-}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -830,308 +336,205 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
+template <int kWarps>
 struct PassSmem {
-    // a stage: state 256 | exposure_timer 256 | infection_timer 256 | strain 256 | paralysis_timer 256 | potentially_paralyzed 256
-    //          (= the [6, 256] box of the tensor copy) | risk 1024 | [date_of_death 1024] | [chronically_missed 256] | [ri_timer 512]
-    //          | [date_of_birth 1024]
-    static constexpr int kOffEt = 256, kOffIt = 512, kOffSt = 768, kOffPt = 1024, kOffPq = 1280, kOffRisk = 1536, kOffDod = 2560;
-    static constexpr int kOffMissed = kOffDod + (kDeaths ? 1024 : 0), kOffTimer = kOffMissed + 256;
-    static constexpr int kOffDob = kOffMissed + ((kRI || kSIA) ? 256 : 0) + (kRI ? 512 : 0);
-    static constexpr int kStageBytes = kOffDob + (kSIA ? 1024 : 0);
-    static constexpr int kFit = (227 * 1024 / kOcc - 1024 - kWarps * QCAP * 8 - 2048) / (kWarps * kStageBytes);  // kOcc blocks per SM
-    static constexpr int kStages = kFit >= 4 ? 4 : (kFit < 1 ? 1 : kFit);
     static constexpr int kOffQueue = 0;
-    static constexpr int kOffSlots = kOffQueue + kWarps * QCAP * 8;
-    static constexpr int kOffBars = kOffSlots + kWarps * kStages * kStageBytes;
-    static constexpr int kOffMeta = (kOffBars + kWarps * kStages * 8 + 15) & ~15;
-    static constexpr int kOffTail = kOffMeta + kWarps * kStages * 16;
+    static constexpr int kOffStage = kOffQueue + kWarps * QCAP * 8;          // 2 x 2 KB per warp
+    static constexpr int kOffBars = kOffStage + kWarps * 2 * LPK_UNIT_AGENTS;  // 2 mbarriers per warp
+    static constexpr int kOffTail = kOffBars + kWarps * 2 * 8;
     static constexpr int kOffAcc = (kOffTail + kWarps * 4 + 15) & ~15;
     static constexpr int kBytes = kOffAcc + kWarps * (int)sizeof(WarpAcc) + 32;
-    static_assert(kStages + 1 <= LPK_UNIT_PAIRS, "the producer may not run further ahead than one work unit");
-    static_assert(kOcc * (kBytes + 1024) <= 228 * 1024, "kOcc blocks per SM");
 };
 
 template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
 __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_constant__ PassParams pp) {
-    typedef PassSmem<kDeaths, kRI, kSIA, kWarps, kOcc> L;
-    constexpr int NST = L::kStages;
+    typedef PassSmem<kWarps> L;
     extern __shared__ __align__(128) unsigned char smem[];
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t count_prev = A.counts[0], n = A.counts[1];
+    const int64_t n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
-    const int tick = A.tick;
+    const int tick = A.tick, e0 = P.risk_e0;
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t total_pairs = (uint32_t)((n + 255) >> 8);
-    const uint32_t full_pairs = P.tile_node ? (uint32_t)(count_prev >> 8) : 0u;  // pairs whose 256 agents all existed at tick t-1
     const uint32_t n_units = (total_pairs + LPK_UNIT_PAIRS - 1) >> LPK_UNIT_LOG;
+    const uint32_t today = (0xC0u | ((uint32_t)tick & 63u)) * 0x01010101u;
+    const float tau_all = ldexpf(1.0f, e0);  // from here on every susceptible passes the pre-test anyway (bound of code 0 x tau >= 1)
 
-    unsigned char *slots = smem + L::kOffSlots + warp * NST * L::kStageBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBars) + warp * NST;
-    int4 *meta = reinterpret_cast<int4 *>(smem + L::kOffMeta) + warp * NST;
+    const uint32_t *stage = reinterpret_cast<const uint32_t *>(smem + L::kOffStage + warp * 2 * LPK_UNIT_AGENTS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBars) + warp * 2;
     WarpQueue Q;
     Q.q = reinterpret_cast<uint2 *>(smem + L::kOffQueue) + warp * QCAP;
     Q.tail = reinterpret_cast<uint32_t *>(smem + L::kOffTail) + warp;
     Q.head = 0u;
     Q.count = 0;
     Q.loaded = false;
+    Q.pend_e = make_uint2(0u, 0u);
+    Q.pend.state = 0; Q.pend.et = 0; Q.pend.it = 0; Q.pend.rk = 0.f; Q.pend.inf = 0.f;
     Q.acc = reinterpret_cast<WarpAcc *>(smem + L::kOffAcc) + warp;
     if (lane == 0) {
         Q.acc->node = -1;
         acc_clear(Q.acc);
         *Q.tail = 0u;
-        for (int k = 0; k < NST; ++k) mbar_init(&bars[k], 1u);
+        mbar_init(&bars[0], 1u);
+        mbar_init(&bars[1], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    // Work distribution: a warp claims RUNS of consecutive units (LPK_UNIT_PAIRS pairs each) from a global counter, so a
-    // warp that meets regions dense in E / I agents (an SIA wave hits whole nodes) simply claims less
-    // (profiles/r1_fused_v10_*: with static round-robin chunks the average SM was busy 58-66 % of the kernel's duration).
-    // Guided self-scheduling: a run is 1 / (3 x warps in the grid) of the units still unclaimed (at most 64, at least 1) --
-    // long runs while there is plenty of work, so that a warp stays in one node and its per-node accumulators are flushed
-    // rarely, single units at the end for balance.
-    // A warp's pairs form one sequence s = 0, 1, ...; the unit of sequence position s sits in register ua / ub (parity of
-    // s >> LPK_UNIT_LOG); the producer runs at most kStages + 1 <= LPK_UNIT_PAIRS positions ahead of the consumer, so two
-    // registers suffice.  The next run is claimed when the last unit of the current one is taken, a unit's worth of time
-    // before it is needed, from a counter value read another unit earlier: no claim latency is ever waited for.
+    // Work distribution: guided self-scheduling -- a run is 1 / (3 x warps in the grid) of the units still unclaimed (at
+    // most 64, at least 1): long runs while there is plenty of work, so that a warp stays in one node and its per-node
+    // accumulators are flushed rarely, single units at the end for balance.  The units behind the node-contiguous initial
+    // population (appended cohorts: mixed-node pairs, the slow general path) are handed out FIRST, one per claim.
     const uint32_t kNoUnit = 0xFFFFFFFFu;
     const uint32_t guide = 3u * gridDim.x * kWarps;
-    uint32_t ua = kNoUnit, ub = kNoUnit;
-    uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: the units of the current run not yet taken
-    bool exhausted = false;                // warp-uniform: a claim came back beyond the last unit
-    uint32_t claim_first = 0u, claim_cnt = 0u, seen = 0u;  // lane 0: the prefetched claim, the counter as last read
     const uint32_t stream_units = A.uniform_agents > 0 ? (uint32_t)(A.uniform_agents >> (8 + LPK_UNIT_LOG)) : n_units;
-    const uint32_t tail_units = n_units - (stream_units < n_units ? stream_units : n_units);  // warp-uniform
-    auto run_length = [&](uint32_t ctr) -> uint32_t {
-        if (ctr < tail_units) return 1u;
-        const uint32_t left = ctr < n_units ? n_units - ctr : 0u;
-        const uint32_t r = left / guide;
-        return r < 1u ? 1u : (r > 64u ? 64u : r);
-    };
-    if (lane == 0) {
-        claim_cnt = run_length(0u);
-        claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
-    }
-    uint32_t gp_looked = 0u;  // pair index of the position node_of looked up last
-    auto pair_of = [&](int s) -> uint32_t {
-        const uint32_t u = ((s >> LPK_UNIT_LOG) & 1) ? ub : ua;
-        return u == kNoUnit ? kNoUnit : (u << LPK_UNIT_LOG) + (uint32_t)(s & (LPK_UNIT_PAIRS - 1));
-    };
-    // node of the pair at position s (called once per s, in order): >= 0 all 256 agents in that node and present at tick
-    // t-1; -1 general handling; -2 no more work for this warp; -3 no such pair (past the end of the table)
-    auto node_of = [&](int s) -> int {
-        if ((s & (LPK_UNIT_PAIRS - 1)) == 0) {
-            uint32_t u = kNoUnit;
-            if (!exhausted) {
-                if (run_next >= run_end) {  // take the prefetched claim
-                    const uint32_t first = __shfl_sync(LPK_FULL, claim_first, 0), cnt = __shfl_sync(LPK_FULL, claim_cnt, 0);
-                    if (first >= n_units) exhausted = true;
-                    else { run_next = first; run_end = first + cnt < n_units ? first + cnt : n_units; }
-                }
-                if (!exhausted) {
-                    // claim index -> unit: the units behind the node-contiguous initial population (appended newborn cohorts:
-                    // their tiles span several nodes, so they run through the general path, ~50 us of a warp's time per unit)
-                    // are handed out FIRST, one per claim; claimed last they formed a tail of that length on every day
-                    // after the first births (plain day 0.54 -> 0.59 ms).  The streaming part follows in ascending order.
-                    const uint32_t c = run_next++;
-                    u = c < tail_units ? n_units - 1u - c : c - tail_units;
-                    if (run_next >= run_end && lane == 0) {  // the run's last unit: claim the next run now
-                        claim_cnt = run_length(seen);
-                        claim_first = atomicAdd(pp.unit_ctr, claim_cnt);
-                    }
-                    if (lane == 0) seen = *reinterpret_cast<volatile uint32_t *>(pp.unit_ctr);
+    const uint32_t tail_units = n_units - (stream_units < n_units ? stream_units : n_units);
+    uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: claim indices of the current run not yet taken
+    auto next_unit = [&]() -> uint32_t {   // warp-uniform result
+        if (run_next >= run_end) {
+            uint32_t first = 0u, cnt = 0u;
+            if (lane == 0) {
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(pp.unit_ctr);
+                if (seen < n_units) {
+                    const uint32_t left = n_units - seen;
+                    cnt = seen < tail_units ? 1u : left / guide;
+                    cnt = cnt < 1u ? 1u : (cnt > 64u ? 64u : cnt);
+                    first = atomicAdd(pp.unit_ctr, cnt);
+                } else {
+                    first = n_units;
                 }
             }
-            if ((s >> LPK_UNIT_LOG) & 1) ub = u; else ua = u;
+            first = __shfl_sync(LPK_FULL, first, 0);
+            cnt = __shfl_sync(LPK_FULL, cnt, 0);
+            if (first >= n_units) return kNoUnit;
+            run_next = first;
+            run_end = first + cnt < n_units ? first + cnt : n_units;
         }
-        const uint32_t gp = pair_of(s);
-        gp_looked = gp;
-        if (gp == kNoUnit) return -2;
-        if (gp >= total_pairs) return -3;  // beyond the table inside the last unit: nothing to do, but the warp goes on
-        return gp < full_pairs ? __ldg(&P.tile_node[gp >> 1]) : -1;
+        const uint32_t c = run_next++;
+        return c < tail_units ? n_units - 1u - c : c - tail_units;
     };
-    int tc_node = -2;  // one-entry cache of tau (and the campaign's target flag) per node: a warp stays in one node for long
-    float tc_tau = 0.f;
+    auto fetch = [&](uint32_t u, int buf) {  // one lane asks the copy engine for the unit's agenda bytes
+        if (elect_one()) {
+            const uint32_t bar = smem_u32(bars) + (uint32_t)buf * 8u;
+            fence_proxy_async_smem();  // the warp's reads of this buffer (previous use) precede the engine's writes
+            mbar_arrive_expect_tx(bar, LPK_UNIT_AGENTS);
+            tma_load(smem_u32(stage) + (uint32_t)buf * LPK_UNIT_AGENTS, P.hot + (int64_t)u * LPK_UNIT_AGENTS, LPK_UNIT_AGENTS, bar);
+        }
+    };
+
+    int tc_node = -2;  // one-entry cache of the node's exposure scale (and the campaign's target flag): a warp stays in one node for long
+    int tc_mode = 0;   // 0 no force of infection, 1 pre-test, 2 every susceptible is a candidate
+    float tc_tauS = 0.f;
     bool tc_sia = false;
     const int sia_lo = kSIA ? A.sia_min_age : 0;
     const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
-    int tn_next = node_of(0);  // node (and pair index) of the next pair to be requested, looked up one request ahead
-    uint32_t gp_next = gp_looked;
-    // request pair s into slot (warp-uniform; the elected lane talks to the TMA engine)
-    auto produce = [&](int s, int slot) {
-        const int tn = tn_next;
-        const uint32_t gp_req = gp_next;
-        tn_next = node_of(s + 1);
-        gp_next = gp_looked;
-        float tau = 0.f;
-        if (tn >= 0) {
+
+    uint32_t u_cur = next_unit();
+    if (u_cur != kNoUnit) fetch(u_cur, 0);
+    uint32_t par0 = 0u, par1 = 0u;  // phase parity of the two buffers
+    int buf = 0;
+#pragma unroll 1
+    while (u_cur != kNoUnit) {
+        const uint32_t u_nxt = next_unit();
+        if (u_nxt != kNoUnit) fetch(u_nxt, buf ^ 1);
+        // per-unit metadata while the copy lands: the unit's 4 tile nodes (lanes 0-3) and, on vital-dynamics ticks, its 8
+        // earliest death dates (lanes 0-7)
+        const uint32_t gp0 = u_cur << LPK_UNIT_LOG;
+        int tnv = -1, mdv = INT_MAX;
+        if (P.tile_node && lane < 4 && gp0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(gp0 >> 1) + lane]);
+        if (kDeaths && lane < LPK_UNIT_PAIRS && gp0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[gp0 + lane];
+        mbar_wait(&bars[buf], buf ? par1 : par0);
+        if (buf) par1 ^= 1u; else par0 ^= 1u;
+        const uint32_t *src = stage + buf * (LPK_UNIT_AGENTS / 4);
+#pragma unroll 1
+        for (int p = 0; p < LPK_UNIT_PAIRS; ++p) {
+            const uint32_t gp = gp0 + (uint32_t)p;
+            if (gp >= total_pairs) break;
+            const int tn = __shfl_sync(LPK_FULL, tnv, p >> 1);
+            const uint32_t hA = src[p * 64 + lane], hB = src[p * 64 + 32 + lane];
+            if (tn < 0) {
+                q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp, n, hA, hB, lane), lane);
+                continue;
+            }
             if (tn != tc_node) {
                 tc_node = tn;
-                tc_tau = pending ? __ldg(&A.q_prev[tn]) : 0.f;
+                const float tau = pending ? __ldg(&A.q_prev[tn]) : 0.f;
+                tc_mode = !(tau > 0.f) ? 0 : (tau >= tau_all ? 2 : 1);
+                tc_tauS = hot_tau_scale(tau, e0);
                 if (kSIA) tc_sia = __ldg(&A.sia_targeted[tn]) != 0;
             }
-            tau = tc_tau;
-        }
-        const bool camp = kSIA && tn >= 0 && tc_sia;
-        // What the copy engine needs goes through ONE warp reduction: its result lives in a uniform register, so the bulk
-        // copies below are issued straight from the uniform datapath by the elected lane.  With the operands in ordinary
-        // registers the compiler wraps every copy in an ELECT / R2UR x 4 / branch loop: 13 instructions per copy, 7-11
-        // copies per pair -- a third of the plain day's instructions (SASS of v19).
-        const uint32_t u = __reduce_max_sync(LPK_FULL, (gp_req & 0xFFFFFFu) | (tau > 0.f ? 1u << 24 : 0u) | (tn >= 0 ? 1u << 25 : 0u) |
-                                                           (camp ? 1u << 26 : 0u) | ((uint32_t)slot << 28));
-        if (elect_one()) {
-            meta[slot] = make_int4(tn, __float_as_int(tau) | (camp ? (int)0x80000000u : 0), (int)gp_req, 0);  // tau >= 0: the sign bit is free
-            const uint32_t uslot = u >> 28;
-            const uint32_t bar = smem_u32(bars) + uslot * 8u;
-            if (u & (1u << 25)) {
-                const int64_t a0 = (int64_t)(u & 0xFFFFFFu) * 256;
-                const uint32_t dst = smem_u32(slots) + uslot * (uint32_t)L::kStageBytes;
-                const bool risk = (u & (1u << 24)) != 0u, ucamp = kSIA && (u & (1u << 26)) != 0u;
-                fence_proxy_async_smem();  // the warp's reads of this slot (previous use) precede the engine's writes
-                const bool missed = kRI || ucamp;
-                mbar_arrive_expect_tx(bar, 1536u + (risk ? 1024u : 0u) + (kDeaths ? 1024u : 0u) + (missed ? 256u : 0u) + (kRI ? 512u : 0u) +
-                                               (ucamp ? 1024u : 0u));
-                if (pp.use_tmap) {
-                    tma_load_box(dst, &pp.tmap, (u & 0xFFFFFFu) << 8, bar);
-                } else {
-                    tma_load(dst, P.disease_state + a0, 256u, bar);
-                    tma_load(dst + L::kOffEt, P.exposure_timer + a0, 256u, bar);
-                    tma_load(dst + L::kOffIt, P.infection_timer + a0, 256u, bar);
-                    tma_load(dst + L::kOffSt, P.strain + a0, 256u, bar);
-                    tma_load(dst + L::kOffPt, P.paralysis_timer + a0, 256u, bar);
-                    tma_load(dst + L::kOffPq, P.potentially_paralyzed + a0, 256u, bar);
+            const int64_t bA = (int64_t)gp * 256 + lane * 4, bB = bA + 128;
+            // ---- exposure trial of tick t-1: pre-test on the risk bound; candidates are decided by the ring handler
+            uint32_t cA = 0u, cB = 0u;
+            if (tc_mode == 1) {
+                const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
+                uint32_t x[4];
+                philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
+                cA = hot_pretest(hA, x[0], x[1], tc_tauS);
+                cB = hot_pretest(hB, x[2], x[3], tc_tauS);
+            } else if (tc_mode == 2) {
+                cA = cB = 0x01010101u;
+            }
+            // ---- agenda: exposed / infectious agents whose day is today
+            const uint32_t vA = hot_due_word(hA, today), vB = hot_due_word(hB, today);
+            uint32_t ev = cA | cB | any_zero_byte(vA) | any_zero_byte(vB);
+            // ---- tick t: deaths, RI timers, campaign window (extra columns only where they can matter)
+            uint32_t dmA = 0u, dmB = 0u, eA = 0u, eB = 0u, sA = 0u, sB = 0u;
+            if (kDeaths) {
+                const int md = __shfl_sync(LPK_FULL, mdv, p);
+                if (md <= tick) {  // warp-uniform: somebody in this pair can die today
+                    const int4 dA = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bA));
+                    const int4 dB = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bB));
+                    const uint32_t aA = hot_mask_alive(hA), aB = hot_mask_alive(hB);
+                    dmA = death_mask(dA, tick) & aA;
+                    dmB = death_mask(dB, tick) & aB;
+                    const int left = __reduce_min_sync(LPK_FULL, min(min_dod_left(dA, aA & ~dmA), min_dod_left(dB, aB & ~dmB)));
+                    if (lane == 0) P.pair_min_dod[gp] = left;
                 }
-                if (risk) tma_load(dst + L::kOffRisk, P.acq_risk_multiplier + a0, 1024u, bar);
-                if (kDeaths) tma_load(dst + L::kOffDod, P.date_of_death + a0, 1024u, bar);
-                if (missed) tma_load(dst + L::kOffMissed, P.chronically_missed + a0, 256u, bar);
-                if (kRI) tma_load(dst + L::kOffTimer, P.ri_timer + a0, 512u, bar);
-                if (ucamp) tma_load(dst + L::kOffDob, P.date_of_birth + a0, 1024u, bar);
-            } else {
-                mbar_arrive(bar);
             }
-        }
-    };
-
-    // process pair s from slot, then re-arm the slot with pair s + NST
-    auto consume = [&](int s, int slot, uint32_t parity) -> bool {
-        mbar_wait(&bars[slot], parity);
-        const int4 mt = meta[slot];
-        const int tn = mt.x;
-        const float tau = __int_as_float(mt.y & 0x7FFFFFFF);
-        const bool camp = kSIA && mt.y < 0;
-        const unsigned char *src = slots + slot * L::kStageBytes;
-        uint32_t wA = 0u, wB = 0u;
-        if (tn >= 0) {
-            wA = *reinterpret_cast<const uint32_t *>(src + lane * 4);
-            wB = *reinterpret_cast<const uint32_t *>(src + 128 + lane * 4);
-        }
-        if (tn < 0) {  // nothing was copied for this position
-            __syncwarp();
-            produce(s + NST, slot);
-            if (tn == -2) return false;
-            if (tn == -1) q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)(uint32_t)mt.z, n, count_prev, lane), lane);
-            return true;
-        }
-        const int64_t gp = (int64_t)(uint32_t)mt.z;
-        const int nd = tn;
-        const int64_t bA = gp * 256 + lane * 4, bB = bA + 128;
-        uint32_t nwA = wA, nwB = wB, xcA = 0u, xcB = 0u;
-        uint32_t fA = 0u, fB = 0u, gA = 0u, gB = 0u, cA = 0u, cB = 0u;
-        // disease-state step of tick t on byte lanes, both rows back to back and without a branch, in the same basic block
-        // as the Philox rounds of the exposure trial: the pass is bound by fixed-latency dependencies (stall_wait 2.2 cycles
-        // per instruction at 4 warps per scheduler), and these are three independent chains.  Only class changes, the
-        // paralytic strain's gate and vaccine-eligible agents go to the ring (their draws follow their own step).
-        auto ds_both = [&]() {
-            gA = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + lane * 4);
-            gB = *reinterpret_cast<const uint32_t *>(src + L::kOffSt + 128 + lane * 4);
-            const DsQuad dA = ds_quad_flat(P, (uint32_t)bA, nwA, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + lane * 4),
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffIt + lane * 4), gA,
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPt + lane * 4),
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPq + lane * 4));
-            const DsQuad dB = ds_quad_flat(P, (uint32_t)bB, nwB, *reinterpret_cast<const uint32_t *>(src + L::kOffEt + 128 + lane * 4),
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffIt + 128 + lane * 4), gB,
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPt + 128 + lane * 4),
-                                           *reinterpret_cast<const uint32_t *>(src + L::kOffPq + 128 + lane * 4));
-            nwA = dA.nw; fA = dA.f; cA = dA.m;
-            nwB = dB.nw; fB = dB.f; cB = dB.m;
-        };
-        if (tau > 0.f) {  // exposure trial of tick t-1: pre-test here, candidates decided by the ring handler
-            const float4 rA = *reinterpret_cast<const float4 *>(src + L::kOffRisk + lane * 16);
-            const float4 rB = *reinterpret_cast<const float4 *>(src + L::kOffRisk + 512 + lane * 16);
-            const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
-            uint32_t x[4];
-            philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
-            const uint32_t sA0 = mask_S(nwA), sB0 = mask_S(nwB);  // susceptible at the end of tick t-1
-            if (!kDeaths) ds_both();
-            const float tau16 = tau * 65536.0f;
-            if (pretest_quad(x[0], x[1], rA, tau16) | pretest_quad(x[2], x[3], rB, tau16)) {
-                xcA = pretest_mask(x[0], x[1], rA, tau16) & sA0;
-                xcB = pretest_mask(x[2], x[3], rB, tau16) & sB0;
+            if (kRI || (kSIA && tc_sia)) {
+                const uint32_t mA = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bA);
+                const uint32_t mB = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bB);
+                const uint32_t aA = hot_mask_alive(hA) & ~dmA, aB = hot_mask_alive(hB) & ~dmB;
+                if (kRI) {
+                    eA = ri_timers_quad(pp, bA, aA, mA, *reinterpret_cast<const uint2 *>(P.ri_timer + bA));
+                    eB = ri_timers_quad(pp, bB, aB, mB, *reinterpret_cast<const uint2 *>(P.ri_timer + bB));
+                }
+                if (kSIA && tc_sia) {
+                    sA = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bA)), tick, sia_lo, sia_span) & aA & ~mA;
+                    sB = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bB)), tick, sia_lo, sia_span) & aB & ~mB;
+                }
             }
-        } else if (!kDeaths) {
-            ds_both();
-        }
-        if (kDeaths) {  // tick t
-            const int4 dA = *reinterpret_cast<const int4 *>(src + L::kOffDod + lane * 16);
-            const int4 dB = *reinterpret_cast<const int4 *>(src + L::kOffDod + 512 + lane * 16);
-            const uint32_t dmA = death_mask(dA, tick, nwA), dmB = death_mask(dB, tick, nwB);
-            if (dmA) { const uint2 o = death_quad(pp, bA, nd, nwA, 0u, xcA, dmA); nwA = o.x; xcA = (o.y >> 1) & 0x01010101u; }
-            if (dmB) { const uint2 o = death_quad(pp, bB, nd, nwB, 0u, xcB, dmB); nwB = o.x; xcB = (o.y >> 1) & 0x01010101u; }
-            ds_both();
-        }
-        uint32_t eA = 0u, eB = 0u, sA = 0u, sB = 0u;
-        if (kRI || camp) {
-            const uint32_t mA = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + lane * 4);
-            const uint32_t mB = *reinterpret_cast<const uint32_t *>(src + L::kOffMissed + 128 + lane * 4);
-            if (kRI) {
-                eA = ri_timers_quad(pp, bA, nwA, mA, *reinterpret_cast<const uint2 *>(src + L::kOffTimer + lane * 8));
-                eB = ri_timers_quad(pp, bB, nwB, mB, *reinterpret_cast<const uint2 *>(src + L::kOffTimer + 256 + lane * 8));
+            ev |= dmA | dmB | eA | eB | sA | sB;
+            int mine = 0;
+            if (ev) {  // rare per lane (a few per cent), common per warp: keep it short
+                const uint32_t FA = (cA & hot_mask_S(hA)) | (zero_bytes(vA) << 1) | (dmA << 2) | (eA << 3) | (sA << 4);
+                const uint32_t FB = (cB & hot_mask_S(hB)) | (zero_bytes(vB) << 1) | (dmB << 2) | (eB << 3) | (sB << 4);
+                mine = q_push_pair(Q.q, Q.tail, (uint32_t)bA, tn, FA, FB);
             }
-            if (camp) {
-                sA = sia_age_mask(*reinterpret_cast<const int4 *>(src + L::kOffDob + lane * 16), tick, sia_lo, sia_span) & mask_alive(nwA) & ~mA;
-                sB = sia_age_mask(*reinterpret_cast<const int4 *>(src + L::kOffDob + 512 + lane * 16), tick, sia_lo, sia_span) & mask_alive(nwB) & ~mB;
-            }
+            q_commit(pp, Q, mine, lane);
         }
-        __syncwarp();
-        produce(s + NST, slot);  // every read of the slot is done: re-arm it
-        if (nwA != wA) *reinterpret_cast<uint32_t *>(P.disease_state + bA) = nwA;
-        if (nwB != wB) *reinterpret_cast<uint32_t *>(P.disease_state + bB) = nwB;
-        q_commit(pp, Q, q_push_pair(Q.q, Q.tail, (uint32_t)bA, nd, fA | (eA << 5) | (sA << 6), (gA & 0x03030303u) | (xcA << 2),
-                                    cA | eA | sA | xcA, fB | (eB << 5) | (sB << 6), (gB & 0x03030303u) | (xcB << 2), cB | eB | sB | xcB), lane);
-        return true;
-    };
-
-    // one copy of the loop body (runtime slot index): the unrolled variant was 100 KB of code and stalled on instruction
-    // fetch (profiles/r1_fused_v10_*: no_instruction 8.4 per issue).  Once a position has no work none after it has, and
-    // nothing was requested from the TMA engine for those, so the warp can leave at the first one.
-    {
-#pragma unroll 1
-        for (int k = 0; k < NST; ++k) produce(k, k);
-        uint32_t parity = 0u;
-        int slot = 0;
-#pragma unroll 1
-        for (int s = 0;; ++s) {
-            if (!consume(s, slot, parity)) break;
-            if (++slot == NST) { slot = 0; parity ^= 1u; }
-        }
+        u_cur = u_nxt;
+        buf ^= 1;
     }
     __syncwarp();
-    if (Q.loaded) active_process(pp, Q.pend, true, Q.acc, lane);
+    if (Q.loaded) active_process(pp, Q.pend_e, Q.pend, true, Q.acc, lane);
     {
         const bool valid = lane < Q.count;
-        ActiveRegs last = {};
-        if (valid) last = active_load(pp, Q.q[(Q.head + lane) & (QCAP - 1)]);
-        active_process(pp, last, valid, Q.acc, lane);
+        uint2 e = make_uint2(0u, 0u);
+        HotPre last;
+        last.state = 0; last.et = 0; last.it = 0; last.rk = 0.f; last.inf = 0.f;
+        if (valid) { e = Q.q[(Q.head + lane) & (QCAP - 1)]; last = hot_preload(P, (int64_t)e.x, e.y); }
+        active_process(pp, e, last, valid, Q.acc, lane);
     }
     if (lane == 0) acc_flush(pp, Q.acc);
 }
 
 template <bool kDeaths, bool kRI, bool kSIA, int kWarps, int kOcc>
 static int launch_pass(const PassParams &pp, cudaStream_t st) {
-    typedef PassSmem<kDeaths, kRI, kSIA, kWarps, kOcc> L;
+    typedef PassSmem<kWarps> L;
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(k_tick_pass<kDeaths, kRI, kSIA, kWarps, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes),
@@ -1143,57 +546,7 @@ static int launch_pass(const PassParams &pp, cudaStream_t st) {
     k_tick_pass<kDeaths, kRI, kSIA, kWarps, kOcc><<<grid, kWarps * 32, L::kBytes, st>>>(pp);
     return LPK_OK;
 }
-// one 4-byte work counter per device, allocated on first use (the pass is launched on one stream per device)
-static uint32_t *pass_unit_counter() {
-    static uint32_t *ctr[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!ctr[dev] && cudaMalloc(&ctr[dev], 256) != cudaSuccess) ctr[dev] = nullptr;
-    return ctr[dev];
-}
-// The byte columns of the disease state as one 2-D uint8 tensor [6 columns, capacity agents]: possible when the caller
-// allocated them at one constant stride, in this order (device.DeviceState does); one tensor copy per pair then replaces six
-// bulk copies.  Encoded once per (base, stride, capacity); any failure just leaves the per-column copies in charge.
-typedef CUresult (*lpk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool pass_tensor_map(const lpk_people &P, CUtensorMap *out) {
-    static lpk_encode_tiled_fn encode = nullptr;
-    static bool looked = false;
-    static struct { const void *base; int64_t stride, capacity; CUtensorMap map; bool ok; } cache = {nullptr, 0, 0, {}, false};
-    const char *env = getenv("LPK_PASS_TMAP");
-    if (env && env[0] == '0') return false;
-    const int8_t *cols[6] = {P.disease_state, P.exposure_timer, P.infection_timer, P.strain, P.paralysis_timer, P.potentially_paralyzed};
-    const int64_t stride = cols[1] - cols[0];
-    if (stride < P.capacity || (stride & 15) || P.capacity >= (1ll << 31)) return false;
-    for (int k = 1; k < 6; ++k)
-        if (cols[k] - cols[k - 1] != stride) return false;
-    if (cache.base == cols[0] && cache.stride == stride && cache.capacity == P.capacity) {
-        if (cache.ok) *out = cache.map;
-        return cache.ok;
-    }
-    if (!looked) {
-        looked = true;
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<lpk_encode_tiled_fn>(fn);
-        else
-            (void)cudaGetLastError();
-    }
-    cache.base = cols[0]; cache.stride = stride; cache.capacity = P.capacity; cache.ok = false;
-    if (!encode) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)P.capacity, 6}, strides[1] = {(cuuint64_t)stride};
-    const cuuint32_t box[2] = {256, 6}, estr[2] = {1, 1};
-    cache.ok = encode(&cache.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(cols[0]), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    if (cache.ok) *out = cache.map;
-    return cache.ok;
-}
 
-// Block shape: 2 blocks of 8 warps per SM for every variant.  3 x 6 warps (96 registers) and 2 x 10 warps were measured
-// (-3 % / +1 %): the pass is bound by the ALU pipe, not by latency hiding.
 extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *stream) {
     REQUIRE(people && args, "tick_pass null struct");
     const lpk_people &P = *people;
@@ -1202,19 +555,21 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     REQUIRE(P.capacity > 0 && P.capacity < (1ll << 32) && A.counts, "tick_pass counts (tables hold < 2^32 slots)");
     REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer && P.potentially_paralyzed &&
                 P.paralyzed && P.ipv_protected && P.node_id && P.acq_risk_multiplier && P.daily_infectivity, "tick_pass agent columns");
-    REQUIRE(ALIGNED(P.disease_state, 4) && ALIGNED(P.node_id, 8) && ALIGNED(P.acq_risk_multiplier, 16), "tick_pass alignment");
+    REQUIRE(P.hot && ALIGNED(P.hot, 16), "tick_pass agenda bytes (lpk_hot_build fills them; 16-byte aligned, padded to 2048 agents)");
     REQUIRE((A.flags & LPK_F_STAGES) != 0, "tick_pass always runs the stages of its tick (LPK_F_STAGES)");
     REQUIRE((A.id_base & 255) == 0, "tick_pass id_base must be a multiple of 256");
+    REQUIRE(A.work_counter, "tick_pass work counter (caller-owned device uint32)");
     REQUIRE(A.new_potential && A.new_paralyzed && A.beta_fx && A.exposure_fx && A.sus && A.risk_hist && A.R_cur && A.tx_hits,
             "tick_pass stage outputs");
     REQUIRE(A.E_cur && A.I_cur && A.tx_hits_by_strain && A.new_exposed_prev && A.new_exposed_by_strain_prev, "tick_pass census");
     if (A.flags & LPK_F_PENDING) REQUIRE(A.q_prev && A.cdf_prev, "tick_pass pending exposure inputs");
     const bool deaths = (A.flags & LPK_F_DEATHS) != 0, ri = (A.flags & LPK_F_RI) != 0, sia = (A.flags & LPK_F_SIA) != 0;
-    if (sia) REQUIRE(P.date_of_birth && ALIGNED(P.date_of_birth, 16) && P.chronically_missed && ALIGNED(P.chronically_missed, 16) &&
+    if (sia) REQUIRE(P.date_of_birth && ALIGNED(P.date_of_birth, 16) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) &&
                          A.sia_targeted && A.vx_prob_sia && A.sia_vaccinated && A.sia_protected && A.sia_new_exposed_by_strain &&
                          A.new_exposed && A.new_exposed_by_strain && A.sia_max_age >= A.sia_min_age && A.sia_strain >= 0 &&
                          A.sia_strain < A.n_strains, "tick_pass SIA");
-    if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && A.deaths && A.dead_pp && A.dead_par, "tick_pass deaths");
+    if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && P.pair_min_dod && A.deaths && A.dead_pp && A.dead_par,
+                        "tick_pass deaths");
     if (ri) REQUIRE(P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
                         A.vx_prob_ipv && A.ri_vaccinated && A.ri_protected && A.ipv_vaccinated && A.new_exposed &&
                         A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0 && A.ri_strain >= 0 &&
@@ -1222,33 +577,87 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     PassParams pp;
     pp.P = P;
     pp.A = A;
-    pp.unit_ctr = pass_unit_counter();
-    pp.use_tmap = pass_tensor_map(P, &pp.tmap) ? 1u : 0u;
+    pp.unit_ctr = A.work_counter;
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("LPK_PASS_DEBUG"); dbg = e ? atoi(e) : 0; }
         pp.debug = (uint32_t)dbg;
     }
-    REQUIRE(pp.unit_ctr, "tick_pass work counter allocation");
-    REQUIRE(ALIGNED(P.disease_state, 16) && ALIGNED(P.exposure_timer, 16) && ALIGNED(P.infection_timer, 16) && ALIGNED(P.strain, 16) &&
-                ALIGNED(P.paralysis_timer, 16) && ALIGNED(P.potentially_paralyzed, 16) &&
-                (!ri || (ALIGNED(P.chronically_missed, 16) && ALIGNED(P.ri_timer, 16))),
-            "tick_pass alignment (bulk copies need 16-byte aligned columns)");
     cudaStream_t st = as_stream(stream);
     int rc;
     if (sia) {
-        if (deaths && ri) rc = launch_pass<true, true, true, 8, 2>(pp, st);
-        else if (deaths) rc = launch_pass<true, false, true, 8, 2>(pp, st);
-        else if (ri) rc = launch_pass<false, true, true, 8, 2>(pp, st);
-        else rc = launch_pass<false, false, true, 8, 2>(pp, st);
-    } else if (deaths && ri) rc = launch_pass<true, true, false, 8, 2>(pp, st);
-    else if (deaths) rc = launch_pass<true, false, false, 8, 2>(pp, st);
-    else if (ri) rc = launch_pass<false, true, false, 8, 2>(pp, st);
-    else rc = launch_pass<false, false, false, 8, 2>(pp, st);
+        if (deaths && ri) rc = launch_pass<true, true, true, 8, 3>(pp, st);
+        else if (deaths) rc = launch_pass<true, false, true, 8, 3>(pp, st);
+        else if (ri) rc = launch_pass<false, true, true, 8, 3>(pp, st);
+        else rc = launch_pass<false, false, true, 8, 3>(pp, st);
+    } else if (deaths && ri) rc = launch_pass<true, true, false, 8, 3>(pp, st);
+    else if (deaths) rc = launch_pass<true, false, false, 8, 3>(pp, st);
+    else if (ri) rc = launch_pass<false, true, false, 8, 3>(pp, st);
+    else rc = launch_pass<false, false, false, 8, 3>(pp, st);
     if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
     return LPK_OK;
 }
+
+// ------------------------------------------------------------------ canonical columns <-> agenda bytes
+__global__ void __launch_bounds__(256) k_hot_build(lpk_people P, int64_t n_slots, int64_t padded, int t_next, int32_t *status) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t h = HOT_DEAD;
+        if (i < n_slots) {
+            bool over = false;
+            h = hot_build_agent(P, i, t_next, P.risk_e0, &over);
+            if (over && status) *status = 2;
+        }
+        P.hot[i] = h;
+    }
+}
+// earliest date of death among the alive agents of every pair: one warp per pair
+__global__ void __launch_bounds__(256) k_pair_min_dod(lpk_people P, int64_t n_slots, int64_t n_pairs) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t gp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gp < n_pairs; gp += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        int m = INT_MAX;
+        for (int k = lane; k < 256; k += 32) {
+            const int64_t i = gp * 256 + k;
+            if (i < n_slots && P.disease_state[i] >= 0) m = min(m, P.date_of_death[i]);
+        }
+        m = __reduce_min_sync(LPK_FULL, m);
+        if (lane == 0) P.pair_min_dod[gp] = m;
+    }
+}
+__global__ void __launch_bounds__(256) k_hot_settle(lpk_people P, int64_t n_slots, int t_next) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x)
+        hot_settle_agent(P, i, t_next);
+}
+static inline int64_t hot_padded(int64_t capacity) { return (capacity + LPK_UNIT_AGENTS - 1) / LPK_UNIT_AGENTS * LPK_UNIT_AGENTS; }
+
+extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t *status, void *stream) {
+    REQUIRE(people, "hot_build null struct");
+    const lpk_people &P = *people;
+    REQUIRE(P.hot && P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer &&
+                P.potentially_paralyzed && P.acq_risk_multiplier, "hot_build columns");
+    REQUIRE(n_slots >= 0 && n_slots <= P.capacity, "hot_build n_slots");
+    cudaStream_t st = as_stream(stream);
+    const int64_t padded = hot_padded(P.capacity);
+    k_hot_build<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded, tick_next, status);
+    CUDA_TRY(cudaGetLastError(), "lpk_hot_build");
+    if (P.pair_min_dod && P.date_of_death) {
+        k_pair_min_dod<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256);
+        CUDA_TRY(cudaGetLastError(), "lpk_hot_build pair_min_dod");
+    }
+    return LPK_OK;
+}
+extern "C" int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, void *stream) {
+    REQUIRE(people, "hot_settle null struct");
+    const lpk_people &P = *people;
+    REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer, "hot_settle columns");
+    REQUIRE(n_slots >= 0 && n_slots <= P.capacity, "hot_settle n_slots");
+    if (n_slots == 0) return LPK_OK;
+    k_hot_settle<<<lpk_sm_count() * 8, 256, 0, as_stream(stream)>>>(P, n_slots, tick_next);
+    CUDA_TRY(cudaGetLastError(), "lpk_hot_settle");
+    return LPK_OK;
+}
+extern "C" int64_t lpk_hot_padded(int64_t capacity) { return hot_padded(capacity); }
+extern "C" int32_t lpk_hot_risk_e0(float max_risk) { return hot_risk_e0(max_risk); }
 
 // ------------------------------------------------------------------ tile -> node table
 __global__ void k_build_tile_nodes(const int16_t *__restrict__ node_id, int64_t first_tile, int64_t n_tiles, int64_t n_slots,

@@ -13,6 +13,7 @@
 // Newborns keep whatever was pre-drawn in their slot for every other column, exactly like the reference (timers, risk,
 // infectivity are drawn for the whole capacity at construction; ri_timer stays at its default).
 #include "lpk_host.cuh"
+#include "lpk_hot.cuh"
 #include "lpk_stages.cuh"
 
 __global__ void __launch_bounds__(1024) k_births_count(lpk_births_args a) {
@@ -54,8 +55,8 @@ __global__ void __launch_bounds__(1024) k_births_count(lpk_births_args a) {
     if (tid == 0) {
         int total = s_carry;
         const long long old_count = a.counts[1];
-        if (old_count + total > a.capacity) {  // LaserFrame.add would raise: flag it, create nobody
-            *a.status = 1;
+        if (old_count + total > a.capacity || (*a.status & 1)) {  // LaserFrame.add would raise: flag it (sticky: no later
+            *a.status |= 1;                                                // cohort is appended either), create nobody
             total = 0;
             for (int n = 0; n < a.n_nodes; ++n) { a.births_row[n] = 0; a.node_offsets_ws[n] = 0; }
         }
@@ -99,6 +100,12 @@ __global__ void k_births_fill(lpk_births_args a) {
         a.date_of_death[slot] = a.tick + newborn_lifespan(a, (uint64_t)slot);
         a.disease_state[slot] = 0;
         if (a.ri_timer && a.ri_newborn_timer >= 0) a.ri_timer[slot] = (int16_t)a.ri_newborn_timer;
+        if (a.hot) {  // fused path: the newborn's agenda byte (a susceptible) and its pair's earliest death date
+            bool over = false;
+            a.hot[slot] = (uint8_t)(HOT_S | risk_code(a.acq_risk_multiplier[slot], a.risk_e0, &over));
+            if (over) *a.status = 2;
+            if (a.pair_min_dod) atomicMin(&a.pair_min_dod[slot >> 8], a.date_of_death[slot]);
+        }
         if (a.sus) {  // fused path: the susceptible-side tallies are carried incrementally (lpk_tick.cu)
             const float rk = a.acq_risk_multiplier[slot];
             atomicAdd(reinterpret_cast<unsigned long long *>(&a.sus[lo]), 1ull);

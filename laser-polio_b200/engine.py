@@ -83,6 +83,17 @@ class FusedEngine:
         if sim.t > 0:  # resuming mid-run: re-base the incremental paralysis census on the last logged row
             self.cur_potp.copy_(dev.res["potentially_paralyzed"][sim.t - 1])
             self.cur_p.copy_(dev.res["paralyzed"][sim.t - 1])
+        # agenda bytes (csrc/lpk_hot.cuh): the one byte per agent the pass streams, the earliest death date of every
+        # 256-slot pair, the pass's work counter; the exponent bias of the 6-bit risk code comes from the largest risk
+        padded = int(_lpk.lib().lpk_hot_padded(cap))
+        self.hot = torch.empty(padded, dtype=torch.uint8, device=d)
+        self.pair_min_dod = torch.empty(padded // 256, dtype=torch.int32, device=d) if "date_of_death" in c else None
+        self.work_counter = torch.zeros(64, dtype=torch.int32, device=d)
+        risk = c["acq_risk_multiplier"]
+        rmax = float(torch.where(torch.isfinite(risk), risk, torch.zeros_like(risk)).max().item()) if risk.numel() else 1.0
+        if not bool(torch.isfinite(risk).all().item()):
+            raise ValueError("acq_risk_multiplier must be finite")
+        self.hot_valid = False  # True while exposure / infection / paralysis timers of E / I agents are deadlines (lpk_hot.cuh)
         P = People()
         for name in ("disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
                      "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
@@ -90,8 +101,11 @@ class FusedEngine:
             setattr(P, name, dp(c.get(name)))
         P.tile_node = dp(self.tile_node)
         P.capacity = cap
+        P.hot, P.pair_min_dod = dp(self.hot), dp(self.pair_min_dod)
+        P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
-        self.rebase_tallies()
+        if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
+            self.rebase_tallies(sim.t)
 
     # ------------------------------------------------------------------ helpers
     def rebuild_tiles(self, first_agent: int):
@@ -100,10 +114,19 @@ class FusedEngine:
                                               C.c_int64(self.sim.people.capacity), _lpk.ptr(self.tile_node), stream_handle()),
               "lpk_build_tile_nodes")
 
-    def rebase_tallies(self):
-        """From-scratch susceptible-side tallies of the table as it stands (engine start, and after any tick that ran
-        through the components, whose kernels do not maintain the carried values)."""
+    def settle(self, t_next):
+        """Deadline timers of the exposed / infectious agents -> the countdown values tick ``t_next`` would test: the
+        table is canonical again (what the per-function kernels and the host read)."""
+        if self.hot_valid:
+            check(_lpk.lib().lpk_hot_settle(C.byref(self.P), C.c_int64(self.dev.sync_count()), C.c_int32(t_next), stream_handle()),
+                  "lpk_hot_settle")
+            self.hot_valid = False
+
+    def rebase_tallies(self, t_next):
+        """From-scratch tallies and agenda bytes of the table as it stands before tick ``t_next`` (engine start, and after
+        any tick that ran through the components, whose kernels do not maintain the carried values)."""
         sim, dev, c = self.sim, self.dev, self.dev.cols
+        assert not self.hot_valid
         K.tx_step_prep(dev.n_nodes, sim.people.count, dev.n_strains, c["strain"], list(sim.pars.strain_r0_scalars.values()),
                        c["disease_state"], c["node_id"], c["daily_infectivity"], c["acq_risk_multiplier"],
                        out=(self.beta, self.expo, self.sus, self.hist))
@@ -112,6 +135,9 @@ class FusedEngine:
                       dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, self.E_cur, self.I_cur, POTP, Pz))
         self.tx_hits.zero_()
         self.tx_hits_s.zero_()
+        check(_lpk.lib().lpk_hot_build(C.byref(self.P), C.c_int64(sim.people.count), C.c_int32(t_next), _lpk.ptr(dev.status),
+                                       stream_handle()), "lpk_hot_build")
+        self.hot_valid = True
 
     def _row(self, name, t):
         r = self.dev.res.get(name)
@@ -159,7 +185,9 @@ class FusedEngine:
 
     # ------------------------------------------------------------------ pipeline
     def drain(self):
-        """Apply the pending exposure trial and census of the last fused tick with the per-function kernels."""
+        """Back to the canonical table: settle the deadline timers, then apply the pending exposure trial and census of
+        the last fused tick with the per-function kernels."""
+        self.settle(self.sim.t)
         if not self.pending:
             return
         sim, dev = self.sim, self.dev
@@ -182,7 +210,7 @@ class FusedEngine:
         self.cur_potp.copy_(r["potentially_paralyzed"][t])
         self.cur_p.copy_(r["paralyzed"][t])
         self.dev.set_count(self.sim.people.count)
-        self.rebase_tallies()
+        self.rebase_tallies(t + 1)
 
     def fused_tick(self, t):
         sim, dev, pars = self.sim, self.dev, self.sim.pars
@@ -195,7 +223,8 @@ class FusedEngine:
         if is_vd:  # births first: the cohort takes part in this tick's tally (reference: VitalDynamics runs first)
             if pars.cbr is None:
                 raise ValueError("VitalDynamics_ABM needs pars.cbr")
-            b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist))
+            b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist),
+                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0)))
             K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns
@@ -234,6 +263,7 @@ class FusedEngine:
         A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
         A.flags = flags
         A.uniform_agents = self.uniform_agents
+        A.work_counter = dp(self.work_counter)
         K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
 
         if sim.shard is not None:  # the one per-tick exchange: sum of the nodes x strains infectivity tally
@@ -305,8 +335,6 @@ class FusedEngine:
                     component.step()
             sim.log_results(t)
             self.after_component_tick(t)
-            if sim.people.count != old and self.dev.tile_node is None:
-                self.rebuild_tiles(old)
         else:
             if self.stop_rule:
                 self.early_stop_rule(t)
