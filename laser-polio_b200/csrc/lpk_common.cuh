@@ -25,7 +25,7 @@
 #define LPK_FULL 0xFFFFFFFFu
 
 // Functions marked LPK_HD also compile for the host: tests/hot_model builds the per-agent logic of the fused pass
-// (lpk_hot.cuh) as a plain CPU program and holds it to the oracle without a GPU.
+// (lpk_hot.cuh) as a plain CPU program and checks it on the CPU without a GPU.
 #define LPK_HD __host__ __device__ __forceinline__
 #ifdef __CUDA_ARCH__
 #define LPK_MULHI(a, b) __umulhi((a), (b))
