@@ -6,7 +6,7 @@
 //   infectious    nothing until the day its paralysis gate opens (paralytic strain) or it recovers
 //   recovered / dead / unborn   nothing
 // so the sweep reads ONE byte per agent, the agenda byte `hot[i]`:
-//   bits 7:6  class   00 susceptible   01 inactive (payload 0 recovered, 1 dead / unborn)   10 exposed   11 infectious
+//   bits 7:6  class   00 exposed   01 infectious   10 inactive (payload 0 recovered, 1 dead / unborn)   11 susceptible
 //   bits 5:0  payload susceptible: a 6-bit upper bound of acq_risk_multiplier (4 steps per octave, see risk_code)
 //                     exposed / infectious: the day of the agent's next event, modulo 64
 // and everything else is event driven: an agent whose payload equals today (or that passes the pre-test of the exposure
@@ -26,11 +26,11 @@
 #pragma once
 #include "lpk_common.cuh"
 
-#define HOT_S 0x00u
-#define HOT_R 0x40u
-#define HOT_DEAD 0x41u
-#define HOT_E 0x80u
-#define HOT_I 0xC0u
+#define HOT_E 0x00u
+#define HOT_I 0x40u
+#define HOT_R 0x80u
+#define HOT_DEAD 0x81u
+#define HOT_S 0xC0u
 #define HOT_LOOKAHEAD 63  // an event further away is reached through check-in events every 63 days
 
 // ring / event flags (bits 16+ of the second entry word; bits 0-15 carry the node)
@@ -61,8 +61,8 @@ LPK_HD int hot_risk_e0(float rmax) {
     int e0 = 15 - need;
     return e0 < -60 ? -60 : (e0 > 60 ? 60 : e0);
 }
-// In the sweep the code is decoded without arithmetic: (hot ^ 0xC0) placed at bits 21-28 of a float is
-// 2^(48 + e - 127) * (1 + m / 4) for a susceptible and at most 2^(33 - 127) for every other class, so
+// In the sweep the code is decoded without arithmetic: the agenda byte placed at bits 21-28 of a float is
+// 2^(48 + e - 127) * (1 + m / 4) for a susceptible (class bits 11) and at most 2^(33 - 127) for every other class, so
 //     U < fma(decoded, tau * 2^(95 - e0), 2^23 + 1),   U = 2^23 + h16
 // is the 16-bit pre-test of lpk_tick.cu with the agent's risk replaced by its upper bound.
 LPK_HD float hot_tau_scale(float tau, int e0) { return ldexpf(tau, 95 - e0); }
@@ -76,9 +76,12 @@ LPK_HD uint8_t hot_due(int tick, int days) {
 LPK_HD uint32_t zero_bytes(uint32_t v) {  // exact, per byte: v == 0
     return (~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) >> 7) & 0x01010101u;
 }
-LPK_HD uint32_t hot_mask_S(uint32_t h) { return (~(h | (h << 1)) >> 7) & 0x01010101u; }
+LPK_HD uint32_t hot_mask_S(uint32_t h) { return ((h & (h << 1)) >> 7) & 0x01010101u; }
+LPK_HD bool hot_is_S(uint32_t byte) { return (byte >> 6) == 3u; }
 LPK_HD uint32_t hot_mask_alive(uint32_t h) { return zero_bytes(h ^ (HOT_DEAD * 0x01010101u)) ^ 0x01010101u; }
-// agents of the quad whose agenda day is today: class 1x and payload == tick mod 64.  today = (0xC0 | tick & 63) * 0x01010101
+// agents of the quad whose agenda day is today: class 0x (exposed / infectious) and payload == tick mod 64; the word
+// has a zero byte exactly for those.  today = hot_today(tick)
+LPK_HD uint32_t hot_today(int tick) { return (0x40u | ((uint32_t)tick & 63u)) * 0x01010101u; }
 LPK_HD uint32_t hot_due_word(uint32_t h, uint32_t today) { return (h | 0x40404040u) ^ today; }
 LPK_HD uint32_t any_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }  // != 0 iff some byte is 0
 
@@ -88,10 +91,9 @@ LPK_HD uint32_t any_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80
 // agent; classes other than susceptible decode to < 2^-16 of the smallest susceptible bound and pass with probability
 // ~2^-16 (the caller masks with hot_mask_S when anything passed).
 LPK_HD uint32_t hot_pretest(uint32_t h, uint32_t xa, uint32_t xb, float tauS) {
-    const uint32_t KX = 0x18000000u, KM = 0x1FFFFFFFu, k23 = 0x4B000000u;
+    const uint32_t KM = 0x1FFFFFFFu, k23 = 0x4B000000u;
     const float c = 8388609.0f;
-    const float d0 = lpk_u2f(((h << 21) ^ KX) & KM), d1 = lpk_u2f(((h << 13) ^ KX) & KM);
-    const float d2 = lpk_u2f(((h << 5) ^ KX) & KM), d3 = lpk_u2f((h >> 3) ^ KX);
+    const float d0 = lpk_u2f((h << 21) & KM), d1 = lpk_u2f((h << 13) & KM), d2 = lpk_u2f((h << 5) & KM), d3 = lpk_u2f(h >> 3);
 #ifdef __CUDA_ARCH__
     const float u0 = __uint_as_float(__byte_perm(xa, k23, 0x7610)), u1 = __uint_as_float(__byte_perm(xa, k23, 0x7632));
     const float u2 = __uint_as_float(__byte_perm(xb, k23, 0x7610)), u3 = __uint_as_float(__byte_perm(xb, k23, 0x7632));

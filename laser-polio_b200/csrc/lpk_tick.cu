@@ -32,7 +32,23 @@ struct PassParams {
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
     uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
+    uint32_t rk[20];     // Philox round keys of the seed (key schedule done once on the host: the sweep's block reads them
+                         // straight from the constant bank instead of spending 20 additions per 8 agents)
 };
+
+// Philox4x32-10 with the key schedule taken from the kernel parameters
+__device__ __forceinline__ void philox_sweep(const PassParams &pp, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ pp.rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ pp.rk[2 * r + 1];
+        c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 
 #define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one pair fit
 #define LPK_UNIT_LOG 3   // a work unit = 8 consecutive pairs of 128-agent rows (2048 agents = 2 KB of agenda bytes)
@@ -246,7 +262,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
     const lpk_tick_args &A = pp.A;
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick, e0 = P.risk_e0;
-    const uint32_t today = 0xC0u | ((uint32_t)tick & 63u);
+    const uint32_t today = hot_today(tick) & 0xFFu;
     int mine = 0;
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
@@ -263,7 +279,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
             const int64_t i = b + k;
             const int nd = P.node_id[i];
             uint32_t fl = 0u;
-            if (pending && (hb >> 6) == 0u) {  // susceptible: pre-test of tick t-1's exposure trial
+            if (pending && hot_is_S(hb)) {  // susceptible: pre-test of tick t-1's exposure trial
                 const float tau = __ldg(&A.q_prev[nd]);
                 if (tau > 0.f) {
                     if (!have_x) {
@@ -356,10 +372,10 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     const int64_t n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick, e0 = P.risk_e0;
-    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint64_t ctr_base = ((A.id_base >> 8) << 5) + (uint64_t)lane;  // Philox counter of pair 0 for this lane
     const uint32_t total_pairs = (uint32_t)((n + 255) >> 8);
     const uint32_t n_units = (total_pairs + LPK_UNIT_PAIRS - 1) >> LPK_UNIT_LOG;
-    const uint32_t today = (0xC0u | ((uint32_t)tick & 63u)) * 0x01010101u;
+    const uint32_t today = hot_today(tick);
     const float tau_all = ldexpf(1.0f, e0);  // from here on every susceptible passes the pre-test anyway (bound of code 0 x tau >= 1)
 
     const uint32_t *stage = reinterpret_cast<const uint32_t *>(smem + L::kOffStage + warp * 2 * LPK_UNIT_AGENTS);
@@ -469,9 +485,9 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             // ---- exposure trial of tick t-1: pre-test on the risk bound; candidates are decided by the ring handler
             uint32_t cA = 0u, cB = 0u;
             if (tc_mode == 1) {
-                const uint64_t c = (((uint64_t)gp + (A.id_base >> 8)) << 5) + (uint64_t)lane;
+                const uint64_t c = ctr_base + ((uint64_t)gp << 5);
                 uint32_t x[4];
-                philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, k0, k1, x);
+                philox_sweep(pp, (uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
                 cA = hot_pretest(hA, x[0], x[1], tc_tauS);
                 cB = hot_pretest(hB, x[2], x[3], tc_tauS);
             } else if (tc_mode == 2) {
@@ -578,6 +594,10 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     pp.P = P;
     pp.A = A;
     pp.unit_ctr = A.work_counter;
+    for (int r = 0; r < 10; ++r) {
+        pp.rk[2 * r] = (uint32_t)A.seed + (uint32_t)r * 0x9E3779B9u;
+        pp.rk[2 * r + 1] = (uint32_t)(A.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("LPK_PASS_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -585,15 +605,25 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     }
     cudaStream_t st = as_stream(stream);
     int rc;
-    if (sia) {
-        if (deaths && ri) rc = launch_pass<true, true, true, 8, 3>(pp, st);
-        else if (deaths) rc = launch_pass<true, false, true, 8, 3>(pp, st);
-        else if (ri) rc = launch_pass<false, true, true, 8, 3>(pp, st);
-        else rc = launch_pass<false, false, true, 8, 3>(pp, st);
-    } else if (deaths && ri) rc = launch_pass<true, true, false, 8, 3>(pp, st);
-    else if (deaths) rc = launch_pass<true, false, false, 8, 3>(pp, st);
-    else if (ri) rc = launch_pass<false, true, false, 8, 3>(pp, st);
-    else rc = launch_pass<false, false, false, 8, 3>(pp, st);
+    // block shape: warps per block x blocks per SM (LPK_PASS_SHAPE: experiments)
+    static int shape = -1;
+    if (shape < 0) { const char *e = getenv("LPK_PASS_SHAPE"); shape = e ? atoi(e) : 1; }
+#define LPK_DISPATCH(W, O)                                                                          \
+    do {                                                                                            \
+        if (sia) {                                                                                  \
+            if (deaths && ri) rc = launch_pass<true, true, true, W, O>(pp, st);                     \
+            else if (deaths) rc = launch_pass<true, false, true, W, O>(pp, st);                     \
+            else if (ri) rc = launch_pass<false, true, true, W, O>(pp, st);                         \
+            else rc = launch_pass<false, false, true, W, O>(pp, st);                                \
+        } else if (deaths && ri) rc = launch_pass<true, true, false, W, O>(pp, st);                 \
+        else if (deaths) rc = launch_pass<true, false, false, W, O>(pp, st);                        \
+        else if (ri) rc = launch_pass<false, true, false, W, O>(pp, st);                            \
+        else rc = launch_pass<false, false, false, W, O>(pp, st);                                   \
+    } while (0)
+    if (shape == 0) LPK_DISPATCH(8, 3);
+    else if (shape == 2) LPK_DISPATCH(9, 2);
+    else LPK_DISPATCH(8, 2);
+#undef LPK_DISPATCH
     if (rc != LPK_OK) return rc;
     CUDA_TRY(cudaGetLastError(), "lpk_tick_pass");
     return LPK_OK;

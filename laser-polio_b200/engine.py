@@ -118,7 +118,7 @@ class FusedEngine:
         """Deadline timers of the exposed / infectious agents -> the countdown values tick ``t_next`` would test: the
         table is canonical again (what the per-function kernels and the host read)."""
         if self.hot_valid:
-            check(_lpk.lib().lpk_hot_settle(C.byref(self.P), C.c_int64(self.dev.sync_count()), C.c_int32(t_next), stream_handle()),
+            check(_lpk.lib().lpk_hot_settle(C.byref(self.P), C.c_int64(self.sim.people.capacity), C.c_int32(t_next), stream_handle()),
                   "lpk_hot_settle")
             self.hot_valid = False
 
@@ -135,7 +135,7 @@ class FusedEngine:
                       dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, self.E_cur, self.I_cur, POTP, Pz))
         self.tx_hits.zero_()
         self.tx_hits_s.zero_()
-        check(_lpk.lib().lpk_hot_build(C.byref(self.P), C.c_int64(sim.people.count), C.c_int32(t_next), _lpk.ptr(dev.status),
+        check(_lpk.lib().lpk_hot_build(C.byref(self.P), C.c_int64(sim.people.capacity), C.c_int32(t_next), _lpk.ptr(dev.status),
                                        stream_handle()), "lpk_hot_build")
         self.hot_valid = True
 

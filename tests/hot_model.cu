@@ -70,7 +70,7 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
     const bool pending = (A.flags & LPK_F_PENDING) != 0, deaths = (A.flags & LPK_F_DEATHS) != 0;
     const bool ri = (A.flags & LPK_F_RI) != 0, sia = (A.flags & LPK_F_SIA) != 0;
     const int tick = A.tick, e0 = P.risk_e0;
-    const uint32_t today = (0xC0u | ((uint32_t)tick & 63u)) * 0x01010101u;
+    const uint32_t today = hot_today(tick);
     const float tau_all = ldexpf(1.0f, e0);
     const int64_t total_pairs = (n + 255) >> 8;
     for (int64_t gp = 0; gp < total_pairs; ++gp) {
@@ -81,7 +81,7 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
                 if (hb == HOT_DEAD) continue;
                 const int nd = P.node_id[i];
                 uint32_t fl = 0;
-                if (pending && (hb >> 6) == 0u) {
+                if (pending && hot_is_S(hb)) {
                     const float tau = A.q_prev[nd];
                     if (tau > 0.f) {
                         const uint64_t id = (uint64_t)i + A.id_base;
