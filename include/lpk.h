@@ -202,6 +202,8 @@ typedef struct lpk_people {
     int32_t *pair_min_dod;           /* [lpk_hot_padded(capacity) / 256] earliest date_of_death among the alive agents of
                                         each 256-slot pair (INT32_MAX: nobody); NULL when there is no date_of_death */
     int32_t risk_e0;                 /* exponent bias of the 6-bit risk code: lpk_hot_risk_e0(largest finite risk in the table) */
+    int32_t *pair_ri_max;            /* [lpk_hot_padded(capacity) / 256] largest stored ri_timer among the alive, not chronically
+                                        missed agents of each pair (INT32_MIN: nobody); NULL when there is no ri_timer */
 } lpk_people;
 
 #define LPK_F_PENDING 1u /* apply tick-1's exposure (q_prev / cdf_prev) and take tick-1's census */
@@ -259,6 +261,14 @@ typedef struct lpk_tick_args {
     /* scheduling hint (results do not depend on it): slots [0, uniform_agents) hold the node-contiguous initial population,
      * slots beyond it appended newborn cohorts; the pass hands the cohort region out first.  0 = unknown */
     int64_t uniform_agents;
+    /* Lazy RI countdown.  fast_ri subtracts ri_step from every alive, not chronically missed agent's ri_timer on every RI
+     * tick (model.py:1825-1833) although only agents a few weeks old can ever become eligible.  The pass does not write
+     * the column: ri_lazy_k = RI ticks run since the last lpk_hot_build whose subtraction is still owed (excluding tick t
+     * itself); an agent's current timer is stored - ri_lazy_k * ri_step, the column is read only in pairs where
+     * pair_ri_max says somebody can still become eligible, an agent that dies gets its debt settled on the spot, newborns
+     * enter with the debt added (lpk_births_args.ri_lazy_k), and lpk_hot_settle pays it for everybody else.  ri_step must
+     * be set on every tick while ri_lazy_k != 0. */
+    int32_t ri_lazy_k;
     uint32_t *work_counter; /* caller-owned device uint32 (one per table / stream): the pass zeroes it on `stream` and claims
                                work units from it, so two tables on one device never share scheduling state */
 } lpk_tick_args;
@@ -281,11 +291,12 @@ int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *str
  *   lpk_hot_build   canonical columns (as every per-function entry point above reads them) -> agenda bytes + deadlines
  *                   + pair_min_dod, for the table as it stands BEFORE tick `tick_next`.  *status = 2 if a risk exceeds the
  *                   range of the code (risk_e0 too large); slots >= n_slots and the padding read as dead.
- *   lpk_hot_settle  the inverse for the timers (deadline -> the value tick `tick_next` would test): call before handing
+ *   lpk_hot_settle  the inverse for the timers (deadline -> the value tick `tick_next` would test; ri_timer -= ri_lazy_k *
+ *                   ri_step for the alive, not chronically missed agents, see lpk_tick_args.ri_lazy_k): call before handing
  *                   the table to the per-function entry points or to the host.  disease_state, strain and every other
  *                   column are kept canonical by the pass at all times. */
 int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t *status, void *stream);
-int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, void *stream);
+int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_lazy_k, int32_t ri_step, void *stream);
 int64_t lpk_hot_padded(int64_t capacity); /* capacity rounded up to the pass's work unit (2048 agents) */
 int32_t lpk_hot_risk_e0(float max_risk);
 
@@ -369,6 +380,8 @@ typedef struct lpk_births_args {
     uint8_t *hot;
     int32_t *pair_min_dod;
     int32_t risk_e0;
+    int32_t *pair_ri_max;        /* with ri_timer: newborns' timers enter the pair's maximum ... */
+    int32_t ri_lazy_k, ri_step;  /* ... stored with the lazy countdown's debt added (lpk_tick_args.ri_lazy_k) */
 } lpk_births_args;
 
 int lpk_vd_births(const lpk_births_args *args, void *stream);

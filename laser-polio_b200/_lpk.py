@@ -113,7 +113,7 @@ class People(C.Structure):
         "disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
         "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
         "daily_infectivity", "date_of_birth", "date_of_death", "tile_node")] + [
-            ("capacity", C.c_int64), ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32)]
+            ("capacity", C.c_int64), ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("pair_ri_max", _VP)]
 
 
 class TickArgs(C.Structure):
@@ -134,7 +134,7 @@ class TickArgs(C.Structure):
         ("sia_vaccinated", _VP), ("sia_protected", _VP), ("sia_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
         ("beta_fx", _VP), ("E_cur", _VP), ("I_cur", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
-        ("uniform_agents", C.c_int64), ("work_counter", _VP),
+        ("uniform_agents", C.c_int64), ("ri_lazy_k", C.c_int32), ("work_counter", _VP),
     ]
 
 
@@ -166,7 +166,8 @@ class BirthsArgs(C.Structure):
         ("cohort_ws", _VP), ("status", _VP), ("disease_state", _VP), ("node_id", _VP), ("date_of_birth", _VP),
         ("date_of_death", _VP), ("ri_timer", _VP), ("tile_node", _VP),
         ("acq_risk_multiplier", _VP), ("sus", _VP), ("exposure_fx", _VP), ("risk_hist", _VP),
-        ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32),
+        ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("pair_ri_max", _VP), ("ri_lazy_k", C.c_int32),
+        ("ri_step", C.c_int32),
     ]
 
 

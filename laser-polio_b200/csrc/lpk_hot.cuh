@@ -131,10 +131,18 @@ LPK_HD uint8_t hot_build_agent(const lpk_people &P, int64_t i, int t_next, int e
     }
     return s == 3 ? (uint8_t)HOT_R : (uint8_t)HOT_DEAD;
 }
-// The inverse for the timers: deadline -> the value tick t_next would test.
-LPK_HD void hot_settle_agent(const lpk_people &P, int64_t i, int t_next) {
+// Lazy RI countdown (include/lpk.h, lpk_tick_args.ri_lazy_k): the agent's timer after k owed subtractions, and whether the
+// RI tick `tick` (the k_after-th subtraction) finds it eligible -- reference model.py:1833-1843 on the wrapped int16 value.
+LPK_HD int16_t ri_owed(int16_t stored, int k, int step) { return (int16_t)(uint16_t)((uint16_t)stored - (uint16_t)(k * step)); }
+LPK_HD bool ri_eligible(int16_t stored, int k_before, int step, int tick) {
+    const int timer = (int)ri_owed(stored, k_before, step) - step;
+    return (tick == step) ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step);
+}
+// The inverse for the timers: deadline -> the value tick t_next would test; the RI countdown's debt is paid.
+LPK_HD void hot_settle_agent(const lpk_people &P, int64_t i, int t_next, int ri_k, int ri_step) {
     const int8_t s = P.disease_state[i];
     const uint8_t t8 = (uint8_t)t_next;
+    if (ri_k && P.ri_timer && s >= 0 && P.chronically_missed[i] != 1) P.ri_timer[i] = ri_owed(P.ri_timer[i], ri_k, ri_step);
     if (s == 1) {
         P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)P.exposure_timer[i] - t8);
     } else if (s == 2) {
@@ -249,6 +257,8 @@ LPK_HD HotDelta hot_event(const lpk_people &P, const lpk_tick_args &A, int64_t i
         d.st = st;
         if (P.potentially_paralyzed[i] == 1) d.died |= 2;
         if (P.paralyzed[i] == 1) d.died |= 4;
+        if (A.ri_lazy_k && P.ri_timer && P.chronically_missed[i] != 1)  // the dead stop counting down: pay the debt so far
+            P.ri_timer[i] = ri_owed(P.ri_timer[i], A.ri_lazy_k, A.ri_step);
         P.disease_state[i] = -1;
         P.hot[i] = HOT_DEAD;
         return d;

@@ -50,7 +50,7 @@ __device__ __forceinline__ void philox_sweep(const PassParams &pp, uint32_t c0, 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-#define QCAP 512         // ring entries per warp: 31 left over + the 256 agents of one pair fit
+#define QCAP 1024        // ring entries per warp: 31 left over + the 512 agents of one tile fit
 #define LPK_UNIT_LOG 3   // a work unit = 8 consecutive pairs of 128-agent rows (2048 agents = 2 KB of agenda bytes)
 #define LPK_UNIT_PAIRS (1 << LPK_UNIT_LOG)
 #define LPK_UNIT_AGENTS (256 << LPK_UNIT_LOG)
@@ -220,16 +220,17 @@ __device__ __forceinline__ uint32_t sia_age_mask(const int4 &d, int tick, int lo
            ((uint32_t)(tick - d.z - lo) <= span ? 0x10000u : 0u) | ((uint32_t)(tick - d.w - lo) <= span ? 0x1000000u : 0u);
 }
 // ---- routine immunisation in a quad (reference model.py:1825-1854) -----------------------------------------------
-// Every alive, not chronically missed agent's ri_timer goes down by the step (four int16 lanes at a time); an agent is
-// eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Eligible agents are the few in
-// the age window; they go to the ring and take their two draws in the handler, after their disease-state step.
-__device__ __forceinline__ uint32_t ri_timers_quad(const PassParams &pp, int64_t b, uint32_t alive, uint32_t missed, uint2 tm) {
+// The reference subtracts the step from every alive, not chronically missed agent's ri_timer on every RI tick; an agent is
+// eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Here the countdown is lazy
+// (lpk_tick_args.ri_lazy_k): nothing is written, the timer after today's subtraction is stored - (k + 1) * step on four
+// int16 lanes.  Eligible agents are the few in the age window; they go to the ring and take their two draws in the
+// handler, after their disease-state step.
+__device__ __forceinline__ uint32_t ri_eligible_quad(const PassParams &pp, uint32_t alive, uint32_t missed, uint2 tm) {
     const int step = pp.A.ri_step;
     const uint32_t ok8 = alive & ~missed;  // missed bytes are 0 / 1
     if (!ok8) return 0u;
-    const uint2 tn = make_uint2(__vsub2(tm.x, __byte_perm(ok8, 0u, 0x4140) * (uint32_t)step),
-                                __vsub2(tm.y, __byte_perm(ok8, 0u, 0x4342) * (uint32_t)step));
-    *reinterpret_cast<uint2 *>(pp.P.ri_timer + b) = tn;
+    const uint32_t debt2 = ((uint32_t)((pp.A.ri_lazy_k + 1) * step) & 0xFFFFu) * 0x10001u;
+    const uint2 tn = make_uint2(__vsub2(tm.x, debt2), __vsub2(tm.y, debt2));
     const int lo = (pp.A.tick == step) ? -step : 1 - step;  // eligible: lo <= timer <= 0
     const uint32_t lo2 = ((uint32_t)lo & 0xFFFFu) * 0x10001u, span2 = ((uint32_t)(-lo) & 0xFFFFu) * 0x10001u;
     const uint32_t ex = __vcmpleu2(__vsub2(tn.x, lo2), span2), ey = __vcmpleu2(__vsub2(tn.y, lo2), span2);
@@ -296,13 +297,7 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
             bool dying = false;
             if (kDeaths && P.date_of_death[i] <= tick) { fl |= EV_DEATH; dying = true; }
             if ((kRI || kSIA) && !dying && P.chronically_missed[i] != 1) {
-                if (kRI) {
-                    const int step = A.ri_step;
-                    const int timer = (int)P.ri_timer[i] - step;
-                    P.ri_timer[i] = (int16_t)timer;
-                    const bool first = (tick == step);
-                    if (first ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step)) fl |= EV_RI;
-                }
+                if (kRI && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) fl |= EV_RI;
                 if (kSIA && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age) &&
                     A.sia_targeted[nd] != 0)
                     fl |= EV_SIA;
@@ -351,6 +346,22 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0u;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// two blocks at once (counters ca, cb; same tick / stage): independent dependency chains in one basic block
+__device__ __forceinline__ void philox_sweep2(const PassParams &pp, uint64_t ca, uint64_t cb, uint32_t c2, uint32_t c3, uint32_t x[4],
+                                              uint32_t y[4]) {
+    uint32_t a0 = (uint32_t)ca, a1 = (uint32_t)(ca >> 32), a2 = c2, a3 = c3;
+    uint32_t b0 = (uint32_t)cb, b1 = (uint32_t)(cb >> 32), b2 = c2, b3 = c3;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t ah0 = __umulhi(0xD2511F53u, a0), al0 = 0xD2511F53u * a0, ah1 = __umulhi(0xCD9E8D57u, a2), al1 = 0xCD9E8D57u * a2;
+        const uint32_t bh0 = __umulhi(0xD2511F53u, b0), bl0 = 0xD2511F53u * b0, bh1 = __umulhi(0xCD9E8D57u, b2), bl1 = 0xCD9E8D57u * b2;
+        a0 = ah1 ^ a1 ^ pp.rk[2 * r]; a1 = al1; a2 = ah0 ^ a3 ^ pp.rk[2 * r + 1]; a3 = al0;
+        b0 = bh1 ^ b1 ^ pp.rk[2 * r]; b1 = bl1; b2 = bh0 ^ b3 ^ pp.rk[2 * r + 1]; b3 = bl0;
+    }
+    x[0] = a0; x[1] = a1; x[2] = a2; x[3] = a3;
+    y[0] = b0; y[1] = b1; y[2] = b2; y[3] = b3;
+}
 
 template <int kWarps>
 struct PassSmem {
@@ -444,6 +455,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     int tc_mode = 0;   // 0 no force of infection, 1 pre-test, 2 every susceptible is a candidate
     float tc_tauS = 0.f;
     bool tc_sia = false;
+    const int ri_debt = kRI ? A.ri_lazy_k * A.ri_step : 0;  // an agent whose stored timer is below this can never be eligible again
     const int sia_lo = kSIA ? A.sia_min_age : 0;
     const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
 
@@ -458,20 +470,27 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         // per-unit metadata while the copy lands: the unit's 4 tile nodes (lanes 0-3) and, on vital-dynamics ticks, its 8
         // earliest death dates (lanes 0-7)
         const uint32_t gp0 = u_cur << LPK_UNIT_LOG;
-        int tnv = -1, mdv = INT_MAX;
+        int tnv = -1, mdv = INT_MAX, rmv = INT_MIN;
         if (P.tile_node && lane < 4 && gp0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(gp0 >> 1) + lane]);
         if (kDeaths && lane < LPK_UNIT_PAIRS && gp0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[gp0 + lane];
+        if (kRI && lane < LPK_UNIT_PAIRS && gp0 + (uint32_t)lane < total_pairs) rmv = P.pair_ri_max[gp0 + lane];
         mbar_wait(&bars[buf], buf ? par1 : par0);
         if (buf) par1 ^= 1u; else par0 ^= 1u;
         const uint32_t *src = stage + buf * (LPK_UNIT_AGENTS / 4);
 #pragma unroll 1
-        for (int p = 0; p < LPK_UNIT_PAIRS; ++p) {
-            const uint32_t gp = gp0 + (uint32_t)p;
+        for (int tp = 0; tp < LPK_UNIT_PAIRS / 2; ++tp) {  // one TILE (two pairs, 16 agents per lane) per iteration: the two
+            const uint32_t gp = gp0 + 2u * (uint32_t)tp;    // Philox blocks are independent chains and interleave
             if (gp >= total_pairs) break;
-            const int tn = __shfl_sync(LPK_FULL, tnv, p >> 1);
-            const uint32_t hA = src[p * 64 + lane], hB = src[p * 64 + 32 + lane];
+            const int tn = __shfl_sync(LPK_FULL, tnv, tp);
+            const uint32_t hA0 = src[tp * 128 + lane], hB0 = src[tp * 128 + 32 + lane];
+            const uint32_t hA1 = src[tp * 128 + 64 + lane], hB1 = src[tp * 128 + 96 + lane];
             if (tn < 0) {
-                q_commit(pp, Q, general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp, n, hA, hB, lane), lane);
+                int mine = general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp, n, hA0, hB0, lane);
+                q_commit(pp, Q, mine, lane);
+                if (gp + 1u < total_pairs) {
+                    mine = general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp + 1, n, hA1, hB1, lane);
+                    q_commit(pp, Q, mine, lane);
+                }
                 continue;
             }
             if (tn != tc_node) {
@@ -481,54 +500,70 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                 tc_tauS = hot_tau_scale(tau, e0);
                 if (kSIA) tc_sia = __ldg(&A.sia_targeted[tn]) != 0;
             }
-            const int64_t bA = (int64_t)gp * 256 + lane * 4, bB = bA + 128;
+            const int64_t bA0 = (int64_t)gp * 256 + lane * 4;  // quads: A0 = bA0, B0 = +128, A1 = +256, B1 = +384
             // ---- exposure trial of tick t-1: pre-test on the risk bound; candidates are decided by the ring handler
-            uint32_t cA = 0u, cB = 0u;
+            uint32_t cA0 = 0u, cB0 = 0u, cA1 = 0u, cB1 = 0u;
             if (tc_mode == 1) {
                 const uint64_t c = ctr_base + ((uint64_t)gp << 5);
-                uint32_t x[4];
-                philox_sweep(pp, (uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
-                cA = hot_pretest(hA, x[0], x[1], tc_tauS);
-                cB = hot_pretest(hB, x[2], x[3], tc_tauS);
+                uint32_t x[4], y[4];
+                philox_sweep2(pp, c, c + 32u, (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x, y);
+                cA0 = hot_pretest(hA0, x[0], x[1], tc_tauS);
+                cB0 = hot_pretest(hB0, x[2], x[3], tc_tauS);
+                cA1 = hot_pretest(hA1, y[0], y[1], tc_tauS);
+                cB1 = hot_pretest(hB1, y[2], y[3], tc_tauS);
             } else if (tc_mode == 2) {
-                cA = cB = 0x01010101u;
+                cA0 = cB0 = cA1 = cB1 = 0x01010101u;
             }
             // ---- agenda: exposed / infectious agents whose day is today
-            const uint32_t vA = hot_due_word(hA, today), vB = hot_due_word(hB, today);
-            uint32_t ev = cA | cB | any_zero_byte(vA) | any_zero_byte(vB);
+            const uint32_t vA0 = hot_due_word(hA0, today), vB0 = hot_due_word(hB0, today);
+            const uint32_t vA1 = hot_due_word(hA1, today), vB1 = hot_due_word(hB1, today);
+            uint32_t ev = cA0 | cB0 | cA1 | cB1 | any_zero_byte(vA0) | any_zero_byte(vB0) | any_zero_byte(vA1) | any_zero_byte(vB1);
             // ---- tick t: deaths, RI timers, campaign window (extra columns only where they can matter)
-            uint32_t dmA = 0u, dmB = 0u, eA = 0u, eB = 0u, sA = 0u, sB = 0u;
-            if (kDeaths) {
-                const int md = __shfl_sync(LPK_FULL, mdv, p);
-                if (md <= tick) {  // warp-uniform: somebody in this pair can die today
-                    const int4 dA = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bA));
-                    const int4 dB = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bB));
-                    const uint32_t aA = hot_mask_alive(hA), aB = hot_mask_alive(hB);
-                    dmA = death_mask(dA, tick) & aA;
-                    dmB = death_mask(dB, tick) & aB;
-                    const int left = __reduce_min_sync(LPK_FULL, min(min_dod_left(dA, aA & ~dmA), min_dod_left(dB, aB & ~dmB)));
-                    if (lane == 0) P.pair_min_dod[gp] = left;
+            uint32_t xA0 = 0u, xB0 = 0u, xA1 = 0u, xB1 = 0u;  // per-agent flag bits 2 (death), 3 (RI), 4 (SIA)
+            if (kDeaths || kRI || kSIA) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t hA = j ? hA1 : hA0, hB = j ? hB1 : hB0;
+                    const int64_t bA = bA0 + 256 * j, bB = bA + 128;
+                    uint32_t dmA = 0u, dmB = 0u, eA = 0u, eB = 0u, sA = 0u, sB = 0u;
+                    if (kDeaths) {
+                        const int md = __shfl_sync(LPK_FULL, mdv, 2 * tp + j);
+                        if (md <= tick) {  // warp-uniform: somebody in this pair can die today
+                            const int4 dA = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bA));
+                            const int4 dB = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bB));
+                            const uint32_t aA = hot_mask_alive(hA), aB = hot_mask_alive(hB);
+                            dmA = death_mask(dA, tick) & aA;
+                            dmB = death_mask(dB, tick) & aB;
+                            const int left = __reduce_min_sync(LPK_FULL, min(min_dod_left(dA, aA & ~dmA), min_dod_left(dB, aB & ~dmB)));
+                            if (lane == 0) P.pair_min_dod[gp + j] = left;
+                        }
+                    }
+                    // RI: only pairs in which somebody's timer has not run out for good (stored >= debt) can hold an eligible agent
+                    const bool ri_pair = kRI && __shfl_sync(LPK_FULL, rmv, 2 * tp + j) >= ri_debt;
+                    if (ri_pair || (kSIA && tc_sia)) {
+                        const uint32_t mA = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bA);
+                        const uint32_t mB = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bB);
+                        const uint32_t aA = hot_mask_alive(hA) & ~dmA, aB = hot_mask_alive(hB) & ~dmB;
+                        if (ri_pair) {
+                            eA = ri_eligible_quad(pp, aA, mA, __ldg(reinterpret_cast<const uint2 *>(P.ri_timer + bA)));
+                            eB = ri_eligible_quad(pp, aB, mB, __ldg(reinterpret_cast<const uint2 *>(P.ri_timer + bB)));
+                        }
+                        if (kSIA && tc_sia) {
+                            sA = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bA)), tick, sia_lo, sia_span) & aA & ~mA;
+                            sB = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bB)), tick, sia_lo, sia_span) & aB & ~mB;
+                        }
+                    }
+                    const uint32_t fA = (dmA << 2) | (eA << 3) | (sA << 4), fB = (dmB << 2) | (eB << 3) | (sB << 4);
+                    if (j) { xA1 = fA; xB1 = fB; } else { xA0 = fA; xB0 = fB; }
                 }
+                ev |= xA0 | xB0 | xA1 | xB1;
             }
-            if (kRI || (kSIA && tc_sia)) {
-                const uint32_t mA = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bA);
-                const uint32_t mB = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bB);
-                const uint32_t aA = hot_mask_alive(hA) & ~dmA, aB = hot_mask_alive(hB) & ~dmB;
-                if (kRI) {
-                    eA = ri_timers_quad(pp, bA, aA, mA, *reinterpret_cast<const uint2 *>(P.ri_timer + bA));
-                    eB = ri_timers_quad(pp, bB, aB, mB, *reinterpret_cast<const uint2 *>(P.ri_timer + bB));
-                }
-                if (kSIA && tc_sia) {
-                    sA = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bA)), tick, sia_lo, sia_span) & aA & ~mA;
-                    sB = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bB)), tick, sia_lo, sia_span) & aB & ~mB;
-                }
-            }
-            ev |= dmA | dmB | eA | eB | sA | sB;
             int mine = 0;
             if (ev) {  // rare per lane (a few per cent), common per warp: keep it short
-                const uint32_t FA = (cA & hot_mask_S(hA)) | (zero_bytes(vA) << 1) | (dmA << 2) | (eA << 3) | (sA << 4);
-                const uint32_t FB = (cB & hot_mask_S(hB)) | (zero_bytes(vB) << 1) | (dmB << 2) | (eB << 3) | (sB << 4);
-                mine = q_push_pair(Q.q, Q.tail, (uint32_t)bA, tn, FA, FB);
+                const uint32_t FA0 = (cA0 & hot_mask_S(hA0)) | (zero_bytes(vA0) << 1) | xA0, FB0 = (cB0 & hot_mask_S(hB0)) | (zero_bytes(vB0) << 1) | xB0;
+                const uint32_t FA1 = (cA1 & hot_mask_S(hA1)) | (zero_bytes(vA1) << 1) | xA1, FB1 = (cB1 & hot_mask_S(hB1)) | (zero_bytes(vB1) << 1) | xB1;
+                if (FA0 | FB0) mine = q_push_pair(Q.q, Q.tail, (uint32_t)bA0, tn, FA0, FB0);
+                if (FA1 | FB1) mine += q_push_pair(Q.q, Q.tail, (uint32_t)bA0 + 256u, tn, FA1, FB1);
             }
             q_commit(pp, Q, mine, lane);
         }
@@ -586,7 +621,8 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
                          A.sia_strain < A.n_strains, "tick_pass SIA");
     if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && P.pair_min_dod && A.deaths && A.dead_pp && A.dead_par,
                         "tick_pass deaths");
-    if (ri) REQUIRE(P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
+    if (A.ri_lazy_k) REQUIRE(A.ri_lazy_k > 0 && A.ri_step > 0 && P.ri_timer && P.chronically_missed, "tick_pass lazy RI countdown");
+    if (ri) REQUIRE(P.pair_ri_max && P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
                         A.vx_prob_ipv && A.ri_vaccinated && A.ri_protected && A.ipv_vaccinated && A.new_exposed &&
                         A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0 && A.ri_strain >= 0 &&
                         A.ri_strain < A.n_strains, "tick_pass RI");
@@ -654,9 +690,22 @@ __global__ void __launch_bounds__(256) k_pair_min_dod(lpk_people P, int64_t n_sl
         if (lane == 0) P.pair_min_dod[gp] = m;
     }
 }
-__global__ void __launch_bounds__(256) k_hot_settle(lpk_people P, int64_t n_slots, int t_next) {
+// largest stored ri_timer among the alive, not chronically missed agents of every pair
+__global__ void __launch_bounds__(256) k_pair_ri_max(lpk_people P, int64_t n_slots, int64_t n_pairs) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t gp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gp < n_pairs; gp += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        int m = INT_MIN;
+        for (int k = lane; k < 256; k += 32) {
+            const int64_t i = gp * 256 + k;
+            if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1) m = max(m, (int)P.ri_timer[i]);
+        }
+        m = __reduce_max_sync(LPK_FULL, m);
+        if (lane == 0) P.pair_ri_max[gp] = m;
+    }
+}
+__global__ void __launch_bounds__(256) k_hot_settle(lpk_people P, int64_t n_slots, int t_next, int ri_k, int ri_step) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x)
-        hot_settle_agent(P, i, t_next);
+        hot_settle_agent(P, i, t_next, ri_k, ri_step);
 }
 static inline int64_t hot_padded(int64_t capacity) { return (capacity + LPK_UNIT_AGENTS - 1) / LPK_UNIT_AGENTS * LPK_UNIT_AGENTS; }
 
@@ -674,15 +723,20 @@ extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t 
         k_pair_min_dod<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256);
         CUDA_TRY(cudaGetLastError(), "lpk_hot_build pair_min_dod");
     }
+    if (P.pair_ri_max && P.ri_timer && P.chronically_missed) {
+        k_pair_ri_max<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256);
+        CUDA_TRY(cudaGetLastError(), "lpk_hot_build pair_ri_max");
+    }
     return LPK_OK;
 }
-extern "C" int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, void *stream) {
+extern "C" int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_lazy_k, int32_t ri_step, void *stream) {
     REQUIRE(people, "hot_settle null struct");
     const lpk_people &P = *people;
     REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer, "hot_settle columns");
     REQUIRE(n_slots >= 0 && n_slots <= P.capacity, "hot_settle n_slots");
     if (n_slots == 0) return LPK_OK;
-    k_hot_settle<<<lpk_sm_count() * 8, 256, 0, as_stream(stream)>>>(P, n_slots, tick_next);
+    REQUIRE(ri_lazy_k == 0 || (P.ri_timer && P.chronically_missed && ri_step > 0), "hot_settle RI countdown");
+    k_hot_settle<<<lpk_sm_count() * 8, 256, 0, as_stream(stream)>>>(P, n_slots, tick_next, ri_lazy_k, ri_step);
     CUDA_TRY(cudaGetLastError(), "lpk_hot_settle");
     return LPK_OK;
 }

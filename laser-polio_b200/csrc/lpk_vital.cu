@@ -100,6 +100,10 @@ __global__ void k_births_fill(lpk_births_args a) {
         a.date_of_death[slot] = a.tick + newborn_lifespan(a, (uint64_t)slot);
         a.disease_state[slot] = 0;
         if (a.ri_timer && a.ri_newborn_timer >= 0) a.ri_timer[slot] = (int16_t)a.ri_newborn_timer;
+        if (a.ri_timer && a.ri_lazy_k) {  // lazy RI countdown (lpk_tick_args.ri_lazy_k): the newborn does not owe the earlier ticks
+            a.ri_timer[slot] = (int16_t)(uint16_t)((uint16_t)a.ri_timer[slot] + (uint16_t)(a.ri_lazy_k * a.ri_step));
+        }
+        if (a.ri_timer && a.pair_ri_max) atomicMax(&a.pair_ri_max[slot >> 8], (int)a.ri_timer[slot]);
         if (a.hot) {  // fused path: the newborn's agenda byte (a susceptible) and its pair's earliest death date
             bool over = false;
             a.hot[slot] = (uint8_t)(HOT_S | risk_code(a.acq_risk_multiplier[slot], a.risk_e0, &over));

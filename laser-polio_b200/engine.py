@@ -88,6 +88,10 @@ class FusedEngine:
         padded = int(_lpk.lib().lpk_hot_padded(cap))
         self.hot = torch.empty(padded, dtype=torch.uint8, device=d)
         self.pair_min_dod = torch.empty(padded // 256, dtype=torch.int32, device=d) if "date_of_death" in c else None
+        self.pair_ri_max = torch.empty(padded // 256, dtype=torch.int32, device=d) if "ri_timer" in c else None
+        self.ri_lazy_k = 0  # RI ticks whose ri_timer subtraction is still owed (lpk_tick_args.ri_lazy_k)
+        ri = self.by_name.get("RI_ABM")
+        self.ri_step = int(ri.step_size) if ri is not None else 0
         self.work_counter = torch.zeros(64, dtype=torch.int32, device=d)
         risk = c["acq_risk_multiplier"]
         rmax = float(torch.where(torch.isfinite(risk), risk, torch.zeros_like(risk)).max().item()) if risk.numel() else 1.0
@@ -101,7 +105,7 @@ class FusedEngine:
             setattr(P, name, dp(c.get(name)))
         P.tile_node = dp(self.tile_node)
         P.capacity = cap
-        P.hot, P.pair_min_dod = dp(self.hot), dp(self.pair_min_dod)
+        P.hot, P.pair_min_dod, P.pair_ri_max = dp(self.hot), dp(self.pair_min_dod), dp(self.pair_ri_max)
         P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
         if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
@@ -118,9 +122,10 @@ class FusedEngine:
         """Deadline timers of the exposed / infectious agents -> the countdown values tick ``t_next`` would test: the
         table is canonical again (what the per-function kernels and the host read)."""
         if self.hot_valid:
-            check(_lpk.lib().lpk_hot_settle(C.byref(self.P), C.c_int64(self.sim.people.capacity), C.c_int32(t_next), stream_handle()),
-                  "lpk_hot_settle")
+            check(_lpk.lib().lpk_hot_settle(C.byref(self.P), C.c_int64(self.sim.people.capacity), C.c_int32(t_next),
+                                            C.c_int32(self.ri_lazy_k), C.c_int32(self.ri_step), stream_handle()), "lpk_hot_settle")
             self.hot_valid = False
+            self.ri_lazy_k = 0
 
     def rebase_tallies(self, t_next):
         """From-scratch tallies and agenda bytes of the table as it stands before tick ``t_next`` (engine start, and after
@@ -224,7 +229,7 @@ class FusedEngine:
             if pars.cbr is None:
                 raise ValueError("VitalDynamics_ABM needs pars.cbr")
             b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist),
-                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0)))
+                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step))
             K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns
@@ -238,10 +243,11 @@ class FusedEngine:
         A.p_paralysis = float(np.float32(pars.p_paralysis))
         A.new_potential, A.new_paralyzed = dp(self._row("new_potentially_paralyzed", t)), dp(self._row("new_paralyzed", t))
         A.deaths, A.dead_pp, A.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
-        if ri is not None and pars["vx_prob_ri"] is not None and t % ri.step_size == 0:
+        A.ri_step, A.ri_lazy_k = self.ri_step, self.ri_lazy_k
+        is_ri = ri is not None and pars["vx_prob_ri"] is not None and t % ri.step_size == 0
+        if is_ri:
             flags |= F_RI
             p_ri, p_ipv = ri._probs(dev)
-            A.ri_step = int(ri.step_size)
             A.ri_strain = 2 if "nOPV" in getattr(pars, "ri_vaccine_type", "tOPV") else 1
             A.vx_prob_ri, A.vx_prob_ipv = dp(p_ri), dp(p_ipv)
             A.ri_vaccinated, A.ri_protected = dp(self._row("ri_vaccinated", t)), dp(self._row("ri_protected", t))
@@ -318,6 +324,8 @@ class FusedEngine:
             evt.record()
             self.cases_evt = {t: evt}
         self.pending = True
+        if is_ri:
+            self.ri_lazy_k += 1
 
     def _seasonality(self):
         from . import utils

@@ -55,10 +55,19 @@ extern "C" int hm_build(const lpk_people *people, int64_t n_slots, int32_t t_nex
             }
             P.pair_min_dod[gp] = m;
         }
+    if (P.pair_ri_max && P.ri_timer)
+        for (int64_t gp = 0; gp < padded / 256; ++gp) {
+            int m = INT_MIN;
+            for (int k = 0; k < 256; ++k) {
+                const int64_t i = gp * 256 + k;
+                if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1 && P.ri_timer[i] > m) m = P.ri_timer[i];
+            }
+            P.pair_ri_max[gp] = m;
+        }
     return over ? 2 : 0;
 }
-extern "C" int hm_settle(const lpk_people *people, int64_t n_slots, int32_t t_next) {
-    for (int64_t i = 0; i < n_slots; ++i) hot_settle_agent(*people, i, t_next);
+extern "C" int hm_settle(const lpk_people *people, int64_t n_slots, int32_t t_next, int32_t ri_k, int32_t ri_step) {
+    for (int64_t i = 0; i < n_slots; ++i) hot_settle_agent(*people, i, t_next, ri_k, ri_step);
     return 0;
 }
 extern "C" int hm_risk_e0(float rmax) { return hot_risk_e0(rmax); }
@@ -97,12 +106,7 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
                 bool dying = false;
                 if (deaths && P.date_of_death[i] <= tick) { fl |= EV_DEATH; dying = true; }
                 if ((ri || sia) && !dying && P.chronically_missed[i] != 1) {
-                    if (ri) {
-                        const int step = A.ri_step;
-                        const int timer = (int)P.ri_timer[i] - step;
-                        P.ri_timer[i] = (int16_t)timer;
-                        if ((tick == step) ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step)) fl |= EV_RI;
-                    }
+                    if (ri && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) fl |= EV_RI;
                     if (sia && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age) &&
                         A.sia_targeted[nd] != 0)
                         fl |= EV_SIA;
@@ -156,19 +160,14 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
                     if (((aB0 & ~dmB) >> (8 * k)) & 1u) left = P.date_of_death[bB + k] < left ? P.date_of_death[bB + k] : left;
                 }
             }
-            if (ri || camp) {
+            const bool ri_pair = ri && P.pair_ri_max[gp] >= A.ri_lazy_k * A.ri_step;
+            if (ri_pair || camp) {
                 const uint32_t aA = aA0 & ~dmA, aB = aB0 & ~dmB;
                 for (int r = 0; r < 2; ++r)
                     for (int k = 0; k < 4; ++k) {
                         const int64_t i = (r ? bB : bA) + k;
                         if (!((((r ? aB : aA)) >> (8 * k)) & 1u) || P.chronically_missed[i] == 1) continue;
-                        if (ri) {
-                            const int step = A.ri_step;
-                            const int timer = (int)P.ri_timer[i] - step;
-                            P.ri_timer[i] = (int16_t)timer;
-                            if ((tick == step) ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step))
-                                (r ? eB : eA) |= 1u << (8 * k);
-                        }
+                        if (ri_pair && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) (r ? eB : eA) |= 1u << (8 * k);
                         if (camp && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age))
                             (r ? sB : sA) |= 1u << (8 * k);
                     }

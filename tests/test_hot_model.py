@@ -50,6 +50,8 @@ class Table:
         padded = (cap + 2047) // 2048 * 2048
         self.hot = np.zeros(padded, np.uint8)
         self.pair_min = np.zeros(padded // 256, np.int32)
+        self.pair_ri = np.zeros(padded // 256, np.int32)
+        self.ri_k = 0
         tiles = (cap + 511) // 512
         nid = cols["node_id"]
         self.tile_node = np.full(tiles, -1, np.int32)
@@ -64,6 +66,7 @@ class Table:
             setattr(P, name, _ptr(cols[name]))
         P.tile_node, P.capacity, P.hot, P.pair_min_dod = _ptr(self.tile_node), cap, _ptr(self.hot), _ptr(self.pair_min)
         P.risk_e0 = hm.hm_risk_e0(C.c_float(float(cols["acq_risk_multiplier"].max())))
+        P.pair_ri_max = _ptr(self.pair_ri)
         self.P = P
         i32 = lambda *s: np.zeros(s, np.int32)  # noqa: E731
         self.E_cur, self.I_cur, self.R_cur = i32(nodes, ns), i32(nodes, ns), i32(nodes)
@@ -80,10 +83,11 @@ class Table:
                                                          c["paralyzed"], self.nodes, self.ns, n)
         self.E_cur[:], self.I_cur[:], self.R_cur[:] = Ebs, Ibs, R
         assert self.hm.hm_build(C.byref(self.P), C.c_int64(self.cap), C.c_int32(t_next)) == 0
+        self.ri_k = 0
 
 
 def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big_first=True, weird_timers=False, tau_boost=1.0,
-             sia_ticks=(9, 23), vd_step=7, ri_step=14, r0=3.0, f_exposed=0.04, f_infected=0.04):
+             sia_ticks=(9, 23), vd_step=7, ri_step=14, r0=3.0, f_exposed=0.04, f_infected=0.04, settle_every=13):
     from laser_polio_b200 import _lpk, synth
 
     ns = 3
@@ -159,6 +163,7 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
         ri_m = [i32(nodes) for _ in range(3)]
         ne_m, nes_m, rines_m = i32(nodes), i32(nodes, ns), i32(nodes, ns)
         A.ri_step, A.ri_strain, A.vx_prob_ri, A.vx_prob_ipv = ri_step, 1, _ptr(pr), _ptr(pi)
+        A.ri_lazy_k = T.ri_k
         A.ri_vaccinated, A.ri_protected, A.ipv_vaccinated = map(_ptr, ri_m)
         A.new_exposed, A.new_exposed_by_strain, A.ri_new_exposed_by_strain = map(_ptr, (ne_m, nes_m, rines_m))
         sia_m = [i32(nodes), i32(nodes)]
@@ -172,6 +177,7 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
             _ptr, (T.beta, T.E_cur, T.I_cur, T.expo, T.sus, T.hist, T.R_cur))
         rc = hm.hm_pass(C.byref(T.P), C.byref(A), C.c_int64(n), _ptr(stats))
         assert rc == 0, f"hm_pass rc={rc}"
+        T.ri_k += 1 if is_ri else 0
 
         # the pass found tick t-1's exposures: they must be what the oracle's tx_infect made on the canonical table
         if pending:
@@ -204,8 +210,8 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
         q_prev[:], cdf_prev[:] = q, cdf
         pending = True
 
-        if t % 13 == 0 or t == ticks:  # leave the fused representation: settle, apply the pending exposure canonically, compare all
-            assert hm.hm_settle(C.byref(T.P), C.c_int64(cap), C.c_int32(t + 1)) == 0
+        if t % settle_every == 0 or t == ticks:  # leave the fused representation: settle, apply the pending exposure canonically, compare all
+            assert hm.hm_settle(C.byref(T.P), C.c_int64(cap), C.c_int32(t + 1), C.c_int32(T.ri_k), C.c_int32(ri_step)) == 0
             orc.tx_infect_bernoulli(nodes, n, ns, mod["node_id"], mod["strain"], mod["disease_state"], mod["acq_risk_multiplier"], q, cdf,
                                     seed=seed, tick=t)
             for name in can:
@@ -229,7 +235,7 @@ def test_agenda_pass_wraparound_timers_and_mixed_nodes(hm, oracle):
 
 def test_agenda_pass_long_infections_check_in(hm, oracle):
     # 140 ticks: infections longer than the 63-day look-ahead need check-in events; p_paralysis = 1 exercises the gate
-    stats, hits = run_case(hm, oracle, n=30_000, nodes=3, ticks=140, seed=7, p_paralysis=1.0, r0=1.5, sia_ticks=(50,))
+    stats, hits = run_case(hm, oracle, n=30_000, nodes=3, ticks=140, seed=7, p_paralysis=1.0, r0=1.5, sia_ticks=(50,), settle_every=75)
     assert hits > 100
 
 
