@@ -204,6 +204,9 @@ typedef struct lpk_people {
     int32_t risk_e0;                 /* exponent bias of the 6-bit risk code: lpk_hot_risk_e0(largest finite risk in the table) */
     int32_t *pair_ri_max;            /* [lpk_hot_padded(capacity) / 256] largest stored ri_timer among the alive, not chronically
                                         missed agents of each pair (INT32_MIN: nobody); NULL when there is no ri_timer */
+    uint8_t *ri_k;                   /* [lpk_hot_padded(capacity)] which RI tick after lpk_hot_build (1, 2, ... 254) finds the agent
+                                        eligible, 0 = none of them (expired, chronically missed, dead); NULL when there is no
+                                        ri_timer.  The pass reads this byte on RI ticks instead of ri_timer + chronically_missed */
 } lpk_people;
 
 #define LPK_F_PENDING 1u /* apply tick-1's exposure (q_prev / cdf_prev) and take tick-1's census */
@@ -295,7 +298,7 @@ int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *str
  *                   ri_step for the alive, not chronically missed agents, see lpk_tick_args.ri_lazy_k): call before handing
  *                   the table to the per-function entry points or to the host.  disease_state, strain and every other
  *                   column are kept canonical by the pass at all times. */
-int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t *status, void *stream);
+int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_step, int32_t *status, void *stream);
 int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_lazy_k, int32_t ri_step, void *stream);
 int64_t lpk_hot_padded(int64_t capacity); /* capacity rounded up to the pass's work unit (2048 agents) */
 int32_t lpk_hot_risk_e0(float max_risk);
@@ -380,7 +383,8 @@ typedef struct lpk_births_args {
     uint8_t *hot;
     int32_t *pair_min_dod;
     int32_t risk_e0;
-    int32_t *pair_ri_max;        /* with ri_timer: newborns' timers enter the pair's maximum ... */
+    uint8_t *ri_k;               /* with ri_timer: the newborn's eligibility tick (lpk_people.ri_k) */
+    int32_t *pair_ri_max;        /* ... its timer enters the pair's maximum ... */
     int32_t ri_lazy_k, ri_step;  /* ... stored with the lazy countdown's debt added (lpk_tick_args.ri_lazy_k) */
 } lpk_births_args;
 

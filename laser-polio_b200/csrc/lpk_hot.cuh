@@ -138,6 +138,18 @@ LPK_HD bool ri_eligible(int16_t stored, int k_before, int step, int tick) {
     const int timer = (int)ri_owed(stored, k_before, step) - step;
     return (tick == step) ? (timer <= 0 && timer >= -step) : (tick > step && timer <= 0 && timer > -step);
 }
+// Which RI tick after a rebase (1 = the next one, ...) finds an alive, not chronically missed agent eligible, given its
+// timer `stored` with `k_done` subtractions owed and `t_last` = the tick before the next one to run; 0 = none of the next
+// 254.  The timer after j more subtractions is stored - (k_done + j) * step; it lies in (-step, 0] for exactly one j
+// (timer > 0), and on the very first RI tick of a run (tick == step) the window also holds -step (model.py:1836-1843).
+LPK_HD uint8_t ri_tick_index(int16_t stored, int k_done, int step, int t_last) {
+    const int cur = (int)ri_owed(stored, k_done, step);
+    const int next_ri_tick = (t_last / step + 1) * step;  // first RI tick > t_last
+    int j = 0;
+    if (cur >= 1) j = (cur + step - 1) / step;
+    else if (cur == 0 && next_ri_tick == step) j = 1;
+    return (j >= 1 && j <= 254) ? (uint8_t)j : (uint8_t)0;
+}
 // The inverse for the timers: deadline -> the value tick t_next would test; the RI countdown's debt is paid.
 LPK_HD void hot_settle_agent(const lpk_people &P, int64_t i, int t_next, int ri_k, int ri_step) {
     const int8_t s = P.disease_state[i];
@@ -320,7 +332,7 @@ LPK_HD HotDelta hot_event(const lpk_people &P, const lpk_tick_args &A, int64_t i
         }
     }
     // ---- 4. vaccine draws, after the agent's own disease-state step (the reference's run order)
-    if ((fl & EV_RI) && (A.flags & LPK_F_RI)) {
+    if ((fl & EV_RI) && (A.flags & LPK_F_RI) && s >= 0) {
         uint32_t x[4];
         philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_RI, x);
         if (u53(x[0], x[1]) < A.vx_prob_ri[nd]) {
@@ -329,7 +341,7 @@ LPK_HD HotDelta hot_event(const lpk_people &P, const lpk_tick_args &A, int64_t i
         }
         if (u53(x[2], x[3]) < A.vx_prob_ipv[nd]) { d.vx |= 4; P.ipv_protected[i] = 1; }
     }
-    if ((fl & EV_SIA) && (A.flags & LPK_F_SIA)) {
+    if ((fl & EV_SIA) && (A.flags & LPK_F_SIA) && s >= 0) {
         uint32_t x[4];
         philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
         const double u = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];

@@ -222,21 +222,10 @@ __device__ __forceinline__ uint32_t sia_age_mask(const int4 &d, int tick, int lo
 // ---- routine immunisation in a quad (reference model.py:1825-1854) -----------------------------------------------
 // The reference subtracts the step from every alive, not chronically missed agent's ri_timer on every RI tick; an agent is
 // eligible when the new timer lies in (-step, 0] ([-step, 0] on the first RI tick).  Here the countdown is lazy
-// (lpk_tick_args.ri_lazy_k): nothing is written, the timer after today's subtraction is stored - (k + 1) * step on four
-// int16 lanes.  Eligible agents are the few in the age window; they go to the ring and take their two draws in the
-// handler, after their disease-state step.
-__device__ __forceinline__ uint32_t ri_eligible_quad(const PassParams &pp, uint32_t alive, uint32_t missed, uint2 tm) {
-    const int step = pp.A.ri_step;
-    const uint32_t ok8 = alive & ~missed;  // missed bytes are 0 / 1
-    if (!ok8) return 0u;
-    const uint32_t debt2 = ((uint32_t)((pp.A.ri_lazy_k + 1) * step) & 0xFFFFu) * 0x10001u;
-    const uint2 tn = make_uint2(__vsub2(tm.x, debt2), __vsub2(tm.y, debt2));
-    const int lo = (pp.A.tick == step) ? -step : 1 - step;  // eligible: lo <= timer <= 0
-    const uint32_t lo2 = ((uint32_t)lo & 0xFFFFu) * 0x10001u, span2 = ((uint32_t)(-lo) & 0xFFFFu) * 0x10001u;
-    const uint32_t ex = __vcmpleu2(__vsub2(tn.x, lo2), span2), ey = __vcmpleu2(__vsub2(tn.y, lo2), span2);
-    return __byte_perm(ex, ey, 0x6420) & ok8;
-}
-
+// (lpk_tick_args.ri_lazy_k): nothing is written.  Eligible agents are the few in the age window; they go to the ring and
+// take their two draws in the handler, after their disease-state step.
+// The sweep reads the agent's precomputed eligibility tick (lpk_people.ri_k: one byte, built by lpk_hot_build / births)
+// and compares it with the number of today's RI tick on byte lanes.
 // append the agents of the two quads a lane owns in a row pair (B = A + 128 agents); F = per-agent flag bytes
 // (bit 0 candidate, 1 agenda day, 2 death, 3 RI, 4 SIA); returns how many
 __device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t idxA, int nd, uint32_t FA, uint32_t FB) {
@@ -296,8 +285,8 @@ __device__ __noinline__ int general_pair(const PassParams &pp, uint2 *q, uint32_
             if ((hb | 0x40u) == today) fl |= EV_FIRE;
             bool dying = false;
             if (kDeaths && P.date_of_death[i] <= tick) { fl |= EV_DEATH; dying = true; }
-            if ((kRI || kSIA) && !dying && P.chronically_missed[i] != 1) {
-                if (kRI && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) fl |= EV_RI;
+            if ((kRI || kSIA) && !dying && (!kSIA || P.chronically_missed[i] != 1)) {
+                if (kRI && P.ri_k[i] == (uint8_t)(A.ri_lazy_k + 1)) fl |= EV_RI;
                 if (kSIA && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age) &&
                     A.sia_targeted[nd] != 0)
                     fl |= EV_SIA;
@@ -344,6 +333,10 @@ __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0u;
+}
+// ask the copy engine to bring a block of global memory into L2 (no destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -448,6 +441,13 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             fence_proxy_async_smem();  // the warp's reads of this buffer (previous use) precede the engine's writes
             mbar_arrive_expect_tx(bar, LPK_UNIT_AGENTS);
             tma_load(smem_u32(stage) + (uint32_t)buf * LPK_UNIT_AGENTS, P.hot + (int64_t)u * LPK_UNIT_AGENTS, LPK_UNIT_AGENTS, bar);
+            // the columns the special days read for (nearly) every pair of the unit: into L2 a unit ahead, so that the loads in
+            // the tile loop cost an L2 hit instead of a DRAM round trip (profiles/r2: the RI day was latency bound, 1.1 ms)
+            const int64_t a0 = (int64_t)u * LPK_UNIT_AGENTS;
+            if ((kRI || kSIA) && a0 + LPK_UNIT_AGENTS <= P.capacity) {
+                if (kRI) tma_prefetch_l2(P.ri_k + a0, LPK_UNIT_AGENTS);
+                if (kSIA) { tma_prefetch_l2(P.chronically_missed + a0, LPK_UNIT_AGENTS); tma_prefetch_l2(P.date_of_birth + a0, 4 * LPK_UNIT_AGENTS); }
+            }
         }
     };
 
@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     float tc_tauS = 0.f;
     bool tc_sia = false;
     const int ri_debt = kRI ? A.ri_lazy_k * A.ri_step : 0;  // an agent whose stored timer is below this can never be eligible again
+    const uint32_t ri_today = ((uint32_t)(A.ri_lazy_k + 1) & 0xFFu) * 0x01010101u;  // today's RI tick as lpk_people.ri_k counts them
     const int sia_lo = kSIA ? A.sia_min_age : 0;
     const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
 
@@ -539,16 +540,15 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                         }
                     }
                     // RI: only pairs in which somebody's timer has not run out for good (stored >= debt) can hold an eligible agent
-                    const bool ri_pair = kRI && __shfl_sync(LPK_FULL, rmv, 2 * tp + j) >= ri_debt;
-                    if (ri_pair || (kSIA && tc_sia)) {
+                    if (kRI && __shfl_sync(LPK_FULL, rmv, 2 * tp + j) >= ri_debt) {  // (the dead are turned away by the handler)
+                        eA = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bA) ^ ri_today) & ~dmA;
+                        eB = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bB) ^ ri_today) & ~dmB;
+                    }
+                    if (kSIA && tc_sia) {
                         const uint32_t mA = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bA);
                         const uint32_t mB = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bB);
                         const uint32_t aA = hot_mask_alive(hA) & ~dmA, aB = hot_mask_alive(hB) & ~dmB;
-                        if (ri_pair) {
-                            eA = ri_eligible_quad(pp, aA, mA, __ldg(reinterpret_cast<const uint2 *>(P.ri_timer + bA)));
-                            eB = ri_eligible_quad(pp, aB, mB, __ldg(reinterpret_cast<const uint2 *>(P.ri_timer + bB)));
-                        }
-                        if (kSIA && tc_sia) {
+                        {
                             sA = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bA)), tick, sia_lo, sia_span) & aA & ~mA;
                             sB = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bB)), tick, sia_lo, sia_span) & aB & ~mB;
                         }
@@ -622,7 +622,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     if (deaths) REQUIRE(P.date_of_death && ALIGNED(P.date_of_death, 16) && P.pair_min_dod && A.deaths && A.dead_pp && A.dead_par,
                         "tick_pass deaths");
     if (A.ri_lazy_k) REQUIRE(A.ri_lazy_k > 0 && A.ri_step > 0 && P.ri_timer && P.chronically_missed, "tick_pass lazy RI countdown");
-    if (ri) REQUIRE(P.pair_ri_max && P.ri_timer && ALIGNED(P.ri_timer, 8) && P.chronically_missed && ALIGNED(P.chronically_missed, 4) && A.vx_prob_ri &&
+    if (ri) REQUIRE(P.pair_ri_max && P.ri_k && ALIGNED(P.ri_k, 16) && A.ri_lazy_k < 254 && P.ri_timer && P.chronically_missed && A.vx_prob_ri &&
                         A.vx_prob_ipv && A.ri_vaccinated && A.ri_protected && A.ipv_vaccinated && A.new_exposed &&
                         A.new_exposed_by_strain && A.ri_new_exposed_by_strain && A.ri_step > 0 && A.ri_strain >= 0 &&
                         A.ri_strain < A.n_strains, "tick_pass RI");
@@ -691,13 +691,18 @@ __global__ void __launch_bounds__(256) k_pair_min_dod(lpk_people P, int64_t n_sl
     }
 }
 // largest stored ri_timer among the alive, not chronically missed agents of every pair
-__global__ void __launch_bounds__(256) k_pair_ri_max(lpk_people P, int64_t n_slots, int64_t n_pairs) {
+__global__ void __launch_bounds__(256) k_pair_ri_max(lpk_people P, int64_t n_slots, int64_t n_pairs, int t_next, int ri_step) {
     const int lane = threadIdx.x & 31;
     for (int64_t gp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gp < n_pairs; gp += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         int m = INT_MIN;
         for (int k = lane; k < 256; k += 32) {
             const int64_t i = gp * 256 + k;
-            if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1) m = max(m, (int)P.ri_timer[i]);
+            uint8_t rk = 0;
+            if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1) {
+                m = max(m, (int)P.ri_timer[i]);
+                rk = ri_tick_index(P.ri_timer[i], 0, ri_step, t_next - 1);
+            }
+            P.ri_k[i] = rk;
         }
         m = __reduce_max_sync(LPK_FULL, m);
         if (lane == 0) P.pair_ri_max[gp] = m;
@@ -709,7 +714,7 @@ __global__ void __launch_bounds__(256) k_hot_settle(lpk_people P, int64_t n_slot
 }
 static inline int64_t hot_padded(int64_t capacity) { return (capacity + LPK_UNIT_AGENTS - 1) / LPK_UNIT_AGENTS * LPK_UNIT_AGENTS; }
 
-extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t *status, void *stream) {
+extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_step, int32_t *status, void *stream) {
     REQUIRE(people, "hot_build null struct");
     const lpk_people &P = *people;
     REQUIRE(P.hot && P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer &&
@@ -723,8 +728,9 @@ extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t 
         k_pair_min_dod<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256);
         CUDA_TRY(cudaGetLastError(), "lpk_hot_build pair_min_dod");
     }
-    if (P.pair_ri_max && P.ri_timer && P.chronically_missed) {
-        k_pair_ri_max<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256);
+    if (P.pair_ri_max && P.ri_timer) {
+        REQUIRE(P.ri_k && P.chronically_missed && ri_step > 0 && tick_next >= 1, "hot_build RI companions");
+        k_pair_ri_max<<<lpk_sm_count() * 8, 256, 0, st>>>(P, n_slots, padded / 256, tick_next, ri_step);
         CUDA_TRY(cudaGetLastError(), "lpk_hot_build pair_ri_max");
     }
     return LPK_OK;

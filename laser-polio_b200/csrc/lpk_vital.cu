@@ -104,6 +104,10 @@ __global__ void k_births_fill(lpk_births_args a) {
             a.ri_timer[slot] = (int16_t)(uint16_t)((uint16_t)a.ri_timer[slot] + (uint16_t)(a.ri_lazy_k * a.ri_step));
         }
         if (a.ri_timer && a.pair_ri_max) atomicMax(&a.pair_ri_max[slot >> 8], (int)a.ri_timer[slot]);
+        if (a.ri_timer && a.ri_k) {  // today's RI tick, if any, comes after the births: the newborn takes part in it
+            const uint8_t j = ri_tick_index(a.ri_timer[slot], a.ri_lazy_k, a.ri_step, a.tick - 1);
+            a.ri_k[slot] = (j && a.ri_lazy_k + (int)j <= 254) ? (uint8_t)(a.ri_lazy_k + j) : (uint8_t)0;
+        }
         if (a.hot) {  // fused path: the newborn's agenda byte (a susceptible) and its pair's earliest death date
             bool over = false;
             a.hot[slot] = (uint8_t)(HOT_S | risk_code(a.acq_risk_multiplier[slot], a.risk_e0, &over));

@@ -89,6 +89,7 @@ class FusedEngine:
         self.hot = torch.empty(padded, dtype=torch.uint8, device=d)
         self.pair_min_dod = torch.empty(padded // 256, dtype=torch.int32, device=d) if "date_of_death" in c else None
         self.pair_ri_max = torch.empty(padded // 256, dtype=torch.int32, device=d) if "ri_timer" in c else None
+        self.ri_k = torch.zeros(padded, dtype=torch.uint8, device=d) if "ri_timer" in c else None
         self.ri_lazy_k = 0  # RI ticks whose ri_timer subtraction is still owed (lpk_tick_args.ri_lazy_k)
         ri = self.by_name.get("RI_ABM")
         self.ri_step = int(ri.step_size) if ri is not None else 0
@@ -105,7 +106,7 @@ class FusedEngine:
             setattr(P, name, dp(c.get(name)))
         P.tile_node = dp(self.tile_node)
         P.capacity = cap
-        P.hot, P.pair_min_dod, P.pair_ri_max = dp(self.hot), dp(self.pair_min_dod), dp(self.pair_ri_max)
+        P.hot, P.pair_min_dod, P.pair_ri_max, P.ri_k = dp(self.hot), dp(self.pair_min_dod), dp(self.pair_ri_max), dp(self.ri_k)
         P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
         if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
@@ -140,7 +141,7 @@ class FusedEngine:
                       dev.n_strains, sim.people.count, out=(S, E, I, self.R_cur, self.E_cur, self.I_cur, POTP, Pz))
         self.tx_hits.zero_()
         self.tx_hits_s.zero_()
-        check(_lpk.lib().lpk_hot_build(C.byref(self.P), C.c_int64(sim.people.capacity), C.c_int32(t_next), _lpk.ptr(dev.status),
+        check(_lpk.lib().lpk_hot_build(C.byref(self.P), C.c_int64(sim.people.capacity), C.c_int32(t_next), C.c_int32(max(self.ri_step, 1)), _lpk.ptr(dev.status),
                                        stream_handle()), "lpk_hot_build")
         self.hot_valid = True
 
@@ -229,7 +230,7 @@ class FusedEngine:
             if pars.cbr is None:
                 raise ValueError("VitalDynamics_ABM needs pars.cbr")
             b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist),
-                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step))
+                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step, self.ri_k))
             K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns

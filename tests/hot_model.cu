@@ -41,7 +41,7 @@ static void apply_delta(const lpk_tick_args &A, const HotDelta &d) {
     }
 }
 
-extern "C" int hm_build(const lpk_people *people, int64_t n_slots, int32_t t_next) {
+extern "C" int hm_build(const lpk_people *people, int64_t n_slots, int32_t t_next, int32_t ri_step) {
     const lpk_people &P = *people;
     const int64_t padded = (P.capacity + 2047) / 2048 * 2048;
     bool over = false;
@@ -60,7 +60,12 @@ extern "C" int hm_build(const lpk_people *people, int64_t n_slots, int32_t t_nex
             int m = INT_MIN;
             for (int k = 0; k < 256; ++k) {
                 const int64_t i = gp * 256 + k;
-                if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1 && P.ri_timer[i] > m) m = P.ri_timer[i];
+                uint8_t rk = 0;
+                if (i < n_slots && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1) {
+                    if (P.ri_timer[i] > m) m = P.ri_timer[i];
+                    rk = ri_tick_index(P.ri_timer[i], 0, ri_step, t_next - 1);
+                }
+                P.ri_k[i] = rk;
             }
             P.pair_ri_max[gp] = m;
         }
@@ -105,8 +110,10 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
                 if ((hb | 0x40u) == (today & 0xFFu)) fl |= EV_FIRE;
                 bool dying = false;
                 if (deaths && P.date_of_death[i] <= tick) { fl |= EV_DEATH; dying = true; }
-                if ((ri || sia) && !dying && P.chronically_missed[i] != 1) {
-                    if (ri && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) fl |= EV_RI;
+                if ((ri || sia) && !dying && (!sia || P.chronically_missed[i] != 1)) {
+                    if (ri && P.ri_k[i] == (uint8_t)(A.ri_lazy_k + 1)) fl |= EV_RI;
+                    if (ri && P.disease_state[i] >= 0 && P.chronically_missed[i] != 1 &&
+                        (P.ri_k[i] == (uint8_t)(A.ri_lazy_k + 1)) != ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) return -11;
                     if (sia && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age) &&
                         A.sia_targeted[nd] != 0)
                         fl |= EV_SIA;
@@ -166,8 +173,10 @@ extern "C" int hm_pass(const lpk_people *people, const lpk_tick_args *args, int6
                 for (int r = 0; r < 2; ++r)
                     for (int k = 0; k < 4; ++k) {
                         const int64_t i = (r ? bB : bA) + k;
+                        const bool dying = (((r ? dmB : dmA) >> (8 * k)) & 1u) != 0;
+                        if (ri_pair && !dying && P.ri_k[i] == (uint8_t)(A.ri_lazy_k + 1)) (r ? eB : eA) |= 1u << (8 * k);
                         if (!((((r ? aB : aA)) >> (8 * k)) & 1u) || P.chronically_missed[i] == 1) continue;
-                        if (ri_pair && ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) (r ? eB : eA) |= 1u << (8 * k);
+                        if (ri_pair && (P.ri_k[i] == (uint8_t)(A.ri_lazy_k + 1)) != ri_eligible(P.ri_timer[i], A.ri_lazy_k, A.ri_step, tick)) return -12;
                         if (camp && (uint32_t)(tick - P.date_of_birth[i] - A.sia_min_age) <= (uint32_t)(A.sia_max_age - A.sia_min_age))
                             (r ? sB : sA) |= 1u << (8 * k);
                     }

@@ -51,6 +51,7 @@ class Table:
         self.hot = np.zeros(padded, np.uint8)
         self.pair_min = np.zeros(padded // 256, np.int32)
         self.pair_ri = np.zeros(padded // 256, np.int32)
+        self.ri_kcol = np.zeros(padded, np.uint8)
         self.ri_k = 0
         tiles = (cap + 511) // 512
         nid = cols["node_id"]
@@ -66,7 +67,7 @@ class Table:
             setattr(P, name, _ptr(cols[name]))
         P.tile_node, P.capacity, P.hot, P.pair_min_dod = _ptr(self.tile_node), cap, _ptr(self.hot), _ptr(self.pair_min)
         P.risk_e0 = hm.hm_risk_e0(C.c_float(float(cols["acq_risk_multiplier"].max())))
-        P.pair_ri_max = _ptr(self.pair_ri)
+        P.pair_ri_max, P.ri_k = _ptr(self.pair_ri), _ptr(self.ri_kcol)
         self.P = P
         i32 = lambda *s: np.zeros(s, np.int32)  # noqa: E731
         self.E_cur, self.I_cur, self.R_cur = i32(nodes, ns), i32(nodes, ns), i32(nodes)
@@ -74,7 +75,7 @@ class Table:
         self.hist = i32(nodes, 192)
         self.counts = np.array([n, n], np.int64)
 
-    def rebase(self, orc, srs, t_next):
+    def rebase(self, orc, srs, t_next, ri_step=14):
         c, n = self.c, self.n
         _, _, sus, bfx, efx = orc.tx_step_prep(self.nodes, n, self.ns, c["strain"], srs, c["disease_state"], c["node_id"],
                                                c["daily_infectivity"], c["acq_risk_multiplier"], mode="fx")
@@ -82,7 +83,7 @@ class Table:
         S, E, I, R, Ebs, Ibs, PP, Pz = orc.count_SEIRP(c["node_id"], c["disease_state"], c["strain"], c["potentially_paralyzed"],
                                                          c["paralyzed"], self.nodes, self.ns, n)
         self.E_cur[:], self.I_cur[:], self.R_cur[:] = Ebs, Ibs, R
-        assert self.hm.hm_build(C.byref(self.P), C.c_int64(self.cap), C.c_int32(t_next)) == 0
+        assert self.hm.hm_build(C.byref(self.P), C.c_int64(self.cap), C.c_int32(t_next), C.c_int32(ri_step)) == 0
         self.ri_k = 0
 
 
@@ -107,7 +108,7 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
     can["date_of_birth"][:n] = -rs.randint(1, 8 * 365, n)
     mod = {k: v.copy() for k, v in can.items()}
     T = Table(hm, mod, n, cap, nodes, ns, seed, orc)
-    T.rebase(orc, srs, 1)
+    T.rebase(orc, srs, 1, ri_step)
 
     W = rs.random_sample((nodes, nodes)) * (0.1 / nodes)
     np.fill_diagonal(W, 0.0)
@@ -216,7 +217,7 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
                                     seed=seed, tick=t)
             for name in can:
                 assert np.array_equal(mod[name], can[name]), f"tick {t}: column {name}"
-            T.rebase(orc, srs, t + 1)
+            T.rebase(orc, srs, t + 1, ri_step)
             pending = False
     return stats, total_hits
 

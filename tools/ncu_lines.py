@@ -29,5 +29,7 @@ for r in csv.reader(src.splitlines()):
 ti, ts = max(sum(inst.values()), 1), max(sum(stall.values()), 1)
 print(f"# launch {which}: {ti} warp-instructions, {ts} stall samples")
 print("# by stall samples: %stall %inst file:line source")
-for key, v in stall.most_common(top):
+order = inst if (len(sys.argv) > 4 and sys.argv[4] == "inst") else stall
+for key, v in order.most_common(top):
+    v = stall[key]
     print(f"{100 * v / ts:5.1f} {100 * inst[key] / ti:5.1f}  {key[0]}:{key[1]:<4d} {text[key]}")
