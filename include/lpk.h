@@ -204,6 +204,11 @@ typedef struct lpk_people {
     int32_t risk_e0;                 /* exponent bias of the 6-bit risk code: lpk_hot_risk_e0(largest finite risk in the table) */
     int32_t *pair_ri_max;            /* [lpk_hot_padded(capacity) / 256] largest stored ri_timer among the alive, not chronically
                                         missed agents of each pair (INT32_MIN: nobody); NULL when there is no ri_timer */
+    uint64_t *rec;                   /* [capacity] per-agent event record while the table is on the fused path: the bytes
+                                        {disease_state, strain, exposure_timer, infection_timer, paralysis_timer,
+                                        potentially_paralyzed, paralyzed, ipv_protected}, timers as deadlines (see below).
+                                        The pass reads and writes THIS instead of the eight columns; lpk_hot_build fills
+                                        it from them, lpk_hot_settle writes it back */
     uint8_t *ri_k;                   /* [lpk_hot_padded(capacity)] which RI tick after lpk_hot_build (1, 2, ... 254) finds the agent
                                         eligible, 0 = none of them (expired, chronically missed, dead); NULL when there is no
                                         ri_timer.  The pass reads this byte on RI ticks instead of ri_timer + chronically_missed */
@@ -287,17 +292,18 @@ int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *str
  *   bits 7:6 class: 00 susceptible, 01 inactive (payload 0 recovered, 1 dead / unborn), 10 exposed, 11 infectious
  *   bits 5:0 susceptible: 6-bit upper bound of acq_risk_multiplier (4 steps per octave; 2^(e - risk_e0) * (1 + m / 4));
  *            exposed / infectious: day of the agent's next event (E -> I, paralysis gate, I -> R) modulo 64
- * and touches the reference's full-width columns only for agents with an event.  While an agent is exposed / infectious
- * its countdown columns hold DEADLINES, (timer + tick) mod 256 -- exposure_timer while disease_state == 1,
- * infection_timer while == 2, paralysis_timer while == 2 and strain == 0 -- so nothing is decremented on the days in
- * between (the reference decrements daily, model.py:419-452; the tested values are identical, int8 wrap-around included).
- *   lpk_hot_build   canonical columns (as every per-function entry point above reads them) -> agenda bytes + deadlines
- *                   + pair_min_dod, for the table as it stands BEFORE tick `tick_next`.  *status = 2 if a risk exceeds the
+ * and touches full-width data only for agents with an event: the 8-byte record people->rec[i] (the eight byte columns of
+ * the disease state side by side) plus risk / infectivity / dates where the event needs them.  While an agent is exposed /
+ * infectious the countdown bytes of its record hold DEADLINES, (timer + tick) mod 256 -- exposure_timer while
+ * disease_state == 1, infection_timer while == 2, paralysis_timer while == 2 and strain == 0 -- so nothing is decremented
+ * on the days in between (the reference decrements daily, model.py:419-452; the tested values are identical, int8
+ * wrap-around included).  The reference-dtype columns are not touched by the pass and are stale until lpk_hot_settle.
+ *   lpk_hot_build   canonical columns (as every per-function entry point above reads them) -> records + agenda bytes +
+ *                   pair_min_dod / pair_ri_max / ri_k, for the table as it stands BEFORE tick `tick_next`.  *status = 2 if a risk exceeds the
  *                   range of the code (risk_e0 too large); slots >= n_slots and the padding read as dead.
- *   lpk_hot_settle  the inverse for the timers (deadline -> the value tick `tick_next` would test; ri_timer -= ri_lazy_k *
- *                   ri_step for the alive, not chronically missed agents, see lpk_tick_args.ri_lazy_k): call before handing
- *                   the table to the per-function entry points or to the host.  disease_state, strain and every other
- *                   column are kept canonical by the pass at all times. */
+ *   lpk_hot_settle  the inverse: records -> the eight columns (deadline -> the value tick `tick_next` would test; ri_timer -=
+ *                   ri_lazy_k * ri_step for the alive, not chronically missed agents, see lpk_tick_args.ri_lazy_k): call
+ *                   before handing the table to the per-function entry points or to the host. */
 int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_step, int32_t *status, void *stream);
 int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_lazy_k, int32_t ri_step, void *stream);
 int64_t lpk_hot_padded(int64_t capacity); /* capacity rounded up to the pass's work unit (2048 agents) */
@@ -383,6 +389,8 @@ typedef struct lpk_births_args {
     uint8_t *hot;
     int32_t *pair_min_dod;
     int32_t risk_e0;
+    uint64_t *rec;               /* the newborn's event record (lpk_people.rec), from the pre-drawn columns of its slot */
+    const int8_t *strain, *exposure_timer, *infection_timer, *paralysis_timer, *potentially_paralyzed, *paralyzed, *ipv_protected;
     uint8_t *ri_k;               /* with ri_timer: the newborn's eligibility tick (lpk_people.ri_k) */
     int32_t *pair_ri_max;        /* ... its timer enters the pair's maximum ... */
     int32_t ri_lazy_k, ri_step;  /* ... stored with the lazy countdown's debt added (lpk_tick_args.ri_lazy_k) */

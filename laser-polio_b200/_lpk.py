@@ -113,7 +113,7 @@ class People(C.Structure):
         "disease_state", "strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed",
         "paralyzed", "ipv_protected", "chronically_missed", "node_id", "ri_timer", "acq_risk_multiplier",
         "daily_infectivity", "date_of_birth", "date_of_death", "tile_node")] + [
-            ("capacity", C.c_int64), ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("pair_ri_max", _VP), ("ri_k", _VP)]
+            ("capacity", C.c_int64), ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("pair_ri_max", _VP), ("rec", _VP), ("ri_k", _VP)]
 
 
 class TickArgs(C.Structure):
@@ -166,7 +166,9 @@ class BirthsArgs(C.Structure):
         ("cohort_ws", _VP), ("status", _VP), ("disease_state", _VP), ("node_id", _VP), ("date_of_birth", _VP),
         ("date_of_death", _VP), ("ri_timer", _VP), ("tile_node", _VP),
         ("acq_risk_multiplier", _VP), ("sus", _VP), ("exposure_fx", _VP), ("risk_hist", _VP),
-        ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("ri_k", _VP), ("pair_ri_max", _VP), ("ri_lazy_k", C.c_int32),
+        ("hot", _VP), ("pair_min_dod", _VP), ("risk_e0", C.c_int32), ("rec", _VP), ("strain", _VP), ("exposure_timer", _VP),
+        ("infection_timer", _VP), ("paralysis_timer", _VP), ("potentially_paralyzed", _VP), ("paralyzed", _VP), ("ipv_protected", _VP),
+        ("ri_k", _VP), ("pair_ri_max", _VP), ("ri_lazy_k", C.c_int32),
         ("ri_step", C.c_int32),
     ]
 

@@ -764,7 +764,11 @@ class VitalDynamics_ABM:
             a.acq_risk_multiplier = c["acq_risk_multiplier"].data_ptr()
             a.sus, a.exposure_fx, a.risk_hist = sus.data_ptr(), expo.data_ptr(), hist.data_ptr()
         if hot is not None:  # fused path: newborns get their agenda byte (csrc/lpk_hot.cuh)
-            hot_bytes, pair_min_dod, e0, pair_ri_max, ri_k, ri_step, ri_kcol = hot
+            hot_bytes, pair_min_dod, e0, pair_ri_max, ri_k, ri_step, ri_kcol, rec = hot
+            a.rec = rec.data_ptr()
+            for name in ("strain", "exposure_timer", "infection_timer", "paralysis_timer", "potentially_paralyzed", "paralyzed",
+                         "ipv_protected"):
+                setattr(a, name, c[name].data_ptr())
             a.ri_k = ri_kcol.data_ptr() if ri_kcol is not None else None
             a.hot = hot_bytes.data_ptr()
             a.pair_min_dod = pair_min_dod.data_ptr() if pair_min_dod is not None else None

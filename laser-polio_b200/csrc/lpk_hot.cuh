@@ -106,30 +106,48 @@ LPK_HD uint32_t hot_pretest(uint32_t h, uint32_t xa, uint32_t xb, float tauS) {
 }
 
 
+// ---------------------------------------------------------------- the event record
+// The eight byte columns an event can touch (disease_state, strain, exposure_timer, infection_timer, paralysis_timer,
+// potentially_paralyzed, paralyzed, ipv_protected) are gathered, while the table is on the fused path, in ONE 8-byte record
+// per agent, lpk_people.rec[i]: an event costs one 8-byte load and one 8-byte store instead of up to twelve scattered
+// sector accesses in eight arrays (profiles/r2_fused_v31_*: after a campaign the handler, not the sweep, set the pace).
+// The reference-dtype columns stay allocated and canonical but are not touched by the pass; lpk_hot_build fills the
+// records from them and lpk_hot_settle writes them back (deadlines converted to countdown values).
+struct HotRec {
+    int8_t state, strain, et, it, pt, pq, par, ipv;  // et / it / pt: deadlines while the owning state lasts (see top)
+};
+union HotRecU {
+    unsigned long long u;
+    HotRec r;
+};
+
 // ---------------------------------------------------------------- canonical <-> agenda
-// Agenda byte of agent i as the table stands before tick t_next runs, converting the timers of exposed / infectious
-// agents to deadline form.  Returns the byte; *over: risk beyond the code range.
+// Record and agenda byte of agent i as the table stands before tick t_next runs (timers of exposed / infectious agents
+// become deadlines in the record).  Returns the byte; *over: risk beyond the code range.
 LPK_HD uint8_t hot_build_agent(const lpk_people &P, int64_t i, int t_next, int e0, bool *over) {
-    const int8_t s = P.disease_state[i];
+    HotRecU x;
+    x.r.state = P.disease_state[i]; x.r.strain = P.strain[i];
+    x.r.et = P.exposure_timer[i]; x.r.it = P.infection_timer[i]; x.r.pt = P.paralysis_timer[i];
+    x.r.pq = P.potentially_paralyzed[i]; x.r.par = P.paralyzed[i]; x.r.ipv = P.ipv_protected[i];
+    const int8_t s = x.r.state;
     const uint8_t t8 = (uint8_t)t_next;
-    if (s == 0) return (uint8_t)(HOT_S | risk_code(P.acq_risk_multiplier[i], e0, over));
-    if (s == 1) {
-        const int8_t et = P.exposure_timer[i];
-        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)et + t8);
-        return (uint8_t)(HOT_E | hot_due(t_next, et));
-    }
-    if (s == 2) {
-        const int8_t it = P.infection_timer[i];
-        P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)it + t8);
-        int next = it < 0 ? 0 : it;
-        if (P.strain[i] == 0) {
-            const int8_t pt = P.paralysis_timer[i];
-            P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)pt + t8);
-            if (P.potentially_paralyzed[i] == -1) { const int g = pt < 0 ? 0 : pt; if (g < next) next = g; }
+    uint8_t h = s == 3 ? (uint8_t)HOT_R : (uint8_t)HOT_DEAD;
+    if (s == 0) {
+        h = (uint8_t)(HOT_S | risk_code(P.acq_risk_multiplier[i], e0, over));
+    } else if (s == 1) {
+        h = (uint8_t)(HOT_E | hot_due(t_next, x.r.et));
+        x.r.et = (int8_t)(uint8_t)((uint8_t)x.r.et + t8);
+    } else if (s == 2) {
+        int next = x.r.it < 0 ? 0 : x.r.it;
+        x.r.it = (int8_t)(uint8_t)((uint8_t)x.r.it + t8);
+        if (x.r.strain == 0) {
+            if (x.r.pq == -1) { const int g = x.r.pt < 0 ? 0 : x.r.pt; if (g < next) next = g; }
+            x.r.pt = (int8_t)(uint8_t)((uint8_t)x.r.pt + t8);
         }
-        return (uint8_t)(HOT_I | hot_due(t_next, next));
+        h = (uint8_t)(HOT_I | hot_due(t_next, next));
     }
-    return s == 3 ? (uint8_t)HOT_R : (uint8_t)HOT_DEAD;
+    P.rec[i] = x.u;
+    return h;
 }
 // Lazy RI countdown (include/lpk.h, lpk_tick_args.ri_lazy_k): the agent's timer after k owed subtractions, and whether the
 // RI tick `tick` (the k_after-th subtraction) finds it eligible -- reference model.py:1833-1843 on the wrapped int16 value.
@@ -150,31 +168,35 @@ LPK_HD uint8_t ri_tick_index(int16_t stored, int k_done, int step, int t_last) {
     else if (cur == 0 && next_ri_tick == step) j = 1;
     return (j >= 1 && j <= 254) ? (uint8_t)j : (uint8_t)0;
 }
-// The inverse for the timers: deadline -> the value tick t_next would test; the RI countdown's debt is paid.
+// The inverse: the record back into the reference's columns, deadlines -> the values tick t_next would test; the RI
+// countdown's debt is paid.
 LPK_HD void hot_settle_agent(const lpk_people &P, int64_t i, int t_next, int ri_k, int ri_step) {
-    const int8_t s = P.disease_state[i];
+    HotRecU x;
+    x.u = P.rec[i];
+    const int8_t s = x.r.state;
     const uint8_t t8 = (uint8_t)t_next;
     if (ri_k && P.ri_timer && s >= 0 && P.chronically_missed[i] != 1) P.ri_timer[i] = ri_owed(P.ri_timer[i], ri_k, ri_step);
     if (s == 1) {
-        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)P.exposure_timer[i] - t8);
+        x.r.et = (int8_t)(uint8_t)((uint8_t)x.r.et - t8);
     } else if (s == 2) {
-        P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)P.infection_timer[i] - t8);
-        if (P.strain[i] == 0) P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)P.paralysis_timer[i] - t8);
+        x.r.it = (int8_t)(uint8_t)((uint8_t)x.r.it - t8);
+        if (x.r.strain == 0) x.r.pt = (int8_t)(uint8_t)((uint8_t)x.r.pt - t8);
     }
+    P.disease_state[i] = x.r.state; P.strain[i] = x.r.strain;
+    P.exposure_timer[i] = x.r.et; P.infection_timer[i] = x.r.it; P.paralysis_timer[i] = x.r.pt;
+    P.potentially_paralyzed[i] = x.r.pq; P.paralyzed[i] = x.r.par; P.ipv_protected[i] = x.r.ipv;
 }
 
 // ---------------------------------------------------------------- the event
 // What hot_event needs from the agent's columns, loaded one ring batch ahead of its use on the device.
 struct HotPre {
-    int8_t state, et, it;
+    unsigned long long rec;
     float rk, inf;
 };
 LPK_HD HotPre hot_preload(const lpk_people &P, int64_t i, uint32_t fl) {
     HotPre r;
-    r.state = P.disease_state[i];
-    r.et = P.exposure_timer[i];
-    r.it = P.infection_timer[i];
-    r.inf = P.daily_infectivity[i];
+    r.rec = P.rec[i];
+    r.inf = (fl & (EV_FIRE | EV_CAND | EV_DEATH)) ? P.daily_infectivity[i] : 0.f;
     r.rk = (fl & (EV_CAND | EV_RI | EV_SIA | EV_DEATH)) ? P.acq_risk_multiplier[i] : 0.f;
     return r;
 }
@@ -223,142 +245,130 @@ LPK_HD int8_t hot_pick_strain(const lpk_tick_args &A, int64_t i, int nd) {  // m
 
 // One agent with something to do in the pass of tick t, in the reference's order: pending exposure trial of t-1
 // (model.py:1010-1149 replacement) -> death (1767-1781) -> disease-state step (419-452) -> RI draws (1825-1854) -> campaign
-// draws (2030-2059).  `fl` says why the sweep sent it; every condition is re-checked against the full-width columns.
+// draws (2030-2059).  `fl` says why the sweep sent it; every condition is re-checked against the agent's record.
 LPK_HD HotDelta hot_event(const lpk_people &P, const lpk_tick_args &A, int64_t i, int nd, uint32_t fl, const HotPre &pre) {
     HotDelta d;
     d.nd = nd; d.st = 0; d.dE = d.dI = d.dR = 0; d.hit = d.vx = d.gate = d.died = 0; d.dbeta = 0; d.efx = 0; d.hbin = -1;
     const int tick = A.tick;
     const uint8_t t8 = (uint8_t)tick;
-    const int8_t s_in = pre.state;
-    int8_t s = s_in, st = 0;
-    bool st_known = false, hot_set = false, fresh = false;
+    HotRecU x;
+    x.u = pre.rec;
+    HotRec &r = x.r;
+    bool hot_set = false;
     uint8_t hot_new = 0;
-    uint8_t etd = (uint8_t)pre.et;  // deadline of an exposed agent; the pre-drawn duration of a susceptible
 
     // ---- 1. exposure trial of tick t-1 (agents born today were not there)
-    if ((fl & EV_CAND) && s == 0 && (A.flags & LPK_F_PENDING)) {
+    if ((fl & EV_CAND) && r.state == 0 && (A.flags & LPK_F_PENDING)) {
         const bool born_today = (A.flags & LPK_F_DEATHS) && P.date_of_birth && P.date_of_birth[i] == tick;
         if (!born_today && hot_exact_trial(A, i, nd, pre.rk)) {
-            s = 1;
-            st = hot_pick_strain(A, i, nd);
-            st_known = true;
-            P.strain[i] = st;
+            r.state = 1;
+            r.strain = hot_pick_strain(A, i, nd);
             d.hit = 1; d.dE = 1;
             d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk);
-            etd = (uint8_t)(etd + t8);  // the first step that tests the exposure timer is today's
-            fresh = true;
+            r.et = (int8_t)(uint8_t)((uint8_t)r.et + t8);  // deadline: the first step that tests the exposure timer is today's
         }
     }
-    // ---- 2. death
-    if ((fl & EV_DEATH) && s >= 0 && P.date_of_death[i] <= tick) {
+    // ---- 2. death: the record goes back to countdown values as of today's (skipped) step
+    if ((fl & EV_DEATH) && r.state >= 0 && P.date_of_death[i] <= tick) {
         d.died = 1;
-        if (s == 0) { d.died |= 8; d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk); }
-        if (s == 1) {
-            if (!st_known) st = P.strain[i];
+        if (r.state == 0) { d.died |= 8; d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk); }
+        if (r.state == 1) {
             d.dE -= 1;
-            if (!fresh) P.exposure_timer[i] = (int8_t)(uint8_t)(etd - t8);
-        } else if (s == 2) {
-            st = P.strain[i];
+            r.et = (int8_t)(uint8_t)((uint8_t)r.et - t8);
+        } else if (r.state == 2) {
             d.dI -= 1;
-            d.dbeta -= to_fx((double)pre.inf * A.strain_r0_scalars[st]);
-            P.infection_timer[i] = (int8_t)(uint8_t)((uint8_t)pre.it - t8);
-            if (st == 0) P.paralysis_timer[i] = (int8_t)(uint8_t)((uint8_t)P.paralysis_timer[i] - t8);
-        } else if (s == 3) {
+            d.dbeta -= to_fx((double)pre.inf * A.strain_r0_scalars[r.strain]);
+            r.it = (int8_t)(uint8_t)((uint8_t)r.it - t8);
+            if (r.strain == 0) r.pt = (int8_t)(uint8_t)((uint8_t)r.pt - t8);
+        } else if (r.state == 3) {
             d.dR -= 1;
         }
-        d.st = st;
-        if (P.potentially_paralyzed[i] == 1) d.died |= 2;
-        if (P.paralyzed[i] == 1) d.died |= 4;
+        d.st = r.strain;
+        if (r.pq == 1) d.died |= 2;
+        if (r.par == 1) d.died |= 4;
         if (A.ri_lazy_k && P.ri_timer && P.chronically_missed[i] != 1)  // the dead stop counting down: pay the debt so far
             P.ri_timer[i] = ri_owed(P.ri_timer[i], A.ri_lazy_k, A.ri_step);
-        P.disease_state[i] = -1;
+        r.state = -1;
+        P.rec[i] = x.u;
         P.hot[i] = HOT_DEAD;
         return d;
     }
     // ---- 3. disease-state step of tick t
     bool turned = false;
-    if (s == 1) {
-        const int8_t etv = (int8_t)(uint8_t)(etd - t8);  // the value today's step tests
+    if (r.state == 1) {
+        const int8_t etv = (int8_t)(uint8_t)((uint8_t)r.et - t8);  // the value today's step tests
         if (etv <= 0) {
-            P.exposure_timer[i] = (int8_t)(etv - 1);
-            s = 2; turned = true;
+            r.et = (int8_t)(etv - 1);
+            r.state = 2; turned = true;
         } else {
-            if (fresh) P.exposure_timer[i] = (int8_t)etd;
             hot_new = (uint8_t)(HOT_E | hot_due(tick, etv)); hot_set = true;
         }
     }
-    if (s == 2) {
-        if (!st_known) { st = P.strain[i]; st_known = true; }
-        const uint8_t itd = turned ? (uint8_t)((uint8_t)pre.it + t8) : (uint8_t)pre.it;
-        const int8_t itv = (int8_t)(uint8_t)(itd - t8);
-        const long long fxv = to_fx((double)pre.inf * A.strain_r0_scalars[st]);
+    if (r.state == 2) {
+        if (turned) r.it = (int8_t)(uint8_t)((uint8_t)r.it + t8);
+        const int8_t itv = (int8_t)(uint8_t)((uint8_t)r.it - t8);
+        const long long fxv = to_fx((double)pre.inf * A.strain_r0_scalars[r.strain]);
         if (turned) { d.dE -= 1; d.dI += 1; d.dbeta += fxv; }
         const bool recover = itv <= 0;
-        const bool wild = st == 0;
-        uint8_t ptd = 0;
-        int8_t ptv = 0, pq = 0;
+        const bool wild = r.strain == 0;
+        int8_t ptv = 0;
         if (wild) {  // paralysis part, model.py:432-452
-            const uint8_t ptc = (uint8_t)P.paralysis_timer[i];
-            ptd = turned ? (uint8_t)(ptc + t8) : ptc;
-            ptv = (int8_t)(uint8_t)(ptd - t8);
-            pq = P.potentially_paralyzed[i];
-            if (ptv <= 0 && pq == -1) {
-                if (P.ipv_protected[i] == 0) {
-                    pq = 1;
+            if (turned) r.pt = (int8_t)(uint8_t)((uint8_t)r.pt + t8);
+            ptv = (int8_t)(uint8_t)((uint8_t)r.pt - t8);
+            if (ptv <= 0 && r.pq == -1) {
+                if (r.ipv == 0) {
+                    r.pq = 1;
                     d.gate = 1;
-                    uint32_t x[4];
-                    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_PARALYSIS, x);
-                    if (u53(x[0], x[1]) < (double)A.p_paralysis) { P.paralyzed[i] = 1; d.gate = 3; }
+                    uint32_t y[4];
+                    philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_PARALYSIS, y);
+                    if (u53(y[0], y[1]) < (double)A.p_paralysis) { r.par = 1; d.gate = 3; }
                 } else {
-                    pq = 0;
+                    r.pq = 0;
                 }
-                P.potentially_paralyzed[i] = pq;
             }
         }
         if (recover) {
-            P.infection_timer[i] = (int8_t)(itv - 1);
-            if (wild) P.paralysis_timer[i] = (int8_t)(ptv - 1);
+            r.it = (int8_t)(itv - 1);
+            if (wild) r.pt = (int8_t)(ptv - 1);
             d.dI -= 1; d.dbeta -= fxv; d.dR += 1;
-            s = 3;
+            r.state = 3;
             hot_new = HOT_R; hot_set = true;
         } else {
-            if (turned) {
-                P.infection_timer[i] = (int8_t)itd;
-                if (wild) P.paralysis_timer[i] = (int8_t)ptd;
-            }
             int next = itv;
-            if (wild && pq == -1 && ptv < next) next = ptv;  // the gate is still closed: ptv > 0
+            if (wild && r.pq == -1 && ptv < next) next = ptv;  // the gate is still closed: ptv > 0
             hot_new = (uint8_t)(HOT_I | hot_due(tick, next)); hot_set = true;
         }
     }
-    // ---- 4. vaccine draws, after the agent's own disease-state step (the reference's run order)
-    if ((fl & EV_RI) && (A.flags & LPK_F_RI) && s >= 0) {
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_RI, x);
-        if (u53(x[0], x[1]) < A.vx_prob_ri[nd]) {
+    d.st = r.strain;
+    // ---- 4. vaccine draws, after the agent's own disease-state step (the reference's run order); the dead take none
+    int8_t vstrain = -1;
+    if ((fl & EV_RI) && (A.flags & LPK_F_RI) && r.state >= 0) {
+        uint32_t y[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_RI, y);
+        if (u53(y[0], y[1]) < A.vx_prob_ri[nd]) {
             d.vx |= 1;
-            if (s == 0) { s = 1; st = (int8_t)A.ri_strain; d.vx |= 2; }
+            if (r.state == 0) { r.state = 1; vstrain = (int8_t)A.ri_strain; d.vx |= 2; }
         }
-        if (u53(x[2], x[3]) < A.vx_prob_ipv[nd]) { d.vx |= 4; P.ipv_protected[i] = 1; }
+        if (u53(y[2], y[3]) < A.vx_prob_ipv[nd]) { d.vx |= 4; r.ipv = 1; }
     }
-    if ((fl & EV_SIA) && (A.flags & LPK_F_SIA) && s >= 0) {
-        uint32_t x[4];
-        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), x);
-        const double u = u53(x[0], x[1]), pv = (double)A.vx_prob_sia[nd];
+    if ((fl & EV_SIA) && (A.flags & LPK_F_SIA) && r.state >= 0) {
+        uint32_t y[4];
+        philox_agent(A.seed, (uint64_t)i + A.id_base, (uint32_t)tick, LPK_STAGE_SIA | (A.sia_event_idx << 8), y);
+        const double u = u53(y[0], y[1]), pv = (double)A.vx_prob_sia[nd];
         if (u < pv) {
             d.vx |= 8;
-            if (s == 0 && u < pv * A.sia_vx_eff) { s = 1; st = (int8_t)A.sia_strain; d.vx |= 16; }
+            if (r.state == 0 && u < pv * A.sia_vx_eff) { r.state = 1; vstrain = (int8_t)A.sia_strain; d.vx |= 16; }
         }
     }
     if (d.vx & 18) {  // left S through a vaccine: exposed from tomorrow's step on
-        P.strain[i] = st;
+        r.strain = vstrain;
+        d.st = vstrain;
         d.efx = risk_fx(pre.rk); d.hbin = risk_bin(pre.rk);
-        const int8_t et0 = pre.et;
-        P.exposure_timer[i] = (int8_t)(uint8_t)((uint8_t)et0 + t8 + 1u);
+        const int8_t et0 = r.et;
+        r.et = (int8_t)(uint8_t)((uint8_t)et0 + t8 + 1u);
         hot_new = (uint8_t)(HOT_E | hot_due(tick, 1 + (et0 < 0 ? 0 : et0))); hot_set = true;
     }
-    d.st = st;
-    if (s != s_in) P.disease_state[i] = s;
+    if (x.u != pre.rec) P.rec[i] = x.u;
     if (hot_set) P.hot[i] = hot_new;
     return d;
 }

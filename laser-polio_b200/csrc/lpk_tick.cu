@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     Q.count = 0;
     Q.loaded = false;
     Q.pend_e = make_uint2(0u, 0u);
-    Q.pend.state = 0; Q.pend.et = 0; Q.pend.it = 0; Q.pend.rk = 0.f; Q.pend.inf = 0.f;
+    Q.pend.rec = 0ull; Q.pend.rk = 0.f; Q.pend.inf = 0.f;
     Q.acc = reinterpret_cast<WarpAcc *>(smem + L::kOffAcc) + warp;
     if (lane == 0) {
         Q.acc->node = -1;
@@ -460,21 +460,26 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     const int sia_lo = kSIA ? A.sia_min_age : 0;
     const uint32_t sia_span = kSIA ? (uint32_t)(A.sia_max_age - A.sia_min_age) : 0u;
 
+    // per-unit metadata, loaded a unit ahead like the agenda bytes: the unit's 4 tile nodes (lanes 0-3), on vital-dynamics
+    // ticks its 8 earliest death dates and on RI ticks its 8 largest RI timers (lanes 0-7)
+    int tnv = -1, mdv = INT_MAX, rmv = INT_MIN;
+    auto fetch_meta = [&](uint32_t u) {
+        const uint32_t g0 = u << LPK_UNIT_LOG;
+        tnv = -1; mdv = INT_MAX; rmv = INT_MIN;
+        if (P.tile_node && lane < 4 && g0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(g0 >> 1) + lane]);
+        if (kDeaths && lane < LPK_UNIT_PAIRS && g0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[g0 + lane];
+        if (kRI && lane < LPK_UNIT_PAIRS && g0 + (uint32_t)lane < total_pairs) rmv = P.pair_ri_max[g0 + lane];
+    };
     uint32_t u_cur = next_unit();
-    if (u_cur != kNoUnit) fetch(u_cur, 0);
+    if (u_cur != kNoUnit) { fetch(u_cur, 0); fetch_meta(u_cur); }
     uint32_t par0 = 0u, par1 = 0u;  // phase parity of the two buffers
     int buf = 0;
 #pragma unroll 1
     while (u_cur != kNoUnit) {
         const uint32_t u_nxt = next_unit();
-        if (u_nxt != kNoUnit) fetch(u_nxt, buf ^ 1);
-        // per-unit metadata while the copy lands: the unit's 4 tile nodes (lanes 0-3) and, on vital-dynamics ticks, its 8
-        // earliest death dates (lanes 0-7)
         const uint32_t gp0 = u_cur << LPK_UNIT_LOG;
-        int tnv = -1, mdv = INT_MAX, rmv = INT_MIN;
-        if (P.tile_node && lane < 4 && gp0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(gp0 >> 1) + lane]);
-        if (kDeaths && lane < LPK_UNIT_PAIRS && gp0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[gp0 + lane];
-        if (kRI && lane < LPK_UNIT_PAIRS && gp0 + (uint32_t)lane < total_pairs) rmv = P.pair_ri_max[gp0 + lane];
+        const int tnv_cur = tnv, mdv_cur = mdv, rmv_cur = rmv;
+        if (u_nxt != kNoUnit) { fetch(u_nxt, buf ^ 1); fetch_meta(u_nxt); }
         mbar_wait(&bars[buf], buf ? par1 : par0);
         if (buf) par1 ^= 1u; else par0 ^= 1u;
         const uint32_t *src = stage + buf * (LPK_UNIT_AGENTS / 4);
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         for (int tp = 0; tp < LPK_UNIT_PAIRS / 2; ++tp) {  // one TILE (two pairs, 16 agents per lane) per iteration: the two
             const uint32_t gp = gp0 + 2u * (uint32_t)tp;    // Philox blocks are independent chains and interleave
             if (gp >= total_pairs) break;
-            const int tn = __shfl_sync(LPK_FULL, tnv, tp);
+            const int tn = __shfl_sync(LPK_FULL, tnv_cur, tp);
             const uint32_t hA0 = src[tp * 128 + lane], hB0 = src[tp * 128 + 32 + lane];
             const uint32_t hA1 = src[tp * 128 + 64 + lane], hB1 = src[tp * 128 + 96 + lane];
             if (tn < 0) {
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                     const int64_t bA = bA0 + 256 * j, bB = bA + 128;
                     uint32_t dmA = 0u, dmB = 0u, eA = 0u, eB = 0u, sA = 0u, sB = 0u;
                     if (kDeaths) {
-                        const int md = __shfl_sync(LPK_FULL, mdv, 2 * tp + j);
+                        const int md = __shfl_sync(LPK_FULL, mdv_cur, 2 * tp + j);
                         if (md <= tick) {  // warp-uniform: somebody in this pair can die today
                             const int4 dA = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bA));
                             const int4 dB = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bB));
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
                         }
                     }
                     // RI: only pairs in which somebody's timer has not run out for good (stored >= debt) can hold an eligible agent
-                    if (kRI && __shfl_sync(LPK_FULL, rmv, 2 * tp + j) >= ri_debt) {  // (the dead are turned away by the handler)
+                    if (kRI && __shfl_sync(LPK_FULL, rmv_cur, 2 * tp + j) >= ri_debt) {  // (the dead are turned away by the handler)
                         eA = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bA) ^ ri_today) & ~dmA;
                         eB = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bB) ^ ri_today) & ~dmB;
                     }
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         const bool valid = lane < Q.count;
         uint2 e = make_uint2(0u, 0u);
         HotPre last;
-        last.state = 0; last.et = 0; last.it = 0; last.rk = 0.f; last.inf = 0.f;
+        last.rec = 0ull; last.rk = 0.f; last.inf = 0.f;
         if (valid) { e = Q.q[(Q.head + lane) & (QCAP - 1)]; last = hot_preload(P, (int64_t)e.x, e.y); }
         active_process(pp, e, last, valid, Q.acc, lane);
     }
@@ -606,6 +611,7 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     REQUIRE(P.capacity > 0 && P.capacity < (1ll << 32) && A.counts, "tick_pass counts (tables hold < 2^32 slots)");
     REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer && P.potentially_paralyzed &&
                 P.paralyzed && P.ipv_protected && P.node_id && P.acq_risk_multiplier && P.daily_infectivity, "tick_pass agent columns");
+    REQUIRE(P.rec && ALIGNED(P.rec, 8), "tick_pass event records (lpk_hot_build fills them)");
     REQUIRE(P.hot && ALIGNED(P.hot, 16), "tick_pass agenda bytes (lpk_hot_build fills them; 16-byte aligned, padded to 2048 agents)");
     REQUIRE((A.flags & LPK_F_STAGES) != 0, "tick_pass always runs the stages of its tick (LPK_F_STAGES)");
     REQUIRE((A.id_base & 255) == 0, "tick_pass id_base must be a multiple of 256");
@@ -717,8 +723,8 @@ static inline int64_t hot_padded(int64_t capacity) { return (capacity + LPK_UNIT
 extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_step, int32_t *status, void *stream) {
     REQUIRE(people, "hot_build null struct");
     const lpk_people &P = *people;
-    REQUIRE(P.hot && P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer &&
-                P.potentially_paralyzed && P.acq_risk_multiplier, "hot_build columns");
+    REQUIRE(P.hot && P.rec && P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer &&
+                P.potentially_paralyzed && P.paralyzed && P.ipv_protected && P.acq_risk_multiplier, "hot_build columns");
     REQUIRE(n_slots >= 0 && n_slots <= P.capacity, "hot_build n_slots");
     cudaStream_t st = as_stream(stream);
     const int64_t padded = hot_padded(P.capacity);
@@ -738,7 +744,8 @@ extern "C" int lpk_hot_build(const lpk_people *people, int64_t n_slots, int32_t 
 extern "C" int lpk_hot_settle(const lpk_people *people, int64_t n_slots, int32_t tick_next, int32_t ri_lazy_k, int32_t ri_step, void *stream) {
     REQUIRE(people, "hot_settle null struct");
     const lpk_people &P = *people;
-    REQUIRE(P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer, "hot_settle columns");
+    REQUIRE(P.rec && P.disease_state && P.strain && P.exposure_timer && P.infection_timer && P.paralysis_timer &&
+                P.potentially_paralyzed && P.paralyzed && P.ipv_protected, "hot_settle columns");
     REQUIRE(n_slots >= 0 && n_slots <= P.capacity, "hot_settle n_slots");
     if (n_slots == 0) return LPK_OK;
     REQUIRE(ri_lazy_k == 0 || (P.ri_timer && P.chronically_missed && ri_step > 0), "hot_settle RI countdown");

@@ -108,7 +108,12 @@ __global__ void k_births_fill(lpk_births_args a) {
             const uint8_t j = ri_tick_index(a.ri_timer[slot], a.ri_lazy_k, a.ri_step, a.tick - 1);
             a.ri_k[slot] = (j && a.ri_lazy_k + (int)j <= 254) ? (uint8_t)(a.ri_lazy_k + j) : (uint8_t)0;
         }
-        if (a.hot) {  // fused path: the newborn's agenda byte (a susceptible) and its pair's earliest death date
+        if (a.hot) {  // fused path: the newborn's event record, agenda byte (a susceptible) and its pair's earliest death date
+            HotRecU x;
+            x.r.state = 0; x.r.strain = a.strain[slot]; x.r.et = a.exposure_timer[slot]; x.r.it = a.infection_timer[slot];
+            x.r.pt = a.paralysis_timer[slot]; x.r.pq = a.potentially_paralyzed[slot]; x.r.par = a.paralyzed[slot];
+            x.r.ipv = a.ipv_protected[slot];
+            a.rec[slot] = x.u;
             bool over = false;
             a.hot[slot] = (uint8_t)(HOT_S | risk_code(a.acq_risk_multiplier[slot], a.risk_e0, &over));
             if (over) *a.status = 2;
@@ -149,6 +154,8 @@ extern "C" int lpk_vd_births(const lpk_births_args *args, void *stream) {
     REQUIRE(a.birth_rate && a.pop_prev && a.births_row && a.counts && a.cum_deaths && a.node_offsets_ws && a.cohort_ws && a.status,
             "vd_births node-level pointers");
     REQUIRE(a.disease_state && a.node_id && a.date_of_birth && a.date_of_death, "vd_births agent columns");
+    REQUIRE(!a.hot || (a.rec && a.acq_risk_multiplier && a.strain && a.exposure_timer && a.infection_timer && a.paralysis_timer &&
+                       a.potentially_paralyzed && a.paralyzed && a.ipv_protected), "vd_births fused-path companions");
     cudaStream_t st = as_stream(stream);
     k_births_count<<<1, 1024, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError(), "lpk_vd_births count");

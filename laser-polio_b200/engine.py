@@ -87,6 +87,7 @@ class FusedEngine:
         # 256-slot pair, the pass's work counter; the exponent bias of the 6-bit risk code comes from the largest risk
         padded = int(_lpk.lib().lpk_hot_padded(cap))
         self.hot = torch.empty(padded, dtype=torch.uint8, device=d)
+        self.rec = torch.empty(cap, dtype=torch.int64, device=d)  # per-agent event records (lpk_people.rec)
         self.pair_min_dod = torch.empty(padded // 256, dtype=torch.int32, device=d) if "date_of_death" in c else None
         self.pair_ri_max = torch.empty(padded // 256, dtype=torch.int32, device=d) if "ri_timer" in c else None
         self.ri_k = torch.zeros(padded, dtype=torch.uint8, device=d) if "ri_timer" in c else None
@@ -107,6 +108,7 @@ class FusedEngine:
         P.tile_node = dp(self.tile_node)
         P.capacity = cap
         P.hot, P.pair_min_dod, P.pair_ri_max, P.ri_k = dp(self.hot), dp(self.pair_min_dod), dp(self.pair_ri_max), dp(self.ri_k)
+        P.rec = dp(self.rec)
         P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
         if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
@@ -230,7 +232,7 @@ class FusedEngine:
             if pars.cbr is None:
                 raise ValueError("VitalDynamics_ABM needs pars.cbr")
             b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist),
-                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step, self.ri_k))
+                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step, self.ri_k, self.rec))
             K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
         A = TickArgs()
         A.tick, A.n_nodes, A.n_strains = t, n, ns

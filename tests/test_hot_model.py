@@ -52,6 +52,7 @@ class Table:
         self.pair_min = np.zeros(padded // 256, np.int32)
         self.pair_ri = np.zeros(padded // 256, np.int32)
         self.ri_kcol = np.zeros(padded, np.uint8)
+        self.rec = np.zeros(cap, np.uint64)
         self.ri_k = 0
         tiles = (cap + 511) // 512
         nid = cols["node_id"]
@@ -67,7 +68,7 @@ class Table:
             setattr(P, name, _ptr(cols[name]))
         P.tile_node, P.capacity, P.hot, P.pair_min_dod = _ptr(self.tile_node), cap, _ptr(self.hot), _ptr(self.pair_min)
         P.risk_e0 = hm.hm_risk_e0(C.c_float(float(cols["acq_risk_multiplier"].max())))
-        P.pair_ri_max, P.ri_k = _ptr(self.pair_ri), _ptr(self.ri_kcol)
+        P.pair_ri_max, P.ri_k, P.rec = _ptr(self.pair_ri), _ptr(self.ri_kcol), _ptr(self.rec)
         self.P = P
         i32 = lambda *s: np.zeros(s, np.int32)  # noqa: E731
         self.E_cur, self.I_cur, self.R_cur = i32(nodes, ns), i32(nodes, ns), i32(nodes)
@@ -199,8 +200,8 @@ def run_case(hm, orc, n=60_000, nodes=7, ticks=40, seed=11, p_paralysis=0.3, big
         assert np.array_equal(T.beta, bfx_o), f"tick {t}: beta_fx"
         assert np.array_equal(T.E_cur, census_o[4]) and np.array_equal(T.I_cur, census_o[5]) and np.array_equal(T.R_cur, census_o[3]), \
             f"tick {t}: E / I / R census"
-        # disease_state is kept canonical by the pass at all times
-        assert np.array_equal(mod["disease_state"], can["disease_state"]), f"tick {t}: disease_state"
+        # the records' state byte follows the canonical disease_state tick by tick
+        assert np.array_equal((T.rec[:n] & 0xFF).astype(np.uint8).view(np.int8), can["disease_state"][:n]), f"tick {t}: disease_state"
 
         # ---------------- node math (same for both) and the oracle's exposure of tick t
         q, cdf, _, _ = orc.tx_node_math_device(bfx_o, efx_o, hist_o, W, 1.05, r0s, pop, 0.2, 2.0, seed, t)
