@@ -242,6 +242,104 @@ __device__ __forceinline__ int q_push_pair(uint2 *q, uint32_t *tail, uint32_t id
     return cnt;
 }
 
+// the same for a pair whose agents live in several nodes: nA / nB = the quads' four int16 node ids
+__device__ __forceinline__ int q_push_pair_nodes(uint2 *q, uint32_t *tail, uint32_t idxA, uint2 nA, uint2 nB, uint32_t FA, uint32_t FB) {
+    uint32_t m = (zero_bytes(FA) ^ 0x01010101u) | ((zero_bytes(FB) ^ 0x01010101u) << 4);
+    const int cnt = __popc(m);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        const bool rowB = (bit & 4) != 0;
+        const int k = bit >> 3;
+        const uint32_t f = ((rowB ? FB : FA) >> (bit & 24)) & 0x1Fu;
+        const uint2 nn = rowB ? nB : nA;
+        const uint32_t nd = (((k & 2) ? nn.y : nn.x) >> (16 * (k & 1))) & 0xFFFFu;
+        const uint32_t pos = atomicAdd(tail, 1u) & (QCAP - 1);
+        q[pos] = make_uint2(idxA + (uint32_t)k + (rowB ? 128u : 0u), nd | (f << 16));
+    }
+    return cnt;
+}
+// pre-test with a scale per agent (agents of different nodes in one quad)
+__device__ __forceinline__ uint32_t hot_pretest_each(uint32_t h, uint32_t xa, uint32_t xb, float t0, float t1, float t2, float t3) {
+    const uint32_t KM = 0x1FFFFFFFu, k23 = 0x4B000000u;
+    const float c = 8388609.0f;
+    const float d0 = __uint_as_float((h << 21) & KM), d1 = __uint_as_float((h << 13) & KM), d2 = __uint_as_float((h << 5) & KM),
+                d3 = __uint_as_float(h >> 3);
+    const float u0 = __uint_as_float(__byte_perm(xa, k23, 0x7610)), u1 = __uint_as_float(__byte_perm(xa, k23, 0x7632));
+    const float u2 = __uint_as_float(__byte_perm(xb, k23, 0x7610)), u3 = __uint_as_float(__byte_perm(xb, k23, 0x7632));
+    return ((u0 < fmaf(d0, t0, c)) ? 1u : 0u) | ((u1 < fmaf(d1, t1, c)) ? 0x100u : 0u) | ((u2 < fmaf(d2, t2, c)) ? 0x10000u : 0u) |
+           ((u3 < fmaf(d3, t3, c)) ? 0x1000000u : 0u);
+}
+
+// ------------------------------------------------------------------ mixed pair: 256 live slots in SEVERAL nodes (appended
+// newborn cohorts are node-major runs of a few hundred agents; node boundaries of the initial population).  Same byte-lane
+// sweep as a node-uniform pair, with the node id read per agent (2 B) and the exposure scale gathered per agent (the ids
+// come in runs, so the gathers hit one or two cache lines per warp).  tau is clamped where every susceptible passes
+// anyway, which also covers tau = "everybody" without a special case.  Round 1 sent these pairs through the one-agent-
+// at-a-time path: ~50 us of a warp's time per 2048 agents, 26 % of the table after seven years of births.
+template <bool kDeaths, bool kRI, bool kSIA>
+__device__ __noinline__ int mixed_pair(const PassParams &pp, uint2 *q, uint32_t *q_tail, uint32_t gp, uint32_t hA, uint32_t hB, int md, int rm,
+                                       uint64_t ctr, int lane) {
+    const lpk_people &P = pp.P;
+    const lpk_tick_args &A = pp.A;
+    const int tick = A.tick, e0 = P.risk_e0;
+    const int64_t bA = (int64_t)gp * 256 + lane * 4, bB = bA + 128;
+    const uint2 nA = __ldg(reinterpret_cast<const uint2 *>(P.node_id + bA)), nB = __ldg(reinterpret_cast<const uint2 *>(P.node_id + bB));
+    uint32_t cA = 0u, cB = 0u;
+    if (A.flags & LPK_F_PENDING) {
+        const float clampv = ldexpf(1.0f, e0 + 5), scale = ldexpf(1.0f, 95 - e0);
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint2 nn = (k & 4) ? nB : nA;
+            const int nd = (int)(int16_t)((((k & 2) ? nn.y : nn.x) >> (16 * (k & 1))) & 0xFFFFu);
+            const float tau = nd >= 0 ? __ldg(&A.q_prev[nd]) : 0.f;
+            t[k] = fminf(fmaxf(tau, 0.f), clampv) * scale;
+        }
+        uint32_t x[4];
+        philox_sweep(pp, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(tick - 1), LPK_STAGE_EXPOSE, x);
+        cA = hot_pretest_each(hA, x[0], x[1], t[0], t[1], t[2], t[3]);
+        cB = hot_pretest_each(hB, x[2], x[3], t[4], t[5], t[6], t[7]);
+    }
+    const uint32_t today = hot_today(tick);
+    const uint32_t vA = hot_due_word(hA, today), vB = hot_due_word(hB, today);
+    uint32_t dmA = 0u, dmB = 0u, eA = 0u, eB = 0u, sA = 0u, sB = 0u;
+    if (kDeaths && md <= tick) {
+        const int4 dA = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bA));
+        const int4 dB = __ldg(reinterpret_cast<const int4 *>(P.date_of_death + bB));
+        const uint32_t aA = hot_mask_alive(hA), aB = hot_mask_alive(hB);
+        dmA = death_mask(dA, tick) & aA;
+        dmB = death_mask(dB, tick) & aB;
+        const int left = __reduce_min_sync(LPK_FULL, min(min_dod_left(dA, aA & ~dmA), min_dod_left(dB, aB & ~dmB)));
+        if (lane == 0) P.pair_min_dod[gp] = left;
+    }
+    if (kRI && rm >= A.ri_lazy_k * A.ri_step) {
+        const uint32_t ri_today = ((uint32_t)(A.ri_lazy_k + 1) & 0xFFu) * 0x01010101u;
+        eA = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bA) ^ ri_today) & ~dmA;
+        eB = zero_bytes(*reinterpret_cast<const uint32_t *>(P.ri_k + bB) ^ ri_today) & ~dmB;
+    }
+    if (kSIA) {
+        const uint32_t span = (uint32_t)(A.sia_max_age - A.sia_min_age);
+        uint32_t tgA = 0u, tgB = 0u;  // agents whose node is targeted by today's campaign
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int na = (int)(int16_t)((((k & 2) ? nA.y : nA.x) >> (16 * (k & 1))) & 0xFFFFu);
+            const int nb = (int)(int16_t)((((k & 2) ? nB.y : nB.x) >> (16 * (k & 1))) & 0xFFFFu);
+            if (na >= 0 && __ldg(&A.sia_targeted[na]) != 0) tgA |= 1u << (8 * k);
+            if (nb >= 0 && __ldg(&A.sia_targeted[nb]) != 0) tgB |= 1u << (8 * k);
+        }
+        if (tgA | tgB) {
+            const uint32_t mA = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bA);
+            const uint32_t mB = *reinterpret_cast<const uint32_t *>(P.chronically_missed + bB);
+            sA = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bA)), tick, A.sia_min_age, span) & hot_mask_alive(hA) & ~dmA & ~mA & tgA;
+            sB = sia_age_mask(__ldg(reinterpret_cast<const int4 *>(P.date_of_birth + bB)), tick, A.sia_min_age, span) & hot_mask_alive(hB) & ~dmB & ~mB & tgB;
+        }
+    }
+    const uint32_t FA = (cA & hot_mask_S(hA)) | (zero_bytes(vA) << 1) | (dmA << 2) | (eA << 3) | (sA << 4);
+    const uint32_t FB = (cB & hot_mask_S(hB)) | (zero_bytes(vB) << 1) | (dmB << 2) | (eB << 3) | (sB << 4);
+    return (FA | FB) ? q_push_pair_nodes(q, q_tail, (uint32_t)bA, nA, nB, FA, FB) : 0;
+}
+
 // ------------------------------------------------------------------ general pair (out of line): 256 agents that are not
 // all in one node (node boundaries, appended cohorts, the table's tail).  One agent at a time; every agent with
 // something to do goes to the ring with its own node.  h: the lane's agenda words of the two rows.
@@ -378,6 +476,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     const int tick = A.tick, e0 = P.risk_e0;
     const uint64_t ctr_base = ((A.id_base >> 8) << 5) + (uint64_t)lane;  // Philox counter of pair 0 for this lane
     const uint32_t total_pairs = (uint32_t)((n + 255) >> 8);
+    const uint32_t full_pairs = (uint32_t)(n >> 8);  // pairs whose 256 slots are all in use
     const uint32_t n_units = (total_pairs + LPK_UNIT_PAIRS - 1) >> LPK_UNIT_LOG;
     const uint32_t today = hot_today(tick);
     const float tau_all = ldexpf(1.0f, e0);  // from here on every susceptible passes the pre-test anyway (bound of code 0 x tau >= 1)
@@ -490,11 +589,17 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
             const int tn = __shfl_sync(LPK_FULL, tnv_cur, tp);
             const uint32_t hA0 = src[tp * 128 + lane], hB0 = src[tp * 128 + 32 + lane];
             const uint32_t hA1 = src[tp * 128 + 64 + lane], hB1 = src[tp * 128 + 96 + lane];
-            if (tn < 0) {
-                int mine = general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp, n, hA0, hB0, lane);
-                q_commit(pp, Q, mine, lane);
-                if (gp + 1u < total_pairs) {
-                    mine = general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp + 1, n, hA1, hB1, lane);
+            if (tn < 0) {  // several nodes in the tile: the mixed sweep for pairs of 256 live slots, one agent at a time at the tail
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    if (gp + (uint32_t)j >= total_pairs) break;
+                    const uint32_t hA = j ? hA1 : hA0, hB = j ? hB1 : hB0;
+                    int mine;
+                    if (gp + (uint32_t)j < full_pairs)
+                        mine = mixed_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, gp + (uint32_t)j, hA, hB, __shfl_sync(LPK_FULL, mdv_cur, 2 * tp + j),
+                                                              __shfl_sync(LPK_FULL, rmv_cur, 2 * tp + j), ctr_base + ((uint64_t)(gp + (uint32_t)j) << 5), lane);
+                    else
+                        mine = general_pair<kDeaths, kRI, kSIA>(pp, Q.q, Q.tail, (int64_t)gp + j, n, hA, hB, lane);
                     q_commit(pp, Q, mine, lane);
                 }
                 continue;
