@@ -1,54 +1,77 @@
 #!/usr/bin/env python
-"""bench.py -- agent-days/sec of the per-tick agent update on the Nigeria-774 shape (BASELINE.json).
+"""bench.py -- agent-days/sec of the per-tick agent update on the shapes BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--agents A] [--nodes M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--config auto|zamfara|nigeria|west_africa|africa] [--scaling auto|shard|weak] [--agents A] [--nodes M]
 
-A "step" is one simulated day over the whole population: every component's step() in the
-reference's run order (deaths/births every 7th tick, disease state, RI every 14th, SIA on campaign
-days, transmission) followed by the census, exactly what ``SEIR_ABM.run()`` does per tick.
+A "step" is one simulated day over the whole population: every component's step() in the reference's run order
+(deaths / births every 7th tick, disease state, RI every 14th, SIA on campaign days, transmission) followed by the
+census, exactly what ``SEIR_ABM.run()`` does per tick.
+
+Workload (``config.workload`` names it on every line):
+  --config auto (default)  the population BASELINE.json's metric is quoted on -- Nigeria, 774 nodes, 2.2e8 agents -- at every GPU
+                           count: ONE population sharded by node over the N ranks (contiguous node blocks balanced by agents),
+                           i.e. strong scaling
+  --config <name>          zamfara | nigeria | west_africa | africa: that population on any N
+  --scaling weak           N copies of the shape's per-GPU load instead (every rank holds the config's agents and nodes,
+                           network over all N x nodes): the round-1 behaviour, kept as a second line
+The only per-tick exchange is the nodes x strains infectivity tally.
 
 * value    whole-job agent-days/s with the agent table already resident in HBM (CUDA events, max over ranks)
-* e2e      the same K ticks through ``SEIR_ABM`` from HOST (pinned) columns: H2D of every agent column
-           and results array, the ticks, and D2H of everything back inside the timed region
-* roofline the dominant kernel's algorithmic bytes / its mean CUDA-event time inside the timed region
-* cpu_baseline  the CPU oracle (C + OpenMP restatement of the reference's numba kernels, "port") timed on
-           this box's host cores on a bounded sample (10 M agents) of the same workload
-
-N > 1 (torchrun, one rank per GPU): the population is sharded by node (contiguous node blocks, weak scaling:
-every rank holds --agents agents); the only per-tick exchange is the nodes x strains infectivity tally.
+* e2e      the same K ticks through ``SEIR_ABM`` from HOST (pinned) columns: H2D of every agent column and results array,
+           the ticks, and D2H of everything the device can have changed, inside the timed region
+* roofline the dominant kernel's algorithmic bytes / its mean CUDA-event time inside the timed region; ``traffic`` = DRAM
+           bytes per launch measured by ncu in this round (profiles/r2_traffic.json names the capture), per day class
+* verified after the timed region (outside it) the carried tallies are recomputed from scratch by the per-function
+           kernels and the head-count / census identities are checked on the table the number was measured on
+* cpu_baseline  the CPU oracle (C + OpenMP restatement of the reference's numba kernels, "port") timed on this box's host
+           cores on a bounded sample of the same workload
 
 --impl reference: the CPU leg alone, with every host thread, K ticks per run.
 """
 
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
-from pathlib import Path
 
-import numpy as np
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    # the CPU leg uses every host core: torchrun pins OMP_NUM_THREADS=1 per rank, and OpenMP reads it when the first
+    # library that links it is loaded -- so it has to be corrected before ANY other import
+    if os.environ.get("OMP_NUM_THREADS") == "1" or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+from pathlib import Path  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 HBM_FALLBACK_GBS = 6650.0
-E2E_REPS = 3
-BENCH_R0 = 1.1  # sets daily_infectivity in the synthetic table; see build_pars
-ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1
-# DRAM bytes per agent of one tick_pass launch from the committed ncu --set full capture of this workload at 2.2e8 agents
-# (profiles/r1_fused_v25_220M_summary.csv: dram__bytes_read.sum 2.391 GB + dram__bytes_write.sum 0.275 GB, tick 40)
-NCU_TRAFFIC_BYTES_PER_AGENT = (2.391031e9 + 0.274833e9) / 220_000_000
+ALGO_BYTES_PER_AGENT_TICK = 14.0  # 6 + 8 f_S + 2 f_E + 11 f_I at f_S -> 1, reference column dtypes
+
+# BASELINE.json configs: nodes, agents, default shape per GPU count
+SHAPES = {
+    "zamfara": {"nodes": 14, "agents": 5_000_000},
+    "nigeria": {"nodes": 774, "agents": 220_000_000},
+    "west_africa": {"nodes": 1921, "agents": 430_000_000},
+    "africa": {"nodes": 5672, "agents": 1_300_000_000},
+}
+# the shape BASELINE.json's configs name for each GPU count (reported next to the headline as "named_shape" at N > 1)
+NAMED_SHAPE = {1: "nigeria", 2: "west_africa", 4: "west_africa", 8: "africa"}
 
 # algorithmic bytes per agent per launch of each kernel, reference column dtypes, each needed column touched once
 # (f_S = 0.93, f_E = f_I = 0.01 synthetic mix; derivations in DESIGN.md section 4)
 KERNEL_BYTES = {
     "tick_pass": ALGO_BYTES_PER_AGENT_TICK,                # fused day: SURVEY 8(d) daily figure (pass A of t + pass B of t-1)
     "tick_node": 0.0,                                      # node-level epilogue + node math: no per-agent traffic
+    "vd_births": 0.0,
     "tx_step_prep": 1 + 2 + 4 * 0.93 + 5 * 0.01,          # state, node_id, risk (S), infectivity + strain (I)
     "tx_infect": 1 + 2 + 4 * 0.93,                         # state, node_id, risk (S)
     "count_SEIRP": 1 + 2 + 1 + 1 + 0.02,                   # state, node_id, potentially_paralyzed, paralyzed, strain (E/I)
@@ -64,6 +87,12 @@ def measured_peak():
     if p.exists():
         return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """DRAM bytes per agent of one tick_pass launch per day class, from this round's ncu --set full capture (the file names it)."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    return json.loads(p.read_text()) if p.exists() else None
 
 
 class ClockSampler(threading.Thread):
@@ -116,76 +145,16 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ workload
-def sia_schedule(start, n_nodes, years, rng):
-    """~8 campaigns per year, under-5s, 30-100 % of nodes, mOPV2 then nOPV2 after year 3 (Nigeria)."""
-    import datetime as dt
-
-    events = []
-    for y in range(years + 1):
-        for k in range(8):
-            day = y * 365 + 20 + k * 44
-            frac = rng.uniform(0.3, 1.0)
-            nodes = np.sort(rng.choice(n_nodes, size=max(1, int(frac * n_nodes)), replace=False)).tolist()
-            events.append({"date": start + dt.timedelta(days=day), "nodes": nodes, "age_range": (0, 5 * 365),
-                           "vaccinetype": "mOPV2" if y < 3 else "nOPV2"})
-    return events
-
-
-def build_pars(lp, sizes, dur, seed, rng):
-    import datetime as dt
-
-    n = len(sizes)
-    xy = rng.uniform(0, 1000.0, (n, 2))  # synthetic node coordinates, km
-    dist = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
-    dist[dist == 0] = 1.0
-    np.fill_diagonal(dist, 0.0)
-    start = dt.date(2017, 1, 1)
-    return lp.PropertySet({
-        "seed": seed, "start_date": start, "dur": dur, "init_pop": np.asarray(sizes), "cbr": np.full(n, 37.0),
-        # r0 chosen so that R_eff ~ 1 with 93 % susceptible agents: prevalence stays near the canonical mix of SURVEY 8(d)
-        # (f_S 0.93, f_E = f_I 0.01) for the whole timed window instead of exploding (the real Nigeria runs divide the force
-        # of infection by a population that is mostly non-agent immunes, model.py:1344-1347)
-        "r0": BENCH_R0, "r0_scalars": rng.uniform(0.8, 1.2, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
-        "distances": dist, "migration_method": "gravity", "gravity_k": 0.5, "gravity_k_exponent": -1.0, "gravity_c": 1.5,
-        "max_migr_frac": 0.1, "vx_prob_ri": rng.uniform(0.3, 0.8, n), "vx_prob_ipv": rng.uniform(0.3, 0.8, n),
-        "vx_prob_sia": rng.uniform(0.4, 0.9, n).tolist(), "sia_schedule": sia_schedule(start, n, dur // 365 + 1, rng),
-        "stop_if_no_cases": False, "verbose": 0, "node_seeding_zero_inflation": 0.0, "node_seeding_dispersion": 1000,
-    })
-
-
-def build_sim(lp, n_agents, n_nodes, dur, seed, device, rank=0, world=1):
-    """Synthetic population generated in HBM, mirrored into pinned host columns (the reference-facing LaserFrame),
-    wrapped by SEIR_ABM.init_from_file + Component.init_from_file (the reference's route for a pre-built table).
-
-    With world > 1 every rank builds the shard it owns of a population of n_nodes * world nodes (weak scaling:
-    n_agents agents and n_nodes nodes per GPU, node ids global, network over all nodes)."""
-    import torch
-
-    from laser_polio_b200 import sharding, synth
-
-    births_room = 1.0 + 37.0 / 1000.0 * (dur + 100) / 365.0 * 1.15
-    capacity = int(n_agents * births_room) + 4096
-    pop = synth.synth_population_device(n_agents, n_nodes, seed=seed + rank, capacity=capacity, device=device, r0=BENCH_R0)
-    if rank > 0:
-        live = pop["node_id"][:n_agents]
-        live += rank * n_nodes  # global node ids
-    people = lp.LaserFrame(capacity=capacity, initial_count=n_agents)
-    for name, dtype in synth.COLUMNS.items():
-        people.add_scalar_property(name, dtype=dtype, default=synth.COLUMN_DEFAULTS[name])
-        torch.from_numpy(getattr(people, name)).copy_(pop[name])
-    del pop
-    torch.cuda.empty_cache()
-    sizes = np.concatenate([synth.node_sizes(n_agents, n_nodes, np.random.default_rng(seed + r)) for r in range(world)])
-    pars = build_pars(lp, sizes, dur, seed, np.random.default_rng(seed + 1000))
-    sim = lp.SEIR_ABM.init_from_file(people, pars)
-    sim.verbose = 0
-    sim.nodes = np.arange(n_nodes * world)
-    sim._components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
-    sim.instances = [c.init_from_file(sim) for c in sim._components]
-    if world > 1:
-        sim.shard = sharding.Shard(rank=rank, world=world, node_lo=rank * n_nodes, node_hi=(rank + 1) * n_nodes)
-        sim.id_base = rank * ((capacity + 255) // 256 * 256)
-    return sim
+def plan(args, world):
+    """(shape name, total nodes, total agents, mode) of this run; mode 'shard' = one population over the ranks,
+    'weak' = every rank holds the shape's full per-GPU load."""
+    name = "nigeria" if args.config == "auto" else args.config  # BASELINE.json metric: Nigeria 774 at 1 / 2 / 4 / 8 B200
+    nodes = args.nodes or SHAPES[name]["nodes"]
+    agents = args.agents or SHAPES[name]["agents"]
+    mode = "shard" if args.scaling in ("auto", "shard", "strong") else "weak"
+    if mode == "weak":
+        return name, nodes * world, agents * world, mode
+    return name, nodes, agents, mode
 
 
 # ------------------------------------------------------------------------------------------ CPU leg (oracle "port")
@@ -193,8 +162,6 @@ def cpu_tick_loop(n_agents, n_nodes, ticks, warm, seed=5):
     """The reference's per-tick call sequence on the CPU oracle; returns (agent_days_per_s, threads, per-stage seconds)."""
     from laser_polio_b200 import synth
 
-    if "WORLD_SIZE" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())  # torchrun pins 1 thread per rank; the CPU leg uses every core
     from oracle import oracle as orc
 
     p = synth.synth_population(n_agents, n_nodes, seed=seed)
@@ -256,15 +223,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = min(args.agents or 220_000_000, args.cpu_agents)
-    nodes = args.nodes
-    value, threads, stage, secs = cpu_tick_loop(n, nodes, args.steps, max(1, min(args.warmup, 2)))
-    sample = f"{n} agents x {nodes} nodes (bounded sample of the {args.agents or 220_000_000}-agent workload), {args.steps} ticks"
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    name, nodes, agents, mode = plan(args, world)
+    n = min(agents, args.cpu_agents)
+    cpu_nodes = min(nodes, max(14, n // 20_000))  # keep the sample's agents-per-node near the workload's
+    value, threads, stage, secs = cpu_tick_loop(n, cpu_nodes, args.steps, max(1, min(args.warmup, 2)))
+    sample = f"{n} agents x {cpu_nodes} nodes (bounded sample of the {agents}-agent {name} workload), {args.steps} ticks"
     line = {
         "impl": "reference", "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8 state machine + f32/f64 tallies", "data": "synthetic",
-        "config": {"workload": f"nigeria-774 shape: {args.agents or 220_000_000} agents, {nodes} nodes", "sample": sample},
+        "config": {"workload": f"{name} shape: {agents} agents, {nodes} nodes", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "agent-days/s", "cores": threads, "kind": "port", "sample": sample,
                          "stage_seconds": {k: round(v, 4) for k, v in stage.items()}},
         "e2e": {"value": value, "unit": "agent-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -273,6 +242,13 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU leg
+def day_class(t):
+    """The day classes of the bench schedule (VD every 7, RI every 14, campaigns on day 20 + 44 k of every year)."""
+    from laser_polio_b200 import synth
+
+    return ("sia" if synth.campaign_day(t) else "") + ("vd" if t % 7 == 0 else "") + ("ri" if t % 14 == 0 else "") or "plain"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -287,17 +263,19 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if rank == 0:
-        entry.build()
+        entry.build_product()
     if world > 1:
         dist.barrier()
     import laser_polio_b200 as lp
     from laser_polio_b200 import kernels as K
 
-    n_agents = args.agents or 220_000_000
-    n_nodes = args.nodes
+    name, n_nodes, n_agents, mode = plan(args, world)
     K_, W_ = args.steps, max(args.warmup, 3)
-    dur = (1 + E2E_REPS) * (K_ + W_) + 40
-    sim = build_sim(lp, n_agents, n_nodes, dur, seed=20261017, device=f"cuda:{local}", rank=rank, world=world)
+    e2e_reps = 3 if K_ <= 400 else 1
+    dur = (1 + e2e_reps) * (K_ + W_) + 40
+    from laser_polio_b200 import synth
+
+    sim, n_local = synth.synth_sim(n_agents, n_nodes, dur, seed=20261017, device=f"cuda:{local}", rank=rank, world=world, mode=mode)
 
     def barrier():
         torch.cuda.synchronize()
@@ -307,7 +285,6 @@ def run_b200(args):
 
     # ---- device-resident throughput
     sim.to_device()
-    live0 = int(sim.people.count)
     for _ in range(W_):
         sim.step_tick(sim.t)
     K.STATS.reset()
@@ -316,6 +293,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     barrier()
+    t_first = sim.t
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K_):
@@ -328,15 +306,35 @@ def run_b200(args):
     ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
     kstats = K.STATS.summary()
+    pass_ms = [a.elapsed_time(b) for a, b in K.STATS.events.get("tick_pass", [])]
     launches = K.STATS.launches
     K.STATS.timing = False
+    # ---- self-check of the table the number was measured on (outside the timed region)
+    eng = sim._engine
+    checks = eng.verify() if eng else {"ok": False, "engine": "components only"}
     sim.to_host()
+    r = sim.results
+    t_last = sim.t - 1
+    census = {
+        "E_equals_sum_by_strain": bool(np.array_equal(r.E[:sim.t], r.E_by_strain[:sim.t].sum(axis=2))),
+        "I_equals_sum_by_strain": bool(np.array_equal(r.I[:sim.t], r.I_by_strain[:sim.t].sum(axis=2))),
+        "pop_bookkeeping": bool(np.array_equal(r.pop[t_last], r.pop[0] + r.births[: sim.t].sum(axis=0) - r.deaths[: sim.t].sum(axis=0))),
+    }
+    own = slice(sim.shard.node_lo, sim.shard.node_hi) if sim.shard is not None else slice(None)
+    st = sim.people.disease_state[: sim.people.count]
+    census["census_row_equals_table"] = bool(
+        int((st == 0).sum()) == int(r.S[t_last, own].sum()) and int((st == 1).sum()) == int(r.E[t_last, own].sum())
+        and int((st == 2).sum()) == int(r.I[t_last, own].sum()))
+    verified = torch.tensor([1 if (checks.get("ok") and all(census.values())) else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(verified, op=dist.ReduceOp.MIN)
+    verified = bool(verified.item())
 
     # ---- end to end through the component API from host columns (H2D + ticks + D2H inside the timed region)
-    # repeated E2E_REPS times, median reported: one pass is ~0.3 s of mostly PCIe traffic from a shared host, and single
-    # shots came out bimodal on this pool (0.30 s / 0.59 s for identical work); every repetition is listed in the JSON line
+    # repeated, median reported: one pass is mostly PCIe traffic from a shared host, and single shots came out bimodal
+    # on this pool; every repetition is listed in the JSON line
     e2e_runs = []
-    for _ in range(E2E_REPS):
+    for _ in range(e2e_reps):
         barrier()
         t0 = time.perf_counter()
         sim.to_device()
@@ -350,43 +348,64 @@ def run_b200(args):
         e2e_runs.append(float(rep_s.item()))
     e2e_s = float(np.median(e2e_runs))
     h2d, d2h = sim.io_bytes
+    live = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(live)
+    agents_total = int(live.item())
 
     if rank != 0:
         return
-    agents_total = live0 * world
     value = agents_total * K_ / (ms / 1e3)
     peak, peak_src = measured_peak()
     top = max(kstats, key=lambda k: kstats[k][0] * kstats[k][1])
     calls, mean_ms = kstats[top]
-    algo = KERNEL_BYTES[top] * live0
+    algo = KERNEL_BYTES[top] * n_local
     achieved = algo / (mean_ms / 1e3) / 1e9
     kernel_share = {k: round(c * m / ms, 4) for k, (c, m) in kstats.items()}
-    cpu_n = min(n_agents, args.cpu_agents)
+    by_class = {}
+    for k, v in enumerate(pass_ms):
+        by_class.setdefault(day_class(t_first + k), []).append(v)
+    traffic = measured_traffic()
+    per_class = {}
+    for cls, v in sorted(by_class.items()):
+        m = float(np.mean(v))
+        per_class[cls] = {"launches": len(v), "mean_ms": round(m, 4), "frac_of_14B_roofline": round(ALGO_BYTES_PER_AGENT_TICK * n_local / (m / 1e3) / 1e9 / peak, 4)}
+        if traffic and cls in traffic.get("bytes_per_agent", {}):
+            moved = traffic["bytes_per_agent"][cls] * n_local
+            per_class[cls]["traffic"] = moved
+            per_class[cls]["moved_frac_of_peak"] = round(moved / (m / 1e3) / 1e9 / peak, 4)
+    plain_traffic = traffic["bytes_per_agent"].get("plain") if traffic else None
     cpu_base = None
     if world == 1:  # the CPU leg is reported at N = 1 only (rank 0's host cores)
-        cpu_value, threads, stage, cpu_secs = cpu_tick_loop(cpu_n, n_nodes, args.cpu_ticks, 1)
+        cpu_n = min(n_agents, args.cpu_agents)
+        cpu_nodes = min(n_nodes, max(14, cpu_n // 20_000))
+        cpu_value, threads, stage, cpu_secs = cpu_tick_loop(cpu_n, cpu_nodes, args.cpu_ticks, 1)
         cpu_base = {"value": cpu_value, "unit": "agent-days/s", "cores": threads, "kind": "port",
-                    "sample": f"{cpu_n} agents x {n_nodes} nodes, {args.cpu_ticks} ticks ({cpu_secs:.1f} s)",
+                    "sample": f"{cpu_n} agents x {cpu_nodes} nodes, {args.cpu_ticks} ticks ({cpu_secs:.1f} s)",
                     "stage_seconds": {k: round(v, 4) for k, v in stage.items()}}
     line = {
         "metric": "agent-days/sec", "value": value, "unit": "agent-days/s", "n_gpus": world, "steps": K_, "warmup": W_,
-        "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 state machine + int64 fixed-point tallies + f64 node math", "data": "synthetic",
-        "config": {"workload": f"nigeria-774 shape (examples/demo_nigeria.py): {n_agents} agents/GPU, {n_nodes} nodes/GPU, 3 strains, "
+        "ms_per_step": ms / K_, "higher_is_better": True, "scaling": "weak" if mode == "weak" else "strong",
+        "vs_baseline": None, "dtype": "u8 agenda bytes + int8 state machine + int64 fixed-point tallies + f64 node math", "data": "synthetic",
+        "config": {"workload": f"{name} shape (BASELINE.json configs): {agents_total} agents, {n_nodes} nodes over {world} GPU(s), 3 strains, "
                                "VD every 7, RI every 14, ~8 SIA/yr, daily transmission + census",
-                   "agents_per_gpu": n_agents, "nodes": n_nodes, "l2_policy": "inputs (>=1 GB per column) far larger than the 126 MB L2",
-                   "parallelism": (f"node-sharded x{world}: {n_nodes * world} nodes, one NCCL all-reduce of the nodes x strains tally per tick"
-                                   if world > 1 else "single GPU")},
+                   "shape": name, "agents_total": agents_total, "agents_rank0": n_local, "nodes": n_nodes,
+                   "l2_policy": "per-tick working set (>= 0.2 GB of agenda bytes + event records) far larger than the 126 MB L2",
+                   "parallelism": (f"{'one population node-sharded' if mode == 'shard' else 'per-GPU replicas of the shape, node-sharded'} x{world}, "
+                                   "one exchange of the nodes x strains tally per tick" if world > 1 else "single GPU")},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (NCU_TRAFFIC_BYTES_PER_AGENT * live0) if top == "tick_pass" else None,
-                     "traffic_source": "ncu --set full capture of one launch at 2.2e8 agents (profiles/r1_fused_v25_220M_summary.csv), scaled per agent",
+                     "traffic": (plain_traffic * n_local) if (plain_traffic and top == "tick_pass") else None,
+                     "traffic_source": traffic.get("source") if traffic else None,
+                     "note": "achieved = 14 B/agent-tick (SURVEY 8d, reference dtypes) x agents / mean launch time, as the contract defines it; the pass "
+                             "itself moves ~3 B/agent (agenda byte + event records), so frac > what the DRAM counters show: see per_day_class.moved_frac_of_peak",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
-                     "tick_frac_of_14B_roofline": (ALGO_BYTES_PER_AGENT_TICK * value / world) / (peak * 1e9),
-                     "kernel_share_of_step": kernel_share},
+                     "per_day_class": per_class, "kernel_share_of_step": kernel_share},
+        "verified": verified, "verified_checks": {**checks, **census},
         "cpu_baseline": cpu_base,
         "e2e": {"value": agents_total * K_ / e2e_s, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
                 "seconds": e2e_s, "seconds_each": [round(x, 4) for x in e2e_runs],
-                "note": f"SEIR_ABM.to_device() + K step_tick() + to_host() from pinned host columns, median of {E2E_REPS} repetitions"},
+                "note": f"SEIR_ABM.to_device() + K step_tick() + to_host() from pinned host columns, median of {e2e_reps} repetition(s); "
+                        "byte counts are rank 0's"},
         "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
@@ -398,8 +417,10 @@ def main():
     ap.add_argument("--steps", type=int, default=140)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--agents", type=int, default=0, help="agents per GPU (default: 220M, the Nigeria config)")
-    ap.add_argument("--nodes", type=int, default=774)
+    ap.add_argument("--config", default="auto", choices=["auto"] + list(SHAPES))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "shard", "strong", "weak"])
+    ap.add_argument("--agents", type=int, default=0, help="total agents (default: the shape's)")
+    ap.add_argument("--nodes", type=int, default=0, help="total nodes (default: the shape's)")
     ap.add_argument("--cpu-agents", type=int, default=20_000_000)
     ap.add_argument("--cpu-ticks", type=int, default=60)
     args = ap.parse_args()

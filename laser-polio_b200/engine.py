@@ -220,8 +220,35 @@ class FusedEngine:
         self.dev.set_count(self.sim.people.count)
         self.rebase_tallies(t + 1)
 
+    def verify(self) -> dict:
+        """Self-check used by bench.py and the tests: settle the table and compare every carried tally with the
+        per-function kernels run from scratch on it (tx_step_prep, count_SEIRP), plus the head-count identity.  The
+        table is left canonical with the last tick's exposure still pending (to_host() / the next tick finish it)."""
+        sim, dev, c = self.sim, self.dev, self.dev.cols
+        self.settle(sim.t)
+        count = dev.sync_count()
+        n, ns = dev.n_nodes, dev.n_strains
+        beta, expo, sus, hist = K.tx_step_prep(n, count, ns, c["strain"], list(sim.pars.strain_r0_scalars.values()), c["disease_state"],
+                                               c["node_id"], c["daily_infectivity"], c["acq_risk_multiplier"])
+        S, E, I, R, Ebs, Ibs, PP, Pz = K.count_SEIRP(c["node_id"], c["disease_state"], c["strain"], c["potentially_paralyzed"],  # noqa: E741
+                                                     c["paralyzed"], n, ns, count)
+        state = c["disease_state"][:count]
+        dead = int((state < 0).sum().item())
+        out = {
+            "beta_fx": bool(torch.equal(beta, self.beta)), "exposure_fx": bool(torch.equal(expo, self.expo)),
+            "sus": bool(torch.equal(sus, self.sus)), "risk_hist": bool(torch.equal(hist, self.hist)),
+            "E_by_strain": bool(torch.equal(Ebs, self.E_cur)), "I_by_strain": bool(torch.equal(Ibs, self.I_cur)),
+            "R": bool(torch.equal(R, self.R_cur)), "S_equals_sus": bool(torch.equal(S.to(torch.int64), self.sus)),
+            "head_count": int(S.sum().item() + E.sum().item() + I.sum().item() + R.sum().item()) + dead == count,
+        }
+        out["ok"] = all(out.values())
+        return out
+
     def fused_tick(self, t):
         sim, dev, pars = self.sim, self.dev, self.sim.pars
+        if not self.hot_valid:  # the table was settled behind the engine's back (verify()): finish and re-base
+            self.drain()
+            self.rebase_tallies(t)
         n, ns = dev.n_nodes, dev.n_strains
         tx = self.by_name["Transmission_ABM"]
         ri = self.by_name.get("RI_ABM")

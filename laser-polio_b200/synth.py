@@ -168,8 +168,14 @@ def synth_population_device(
     missed_frac: float = 0.1,
     ipv_frac: float = 0.3,
     max_age_days: int = 15 * 365,
+    sizes=None,
+    node_offset: int = 0,
 ) -> dict:
     """Same distributions as :func:`synth_population`, generated directly in HBM with torch (seeded).
+
+    ``sizes`` (optional): explicit agents per node for the ``n_nodes`` nodes of this table (a node shard of a larger
+    population); node ids are ``node_offset + 0 .. n_nodes - 1``.
+
 
     Used for the full-size configurations (2.2e8 .. 1.3e9 agents) where a host-side build would
     dominate the run.  Values differ from the numpy generator (different RNG); shapes, dtypes and
@@ -182,12 +188,13 @@ def synth_population_device(
     g.manual_seed(int(seed))
     capacity = int(capacity or n_agents)
     n = int(n_agents)
-    sizes = node_sizes(n, n_nodes, np.random.default_rng(seed))
+    sizes = node_sizes(n, n_nodes, np.random.default_rng(seed)) if sizes is None else np.asarray(sizes, dtype=np.int64)
+    assert len(sizes) == n_nodes and int(sizes.sum()) == n
     tdt = {np.int8: torch.int8, np.uint8: torch.uint8, np.int16: torch.int16, np.int32: torch.int32, np.float32: torch.float32}
     cols = {k: torch.full((capacity,), COLUMN_DEFAULTS[k], dtype=tdt[d], device=dev) for k, d in COLUMNS.items()}
 
     cols["node_id"][:n] = torch.repeat_interleave(
-        torch.arange(n_nodes, dtype=torch.int16, device=dev), torch.from_numpy(sizes).to(dev), output_size=n
+        torch.arange(node_offset, node_offset + n_nodes, dtype=torch.int16, device=dev), torch.from_numpy(sizes).to(dev), output_size=n
     )
     u = torch.rand(n, generator=g, device=dev)
     e = np.cumsum([f_dead, f_exposed, f_infected, f_recovered])
@@ -233,3 +240,99 @@ def synth_population_device(
     out = {"count": n, "capacity": capacity, "n_nodes": int(n_nodes), "n_strains": int(n_strains), "node_sizes": sizes}
     out.update(cols)
     return out
+
+
+# ------------------------------------------------------------------------------------------ a runnable sim on a synthetic table
+WORKLOAD_R0 = 1.1  # sets daily_infectivity in the synthetic table; see workload_pars
+
+
+def campaign_schedule(start, n_nodes, years, rng):
+    """~8 campaigns per year, under-5s, 30-100 % of nodes, mOPV2 then nOPV2 after year 3 (Nigeria)."""
+    import datetime as dt
+
+    events = []
+    for y in range(years + 1):
+        for k in range(8):
+            day = y * 365 + 20 + k * 44
+            frac = rng.uniform(0.3, 1.0)
+            nodes = np.sort(rng.choice(n_nodes, size=max(1, int(frac * n_nodes)), replace=False)).tolist()
+            events.append({"date": start + dt.timedelta(days=day), "nodes": nodes, "age_range": (0, 5 * 365),
+                           "vaccinetype": "mOPV2" if y < 3 else "nOPV2"})
+    return events
+
+
+def campaign_day(t: int) -> bool:
+    """Is tick t a campaign day of :func:`campaign_schedule`?"""
+    d = t % 365
+    return d >= 20 and (d - 20) % 44 == 0 and (d - 20) // 44 < 8
+
+
+def workload_pars(sizes, dur, seed, rng, cbr=37.0, **over):
+    """PropertySet of the full-feature workload on nodes of the given sizes: vital dynamics every 7 ticks, RI every 14,
+    ~8 campaigns a year, gravity network with seasonality, three strains."""
+    import datetime as dt
+
+    from .core import PropertySet
+
+    n = len(sizes)
+    xy = rng.uniform(0, 1000.0, (n, 2))  # synthetic node coordinates, km
+    dist = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+    dist[dist == 0] = 1.0
+    np.fill_diagonal(dist, 0.0)
+    start = dt.date(2017, 1, 1)
+    p = {
+        "seed": seed, "start_date": start, "dur": dur, "init_pop": np.asarray(sizes), "cbr": np.full(n, float(cbr)),
+        # r0 chosen so that R_eff ~ 1 with 93 % susceptible agents: prevalence stays near the canonical mix of SURVEY 8(d)
+        # (f_S 0.93, f_E = f_I 0.01) for the whole timed window instead of exploding (the real Nigeria runs divide the force
+        # of infection by a population that is mostly non-agent immunes, model.py:1344-1347)
+        "r0": WORKLOAD_R0, "r0_scalars": rng.uniform(0.8, 1.2, n), "seasonal_amplitude": 0.1, "seasonal_peak_doy": 159,
+        "distances": dist, "migration_method": "gravity", "gravity_k": 0.5, "gravity_k_exponent": -1.0, "gravity_c": 1.5,
+        "max_migr_frac": 0.1, "vx_prob_ri": rng.uniform(0.3, 0.8, n), "vx_prob_ipv": rng.uniform(0.3, 0.8, n),
+        "vx_prob_sia": rng.uniform(0.4, 0.9, n).tolist(), "sia_schedule": campaign_schedule(start, n, dur // 365 + 1, rng),
+        "stop_if_no_cases": False, "verbose": 0, "node_seeding_zero_inflation": 0.0, "node_seeding_dispersion": 1000,
+    }
+    p.update(over)
+    return PropertySet(p)
+
+
+def synth_sim(n_agents, n_nodes, dur, seed, device="cuda", rank=0, world=1, mode="shard", cbr=37.0, pars_over=None, pop_over=None):
+    """A SEIR_ABM with the five stock components on a synthetic table generated in HBM and mirrored into host columns (the
+    reference-facing LaserFrame), wrapped by SEIR_ABM.init_from_file + Component.init_from_file -- the reference's route for
+    a pre-built table (run_sim.py:398-409).  Returns (sim, agents on this rank).
+
+    n_agents / n_nodes are the totals over all ranks.  Every rank builds the node block it owns: in 'shard' mode contiguous
+    blocks of ONE heavy-tailed size vector balanced by agents (sharding.plan_node_blocks), in 'weak' mode block r is the
+    r-th copy of a per-GPU shape.  Node ids are global, the network spans all nodes."""
+    import torch
+
+    from . import abm, core, sharding
+
+    if mode == "weak":
+        per_nodes, per_agents = n_nodes // world, n_agents // world
+        sizes_all = np.concatenate([node_sizes(per_agents, per_nodes, np.random.default_rng(seed + r)) for r in range(world)])
+        blocks = [(r * per_nodes, (r + 1) * per_nodes) for r in range(world)]
+    else:
+        sizes_all = node_sizes(n_agents, n_nodes, np.random.default_rng(seed))
+        blocks = sharding.plan_node_blocks(sizes_all, world) if world > 1 else [(0, n_nodes)]
+    births_room = 1.0 + float(cbr) / 1000.0 * (dur + 100) / 365.0 * 1.15
+    caps = [int(int(sizes_all[lo:hi].sum()) * births_room) + 4096 for lo, hi in blocks]
+    lo, hi = blocks[rank]
+    n_r, capacity = int(sizes_all[lo:hi].sum()), caps[rank]
+    pop = synth_population_device(n_r, hi - lo, seed=seed + rank, capacity=capacity, device=device, r0=WORKLOAD_R0,
+                                  sizes=sizes_all[lo:hi], node_offset=lo, **(pop_over or {}))
+    people = core.LaserFrame(capacity=capacity, initial_count=n_r)
+    for name, dtype in COLUMNS.items():
+        people.add_scalar_property(name, dtype=dtype, default=COLUMN_DEFAULTS[name])
+        torch.from_numpy(getattr(people, name)).copy_(pop[name])
+    del pop
+    torch.cuda.empty_cache()
+    pars = workload_pars(sizes_all, dur, seed, np.random.default_rng(seed + 1000), cbr=cbr, **(pars_over or {}))
+    sim = abm.SEIR_ABM.init_from_file(people, pars)
+    sim.verbose = 0
+    sim.nodes = np.arange(n_nodes)
+    sim._components = [abm.VitalDynamics_ABM, abm.DiseaseState_ABM, abm.RI_ABM, abm.SIA_ABM, abm.Transmission_ABM]
+    sim.instances = [c.init_from_file(sim) for c in sim._components]
+    if world > 1:
+        sim.shard = sharding.Shard(rank=rank, world=world, node_lo=lo, node_hi=hi)
+        sim.id_base = sharding.id_bases(sizes_all, blocks, capacity_per_block=caps)[rank]
+    return sim, n_r
