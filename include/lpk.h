@@ -279,6 +279,8 @@ typedef struct lpk_tick_args {
     int32_t ri_lazy_k;
     uint32_t *work_counter; /* caller-owned device uint32 (one per table / stream): the pass zeroes it on `stream` and claims
                                work units from it, so two tables on one device never share scheduling state */
+    uint32_t *work_counter_next; /* optional (lpk_run_days): when set, *work_counter is taken to be zero already (no memset
+                               node on the stream) and this launch zeroes *work_counter_next for the launch after it */
 } lpk_tick_args;
 
 /* tile_node[k] for tiles first_tile .. last tile covering [0, n_slots): node id if node_id is constant over the
@@ -289,7 +291,7 @@ int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args, void *str
 
 /* ---- Agenda bytes: what the pass streams (csrc/lpk_hot.cuh) ----------------------------------------------------------
  * lpk_tick_pass reads ONE byte per agent per day, people->hot[i]:
- *   bits 7:6 class: 00 susceptible, 01 inactive (payload 0 recovered, 1 dead / unborn), 10 exposed, 11 infectious
+ *   bits 7:6 class: 00 exposed, 01 infectious, 10 inactive (payload 0 recovered, 1 dead / unborn), 11 susceptible
  *   bits 5:0 susceptible: 6-bit upper bound of acq_risk_multiplier (4 steps per octave; 2^(e - risk_e0) * (1 + m / 4));
  *            exposed / infectious: day of the agent's next event (E -> I, paralysis gate, I -> R) modulo 64
  * and touches full-width data only for agents with an event: the 8-byte record people->rec[i] (the eight byte columns of
@@ -349,6 +351,11 @@ typedef struct lpk_node_args {
     /* node shard: only nodes [node_lo, node_hi) are this rank's -- their rows are written, their columns of
      * the network are read (1 / world of the matrix per tick); node_hi == 0 means every node */
     int32_t node_lo, node_hi;
+    /* tally exchange of a sharded run (lpk_xchg, set by lpk_run_days): beta_fx is this rank's receive buffer, and the node
+     * kernels wait until xchg_flags[r] has reached xchg_seq for every rank r < xchg_world before reading it; NULL = no wait */
+    const uint32_t *xchg_flags;
+    int32_t xchg_world;
+    uint32_t xchg_seq;
 } lpk_node_args;
 
 int lpk_tick_node(const lpk_node_args *args, void *stream);
@@ -397,6 +404,73 @@ typedef struct lpk_births_args {
 } lpk_births_args;
 
 int lpk_vd_births(const lpk_births_args *args, void *stream);
+
+/* ---- A run of fused days driven from C (SURVEY.md 7 "hard parts": host glue; 8e: the tick is launched without the host) ----
+ * The reference's loop body is Python per tick (model.py:252-263).  At 2.2e8 agents a fused day is ~0.3 ms of device time
+ * and at 8 GPUs ~0.05 ms, less than the Python that assembles its arguments, so the loop itself lives here:
+ * lpk_run_days() derives every day's lpk_births_args / lpk_tick_args / lpk_node_args from ONE template (row pointers are
+ * base + tick * row length) and launches vital dynamics -> pass -> [tally exchange] -> node kernels for n_days consecutive
+ * days back to back on `stream`, with no host work in between other than the launches (~4 per plain day).  With
+ * run->graph != 0 the days are captured into a CUDA graph and launched as one.  Results are those of calling
+ * lpk_vd_births / lpk_tick_pass / lpk_tick_node day by day (tests/test_gpu_fused.py runs both). */
+typedef struct lpk_rows { /* device results arrays of the run: [nt, nodes] or [nt, nodes, strains] int32; NULL = absent */
+    int32_t *S, *E, *I, *R, *pop, *births, *deaths, *new_exposed, *new_potentially_paralyzed, *new_paralyzed;
+    int32_t *potentially_paralyzed, *paralyzed, *ri_vaccinated, *ri_protected, *ipv_vaccinated, *sia_vaccinated, *sia_protected;
+    int32_t *E_by_strain, *I_by_strain, *new_exposed_by_strain, *ri_new_exposed_by_strain, *sia_new_exposed_by_strain;
+    int32_t *sink; /* [nodes * strains] scratch row that stands in for the rows of absent arrays */
+} lpk_rows;
+
+typedef struct lpk_day { /* what changes from day to day */
+    int32_t tick;
+    uint32_t flags;          /* LPK_F_DEATHS | LPK_F_RI | LPK_F_SIA of this day (PENDING / STAGES / ROWSUMS are the driver's) */
+    double beta_seasonality; /* get_seasonality(sim) of the day (utils.py:616-625) */
+    const uint8_t *sia_targeted; /* the day's single campaign event (LPK_F_SIA): lpk_tick_args.sia_* */
+    double sia_vx_eff;
+    int32_t sia_min_age, sia_max_age, sia_strain, _pad;
+} lpk_day;
+
+/* Tally exchange of a node-sharded run: every rank's rows [node_lo, node_hi) of the nodes x strains infectivity
+ * tally, written straight into every peer's HBM over NVLink by a kernel between the pass and the node kernels (peer
+ * memory mapped through CUDA IPC; one process per GPU), followed by a system-scope flag; the node kernels wait on the
+ * flags of all ranks before they read the gathered tally.  No NCCL call, no host synchronisation per tick.  Rows are
+ * disjoint between ranks, so gathering them IS the all-reduce (sum) of the reference design, and it is exact. */
+typedef struct lpk_xchg lpk_xchg;
+#define LPK_XCHG_HANDLE_BYTES 64
+/* allocate this rank's receive buffers (2 x n_elems int64 + flags) and export their IPC handle */
+int lpk_xchg_create(int32_t rank, int32_t world, int64_t n_elems, lpk_xchg **out, void *handle_out);
+/* handles: world x LPK_XCHG_HANDLE_BYTES, every rank's handle in rank order (exchanged by the caller, e.g. all_gather) */
+int lpk_xchg_connect(lpk_xchg *x, const void *handles);
+/* teardown in two phases: every rank disconnects (unmaps its peers), the caller runs a barrier, every rank destroys */
+int lpk_xchg_disconnect(lpk_xchg *x);
+int lpk_xchg_destroy(lpk_xchg *x);
+
+typedef struct lpk_run {
+    lpk_people people;
+    lpk_tick_args tick;     /* template: constants, carried tallies, scratch; per-day fields are filled by the driver */
+    lpk_node_args node;     /* template likewise (network, r0_scalars, q / cdf outputs, snapshots, node shard) */
+    lpk_births_args births; /* template; births.capacity == 0: VitalDynamics_ABM is not a component */
+    lpk_rows rows;
+    const int32_t *zero_pop; /* [nodes] zeros: the population row when nobody maintains results.pop */
+    int32_t *any_cases;      /* optional device int32[nt]: lpk_node_args.any_cases of tick t is any_cases + t */
+    uint32_t *work_counters; /* device uint32[2], both zero before the first day: the passes alternate between them */
+    lpk_xchg *xchg;          /* NULL: single table */
+    int32_t pending;         /* in / out: the previous tick's exposure trial + census are still to be applied */
+    int32_t ri_lazy_k;       /* in / out: lpk_tick_args.ri_lazy_k */
+    int32_t rowsums_valid;   /* in / out: node.rowsum_ws holds the row sums of node.network */
+    int32_t graph;           /* != 0: capture the days into a CUDA graph and launch that */
+    uint32_t seq;            /* in / out: exchange sequence number (flags are compared against it) */
+    int32_t _pad;
+} lpk_run;
+
+/* ms: optional HOST float[n_days][3]; when given, every day's births kernels, pass and node kernels (exchange included) are
+ * bracketed by CUDA events on `stream`, the call synchronises at the end and writes the three elapsed times per day
+ * (measurement runs only; forces graph off).  launches: optional, += the number of kernels launched. */
+int lpk_run_days(lpk_run *run, const lpk_day *days, int32_t n_days, float *ms, int64_t *launches, void *stream);
+/* the two halves of one day, for callers that do the tally exchange themselves between them (torch.distributed) */
+int lpk_run_day_pass(lpk_run *run, const lpk_day *day, int64_t *launches, void *stream);
+int lpk_run_day_node(lpk_run *run, const lpk_day *day, const int64_t *beta_all, int64_t *launches, void *stream);
+/* waits for and frees the executable graphs of earlier lpk_run_days calls of this thread (they are otherwise freed lazily) */
+int lpk_run_release(void);
 
 /* ---- Population initialisation in HBM -------------------------------------------------------
  * The reference draws every per-agent column on the host at construction.  Each entry below replaces one of those

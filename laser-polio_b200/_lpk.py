@@ -22,7 +22,8 @@ FX_SCALE = float(2**30)
 EXPORTS = (
     "lpk_last_error", "lpk_version", "lpk_philox_selftest", "lpk_get_deaths", "lpk_disease_state_step", "lpk_fast_ri",
     "lpk_fast_sia", "lpk_tx_step_prep", "lpk_tx_node_math", "lpk_tx_infect", "lpk_count_seirp", "lpk_build_tile_nodes",
-    "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births", "lpk_hot_build", "lpk_hot_settle", "lpk_hot_padded", "lpk_hot_risk_e0",
+    "lpk_tick_pass", "lpk_tick_node", "lpk_vd_births", "lpk_run_days", "lpk_run_day_pass", "lpk_run_day_node", "lpk_run_release",
+    "lpk_xchg_create", "lpk_xchg_connect", "lpk_xchg_disconnect", "lpk_xchg_destroy", "lpk_hot_build", "lpk_hot_settle", "lpk_hot_padded", "lpk_hot_risk_e0",
     "lpk_init_heterogeneity", "lpk_init_timers", "lpk_init_demography", "lpk_init_missed",
     "lpk_net_haversine", "lpk_net_gravity", "lpk_net_radiation", "lpk_net_row_normalize",
 )
@@ -134,7 +135,7 @@ class TickArgs(C.Structure):
         ("sia_vaccinated", _VP), ("sia_protected", _VP), ("sia_new_exposed_by_strain", _VP),
         ("strain_r0_scalars", C.c_double * MAX_STRAINS),
         ("beta_fx", _VP), ("E_cur", _VP), ("I_cur", _VP), ("exposure_fx", _VP), ("sus", _VP), ("risk_hist", _VP), ("R_cur", _VP),
-        ("uniform_agents", C.c_int64), ("ri_lazy_k", C.c_int32), ("work_counter", _VP),
+        ("uniform_agents", C.c_int64), ("ri_lazy_k", C.c_int32), ("work_counter", _VP), ("work_counter_next", _VP),
     ]
 
 
@@ -153,6 +154,7 @@ class NodeArgs(C.Structure):
         ("E_cur", _VP), ("I_cur", _VP), ("E_snap", _VP), ("I_snap", _VP), ("tx_hits_by_strain", _VP), ("any_cases", _VP),
         ("sus", _VP), ("R_cur", _VP), ("tx_hits", _VP), ("S_snap", _VP), ("R_snap", _VP), ("S_prev", _VP), ("R_prev", _VP),
         ("counts", _VP), ("node_lo", C.c_int32), ("node_hi", C.c_int32),
+        ("xchg_flags", _VP), ("xchg_world", C.c_int32), ("xchg_seq", C.c_uint32),
     ]
 
 
@@ -171,6 +173,35 @@ class BirthsArgs(C.Structure):
         ("ri_k", _VP), ("pair_ri_max", _VP), ("ri_lazy_k", C.c_int32),
         ("ri_step", C.c_int32),
     ]
+
+
+class Rows(C.Structure):
+    """struct lpk_rows"""
+
+    NAMES = ("S", "E", "I", "R", "pop", "births", "deaths", "new_exposed", "new_potentially_paralyzed", "new_paralyzed",
+             "potentially_paralyzed", "paralyzed", "ri_vaccinated", "ri_protected", "ipv_vaccinated", "sia_vaccinated", "sia_protected",
+             "E_by_strain", "I_by_strain", "new_exposed_by_strain", "ri_new_exposed_by_strain", "sia_new_exposed_by_strain")
+    _fields_ = [(n, _VP) for n in NAMES] + [("sink", _VP)]
+
+
+class Day(C.Structure):
+    """struct lpk_day"""
+
+    _fields_ = [("tick", C.c_int32), ("flags", C.c_uint32), ("beta_seasonality", C.c_double), ("sia_targeted", _VP),
+                ("sia_vx_eff", C.c_double), ("sia_min_age", C.c_int32), ("sia_max_age", C.c_int32), ("sia_strain", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class Run(C.Structure):
+    """struct lpk_run"""
+
+    _fields_ = [("people", People), ("tick", TickArgs), ("node", NodeArgs), ("births", BirthsArgs), ("rows", Rows),
+                ("zero_pop", _VP), ("any_cases", _VP), ("work_counters", _VP), ("xchg", _VP),
+                ("pending", C.c_int32), ("ri_lazy_k", C.c_int32), ("rowsums_valid", C.c_int32), ("graph", C.c_int32),
+                ("seq", C.c_uint32), ("_pad", C.c_int32)]
+
+
+XCHG_HANDLE_BYTES = 64
 
 
 class Dist(C.Structure):

@@ -218,6 +218,7 @@ class SEIR_ABM:
         if self.dev is not None:
             if self._engine:  # None: never started, False: components only
                 self._engine.drain()
+                self._engine.close()
             self._engine = None
             self.dev.download()
             self.io_bytes = (self.dev.h2d_bytes, self.dev.d2h_bytes)
@@ -249,18 +250,27 @@ class SEIR_ABM:
         else:
             self._engine.tick(tick)
 
+    def run_ticks(self, n: int) -> None:
+        """Advance up to ``n`` ticks on the device (fewer on an early stop), leaving the population resident.  With the
+        stock component list consecutive fused days are launched from C in one call (engine.FusedEngine.advance)."""
+        t_end = min(self.t + int(n), self.nt)
+        while self.t < t_end:
+            if getattr(self, "_engine", None) and self.t >= 1:
+                self._engine.advance(t_end)
+            else:
+                self.step_tick(self.t)
+            if self.t > 1 and self.should_stop:
+                break
+
     def run(self):
         if self.verbose >= 1:
             _say("cyan", "Initialization complete. Running simulation...")
         self.to_device()
         try:
-            for tick in range(self.t, self.nt):
-                self.step_tick(tick)
-                if tick > 0 and self.should_stop:
-                    if self.verbose >= 1:
-                        _say("yellow", f"[SEIR_ABM] Early stopping at t={self.t}: no E/I and no future seed_schedule events. "
-                                       "This stops all components (e.g., no births, deaths, or vaccination)")
-                    break
+            self.run_ticks(self.nt - self.t)
+            if self.should_stop and self.verbose >= 1:
+                _say("yellow", f"[SEIR_ABM] Early stopping at t={self.t}: no E/I and no future seed_schedule events. "
+                               "This stops all components (e.g., no births, deaths, or vaccination)")
         finally:
             self.to_host()
         if self.verbose >= 1:

@@ -663,6 +663,26 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
     return (float)(t > 3.0e38 ? 3.0e38 : t);
 }
 
+// Sharded runs (lpk_xchg): the gathered tally in beta_fx is complete once every rank's flag has reached `seq`.  One thread
+// per block acquires the flags at system scope (the peers' stores arrive over NVLink), the block barrier publishes that to
+// the other threads.  A peer that never arrives turns into a trap after ~10 s instead of a hung device.
+__device__ __forceinline__ void xchg_wait(const uint32_t *flags, int world, uint32_t seq) {
+    if (flags) {
+        if (threadIdx.x == 0) {
+            for (int r = 0; r < world; ++r) {
+                uint32_t v, spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+                    if ((int32_t)(v - seq) >= 0) break;
+                    if (++spins > (1u << 24)) __trap();
+                    __nanosleep(64);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // One block = 32 destination nodes x 32 source slices (1024 threads).  The infectivity tally is staged through shared
 // memory 1024 source rows at a time (the previous version re-read it from global in a dependent loop and took 41 us at 774
 // nodes: profiles/r1_v18_launches.csv); the block's 32 warps then solve tau for its 32 nodes.
@@ -673,9 +693,11 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
 // does not depend on which block finishes first.
 __global__ void __launch_bounds__(1024) k_node_matvec_partial(int n, int n_strains, const int64_t *__restrict__ beta_fx,
                                                                const double *__restrict__ W, int j_lo, int j_hi,
-                                                               double *__restrict__ partial) {
+                                                               double *__restrict__ partial, const uint32_t *xflags, int xworld,
+                                                               uint32_t xseq) {
     __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];
     __shared__ unsigned char snz[NM_ROWS];
+    xchg_wait(xflags, xworld, xseq);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = j_lo + blockIdx.x * 32 + tx, base = blockIdx.y * NM_ROWS;
     const int rows = min(NM_ROWS, n - base);
@@ -683,7 +705,7 @@ __global__ void __launch_bounds__(1024) k_node_matvec_partial(int n, int n_strai
         bool nz = false;
 #pragma unroll
         for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
-            const long long b = (s < n_strains) ? beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s] : 0;
+            const long long b = (s < n_strains) ? __ldcg(&beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s]) : 0;
             nz |= (b != 0);
             sbeta[s][threadIdx.x] = (double)b / LPK_FX_SCALE;
         }
@@ -722,10 +744,11 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
                                                         double *target, double *strain_cdf, double *prob, double *expected,
                                                         const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
                                                         uint32_t tick, int j_lo, int j_hi, const double *__restrict__ partial,
-                                                        int n_chunks) {
+                                                        int n_chunks, const uint32_t *xflags, int xworld, uint32_t xseq) {
     __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
     __shared__ unsigned char snz[NM_ROWS];
     __shared__ double stgt[32];
+    xchg_wait(xflags, xworld, xseq);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = j_lo + blockIdx.x * 32 + tx;  // destination nodes [j_lo, j_hi): all of them, or this rank's shard
     double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
@@ -743,7 +766,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
             bool nz = false;
 #pragma unroll
             for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
-                const long long b = (s < n_strains) ? beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s] : 0;
+                const long long b = (s < n_strains) ? __ldcg(&beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s]) : 0;
                 nz |= (b != 0);
                 sbeta[s][threadIdx.x] = (double)b / LPK_FX_SCALE;
             }
@@ -773,7 +796,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
             for (int s = 0; s < n_strains; ++s) {
                 double inc = 0.0;
                 for (int y = 0; y < 32; ++y) inc += part[(y * LPK_MAX_STRAINS + s) * 32 + tx];
-                const double pre = (double)beta_fx[(int64_t)j * n_strains + s] / LPK_FX_SCALE;
+                const double pre = (double)__ldcg(&beta_fx[(int64_t)j * n_strains + s]) / LPK_FX_SCALE;
                 local += pre;
                 double b = pre + inc - pre * rowsum[j];
                 b = b * season * r0_scalars[j];
@@ -808,7 +831,7 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
-                         int32_t node_lo, int32_t node_hi) {
+                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq) {
     double *rowsum = ws, *target = ws + num_nodes;
     if (!rowsums_done) {
         k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
@@ -835,14 +858,14 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
             scratch_bytes[dev] = need;
         }
         k_node_matvec_partial<<<dim3((node_hi - node_lo + 31) / 32, n_chunks), 1024, 0, st>>>(num_nodes, n_strains, beta_fx, network, node_lo,
-                                                                                             node_hi, scratch[dev]);
+                                                                                             node_hi, scratch[dev], xchg_flags, xchg_world, xchg_seq);
         CUDA_TRY(cudaGetLastError(), "node_math matvec");
         partial = scratch[dev];
     }
     k_tx_node_math<<<(node_hi - node_lo + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
                                                                    beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
                                                                    strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi,
-                                                                   partial, n_chunks);
+                                                                   partial, n_chunks, xchg_flags, xchg_world, xchg_seq);
     CUDA_TRY(cudaGetLastError(), "node_math");
     return LPK_OK;
 }
@@ -858,5 +881,5 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
                 expected && ws, "tx_node_math null pointer");
     return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
                                 alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
-                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes);
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes, nullptr, 0, 0u);
 }

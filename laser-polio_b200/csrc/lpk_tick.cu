@@ -30,7 +30,8 @@
 struct PassParams {
     lpk_people P;
     lpk_tick_args A;
-    uint32_t *unit_ctr;  // work counter of this launch (zeroed on the stream before the kernel)
+    uint32_t *unit_ctr;  // work counter of this launch (zero when the kernel starts)
+    uint32_t *unit_ctr_next;  // optional: the counter of the NEXT launch, zeroed by this one (lpk_tick_args.work_counter_next)
     uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
     uint32_t rk[20];     // Philox round keys of the seed (key schedule done once on the host: the sweep's block reads them
                          // straight from the constant bank instead of spending 20 additions per 8 agents)
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     const lpk_people &P = pp.P;
     const lpk_tick_args &A = pp.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (pp.unit_ctr_next && blockIdx.x == 0 && threadIdx.x == 0) *pp.unit_ctr_next = 0u;  // nobody claims from it during this launch
     const int64_t n = A.counts[1];
     const bool pending = (A.flags & LPK_F_PENDING) != 0;
     const int tick = A.tick, e0 = P.risk_e0;
@@ -703,7 +705,7 @@ static int launch_pass(const PassParams &pp, cudaStream_t st) {
         configured = true;
     }
     const int grid = lpk_sm_count() * kOcc;
-    CUDA_TRY(cudaMemsetAsync(pp.unit_ctr, 0, sizeof(uint32_t), st), "tick_pass work counter");
+    if (!pp.unit_ctr_next) CUDA_TRY(cudaMemsetAsync(pp.unit_ctr, 0, sizeof(uint32_t), st), "tick_pass work counter");
     k_tick_pass<kDeaths, kRI, kSIA, kWarps, kOcc><<<grid, kWarps * 32, L::kBytes, st>>>(pp);
     return LPK_OK;
 }
@@ -741,6 +743,8 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
     pp.P = P;
     pp.A = A;
     pp.unit_ctr = A.work_counter;
+    pp.unit_ctr_next = A.work_counter_next;
+    REQUIRE(A.work_counter_next != A.work_counter, "tick_pass work counters must differ");
     for (int r = 0; r < 10; ++r) {
         pp.rk[2 * r] = (uint32_t)A.seed + (uint32_t)r * 0x9E3779B9u;
         pp.rk[2 * r + 1] = (uint32_t)(A.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -964,7 +968,7 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
-                         int32_t node_lo, int32_t node_hi);
+                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
@@ -988,5 +992,5 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
                                 a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true, a.node_hi > 0 ? a.node_lo : 0,
-                                a.node_hi > 0 ? a.node_hi : a.n_nodes);
+                                a.node_hi > 0 ? a.node_hi : a.n_nodes, a.xchg_flags, a.xchg_world, a.xchg_seq);
 }

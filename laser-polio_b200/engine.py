@@ -21,7 +21,7 @@ import torch
 
 from . import _lpk
 from . import kernels as K
-from ._lpk import F_DEATHS, F_PENDING, F_RI, F_SIA, F_STAGES, NodeArgs, People, TickArgs, check, dp, stream_handle
+from ._lpk import F_DEATHS, F_RI, F_SIA, Day, People, Rows, Run, check, dp, stream_handle
 
 
 def eligible(sim) -> bool:
@@ -111,8 +111,36 @@ class FusedEngine:
         P.rec = dp(self.rec)
         P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
+        self.use_graph = bool(getattr(sim, "cuda_graph", False))
+        self.xchg = self._open_exchange()
+        self._template()
         if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
             self.rebase_tallies(sim.t)
+
+    def _open_exchange(self):
+        """Peer-memory tally exchange of a node-sharded run (include/lpk.h, lpk_xchg): every rank's receive buffer is
+        mapped into every other rank through CUDA IPC.  Used when the shard's process group runs on NCCL (one process per
+        GPU); other groups (gloo in the tests, several ranks on one GPU) keep torch.distributed's all-reduce."""
+        import os
+
+        sim = self.sim
+        if sim.shard is None or sim.shard.world <= 1 or os.environ.get("LPK_XCHG", "1") == "0":
+            return None
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(sim.shard.group) != "nccl":
+            return None
+        lib = _lpk.lib()
+        x, handle = C.c_void_p(), (C.c_char * _lpk.XCHG_HANDLE_BYTES)()
+        check(lib.lpk_xchg_create(C.c_int32(sim.shard.rank), C.c_int32(sim.shard.world), C.c_int64(self.dev.n_nodes * self.dev.n_strains),
+                                  C.byref(x), handle), "lpk_xchg_create")
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.dev.device)
+        every = [torch.empty_like(mine) for _ in range(sim.shard.world)]
+        dist.all_gather(every, mine, group=sim.shard.group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
+        check(lib.lpk_xchg_connect(x, blob), "lpk_xchg_connect")
+        dist.barrier(group=sim.shard.group)
+        return x
 
     # ------------------------------------------------------------------ helpers
     def rebuild_tiles(self, first_agent: int):
@@ -244,106 +272,141 @@ class FusedEngine:
         out["ok"] = all(out.values())
         return out
 
-    def fused_tick(self, t):
+    # ------------------------------------------------------------------ the run template (include/lpk.h, lpk_run)
+    def _template(self):
+        """Everything a fused day needs that does not change from tick to tick, laid out once as liblpk's ``lpk_run``:
+        lpk_run_days derives each day's births / pass / node arguments from it, so a day costs the host its launches only."""
         sim, dev, pars = self.sim, self.dev, self.sim.pars
-        if not self.hot_valid:  # the table was settled behind the engine's back (verify()): finish and re-base
-            self.drain()
-            self.rebase_tallies(t)
         n, ns = dev.n_nodes, dev.n_strains
-        tx = self.by_name["Transmission_ABM"]
-        ri = self.by_name.get("RI_ABM")
-        vd = self.by_name.get("VitalDynamics_ABM")
-        is_vd = vd is not None and t % vd.step_size == 0
-        flags = F_STAGES | (F_PENDING if self.pending else 0) | (F_DEATHS if is_vd else 0)
-        if is_vd:  # births first: the cohort takes part in this tick's tally (reference: VitalDynamics runs first)
-            if pars.cbr is None:
-                raise ValueError("VitalDynamics_ABM needs pars.cbr")
-            b = vd.births_args(dev, t, self.tile_node, tallies=(self.sus, self.expo, self.hist),
-                               hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, self.ri_lazy_k, self.ri_step, self.ri_k, self.rec))
-            K.STATS.record("vd_births", lambda: check(_lpk.lib().lpk_vd_births(C.byref(b), stream_handle()), "lpk_vd_births"), 3)
-        A = TickArgs()
-        A.tick, A.n_nodes, A.n_strains = t, n, ns
+        R = Run()
+        R.people = self.P
+        A = R.tick
+        A.n_nodes, A.n_strains = n, ns
         A.seed, A.id_base = int(pars.seed) & 0xFFFFFFFFFFFFFFFF, sim.id_base
         A.counts = dp(dev.counts)
         A.q_prev, A.cdf_prev = dp(self.q), dp(self.cdf)
-        tp = max(t - 1, 0)
-        A.new_exposed_prev, A.new_exposed_by_strain_prev = dp(self._row("new_exposed", tp)), dp(self._row("new_exposed_by_strain", tp))
         A.tx_hits, A.tx_hits_by_strain, A.R_cur = dp(self.tx_hits), dp(self.tx_hits_s), dp(self.R_cur)
         A.E_cur, A.I_cur = dp(self.E_cur), dp(self.I_cur)
         A.p_paralysis = float(np.float32(pars.p_paralysis))
-        A.new_potential, A.new_paralyzed = dp(self._row("new_potentially_paralyzed", t)), dp(self._row("new_paralyzed", t))
         A.deaths, A.dead_pp, A.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
-        A.ri_step, A.ri_lazy_k = self.ri_step, self.ri_lazy_k
-        is_ri = ri is not None and pars["vx_prob_ri"] is not None and t % ri.step_size == 0
-        if is_ri:
-            flags |= F_RI
+        A.ri_step = self.ri_step
+        ri = self.by_name.get("RI_ABM")
+        self.ri_active = ri is not None and pars["vx_prob_ri"] is not None
+        if self.ri_active:
             p_ri, p_ipv = ri._probs(dev)
             A.ri_strain = 2 if "nOPV" in getattr(pars, "ri_vaccine_type", "tOPV") else 1
             A.vx_prob_ri, A.vx_prob_ipv = dp(p_ri), dp(p_ipv)
-            A.ri_vaccinated, A.ri_protected = dp(self._row("ri_vaccinated", t)), dp(self._row("ri_protected", t))
-            A.ipv_vaccinated = dp(self._row("ipv_vaccinated", t))
-            A.new_exposed, A.new_exposed_by_strain = dp(self._row("new_exposed", t)), dp(self._row("new_exposed_by_strain", t))
-            A.ri_new_exposed_by_strain = dp(self._row("ri_new_exposed_by_strain", t))
-        events = self.sia_events(t)
-        if events:  # exactly one (needs_components): the campaign runs inside the pass, after RI, like SIA_ABM.step
-            flags |= F_SIA
-            targeted, vx_prob, vx_eff, lo, hi, vstrain = self.by_name["SIA_ABM"].event_args(dev, events[0])
-            A.sia_targeted, A.vx_prob_sia, A.sia_vx_eff = dp(targeted), dp(vx_prob), float(vx_eff)
-            A.sia_min_age, A.sia_max_age, A.sia_strain, A.sia_event_idx = int(lo), int(hi), int(vstrain), 0
-            A.sia_vaccinated, A.sia_protected = dp(self._row("sia_vaccinated", t)), dp(self._row("sia_protected", t))
-            A.sia_new_exposed_by_strain = dp(self._row("sia_new_exposed_by_strain", t))
-            A.new_exposed, A.new_exposed_by_strain = dp(self._row("new_exposed", t)), dp(self._row("new_exposed_by_strain", t))
-        for s, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
-            A.strain_r0_scalars[s] = float(v)
-        beta_fx, exposure_fx, sus, risk_hist = self.beta, self.expo, self.sus, self.hist
-        A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(beta_fx), dp(exposure_fx), dp(sus), dp(risk_hist)
-        A.flags = flags
+        for k, v in enumerate(list(pars.strain_r0_scalars.values())[:ns]):
+            A.strain_r0_scalars[k] = float(v)
+        A.beta_fx, A.exposure_fx, A.sus, A.risk_hist = dp(self.beta), dp(self.expo), dp(self.sus), dp(self.hist)
         A.uniform_agents = self.uniform_agents
-        A.work_counter = dp(self.work_counter)
-        K.STATS.record("tick_pass", lambda: check(_lpk.lib().lpk_tick_pass(C.byref(self.P), C.byref(A), stream_handle()), "lpk_tick_pass"), 1)
-
-        if sim.shard is not None:  # the one per-tick exchange: sum of the nodes x strains infectivity tally
-            from . import sharding
-
-            self.beta_sum.copy_(self.beta)  # the carried tally stays local; the node math sees the sum over ranks
-            beta_fx = self.beta_sum
-            sharding.allreduce_tally(beta_fx, sim.shard)
-        N = NodeArgs()
-        N.flags, N.tick, N.n_nodes, N.n_strains = flags, t, n, ns
+        N = R.node
+        N.n_nodes, N.n_strains, N.seed = n, ns, A.seed
         if sim.shard is not None:  # the node kernels touch this rank's nodes only: 1 / world of the network per tick
             N.node_lo, N.node_hi = int(sim.shard.node_lo), int(sim.shard.node_hi)
-        N.seed = A.seed
-        N.beta_fx, N.exposure_fx, N.risk_hist = dp(beta_fx), dp(exposure_fx), dp(risk_hist)
-        net = dev.network_tensor(tx.network)
-        N.network, N.r0_scalars = dp(net), dp(tx._r0_scalars_dev(dev))
-        if self._rowsum_of is net:  # the row sums in self.rowsum belong to this very matrix: do not re-read it
-            N.flags |= _lpk.F_ROWSUMS
-        self._rowsum_of = net
-        N.beta_seasonality = float(self._seasonality())
+        N.beta_fx, N.exposure_fx, N.risk_hist = dp(self.beta), dp(self.expo), dp(self.hist)
         N.zero_inflation, N.dispersion = float(pars.node_seeding_zero_inflation), float(pars.node_seeding_dispersion)
         N.q, N.strain_cdf, N.prob, N.expected, N.rowsum_ws = dp(self.q), dp(self.cdf), dp(self.prob), dp(self.expected), dp(self.rowsum)
-        if vd is not None:  # pop[t] = pop[t-1] (+ births[t] - deaths on vital-dynamics ticks), model.py:1694, 1751-1755
-            r = dev.res
-            N.pop_prev, N.pop = dp(r["pop"][t - 1]), dp(r["pop"][t])
-            if is_vd:
-                N.births_row, N.deaths_row = dp(r["births"][t]), dp(r["deaths"][t])
-        else:  # nobody maintains results.pop: rows after 0 stay zero, the rate is divided by max(0, 1)
-            N.pop_prev, N.pop = dp(dev.pop_row(t)), None
         N.deaths, N.dead_pp, N.dead_par = dp(self.deaths), dp(self.dead_pp), dp(self.dead_par)
         N.cur_potp, N.cur_p = dp(self.cur_potp), dp(self.cur_p)
-        N.new_potential, N.new_paralyzed = A.new_potential, A.new_paralyzed
-        N.potp_row, N.p_row = dp(self._row("potentially_paralyzed", t)), dp(self._row("paralyzed", t))
-        N.E_by_strain_prev, N.I_by_strain_prev = dp(self._row("E_by_strain", tp)), dp(self._row("I_by_strain", tp))
-        N.E_prev, N.I_prev = dp(self._row("E", tp)), dp(self._row("I", tp))
         N.E_cur, N.I_cur, N.E_snap, N.I_snap = dp(self.E_cur), dp(self.I_cur), dp(self.E_snap), dp(self.I_snap)
         N.tx_hits_by_strain = dp(self.tx_hits_s)
         N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
-        N.S_prev, N.R_prev = dp(self._row("S", tp)), dp(self._row("R", tp))
         N.counts = dp(dev.counts)
+        vd = self.by_name.get("VitalDynamics_ABM")
+        if vd is not None and pars.cbr is not None:
+            R.births = vd.births_args(dev, 1, self.tile_node, tallies=(self.sus, self.expo, self.hist),
+                                      hot=(self.hot, self.pair_min_dod, int(self.P.risk_e0), self.pair_ri_max, 0, self.ri_step, self.ri_k, self.rec))
+        elif vd is not None:  # the component is there but cannot create anybody: its rows are still maintained; a
+            R.births.capacity = -1  # vital-dynamics tick raises (ValueError, like the component's step)
+        for name in Rows.NAMES:
+            setattr(R.rows, name, dp(dev.res.get(name)))
+        R.rows.sink = dp(self.dummy_row)
+        R.zero_pop = dp(dev.zero_pop)
+        R.any_cases = dp(self.cases_dev) if self.stop_rule else None
+        R.work_counters = dp(self.work_counter)
+        R.xchg = self.xchg
+        R.graph = 1 if (self.use_graph and not self.stop_rule) else 0
+        self.R = R
+
+    def _days(self, t0, n_days):
+        """``lpk_day`` array for ticks t0 .. t0 + n_days - 1 (flags, seasonality, the day's single campaign event) and the
+        per-span refresh of what the reference re-reads from host attributes (the network, r0_scalars)."""
+        from . import utils
+
+        sim, dev, pars, R = self.sim, self.dev, self.sim.pars, self.R
+        tx = self.by_name["Transmission_ABM"]
+        vd, ri = self.by_name.get("VitalDynamics_ABM"), self.by_name.get("RI_ABM")
+        net = dev.network_tensor(tx.network)
+        if self._rowsum_of is not net:  # a new matrix: its row sums are recomputed by the first node kernel that sees it
+            R.rowsums_valid = 0
+            self._rowsum_of = net
+        R.node.network, R.node.r0_scalars = dp(net), dp(tx._r0_scalars_dev(dev))
+        days = (Day * n_days)()
+        n_vd = 0
+        t_saved = sim.t
+        for k in range(n_days):
+            t, d = t0 + k, days[k]
+            flags = 0
+            if vd is not None and t % vd.step_size == 0:
+                if pars.cbr is None:
+                    raise ValueError("VitalDynamics_ABM needs pars.cbr")
+                flags |= F_DEATHS
+                n_vd += 1
+            if self.ri_active and t % ri.step_size == 0:
+                flags |= F_RI
+            events = self.sia_events(t)
+            if events:  # exactly one (needs_components): the campaign runs inside the pass, after RI, like SIA_ABM.step
+                flags |= F_SIA
+                targeted, vx_prob, vx_eff, lo, hi, vstrain = self.by_name["SIA_ABM"].event_args(dev, events[0])
+                R.tick.vx_prob_sia = dp(vx_prob)
+                d.sia_targeted, d.sia_vx_eff = dp(targeted), float(vx_eff)
+                d.sia_min_age, d.sia_max_age, d.sia_strain = int(lo), int(hi), int(vstrain)
+            sim.t = t
+            d.tick, d.flags, d.beta_seasonality = t, flags, float(utils.get_seasonality(sim))
+        sim.t = t_saved
+        return days, n_vd
+
+    def run_days(self, t0, n_days):
+        """Ticks t0 .. t0 + n_days - 1 as fused days, launched from C back to back (lpk_run_days); none of them may need the
+        components (needs_components).  Does not advance sim.t."""
+        sim, R = self.sim, self.R
+        if not self.hot_valid:  # the table was settled behind the engine's back (verify()): finish and re-base
+            self.drain()
+            self.rebase_tallies(t0)
+        days, n_vd = self._days(t0, n_days)
+        R.pending, R.ri_lazy_k = int(self.pending), int(self.ri_lazy_k)
+        launches = C.c_int64(0)
+        lib = _lpk.lib()
+        st = K.STATS
+        if sim.shard is not None and sim.shard.world > 1 and self.xchg is None:
+            # no peer-memory exchange (gloo / CPU-side process groups): the tally is summed by torch.distributed between
+            # the two halves of every day
+            from . import sharding
+
+            for k in range(n_days):
+                st.record("tick_pass", lambda k=k: check(lib.lpk_run_day_pass(C.byref(R), C.byref(days[k]), C.byref(launches), stream_handle()),
+                                                        "lpk_run_day_pass"), 0)
+                self.beta_sum.copy_(self.beta)  # the carried tally stays local; the node math sees the sum over ranks
+                sharding.allreduce_tally(self.beta_sum, sim.shard)
+                st.record("tick_node", lambda k=k: check(lib.lpk_run_day_node(C.byref(R), C.byref(days[k]), _lpk.ptr(self.beta_sum),
+                                                                              C.byref(launches), stream_handle()), "lpk_run_day_node"), 0)
+        else:
+            ms = (C.c_float * (3 * n_days))() if st.timing else None
+            check(lib.lpk_run_days(C.byref(R), days, C.c_int32(n_days), ms, C.byref(launches), stream_handle()), "lpk_run_days")
+            for name, cnt in (("tick_pass", n_days), ("tick_node", n_days), ("vd_births", n_vd)):
+                if cnt:
+                    st.calls[name] = st.calls.get(name, 0) + cnt
+            if ms is not None:
+                for k in range(n_days):
+                    if days[k].flags & F_DEATHS:
+                        st.times.setdefault("vd_births", []).append(ms[3 * k])
+                    st.times.setdefault("tick_pass", []).append(ms[3 * k + 1])
+                    st.times.setdefault("tick_node", []).append(ms[3 * k + 2])
+        st.launches += int(launches.value)
+        self.pending, self.ri_lazy_k = bool(R.pending), int(R.ri_lazy_k)
         if self.stop_rule:
-            N.any_cases = self.cases_dev[t:].data_ptr()
-        K.STATS.record("tick_node", lambda: check(_lpk.lib().lpk_tick_node(C.byref(N), stream_handle()), "lpk_tick_node"), 2)
-        if self.stop_rule:
+            t = t0 + n_days - 1
             flag = self.cases_dev[t:t + 1]
             if sim.shard is not None and sim.shard.world > 1:
                 import torch.distributed as dist
@@ -353,9 +416,28 @@ class FusedEngine:
             evt = torch.cuda.Event()
             evt.record()
             self.cases_evt = {t: evt}
-        self.pending = True
-        if is_ri:
-            self.ri_lazy_k += 1
+
+    def fused_span(self, t0, t_end) -> int:
+        """How many consecutive ticks from t0 (below t_end) can run as one lpk_run_days call."""
+        if self.stop_rule:  # the host decides tick by tick (one tick behind the device)
+            return 0 if self.needs_components(t0) else 1
+        n = 0
+        while t0 + n < t_end and not self.needs_components(t0 + n):
+            n += 1
+        return n
+
+    def close(self):
+        """Release the peer-memory exchange (collective: every rank of the shard group calls it)."""
+        _lpk.lib().lpk_run_release()
+        if self.xchg is not None:
+            import torch.distributed as dist
+
+            lib = _lpk.lib()
+            lib.lpk_xchg_disconnect(self.xchg)
+            dist.barrier(group=self.sim.shard.group)
+            lib.lpk_xchg_destroy(self.xchg)
+            self.xchg = None
+            self.R.xchg = None
 
     def _seasonality(self):
         from . import utils
@@ -377,5 +459,18 @@ class FusedEngine:
             if self.stop_rule:
                 self.early_stop_rule(t)
             with sim.perf_stats.start("FusedTick.step()"):
-                self.fused_tick(t)
+                self.run_days(t, 1)
         sim.t += 1
+
+    def advance(self, t_end):
+        """Ticks sim.t .. t_end - 1 (or up to an early stop): fused days in spans launched from C, the days in between
+        through the components.  What SEIR_ABM.run() and run_ticks() drive."""
+        sim = self.sim
+        while sim.t < t_end and not (sim.t > 1 and sim.should_stop):
+            n = self.fused_span(sim.t, t_end)
+            if n <= 1 or self.stop_rule:
+                self.tick(sim.t)
+                continue
+            with sim.perf_stats.start("FusedTick.step()"):
+                self.run_days(sim.t, n)
+            sim.t += n

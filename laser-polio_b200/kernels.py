@@ -156,10 +156,11 @@ class LaunchStats:
         self.launches = 0
         self.calls = {}
         self.events = {}
+        self.times = {}  # name -> [ms]: launches timed by liblpk itself (lpk_run_days brackets them with its own events)
 
     def record(self, name, fn, n_kernels):
         """Run ``fn`` (a liblpk launch), counting it and, when timing is on, bracketing it with CUDA events."""
-        self.launches += n_kernels
+        self.launches += n_kernels  # 0: the call counts its own launches
         self.calls[name] = self.calls.get(name, 0) + 1
         if not self.timing:
             return fn()
@@ -173,7 +174,9 @@ class LaunchStats:
     def summary(self):
         """{name: (calls, mean_ms)}; synchronises the device."""
         torch.cuda.synchronize()
-        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1)) for k, v in self.events.items()}
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1)) for k, v in self.events.items()}
+        out.update({k: (len(v), sum(v) / max(len(v), 1)) for k, v in self.times.items()})
+        return out
 
 
 STATS = LaunchStats()

@@ -201,3 +201,28 @@ def test_step_tick_resume_after_to_host(lp, pyramid):
     parts.to_host()
     assert np.array_equal(snapshot, whole.results.S[19])
     assert_identical(whole, parts)
+
+
+def test_graph_launched_spans_equal_stream_launched(lp, pyramid):
+    """lpk_run_days with lpk_run.graph: every span of fused days captured into one CUDA graph -- same results."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    plain = make(lp, pyramid, True, comps, sia_schedule=[dict(e) for e in SIA_DAYS], dur=35)
+    plain.run()
+    graph = make(lp, pyramid, True, comps, sia_schedule=[dict(e) for e in SIA_DAYS], dur=35)
+    graph.cuda_graph = True
+    graph.run()
+    assert_identical(plain, graph)
+    assert graph.results.sia_protected.sum() > 0 and graph.results.births.sum() > 0
+
+
+def test_run_ticks_in_pieces_equals_one_run(lp, pyramid):
+    """run_ticks(n) leaves the population resident: spans of 1, 3 and the rest give the same answer as run()."""
+    comps = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    whole = make(lp, pyramid, True, comps)
+    whole.run()
+    parts = make(lp, pyramid, True, comps)
+    for n in (1, 1, 3, 9, 1, 100):
+        parts.run_ticks(n)
+    parts.to_host()
+    assert parts.t == whole.t
+    assert_identical(whole, parts)
