@@ -319,9 +319,9 @@ def run_b200(args):
     census = {
         "E_equals_sum_by_strain": bool(np.array_equal(r.E[:sim.t], r.E_by_strain[:sim.t].sum(axis=2))),
         "I_equals_sum_by_strain": bool(np.array_equal(r.I[:sim.t], r.I_by_strain[:sim.t].sum(axis=2))),
-        "pop_bookkeeping": bool(np.array_equal(r.pop[t_last], r.pop[0] + r.births[: sim.t].sum(axis=0) - r.deaths[: sim.t].sum(axis=0))),
     }
-    own = slice(sim.shard.node_lo, sim.shard.node_hi) if sim.shard is not None else slice(None)
+    own = slice(sim.shard.node_lo, sim.shard.node_hi) if sim.shard is not None else slice(None)  # a rank maintains the rows of its nodes
+    census["pop_bookkeeping"] = bool(np.array_equal(r.pop[t_last, own], (r.pop[0] + r.births[: sim.t].sum(axis=0) - r.deaths[: sim.t].sum(axis=0))[own]))
     st = sim.people.disease_state[: sim.people.count]
     census["census_row_equals_table"] = bool(
         int((st == 0).sum()) == int(r.S[t_last, own].sum()) and int((st == 1).sum()) == int(r.E[t_last, own].sum())

@@ -45,19 +45,26 @@ RESULT_KEYS = ("S", "E", "I", "R", "E_by_strain", "I_by_strain", "new_exposed", 
                "sia_vaccinated", "sia_protected", "sia_new_exposed_by_strain")
 
 
-def gpu_rank(rank, world, port, workdir, fused):
-    """One rank of the single-GPU sharded run: both ranks share cuda:0, the tally all-reduce goes over gloo."""
+def gpu_rank(rank, world, port, workdir, fused, backend="gloo"):
+    """One rank of a sharded run.  gloo: both ranks share cuda:0 and the tally all-reduce goes through torch.distributed;
+    nccl: one GPU per rank, the tally travels through the peer-memory exchange of liblpk (lpk_xchg) on fused days."""
     import torch
     import torch.distributed as dist
 
     import laser_polio_b200 as lp
 
-    torch.cuda.set_device(0)
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.cuda.set_device(rank if backend == "nccl" else 0)
+    kw = {"device_id": torch.device(f"cuda:{rank}")} if backend == "nccl" else {}
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, **kw)
     np.random.seed(0)
     sim = make_sim(lp, os.path.join(workdir, "pyramid.csv"))
     sim.fused = fused
     shard = sim.shard_to(rank, world)
+    sim.to_device()
+    sim.step_tick(0)
+    sim.step_tick(1)  # creates the engine: is the tally exchange the one this backend should get?
+    if fused:
+        assert (sim._engine.xchg is not None) == (backend == "nccl"), "peer-memory exchange"
     sim.run()
     out = {k: getattr(sim.results, k) for k in RESULT_KEYS}
     out["node_lo"], out["node_hi"], out["id_base"], out["count"] = shard.node_lo, shard.node_hi, sim.id_base, sim.people.count

@@ -24,13 +24,25 @@ def free_port():
 def test_two_shards_equal_one_table(tmp_path, fused):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+    two_shards_vs_one_table(tmp_path, fused, "gloo")
+
+
+def test_two_shards_on_two_gpus_peer_memory_exchange(tmp_path):
+    """One rank per GPU over NCCL: on fused days the tally goes through liblpk's peer-memory exchange (CUDA IPC + NVLink
+    stores + system-scope flags) instead of an all-reduce call.  Needs two GPUs (gpurun --gpus 2); skipped on one."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    two_shards_vs_one_table(tmp_path, True, "nccl")
+
+
+def two_shards_vs_one_table(tmp_path, fused, backend):
     import torch.multiprocessing as mp
 
     import laser_polio_b200 as lp
     from sharded_worker import RESULT_KEYS, gpu_rank, make_sim, pyramid_file
 
     pyr = pyramid_file(tmp_path / "pyramid.csv")
-    mp.spawn(gpu_rank, args=(2, free_port(), str(tmp_path), fused), nprocs=2, join=True)
+    mp.spawn(gpu_rank, args=(2, free_port(), str(tmp_path), fused, backend), nprocs=2, join=True)
     ranks = [dict(np.load(tmp_path / f"rank{r}_{int(fused)}.npz")) for r in range(2)]
 
     # the same population as one table with the shards' global ids
