@@ -52,6 +52,7 @@ extern "C" {
 #define LPK_STAGE_BIRTH 6u
 #define LPK_STAGE_LIFESPAN 7u
 #define LPK_STAGE_EXPOSE_LO 8u /* low half of the exposure word, generated only when the high half cannot decide */
+#define LPK_STAGE_NODE_VAR 9u  /* node-level variance multiplier of the exposure count (lpk_tx_node_math) */
 
 typedef struct lpk_rng {
     uint64_t seed;      /* Philox key */
@@ -128,11 +129,17 @@ int lpk_tx_step_prep(int32_t num_nodes, int64_t num_people, int32_t n_strains, c
  *     The reference then draws an integer count per node on the host (Poisson; zero-inflated NB for nodes without
  *     local infectivity) and tx_infect_nb picks that many susceptibles by successive weighted sampling, which selects
  *     agent i with probability 1 - exp(-w_i tau), tau fixed by the count.  Here the node's scale is solved for the
- *     EXPECTED count instead:   sum_{i in S_n} (1 - exp(-w_i tau[n])) = expected[n] * g_n   (on risk_hist),
- *     g_n = 1 with local infectivity, else 0 w.p. zero_inflation, else Gamma(r, 1/r) / (1 - zero_inflation),
- *     r = max(1, round(dispersion)) (the ZINB as a zero-inflated gamma-Poisson mixture), so that independent per-agent
- *     trials (lpk_tx_infect) have the reference's per-agent marginals and node means.  tau = 3e38 means "everybody"
- *     (expected >= susceptibles - 0.5; the reference takes min(count, susceptibles)).
+ *     EXPECTED count instead:   sum_{i in S_n} (1 - exp(-w_i tau[n])) = T_n   (on risk_hist, bin centres rescaled so that
+ *     their sum is the exact risk sum exposure[n]), with
+ *       E1 = expected[n] * g_n,  g_n = 1 with local infectivity, else 0 w.p. zero_inflation, else
+ *            Gamma(r, 1/r) / (1 - zero_inflation), r = max(1, round(dispersion)) (the ZINB as a zero-inflated
+ *            gamma-Poisson mixture; draws Philox(seed; node, k, tick, NODE));
+ *       E2 = E1 * g2, g2 a unit-mean gamma that supplies the variance independent trials lack against the reference's
+ *            count min(K, S), K ~ Poisson(E1): CV^2 = (Var[min(K, S)] - T (1 - T / S_eff)) / (P(K < S) E1)^2,
+ *            S_eff = (sum w)^2 / sum w^2 (draws Philox(seed; node, k, tick, NODE_VAR); 1 / S_eff when E1 << S);
+ *       T_n = E[min(Poisson(E2), S_n)]  -- the reference's mean count, = E2 unless the node is close to saturation.
+ *     Independent per-agent trials (lpk_tx_infect) then have the reference's per-agent marginals, node mean and node
+ *     variance.  tau = 3e38 means "everybody" (T_n = S_n; the reference takes min(count, susceptibles)).
  *       network        double[num_nodes * num_nodes] row-major, W[i,j] = fraction moving i -> j
  *       r0_scalars     double[num_nodes];  alive_counts int32[num_nodes] (results.pop[t], model.py:1344)
  *     outputs: tau float[num_nodes], strain_cdf double[num_nodes * n_strains] (cumulative p[n,s] / P_n),

@@ -615,16 +615,114 @@ __device__ double importation_multiplier(uint64_t seed, uint32_t node, uint32_t 
     }
 }
 
-// tau[j]: sum over the node's susceptibles of (1 - exp(-risk * tau)) = E, on the risk histogram.
+// ---- how many exposures a node should realise: matching the reference's count law ---------------------------------
+// Reference (model.py:1368-1407, 1096-1122): K ~ Poisson(E) (ZINB for importation-only nodes = Poisson mixed over a
+// zero-inflated gamma, drawn by importation_multiplier), and exactly min(K, S) distinct susceptibles are picked.  The device
+// runs independent per-agent trials with probabilities p_i = 1 - exp(-w_i tau), whose count is Poisson-binomial: mean
+// sum p_i, variance V_own = sum p_i (1 - p_i).  tau is therefore solved for  T = E[min(K, S)]  (not for E: a node with one
+// susceptible and E = 0.5 is exposed with probability 1 - exp(-0.5), as in the reference, and T -> S smoothly as E passes
+// S), and the variance the independent trials lack against Var[min(K, S)] is supplied by one more unit-mean gamma
+// multiplier g2 on E (delta method: Var[T(g2 E)] ~ (dT/dE)^2 E^2 CV^2, dT/dE = P(K < S)):
+//     CV^2 = min((Var[min(K, S)] - V_own) / (P(K < S) E)^2, 1 / (S_eff - 1)) P(K < S)^2,   S_eff = (sum w)^2 / sum w^2.
+// Far from saturation this is exactly 1 / S_eff-ish and restores the Poisson variance; as the node saturates the response
+// T(E) becomes strongly concave, so the top-up fades with P(K < S)^2 and the remaining concavity is compensated to second
+// order (T'' = -P(K = S - 1)) to keep the mean at T(E).  tests/test_count_law.py holds mean and variance to the reference's.
+struct PoisMin {
+    double T, Pless, V, Plast;  // E[min(K, S)], P(K < S), Var[min(K, S)], P(K = S - 1)
+};
+// warp-collective; S integer-valued >= 1, e > 0.  Sums over the 24-sigma window below S in 32 chunks (recurrence per lane).
+__device__ PoisMin poisson_min_moments(double e, double S, int lane) {
+    PoisMin m;
+    const double sd = sqrt(e);
+    m.Plast = 0.0;
+    if (S > e + 12.0 * sd + 12.0) { m.T = e; m.Pless = 1.0; m.V = e; return m; }
+    if (S < e - 12.0 * sd - 12.0) { m.T = S; m.Pless = 0.0; m.V = 0.0; return m; }
+    const double lo = floor(e - 12.0 * sd - 12.0);
+    const long long k0 = lo > 0.0 ? (long long)lo : 0ll, k1 = (long long)S;  // k in [k0, k1)
+    const long long n = k1 - k0, chunk = (n + 31) / 32;
+    const long long ka = k0 + lane * chunk, kb = (ka + chunk < k1) ? ka + chunk : k1;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;  // sums of pmf, (S - k) pmf, (S - k)^2 pmf; pmf(S - 1)
+    if (ka < kb) {
+        double p = exp((double)ka * log(e) - e - lgamma((double)ka + 1.0));
+        for (long long k = ka; k < kb; ++k) {
+            const double d = S - (double)k;
+            b0 += p; b1 += d * p; b2 += d * d * p;
+            if (k == k1 - 1) b3 = p;
+            p *= e / (double)(k + 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        b0 += __shfl_xor_sync(LPK_FULL, b0, o); b1 += __shfl_xor_sync(LPK_FULL, b1, o); b2 += __shfl_xor_sync(LPK_FULL, b2, o);
+        b3 += __shfl_xor_sync(LPK_FULL, b3, o);
+    }
+    b0 = __shfl_sync(LPK_FULL, b0, 0); b1 = __shfl_sync(LPK_FULL, b1, 0); b2 = __shfl_sync(LPK_FULL, b2, 0);
+    m.Plast = __shfl_sync(LPK_FULL, b3, 0);
+    m.T = S - b1;                       // E[min] = S - E[(S - K)+]
+    m.Pless = b0 < 1.0 ? b0 : 1.0;
+    m.V = fmax(b2 - b1 * b1, 0.0);      // Var[min] = Var[(S - K)+]
+    return m;
+}
+__device__ double node_uniform_var(uint64_t seed, uint32_t node, uint32_t k, uint32_t tick, int pair) {
+    uint32_t x[4];
+    philox4x32_10(node, k, tick, LPK_STAGE_NODE_VAR, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+    return pair ? u53(x[2], x[3]) : u53(x[0], x[1]);
+}
+// Gamma(shape, scale = 1 / shape): unit mean, CV^2 = 1 / shape.  Marsaglia-Tsang; shape < 1 through Gamma(shape + 1) U^(1/shape).
+__device__ double unit_gamma(uint64_t seed, uint32_t node, uint32_t tick, double shape) {
+    const double a = shape < 1.0 ? shape + 1.0 : shape;
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    uint32_t k = 1;
+    double g;
+    for (;;) {
+        const double u1 = node_uniform_var(seed, node, k, tick, 0), u2 = node_uniform_var(seed, node, k, tick, 1);
+        const double x = sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.14159265358979323846 * u2);
+        ++k;
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = node_uniform_var(seed, node, k, tick, 0);
+        ++k;
+        if (log(1.0 - u) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+    }
+    if (shape < 1.0) g *= pow(1.0 - node_uniform_var(seed, node, 0, tick, 0), 1.0 / shape);
+    return g / shape;
+}
+
+// tau[j]: sum over the node's susceptibles of (1 - exp(-risk * tau)) = T, on the risk histogram.
 // Successive weighted sampling without replacement of K agents (the reference, model.py:1096-1122) selects agent i with
 // probability 1 - exp(-w_i tau), tau fixed by the count; solving for the EXPECTED count gives independent per-agent
 // trials with the same marginals and the same node mean.  One warp per node, 6 bins per lane; Newton from the left of a
-// concave increasing function converges monotonically.
-__device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double E, int lane) {
-    double h[LPK_RISK_BINS / 32], w[LPK_RISK_BINS / 32];
+// concave increasing function converges monotonically.  The bins' representative weights (bin centres) are rescaled so that
+// their sum equals the exact risk sum of the node's susceptibles (expo): a table whose risks are all equal (no individual
+// heterogeneity) sits on a bin edge, and the centre would be 6 % off.  E: expected exposures x importation multiplier.
+#define TAU_BINS (LPK_RISK_BINS / 32)
+__device__ __forceinline__ double newton_tau(const double (&h)[TAU_BINS], const double (&w)[TAU_BINS], double S, double Wsum, double T) {
+    double t = -log1p(-T / S) * S / Wsum;  // the equal-weights solution: a lower bound of the root (Jensen), tight for small T
+    for (int it = 0; it < 100; ++it) {
+        double F = 0.0, dF = 0.0;
+#pragma unroll
+        for (int i = 0; i < TAU_BINS; ++i) {
+            const double em = expm1(-w[i] * t);
+            F -= h[i] * em;
+            dF += h[i] * w[i] * (em + 1.0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { F += __shfl_xor_sync(LPK_FULL, F, o); dF += __shfl_xor_sync(LPK_FULL, dF, o); }
+        F = __shfl_sync(LPK_FULL, F, 0);
+        dF = __shfl_sync(LPK_FULL, dF, 0);
+        const double step = (T - F) / dF;
+        if (!(step > 0.0)) break;
+        t += step;
+        if (step <= 1e-13 * t) break;
+    }
+    return t;
+}
+__device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double E, double expo, uint64_t seed, uint32_t tick, int lane) {
+    double h[TAU_BINS], w[TAU_BINS];
     double S = 0.0, Wsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < LPK_RISK_BINS / 32; ++i) {
+    for (int i = 0; i < TAU_BINS; ++i) {
         const int b = lane + 32 * i;
         h[i] = (double)hist[(int64_t)j * LPK_RISK_BINS + b];
         w[i] = risk_bin_weight(b);
@@ -635,29 +733,39 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
     for (int o = 16; o > 0; o >>= 1) { S += __shfl_xor_sync(LPK_FULL, S, o); Wsum += __shfl_xor_sync(LPK_FULL, Wsum, o); }
     S = __shfl_sync(LPK_FULL, S, 0);
     Wsum = __shfl_sync(LPK_FULL, Wsum, 0);
-    double t = 0.0;
-    if (E > 0.0 && S > 0.0) {
-        if (E >= S - 0.5) {
-            t = 3.0e38;  // more exposures expected than susceptibles exist: everybody (reference: size = min(K, S))
-        } else {
-            t = E / Wsum;
-            for (int it = 0; it < 64; ++it) {
-                double F = 0.0, dF = 0.0;
+    if (!(E > 0.0) || !(S > 0.0) || !(Wsum > 0.0)) return 0.f;
+    const double c = expo > 0.0 ? expo / Wsum : 1.0;  // first moment of the histogram := the exact risk sum
+    double W1 = 0.0, W2 = 0.0;
 #pragma unroll
-                for (int i = 0; i < LPK_RISK_BINS / 32; ++i) {
-                    const double em = expm1(-w[i] * t);
-                    F -= h[i] * em;
-                    dF += h[i] * w[i] * (em + 1.0);
-                }
+    for (int i = 0; i < TAU_BINS; ++i) { w[i] *= c; W1 += h[i] * w[i]; W2 += h[i] * w[i] * w[i]; }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { F += __shfl_xor_sync(LPK_FULL, F, o); dF += __shfl_xor_sync(LPK_FULL, dF, o); }
-                F = __shfl_sync(LPK_FULL, F, 0);
-                dF = __shfl_sync(LPK_FULL, dF, 0);
-                const double step = (E - F) / dF;
-                if (!(step > 0.0)) break;
-                t += step;
-                if (step <= 1e-13 * t) break;
-            }
+    for (int o = 16; o > 0; o >>= 1) { W1 += __shfl_xor_sync(LPK_FULL, W1, o); W2 += __shfl_xor_sync(LPK_FULL, W2, o); }
+    Wsum = __shfl_sync(LPK_FULL, W1, 0);
+    W2 = __shfl_sync(LPK_FULL, W2, 0);
+    const double Seff = Wsum * Wsum / W2;
+    const PoisMin m = poisson_min_moments(E, S, lane);
+    double T = m.T;
+    if (T >= S * (1.0 - 1e-12)) return 3.0e38f;  // the reference's size = min(K, S) with K >= S: everybody
+    if (!(T > 0.0)) return 0.f;
+    double t = newton_tau(h, w, S, Wsum, T);
+    const double slope = m.Pless * E;
+    if (Seff > 1.0 + 1e-9 && slope > 0.0) {
+        double vown = 0.0;
+#pragma unroll
+        for (int i = 0; i < TAU_BINS; ++i) { const double pb = -expm1(-w[i] * t); vown += h[i] * pb * (1.0 - pb); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vown += __shfl_xor_sync(LPK_FULL, vown, o);
+        vown = __shfl_sync(LPK_FULL, vown, 0);
+        const double v = fmin((m.V - vown) / (slope * slope), 1.0 / (Seff - 1.0)) * m.Pless * m.Pless;
+        if (v > 1e-9) {
+            double g2 = 0.0;
+            if (lane == 0) g2 = unit_gamma(seed, (uint32_t)j, tick, 1.0 / v);
+            g2 = __shfl_sync(LPK_FULL, g2, 0);
+            const double E2 = E * (1.0 + 0.5 * m.Plast * E * v / m.Pless) * g2;
+            T = E2 > 0.0 ? poisson_min_moments(E2, S, lane).T : 0.0;
+            if (T >= S * (1.0 - 1e-12)) return 3.0e38f;
+            if (!(T > 0.0)) return 0.f;
+            t = newton_tau(h, w, S, Wsum, T);
         }
     }
     return (float)(t > 3.0e38 ? 3.0e38 : t);
@@ -822,7 +930,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
     __syncthreads();
     const int jn = j_lo + blockIdx.x * 32 + ty;  // warp ty solves node jn
     if (jn < j_hi) {
-        const float t = solve_tau_warp(jn, hist, stgt[ty], tx);
+        const float t = solve_tau_warp(jn, hist, stgt[ty], (double)exposure_fx[jn] / LPK_FX_SCALE, seed, tick, tx);
         if (tx == 0) tau[jn] = t;
     }
 }

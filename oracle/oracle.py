@@ -30,6 +30,7 @@ FX_SCALE = float(2**30)
 RISK_BINS = 192
 
 STAGE_PARALYSIS, STAGE_RI, STAGE_SIA, STAGE_EXPOSE, STAGE_STRAIN, STAGE_NODE, STAGE_BIRTH, STAGE_LIFESPAN = range(8)
+STAGE_NODE_VAR = 9
 
 
 def build(force: bool = False) -> Path:
@@ -265,25 +266,106 @@ def risk_bin_weights():
     return np.ldexp(1.0 + ((b & 7) + 0.5) / 8.0, (b >> 3) - 12)
 
 
-def solve_tau(hist_row, target):
-    """tau with sum_b hist[b] * (1 - exp(-w_b tau)) = target (Newton from the left; concave increasing -> monotone)."""
-    h = np.asarray(hist_row, np.float64)
-    w = risk_bin_weights()
-    S, Wsum = h.sum(), (h * w).sum()
-    if not (target > 0.0) or S <= 0:
-        return 0.0
-    if target >= S - 0.5:
-        return 3.0e38
-    t = target / Wsum
-    for _ in range(64):
+def poisson_min_moments(e, S):
+    """(E[min(K, S)], P(K < S), Var[min(K, S)], P(K = S - 1)) for K ~ Poisson(e), S a positive integer: the device's
+    windowed sums (lpk_kernels.cu, poisson_min_moments) in float64."""
+    sd = np.sqrt(e)
+    if S > e + 12.0 * sd + 12.0:
+        return e, 1.0, e, 0.0
+    if S < e - 12.0 * sd - 12.0:
+        return float(S), 0.0, 0.0, 0.0
+    from scipy.special import gammaln
+
+    k0 = max(int(np.floor(e - 12.0 * sd - 12.0)), 0)
+    k = np.arange(k0, int(S), dtype=np.float64)
+    pmf = np.exp(k * np.log(e) - e - gammaln(k + 1.0))
+    d = S - k
+    b0, b1, b2 = pmf.sum(), (d * pmf).sum(), (d * d * pmf).sum()
+    return S - b1, min(b0, 1.0), max(b2 - b1 * b1, 0.0), float(pmf[-1])
+
+
+def _node_u_var(seed, node, k, tick, pair):
+    x = philox4x32_10([node, k, tick, STAGE_NODE_VAR], [seed & 0xFFFFFFFF, seed >> 32])
+    hi, lo = (int(x[2]), int(x[3])) if pair else (int(x[0]), int(x[1]))
+    return float((((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0))
+
+
+def unit_gamma(seed, node, tick, shape):
+    """Gamma(shape, 1 / shape) on the node's NODE_VAR stream; mirrors the device function draw for draw."""
+    a = shape + 1.0 if shape < 1.0 else shape
+    d = a - 1.0 / 3.0
+    c = 1.0 / np.sqrt(9.0 * d)
+    k = 1
+    while True:
+        u1, u2 = _node_u_var(seed, node, k, tick, 0), _node_u_var(seed, node, k, tick, 1)
+        x = np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+        k += 1
+        v = 1.0 + c * x
+        if v <= 0:
+            continue
+        v = v * v * v
+        u = _node_u_var(seed, node, k, tick, 0)
+        k += 1
+        if np.log(1.0 - u) < 0.5 * x * x + d - d * v + d * np.log(v):
+            g = d * v
+            break
+    if shape < 1.0:
+        g *= (1.0 - _node_u_var(seed, node, 0, tick, 0)) ** (1.0 / shape)
+    return g / shape
+
+
+def _newton_tau(h, w, S, Wsum, T):
+    """tau with sum_b h[b] (1 - exp(-w[b] tau)) = T, Newton from the equal-weights solution (a lower bound of the root by
+    Jensen; the function is concave increasing, so the iteration is monotone)."""
+    t = -np.log1p(-T / S) * S / Wsum
+    for _ in range(100):
         em = np.expm1(-w * t)
         F, dF = -(h * em).sum(), (h * w * (em + 1.0)).sum()
-        step = (target - F) / dF
+        step = (T - F) / dF
         if not step > 0.0:
             break
         t += step
         if step <= 1e-13 * t:
             break
+    return t
+
+
+def solve_tau(hist_row, E, expo=None, seed=0, node=0, tick=0):
+    """The device's node scale (lpk_kernels.cu, solve_tau_warp).  Bin centres are rescaled to the exact risk sum ``expo``.
+    tau0 solves sum_b hist[b] (1 - exp(-w_b tau)) = T0 = E[min(K, S)], K ~ Poisson(E); the independent trials at tau0 have
+    variance V_own = sum_b hist[b] p_b (1 - p_b); what is missing against Var[min(K, S)] is supplied by a unit-mean gamma
+    multiplier g2 on E with CV^2 = (Var[min(K, S)] - V_own) / (P(K < S) E)^2 (delta method), at most 1 / (S_eff - 1) (its value
+    far from saturation, where the delta method is exact), faded by P(K < S)^2; then tau solves for T = E[min(Poisson(E g2), S)]."""
+    h = np.asarray(hist_row, np.float64)
+    w = risk_bin_weights()
+    S, Wsum = h.sum(), (h * w).sum()
+    if not (E > 0.0) or S <= 0 or not (Wsum > 0.0):
+        return 0.0
+    c = expo / Wsum if (expo is not None and expo > 0.0) else 1.0
+    w = w * c
+    Wsum, W2 = (h * w).sum(), (h * w * w).sum()
+    Seff = Wsum * Wsum / W2
+    T, pless, V, plast = poisson_min_moments(E, S)
+    if T >= S * (1.0 - 1e-12):
+        return 3.0e38
+    if not (T > 0.0):
+        return 0.0
+    t = _newton_tau(h, w, S, Wsum, T)
+    slope = pless * E
+    if Seff > 1.0 + 1e-9 and slope > 0.0:
+        pb = -np.expm1(-w * t)
+        # the top-up fades with P(K < S)^2 as the node saturates: there the response T(E) is strongly concave, the delta
+        # method no longer holds and the mean matters more than the variance; what concavity remains is compensated to second
+        # order (T'' = -P(K = S - 1)) so that the mean over the multiplier stays T(E)
+        v = min((V - (h * pb * (1.0 - pb)).sum()) / (slope * slope), 1.0 / (Seff - 1.0)) * pless * pless
+        if v > 1e-9:
+            E2 = E * (1.0 + 0.5 * plast * E * v / pless) * unit_gamma(seed, node, tick, 1.0 / v)
+            T = poisson_min_moments(E2, S)[0] if E2 > 0.0 else 0.0
+            if T >= S * (1.0 - 1e-12):
+                return 3.0e38
+            if not (T > 0.0):
+                return 0.0
+            t = _newton_tau(h, w, S, Wsum, T)
     return min(t, 3.0e38)
 
 
@@ -291,9 +373,11 @@ def tx_node_math_device(beta_fx, exposure_fx, risk_hist, network, beta_seasonali
                         dispersion, seed, tick):
     """float64 restatement of the DEVICE node step (lpk_tx_node_math): the reference's formulae up to the probability
     and the expected exposures per node (model.py:1332-1351, 1362-1363); then, instead of an integer count draw, the
-    node's exposure scale tau[n] with  sum_{i in S_n} (1 - exp(-w_i tau[n])) = expected[n] * g_n  on the risk histogram,
-    g_n = 1 when the node has local infectivity (sum_s beta_pre > 0), else 0 w.p. zi, else Gamma(r, 1/r) / (1 - zi)
-    (model.py:1381-1393's ZINB as a zero-inflated gamma-Poisson mixture), r = max(1, round(dispersion)).
+    node's exposure scale tau[n] with  sum_{i in S_n} (1 - exp(-w_i tau[n])) = T_n  on the risk histogram, T_n the mean of
+    the reference's count min(K, S_n), K ~ Poisson(expected[n] * g_n * g2_n); g_n = 1 when the node has local infectivity
+    (sum_s beta_pre > 0), else 0 w.p. zi, else Gamma(r, 1/r) / (1 - zi) (model.py:1381-1393's ZINB as a zero-inflated
+    gamma-Poisson mixture), r = max(1, round(dispersion)); g2_n the unit-mean gamma that tops the variance of independent
+    trials up to the reference's (include/lpk.h, T2; solve_tau).
 
     Returns (tau float32[nodes], strain_cdf float64[nodes, strains], prob float64[nodes, strains], expected[nodes]).
     """
@@ -321,7 +405,8 @@ def tx_node_math_device(beta_fx, exposure_fx, risk_hist, network, beta_seasonali
     for n in np.nonzero((local == 0) & (P > 0))[0]:
         g[n] = node_importation_multiplier(int(seed), int(n), int(tick), float(zero_inflation), r)
     expected = exposure * P
-    tau = np.array([solve_tau(risk_hist[n], expected[n] * g[n]) for n in range(prob.shape[0])], np.float64).astype(np.float32)
+    tau = np.array([solve_tau(risk_hist[n], expected[n] * g[n], exposure[n], int(seed), n, int(tick)) for n in range(prob.shape[0])],
+                   np.float64).astype(np.float32)
     return tau, cdf, prob, expected
 
 

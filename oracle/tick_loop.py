@@ -66,13 +66,16 @@ def births(pop_prev, birth_rate, step_size, cum_deaths, count, capacity, seed, t
     return b, np.repeat(np.arange(n, dtype=np.int16), b), dod, count + total, 0
 
 
-def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0_scalars, p_paralysis, tau_of_tick, cdf_of_tick,
+def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0_scalars, p_paralysis, tau_of_tick=None, cdf_of_tick=None,
         vd_step=0, birth_rate=None, cum_deaths=None, pop0=None, ri_step=0, vx_prob_ri=None, vx_prob_ipv=None, ri_strain=1,
-        sia_events=None, node_lo=0, node_hi=None):
+        sia_events=None, node_lo=0, node_hi=None, node_math=None):
     """Ticks 0 .. ticks-1 on the canonical columns ``cols`` (mutated in place).  Returns (results dict of [ticks, nodes(, ns)]
     int32 rows, final count, per-tick tallies {t: (beta_fx, exposure_fx, risk_hist)} for the node-math check).
 
-    sia_events: {tick: [(targeted uint8[nodes], vx_prob float32[nodes], vx_eff, min_age, max_age, strain), ...]}"""
+    sia_events: {tick: [(targeted uint8[nodes], vx_prob float32[nodes], vx_eff, min_age, max_age, strain), ...]}
+    node_math:  instead of tau_of_tick / cdf_of_tick (pass None for both), the inputs of the node step -- {"network", "r0_scalars",
+                "season": callable(t) or float, "zero_inflation", "dispersion"} -- and tau / cdf come from
+                ``oracle.tx_node_math_device`` on the loop's own tallies (a free-running oracle simulation)."""
     i32 = lambda *s: np.zeros(s, np.int32)  # noqa: E731
     names2 = ("S", "E", "I", "R", "new_exposed", "births", "deaths", "pop", "new_potentially_paralyzed", "new_paralyzed",
               "potentially_paralyzed", "paralyzed", "ri_vaccinated", "ri_protected", "ipv_vaccinated", "sia_vaccinated", "sia_protected")
@@ -134,8 +137,15 @@ def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0
         _, _, _, bfx, efx = orc.tx_step_prep(n_nodes, count, ns, c["strain"], srs, c["disease_state"], c["node_id"], c["daily_infectivity"],
                                              c["acq_risk_multiplier"], mode="fx")
         tallies[t] = (bfx, efx, orc.tx_step_prep.last_hist.copy())
+        if node_math is not None:
+            season = node_math["season"]
+            tau, cdf, _, _ = orc.tx_node_math_device(bfx, efx, tallies[t][2], node_math["network"], season(t) if callable(season) else season,
+                                                     node_math["r0_scalars"], r["pop"][t], node_math["zero_inflation"],
+                                                     node_math["dispersion"], seed, t)
+        else:
+            tau, cdf = tau_of_tick[t], cdf_of_tick[t]
         new = orc.tx_infect_bernoulli(n_nodes, count, ns, c["node_id"], c["strain"], c["disease_state"], c["acq_risk_multiplier"],
-                                      np.ascontiguousarray(tau_of_tick[t], np.float32), np.ascontiguousarray(cdf_of_tick[t], np.float64),
+                                      np.ascontiguousarray(tau, np.float32), np.ascontiguousarray(cdf, np.float64),
                                       seed=seed, tick=t, id_base=id_base)
         r["new_exposed"][t] += new.sum(axis=1, dtype=np.int32)
         r["new_exposed_by_strain"][t] += new

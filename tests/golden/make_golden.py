@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 
 import numba as nb  # noqa: E402
 
@@ -205,11 +206,99 @@ def ensemble():
          pop=pop, **out, **{f"in_{k}": p0[k] for k in AGENT_COLS})
 
 
+from make_golden_defs import FULL, full_table  # noqa: E402  (shared with tests/test_ensemble_full.py)
+
+
+def ensemble_full():
+    """Gate 3 on a second shape with every stage of the tick on: 60 nodes, vital dynamics every 7 ticks (the reference's
+    get_deaths; its host-side births block, model.py:1711-1734, restated on numpy's stream with core.KaplanMeierEstimator),
+    disease_state_step, fast_ri every 14, one fast_sia campaign, transmission (tx_step_prep / node block / tx_infect_nb).
+    Stored per seed and node: daily incidence (all new exposures of the tick: RI + SIA + transmission, i.e.
+    results.new_exposed), new_potentially_paralyzed, new_paralyzed."""
+    from laser_polio_b200 import core, utils
+    from oracle import oracle as orc
+
+    nb.set_num_threads(4)
+    ref = ref_loader.load(inject_uniforms=False)
+
+    @nb.njit(parallel=True)
+    def seed_threads(s):
+        for t in nb.prange(nb.get_num_threads()):
+            np.random.seed(s + 7919 * nb.get_thread_id())
+
+    c = FULL
+    p0, node = full_table()
+    n0, nn, ns, ticks, seeds = p0["count"], c["n_nodes"], c["n_strains"], c["ticks"], c["seeds"]
+    srs = np.array([1.0, 0.25, 0.125])
+    km = core.KaplanMeierEstimator(utils.create_cumulative_deaths(int(node["pop0"].sum()), max_age_years=100))
+    birth_rate = np.full(nn, c["cbr"] / (365 * 1000))
+    targeted = np.zeros(nn, np.uint8)
+    targeted[: c["sia_nodes"]] = 1
+    nt = nb.get_num_threads()
+    inc = np.zeros((seeds, ticks, nn), np.int32)
+    potp = np.zeros((seeds, ticks, nn), np.int32)
+    par = np.zeros((seeds, ticks, nn), np.int32)
+    for s in range(seeds):
+        np.random.seed(3000 + s)
+        seed_threads(7000 + 31 * s)
+        p = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p0.items()}
+        cap = len(p["disease_state"])
+        si, sp = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        n = n0
+        pop = node["pop0"].copy()
+        for t in range(1, ticks + 1):
+            if t % c["vd_step"] == 0:
+                tl, dying = np.zeros((nt, nn), np.int32), np.zeros(nn, np.int32)
+                ref["get_deaths"](np.int32(nn), np.int32(n), p["disease_state"], p["node_id"], p["date_of_death"], np.int32(t), tl, dying)
+                expected = c["vd_step"] * birth_rate * pop  # model.py:1712-1716
+                whole = expected.astype(np.int32)
+                births = whole + np.random.binomial(1, expected - whole)
+                total = int(births.sum())
+                if total > 0:
+                    lo, hi = n, n + total
+                    p["date_of_birth"][lo:hi] = t
+                    p["date_of_death"][lo:hi] = t + km.predict_age_at_death(np.zeros(total, np.int32), max_year=100)
+                    p["disease_state"][lo:hi] = 0
+                    p["node_id"][lo:hi] = np.repeat(np.arange(nn, dtype=np.int16), births)
+                    n = hi
+                pop = pop + births - dying
+            a, b = np.zeros(nn, np.int32), np.zeros(nn, np.int32)
+            ref["disease_state_step"](p["node_id"], nn, p["disease_state"], p["strain"], n, p["exposure_timer"], p["infection_timer"],
+                                      p["potentially_paralyzed"], p["paralyzed"], p["ipv_protected"], p["paralysis_timer"],
+                                      nb.float32(c["p_paralysis"]), a, b)
+            potp[s, t - 1], par[s, t - 1] = a, b
+            if t % c["ri_step"] == 0:
+                l1, l2, l3 = (np.zeros((nt, nn), np.int32) for _ in range(3))
+                ref["fast_ri"](c["ri_step"], p["node_id"], p["disease_state"], p["strain"], p["ipv_protected"], p["ri_timer"], t,
+                               node["vx_prob_ri"], node["vx_prob_ipv"], n, l1, l2, l3, p["chronically_missed"], np.int8(1))
+                inc[s, t - 1] += l2.sum(axis=0)
+            if t == c["sia_tick"]:
+                l1, l2 = np.zeros((nt, nn), np.int32), np.zeros((nt, nn), np.int32)
+                ref["fast_sia"](p["node_id"], p["disease_state"], p["strain"], p["date_of_birth"], t, node["vx_prob_sia"], c["sia_eff"], n,
+                                targeted, c["sia_age"][0], c["sia_age"][1], l1, l2, p["chronically_missed"], np.int8(2))
+                inc[s, t - 1] += l2.sum(axis=0)
+            beta, expo, sus = ref["tx_step_prep"](nn, n, ns, p["strain"][:n], srs, p["disease_state"][:n], p["node_id"][:n],
+                                                  p["daily_infectivity"][:n], p["acq_risk_multiplier"][:n])
+            beta_pre, prob = orc.tx_foi(beta, node["network"], 1.0, node["r0_scalars"], pop)
+            want, _ = orc.tx_draw_counts_ref(beta_pre, prob, expo, c["zi"], c["disp"], rs=np.random)
+            new = ref["tx_infect_nb"](nn, n, ns, sus, p["node_id"][:n], p["strain"][:n], p["disease_state"][:n], si, sp,
+                                      p["acq_risk_multiplier"][:n], prob, want)
+            inc[s, t - 1] += new.sum(axis=1)
+        if s % 16 == 0:
+            print("seed", s, "agents", n, "incidence", inc[s].sum(), "potentially paralysed", potp[s].sum(), "paralysed", par[s].sum())
+    print("mean cumulative incidence of the network", inc.sum((1, 2)).mean(), "paralysed", par.sum((1, 2)).mean())
+    save("ensemble_full_ref", incidence=inc.astype(np.int16), new_potentially_paralyzed=potp.astype(np.int16), new_paralyzed=par.astype(np.int16))
+
+
 if __name__ == "__main__":
     if "--ensemble" in sys.argv:
         ensemble()
+        raise SystemExit(0)
+    if "--ensemble-full" in sys.argv:
+        ensemble_full()
         raise SystemExit(0)
     if not ref_loader.available():
         raise SystemExit("needs the reference checkout at /root/reference")
     main()
     ensemble()
+    ensemble_full()

@@ -64,30 +64,41 @@ def test_progression_without_transmission(lp, pyramid):
 
 # ---------------------------------------------------------------- tests/test_diseasestate_abm.py:258-351
 def test_disease_timers_with_trans_explicit(lp, pyramid):
+    """Two agents in two nodes; the lone susceptible sits in the OTHER node, so its exposure goes through the importation
+    branch with an expected count of ~1: in the reference a Poisson-like draw that is >= 1 with probability ~0.63, which its
+    seed = 124 happens to realise on day 1.  Here the same event has the same probability (the node's scale is
+    solved for E[min(K, 1)] = 1 - exp(-E)), so the test walks seeds from 124 until the exposure lands on day 1 -- the timer
+    arithmetic after that is seed-free -- and also checks that it does not land there for every seed."""
     dur_exp, dur_inf = 2, 3
-    pars = base_pars(
-        lp, pyramid, start_date=lp.date("2018-01-01"), dur=30, init_pop=np.array([1, 1]), cbr=np.array([0, 0]),
-        r0_scalars=np.array([1.0, 1.0]), init_prev=1, dur_exp=lp.constant(value=dur_exp), dur_inf=lp.constant(value=dur_inf),
-        t_to_paralysis=lp.constant(value=10), p_paralysis=1 / 2000, r0=999, distances=np.array([[0, 1], [1, 0]]),
-        individual_heterogeneity=False, seed=124,
-    )
-    sim = lp.SEIR_ABM(pars)
-    sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM, lp.VitalDynamics_ABM]
-    state = sim.people.disease_state[: sim.people.count]
-    assert (np.sum(state == 0), np.sum(state == 1), np.sum(state == 2), np.sum(state == 3)) == (1, 0, 1, 0)
-    assert np.all(sim.people.exposure_timer == dur_exp) and np.all(sim.people.infection_timer == dur_inf)
-    assert np.all(sim.people.paralysis_timer <= sim.people.infection_timer)
-    sim.run()
-    n_s, n_e, n_i, n_r = (np.sum(getattr(sim.results, k), axis=1) for k in "SEIR")
-    n_npp = np.sum(sim.results.new_potentially_paralyzed, axis=1)
-    zeros = np.zeros(sim.pars.dur + 1, int)
-    s_exp = zeros.copy(); s_exp[0] = 1  # noqa: E702
-    e_exp = zeros.copy(); e_exp[1 : 2 + dur_exp] = 1  # noqa: E702
-    i_exp = zeros.copy(); i_exp[0 : dur_inf + 1] += 1; i_exp[2 + dur_exp : 2 + dur_exp + dur_inf] += 1  # noqa: E702
-    r_exp = zeros.copy(); r_exp[1 + dur_inf :] += 1; r_exp[2 + dur_exp + dur_inf :] += 1  # noqa: E702
-    p_exp = zeros.copy(); p_exp[1 + dur_inf] += 1; p_exp[2 + dur_exp + dur_inf] += 1  # noqa: E702
-    assert np.all(n_s == s_exp) and np.all(n_e == e_exp) and np.all(n_i == i_exp) and np.all(n_r == r_exp)
-    assert np.all(n_npp == p_exp)
+    day1 = []
+    for seed in range(124, 140):
+        pars = base_pars(
+            lp, pyramid, start_date=lp.date("2018-01-01"), dur=30, init_pop=np.array([1, 1]), cbr=np.array([0, 0]),
+            r0_scalars=np.array([1.0, 1.0]), init_prev=1, dur_exp=lp.constant(value=dur_exp), dur_inf=lp.constant(value=dur_inf),
+            t_to_paralysis=lp.constant(value=10), p_paralysis=1 / 2000, r0=999, distances=np.array([[0, 1], [1, 0]]),
+            individual_heterogeneity=False, seed=seed,
+        )
+        sim = lp.SEIR_ABM(pars)
+        sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM, lp.VitalDynamics_ABM]
+        state = sim.people.disease_state[: sim.people.count]
+        assert (np.sum(state == 0), np.sum(state == 1), np.sum(state == 2), np.sum(state == 3)) == (1, 0, 1, 0)
+        assert np.all(sim.people.exposure_timer == dur_exp) and np.all(sim.people.infection_timer == dur_inf)
+        assert np.all(sim.people.paralysis_timer <= sim.people.infection_timer)
+        sim.run()
+        day1.append(bool(sim.results.E[1].sum() == 1))
+        if not day1[-1]:
+            continue
+        n_s, n_e, n_i, n_r = (np.sum(getattr(sim.results, k), axis=1) for k in "SEIR")
+        n_npp = np.sum(sim.results.new_potentially_paralyzed, axis=1)
+        zeros = np.zeros(sim.pars.dur + 1, int)
+        s_exp = zeros.copy(); s_exp[0] = 1  # noqa: E702
+        e_exp = zeros.copy(); e_exp[1 : 2 + dur_exp] = 1  # noqa: E702
+        i_exp = zeros.copy(); i_exp[0 : dur_inf + 1] += 1; i_exp[2 + dur_exp : 2 + dur_exp + dur_inf] += 1  # noqa: E702
+        r_exp = zeros.copy(); r_exp[1 + dur_inf :] += 1; r_exp[2 + dur_exp + dur_inf :] += 1  # noqa: E702
+        p_exp = zeros.copy(); p_exp[1 + dur_inf] += 1; p_exp[2 + dur_exp + dur_inf] += 1  # noqa: E702
+        assert np.all(n_s == s_exp) and np.all(n_e == e_exp) and np.all(n_i == i_exp) and np.all(n_r == r_exp)
+        assert np.all(n_npp == p_exp)
+    assert 4 <= sum(day1) <= 15, day1  # ~0.63 per seed: neither never nor always
 
 
 # ---------------------------------------------------------------- tests/test_diseasestate_abm.py:497-541
@@ -370,3 +381,29 @@ def test_snapshot_reload_runs_like_a_fresh_sim(lp, pyramid, tmp_path):
     tot_a, tot_b = a.new_exposed.sum(), b.new_exposed.sum()
     assert tot_a > 500 and abs(tot_a - tot_b) < 0.1 * tot_a
     assert abs(int(a.births.sum()) - int(b.births.sum())) < 0.2 * a.births.sum() + 10
+
+
+# ---------------------------------------------------------------- tests_scientific/outbreak_size.py:60-80 (analytic anchor)
+@pytest.mark.parametrize("r0", [1.5, 2.5, 5.0])
+def test_final_size_matches_kermack_mckendrick(lp, pyramid, r0):
+    """Single node, everybody susceptible, no heterogeneity, no exposed period, no births / deaths / vaccination / season:
+    the total number of infections must solve the final-size relation z = S0 (1 - exp(-R0 (z + I0))) the reference's
+    scientific test compares against.  (The fused engine runs every day.)"""
+    from scipy.optimize import brentq
+
+    n, i0 = 300_000, 60
+    sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=1200, init_pop=np.array([n]), cbr=np.array([0.0]), r0_scalars=np.array([1.0]), r0=r0,
+                                init_prev=i0 / n, init_immun=0.0, seasonal_amplitude=0.0, dur_exp=lp.constant(value=0),
+                                individual_heterogeneity=False, vx_prob_ri=None, vx_prob_sia=None, seed=int(10 * r0),
+                                distances=np.zeros((1, 1))))
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    # the reproduction number the model implements: infectivity per day x days infectious.  The infectious period is the
+    # gamma draw truncated to whole int8 days (model.py:575-579: half a day short of its mean) and the daily infectivity is
+    # r0 over a 1000-draw sample mean (model.py:845), so R differs from pars.r0 by ~2 %
+    r_eff = float(sim.people.daily_infectivity[0]) * float(sim.people.infection_timer[: sim.people.count].mean())
+    assert abs(r_eff / r0 - 1) < 0.06
+    sim.run()
+    total = sim.results.new_exposed.sum() / n
+    expected = brentq(lambda z: z - (1 - np.exp(-r_eff * (z + i0 / n))), 1e-6, 1.0)
+    assert abs(total - expected) < 0.02, (r0, r_eff, total, expected)
+    assert sim.results.I[-1].sum() == 0  # the outbreak is over inside the window
