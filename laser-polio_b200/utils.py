@@ -10,7 +10,7 @@ from time import perf_counter_ns
 import numpy as np
 
 __all__ = ["date", "daterange", "get_doy", "get_seasonality", "create_cumulative_deaths", "TimingStats", "save_sim_results",
-           "add_temporal_groupings", "results_long_table"]
+           "add_temporal_groupings", "add_regional_groupings", "results_long_table"]
 
 
 def date(value):
@@ -119,10 +119,57 @@ def add_temporal_groupings(df, time_config):
     return df
 
 
+root = None  # like the reference's ``lp.root``: where data/regions.yaml lives (set by the caller; None = current directory)
+
+
+def add_regional_groupings(df, region_groupings=None, grouping_level="adm0", regions_yaml_path=None):
+    """``adm0`` / ``adm1`` / ``adm01`` columns from ``dot_name`` ("AFRO:COUNTRY:STATE:LGA") and a ``region`` column = the
+    chosen admin level, overridden by the named groups of regions.yaml for the countries in ``region_groupings``
+    (reference utils.py:1076-1159; calibration targets aggregate by it, calib/targets.py).  A group's patterns match the
+    adm01 value when grouping at adm01 and the pattern has a colon, the adm1 value at adm1, else any dot_name containing
+    the pattern (case-insensitive).  Unknown countries and a missing YAML keep the admin level, with a warning."""
+    from pathlib import Path
+
+    df = df.copy()
+    parts = df["dot_name"].astype(str).str.split(":", expand=True)
+    df["adm0"], df["adm1"] = parts[1], parts[2]
+    df["adm01"] = df["adm0"] + ":" + df["adm1"]
+    if grouping_level not in {"adm0", "adm01", "dot_name"}:
+        raise ValueError(f"Invalid grouping_level: {grouping_level}. Must be one of 'adm0', 'adm01', or 'dot_name'.")
+    df["region"] = df[grouping_level]
+    if not region_groupings:
+        return df
+    path = Path(regions_yaml_path) if regions_yaml_path else Path(root or ".") / "data" / "regions.yaml"
+    try:
+        import yaml
+
+        with open(path) as fh:
+            groups_by_country = yaml.safe_load(fh)
+    except (FileNotFoundError, ImportError):
+        print(f"Warning: Could not load {path}, using adm0 for all countries")
+        return df
+    names = df["dot_name"].astype(str)
+    for country in region_groupings:
+        key = country.upper()
+        if key not in groups_by_country:
+            print(f"Warning: Custom regions not found for {country} in regions.yaml, using adm0")
+            continue
+        in_country = df["adm0"] == key
+        for group, patterns in groups_by_country[key].items():
+            hit = np.zeros(len(df), dtype=bool)
+            for pattern in patterns:
+                if grouping_level == "adm01" and ":" in pattern:
+                    hit |= (df["adm01"] == pattern).to_numpy()
+                else:
+                    hit |= names.str.contains(pattern, case=False, na=False).to_numpy()
+            df.loc[in_country.to_numpy() & hit, "region"] = group
+    return df
+
+
 def save_sim_results(sim, filename="simulation_results.h5", summary_config=None):
-    """Reference ``save_sim_results`` (utils.py:690-786): the long table as a DataFrame, written as HDF5 (key "results") when
-    pandas can (PyTables present) and the name ends in .h5, else as CSV next to it.  Temporal groupings are applied;
-    regional groupings need the reference's region YAMLs and are left to the caller (``dot_name`` is in the table)."""
+    """Reference ``save_sim_results`` (utils.py:690-786): the long table as a DataFrame with the temporal and regional
+    groupings of ``summary_config`` applied, written as HDF5 (key "results") when pandas can (PyTables present) and the name
+    ends in .h5, else as CSV (next to it when PyTables is missing)."""
     from pathlib import Path
 
     import pandas as pd
@@ -133,6 +180,11 @@ def save_sim_results(sim, filename="simulation_results.h5", summary_config=None)
         df["date"] = pd.to_datetime(df["date"])
         if "time_periods" in summary_config:
             df = add_temporal_groupings(df, summary_config["time_periods"])
+        groupings, level = summary_config.get("region_groupings"), summary_config.get("grouping_level")
+        if groupings is not None:
+            df = add_regional_groupings(df, groupings, level if level is not None else "adm0")
+        else:  # the reference always adds the admin columns; without a level the region is the node itself
+            df = add_regional_groupings(df, grouping_level=level if level is not None else "dot_name")
     path = Path(filename)
     if path.suffix == ".h5":
         try:
