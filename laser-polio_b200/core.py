@@ -195,12 +195,20 @@ class LaserFrame:
             try:
                 import h5py
 
+                # layout as recalled from laser-core ~0.6's LaserFrame.save_snapshot (not in the checkout: unverified):
+                # group "people" with attrs count / capacity and one dataset per column (live prefix), dataset "recovered",
+                # group "pars" with one attribute per parameter; plus our own "meta" attribute for an exact round trip
                 with h5py.File(path, "w") as f:
                     g = f.create_group("people")
+                    g.attrs["count"], g.attrs["capacity"] = meta["count"], meta["capacity"]
                     for k, v in cols.items():
                         g.create_dataset(k, data=v)
                     if results_r is not None:
                         f.create_dataset("recovered", data=np.asarray(results_r))
+                    if "pars" in meta:
+                        pg = f.create_group("pars")
+                        for k, v in meta["pars"].items():
+                            pg.attrs[k] = v
                     f.attrs["meta"] = json.dumps(meta)
                 return
             except ImportError:
@@ -230,7 +238,12 @@ class LaserFrame:
                     with h5py.File(path, "r") as f:
                         cols = {k: f["people"][k][...] for k in f["people"]}
                         recovered = f["recovered"][...] if "recovered" in f else None
-                        meta = json.loads(f.attrs["meta"])
+                        if "meta" in f.attrs:
+                            meta = json.loads(f.attrs["meta"])
+                        else:  # a file written by laser-core itself
+                            meta = {"count": int(f["people"].attrs["count"]), "capacity": int(f["people"].attrs["capacity"])}
+                            if "pars" in f:
+                                meta["pars"] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in f["pars"].attrs.items()}
                     loaded = True
             except ImportError:
                 pass

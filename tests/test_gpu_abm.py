@@ -407,3 +407,23 @@ def test_final_size_matches_kermack_mckendrick(lp, pyramid, r0):
     expected = brentq(lambda z: z - (1 - np.exp(-r_eff * (z + i0 / n))), 1e-6, 1.0)
     assert abs(total - expected) < 0.02, (r0, r_eff, total, expected)
     assert sim.results.I[-1].sum() == 0  # the outbreak is over inside the window
+
+
+# ---------------------------------------------------------------- tests/test_migration.py:13-72 (radiation spread is monotone in k)
+def test_radiation_spread_increases_with_k(lp, pyramid):
+    n_nodes = 14
+    rs = np.random.RandomState(2)
+    xy = rs.uniform(0, 200, (n_nodes, 2))
+    d = np.sqrt(((xy[:, None] - xy[None]) ** 2).sum(-1))
+
+    def nodes_reached(k_log10, seed):
+        sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=30, init_pop=np.full(n_nodes, 8000), cbr=np.zeros(n_nodes), r0_scalars=np.ones(n_nodes),
+                                    init_prev=[0.01] + [0.0] * (n_nodes - 1), r0=14, distances=d, migration_method="radiation",
+                                    radiation_k_log10=k_log10, max_migr_frac=1.0, vx_prob_ri=None, vx_prob_sia=None, seed=seed))
+        sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM]
+        sim.run()
+        return np.count_nonzero(sim.results.I.sum(axis=0) > 0)
+
+    zero, low, high = (np.mean([nodes_reached(k, 1000 + i) for i in range(4)]) for k in (-9, -2.5, -1))
+    assert zero == 1.0, zero          # no migration: the infection stays in its home node
+    assert low > zero and high >= low + 2, (zero, low, high)

@@ -41,3 +41,27 @@ def test_round_trip(tmp_path):
     f.save_snapshot(tmp_path / "bare.h5")
     g, R2, p2 = lp.LaserFrame.load_snapshot(tmp_path / "bare.h5")
     assert R2 is None and p2 is None and g.count == 600
+
+
+def test_every_people_column_round_trips_through_a_full_sim(tmp_path):
+    """The reference's tests/test_init_pop.py:171-175 on the CPU: a sim built with every stock component, its people frame
+    saved and reloaded, every column identical over the live prefix (construction is host-side; nothing runs)."""
+    rows = ["Age,M,F"] + [f"{5 * k}-{5 * k + 4},{int(1.7e7 * np.exp(-0.16 * k))},{int(1.6e7 * np.exp(-0.16 * k))}" for k in range(20)]
+    (tmp_path / "pyramid.csv").write_text("\n".join(rows + ["100+,300,500"]) + "\n")
+    pars = lp.PropertySet({
+        "start_date": lp.date("2020-01-01"), "dur": 40, "init_pop": np.array([3000, 2000, 1000]), "cbr": np.array([35.0, 30.0, 25.0]),
+        "r0_scalars": np.ones(3), "age_pyramid_path": str(tmp_path / "pyramid.csv"), "init_immun": 0.2, "init_prev": 0.01, "seed": 5,
+        "vx_prob_ri": 0.3, "vx_prob_ipv": 0.3, "distances": np.array([[0, 40, 70], [40, 0, 50], [70, 50, 0.0]]), "verbose": 0,
+        "stop_if_no_cases": False, "vx_prob_sia": [0.5, 0.5, 0.5],
+        "sia_schedule": [{"date": "2020-01-10", "nodes": [0, 1], "age_range": (0, 1825), "vaccinetype": "nOPV2"}]})
+    sim = lp.SEIR_ABM(pars)
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.RI_ABM, lp.SIA_ABM, lp.Transmission_ABM]
+    path = tmp_path / "init_pop.h5"
+    sim.people.save_snapshot(path, sim.results.R[:], sim.pars)
+    people, R, loaded = lp.LaserFrame.load_snapshot(path, n_ppl=pars["init_pop"], cbr=pars["cbr"], nt=pars["dur"] + 10)
+    n = sim.people.count
+    assert people.count == n and set(people.columns()) == set(sim.people.columns()) and len(people.columns()) >= 15
+    for name, col in sim.people.columns().items():
+        got = getattr(people, name)
+        assert got.dtype == col.dtype and np.array_equal(got[:n], col[:n]), name
+    assert np.array_equal(R, sim.results.R) and loaded["r0"] == sim.pars.r0
