@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "lpk_host.cuh"
+#include "lpk_node.cuh"
 #include "lpk_stages.cuh"
 
 // ------------------------------------------------------------------ error plumbing
@@ -697,8 +698,11 @@ __device__ double unit_gamma(uint64_t seed, uint32_t node, uint32_t tick, double
 // their sum equals the exact risk sum of the node's susceptibles (expo): a table whose risks are all equal (no individual
 // heterogeneity) sits on a bin edge, and the centre would be 6 % off.  E: expected exposures x importation multiplier.
 #define TAU_BINS (LPK_RISK_BINS / 32)
-__device__ __forceinline__ double newton_tau(const double (&h)[TAU_BINS], const double (&w)[TAU_BINS], double S, double Wsum, double T) {
-    double t = -log1p(-T / S) * S / Wsum;  // the equal-weights solution: a lower bound of the root (Jensen), tight for small T
+// t: a point at or left of the root, e.g. tau_lower_bound
+__device__ __forceinline__ double tau_lower_bound(double S, double Wsum, double T) {
+    return -log1p(-T / S) * S / Wsum;  // the equal-weights solution: a lower bound of the root (Jensen), tight for small T
+}
+__device__ __forceinline__ double newton_tau(const double (&h)[TAU_BINS], const double (&w)[TAU_BINS], double T, double t, double tol) {
     for (int it = 0; it < 100; ++it) {
         double F = 0.0, dF = 0.0;
 #pragma unroll
@@ -714,7 +718,7 @@ __device__ __forceinline__ double newton_tau(const double (&h)[TAU_BINS], const 
         const double step = (T - F) / dF;
         if (!(step > 0.0)) break;
         t += step;
-        if (step <= 1e-13 * t) break;
+        if (step <= tol * t) break;
     }
     return t;
 }
@@ -747,7 +751,8 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
     double T = m.T;
     if (T >= S * (1.0 - 1e-12)) return 3.0e38f;  // the reference's size = min(K, S) with K >= S: everybody
     if (!(T > 0.0)) return 0.f;
-    double t = newton_tau(h, w, S, Wsum, T);
+    double t = newton_tau(h, w, T, tau_lower_bound(S, Wsum, T), 1e-7);  // enough for V_own; refined below if it is final
+    bool redo = false;
     const double slope = m.Pless * E;
     if (Seff > 1.0 + 1e-9 && slope > 0.0) {
         double vown = 0.0;
@@ -765,9 +770,10 @@ __device__ float solve_tau_warp(int j, const int32_t *__restrict__ hist, double 
             T = E2 > 0.0 ? poisson_min_moments(E2, S, lane).T : 0.0;
             if (T >= S * (1.0 - 1e-12)) return 3.0e38f;
             if (!(T > 0.0)) return 0.f;
-            t = newton_tau(h, w, S, Wsum, T);
+            redo = true;
         }
     }
+    t = newton_tau(h, w, T, redo ? tau_lower_bound(S, Wsum, T) : t, 1e-11);
     return (float)(t > 3.0e38 ? 3.0e38 : t);
 }
 
@@ -852,7 +858,8 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
                                                         double *target, double *strain_cdf, double *prob, double *expected,
                                                         const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
                                                         uint32_t tick, int j_lo, int j_hi, const double *__restrict__ partial,
-                                                        int n_chunks, const uint32_t *xflags, int xworld, uint32_t xseq) {
+                                                        int n_chunks, const uint32_t *xflags, int xworld, uint32_t xseq,
+                                                        const __grid_constant__ lpk_node_args ep, int run_ep) {
     __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
     __shared__ unsigned char snz[NM_ROWS];
     __shared__ double stgt[32];
@@ -899,6 +906,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
     if (ty == 0) {
         double tgt = 0.0;
         if (j < j_hi) {
+            if (run_ep) epilogue_node(ep, j, j_lo);  // the tick's bookkeeping of node j (writes results.pop[t][j], read just below)
             double P = 0.0, local = 0.0, p[LPK_MAX_STRAINS];
             const double popn = fmax((double)alive[j], 1.0);
             for (int s = 0; s < n_strains; ++s) {
@@ -939,7 +947,8 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
-                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq) {
+                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq,
+                         const lpk_node_args *inline_epilogue) {
     double *rowsum = ws, *target = ws + num_nodes;
     if (!rowsums_done) {
         k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
@@ -973,7 +982,8 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
     k_tx_node_math<<<(node_hi - node_lo + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
                                                                    beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
                                                                    strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi,
-                                                                   partial, n_chunks, xchg_flags, xchg_world, xchg_seq);
+                                                                   partial, n_chunks, xchg_flags, xchg_world, xchg_seq,
+                                                                   inline_epilogue ? *inline_epilogue : lpk_node_args{}, inline_epilogue ? 1 : 0);
     CUDA_TRY(cudaGetLastError(), "node_math");
     return LPK_OK;
 }
@@ -989,5 +999,5 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
                 expected && ws, "tx_node_math null pointer");
     return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
                                 alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
-                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes, nullptr, 0, 0u);
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes, nullptr, 0, 0u, nullptr);
 }

@@ -26,12 +26,14 @@
 
 #include "lpk_host.cuh"
 #include "lpk_hot.cuh"
+#include "lpk_node.cuh"
 
 struct PassParams {
     lpk_people P;
     lpk_tick_args A;
     uint32_t *unit_ctr;  // work counter of this launch (zero when the kernel starts)
     uint32_t *unit_ctr_next;  // optional: the counter of the NEXT launch, zeroed by this one (lpk_tick_args.work_counter_next)
+    uint32_t unit_log;   // log2 of the pairs per work unit of this launch (1 .. LPK_UNIT_LOG): LPK_PASS_UNIT_LOG experiments
     uint32_t debug;      // timing experiments only (LPK_PASS_DEBUG): 1 = drop ring batches
     uint32_t rk[20];     // Philox round keys of the seed (key schedule done once on the host: the sweep's block reads them
                          // straight from the constant bank instead of spending 20 additions per 8 agents)
@@ -479,7 +481,8 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     const uint64_t ctr_base = ((A.id_base >> 8) << 5) + (uint64_t)lane;  // Philox counter of pair 0 for this lane
     const uint32_t total_pairs = (uint32_t)((n + 255) >> 8);
     const uint32_t full_pairs = (uint32_t)(n >> 8);  // pairs whose 256 slots are all in use
-    const uint32_t n_units = (total_pairs + LPK_UNIT_PAIRS - 1) >> LPK_UNIT_LOG;
+    const uint32_t upl = pp.unit_log, unit_pairs = 1u << upl, unit_bytes = 256u << upl;
+    const uint32_t n_units = (total_pairs + unit_pairs - 1u) >> upl;
     const uint32_t today = hot_today(tick);
     const float tau_all = ldexpf(1.0f, e0);  // from here on every susceptible passes the pre-test anyway (bound of code 0 x tau >= 1)
 
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     // population (appended cohorts: mixed-node pairs, the slow general path) are handed out FIRST, one per claim.
     const uint32_t kNoUnit = 0xFFFFFFFFu;
     const uint32_t guide = 3u * gridDim.x * kWarps;
-    const uint32_t stream_units = A.uniform_agents > 0 ? (uint32_t)(A.uniform_agents >> (8 + LPK_UNIT_LOG)) : n_units;
+    const uint32_t stream_units = A.uniform_agents > 0 ? (uint32_t)(A.uniform_agents >> (8 + upl)) : n_units;
     const uint32_t tail_units = n_units - (stream_units < n_units ? stream_units : n_units);
     uint32_t run_next = 0u, run_end = 0u;  // warp-uniform: claim indices of the current run not yet taken
     auto next_unit = [&]() -> uint32_t {   // warp-uniform result
@@ -540,14 +543,14 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
         if (elect_one()) {
             const uint32_t bar = smem_u32(bars) + (uint32_t)buf * 8u;
             fence_proxy_async_smem();  // the warp's reads of this buffer (previous use) precede the engine's writes
-            mbar_arrive_expect_tx(bar, LPK_UNIT_AGENTS);
-            tma_load(smem_u32(stage) + (uint32_t)buf * LPK_UNIT_AGENTS, P.hot + (int64_t)u * LPK_UNIT_AGENTS, LPK_UNIT_AGENTS, bar);
+            mbar_arrive_expect_tx(bar, unit_bytes);
+            tma_load(smem_u32(stage) + (uint32_t)buf * LPK_UNIT_AGENTS, P.hot + (int64_t)u * unit_bytes, unit_bytes, bar);
             // the columns the special days read for (nearly) every pair of the unit: into L2 a unit ahead, so that the loads in
             // the tile loop cost an L2 hit instead of a DRAM round trip (profiles/r2: the RI day was latency bound, 1.1 ms)
-            const int64_t a0 = (int64_t)u * LPK_UNIT_AGENTS;
-            if ((kRI || kSIA) && a0 + LPK_UNIT_AGENTS <= P.capacity) {
-                if (kRI) tma_prefetch_l2(P.ri_k + a0, LPK_UNIT_AGENTS);
-                if (kSIA) { tma_prefetch_l2(P.chronically_missed + a0, LPK_UNIT_AGENTS); tma_prefetch_l2(P.date_of_birth + a0, 4 * LPK_UNIT_AGENTS); }
+            const int64_t a0 = (int64_t)u * unit_bytes;
+            if ((kRI || kSIA) && a0 + unit_bytes <= P.capacity) {
+                if (kRI) tma_prefetch_l2(P.ri_k + a0, unit_bytes);
+                if (kSIA) { tma_prefetch_l2(P.chronically_missed + a0, unit_bytes); tma_prefetch_l2(P.date_of_birth + a0, 4u * unit_bytes); }
             }
         }
     };
@@ -565,11 +568,11 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
     // ticks its 8 earliest death dates and on RI ticks its 8 largest RI timers (lanes 0-7)
     int tnv = -1, mdv = INT_MAX, rmv = INT_MIN;
     auto fetch_meta = [&](uint32_t u) {
-        const uint32_t g0 = u << LPK_UNIT_LOG;
+        const uint32_t g0 = u << upl;
         tnv = -1; mdv = INT_MAX; rmv = INT_MIN;
-        if (P.tile_node && lane < 4 && g0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(g0 >> 1) + lane]);
-        if (kDeaths && lane < LPK_UNIT_PAIRS && g0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[g0 + lane];
-        if (kRI && lane < LPK_UNIT_PAIRS && g0 + (uint32_t)lane < total_pairs) rmv = P.pair_ri_max[g0 + lane];
+        if (P.tile_node && (uint32_t)lane < (unit_pairs >> 1) && g0 + 2u * (uint32_t)lane < total_pairs) tnv = __ldg(&P.tile_node[(g0 >> 1) + lane]);
+        if (kDeaths && (uint32_t)lane < unit_pairs && g0 + (uint32_t)lane < total_pairs) mdv = P.pair_min_dod[g0 + lane];
+        if (kRI && (uint32_t)lane < unit_pairs && g0 + (uint32_t)lane < total_pairs) rmv = P.pair_ri_max[g0 + lane];
     };
     uint32_t u_cur = next_unit();
     if (u_cur != kNoUnit) { fetch(u_cur, 0); fetch_meta(u_cur); }
@@ -578,14 +581,14 @@ __global__ void __launch_bounds__(kWarps * 32, kOcc) k_tick_pass(const __grid_co
 #pragma unroll 1
     while (u_cur != kNoUnit) {
         const uint32_t u_nxt = next_unit();
-        const uint32_t gp0 = u_cur << LPK_UNIT_LOG;
+        const uint32_t gp0 = u_cur << upl;
         const int tnv_cur = tnv, mdv_cur = mdv, rmv_cur = rmv;
         if (u_nxt != kNoUnit) { fetch(u_nxt, buf ^ 1); fetch_meta(u_nxt); }
         mbar_wait(&bars[buf], buf ? par1 : par0);
         if (buf) par1 ^= 1u; else par0 ^= 1u;
         const uint32_t *src = stage + buf * (LPK_UNIT_AGENTS / 4);
 #pragma unroll 1
-        for (int tp = 0; tp < LPK_UNIT_PAIRS / 2; ++tp) {  // one TILE (two pairs, 16 agents per lane) per iteration: the two
+        for (int tp = 0; tp < (int)(unit_pairs >> 1); ++tp) {  // one TILE (two pairs, 16 agents per lane) per iteration: the two
             const uint32_t gp = gp0 + 2u * (uint32_t)tp;    // Philox blocks are independent chains and interleave
             if (gp >= total_pairs) break;
             const int tn = __shfl_sync(LPK_FULL, tnv_cur, tp);
@@ -754,6 +757,11 @@ extern "C" int lpk_tick_pass(const lpk_people *people, const lpk_tick_args *args
         if (dbg < 0) { const char *e = getenv("LPK_PASS_DEBUG"); dbg = e ? atoi(e) : 0; }
         pp.debug = (uint32_t)dbg;
     }
+    {   // pairs per work unit: 8; LPK_PASS_UNIT_LOG=1|2 for experiments (smaller units did not help small tables: DESIGN.md section 4)
+        static int forced = -2;
+        if (forced == -2) { const char *e = getenv("LPK_PASS_UNIT_LOG"); forced = e ? atoi(e) : -1; }
+        pp.unit_log = (uint32_t)((forced >= 1 && forced <= LPK_UNIT_LOG) ? forced : LPK_UNIT_LOG);
+    }
     cudaStream_t st = as_stream(stream);
     int rc;
     // block shape: warps per block x blocks per SM (LPK_PASS_SHAPE: experiments)
@@ -892,7 +900,8 @@ extern "C" int lpk_build_tile_nodes(const int16_t *node_id, int64_t first_tile, 
 }
 
 // ------------------------------------------------------------------ node-level epilogue of tick t
-// one warp per node: the row sum of the network (coalesced) by all lanes, the node's bookkeeping by lane 0
+// one warp per node: the row sum of the network (coalesced) by all lanes, the node's bookkeeping by lane 0.  Launched on
+// the first tick of a network only (row sums); afterwards the bookkeeping runs inside k_tx_node_math (lpk_node.cuh).
 __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ lpk_node_args a) {
     const int n_lo = a.node_hi > 0 ? a.node_lo : 0, n_hi = a.node_hi > 0 ? a.node_hi : a.n_nodes;
     const int n = n_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -909,66 +918,15 @@ __global__ void __launch_bounds__(256) k_tick_epilogue(const __grid_constant__ l
         if (lane == 0) a.rowsum_ws[n] = sum;
     }
     if (lane != 0) return;
-    if (n == n_lo && a.counts) a.counts[0] = a.counts[1];
-    const int ns = a.n_strains;
-    int d = 0, dpp = 0, dpar = 0;
-    if (a.deaths) {
-        d = a.deaths[n]; dpp = a.dead_pp[n]; dpar = a.dead_par[n];
-        a.deaths[n] = 0; a.dead_pp[n] = 0; a.dead_par[n] = 0;
-    }
-    if (a.pop) {
-        const int births = a.births_row ? a.births_row[n] : 0;
-        if (a.flags & LPK_F_DEATHS) {
-            a.deaths_row[n] = d;  // "=": overwrites pre-modelled deaths of the non-agent immunes (model.py:1749)
-            a.pop[n] = a.pop_prev[n] + births - d;
-        } else {
-            a.pop[n] = a.pop_prev[n];
-        }
-    }
-    if (a.cur_potp) {
-        const int potp = a.cur_potp[n] + a.new_potential[n] - dpp;
-        const int par = a.cur_p[n] + a.new_paralyzed[n] - dpar;
-        a.cur_potp[n] = potp; a.cur_p[n] = par;
-        a.potp_row[n] = potp; a.p_row[n] = par;
-    }
-    if (a.S_snap) {
-        if (a.flags & LPK_F_PENDING) {
-            a.S_prev[n] = a.S_snap[n] - a.tx_hits[n];  // "=" (model.py:1476)
-            a.R_prev[n] += a.R_snap[n];                // "+=" on top of the pre-seeded immunes (model.py:1481)
-        }
-        a.tx_hits[n] = 0;
-        a.S_snap[n] = (int32_t)a.sus[n];
-        a.R_snap[n] = a.R_cur[n];
-    }
-    // exposed / infectious census of tick t-1 from the carried counts: the snapshot taken when tick t-1's stages ended,
-    // plus tick t-1's exposures (found by this pass); "=" like Transmission_ABM.log (model.py:1477-1480)
-    if (a.flags & LPK_F_PENDING) {
-        int e = 0, i = 0;
-        for (int s = 0; s < ns; ++s) {
-            const int64_t c = (int64_t)n * ns + s;
-            const int es = a.E_snap[c] + a.tx_hits_by_strain[c], is = a.I_snap[c];
-            a.E_by_strain_prev[c] = es; a.I_by_strain_prev[c] = is;
-            e += es; i += is;
-        }
-        a.E_prev[n] = e; a.I_prev[n] = i;
-    }
-    int cases = 0;
-    for (int s = 0; s < ns; ++s) {
-        const int64_t c = (int64_t)n * ns + s;
-        a.tx_hits_by_strain[c] = 0;
-        const int e = a.E_cur[c], i = a.I_cur[c];
-        a.E_snap[c] = e;
-        a.I_snap[c] = i;
-        cases |= e | i;
-    }
-    if (cases && a.any_cases) *a.any_cases = 1;
+    epilogue_node(a, n, n_lo);
 }
 
 int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *beta_fx, const int64_t *exposure_fx,
                          const int32_t *risk_hist, const double *network, double beta_seasonality, const double *r0_scalars,
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
-                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq);
+                         int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq,
+                         const lpk_node_args *inline_epilogue);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
@@ -987,10 +945,13 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     cudaStream_t st = as_stream(stream);
     REQUIRE(a.node_hi == 0 || (a.node_lo >= 0 && a.node_lo < a.node_hi && a.node_hi <= a.n_nodes), "tick_node node shard");
     const int owned = a.node_hi > 0 ? a.node_hi - a.node_lo : a.n_nodes;
-    k_tick_epilogue<<<(owned + 7) / 8, 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
+    const bool inline_ep = (a.flags & LPK_F_ROWSUMS) != 0;  // nothing but bookkeeping left: k_tx_node_math does it itself
+    if (!inline_ep) {
+        k_tick_epilogue<<<(owned + 7) / 8, 256, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError(), "lpk_tick_node epilogue");
+    }
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
                                 a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true, a.node_hi > 0 ? a.node_lo : 0,
-                                a.node_hi > 0 ? a.node_hi : a.n_nodes, a.xchg_flags, a.xchg_world, a.xchg_seq);
+                                a.node_hi > 0 ? a.node_hi : a.n_nodes, a.xchg_flags, a.xchg_world, a.xchg_seq, inline_ep ? &a : nullptr);
 }

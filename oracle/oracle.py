@@ -314,10 +314,14 @@ def unit_gamma(seed, node, tick, shape):
     return g / shape
 
 
-def _newton_tau(h, w, S, Wsum, T):
-    """tau with sum_b h[b] (1 - exp(-w[b] tau)) = T, Newton from the equal-weights solution (a lower bound of the root by
-    Jensen; the function is concave increasing, so the iteration is monotone)."""
-    t = -np.log1p(-T / S) * S / Wsum
+def _tau_lower_bound(S, Wsum, T):
+    """the equal-weights solution: a lower bound of the root by Jensen"""
+    return -np.log1p(-T / S) * S / Wsum
+
+
+def _newton_tau(h, w, T, t, tol):
+    """tau with sum_b h[b] (1 - exp(-w[b] tau)) = T by Newton from t at or left of the root (the function is concave
+    increasing, so the iteration is monotone)."""
     for _ in range(100):
         em = np.expm1(-w * t)
         F, dF = -(h * em).sum(), (h * w * (em + 1.0)).sum()
@@ -325,7 +329,7 @@ def _newton_tau(h, w, S, Wsum, T):
         if not step > 0.0:
             break
         t += step
-        if step <= 1e-13 * t:
+        if step <= tol * t:
             break
     return t
 
@@ -350,7 +354,8 @@ def solve_tau(hist_row, E, expo=None, seed=0, node=0, tick=0):
         return 3.0e38
     if not (T > 0.0):
         return 0.0
-    t = _newton_tau(h, w, S, Wsum, T)
+    t = _newton_tau(h, w, T, _tau_lower_bound(S, Wsum, T), 1e-7)
+    redo = False
     slope = pless * E
     if Seff > 1.0 + 1e-9 and slope > 0.0:
         pb = -np.expm1(-w * t)
@@ -365,7 +370,8 @@ def solve_tau(hist_row, E, expo=None, seed=0, node=0, tick=0):
                 return 3.0e38
             if not (T > 0.0):
                 return 0.0
-            t = _newton_tau(h, w, S, Wsum, T)
+            redo = True
+    t = _newton_tau(h, w, T, _tau_lower_bound(S, Wsum, T) if redo else t, 1e-11)
     return min(t, 3.0e38)
 
 

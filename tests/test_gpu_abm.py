@@ -420,7 +420,9 @@ def test_radiation_spread_increases_with_k(lp, pyramid):
         sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=30, init_pop=np.full(n_nodes, 8000), cbr=np.zeros(n_nodes), r0_scalars=np.ones(n_nodes),
                                     init_prev=[0.01] + [0.0] * (n_nodes - 1), r0=14, distances=d, migration_method="radiation",
                                     radiation_k_log10=k_log10, max_migr_frac=1.0, vx_prob_ri=None, vx_prob_sia=None, seed=seed))
-        sim.components = [lp.DiseaseState_ABM, lp.Transmission_ABM]
+        # VitalDynamics_ABM maintains results.pop, the denominator of the force of infection (without it the reference divides
+        # by max(0, 1), model.py:1344-1347, and the home node's outbreak is 8000 times stronger)
+        sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
         sim.run()
         return np.count_nonzero(sim.results.I.sum(axis=0) > 0)
 
