@@ -850,22 +850,28 @@ __global__ void __launch_bounds__(1024) k_node_matvec_partial(int n, int n_strai
         }
     }
 }
-__global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
-                                                        const int64_t *__restrict__ exposure_fx,
-                                                        const double *__restrict__ W, const double *__restrict__ rowsum,
-                                                        double season, const double *__restrict__ r0_scalars,
-                                                        const int32_t *__restrict__ alive, double zi, double disp_r,
-                                                        double *target, double *strain_cdf, double *prob, double *expected,
-                                                        const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
-                                                        uint32_t tick, int j_lo, int j_hi, const double *__restrict__ partial,
-                                                        int n_chunks, const uint32_t *xflags, int xworld, uint32_t xseq,
-                                                        const __grid_constant__ lpk_node_args ep, int run_ep) {
-    __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; reused as part[32 slices][strains][32 nodes] for the reduction
+// One block = NM_NPB destination nodes x 32 source slices.  With 32 nodes per block (round 1) the 774 nodes of Nigeria made 25
+// blocks on 25 SMs, each running 32 double-precision Newton solves; eight nodes per block spread the solves over 97 SMs (node
+// step of a day at 2.75e7 agents: 41 -> 32 us).  The solve itself is one dependent chain of ~5000 instructions per warp
+// (profiles/r2_nodemath_*): latency, not throughput.
+#define NM_NPB 8
+#define NM_THREADS (NM_NPB * 32)
+__global__ void __launch_bounds__(NM_THREADS) k_tx_node_math(int n, int n_strains, const int64_t *__restrict__ beta_fx,
+                                                              const int64_t *__restrict__ exposure_fx,
+                                                              const double *__restrict__ W, const double *__restrict__ rowsum,
+                                                              double season, const double *__restrict__ r0_scalars,
+                                                              const int32_t *__restrict__ alive, double zi, double disp_r,
+                                                              double *target, double *strain_cdf, double *prob, double *expected,
+                                                              const int32_t *__restrict__ hist, float *__restrict__ tau, uint64_t seed,
+                                                              uint32_t tick, int j_lo, int j_hi, const double *__restrict__ partial,
+                                                              int n_chunks, const uint32_t *xflags, int xworld, uint32_t xseq,
+                                                              const __grid_constant__ lpk_node_args ep, int run_ep) {
+    __shared__ double sbeta[LPK_MAX_STRAINS][NM_ROWS];  // 32 KB; its head is reused as part[32 slices][strains][NM_NPB nodes]
     __shared__ unsigned char snz[NM_ROWS];
-    __shared__ double stgt[32];
+    __shared__ double stgt[NM_NPB];
     xchg_wait(xflags, xworld, xseq);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = j_lo + blockIdx.x * 32 + tx;  // destination nodes [j_lo, j_hi): all of them, or this rank's shard
+    const int tx = threadIdx.x % NM_NPB, ty = threadIdx.x / NM_NPB;  // node of the block, slice of the source rows (0 .. 31)
+    const int j = j_lo + blockIdx.x * NM_NPB + tx;  // destination nodes [j_lo, j_hi): all of them, or this rank's shard
     double in[LPK_MAX_STRAINS] = {0.0, 0.0, 0.0, 0.0};
     if (partial) {  // the transfer was summed per chunk of source rows by k_node_matvec_partial: add the chunks in order
         if (ty == 0 && j < j_hi) {
@@ -877,21 +883,21 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
     for (int base = 0; base < n; base += NM_ROWS) {
         const int rows = min(NM_ROWS, n - base);
         __syncthreads();
-        if ((int)threadIdx.x < rows) {
+        for (int r = threadIdx.x; r < rows; r += NM_THREADS) {
             bool nz = false;
 #pragma unroll
             for (int s = 0; s < LPK_MAX_STRAINS; ++s) {
-                const long long b = (s < n_strains) ? __ldcg(&beta_fx[(int64_t)(base + threadIdx.x) * n_strains + s]) : 0;
+                const long long b = (s < n_strains) ? __ldcg(&beta_fx[(int64_t)(base + r) * n_strains + s]) : 0;
                 nz |= (b != 0);
-                sbeta[s][threadIdx.x] = (double)b / LPK_FX_SCALE;
+                sbeta[s][r] = (double)b / LPK_FX_SCALE;
             }
-            snz[threadIdx.x] = nz ? 1 : 0;
+            snz[r] = nz ? 1 : 0;
         }
         __syncthreads();
         if (j < j_hi) {
 #pragma unroll 4
             for (int i = ty; i < rows; i += 32) {
-                if (!snz[i]) continue;  // warp-uniform: rows without infectivity contribute nothing
+                if (!snz[i]) continue;  // rows without infectivity contribute nothing
                 const double w = W[(int64_t)(base + i) * n + j];
 #pragma unroll
                 for (int s = 0; s < LPK_MAX_STRAINS; ++s) in[s] += sbeta[s][i] * w;
@@ -899,9 +905,9 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
         }
     }
     __syncthreads();
-    double *part = &sbeta[0][0];  // [ty][s][tx], 32 * 4 * 32 doubles = 32 KB
+    double *part = &sbeta[0][0];  // [ty][s][tx]
 #pragma unroll
-    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[(ty * LPK_MAX_STRAINS + s) * 32 + tx] = in[s];
+    for (int s = 0; s < LPK_MAX_STRAINS; ++s) part[(ty * LPK_MAX_STRAINS + s) * NM_NPB + tx] = in[s];
     __syncthreads();
     if (ty == 0) {
         double tgt = 0.0;
@@ -911,7 +917,7 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
             const double popn = fmax((double)alive[j], 1.0);
             for (int s = 0; s < n_strains; ++s) {
                 double inc = 0.0;
-                for (int y = 0; y < 32; ++y) inc += part[(y * LPK_MAX_STRAINS + s) * 32 + tx];
+                for (int y = 0; y < 32; ++y) inc += part[(y * LPK_MAX_STRAINS + s) * NM_NPB + tx];
                 const double pre = (double)__ldcg(&beta_fx[(int64_t)j * n_strains + s]) / LPK_FX_SCALE;
                 local += pre;
                 double b = pre + inc - pre * rowsum[j];
@@ -936,10 +942,11 @@ __global__ void __launch_bounds__(1024) k_tx_node_math(int n, int n_strains, con
         stgt[tx] = tgt;
     }
     __syncthreads();
-    const int jn = j_lo + blockIdx.x * 32 + ty;  // warp ty solves node jn
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jn = j_lo + blockIdx.x * NM_NPB + wq;  // warp wq solves node jn
     if (jn < j_hi) {
-        const float t = solve_tau_warp(jn, hist, stgt[ty], (double)exposure_fx[jn] / LPK_FX_SCALE, seed, tick, tx);
-        if (tx == 0) tau[jn] = t;
+        const float t = solve_tau_warp(jn, hist, stgt[wq], (double)exposure_fx[jn] / LPK_FX_SCALE, seed, tick, lane);
+        if (lane == 0) tau[jn] = t;
     }
 }
 
@@ -979,7 +986,7 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
         CUDA_TRY(cudaGetLastError(), "node_math matvec");
         partial = scratch[dev];
     }
-    k_tx_node_math<<<(node_hi - node_lo + 31) / 32, 1024, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
+    k_tx_node_math<<<(node_hi - node_lo + NM_NPB - 1) / NM_NPB, NM_THREADS, 0, st>>>(num_nodes, n_strains, beta_fx, exposure_fx, network, rowsum,
                                                                    beta_seasonality, r0_scalars, alive_counts, zero_inflation, r, target,
                                                                    strain_cdf, prob, expected, risk_hist, tau, seed, tick, node_lo, node_hi,
                                                                    partial, n_chunks, xchg_flags, xchg_world, xchg_seq,
