@@ -373,8 +373,8 @@ int lpk_tick_node(const lpk_node_args *args, void *stream);
  *     inverse CDF on cum_deaths (laser-core KaplanMeierEstimator.predict_age_at_death semantics: year by
  *     searchsorted-left on the cumulative table, uniform day within the year), disease_state = 0.  Draws are
  *     Philox(seed; node, tick, BIRTH) / Philox(seed; agent, tick, LIFESPAN) instead of the host numpy stream.
- *     counts[1] += sum(births); if that would exceed capacity nobody is born and *status is set to 1 (the device
- *     analogue of LaserFrame.add raising; the host raises when it next reads status). */
+ *     counts[1] += sum(births); if that would exceed capacity nobody is born, status[0] |= 1 and status[1] = tick (the
+ *     device analogue of LaserFrame.add raising; the host mirrors status behind an event and raises one call later). */
 typedef struct lpk_births_args {
     int32_t tick, n_nodes;
     uint64_t seed, id_base;
@@ -389,7 +389,8 @@ typedef struct lpk_births_args {
     int32_t ri_newborn_timer;    /* < 0: leave ri_timer as pre-set (reference behaviour); else value for newborns */
     int32_t *node_offsets_ws;    /* scratch int32[nodes + 1] */
     int64_t *cohort_ws;          /* scratch int64[2] = {first slot, size} of the cohort just created */
-    int32_t *status;             /* device int32 flag */
+    int32_t *status;             /* device int32[2]: flag bits (1 = a cohort did not fit: sticky, no later cohort is created
+                                    either; 2 = a risk beyond the agenda code), and the tick of the first overflow */
     int8_t *disease_state;
     int16_t *node_id;
     int32_t *date_of_birth, *date_of_death;

@@ -99,6 +99,8 @@ def make_rng(seed=0, tick=0, u1=None, u2=None, x=None, id_base=0) -> Rng:
     r.u2 = u2.data_ptr() if u2 is not None else None
     r.x = x.data_ptr() if x is not None else None
     r.id_base = int(id_base)
+    if r.id_base % 256:
+        raise ValueError("id_base must be a multiple of 256 (exposure draws are shared by aligned groups of 256 agents)")
     r._keep = (u1, u2, x)  # the struct only holds raw pointers: keep the tensors alive with it
     return r
 

@@ -220,9 +220,11 @@ class SEIR_ABM:
                 self._engine.drain()
                 self._engine.close()
             self._engine = None
-            self.dev.download()
-            self.io_bytes = (self.dev.h2d_bytes, self.dev.d2h_bytes)
-            self.dev = None
+            dev, self.dev = self.dev, None
+            try:
+                dev.download()  # raises (after copying everything back) if a newborn cohort did not fit the frame
+            finally:
+                self.io_bytes = (dev.h2d_bytes, dev.d2h_bytes)
 
     # ------------------------------------------------------------------ tick loop
     def _component_tick(self, tick: int) -> None:

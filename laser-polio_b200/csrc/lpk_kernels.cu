@@ -570,7 +570,7 @@ extern "C" int lpk_tx_infect(int32_t num_nodes, int64_t num_people, int32_t num_
     REQUIRE(num_strains >= 1 && num_strains <= LPK_MAX_STRAINS, "tx_infect n_strains");
     REQUIRE(node_ids && strain && disease_state && risks && q && strain_cdf && n_new, "tx_infect null pointer");
     REQUIRE(ALIGNED(disease_state, 4) && ALIGNED(node_ids, 8) && ALIGNED(risks, 16), "tx_infect alignment");
-    REQUIRE(!rng || (rng->id_base & 3) == 0, "tx_infect id_base must be a multiple of 4");
+    REQUIRE(!rng || (rng->id_base & 255) == 0, "tx_infect id_base must be a multiple of 256 (exposure draws are shared by aligned groups of 256 agents)");
     cudaStream_t st = as_stream(stream);
     CUDA_TRY(cudaMemsetAsync(n_new, 0, sizeof(int32_t) * num_nodes * num_strains, st), "tx_infect memset");
     if (num_people == 0) return LPK_OK;

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(1024) k_births_count(lpk_births_args a) {
         int total = s_carry;
         const long long old_count = a.counts[1];
         if (old_count + total > a.capacity || (*a.status & 1)) {  // LaserFrame.add would raise: flag it (sticky: no later
-            *a.status |= 1;                                                // cohort is appended either), create nobody
+            if (!(*a.status & 1)) a.status[1] = a.tick;                    // cohort is appended either), remember the tick,
+            *a.status |= 1;                                                // create nobody
             total = 0;
             for (int n = 0; n < a.n_nodes; ++n) { a.births_row[n] = 0; a.node_offsets_ws[n] = 0; }
         }

@@ -80,7 +80,7 @@ class DeviceState:
         self.zero_pop = torch.zeros(n, dtype=torch.int32, device=dev)
         # live-slot counters {agents when the previous tick ended, agents now}: births are created on the device
         self.counts = torch.tensor([people.count, people.count], dtype=torch.int64, device=dev)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(2, dtype=torch.int32, device=dev)  # lpk_births_args.status: flag bits, tick of the first overflow
         self.cohort_ws = torch.zeros(2, dtype=torch.int64, device=dev)
         self.node_offsets_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)
         self.tile_node = None  # owned by engine.FusedEngine when ticks are fused
@@ -109,7 +109,7 @@ class DeviceState:
         date_of_death) come back for the cohorts appended since upload()."""
         people, results = self.sim.people, self.sim.results
         torch.cuda.current_stream().synchronize()
-        count = self.sync_count()
+        count = self.sync_count(check=False)  # a cohort that did not fit raises AFTER everything has been copied back
         for name, t in self.cols.items():
             host = getattr(people, name)
             if name in self.dirty:
@@ -128,6 +128,8 @@ class DeviceState:
             host = getattr(results, name)
             torch.from_numpy(host).copy_(t, non_blocking=False)
             self.d2h_bytes += host.nbytes
+        self.release_network()
+        self.check_status()
 
     def push_rows(self, name: str, start: int, end: int):
         """H2D of a slice of one agent column (newborn cohort written on the host)."""
@@ -140,12 +142,22 @@ class DeviceState:
         pop = self.res.get("pop")
         return self.zero_pop if pop is None else pop[t]
 
-    def sync_count(self) -> int:
+    def check_status(self, status=None):
+        """Raise what LaserFrame.add raises in the reference when a cohort does not fit (the device flags it and creates no
+        further cohort: lpk_births_args.status)."""
+        flags, tick = (int(v) for v in (self.status.tolist() if status is None else status))
+        if flags & 1:
+            raise ValueError(f"frame.add() exceeds capacity (capacity={self.sim.people.capacity}) at tick {tick}: "
+                             "that cohort and every later one were not created")
+        if flags & 2:
+            raise ValueError("an acq_risk_multiplier exceeds the range of the agenda's risk code")
+
+    def sync_count(self, check=True) -> int:
         """Device -> host: how many slots are in use (blocks on the stream), and whether a cohort overflowed capacity."""
-        count, status = int(self.counts[1].item()), int(self.status.item())
-        if status != 0:
-            raise ValueError(f"frame.add() exceeds capacity (capacity={self.sim.people.capacity}): births were dropped on the device")
+        count = int(self.counts[1].item())
         self.sim.people._count = count
+        if check:
+            self.check_status()
         return count
 
     def set_count(self, count: int):
@@ -159,6 +171,19 @@ class DeviceState:
             if arr.shape != (self.n_nodes, self.n_nodes):
                 raise ValueError(f"network must be {self.n_nodes}x{self.n_nodes}, got {arr.shape}")
             self.network = torch.from_numpy(arr).to(self.device)
+            self.release_network()
             self._net_src = host_network
+            # the reference re-reads tx.network every tick, so an in-place edit takes effect there; here the device holds a
+            # copy, so while it does the host array is read-only: an in-place edit raises instead of being silently ignored
+            # (assign a new array to tx.network to change it; the identity check above picks that up)
+            if isinstance(host_network, np.ndarray) and host_network.flags.writeable:
+                host_network.setflags(write=False)
+                self._net_locked = True
             self.h2d_bytes += arr.nbytes
         return self.network
+
+    def release_network(self):
+        """Give the host network array back its write permission (download(), or a new array took its place)."""
+        if getattr(self, "_net_locked", False) and isinstance(self._net_src, np.ndarray):
+            self._net_src.setflags(write=True)
+        self._net_locked = False

@@ -76,6 +76,10 @@ class FusedEngine:
         # early stop (pars.stop_if_no_cases): "somebody is still exposed or infectious after tick t", one flag per tick,
         # mirrored into pinned host memory with an event so that the host never waits for more than one tick
         self.stop_rule = bool(sim.pars["stop_if_no_cases"])
+        # capacity overflow at birth (lpk_births_args.status) mirrored into pinned memory behind an event: the host looks at it
+        # one call late instead of synchronising, and raises like LaserFrame.add does in the reference
+        self.status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.status_evt = None
         if self.stop_rule:
             self.cases_dev = i32(sim.nt + 1)
             self.cases_host = torch.zeros(sim.nt + 1, dtype=torch.int32).pin_memory()
@@ -371,6 +375,10 @@ class FusedEngine:
         """Ticks t0 .. t0 + n_days - 1 as fused days, launched from C back to back (lpk_run_days); none of them may need the
         components (needs_components).  Does not advance sim.t."""
         sim, R = self.sim, self.R
+        if self.status_evt is not None:  # the previous call's births: did a cohort not fit?
+            self.status_evt.synchronize()
+            self.status_evt = None
+            self.dev.check_status(self.status_host.tolist())
         if not self.hot_valid:  # the table was settled behind the engine's back (verify()): finish and re-base
             self.drain()
             self.rebase_tallies(t0)
@@ -405,6 +413,10 @@ class FusedEngine:
                     st.times.setdefault("tick_node", []).append(ms[3 * k + 2])
         st.launches += int(launches.value)
         self.pending, self.ri_lazy_k = bool(R.pending), int(R.ri_lazy_k)
+        if n_vd:
+            self.status_host.copy_(self.dev.status, non_blocking=True)
+            self.status_evt = torch.cuda.Event()
+            self.status_evt.record()
         if self.stop_rule:
             t = t0 + n_days - 1
             flag = self.cases_dev[t:t + 1]

@@ -78,6 +78,9 @@ default_pars = PropertySet(
         "verbose": 1,
         "stop_if_no_cases": True,
         "device_init": False,  # extension (not a reference key): draw the per-agent columns on the GPU (popinit.py)
+        # extension: newborns get ri_timer = 182 as the reference intends (model.py:1731-1732); False reproduces what it does --
+        # its isinstance test on classes never fires, so newborn timers stay at -1 and newborns never receive RI
+        "ri_newborn_timer": False,
     }
 )
 

@@ -429,3 +429,38 @@ def test_radiation_spread_increases_with_k(lp, pyramid):
     zero, low, high = (np.mean([nodes_reached(k, 1000 + i) for i in range(4)]) for k in (-9, -2.5, -1))
     assert zero == 1.0, zero          # no migration: the infection stays in its home node
     assert low > zero and high >= low + 2, (zero, low, high)
+
+
+# ---------------------------------------------------------------- LaserFrame.add raising when a cohort does not fit (laser-core)
+def test_cohort_that_does_not_fit_raises_after_results_are_back(lp, pyramid):
+    """The reference's LaserFrame.add raises at the tick whose cohort exceeds the capacity.  Births are created on the
+    device here, so the overflow is a sticky device flag: no later cohort is created either, the host sees the flag one call
+    late, and run() raises ValueError naming the tick -- after the columns and results were copied back."""
+    sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=40, init_pop=np.array([30_000, 20_000]), cbr=np.array([30.0, 25.0]), init_prev=0.01,
+                                distances=np.array([[0, 50], [50, 0.0]])))
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    vd = next(i for i in sim.instances if type(i).__name__ == "VitalDynamics_ABM")
+    room = sim.people.capacity - sim.people.count
+    vd.birth_rate[:] = 4.0 * room / (7 * 50_000 * 3)  # the third vital-dynamics tick (t = 21) no longer fits
+    with pytest.raises(ValueError, match="exceeds capacity .* at tick 21"):
+        sim.run()
+    assert sim.dev is None and sim.results.S[30].sum() > 0 and sim.results.births[14].sum() > 0
+    assert sim.results.births[21].sum() == 0 and sim.results.births[28].sum() == 0  # sticky: nobody is created afterwards
+    assert sim.people.count <= sim.people.capacity
+
+
+def test_network_is_read_only_while_resident(lp, pyramid):
+    """tx.network is re-read every tick by the reference (model.py:1335); the device holds a copy, so an in-place edit after
+    to_device() raises instead of being silently ignored, and replacing the array is picked up."""
+    sim = lp.SEIR_ABM(base_pars(lp, pyramid, dur=10, init_pop=np.array([5_000, 5_000]), init_prev=[0.02, 0.0], r0=14,
+                                distances=np.array([[0, 50], [50, 0.0]])))
+    sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
+    tx = next(i for i in sim.instances if type(i).__name__ == "Transmission_ABM")
+    sim.run_ticks(3)
+    with pytest.raises(ValueError):
+        tx.network[0, 1] = 0.5
+    tx.network = np.zeros((2, 2))  # cut the nodes off from now on
+    sim.run_ticks(20)
+    sim.to_host()
+    tx.network[0, 1] = 0.0  # writable again once the population is back on the host
+    assert sim.t == sim.nt
