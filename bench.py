@@ -24,6 +24,8 @@ The only per-tick exchange is the nodes x strains infectivity tally.
            bytes per launch measured by ncu in this round (profiles/r2_traffic.json names the capture), per day class
 * verified after the timed region (outside it) the carried tallies are recomputed from scratch by the per-function
            kernels and the head-count / census identities are checked on the table the number was measured on
+* named_shape  (N > 1, --config auto) the same K days on the shape BASELINE.json's configs name for this GPU count -- West Africa
+           (1921 nodes, 4.3e8 agents) on 2 and 4 GPUs, Africa (5672 nodes, 1.3e9 agents) on 8 -- device-resident, verified
 * cpu_baseline  the CPU oracle (C + OpenMP restatement of the reference's numba kernels, "port") timed on this box's host
            cores on a bounded sample of the same workload
 
@@ -249,6 +251,40 @@ def day_class(t):
     return ("sia" if synth.campaign_day(t) else "") + ("vd" if t % 7 == 0 else "") + ("ri" if t % 14 == 0 else "") or "plain"
 
 
+def measure_named_shape(name, K_, W_, local, rank, world, barrier):
+    """K device-resident days of the named shape sharded over the ranks (collective: every rank calls it); rank 0 gets the
+    summary dict, timed like the headline (CUDA events around the K days, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from laser_polio_b200 import kernels as K
+    from laser_polio_b200 import synth
+
+    n_nodes, n_agents = SHAPES[name]["nodes"], SHAPES[name]["agents"]
+    sim, n_local = synth.synth_sim(n_agents, n_nodes, K_ + W_ + 40, seed=20261018, device=f"cuda:{local}", rank=rank, world=world, mode="shard")
+    sim.to_device()
+    sim.run_ticks(W_)
+    K.STATS.reset()
+    K.STATS.timing = True
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sim.run_ticks(K_)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    kstats = K.STATS.summary()
+    K.STATS.timing = False
+    ok = torch.tensor([1 if sim._engine.verify().get("ok") else 0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    sim.to_host()
+    ms = float(ms.item())
+    return {"workload": f"{name} shape: {n_agents} agents, {n_nodes} nodes, one population node-sharded x{world}", "value": n_agents * K_ / (ms / 1e3),
+            "unit": "agent-days/s", "ms_per_step": ms / K_, "steps": K_, "agents_rank0": n_local, "verified": bool(ok.item()),
+            "kernel_mean_ms_rank0": {k: round(m, 4) for k, (c, m) in kstats.items()}}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -353,6 +389,17 @@ def run_b200(args):
         dist.all_reduce(live)
     agents_total = int(live.item())
 
+    # ---- the shape BASELINE.json's configs name for this GPU count, as a second measurement in the same line (N > 1 only:
+    # the headline at every N is the Nigeria population sharded N ways; this one keeps the per-GPU load near one GPU's)
+    named = None
+    if world > 1 and args.config == "auto" and mode == "shard" and not args.no_named_shape:
+        del sim
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        named = measure_named_shape(NAMED_SHAPE.get(world, "nigeria"), K_, W_, local, rank, world, barrier)
+
     if rank != 0:
         return
     value = agents_total * K_ / (ms / 1e3)
@@ -401,6 +448,7 @@ def run_b200(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
                      "per_day_class": per_class, "kernel_share_of_step": kernel_share},
         "verified": verified, "verified_checks": {**checks, **census},
+        "named_shape": named,
         "cpu_baseline": cpu_base,
         "e2e": {"value": agents_total * K_ / e2e_s, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
                 "seconds": e2e_s, "seconds_each": [round(x, 4) for x in e2e_runs],
@@ -422,6 +470,7 @@ def main():
     ap.add_argument("--agents", type=int, default=0, help="total agents (default: the shape's)")
     ap.add_argument("--nodes", type=int, default=0, help="total nodes (default: the shape's)")
     ap.add_argument("--graph", type=int, default=0, help="1: lpk_run_days captures each span of days into a CUDA graph (no per-kernel timing)")
+    ap.add_argument("--no-named-shape", action="store_true", help="N > 1: skip the second measurement on the shape named for this GPU count")
     ap.add_argument("--cpu-agents", type=int, default=20_000_000)
     ap.add_argument("--cpu-ticks", type=int, default=60)
     args = ap.parse_args()

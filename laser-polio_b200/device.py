@@ -176,7 +176,9 @@ class DeviceState:
             # the reference re-reads tx.network every tick, so an in-place edit takes effect there; here the device holds a
             # copy, so while it does the host array is read-only: an in-place edit raises instead of being silently ignored
             # (assign a new array to tx.network to change it; the identity check above picks that up)
-            if isinstance(host_network, np.ndarray) and host_network.flags.writeable:
+            # (only arrays that can be unlocked again: numpy refuses to re-enable writing on a view of foreign memory)
+            if isinstance(host_network, np.ndarray) and host_network.flags.writeable and \
+                    (host_network.flags.owndata or isinstance(host_network.base, np.ndarray)):
                 host_network.setflags(write=False)
                 self._net_locked = True
             self.h2d_bytes += arr.nbytes
@@ -185,5 +187,8 @@ class DeviceState:
     def release_network(self):
         """Give the host network array back its write permission (download(), or a new array took its place)."""
         if getattr(self, "_net_locked", False) and isinstance(self._net_src, np.ndarray):
-            self._net_src.setflags(write=True)
+            try:
+                self._net_src.setflags(write=True)
+            except ValueError:  # a view whose owner is itself read-only: leave it
+                pass
         self._net_locked = False

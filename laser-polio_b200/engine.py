@@ -234,7 +234,8 @@ class FusedEngine:
         t = sim.t - 1  # the tick the pending work belongs to
         c, r = dev.cols, dev.res
         n, ns = dev.n_nodes, dev.n_strains
-        count = dev.sync_count()  # births of fused vital-dynamics ticks happened on the device
+        count = dev.sync_count(check=False)  # births of fused vital-dynamics ticks happened on the device (an overflow is reported by
+        # the next run_days call or by download(), not from inside the drain)
         K.tx_infect(n, count, ns, c["node_id"], c["strain"], c["disease_state"], c["acq_risk_multiplier"], self.q, self.cdf,
                     rng=K.make_rng(sim.pars.seed, t, id_base=sim.id_base), out=dev.n_new)
         r["new_exposed"][t] += dev.n_new.sum(dim=1, dtype=torch.int32)

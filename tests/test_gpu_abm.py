@@ -441,7 +441,7 @@ def test_cohort_that_does_not_fit_raises_after_results_are_back(lp, pyramid):
     sim.components = [lp.VitalDynamics_ABM, lp.DiseaseState_ABM, lp.Transmission_ABM]
     vd = next(i for i in sim.instances if type(i).__name__ == "VitalDynamics_ABM")
     room = sim.people.capacity - sim.people.count
-    vd.birth_rate[:] = 4.0 * room / (7 * 50_000 * 3)  # the third vital-dynamics tick (t = 21) no longer fits
+    vd.birth_rate[:] = 0.4 * room / (7 * 50_000)  # each cohort takes ~40 % of the room: the third one (t = 21) no longer fits
     with pytest.raises(ValueError, match="exceeds capacity .* at tick 21"):
         sim.run()
     assert sim.dev is None and sim.results.S[30].sum() > 0 and sim.results.births[14].sum() > 0
