@@ -363,6 +363,10 @@ typedef struct lpk_node_args {
     const uint32_t *xchg_flags;
     int32_t xchg_world;
     uint32_t xchg_seq;
+    /* optional caller-owned scratch for n_nodes > 1024 (the transfer is then summed per chunk of 1024 source rows):
+     * double[ceil(n_nodes / 1024) * LPK_MAX_STRAINS * n_nodes]; NULL = a library-owned buffer per device (not safe for two
+     * tables on one device from different streams) */
+    double *matvec_ws;
 } lpk_node_args;
 
 int lpk_tick_node(const lpk_node_args *args, void *stream);

@@ -156,7 +156,7 @@ class NodeArgs(C.Structure):
         ("E_cur", _VP), ("I_cur", _VP), ("E_snap", _VP), ("I_snap", _VP), ("tx_hits_by_strain", _VP), ("any_cases", _VP),
         ("sus", _VP), ("R_cur", _VP), ("tx_hits", _VP), ("S_snap", _VP), ("R_snap", _VP), ("S_prev", _VP), ("R_prev", _VP),
         ("counts", _VP), ("node_lo", C.c_int32), ("node_hi", C.c_int32),
-        ("xchg_flags", _VP), ("xchg_world", C.c_int32), ("xchg_seq", C.c_uint32),
+        ("xchg_flags", _VP), ("xchg_world", C.c_int32), ("xchg_seq", C.c_uint32), ("matvec_ws", _VP),
     ]
 
 

@@ -955,7 +955,7 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
                          int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq,
-                         const lpk_node_args *inline_epilogue) {
+                         const lpk_node_args *inline_epilogue, double *matvec_ws) {
     double *rowsum = ws, *target = ws + num_nodes;
     if (!rowsums_done) {
         k_row_sums<<<(num_nodes + 7) / 8, 256, 0, st>>>(num_nodes, network, rowsum);
@@ -967,7 +967,12 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
     const int n_chunks = (num_nodes + NM_ROWS - 1) / NM_ROWS;
     static int split = -1;  // LPK_NODE_SPLIT=0: experiments only (single-block form for any size)
     if (split < 0) { const char *e = getenv("LPK_NODE_SPLIT"); split = (e && e[0] == '0') ? 0 : 1; }
-    if (n_chunks > 1 && split) {  // library-owned scratch, one per device, grown on demand (chunks x strains x nodes doubles: 1.4 MB at 6192 nodes)
+    if (n_chunks > 1 && split && matvec_ws) {  // caller-owned scratch (lpk_node_args.matvec_ws)
+        k_node_matvec_partial<<<dim3((node_hi - node_lo + 31) / 32, n_chunks), 1024, 0, st>>>(num_nodes, n_strains, beta_fx, network, node_lo,
+                                                                                             node_hi, matvec_ws, xchg_flags, xchg_world, xchg_seq);
+        CUDA_TRY(cudaGetLastError(), "node_math matvec");
+        partial = matvec_ws;
+    } else if (n_chunks > 1 && split) {  // library-owned scratch, one per device, grown on demand (chunks x strains x nodes doubles: 1.4 MB at 6192 nodes)
         static double *scratch[64] = {nullptr};
         static size_t scratch_bytes[64] = {0};
         int dev = 0;
@@ -1006,5 +1011,5 @@ extern "C" int lpk_tx_node_math(int32_t num_nodes, int32_t n_strains, const int6
                 expected && ws, "tx_node_math null pointer");
     return lpk_launch_node_math(num_nodes, n_strains, beta_fx, exposure_fx, risk_hist, network, beta_seasonality, r0_scalars,
                                 alive_counts, zero_inflation, dispersion, tau, strain_cdf, prob, expected, ws,
-                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes, nullptr, 0, 0u, nullptr);
+                                rng ? rng->seed : 0, rng ? rng->tick : 0, as_stream(stream), false, 0, num_nodes, nullptr, 0, 0u, nullptr, nullptr);
 }

@@ -926,7 +926,7 @@ int lpk_launch_node_math(int32_t num_nodes, int32_t n_strains, const int64_t *be
                          const int32_t *alive_counts, double zero_inflation, double dispersion, float *tau, double *strain_cdf,
                          double *prob, double *expected, double *ws, uint64_t seed, uint32_t tick, cudaStream_t st, bool rowsums_done,
                          int32_t node_lo, int32_t node_hi, const uint32_t *xchg_flags, int32_t xchg_world, uint32_t xchg_seq,
-                         const lpk_node_args *inline_epilogue);
+                         const lpk_node_args *inline_epilogue, double *matvec_ws);
 
 extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     REQUIRE(args, "tick_node null struct");
@@ -953,5 +953,6 @@ extern "C" int lpk_tick_node(const lpk_node_args *args, void *stream) {
     return lpk_launch_node_math(a.n_nodes, a.n_strains, a.beta_fx, a.exposure_fx, a.risk_hist, a.network, a.beta_seasonality,
                                 a.r0_scalars, a.pop ? a.pop : a.pop_prev, a.zero_inflation, a.dispersion, a.q, a.strain_cdf, a.prob,
                                 a.expected, a.rowsum_ws, a.seed, (uint32_t)a.tick, st, true, a.node_hi > 0 ? a.node_lo : 0,
-                                a.node_hi > 0 ? a.node_hi : a.n_nodes, a.xchg_flags, a.xchg_world, a.xchg_seq, inline_ep ? &a : nullptr);
+                                a.node_hi > 0 ? a.node_hi : a.n_nodes, a.xchg_flags, a.xchg_world, a.xchg_seq, inline_ep ? &a : nullptr,
+                                a.matvec_ws);
 }

@@ -318,6 +318,9 @@ class FusedEngine:
         N.tx_hits_by_strain = dp(self.tx_hits_s)
         N.sus, N.R_cur, N.tx_hits, N.S_snap, N.R_snap = dp(self.sus), dp(self.R_cur), dp(self.tx_hits), dp(self.S_snap), dp(self.R_snap)
         N.counts = dp(dev.counts)
+        if n > 1024:  # the network transfer is summed per chunk of 1024 source rows: scratch owned by this table
+            self.matvec_ws = torch.zeros(((n + 1023) // 1024) * _lpk.MAX_STRAINS * n, dtype=torch.float64, device=dev.device)
+            N.matvec_ws = dp(self.matvec_ws)
         vd = self.by_name.get("VitalDynamics_ABM")
         if vd is not None and pars.cbr is not None:
             R.births = vd.births_args(dev, 1, self.tile_node, tallies=(self.sus, self.expo, self.hist),
