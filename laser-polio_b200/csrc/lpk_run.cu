@@ -215,7 +215,8 @@ static int day_node(lpk_run &R, const lpk_day &D, const lpk_tick_args &A, const 
     if (beta_all) N.beta_fx = beta_all;
     const int rc = lpk_tick_node(&N, st);
     if (rc != LPK_OK) return rc;
-    if (launches) *launches += 2 + (N.n_nodes > 1024 ? 1 : 0);
+    // k_tx_node_math (+ k_tick_epilogue on a network's first tick, + k_node_matvec_partial above 1024 nodes)
+    if (launches) *launches += 1 + (R.rowsums_valid ? 0 : 1) + (N.n_nodes > 1024 ? 1 : 0);
     R.rowsums_valid = 1;
     R.pending = 1;
     if (D.flags & LPK_F_RI) R.ri_lazy_k += 1;
