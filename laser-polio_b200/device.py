@@ -25,8 +25,6 @@ HOST_ONLY_RESULTS = ("network",)
 # agent columns no kernel writes (the host copy stays current), and columns only births write (appended cohorts)
 READ_ONLY_COLUMNS = frozenset({"chronically_missed", "acq_risk_multiplier", "daily_infectivity"})
 APPEND_ONLY_COLUMNS = frozenset({"node_id", "date_of_birth", "date_of_death"})
-# byte columns of the disease state, in the row order of the fused pass's tensor copy (csrc/lpk_tick.cu, PassSmem)
-BYTE_ARENA = ("disease_state", "exposure_timer", "infection_timer", "strain", "paralysis_timer", "potentially_paralyzed")
 
 
 def _to_dev(arr: np.ndarray, device) -> torch.Tensor:
@@ -54,23 +52,8 @@ class DeviceState:
         people, results = self.sim.people, self.sim.results
         self.count0 = int(people.count)  # slots in use at upload: append-only columns come back from here on
         columns = people.columns()
-        # the six byte columns the fused pass streams every day live in ONE arena at a constant stride, in the order of
-        # the pass's shared-memory stage: liblpk then fetches them with one 2-D tensor copy per 256 agents instead of six
-        # bulk copies (lpk_tick.cu, pass_tensor_map); they stay ordinary per-column views for everything else
-        arena_ok = all(n in columns and columns[n].dtype == np.int8 for n in BYTE_ARENA)
-        if arena_ok:
-            cap = people.capacity
-            stride = (cap + 255) // 256 * 256
-            self.byte_arena = torch.empty(len(BYTE_ARENA) * stride, dtype=torch.int8, device=self.device)
         for name, col in columns.items():
-            if arena_ok and name in BYTE_ARENA:
-                k = BYTE_ARENA.index(name)
-                view = self.byte_arena[k * stride:k * stride + cap]
-                src = torch.from_numpy(col)
-                view.copy_(src, non_blocking=src.is_pinned())
-                self.cols[name] = view
-            else:
-                self.cols[name] = _to_dev(col, self.device)
+            self.cols[name] = _to_dev(col, self.device)
             self.h2d_bytes += col.nbytes
         for name, arr in results.__dict__.items():
             if isinstance(arr, np.ndarray) and arr.dtype == np.int32 and arr.ndim >= 2 and name not in HOST_ONLY_RESULTS:
