@@ -311,7 +311,8 @@ def run_b200(args):
     dur = (1 + e2e_reps) * (K_ + W_) + 40
     from laser_polio_b200 import synth
 
-    sim, n_local = synth.synth_sim(n_agents, n_nodes, dur, seed=20261017, device=f"cuda:{local}", rank=rank, world=world, mode=mode)
+    sim, n_local = synth.synth_sim(n_agents, n_nodes, dur, seed=20261017, device=f"cuda:{local}", rank=rank, world=world, mode=mode,
+                                   pars_over={"compact_every": args.compact_every} if args.compact_every else None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -448,6 +449,7 @@ def run_b200(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "mean_ms": mean_ms, "launches": calls,
                      "per_day_class": per_class, "kernel_share_of_step": kernel_share},
         "verified": verified, "verified_checks": {**checks, **census},
+        "compact_every": args.compact_every, "compactions": int(getattr(sim, "_compactions", 0)) if world == 1 or args.config != "auto" else None,
         "named_shape": named,
         "cpu_baseline": cpu_base,
         "e2e": {"value": agents_total * K_ / e2e_s, "unit": "agent-days/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
@@ -470,6 +472,7 @@ def main():
     ap.add_argument("--agents", type=int, default=0, help="total agents (default: the shape's)")
     ap.add_argument("--nodes", type=int, default=0, help="total nodes (default: the shape's)")
     ap.add_argument("--graph", type=int, default=0, help="1: lpk_run_days captures each span of days into a CUDA graph (no per-kernel timing)")
+    ap.add_argument("--compact-every", type=int, default=0, help="pars.compact_every: compact the device table every that many ticks (0 = never)")
     ap.add_argument("--no-named-shape", action="store_true", help="N > 1: skip the second measurement on the shape named for this GPU count")
     ap.add_argument("--cpu-agents", type=int, default=20_000_000)
     ap.add_argument("--cpu-ticks", type=int, default=60)

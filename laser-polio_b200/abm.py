@@ -250,6 +250,8 @@ class SEIR_ABM:
             self._component_tick(tick)
             self._engine.after_component_tick(0)
         else:
+            if self._engine.compaction_due(tick):
+                self._engine.compact(tick)
             self._engine.tick(tick)
 
     def run_ticks(self, n: int) -> None:
@@ -763,7 +765,7 @@ class VitalDynamics_ABM:
         a.seed, a.id_base = int(sim.pars.seed) & 0xFFFFFFFFFFFFFFFF, sim.id_base
         a.step_size = float(self.step_size)
         a.birth_rate, a.pop_prev, a.births_row = self._rate_dev.data_ptr(), r["pop"][t - 1].data_ptr(), r["births"][t].data_ptr()
-        a.counts, a.capacity = dev.counts.data_ptr(), self.people.capacity
+        a.counts, a.capacity = dev.counts.data_ptr(), dev.cap_eff  # (the graveyard of a compacted table is not available for births)
         a.cum_deaths, a.max_year = self._cd_dev.data_ptr(), min(100, len(self.death_estimator._cd) - 2)
         a.ri_newborn_timer = 182 if (getattr(self.pars, "ri_newborn_timer", False) and "ri_timer" in c) else -1
         a.node_offsets_ws, a.cohort_ws, a.status = dev.node_offsets_ws.data_ptr(), dev.cohort_ws.data_ptr(), dev.status.data_ptr()

@@ -80,6 +80,12 @@ class DeviceState:
         self.census = (mk(n), mk(n), mk(n), mk(n), mk(n, ns), mk(n, ns), mk(n), mk(n))
         self._net_src = None
         self.network = None
+        # compaction (pars.compact_every): slots [0, counts[1]) live + recently dead, [counts[1], cap_eff) unborn pre-drawn slots,
+        # [cap_eff, capacity) the graveyard (dead agents moved out of the swept range); orig[slot] = the agent's index in the
+        # reference's order (None: identity, never compacted)
+        self.cap_eff = int(people.capacity)
+        self.graveyard = 0
+        self.orig = None
 
     def mark_dirty(self, name: str):
         """A custom component wrote column ``name`` on the device: bring it back whole at download()."""
@@ -93,8 +99,18 @@ class DeviceState:
         people, results = self.sim.people, self.sim.results
         torch.cuda.current_stream().synchronize()
         count = self.sync_count(check=False)  # a cohort that did not fit raises AFTER everything has been copied back
+        inv = None
+        if self.orig is not None:  # compacted: slot s holds the agent the reference keeps at index orig[s]
+            inv = torch.empty_like(self.orig, dtype=torch.int64)
+            inv[self.orig.long()] = torch.arange(self.orig.numel(), dtype=torch.int64, device=self.device)
         for name, t in self.cols.items():
             host = getattr(people, name)
+            if inv is not None:
+                if name in READ_ONLY_COLUMNS and name not in self.dirty:
+                    continue  # permuted on the device, unchanged in value: the host copy is current, in the reference's order
+                torch.from_numpy(host).copy_(t[inv], non_blocking=False)
+                self.d2h_bytes += host.nbytes
+                continue
             if name in self.dirty:
                 pass
             elif name in READ_ONLY_COLUMNS:
@@ -136,15 +152,55 @@ class DeviceState:
             raise ValueError("an acq_risk_multiplier exceeds the range of the agenda's risk code")
 
     def sync_count(self, check=True) -> int:
-        """Device -> host: how many slots are in use (blocks on the stream), and whether a cohort overflowed capacity."""
+        """Device -> host: how many slots are in use on the device (blocks on the stream), and whether a cohort overflowed
+        capacity.  people.count is the reference's count: every agent ever created, i.e. device slots in use + graveyard."""
         count = int(self.counts[1].item())
-        self.sim.people._count = count
+        self.sim.people._count = count + self.graveyard
         if check:
             self.check_status()
         return count
 
     def set_count(self, count: int):
+        """``count`` in the reference's sense (people.count)."""
+        count = int(count) - self.graveyard
         self.counts.copy_(torch.tensor([count, count], dtype=torch.int64))
+
+    # ------------------------------------------------------------------ compaction (north star: free-slot reuse + compaction)
+    def warm_compaction(self):
+        """One throw-away sort + gather of the table's size, so that the caching allocator already holds the multi-GB scratch a
+        compaction needs (the first cudaMalloc of it costs ~0.5 s at 2.2e8 agents, against ~40 ms for the compaction itself)."""
+        key = torch.zeros(self.cap_eff, dtype=torch.int16, device=self.device)
+        perm = torch.sort(key, stable=True).indices
+        _ = self.cols["date_of_death" if "date_of_death" in self.cols else "node_id"][:self.cap_eff][perm]
+        del key, perm, _
+
+    def compact(self):
+        """Stable re-sort of the canonical table: live agents by node (previous order kept within a node), then the unborn
+        pre-drawn slots in their order, then the agents that died since the last compaction, which join the graveyard at the end
+        of the table and are no longer swept.  Every column moves together, and ``orig`` with them, so to_host() can hand the
+        columns back in the reference's order.  The reference appends forever and scans its tombstones on every tick
+        (model.py:1719-1732); this is the table operation the north star asks for instead.  Returns (live, newly dead).
+
+        A maintenance operation, not a per-tick kernel: one radix sort of int16 keys (torch.sort) and one gather per column."""
+        n, cap_eff = self.n_nodes, self.cap_eff
+        count = int(self.counts[1].item())
+        if self.orig is None:
+            self.orig = torch.arange(self.sim.people.capacity, dtype=torch.int32, device=self.device)
+        state, nid = self.cols["disease_state"], self.cols["node_id"]
+        key = torch.full((cap_eff,), n, dtype=torch.int16, device=self.device)  # unborn slots: after every node
+        key[:count] = torch.where(state[:count] >= 0, nid[:count], torch.full_like(nid[:count], n + 1))  # the dead: last
+        live = int((key[:count] < n).sum().item())
+        dead = count - live
+        perm = torch.sort(key, stable=True).indices
+        del key
+        for t in list(self.cols.values()) + [self.orig]:
+            t[:cap_eff] = t[:cap_eff][perm]
+        del perm
+        self.cap_eff -= dead
+        self.graveyard += dead
+        self.counts.copy_(torch.tensor([live, live], dtype=torch.int64))
+        return live, dead
+
 
     def network_tensor(self, host_network) -> torch.Tensor:
         """Device copy of ``tx.network`` (float64, row-major); re-uploaded when the host object is replaced

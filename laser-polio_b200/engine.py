@@ -116,6 +116,8 @@ class FusedEngine:
         P.risk_e0 = int(_lpk.lib().lpk_hot_risk_e0(C.c_float(rmax)))
         self.P = P
         self.use_graph = bool(getattr(sim, "cuda_graph", False))
+        if int(getattr(sim.pars, "compact_every", 0) or 0) > 0:
+            dev.warm_compaction()
         self.xchg = self._open_exchange()
         self._template()
         if sim.t > 0:  # resuming mid-run; a fresh run builds tallies and agenda after tick 0 (after_component_tick)
@@ -335,6 +337,9 @@ class FusedEngine:
         R.work_counters = dp(self.work_counter)
         R.xchg = self.xchg
         R.graph = 1 if (self.use_graph and not self.stop_rule) else 0
+        old = getattr(self, "R", None)
+        if old is not None:  # rebuilt after a compaction: the exchange's sequence number and the row sums carry over
+            R.seq, R.rowsums_valid = old.seq, old.rowsums_valid
         self.R = R
 
     def _days(self, t0, n_days):
@@ -438,9 +443,26 @@ class FusedEngine:
         if self.stop_rule:  # the host decides tick by tick (one tick behind the device)
             return 0 if self.needs_components(t0) else 1
         n = 0
-        while t0 + n < t_end and not self.needs_components(t0 + n):
+        while t0 + n < t_end and not self.needs_components(t0 + n) and not (n > 0 and self.compaction_due(t0 + n)):
             n += 1
         return n
+
+    # ------------------------------------------------------------------ compaction (pars.compact_every)
+    def compaction_due(self, t) -> bool:
+        k = int(getattr(self.sim.pars, "compact_every", 0) or 0)
+        return k > 0 and t > 1 and t % k == 0
+
+    def compact(self, t):
+        """Before tick t: finish what is pipelined, compact the canonical table (device.DeviceState.compact), re-derive tiles,
+        tallies and agenda from it.  Every live agent is node-contiguous again (uniform tiles) and the dead leave the sweep."""
+        self.drain()
+        live, dead = self.dev.compact()
+        self.rebuild_tiles(0)
+        self.uniform_agents = live
+        self._template()
+        self.rebase_tallies(t)
+        self.sim._compactions = getattr(self.sim, "_compactions", 0) + 1
+        return live, dead
 
     def close(self):
         """Release the peer-memory exchange (collective: every rank of the shard group calls it)."""
@@ -483,6 +505,8 @@ class FusedEngine:
         through the components.  What SEIR_ABM.run() and run_ticks() drive."""
         sim = self.sim
         while sim.t < t_end and not (sim.t > 1 and sim.should_stop):
+            if self.compaction_due(sim.t):
+                self.compact(sim.t)
             n = self.fused_span(sim.t, t_end)
             if n <= 1 or self.stop_rule:
                 self.tick(sim.t)

@@ -81,6 +81,10 @@ default_pars = PropertySet(
         # extension: newborns get ri_timer = 182 as the reference intends (model.py:1731-1732); False reproduces what it does --
         # its isinstance test on classes never fires, so newborn timers stay at -1 and newborns never receive RI
         "ri_newborn_timer": False,
+        # extension: every `compact_every` ticks the device table is compacted -- live agents stably re-sorted by node, the slots
+        # of the dead moved out of the swept range (free-slot reuse), host order restored at to_host(); 0 = never (the reference
+        # never compacts).  Fused path only.  Changes which slot, hence which random stream, an agent has: DESIGN.md section 3
+        "compact_every": 0,
     }
 )
 

@@ -20,7 +20,7 @@ RESULT_ROWS = ("S", "E", "I", "R", "new_exposed", "births", "deaths", "pop", "ne
                "E_by_strain", "I_by_strain", "new_exposed_by_strain", "ri_new_exposed_by_strain", "sia_new_exposed_by_strain")
 
 
-def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 2, 7, 14), pars_over=None, pop_over=None, via="step_tick"):
+def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 2, 7, 14), pars_over=None, pop_over=None, compact_every=0):
     """Runs ``dur`` ticks of the fused engine and of the oracle on the same table; raises AssertionError on the first
     difference.  Returns a summary dict (counts that show the run was not trivial)."""
     import torch
@@ -28,6 +28,9 @@ def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 
     from laser_polio_b200 import kernels as K
     from laser_polio_b200 import synth, utils
 
+    pars_over = dict(pars_over or {})
+    if compact_every:
+        pars_over["compact_every"] = int(compact_every)
     sim, n = synth.synth_sim(n_agents, n_nodes, dur, seed, cbr=cbr, pars_over=pars_over, pop_over=pop_over)
     people, pars = sim.people, sim.pars
     cols = {name: col.copy() for name, col in people.columns().items()}
@@ -70,7 +73,7 @@ def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 
         tau_of_tick=taus, cdf_of_tick=cdfs, vd_step=int(vd.step_size), birth_rate=vd.birth_rate,
         cum_deaths=np.asarray(vd.death_estimator._cd, np.int64), pop0=np.asarray(pars.init_pop, np.int32),
         ri_step=int(ri.step_size), vx_prob_ri=np.asarray(pars.vx_prob_ri, np.float64), vx_prob_ipv=np.asarray(pars.vx_prob_ipv, np.float64),
-        ri_strain=1, sia_events=events)
+        ri_strain=1, sia_events=events, compact_every=int(compact_every))
 
     # ---- bit-exact: head count, every results array, every agent column
     assert count == people.count, f"count {people.count} vs oracle {count}"
@@ -104,4 +107,5 @@ def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 
         "new_exposed": int(res.new_exposed.sum()), "deaths": int(res.deaths.sum()), "births": int(res.births.sum()),
         "ri_vaccinated": int(res.ri_vaccinated.sum()), "sia_protected": int(res.sia_protected.sum()),
         "new_potentially_paralyzed": int(res.new_potentially_paralyzed.sum()), "calls": calls,
+        "compactions": int(getattr(sim, "_compactions", 0)),
     }

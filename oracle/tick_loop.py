@@ -68,11 +68,15 @@ def births(pop_prev, birth_rate, step_size, cum_deaths, count, capacity, seed, t
 
 def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0_scalars, p_paralysis, tau_of_tick=None, cdf_of_tick=None,
         vd_step=0, birth_rate=None, cum_deaths=None, pop0=None, ri_step=0, vx_prob_ri=None, vx_prob_ipv=None, ri_strain=1,
-        sia_events=None, node_lo=0, node_hi=None, node_math=None):
+        sia_events=None, node_lo=0, node_hi=None, node_math=None, compact_every=0):
     """Ticks 0 .. ticks-1 on the canonical columns ``cols`` (mutated in place).  Returns (results dict of [ticks, nodes(, ns)]
     int32 rows, final count, per-tick tallies {t: (beta_fx, exposure_fx, risk_hist)} for the node-math check).
 
     sia_events: {tick: [(targeted uint8[nodes], vx_prob float32[nodes], vx_eff, min_age, max_age, strain), ...]}
+    compact_every: the device's table compaction (laser_polio_b200.device.DeviceState.compact) before every tick t > 1 with
+                t % compact_every == 0: live agents stably sorted by node, then the unborn slots, then the newly dead, which
+                leave the swept range.  The returned columns are back in the reference's order and ``count`` is the
+                reference's (every agent ever created).
     node_math:  instead of tau_of_tick / cdf_of_tick (pass None for both), the inputs of the node step -- {"network", "r0_scalars",
                 "season": callable(t) or float, "zero_inflation", "dispersion"} -- and tau / cdf come from
                 ``oracle.tx_node_math_device`` on the loop's own tallies (a free-running oracle simulation)."""
@@ -96,8 +100,20 @@ def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0
         r["R"][t] += R
         r["potentially_paralyzed"][t], r["paralyzed"][t] = PP, Pz
 
+    cap_eff, graveyard = capacity, 0
+    orig = np.arange(capacity, dtype=np.int64)
     census(0)
     for t in range(1, ticks):
+        if compact_every and t > 1 and t % compact_every == 0:
+            key = np.full(cap_eff, n_nodes, np.int64)
+            key[:count] = np.where(c["disease_state"][:count] >= 0, c["node_id"][:count], n_nodes + 1)
+            live = int((key[:count] < n_nodes).sum())
+            perm = np.argsort(key, kind="stable")
+            for name in c:
+                c[name][:cap_eff] = c[name][:cap_eff][perm]
+            orig[:cap_eff] = orig[:cap_eff][perm]
+            dead = count - live
+            cap_eff, graveyard, count = cap_eff - dead, graveyard + dead, live
         if vd_step:
             if t % vd_step == 0:
                 dying = i32(n_nodes)
@@ -106,7 +122,7 @@ def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0
                 if node_hi is not None:  # a node shard creates the cohorts of its own nodes only
                     rate[:node_lo] = 0.0
                     rate[node_hi:] = 0.0
-                b, nid, dod, new_count, status = births(r["pop"][t - 1], rate, vd_step, cum_deaths, count, capacity, seed, t, id_base)
+                b, nid, dod, new_count, status = births(r["pop"][t - 1], rate, vd_step, cum_deaths, count, cap_eff, seed, t, id_base)
                 assert status == 0, "oracle births: capacity"
                 c["node_id"][count:new_count], c["date_of_death"][count:new_count] = nid, dod
                 c["date_of_birth"][count:new_count], c["disease_state"][count:new_count] = t, 0
@@ -150,4 +166,10 @@ def run(cols, count, capacity, n_nodes, ns, ticks, *, seed, id_base=0, strain_r0
         r["new_exposed"][t] += new.sum(axis=1, dtype=np.int32)
         r["new_exposed_by_strain"][t] += new
         census(t)
+    if graveyard:  # back to the reference's order
+        for name in c:
+            out = np.empty_like(c[name])
+            out[orig] = c[name]
+            c[name][:] = out
+        count += graveyard
     return r, count, tallies

@@ -30,3 +30,12 @@ def test_engine_vs_oracle_774_nodes_20M_agents_60_days(check):
     assert out["cohort_share"] >= 0.10, out
     assert out["new_exposed"] > 100_000 and out["deaths"] > 1000 and out["ri_vaccinated"] > 1000 and out["sia_protected"] > 100_000
     assert out["new_potentially_paralyzed"] > 0
+
+
+def test_engine_vs_oracle_with_compaction(check):
+    """pars.compact_every: every 10 ticks the live agents are stably re-sorted by node and the dead leave the swept range (the
+    oracle's tick loop applies the same table operation); columns come back in the reference's order, bit for bit, tombstones
+    and cohorts included.  cbr 400 and the synthetic death dates make both births and deaths plentiful."""
+    out = check.run_and_compare(400_000, 23, 55, seed=12, cbr=400.0, compact_every=10, node_math_ticks=(1, 10, 11, 30, 54))
+    assert out["compactions"] == 5 and out["deaths"] > 200 and out["births"] > 10_000 and out["new_exposed"] > 500
+    assert out["sia_protected"] > 0 and out["ri_vaccinated"] > 0
