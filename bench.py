@@ -302,7 +302,6 @@ def run_b200(args):
         entry.build_product()
     if world > 1:
         dist.barrier()
-    import laser_polio_b200 as lp
     from laser_polio_b200 import kernels as K
 
     name, n_nodes, n_agents, mode = plan(args, world)

@@ -477,11 +477,6 @@ class FusedEngine:
             self.xchg = None
             self.R.xchg = None
 
-    def _seasonality(self):
-        from . import utils
-
-        return utils.get_seasonality(self.sim)
-
     def tick(self, t):
         """Tick t >= 1 (tick 0 only logs, through the components)."""
         sim = self.sim

@@ -23,8 +23,6 @@ RESULT_ROWS = ("S", "E", "I", "R", "new_exposed", "births", "deaths", "pop", "ne
 def run_and_compare(n_agents, n_nodes, dur, seed, cbr=37.0, node_math_ticks=(1, 2, 7, 14), pars_over=None, pop_over=None, compact_every=0):
     """Runs ``dur`` ticks of the fused engine and of the oracle on the same table; raises AssertionError on the first
     difference.  Returns a summary dict (counts that show the run was not trivial)."""
-    import torch
-
     from laser_polio_b200 import kernels as K
     from laser_polio_b200 import synth, utils
 
