@@ -384,6 +384,9 @@ class FusedEngine:
         """Ticks t0 .. t0 + n_days - 1 as fused days, launched from C back to back (lpk_run_days); none of them may need the
         components (needs_components).  Does not advance sim.t."""
         sim, R = self.sim, self.R
+        if self.ri_lazy_k >= self.RI_DEBT_MAX:  # pay the lazy RI countdown's debt before the eligibility byte runs out of range
+            self.drain()
+            self.rebase_tallies(t0)
         if self.status_evt is not None:  # the previous call's births: did a cohort not fit?
             self.status_evt.synchronize()
             self.status_evt = None
@@ -438,12 +441,16 @@ class FusedEngine:
             evt.record()
             self.cases_evt = {t: evt}
 
+    MAX_SPAN = 128   # days per lpk_run_days call: bounds what one call adds to the lazy RI debt (and the size of a captured graph)
+    RI_DEBT_MAX = 200  # RI ticks owed (ri_lazy_k) at which the table is settled and re-based: lpk_people.ri_k is one byte (< 254)
+
     def fused_span(self, t0, t_end) -> int:
         """How many consecutive ticks from t0 (below t_end) can run as one lpk_run_days call."""
         if self.stop_rule:  # the host decides tick by tick (one tick behind the device)
             return 0 if self.needs_components(t0) else 1
         n = 0
-        while t0 + n < t_end and not self.needs_components(t0 + n) and not (n > 0 and self.compaction_due(t0 + n)):
+        while (t0 + n < t_end and n < self.MAX_SPAN and not self.needs_components(t0 + n)
+               and not (n > 0 and self.compaction_due(t0 + n))):
             n += 1
         return n
 

@@ -39,3 +39,11 @@ def test_engine_vs_oracle_with_compaction(check):
     out = check.run_and_compare(400_000, 23, 55, seed=12, cbr=400.0, compact_every=10, node_math_ticks=(1, 10, 11, 30, 54))
     assert out["compactions"] == 5 and out["deaths"] > 200 and out["births"] > 10_000 and out["new_exposed"] > 500
     assert out["sia_protected"] > 0 and out["ri_vaccinated"] > 0
+
+
+def test_engine_vs_oracle_ten_years(check):
+    """3700 days on a small table: the agenda's 63-day check-ins, int8 deadline wrap-around, more than 254 RI ticks (the lazy RI
+    debt is paid and the table re-based on the way), ~80 campaigns, hundreds of cohorts -- still bit-identical to the oracle."""
+    out = check.run_and_compare(60_000, 5, 3700, seed=13, cbr=37.0, node_math_ticks=(1, 1000, 3600))
+    assert out["ticks"] == 3701 and out["deaths"] > 1000 and out["births"] > 10_000 and out["sia_protected"] > 10_000
+    assert out["calls"]["tick_pass"] >= 3690
