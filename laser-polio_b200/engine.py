@@ -441,7 +441,7 @@ class FusedEngine:
             evt.record()
             self.cases_evt = {t: evt}
 
-    MAX_SPAN = 128   # days per lpk_run_days call: bounds what one call adds to the lazy RI debt (and the size of a captured graph)
+    MAX_SPAN = 256   # days per lpk_run_days call: bounds what one call adds to the lazy RI debt (and the size of a captured graph)
     RI_DEBT_MAX = 200  # RI ticks owed (ri_lazy_k) at which the table is settled and re-based: lpk_people.ri_k is one byte (< 254)
 
     def fused_span(self, t0, t_end) -> int:
